@@ -1,0 +1,152 @@
+/* include/kslam.h — C ABI of the B200-native k-SLAM matching path (libkslam.so).
+ *
+ * The reference (aindj/k-SLAM) has no plugin/FFI interface for this path: the batch loop calls two
+ * C++ templates directly. This header is therefore the boundary a maintainer would
+ * bind INSTEAD of those two calls (see INTEGRATION.md for the stub):
+ *
+ *   kslam_load_genomes   replaces GenbankIndex::getKMers + the per-batch re-sort of genome k-mers
+ *                        /root/reference/src/GenbankTools.h:211-219, /root/reference/src/SLAM.h:65-66
+ *   kslam_align_batch    replaces alignToDatabase            /root/reference/src/SLAM.h:60-79
+ *   kslam_pair_batch     replaces screenOverlapsByScoreThreshold + getPairedOverlaps
+ *                        /root/reference/src/Overlap.h:329-341, /root/reference/src/PairedOverlap.h:243-272
+ *   kslam_ssw_batch      replaces StripedSmithWaterman::Aligner::Align, batched
+ *                        /root/reference/src/ssw_cpp.cpp:234-283 (C ABI below it: ssw.h:97-192)
+ *
+ * Plain pointers and sizes only; no exceptions cross the boundary (0 = ok, negative = error, text
+ * from kslam_last_error). Sequences are passed as ONE concatenated byte array plus n+1 offsets
+ * (sequence i = bases[offs[i] .. offs[i+1])), exactly the bytes of std::string `bases` in the
+ * reference's FASTQSequence / GenbankEntry. Result buffers are owned by the ctx and stay valid until
+ * the next call of the same function or kslam_destroy. One in-flight batch per ctx; use one ctx per
+ * GPU (and two per GPU to double-buffer). There is NO CPU fallback: every entry point that computes
+ * fails with KSLAM_ERR_CUDA if no sm_100 device is usable.
+ *
+ * All arithmetic on this path is integer; results are bit-exact with the reference for scoring
+ * parameters inside the domain reported by kslam_params_exact() (the defaults 2/3/5/2 are inside).
+ */
+#ifndef KSLAM_H_
+#define KSLAM_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KSLAM_K 32u /* Globals.h:25 */
+
+#define KSLAM_OK 0
+#define KSLAM_ERR_ARG (-1)
+#define KSLAM_ERR_CUDA (-2)
+#define KSLAM_ERR_NOMEM (-3)
+#define KSLAM_ERR_STATE (-4)
+
+typedef struct kslam_ctx kslam_ctx;
+
+/* Globals.h:27-42 as filled by main.cpp:36-58; narrowed to u8 as at ssw_cpp.cpp:114-117. */
+typedef struct {
+  uint8_t match, mismatch, gap_open, gap_extend; /* defaults 2 3 5 2 */
+  uint16_t score_threshold;                      /* --min-alignment-score, default 0 */
+  uint8_t report_cigar;                          /* reportCigar: true iff --sam-file (SLAM.h:169) */
+  uint8_t reserved0;
+  int32_t device;                                /* CUDA device ordinal */
+  uint32_t genome_gap;                           /* k/2 = 16 (SLAM.h:65); 0 = default */
+  uint32_t max_cigar_ops;                        /* per-alignment cigar capacity, 0 = default 32 */
+  uint32_t reserved1;
+} kslam_params;
+
+/* KMerAndData, KMer.h:58-116. id_flags: bits 0-29 id, bit 30 revComp, bit 31 isFromGB. */
+typedef struct { uint64_t kmer; uint32_t id_flags; uint32_t offset; } kslam_kmer;
+/* OverlapTemp, Overlap.h:36-52. */
+typedef struct { uint32_t read; uint32_t entry; int32_t rel; uint32_t rev_comp; } kslam_seed;
+/* Overlap (Overlap.h:53-74) with its StripedSmithWaterman::Alignment (ssw_cpp.h:10-18). The cigar of
+ * overlap i is cigar_pool[cigar_off .. cigar_off+cigar_len), BAM encoding len<<4|op (M0 I1 D2). */
+typedef struct {
+  uint32_t read, entry; int32_t rel; uint32_t rev_comp;
+  int32_t ref_begin, ref_end, query_begin, query_end;
+  uint32_t sw_score, cigar_off, cigar_len, flags;
+} kslam_overlap;
+#define KSLAM_FLAG_UNDEFINED 1u      /* the reference's behaviour is undefined for this input (score 0 with
+                                        cigar requested, or its traceback leaves the written band) */
+#define KSLAM_FLAG_CIGAR_OVERFLOW 2u /* more than max_cigar_ops ops; cigar truncated */
+/* PairedOverlap, PairedOverlap.h:32-58. r1_idx / r2_idx index `sorted_overlaps`; -1 = absent mate. */
+typedef struct {
+  uint32_t combined_score, entry; int32_t ref_start, ref_end;
+  uint32_t insert_size; int32_t r1_idx, r2_idx; uint32_t pad;
+} kslam_pair;
+
+typedef struct {
+  uint64_t n_overlaps;            /* == alignToDatabase(...).size(), same order */
+  const kslam_overlap *overlaps;  /* host, pinned, ctx-owned */
+  uint64_t n_cigar_words;
+  const uint32_t *cigar_pool;     /* host, pinned, ctx-owned */
+} kslam_alignments;
+
+typedef struct {
+  uint64_t n_sorted;                    /* overlaps surviving the score screen */
+  const kslam_overlap *sorted_overlaps; /* in getPairedOverlaps' sorted order */
+  uint64_t n_cigar_words;
+  const uint32_t *cigar_pool;
+  uint64_t n_pairs;
+  const kslam_pair *pairs;              /* == getPairedOverlaps(...) order */
+} kslam_pairs;
+
+/* Device time of the stages of the last kslam_align_batch / kslam_pair_batch (CUDA events on the
+ * ctx stream) and the unit counts the roofline figures are computed from. */
+typedef struct {
+  float ms_h2d, ms_pack, ms_extract, ms_sort, ms_join, ms_seed_sort, ms_unique;
+  float ms_sw_prepare, ms_sw_forward, ms_sw_reverse, ms_sw_traceback, ms_sw_slow, ms_d2h, ms_pair, ms_total;
+  uint64_t n_read_kmers, n_genome_kmers, n_raw_seeds, n_seeds, n_sort_passes;
+  uint64_t sw_cells_forward, sw_cells_reverse, n_sw_fast, n_sw_slow, n_pairs;
+  uint64_t kernel_launches;
+} kslam_timings;
+
+int kslam_create(const kslam_params *params, kslam_ctx **out);
+void kslam_destroy(kslam_ctx *ctx);
+const char *kslam_last_error(const kslam_ctx *ctx); /* ctx may be NULL: last create error */
+/* 1 if results are proven bit-exact with the reference for these scoring parameters
+ * (gap_extend < gap_open and mismatch <= 2*gap_extend, DESIGN.md §SSW equivalence), else 0. */
+int kslam_params_exact(const kslam_params *params);
+const char *kslam_version(void);
+
+/* Pack the genomes, extract every genome_gap-th canonical 32-mer (KMer.h:160-181), sort once
+ * (KMer.h:388-398) and keep everything resident in HBM. */
+int kslam_load_genomes(kslam_ctx *ctx, uint64_t n_entries, const char *bases, const uint64_t *offs);
+
+/* alignToDatabase (SLAM.h:60-79) for one batch: reads[0..n_reads), paired data laid out R1 block then
+ * R2 block (FASTQsequence.h:110-123). */
+int kslam_align_batch(kslam_ctx *ctx, uint64_t n_reads, const char *bases, const uint64_t *offs,
+                      kslam_alignments *out);
+/* Same work, split for measurement with HBM-resident inputs: upload once, run many times. */
+int kslam_upload_reads(kslam_ctx *ctx, uint64_t n_reads, const char *bases, const uint64_t *offs);
+int kslam_align_resident(kslam_ctx *ctx, int fetch_results, kslam_alignments *out /* may be NULL */);
+
+/* screenOverlapsByScoreThreshold (Overlap.h:329-341) + getPairedOverlaps (PairedOverlap.h:243-272) on
+ * the alignments of the last batch (device-resident). */
+int kslam_pair_batch(kslam_ctx *ctx, int fetch_results, kslam_pairs *out /* may be NULL */);
+
+/* Aligner::Align (ssw_cpp.cpp:234-283) for n independent (query, ref) pairs, SSW's own coordinates
+ * (no window un-flip). out[n] and cigar_pool[n * max_cigar_ops] are caller buffers (host). */
+int kslam_ssw_batch(kslam_ctx *ctx, uint64_t n, const char *q, const uint64_t *qoffs, const char *r,
+                    const uint64_t *roffs, kslam_overlap *out, uint32_t *cigar_pool);
+int kslam_ssw_upload(kslam_ctx *ctx, uint64_t n, const char *q, const uint64_t *qoffs, const char *r,
+                     const uint64_t *roffs);
+int kslam_ssw_resident(kslam_ctx *ctx, kslam_overlap *out /* may be NULL */, uint32_t *cigar_pool /* may be NULL */);
+
+/* Stage taps for parity tests (results of the last batch; copy to caller buffers; pass NULL to query
+ * the count). Returns the count or a negative error. */
+int64_t kslam_get_genome_kmers(kslam_ctx *ctx, kslam_kmer *out, uint64_t cap);      /* sorted, resident */
+int64_t kslam_get_read_kmers(kslam_ctx *ctx, kslam_kmer *out, uint64_t cap);        /* sorted by kmer */
+int64_t kslam_get_raw_seeds(kslam_ctx *ctx, kslam_seed *out, uint64_t cap);         /* after the join */
+int64_t kslam_get_seeds(kslam_ctx *ctx, kslam_seed *out, uint64_t cap);             /* after sort+unique */
+/* Generic hand-written LSD radix sort of 16-byte records by bits [lo_bit,hi_bit) of their first u64
+ * (exposed for parity tests and the sort microbenchmark). In place on a host buffer. */
+int kslam_sort_records(kslam_ctx *ctx, kslam_kmer *recs, uint64_t n, uint32_t lo_bit, uint32_t hi_bit,
+                       float *device_ms /* may be NULL */);
+
+int kslam_get_timings(const kslam_ctx *ctx, kslam_timings *out);
+/* Keep (1, default) or drop (0) stage-tap buffers between stages; dropping saves HBM on big batches. */
+int kslam_set_debug_taps(kslam_ctx *ctx, int keep);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KSLAM_H_ */

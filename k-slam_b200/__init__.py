@@ -1,0 +1,290 @@
+"""kslam_b200 — host-side mirror of the reference's matching-path interface over libkslam.so.
+
+The product is the CUDA library behind the C ABI in include/kslam.h; this module is the thin
+Python host layer used by the tests, bench.py and the multi-GPU driver. It mirrors the reference's
+operator names for this path:
+
+    Aligner.load_genomes   <- GenbankIndex (GenbankTools.h:189-219) handed to alignToDatabase
+    Aligner.align_batch    <- alignToDatabase            (/root/reference/src/SLAM.h:60-79)
+    Aligner.pair_batch     <- screenOverlapsByScoreThreshold + getPairedOverlaps
+                              (/root/reference/src/Overlap.h:329-341, PairedOverlap.h:243-272)
+    Aligner.ssw_batch      <- StripedSmithWaterman::Aligner::Align (/root/reference/src/ssw_cpp.cpp:234-283)
+
+There is no CPU fallback: importing works anywhere (so the CPU test tier can check symbols), but every
+compute call needs libkslam.so and an sm_100 GPU and raises KslamError otherwise. Nothing here imports
+or loads oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import synth  # noqa: F401  (seeded workload generators)
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG_DIR)
+LIB_PATH = os.path.join(PKG_DIR, "libkslam.so")
+HEADER = os.path.join(ROOT, "include", "kslam.h")
+
+KMER_DT = np.dtype([("kmer", "<u8"), ("id_flags", "<u4"), ("offset", "<u4")])
+SEED_DT = np.dtype([("read", "<u4"), ("entry", "<u4"), ("rel", "<i4"), ("rev_comp", "<u4")])
+OVERLAP_DT = np.dtype([("read", "<u4"), ("entry", "<u4"), ("rel", "<i4"), ("rev_comp", "<u4"),
+                       ("ref_begin", "<i4"), ("ref_end", "<i4"), ("query_begin", "<i4"), ("query_end", "<i4"),
+                       ("sw_score", "<u4"), ("cigar_off", "<u4"), ("cigar_len", "<u4"), ("flags", "<u4")])
+PAIR_DT = np.dtype([("combined_score", "<u4"), ("entry", "<u4"), ("ref_start", "<i4"), ("ref_end", "<i4"),
+                    ("insert_size", "<u4"), ("r1_idx", "<i4"), ("r2_idx", "<i4"), ("pad", "<u4")])
+FLAG_UNDEFINED = 1
+FLAG_CIGAR_OVERFLOW = 2
+
+
+class KslamError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("match", C.c_uint8), ("mismatch", C.c_uint8), ("gap_open", C.c_uint8), ("gap_extend", C.c_uint8),
+                ("score_threshold", C.c_uint16), ("report_cigar", C.c_uint8), ("reserved0", C.c_uint8),
+                ("device", C.c_int32), ("genome_gap", C.c_uint32), ("max_cigar_ops", C.c_uint32),
+                ("reserved1", C.c_uint32)]
+
+
+class _Alignments(C.Structure):
+    _fields_ = [("n_overlaps", C.c_uint64), ("overlaps", C.c_void_p), ("n_cigar_words", C.c_uint64),
+                ("cigar_pool", C.c_void_p)]
+
+
+class _Pairs(C.Structure):
+    _fields_ = [("n_sorted", C.c_uint64), ("sorted_overlaps", C.c_void_p), ("n_cigar_words", C.c_uint64),
+                ("cigar_pool", C.c_void_p), ("n_pairs", C.c_uint64), ("pairs", C.c_void_p)]
+
+
+class Timings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("ms_h2d", "ms_pack", "ms_extract", "ms_sort", "ms_join", "ms_seed_sort",
+                                         "ms_unique", "ms_sw_prepare", "ms_sw_forward", "ms_sw_reverse",
+                                         "ms_sw_traceback", "ms_sw_slow", "ms_d2h", "ms_pair", "ms_total")] + \
+               [("_pad", C.c_float)] + \
+               [(n, C.c_uint64) for n in ("n_read_kmers", "n_genome_kmers", "n_raw_seeds", "n_seeds", "n_sort_passes",
+                                          "sw_cells_forward", "sw_cells_reverse", "n_sw_fast", "n_sw_slow", "n_pairs",
+                                          "kernel_launches")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "_pad"}
+
+
+def declared_symbols():
+    """Every function the public header declares (used by the CPU-tier symbol test)."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kslam_[a-z_0-9]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def lib():
+    """dlopen libkslam.so and bind every entry point; raises KslamError (never falls back) if missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KslamError(f"{LIB_PATH} not built: run `python __graft_entry__.py` (nvcc, sm_100a). "
+                         "There is no CPU fallback for the matching path.")
+    L = C.CDLL(LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(L, s)]
+    if missing:
+        raise KslamError(f"libkslam.so lacks symbols declared in include/kslam.h: {missing}")
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    L.kslam_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.kslam_destroy.argtypes = [vp]
+    L.kslam_destroy.restype = None
+    L.kslam_last_error.argtypes = [vp]
+    L.kslam_last_error.restype = C.c_char_p
+    L.kslam_version.restype = C.c_char_p
+    L.kslam_params_exact.argtypes = [C.POINTER(Params)]
+    L.kslam_load_genomes.argtypes = [vp, u64, vp, vp]
+    L.kslam_align_batch.argtypes = [vp, u64, vp, vp, C.POINTER(_Alignments)]
+    L.kslam_upload_reads.argtypes = [vp, u64, vp, vp]
+    L.kslam_align_resident.argtypes = [vp, i32, C.POINTER(_Alignments)]
+    L.kslam_pair_batch.argtypes = [vp, i32, C.POINTER(_Pairs)]
+    L.kslam_ssw_batch.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
+    L.kslam_ssw_upload.argtypes = [vp, u64, vp, vp, vp, vp]
+    L.kslam_ssw_resident.argtypes = [vp, vp, vp]
+    for name in ("kslam_get_genome_kmers", "kslam_get_read_kmers", "kslam_get_raw_seeds", "kslam_get_seeds"):
+        getattr(L, name).argtypes = [vp, vp, u64]
+        getattr(L, name).restype = C.c_int64
+    L.kslam_sort_records.argtypes = [vp, vp, u64, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
+    L.kslam_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.kslam_set_debug_taps.argtypes = [vp, i32]
+    _lib = L
+    return L
+
+
+def _u8(a):
+    if isinstance(a, (bytes, bytearray)):
+        a = np.frombuffer(a, dtype=np.uint8)
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _view(ptr, n, dtype):
+    if not n or not ptr:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n)
+
+
+@dataclass
+class Alignments:
+    """alignToDatabase's std::vector<Overlap>, same order; cigar i = cigar_pool[cigar_off:cigar_off+cigar_len]."""
+    overlaps: np.ndarray
+    cigar_pool: np.ndarray
+
+
+@dataclass
+class Pairs:
+    """getPairedOverlaps' std::vector<PairedOverlap> plus the pair-sorted overlap array r1_idx/r2_idx point into."""
+    sorted_overlaps: np.ndarray
+    cigar_pool: np.ndarray
+    pairs: np.ndarray
+
+
+class Aligner:
+    """One matching context on one GPU (one kslam_ctx)."""
+
+    def __init__(self, match=2, mismatch=3, gap_open=5, gap_extend=2, score_threshold=0, report_cigar=False,
+                 device=0, genome_gap=16, max_cigar_ops=32):
+        self.L = lib()
+        self.params = Params(match, mismatch, gap_open, gap_extend, score_threshold, int(bool(report_cigar)), 0,
+                             device, genome_gap, max_cigar_ops, 0)
+        h = C.c_void_p()
+        rc = self.L.kslam_create(C.byref(self.params), C.byref(h))
+        if rc != 0:
+            raise KslamError(f"kslam_create failed ({rc}): {self.L.kslam_last_error(None).decode()}")
+        self.h = h
+        self._keep = []
+
+    # -- lifecycle
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.kslam_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc < 0:
+            raise KslamError(f"{what} failed ({rc}): {self.L.kslam_last_error(self.h).decode()}")
+        return rc
+
+    @property
+    def exact(self):
+        return bool(self.L.kslam_params_exact(C.byref(self.params)))
+
+    # -- the path
+    def load_genomes(self, bases, offs):
+        bases, offs = _u8(bases), _u64(offs)
+        self._check(self.L.kslam_load_genomes(self.h, len(offs) - 1, _ptr(bases), _ptr(offs)), "kslam_load_genomes")
+
+    def align_batch(self, bases, offs, copy=True) -> Alignments:
+        bases, offs = _u8(bases), _u64(offs)
+        out = _Alignments()
+        self._check(self.L.kslam_align_batch(self.h, len(offs) - 1, _ptr(bases), _ptr(offs), C.byref(out)),
+                    "kslam_align_batch")
+        return self._alignments(out, copy)
+
+    def upload_reads(self, bases, offs):
+        bases, offs = _u8(bases), _u64(offs)
+        self._check(self.L.kslam_upload_reads(self.h, len(offs) - 1, _ptr(bases), _ptr(offs)), "kslam_upload_reads")
+
+    def align_resident(self, fetch=False, copy=True):
+        out = _Alignments()
+        self._check(self.L.kslam_align_resident(self.h, int(fetch), C.byref(out)), "kslam_align_resident")
+        return self._alignments(out, copy) if fetch else int(out.n_overlaps)
+
+    def _alignments(self, out, copy):
+        ov = _view(out.overlaps, out.n_overlaps, OVERLAP_DT)
+        cg = _view(out.cigar_pool, out.n_cigar_words, np.dtype("<u4"))
+        return Alignments(ov.copy() if copy else ov, cg.copy() if copy else cg)
+
+    def pair_batch(self, fetch=True, copy=True):
+        out = _Pairs()
+        self._check(self.L.kslam_pair_batch(self.h, int(fetch), C.byref(out)), "kslam_pair_batch")
+        if not fetch:
+            return int(out.n_pairs)
+        so = _view(out.sorted_overlaps, out.n_sorted, OVERLAP_DT)
+        cg = _view(out.cigar_pool, out.n_cigar_words, np.dtype("<u4"))
+        pr = _view(out.pairs, out.n_pairs, PAIR_DT)
+        return Pairs(so.copy() if copy else so, cg.copy() if copy else cg, pr.copy() if copy else pr)
+
+    def ssw_batch(self, q, qoffs, r, roffs):
+        """Batched Aligner::Align; returns (overlap records in SSW coordinates, cigar pool)."""
+        q, r, qoffs, roffs = _u8(q), _u8(r), _u64(qoffs), _u64(roffs)
+        n = len(qoffs) - 1
+        out = np.zeros(n, dtype=OVERLAP_DT)
+        pool = np.zeros(max(1, n * self.params.max_cigar_ops), dtype=np.uint32)
+        self._check(self.L.kslam_ssw_batch(self.h, n, _ptr(q), _ptr(qoffs), _ptr(r), _ptr(roffs), _ptr(out), _ptr(pool)),
+                    "kslam_ssw_batch")
+        return out, pool
+
+    def ssw_upload(self, q, qoffs, r, roffs):
+        q, r, qoffs, roffs = _u8(q), _u8(r), _u64(qoffs), _u64(roffs)
+        self._check(self.L.kslam_ssw_upload(self.h, len(qoffs) - 1, _ptr(q), _ptr(qoffs), _ptr(r), _ptr(roffs)),
+                    "kslam_ssw_upload")
+
+    def ssw_resident(self):
+        self._check(self.L.kslam_ssw_resident(self.h, None, None), "kslam_ssw_resident")
+
+    # -- taps
+    def _tap(self, fn, dtype):
+        n = self._check(fn(self.h, None, 0), fn.__name__)
+        out = np.zeros(n, dtype=dtype)
+        if n:
+            self._check(fn(self.h, _ptr(out), n), fn.__name__)
+        return out
+
+    def genome_kmers(self):
+        return self._tap(self.L.kslam_get_genome_kmers, KMER_DT)
+
+    def read_kmers(self):
+        return self._tap(self.L.kslam_get_read_kmers, KMER_DT)
+
+    def raw_seeds(self):
+        return self._tap(self.L.kslam_get_raw_seeds, SEED_DT)
+
+    def seeds(self):
+        return self._tap(self.L.kslam_get_seeds, SEED_DT)
+
+    def sort_records(self, recs, lo_bit=0, hi_bit=64):
+        recs = np.ascontiguousarray(recs, dtype=KMER_DT).copy()
+        ms = C.c_float()
+        self._check(self.L.kslam_sort_records(self.h, _ptr(recs), len(recs), lo_bit, hi_bit, C.byref(ms)), "kslam_sort_records")
+        return recs, ms.value
+
+    def timings(self) -> dict:
+        t = Timings()
+        self._check(self.L.kslam_get_timings(self.h, C.byref(t)), "kslam_get_timings")
+        return t.as_dict()
+
+    def set_debug_taps(self, keep: bool):
+        self._check(self.L.kslam_set_debug_taps(self.h, int(keep)), "kslam_set_debug_taps")

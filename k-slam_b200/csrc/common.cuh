@@ -1,0 +1,160 @@
+// common.cuh — internal declarations shared by the CUDA translation units of libkslam.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/kslam.h"
+
+#define KSLAM_NUM_SMS_DEFAULT 148
+
+struct CudaError {
+  cudaError_t e; const char *what; const char *file; int line;
+};
+
+#define CUDA_TRY(x)                                                        \
+  do {                                                                     \
+    cudaError_t e_ = (x);                                                  \
+    if (e_ != cudaSuccess) throw CudaError{e_, #x, __FILE__, __LINE__};    \
+  } while (0)
+
+// Growable device buffer owned by a ctx; never shrinks (batches have similar sizes).
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) CUDA_TRY(cudaFree(p));
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CUDA_TRY(cudaMalloc(&p, want));
+    cap = want;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T *as() const { return (T *)p; }
+};
+
+// Growable pinned host buffer.
+struct HostBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    CUDA_TRY(cudaMallocHost(&p, want));
+    cap = want;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T *as() const { return (T *)p; }
+};
+
+// 16-byte record moved by the radix sort: the sort key is `key`, `val` rides along.
+// A k-mer record is {key = kMerInt, val = id_flags | offset << 32} == kslam_kmer's memory layout.
+struct __align__(16) Rec16 { uint64_t key; uint64_t val; };
+
+// A packed sequence set in HBM (reads of a batch, or the genomes). Sequence i occupies 32-base
+// words [word_off[i], word_off[i+1]) of every plane; base b of the word sits at bits 2b..2b+1
+// (2-bit planes) / bit b (mask plane).
+struct PackedSeqs {
+  uint64_t n = 0;          // sequences
+  uint64_t n_bases = 0;    // raw bytes
+  uint64_t n_words = 0;    // 32-base words
+  DevBuf raw;              // u8  raw bytes (transient for reads; dropped for genomes after packing)
+  DevBuf offs;             // u64 n+1 raw offsets
+  DevBuf word_off;         // u64 n+1 word offsets
+  DevBuf kbits;            // u64 per word: k-mer alphabet A0 C1 T2 G3, everything else 0 (KMer.h:246-266)
+  DevBuf sbits;            // u64 per word: SSW alphabet A0 C1 G2 T3 (U->0), code-4 bases 0 (ssw_cpp.cpp:11-23)
+  DevBuf nmask;            // u32 per word: bit set where the SSW code is 4
+  DevBuf xmask;            // u32 per word: bit set for a c g t U u (SSW code < 4 but never complemented)
+  DevBuf kmer_off;         // u64 n+1: first k-mer record index of each sequence
+  uint64_t n_kmers = 0;
+  uint32_t max_len = 0;
+  std::vector<uint64_t> h_offs;  // host copy of raw offsets
+  void release() { raw.release(); offs.release(); word_off.release(); kbits.release(); sbits.release();
+                   nmask.release(); xmask.release(); kmer_off.release(); }
+};
+
+struct SwWorkspace;
+
+struct kslam_ctx {
+  kslam_params prm;
+  int device = 0;
+  int num_sms = KSLAM_NUM_SMS_DEFAULT;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  bool keep_taps = true;
+
+  PackedSeqs genomes, reads;
+  bool genomes_loaded = false, reads_loaded = false, aligned = false;
+  DevBuf g_keys;   // u64 sorted genome k-mers
+  DevBuf g_vals;   // u64 id_flags | offset<<32, same order
+  uint64_t n_gk = 0;
+  uint32_t max_genome_len = 0;
+
+  DevBuf recA, recB;        // Rec16 ping-pong (read k-mers, then seeds)
+  DevBuf sort_hist;         // radix-sort histograms + look-back state
+  DevBuf scan_tmp;
+  DevBuf counters;          // small u64 counter block
+  HostBuf h_counters;
+  uint64_t n_rk = 0;        // read k-mer records
+  Rec16 *sorted_rk = nullptr;  // points into recA/recB
+
+  DevBuf raw_seeds;         // kslam_seed (tap) / Rec16 packed seeds
+  DevBuf seedA, seedB;      // Rec16 packed seeds ping-pong
+  DevBuf seed_keep;         // u8
+  DevBuf seeds;             // kslam_seed, de-duplicated, final order
+  uint64_t n_raw = 0, n_seeds = 0;
+
+  DevBuf ov;                // kslam_overlap[n_seeds]
+  DevBuf cig;               // u32[n_seeds * max_cigar_ops]
+  SwWorkspace *sw = nullptr;
+  HostBuf h_ov, h_cig;
+
+  DevBuf pair_keys, pair_keys2, ov_sorted, cig_sorted, pair_cnt, pairs;
+  HostBuf h_ov_sorted, h_cig_sorted, h_pairs;
+  uint64_t n_sorted = 0, n_pairs = 0;
+
+  // microbench / Aligner::Align batch
+  PackedSeqs swq, swr;
+  bool sw_loaded = false;
+
+  kslam_timings tm;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  uint64_t launches = 0;
+};
+
+// ---- helpers implemented across the .cu files ---------------------------------------------
+// pack.cu
+void pack_sequences(kslam_ctx *c, PackedSeqs &s, uint64_t n, const char *bases, const uint64_t *offs,
+                    uint32_t kmer_gap, bool keep_raw);
+// kmer.cu
+void extract_kmers(kslam_ctx *c, const PackedSeqs &s, bool is_gb, uint32_t gap, Rec16 *out);
+// radix_sort.cu
+// Sorts n records by bits [lo_bit, hi_bit) of their .key (word 0) or .val (word 1); stable.
+// Returns the buffer (a or b) holding the result; *passes_done is incremented per executed pass.
+Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, uint32_t lo_bit, uint32_t hi_bit,
+                  uint64_t *passes_done);
+// scan.cu
+void exclusive_scan_u32(kslam_ctx *c, const uint32_t *in, uint32_t *out, uint64_t n, uint64_t *total_dev);
+// join.cu
+void join_and_unique(kslam_ctx *c);
+// sw.cu
+void sw_align_seeds(kslam_ctx *c);
+void sw_align_pairs(kslam_ctx *c, uint64_t n, kslam_overlap *out_dev, uint32_t *cig_dev);
+void sw_workspace_free(kslam_ctx *c);
+// pair.cu
+void pair_overlaps(kslam_ctx *c);
+
+// event-based stage timing
+cudaEvent_t tm_mark(kslam_ctx *c);
+float tm_ms(cudaEvent_t a, cudaEvent_t b);
+
+static inline uint32_t ceil_log2_u64(uint64_t x) {
+  uint32_t b = 0;
+  while (b < 64 && (1ull << b) < x) b++;
+  return b;
+}

@@ -1,0 +1,101 @@
+// kmer.cu — canonical 32-mer extraction from 2-bit packed sequences (kernel K1).
+//
+// Restates /root/reference/src/KMer.h:160-181 (splitIntoKMersAndAddToVector) + :272-280
+// (addBaseToKMers) without the rolling loop: the forward k-mer at base p is a 64-bit funnel shift of
+// two packed words, its reverse complement is a bit-reversal + pair swap + complement mask, so every
+// k-mer position is independent and one lane owns one record. Output is the reference's 16-byte
+// record (KMer.h:58-116) written with one 128-bit store per lane, 512 B contiguous per warp.
+//
+// Algorithmic bytes: 16 B written per record (+0.25 B read per base) — HBM-write bound.
+#include "common.cuh"
+
+__device__ __forceinline__ uint64_t revcomp32(uint64_t f) {
+  // reverse the order of the 32 two-bit groups, then complement (code ^ 2, KMer.h:279)
+  uint64_t r = __brevll(f);                                   // reverses bits: groups reversed AND bit-swapped
+  r = ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+  return r ^ 0xAAAAAAAAAAAAAAAAull;
+}
+
+__device__ __forceinline__ void emit_kmer(Rec16 *out, uint64_t f, uint32_t id, uint32_t pos, uint32_t len,
+                                          bool is_gb) {
+  uint64_t rc = revcomp32(f);
+  Rec16 r;
+  uint32_t flags = (id & 0x3FFFFFFFu) | (is_gb ? 0x80000000u : 0u);
+  if (f < rc) {                       // forward wins only if strictly smaller (KMer.h:173)
+    r.key = f; r.val = (uint64_t)flags | ((uint64_t)pos << 32);
+  } else {                            // palindromes take the rc branch; read offsets are measured on the
+    uint32_t off = is_gb ? pos : len - KSLAM_K - pos;   // reverse strand: len-1-i with i = pos+31 (KMer.h:176)
+    r.key = rc; r.val = (uint64_t)(flags | 0x40000000u) | ((uint64_t)off << 32);
+  }
+  *reinterpret_cast<ulonglong2 *>(out) = make_ulonglong2(r.key, r.val);
+}
+
+__device__ __forceinline__ uint64_t kmer_at(const uint64_t *__restrict__ kbits, uint64_t woff, uint32_t p) {
+  uint32_t wi = p >> 5, r = p & 31;
+  uint64_t w0 = __ldg(&kbits[woff + wi]);
+  if (r == 0) return w0;
+  uint64_t w1 = __ldg(&kbits[woff + wi + 1]);   // guard words past the end make this always readable
+  return (w0 << (2 * r)) | (w1 >> (64 - 2 * r));
+}
+
+// Reads (gap 1): one warp per sequence, lanes stride over k-mer positions.
+__global__ void __launch_bounds__(256)
+k_extract_reads(const uint64_t *__restrict__ kbits, const uint64_t *__restrict__ offs,
+                const uint64_t *__restrict__ word_off, const uint64_t *__restrict__ kmer_off,
+                uint64_t n_seqs, Rec16 *__restrict__ out) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t seq = warp; seq < n_seqs; seq += nwarps) {
+    uint64_t len64 = __ldg(&offs[seq + 1]) - __ldg(&offs[seq]);
+    if (len64 < KSLAM_K) continue;              // KMer.h:167
+    uint32_t len = (uint32_t)len64;
+    uint64_t woff = __ldg(&word_off[seq]), koff = __ldg(&kmer_off[seq]);
+    uint32_t nk = len - KSLAM_K + 1;
+    for (uint32_t p = lane; p < nk; p += 32)
+      emit_kmer(out + koff + p, kmer_at(kbits, woff, p), (uint32_t)seq, p, len, false);
+  }
+}
+
+// Genomes (gap 16 by default): few long sequences; one thread per record, owner found by binary
+// search over kmer_off. Runs once per database load.
+__global__ void __launch_bounds__(256)
+k_extract_flat(const uint64_t *__restrict__ kbits, const uint64_t *__restrict__ offs,
+               const uint64_t *__restrict__ word_off, const uint64_t *__restrict__ kmer_off,
+               uint64_t n_seqs, uint64_t n_recs, uint32_t gap, bool is_gb, Rec16 *__restrict__ out) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_recs;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t lo = 0, hi = n_seqs;
+    while (hi - lo > 1) {
+      uint64_t mid = (lo + hi) >> 1;
+      if (__ldg(&kmer_off[mid]) <= i) lo = mid; else hi = mid;
+    }
+    uint64_t seq = lo;
+    uint64_t len = __ldg(&offs[seq + 1]) - __ldg(&offs[seq]);
+    uint64_t p = (i - __ldg(&kmer_off[seq])) * gap;
+    emit_kmer(out + i, kmer_at(kbits, __ldg(&word_off[seq]), (uint32_t)p), (uint32_t)seq, (uint32_t)p,
+              (uint32_t)len, is_gb);
+  }
+}
+
+void extract_kmers(kslam_ctx *c, const PackedSeqs &s, bool is_gb, uint32_t gap, Rec16 *out) {
+  if (!s.n_kmers) return;
+  if (!is_gb && gap == 1) {
+    uint64_t warps = s.n;
+    uint64_t blocks = (warps * 32 + 255) / 256;
+    uint64_t maxb = (uint64_t)c->num_sms * 8;
+    if (blocks > maxb) blocks = maxb;
+    k_extract_reads<<<(unsigned)blocks, 256, 0, c->stream>>>(s.kbits.as<uint64_t>(), s.offs.as<uint64_t>(),
+                                                             s.word_off.as<uint64_t>(), s.kmer_off.as<uint64_t>(),
+                                                             s.n, out);
+  } else {
+    uint64_t blocks = (s.n_kmers + 255) / 256;
+    uint64_t maxb = (uint64_t)c->num_sms * 16;
+    if (blocks > maxb) blocks = maxb;
+    k_extract_flat<<<(unsigned)blocks, 256, 0, c->stream>>>(s.kbits.as<uint64_t>(), s.offs.as<uint64_t>(),
+                                                            s.word_off.as<uint64_t>(), s.kmer_off.as<uint64_t>(),
+                                                            s.n, s.n_kmers, gap, is_gb, out);
+  }
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+}

@@ -1,0 +1,116 @@
+// pack.cu — raw sequence bytes -> bit planes in HBM.
+//
+// Three alphabets exist on this path and packing must not lose any of them:
+//   k-mer codec  /root/reference/src/KMer.h:246-266      A0 C1 T2 G3, every other byte 0
+//   SSW codec    /root/reference/src/ssw_cpp.cpp:11-23   A/a0 C/c1 G/g2 T/t3 U/u0, every other byte 4
+//   complement  /root/reference/src/sequenceTools.h:98-116 only swaps UPPER-CASE A/C/G/T (window rev-comp)
+// so each 32-base word is stored as: kbits (u64, k-mer codes, FIRST base in the MOST significant
+// bit pair so a 32-mer is a funnel shift of two words), sbits (u64, SSW codes 0-3, base b at bits
+// 2b..2b+1), nmask (u32, bit b set where the SSW code is 4) and xmask (u32, bit b set where the byte
+// is not upper-case ACGT but still has an SSW code < 4: a c g t U u — such bases are NOT complemented).
+#include "common.cuh"
+
+__constant__ uint8_t c_kcode[256];  // k-mer alphabet
+__constant__ uint8_t c_scode[256];  // SSW alphabet (0..4) | 8 when the byte is a/c/g/t/U/u
+
+static bool g_tables_ready[64] = {false};
+
+static void ensure_tables(int device) {
+  if (device < 64 && g_tables_ready[device]) return;
+  uint8_t k[256], s[256];
+  for (int i = 0; i < 256; i++) { k[i] = 0; s[i] = 4; }
+  k['A'] = 0; k['C'] = 1; k['T'] = 2; k['G'] = 3;
+  s['A'] = s['a'] = s['U'] = s['u'] = 0;
+  s['C'] = s['c'] = 1; s['G'] = s['g'] = 2; s['T'] = s['t'] = 3;
+  s['a'] |= 8; s['c'] |= 8; s['g'] |= 8; s['t'] |= 8; s['U'] |= 8; s['u'] |= 8;
+  CUDA_TRY(cudaMemcpyToSymbol(c_kcode, k, 256));
+  CUDA_TRY(cudaMemcpyToSymbol(c_scode, s, 256));
+  if (device < 64) g_tables_ready[device] = true;
+}
+
+// One thread per 32-base word. The sequence owning a word is found by binary search in word_off
+// (L2-resident); bytes are read through the read-only path (a warp covers 1 KB of contiguous input).
+__global__ void __launch_bounds__(256)
+k_pack(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ offs,
+       const uint64_t *__restrict__ word_off, uint64_t n_seqs, uint64_t n_words,
+       uint64_t *__restrict__ kbits, uint64_t *__restrict__ sbits, uint32_t *__restrict__ nmask,
+       uint32_t *__restrict__ xmask) {
+  __shared__ uint8_t s_k[256], s_s[256];
+  s_k[threadIdx.x] = c_kcode[threadIdx.x];
+  s_s[threadIdx.x] = c_scode[threadIdx.x];
+  __syncthreads();
+  for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words;
+       w += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t lo = 0, hi = n_seqs;  // last seq with word_off[seq] <= w  (empty sequences own no word)
+    while (hi - lo > 1) {
+      uint64_t mid = (lo + hi) >> 1;
+      if (__ldg(&word_off[mid]) <= w) lo = mid; else hi = mid;
+    }
+    uint64_t seq = lo;
+    uint64_t base0 = __ldg(&offs[seq]) + (w - __ldg(&word_off[seq])) * 32;
+    uint64_t end = __ldg(&offs[seq + 1]);
+    uint32_t cnt = (uint32_t)((end - base0) < 32 ? (end - base0) : 32);
+    uint64_t kb = 0, sb = 0; uint32_t nm = 0, xm = 0;
+#pragma unroll 8
+    for (uint32_t b = 0; b < 32; b++) {
+      if (b < cnt) {
+        uint8_t ch = __ldg(&raw[base0 + b]);
+        uint32_t sc = s_s[ch];
+        kb |= (uint64_t)s_k[ch] << (62 - 2 * b);
+        sb |= (uint64_t)(sc & 3) << (2 * b);
+        nm |= ((sc >> 2) & 1) << b;
+        xm |= (sc >> 3) << b;
+      }
+    }
+    kbits[w] = kb; sbits[w] = sb; nmask[w] = nm; xmask[w] = xm;
+  }
+}
+
+void pack_sequences(kslam_ctx *c, PackedSeqs &s, uint64_t n, const char *bases, const uint64_t *offs,
+                    uint32_t kmer_gap, bool keep_raw) {
+  ensure_tables(c->device);
+  s.n = n;
+  s.h_offs.assign(offs, offs + n + 1);
+  s.n_bases = offs[n] - offs[0];
+  std::vector<uint64_t> wo(n + 1), ko(n + 1);
+  uint64_t w = 0, k = 0; uint32_t max_len = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    uint64_t len = offs[i + 1] - offs[i];
+    wo[i] = w; ko[i] = k;
+    w += (len + 31) / 32;
+    if (len >= KSLAM_K) k += (len - KSLAM_K) / kmer_gap + 1;  // KMer.h:202
+    if (len > max_len) max_len = (uint32_t)(len > 0xffffffffull ? 0xffffffffull : len);
+  }
+  wo[n] = w; ko[n] = k;
+  s.n_words = w; s.n_kmers = k; s.max_len = max_len;
+  // rebase raw offsets to 0
+  std::vector<uint64_t> ro(n + 1);
+  for (uint64_t i = 0; i <= n; i++) ro[i] = offs[i] - offs[0];
+  s.raw.reserve(s.n_bases + 16);
+  s.offs.reserve((n + 1) * 8); s.word_off.reserve((n + 1) * 8); s.kmer_off.reserve((n + 1) * 8);
+  s.kbits.reserve((w + 2) * 8); s.sbits.reserve((w + 2) * 8); s.nmask.reserve((w + 2) * 4);
+  s.xmask.reserve((w + 2) * 4);
+  cudaStream_t st = c->stream;
+  if (s.n_bases) CUDA_TRY(cudaMemcpyAsync(s.raw.p, bases + offs[0], s.n_bases, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(s.offs.p, ro.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(s.word_off.p, wo.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(s.kmer_off.p, ko.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  // two guard words past the end so funnel shifts / window gathers may read one word ahead
+  CUDA_TRY(cudaMemsetAsync((char *)s.kbits.p + w * 8, 0, 16, st));
+  CUDA_TRY(cudaMemsetAsync((char *)s.sbits.p + w * 8, 0, 16, st));
+  CUDA_TRY(cudaMemsetAsync((char *)s.nmask.p + w * 4, 0, 8, st));
+  CUDA_TRY(cudaMemsetAsync((char *)s.xmask.p + w * 4, 0, 8, st));
+  if (w) {
+    uint64_t blocks = (w + 255) / 256;
+    uint64_t maxb = (uint64_t)c->num_sms * 8;
+    if (blocks > maxb) blocks = maxb;
+    k_pack<<<(unsigned)blocks, 256, 0, st>>>(s.raw.as<uint8_t>(), s.offs.as<uint64_t>(),
+                                             s.word_off.as<uint64_t>(), n, w, s.kbits.as<uint64_t>(),
+                                             s.sbits.as<uint64_t>(), s.nmask.as<uint32_t>(), s.xmask.as<uint32_t>());
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  // the host staging vectors (ro/wo/ko) must outlive the async copies
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (!keep_raw) s.raw.release();
+}

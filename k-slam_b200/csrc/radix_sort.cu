@@ -1,0 +1,235 @@
+// radix_sort.cu — hand-written LSD radix sort of 16-byte records by a 64-bit key (kernel K2).
+//
+// Replaces __gnu_parallel::sort in sortKMers (/root/reference/src/KMer.h:388-398) and the seed / pairing
+// sorts (/root/reference/src/Overlap.h:289, /root/reference/src/PairedOverlap.h:248-257). Design
+// ("onesweep"): ONE histogram launch counts every 8-bit digit of every pass in shared memory; then each
+// pass is ONE launch in which a CTA ranks a 4096-record tile with warp-wide digit matching
+// (__match_any_sync + popc ballots, per-warp shared-memory histograms), learns its global digit offsets
+// by decoupled look-back over the previous tiles' published counts, stages the tile in shared memory in
+// digit order and writes it out in contiguous runs. Per pass every record is read once and written once
+// (32 B); passes whose digit is constant over the whole input are skipped. Stable, so LSD order holds.
+//
+// Roofline: HBM. Algorithmic bytes per record = 32 B x passes (+16 B for the histogram read).
+#include "common.cuh"
+
+#define RS_THREADS 256
+#define RS_WARPS (RS_THREADS / 32)
+#define RS_IPT 16
+#define RS_TILE (RS_THREADS * RS_IPT)
+#define RS_MAX_PASSES 8
+
+#define RS_FLAG_AGG (1ull << 62)
+#define RS_FLAG_INCL (2ull << 62)
+#define RS_VAL_MASK ((1ull << 62) - 1)
+
+struct PassPlan {
+  uint32_t n_passes;
+  uint32_t shift[RS_MAX_PASSES];
+  uint32_t mask[RS_MAX_PASSES];
+};
+
+// ---- histogram of all digits in one read of the keys ----------------------------------------
+__global__ void __launch_bounds__(512)
+k_rs_hist(const Rec16 *__restrict__ in, uint64_t n, PassPlan plan, uint32_t word,
+          unsigned long long *__restrict__ ghist) {
+  __shared__ uint32_t s_hist[RS_MAX_PASSES * 256];
+  for (uint32_t i = threadIdx.x; i < plan.n_passes * 256; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t key = word ? __ldg(&in[i].val) : __ldg(&in[i].key);
+#pragma unroll
+    for (uint32_t p = 0; p < RS_MAX_PASSES; p++)
+      if (p < plan.n_passes) atomicAdd(&s_hist[p * 256 + ((uint32_t)(key >> plan.shift[p]) & plan.mask[p])], 1u);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < plan.n_passes * 256; i += blockDim.x) {
+    uint32_t v = s_hist[i];
+    if (v) atomicAdd(&ghist[i], (unsigned long long)v);
+  }
+}
+
+// exclusive scan of each pass' 256 counts; trivial[p] = 1 when one digit holds every record
+__global__ void __launch_bounds__(256)
+k_rs_scan_hist(unsigned long long *__restrict__ ghist, uint32_t n_passes, uint64_t n, uint32_t *__restrict__ trivial) {
+  __shared__ unsigned long long s[256];
+  for (uint32_t p = 0; p < n_passes; p++) {
+    unsigned long long v = ghist[p * 256 + threadIdx.x];
+    s[threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long run = 0; uint32_t triv = 0;
+      for (int d = 0; d < 256; d++) { unsigned long long t = s[d]; if (t == n) triv = 1; s[d] = run; run += t; }
+      trivial[p] = triv;
+    }
+    __syncthreads();
+    ghist[p * 256 + threadIdx.x] = s[threadIdx.x];
+    __syncthreads();
+  }
+}
+
+// ---- one LSD pass ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RS_THREADS, 2)
+k_rs_onesweep(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n, uint32_t shift, uint32_t mask,
+              uint32_t word,                                       // 0: sort by .key, 1: sort by .val
+              const unsigned long long *__restrict__ digit_base,  // [256] exclusive global offsets
+              volatile unsigned long long *tile_state,            // [tiles][256], zero-initialised
+              uint32_t *__restrict__ ticket) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Rec16 *stage = reinterpret_cast<Rec16 *>(smem_raw);                               // RS_TILE records
+  uint32_t *whist = reinterpret_cast<uint32_t *>(smem_raw + RS_TILE * sizeof(Rec16)); // [RS_WARPS][256]
+  __shared__ uint32_t s_dexcl[256];
+  __shared__ unsigned long long s_gbase[256];
+  __shared__ uint32_t s_scan[32];
+  __shared__ uint32_t s_tile;
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+#pragma unroll
+  for (uint32_t i = tid; i < RS_WARPS * 256; i += RS_THREADS) whist[i] = 0;
+  __syncthreads();
+  const uint64_t tile = s_tile;
+  const uint64_t tile_base = tile * RS_TILE;
+  const uint32_t count = (uint32_t)((n - tile_base) < RS_TILE ? (n - tile_base) : RS_TILE);
+
+  // 1. load, warp-striped so that (warp, item, lane) order == input order (stability)
+  uint64_t key[RS_IPT], val[RS_IPT];
+  uint32_t rank[RS_IPT];
+  const uint32_t wbase = warp * 32 * RS_IPT;
+#pragma unroll
+  for (int i = 0; i < RS_IPT; i++) {
+    uint32_t idx = wbase + i * 32 + lane;
+    if (idx < count) {
+      ulonglong2 r = __ldg(reinterpret_cast<const ulonglong2 *>(in + tile_base + idx));
+      key[i] = r.x; val[i] = r.y;
+    } else { key[i] = ~0ull; val[i] = 0; }   // padding sorts to the very end of the tile
+  }
+
+  // 2. per-warp digit ranks: peers with my digit via match_any, rank = earlier peers + warp running count
+  uint32_t *myhist = whist + warp * 256;
+  const uint32_t lt_mask = (1u << lane) - 1;
+#pragma unroll
+  for (int i = 0; i < RS_IPT; i++) {
+    uint32_t idx = wbase + i * 32 + lane;
+    uint32_t d = idx < count ? ((uint32_t)((word ? val[i] : key[i]) >> shift) & mask) : 255u;
+    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    uint32_t leader = __ffs(peers) - 1;
+    uint32_t old = 0;
+    if (lane == leader) { old = myhist[d]; myhist[d] = old + __popc(peers); }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[i] = old + __popc(peers & lt_mask);
+    __syncwarp();
+  }
+  __syncthreads();
+
+  // 3. thread d owns digit d: exclusive offsets over warps, tile count
+  uint32_t cnt_d = 0;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; w++) { uint32_t t = whist[w * 256 + tid]; whist[w * 256 + tid] = cnt_d; cnt_d += t; }
+  uint32_t real_d = cnt_d;
+  if (tid == 255) real_d -= (RS_TILE - count);   // padding records were counted in digit 255
+
+  // 4. publish, then look back for the exclusive prefix over earlier tiles
+  volatile unsigned long long *my_state = tile_state + tile * 256 + tid;
+  if (tile == 0) *my_state = RS_FLAG_INCL | real_d; else *my_state = RS_FLAG_AGG | real_d;
+  unsigned long long excl = 0;
+  if (tile > 0) {
+    for (int64_t t = (int64_t)tile - 1; t >= 0; t--) {
+      volatile unsigned long long *ps = tile_state + (uint64_t)t * 256 + tid;
+      unsigned long long s;
+      do { s = *ps; } while ((s >> 62) == 0);
+      excl += s & RS_VAL_MASK;
+      if ((s >> 62) == 2) break;
+    }
+    *my_state = RS_FLAG_INCL | (excl + real_d);
+  }
+  s_gbase[tid] = digit_base[tid] + excl;
+
+  // 5. tile-local exclusive scan over digits (counts include padding so positions cover the tile)
+  {
+    uint32_t inc = cnt_d;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, dlt); if (lane >= dlt) inc += t; }
+    if (lane == 31) s_scan[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = lane < RS_WARPS ? s_scan[lane] : 0, winc = w;
+#pragma unroll
+      for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, winc, dlt); if (lane >= dlt) winc += t; }
+      s_scan[lane] = winc - w;
+    }
+    __syncthreads();
+    s_dexcl[tid] = s_scan[warp] + inc - cnt_d;
+  }
+  __syncthreads();
+
+  // 6. stage in digit order
+#pragma unroll
+  for (int i = 0; i < RS_IPT; i++) {
+    uint32_t idx = wbase + i * 32 + lane;
+    uint32_t d = idx < count ? ((uint32_t)((word ? val[i] : key[i]) >> shift) & mask) : 255u;
+    uint32_t pos = s_dexcl[d] + myhist[d] + rank[i];
+    *reinterpret_cast<ulonglong2 *>(stage + pos) = make_ulonglong2(key[i], val[i]);
+  }
+  __syncthreads();
+
+  // 7. write out: position j of the staged tile belongs to digit d at global gbase[d] + (j - dexcl[d])
+  for (uint32_t j = tid; j < count; j += RS_THREADS) {
+    ulonglong2 r = *reinterpret_cast<const ulonglong2 *>(stage + j);
+    uint32_t d = (uint32_t)((word ? r.y : r.x) >> shift) & mask;
+    *reinterpret_cast<ulonglong2 *>(out + s_gbase[d] + (j - s_dexcl[d])) = r;
+  }
+}
+
+static const size_t RS_SMEM = RS_TILE * sizeof(Rec16) + RS_WARPS * 256 * sizeof(uint32_t);
+
+Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, uint32_t lo_bit, uint32_t hi_bit,
+                  uint64_t *passes_done) {
+  if (n < 2 || hi_bit <= lo_bit) return a;
+  if (hi_bit > 64) hi_bit = 64;
+  cudaStream_t st = c->stream;
+  // a wide key range is sorted in groups of <= 8 passes
+  Rec16 *cur = a, *alt = b;
+  static bool attr_set[64] = {false};
+  if (!(c->device < 64 && attr_set[c->device])) {
+    CUDA_TRY(cudaFuncSetAttribute(k_rs_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
+    if (c->device < 64) attr_set[c->device] = true;
+  }
+  PassPlan plan;
+  plan.n_passes = 0;
+  for (uint32_t s = lo_bit; s < hi_bit && plan.n_passes < RS_MAX_PASSES; s += 8) {
+    uint32_t bits = hi_bit - s < 8 ? hi_bit - s : 8;
+    plan.shift[plan.n_passes] = s; plan.mask[plan.n_passes] = (1u << bits) - 1; plan.n_passes++;
+  }
+  const uint64_t tiles = (n + RS_TILE - 1) / RS_TILE;
+  // layout of sort_hist: [8*256 u64 hist][8 u32 trivial][8 u32 tickets][pad][tiles*256 u64 state]
+  const size_t hist_bytes = RS_MAX_PASSES * 256 * 8, misc_bytes = 128;
+  c->sort_hist.reserve(hist_bytes + misc_bytes + tiles * 256 * 8);
+  unsigned long long *ghist = c->sort_hist.as<unsigned long long>();
+  uint32_t *trivial = reinterpret_cast<uint32_t *>((char *)c->sort_hist.p + hist_bytes);
+  uint32_t *tickets = trivial + 8;
+  unsigned long long *state = reinterpret_cast<unsigned long long *>((char *)c->sort_hist.p + hist_bytes + misc_bytes);
+  CUDA_TRY(cudaMemsetAsync(c->sort_hist.p, 0, hist_bytes + misc_bytes, st));
+  {
+    uint64_t blocks = (n + 512 * 16 - 1) / (512 * 16);
+    uint64_t maxb = (uint64_t)c->num_sms * 4;
+    if (blocks > maxb) blocks = maxb;
+    k_rs_hist<<<(unsigned)blocks, 512, 0, st>>>(cur, n, plan, word, ghist);
+    k_rs_scan_hist<<<1, 256, 0, st>>>(ghist, plan.n_passes, n, trivial);
+    c->launches += 2;
+  }
+  uint32_t h_trivial[8];
+  CUDA_TRY(cudaMemcpyAsync(h_trivial, trivial, sizeof(h_trivial), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (uint32_t p = 0; p < plan.n_passes; p++) {
+    if (h_trivial[p]) continue;   // every record has the same digit: the pass would be the identity
+    CUDA_TRY(cudaMemsetAsync(state, 0, tiles * 256 * 8, st));
+    k_rs_onesweep<<<(unsigned)tiles, RS_THREADS, RS_SMEM, st>>>(cur, alt, n, plan.shift[p], plan.mask[p], word,
+                                                                 ghist + p * 256, state, tickets + p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    Rec16 *t = cur; cur = alt; alt = t;
+    if (passes_done) (*passes_done)++;
+  }
+  return cur;
+}

@@ -1,0 +1,727 @@
+// sw.cu — Smith-Waterman validation of seeds (kernels K5-K8).
+//
+// Reference: performSmithWatermanOnRange2 (/root/reference/src/SmithWaterman.h:184-233) builds the window,
+// calls StripedSmithWaterman::Aligner::Align (/root/reference/src/ssw_cpp.cpp:234-283) which runs SSW's
+// striped forward pass, reverse pass and banded traceback (/root/reference/src/ssw.c:841-951, :143-592,
+// :594-792), then un-flips coordinates for reverse-complement seeds.
+//
+// Here:
+//  * k_sw_fast<LANES, REVERSE>: a group of LANES threads owns TWO alignments packed in the halves of s16x2
+//    registers; each lane keeps SW_R=20 query rows (H, E and a 4-byte score profile per row) in registers and
+//    the group sweeps the columns as an anti-diagonal wavefront (lane g works on column t-g at step t,
+//    boundary H/F handed down with shuffles). One PRMT builds the packed substitution score from the two
+//    profiles, the recurrences are DPX VIADDMNMX/VIMNMX ops. Scores are scaled by 32 so the free low 5 bits
+//    of every cell carry (31 - row-in-lane): a single viaddmax per cell tracks "max score, then smallest row",
+//    which together with the step counter reproduces SSW's tie rules exactly (first column, then smallest row).
+//    REVERSE=true runs the same sweep over the reversed prefixes and records the first column reaching the
+//    forward score (ssw.c:905-923). No tensor cores: nothing here is a dense contraction.
+//  * k_sw_slow: exact scalar fallback (one thread per alignment) for shapes outside the fast kernel's range.
+//  * k_sw_traceback: literal restatement of banded_sw (ssw.c:594-792) — rolling h_b/e_b/h_c arrays with the
+//    reference's index maps (set_u/set_d), direction bytes, band doubling, traceback quirks — one thread per
+//    alignment, then the reverse-complement un-flip and refStart offset (SmithWaterman.h:212-229).
+// Roofline: integer (ALU) pipe; cells/s reported as GCUPS next to the counted ops/cell.
+#include "common.cuh"
+
+#define SW_R 20
+#define SW_MAXCOLS 512
+#define SW_BLOCK 128
+#define SW_INVALID 0xFFFFFFFFu
+#define SW_TB_MAXBAND 7
+#define SW_TB_MAXROWS 160
+
+struct __align__(16) SwTask {
+  uint64_t q_word;   // first 32-base word of the query in the query planes
+  uint64_t w_word;   // first word of the sequence holding the window
+  uint32_t m;        // query length
+  uint32_t n;        // window length (== ref_len passed to Align)
+  uint32_t w_start;  // window start (bases) inside its sequence
+  uint32_t flags;    // bit0: window is reverse-complemented; bits 8-15: class
+};
+#define SWT_REV 1u
+#define SWC_FAST8 0u
+#define SWC_SLOW 3u
+#define SWC_NONE 4u   // empty query or window: score 0, nothing to run
+
+struct __align__(16) SwRes {
+  int32_t score, ref_end, read_end, ref_begin, read_begin;
+  uint32_t flags, pad0, pad1;
+};
+
+struct SwPlanes {
+  const uint64_t *q_sbits; const uint32_t *q_nmask;
+  const uint64_t *w_sbits; const uint32_t *w_nmask; const uint32_t *w_xmask;
+};
+
+struct SwScore {
+  int32_t match, mismatch, gap_open, gap_extend;   // positive magnitudes, as given
+  uint32_t score_threshold; uint32_t report_cigar; uint32_t cigar_cap;
+};
+
+struct SwWorkspace {
+  DevBuf tasks, res, keys, keys2, items, tb_scratch;
+  uint64_t n = 0;
+};
+
+// ---------------------------------------------------------------- sequence accessors
+__device__ __forceinline__ uint32_t q_code(const SwPlanes &p, const SwTask &t, uint32_t i) {
+  uint64_t w = t.q_word + (i >> 5); uint32_t b = i & 31;
+  if ((__ldg(&p.q_nmask[w]) >> b) & 1) return 4;
+  return (uint32_t)(__ldg(&p.q_sbits[w]) >> (2 * b)) & 3;
+}
+// window base x (0..n-1) in the orientation Align sees (SmithWaterman.h:206-208): reversed + complemented
+// when the seed is reverse-complement; only upper-case ACGT are complemented (sequenceTools.h:98-116)
+__device__ __forceinline__ uint32_t w_code(const SwPlanes &p, const SwTask &t, uint32_t x) {
+  uint32_t pos = (t.flags & SWT_REV) ? t.w_start + t.n - 1 - x : t.w_start + x;
+  uint64_t w = t.w_word + (pos >> 5); uint32_t b = pos & 31;
+  if ((__ldg(&p.w_nmask[w]) >> b) & 1) return 4;
+  uint32_t c = (uint32_t)(__ldg(&p.w_sbits[w]) >> (2 * b)) & 3;
+  if ((t.flags & SWT_REV) && !((__ldg(&p.w_xmask[w]) >> b) & 1)) c = 3 - c;
+  return c;
+}
+
+__device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
+
+// ---------------------------------------------------------------- fast kernel
+template <int LANES, bool REVERSE>
+__global__ void __launch_bounds__(SW_BLOCK, 4)
+k_sw_fast(const SwTask *__restrict__ tasks, const uint2 *__restrict__ items, uint32_t n_items, SwPlanes pl,
+          SwScore sc, SwRes *__restrict__ res) {
+  constexpr int GROUPS = SW_BLOCK / LANES;
+  __shared__ uint32_t s_sel[GROUPS][SW_MAXCOLS];
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t g = lane % LANES;
+  const uint32_t grp = threadIdx.x / LANES;
+  const uint32_t gmask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << (lane - g));
+  const uint32_t item = blockIdx.x * GROUPS + grp;
+  uint2 it = make_uint2(SW_INVALID, SW_INVALID);
+  if (item < n_items) it = items[item];
+  if (it.x == SW_INVALID) return;            // whole group leaves together (shuffles below use gmask only)
+  const SwTask ta = tasks[it.x], tb = tasks[it.y];
+  SwRes ra, rb;
+  uint32_t ncols, rowsA, rowsB;
+  if (REVERSE) {
+    ra = res[it.x]; rb = res[it.y];
+    ncols = (uint32_t)ra.ref_end + 1; rowsA = (uint32_t)ra.read_end + 1; rowsB = (uint32_t)rb.read_end + 1;
+  } else { ncols = ta.n; rowsA = ta.m; rowsB = tb.m; }
+
+  // column selectors: PRMT nibbles picking byte w of profile A (-> low half, sign-extended) and byte w of
+  // profile B (-> high half); flag bits 16/17 mark code-4 columns (score 0 against everything)
+  for (uint32_t j = g; j < ncols; j += LANES) {
+    uint32_t xa = REVERSE ? (uint32_t)ra.ref_end - j : j, xb = REVERSE ? (uint32_t)rb.ref_end - j : j;
+    uint32_t wa = w_code(pl, ta, xa), wb = w_code(pl, tb, xb);
+    uint32_t fl = (wa == 4 ? 0x10000u : 0u) | (wb == 4 ? 0x20000u : 0u);
+    wa &= 3; wb &= 3;
+    s_sel[grp][j] = wa | ((8u | wa) << 4) | ((4u + wb) << 8) | ((12u + wb) << 12) | fl;
+  }
+  // row profiles: bytes [s(q,A) s(q,C) s(q,G) s(q,T)] scaled by 32; code-4 query rows score 0; padding rows
+  // (beyond the query) mismatch everything so they can never create or extend a maximum
+  const uint32_t mis_b = (uint32_t)(-(sc.mismatch * 32)) & 0xffu, mat_b = (uint32_t)(sc.match * 32) & 0xffu;
+  uint32_t PA[SW_R], PB[SW_R];
+#pragma unroll
+  for (int r = 0; r < SW_R; r++) {
+    uint32_t i = g * SW_R + r;
+    uint32_t pa = mis_b * 0x01010101u, pb = pa;
+    if (i < rowsA) { uint32_t c = q_code(pl, ta, REVERSE ? rowsA - 1 - i : i);
+                     pa = c == 4 ? 0u : (pa ^ ((mis_b ^ mat_b) << (8 * c))); }
+    if (i < rowsB) { uint32_t c = q_code(pl, tb, REVERSE ? rowsB - 1 - i : i);
+                     pb = c == 4 ? 0u : (pb ^ ((mis_b ^ mat_b) << (8 * c))); }
+    PA[r] = pa; PB[r] = pb;
+  }
+  __syncwarp(gmask);
+
+  const uint32_t NEG_GO = pack2(-sc.gap_open * 32), NEG_GE = pack2(-sc.gap_extend * 32), MIN2 = 0x80008000u;
+  uint32_t H[SW_R], E[SW_R];
+#pragma unroll
+  for (int r = 0; r < SW_R; r++) { H[r] = 0; E[r] = 0; }
+  uint32_t lastH = 0, lastF = 0, prevUpH = 0;
+  // forward: best = (H*32 | 31) of the running maximum, info = step << 16 | key at the step it was set
+  // reverse: thr = forward score * 32, info = first step whose lane maximum reaches it
+  uint32_t bestA = 31, bestB = 31, infoA = 0, infoB = 0;
+  const uint32_t thrA = REVERSE ? (uint32_t)ra.score * 32u : 0u, thrB = REVERSE ? (uint32_t)rb.score * 32u : 0u;
+  bool hitA = false, hitB = false;
+
+  const uint32_t steps = ncols + LANES - 1;
+  for (uint32_t t = 0; t < steps; t++) {
+    uint32_t upH = __shfl_up_sync(gmask, lastH, 1, LANES);
+    uint32_t upF = __shfl_up_sync(gmask, lastF, 1, LANES);
+    if (g == 0) { upH = 0; upF = 0; }
+    const int32_t j = (int32_t)t - (int32_t)g;
+    if (j >= 0 && j < (int32_t)ncols) {
+      const uint32_t selw = s_sel[grp][j];
+      const uint32_t sel = selw & 0xffffu;
+      uint32_t hd = prevUpH, f = upF, acc = 0;
+      if (selw >> 16) {
+        // a code-4 (N) column in one or both alignments: substitution score 0 there (ssw_cpp.cpp:43-48)
+        const uint32_t cm = ((selw & 0x10000u) ? 0u : 0xffffu) | ((selw & 0x20000u) ? 0u : 0xffff0000u);
+#pragma unroll
+        for (int r = 0; r < SW_R; r++) {
+          uint32_t s = __byte_perm(PA[r], PB[r], sel) & cm;
+          uint32_t h = __viaddmax_s16x2_relu(hd, s, E[r]);
+          h = __vimax3_s16x2(h, f, f);
+          hd = H[r]; H[r] = h;
+          uint32_t hgo = __viaddmax_s16x2(h, NEG_GO, MIN2);
+          E[r] = __viaddmax_s16x2(E[r], NEG_GE, hgo);
+          f = __viaddmax_s16x2(f, NEG_GE, hgo);
+          acc = __viaddmax_s16x2(h, (uint32_t)(31 - r) * 0x10001u, acc);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < SW_R; r++) {
+          uint32_t s = __byte_perm(PA[r], PB[r], sel);
+          uint32_t h = __viaddmax_s16x2_relu(hd, s, E[r]);       // max(H[i-1][j-1] + s, E, 0)
+          h = __vimax3_s16x2(h, f, f);                            // ... and F
+          hd = H[r]; H[r] = h;
+          uint32_t hgo = __viaddmax_s16x2(h, NEG_GO, MIN2);       // H - gapOpen
+          E[r] = __viaddmax_s16x2(E[r], NEG_GE, hgo);             // E for column j+1
+          f = __viaddmax_s16x2(f, NEG_GE, hgo);                   // F for row i+1
+          acc = __viaddmax_s16x2(h, (uint32_t)(31 - r) * 0x10001u, acc);  // max of H*32 + (31 - r)
+        }
+      }
+      lastH = H[SW_R - 1]; lastF = f; prevUpH = upH;
+      const uint32_t aA = acc & 0xffffu, aB = acc >> 16;
+      if (REVERSE) {
+        if (!hitA && aA >= thrA) { hitA = true; infoA = (t << 16) | aA; }
+        if (!hitB && aB >= thrB) { hitB = true; infoB = (t << 16) | aB; }
+      } else {
+        if (aA > bestA) { bestA = aA | 31u; infoA = (t << 16) | aA; }
+        if (aB > bestB) { bestB = aB | 31u; infoB = (t << 16) | aB; }
+      }
+    }
+  }
+
+  // group reduction. forward: max score, then smallest column, then smallest row. reverse: first column
+  // (smallest scan index) that reached the score, then smallest row.
+  uint32_t keyA, keyB;
+  {
+    uint32_t colA = (infoA >> 16) - g, rowA = g * SW_R + (31u - (infoA & 31u));
+    uint32_t colB = (infoB >> 16) - g, rowB = g * SW_R + (31u - (infoB & 31u));
+    if (REVERSE) {
+      keyA = hitA ? (((1023u - colA) << 10) | (1023u - rowA)) : 0u;
+      keyB = hitB ? (((1023u - colB) << 10) | (1023u - rowB)) : 0u;
+    } else {
+      keyA = bestA > 31u ? (((bestA >> 5) << 20) | ((1023u - colA) << 10) | (1023u - rowA)) : 0u;
+      keyB = bestB > 31u ? (((bestB >> 5) << 20) | ((1023u - colB) << 10) | (1023u - rowB)) : 0u;
+    }
+  }
+#pragma unroll
+  for (int d = 1; d < LANES; d <<= 1) {
+    uint32_t oa = __shfl_xor_sync(gmask, keyA, d, LANES), ob = __shfl_xor_sync(gmask, keyB, d, LANES);
+    keyA = keyA > oa ? keyA : oa; keyB = keyB > ob ? keyB : ob;
+  }
+  if (g == 0) {
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      if (half == 1 && it.y == it.x) break;
+      const uint32_t key = half ? keyB : keyA;
+      const uint32_t idx = half ? it.y : it.x;
+      const uint32_t col = 1023u - ((key >> 10) & 1023u), row = 1023u - (key & 1023u);
+      if (REVERSE) {
+        const SwRes &r0 = half ? rb : ra;
+        if (key) { res[idx].ref_begin = r0.ref_end - (int32_t)col; res[idx].read_begin = r0.read_end - (int32_t)row; }
+        else { res[idx].ref_begin = 0; res[idx].read_begin = 0; res[idx].flags = r0.flags | KSLAM_FLAG_UNDEFINED; }
+      } else {
+        SwRes o;
+        o.flags = 0; o.pad0 = o.pad1 = 0; o.ref_begin = -1; o.read_begin = 0;
+        if (key) { o.score = (int32_t)(key >> 20); o.ref_end = (int32_t)col; o.read_end = (int32_t)row; }
+        else { o.score = 0; o.ref_end = -1; o.read_end = 0; }        // ssw.c:169 (no positive cell)
+        res[idx] = o;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- slow exact fallback
+// One thread per alignment, plain Gotoh in int32 with SSW's tie rules; H/E rows live in global scratch.
+__device__ void sw_scan_slow(const SwPlanes &pl, const SwTask &t, const SwScore &sc, bool reverse, int32_t rows,
+                             int32_t cols, int32_t ref_end, int32_t read_end, int32_t terminate, int32_t *H,
+                             int32_t *E, uint32_t stride, int32_t *o_score, int32_t *o_ref, int32_t *o_read) {
+  int32_t best = 0, bref = -1, bread = 0;
+  for (int32_t i = 0; i < rows; i++) { H[(size_t)i * stride] = 0; E[(size_t)i * stride] = 0; }
+  for (int32_t c = 0; c < cols; c++) {
+    uint32_t wc = w_code(pl, t, reverse ? (uint32_t)(ref_end - c) : (uint32_t)c);
+    int32_t F = 0, diag = 0, colmax = 0, colrow = 0;
+    for (int32_t i = 0; i < rows; i++) {
+      uint32_t qc = q_code(pl, t, reverse ? (uint32_t)(read_end - i) : (uint32_t)i);
+      int32_t s = (wc == 4 || qc == 4) ? 0 : (wc == qc ? sc.match : -sc.mismatch);
+      int32_t h = diag + s, e = E[(size_t)i * stride];
+      if (h < e) h = e; if (h < F) h = F; if (h < 0) h = 0;
+      diag = H[(size_t)i * stride]; H[(size_t)i * stride] = h;
+      if (h > colmax) { colmax = h; colrow = i; }
+      int32_t hg = h - sc.gap_open; if (hg < 0) hg = 0;
+      e -= sc.gap_extend; if (e < 0) e = 0; E[(size_t)i * stride] = e > hg ? e : hg;
+      F -= sc.gap_extend; if (F < 0) F = 0; if (F < hg) F = hg;
+    }
+    if (colmax > best) { best = colmax; bref = c; bread = colrow; }
+    if (terminate >= 0 && colmax == terminate) break;
+  }
+  *o_score = best; *o_ref = bref; *o_read = bread;
+}
+
+__global__ void __launch_bounds__(128)
+k_sw_slow(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, uint32_t n_list, SwPlanes pl,
+          SwScore sc, SwRes *__restrict__ res, int32_t *__restrict__ scratch, uint32_t max_rows) {
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  int32_t *H = scratch + tid, *E = scratch + (size_t)max_rows * nthreads + tid;
+  for (uint32_t k = tid; k < n_list; k += nthreads) {
+    const uint32_t idx = list[k];
+    const SwTask t = tasks[idx];
+    SwRes o; o.flags = 0; o.pad0 = o.pad1 = 0; o.ref_begin = -1; o.read_begin = 0;
+    int32_t s, r, q;
+    sw_scan_slow(pl, t, sc, false, (int32_t)t.m, (int32_t)t.n, 0, 0, -1, H, E, nthreads, &s, &r, &q);
+    o.score = s; o.ref_end = r; o.read_end = q;
+    if (s > 0) {
+      int32_t s2, r2, q2;
+      sw_scan_slow(pl, t, sc, true, q + 1, r + 1, r, q, s, H, E, nthreads, &s2, &r2, &q2);
+      o.ref_begin = r - r2; o.read_begin = q - q2;
+    } else { o.ref_end = -1; o.read_end = 0; }
+    res[idx] = o;
+  }
+}
+
+// ---------------------------------------------------------------- banded traceback (ssw.c:594-792)
+#define SET_U(u, w, i, j) { int x_ = (i) - (w); x_ = x_ > 0 ? x_ : 0; (u) = (j) - x_ + 1; }
+
+// Returns cigar length (>= 1), -1 = undefined in the reference, -2 = "no cigar" (ssw.c:631-642),
+// -3 = scratch too small for the band this alignment needs (caller retries with the big-scratch path).
+// dir holds one byte per band cell: bit0 = (E came from H, code 3), bit1 = (F came from H, code 5),
+// bits 2-4 = the H direction code 1..5 exactly as banded_sw would store it.
+__device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const SwScore &sc, int32_t ref0,
+                                    int32_t read0, int32_t refLen, int32_t readLen, int32_t score, int32_t *h_b,
+                                    int32_t *e_b, int32_t *h_c, uint32_t arr_cap, uint8_t *dir, size_t dir_cap,
+                                    size_t dstride, uint32_t *cig, uint32_t cig_cap, bool reverse_out,
+                                    uint32_t *overflow) {
+  const int32_t go = sc.gap_open, ge = sc.gap_extend;
+  int32_t band = (refLen > readLen ? refLen - readLen : readLen - refLen) + 1;
+  int32_t width = 0, width_d = 0, maxv = 0;
+  do {
+    width = band * 2 + 3; width_d = band * 2 + 1;
+    if ((int64_t)width_d * readLen * 3 >= (1ll << 30)) return -2;
+    if ((uint32_t)width > arr_cap || (size_t)width_d * (size_t)readLen > dir_cap) return -3;
+    for (int32_t j = 1; j < width - 1; j++) h_b[j] = 0;
+    for (int32_t i = 0; i < readLen; i++) {
+      int32_t beg = i - band > 0 ? i - band : 0, end = i + band < refLen - 1 ? i + band : refLen - 1;
+      int32_t edge = end + 1 < width - 1 ? end + 1 : width - 1, u = 0;
+      int32_t f = 0;
+      h_b[0] = 0; e_b[0] = 0; h_b[edge] = 0; e_b[edge] = 0; h_c[0] = 0;
+      const uint32_t qc = q_code(pl, t, (uint32_t)(read0 + i));
+      uint8_t *dl = dir + (size_t)width_d * i * dstride;
+      const int32_t xoff = i - band > 0 ? i - band : 0;
+      for (int32_t j = beg; j <= end; j++) {
+        int32_t e, b, d;
+        SET_U(u, band, i, j); SET_U(e, band, i - 1, j); SET_U(b, band, i, j - 1); SET_U(d, band, i - 1, j - 1);
+        int32_t t1 = i == 0 ? -go : h_b[e] - go;
+        int32_t t2 = i == 0 ? -ge : e_b[e] - ge;
+        const int32_t ev = t1 > t2 ? t1 : t2;
+        const uint32_t de = t1 > t2 ? 3u : 2u;
+        e_b[u] = ev;
+        t1 = h_c[b] - go; t2 = f - ge;
+        f = t1 > t2 ? t1 : t2;
+        const uint32_t df = t1 > t2 ? 5u : 4u;
+        const int32_t e1 = ev > 0 ? ev : 0, f1 = f > 0 ? f : 0;
+        t1 = e1 > f1 ? e1 : f1;
+        const uint32_t wc = w_code(pl, t, (uint32_t)(ref0 + j));
+        const int32_t s = (wc == 4 || qc == 4) ? 0 : (wc == qc ? sc.match : -sc.mismatch);
+        t2 = h_b[d] + s;
+        const int32_t hv = t1 > t2 ? t1 : t2;
+        h_c[u] = hv;
+        if (hv > maxv) maxv = hv;
+        const uint32_t dh = t1 <= t2 ? 1u : (e1 > f1 ? de : df);
+        dl[(size_t)(j - xoff) * dstride] = (uint8_t)((de == 3u) | ((df == 5u) << 1) | (dh << 2));
+      }
+      for (int32_t j = 1; j <= u; j++) h_b[j] = h_c[j];
+    }
+    band *= 2;
+  } while (maxv < score);
+  band /= 2;
+
+  // trace back from the bottom-right corner while i > 0 (ssw.c:698-753); ops collected in reverse
+  int32_t i = readLen - 1, j = refLen - 1, e = 0, l = 0, f = 0, cur = 0, st = 2;
+  // pass 1 counts ops so that pass 2 can place them without a temporary list
+  for (int pass = 0; pass < 2; pass++) {
+    const int32_t total = l;
+    i = readLen - 1; j = refLen - 1; e = 0; l = 0; f = 0; cur = 0; st = 2;
+    while (i > 0) {
+      const int32_t lo = i - band > 0 ? i - band : 0, hi = i + band < refLen - 1 ? i + band : refLen - 1;
+      if (j < lo || j > hi) return -1;
+      const uint32_t cell = dir[((size_t)width_d * i + (size_t)(j - lo)) * dstride];
+      uint32_t code = st == 2 ? (cell >> 2) : (st == 0 ? ((cell & 1u) ? 3u : 2u) : ((cell & 2u) ? 5u : 4u));
+      switch (code) {
+        case 1: --i; --j; st = 2; f = 0; break;
+        case 2: --i; st = 0; f = 1; break;
+        case 3: --i; st = 2; f = 1; break;
+        case 4: --j; st = 1; f = 2; break;
+        case 5: --j; st = 2; f = 2; break;
+        default: return -1;
+      }
+      if (f == cur) ++e;
+      else {
+        ++l;
+        if (pass == 1) {      // op number l-1 in trace order; final cigar is the reverse of the trace order
+          const int32_t k = reverse_out ? l - 1 : total - l;
+          if (k >= 0 && (uint32_t)k < cig_cap) cig[k] = ((uint32_t)e << 4) | (uint32_t)cur;
+        }
+        cur = f; e = 1;
+      }
+    }
+    if (f == 0) {
+      ++l;
+      if (pass == 1) { const int32_t k = reverse_out ? l - 1 : total - l; if (k >= 0 && (uint32_t)k < cig_cap) cig[k] = (uint32_t)(e + 1) << 4; }
+    } else {
+      l += 2;
+      if (pass == 1) {
+        int32_t k = reverse_out ? l - 2 : total - (l - 1); if (k >= 0 && (uint32_t)k < cig_cap) cig[k] = ((uint32_t)e << 4) | (uint32_t)f;
+        k = reverse_out ? l - 1 : total - l; if (k >= 0 && (uint32_t)k < cig_cap) cig[k] = 16u;
+      }
+    }
+  }
+  if ((uint32_t)l > cig_cap) *overflow = 1;
+  return l;
+}
+
+// Finishes every alignment: cigar (if requested and score >= threshold, ssw.c:924-927), un-flip for
+// reverse-complement seeds and + refStart (SmithWaterman.h:212-229), and writes the kslam_overlap fields.
+// mode 0: first attempt with per-thread local arrays (band <= SW_TB_MAXBAND, rows <= SW_TB_MAXROWS); tasks that
+// need more are appended to retry_list. mode 1: retry path with global scratch (one thread per alignment).
+__global__ void __launch_bounds__(128)
+k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, uint32_t n, const uint32_t *list,
+               SwPlanes pl, SwScore sc, kslam_overlap *__restrict__ ov, uint32_t *__restrict__ cigs, int unflip,
+               int mode, uint32_t *__restrict__ retry_list, uint32_t *__restrict__ retry_count,
+               uint8_t *__restrict__ big, size_t big_per_thread) {
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  int32_t l_hb[SW_TB_MAXBAND * 2 + 3], l_eb[SW_TB_MAXBAND * 2 + 3], l_hc[SW_TB_MAXBAND * 2 + 3];
+  uint8_t l_dir[SW_TB_MAXROWS * (SW_TB_MAXBAND * 2 + 1)];
+  for (uint32_t k = gtid; k < n; k += nthreads) {
+    const uint32_t idx = list ? list[k] : k;
+    const SwTask t = tasks[idx];
+    const SwRes r = res[idx];
+    kslam_overlap o = ov[idx];
+    o.sw_score = (uint32_t)r.score & 0xffffu;
+    o.ref_begin = r.ref_begin; o.ref_end = r.ref_end; o.query_begin = r.read_begin; o.query_end = r.read_end;
+    o.cigar_len = 0; o.cigar_off = idx * sc.cigar_cap; o.flags = r.flags;
+    const bool rev = (t.flags & SWT_REV) != 0;
+    uint32_t *cig = cigs ? cigs + (size_t)idx * sc.cigar_cap : nullptr;
+    bool deferred = false;
+    if (sc.report_cigar && cig && (uint32_t)r.score >= sc.score_threshold && !(r.flags & KSLAM_FLAG_UNDEFINED)) {
+      if (r.score == 0) o.flags |= KSLAM_FLAG_UNDEFINED;      // the reference reads ref[-1] here
+      else {
+        const int32_t refLen = r.ref_end - r.ref_begin + 1, readLen = r.read_end - r.read_begin + 1;
+        uint32_t overflow = 0; int32_t len;
+        if (mode == 0)
+          len = banded_traceback(pl, t, sc, r.ref_begin, r.read_begin, refLen, readLen, r.score, l_hb, l_eb, l_hc,
+                                 SW_TB_MAXBAND * 2 + 3, l_dir, sizeof(l_dir), 1, cig, sc.cigar_cap, rev && unflip, &overflow);
+        else {
+          uint8_t *base = big + (size_t)gtid * big_per_thread;
+          const uint32_t arr_cap = (uint32_t)(big_per_thread / 64);   // ints per rolling array
+          int32_t *hb = reinterpret_cast<int32_t *>(base), *eb = hb + arr_cap, *hc = eb + arr_cap;
+          uint8_t *d = base + (size_t)arr_cap * 12;
+          len = banded_traceback(pl, t, sc, r.ref_begin, r.read_begin, refLen, readLen, r.score, hb, eb, hc, arr_cap, d,
+                                 big_per_thread - (size_t)arr_cap * 12, 1, cig, sc.cigar_cap, rev && unflip, &overflow);
+        }
+        if (len == -3) {
+          if (mode == 0) { deferred = true; retry_list[atomicAdd(retry_count, 1u)] = idx; }
+          else o.flags |= KSLAM_FLAG_UNDEFINED;   // beyond even the big scratch: report, never guess
+        } else if (len == -2) { o.cigar_len = 0; o.sw_score = 0; }           // ssw.c:941-944
+        else if (len == -1) o.flags |= KSLAM_FLAG_UNDEFINED;
+        else { o.cigar_len = (uint32_t)len < sc.cigar_cap ? (uint32_t)len : sc.cigar_cap; if (overflow) o.flags |= KSLAM_FLAG_CIGAR_OVERFLOW; }
+      }
+    }
+    if (deferred) continue;
+    if (unflip) {
+      if (rev) {     // SmithWaterman.h:212-227
+        const int32_t wl = (int32_t)t.n, ql = (int32_t)t.m;
+        int32_t tmp = o.ref_begin; o.ref_begin = wl - (o.ref_end + 1); o.ref_end = wl - (tmp + 1);
+        tmp = o.query_begin; o.query_begin = ql - (o.query_end + 1); o.query_end = ql - (tmp + 1);
+      }
+      o.ref_begin += (int32_t)t.w_start; o.ref_end += (int32_t)t.w_start;   // :228-229
+    }
+    ov[idx] = o;
+  }
+}
+
+// ---------------------------------------------------------------- task preparation and bucketing
+__device__ __forceinline__ uint32_t classify(uint32_t m, uint32_t n, const SwScore &sc) {
+  if (m == 0 || n == 0) return SWC_NONE;
+  const uint32_t mn = m < n ? m : n;
+  const bool score_ok = sc.match * 32 <= 127 && sc.mismatch * 32 <= 128 && (uint32_t)sc.match * mn <= 1000u &&
+                        sc.gap_open * 32 <= 30000 && sc.gap_extend * 32 <= 30000;
+  if (score_ok && m <= 8 * SW_R && n <= SW_MAXCOLS) return SWC_FAST8;
+  return SWC_SLOW;
+}
+
+// pipeline mode: one task per seed (SmithWaterman.h:199-211)
+__global__ void __launch_bounds__(256)
+k_sw_prepare_seeds(const kslam_seed *__restrict__ seeds, uint32_t n, const uint64_t *__restrict__ r_offs,
+                   const uint64_t *__restrict__ r_word, const uint64_t *__restrict__ g_offs,
+                   const uint64_t *__restrict__ g_word, SwScore sc, SwTask *__restrict__ tasks,
+                   Rec16 *__restrict__ keys, uint32_t *__restrict__ counts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const kslam_seed s = seeds[i];
+  const uint64_t qlen = r_offs[s.read + 1] - r_offs[s.read], glen = g_offs[s.entry + 1] - g_offs[s.entry];
+  const uint64_t start = s.rel > 0 ? (uint64_t)s.rel : 0;                     // :205
+  const uint64_t wlen = start >= glen ? 0 : (glen - start < qlen ? glen - start : qlen);   // substr clamp :206-207
+  SwTask t;
+  t.q_word = r_word[s.read]; t.w_word = g_word[s.entry];
+  t.m = (uint32_t)qlen; t.n = (uint32_t)wlen; t.w_start = (uint32_t)start;
+  const uint32_t cls = classify(t.m, t.n, sc);
+  t.flags = (s.rev_comp ? SWT_REV : 0u) | (cls << 8);
+  tasks[i] = t;
+  keys[i].key = ((uint64_t)cls << 32) | t.n; keys[i].val = i;
+  atomicAdd(&counts[cls], 1u);
+}
+
+// Aligner::Align batch mode: query i against ref i, whole sequences
+__global__ void __launch_bounds__(256)
+k_sw_prepare_pairs(uint32_t n, const uint64_t *__restrict__ q_offs, const uint64_t *__restrict__ q_word,
+                   const uint64_t *__restrict__ r_offs, const uint64_t *__restrict__ r_word, SwScore sc,
+                   SwTask *__restrict__ tasks, Rec16 *__restrict__ keys, uint32_t *__restrict__ counts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  SwTask t;
+  t.q_word = q_word[i]; t.w_word = r_word[i];
+  t.m = (uint32_t)(q_offs[i + 1] - q_offs[i]); t.n = (uint32_t)(r_offs[i + 1] - r_offs[i]); t.w_start = 0;
+  const uint32_t cls = classify(t.m, t.n, sc);
+  t.flags = cls << 8;
+  tasks[i] = t;
+  keys[i].key = ((uint64_t)cls << 32) | t.n; keys[i].val = i;
+  atomicAdd(&counts[cls], 1u);
+}
+
+// keys for the reverse pass: bucket by the number of columns it sweeps (ref_end + 1); alignments with
+// score 0 have no reverse pass (ssw.c:903 is reached with an empty range)
+__global__ void __launch_bounds__(256)
+k_sw_rev_keys(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, uint32_t n, Rec16 *__restrict__ keys,
+              uint32_t *__restrict__ counts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t cls = (tasks[i].flags >> 8) & 0xffu;
+  const bool run = cls == SWC_FAST8 && res[i].score > 0;
+  keys[i].key = run ? (uint64_t)(res[i].ref_end + 1) : (1ull << 40);
+  keys[i].val = i;
+  if (run) atomicAdd(&counts[8], 1u);
+}
+
+// sorted (by class, columns) task ids -> work items: two alignments with the same column count share a group;
+// an unequal neighbour pair becomes two single items (both halves run the same alignment)
+__global__ void __launch_bounds__(256)
+k_sw_make_items(const Rec16 *__restrict__ sorted, uint32_t n_fast, uint2 *__restrict__ items) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (2 * w >= n_fast) return;
+  const Rec16 a = sorted[2 * w];
+  uint2 i0 = make_uint2((uint32_t)a.val, (uint32_t)a.val), i1 = make_uint2(SW_INVALID, SW_INVALID);
+  if (2 * w + 1 < n_fast) {
+    const Rec16 b = sorted[2 * w + 1];
+    if (b.key == a.key) i0.y = (uint32_t)b.val; else i1 = make_uint2((uint32_t)b.val, (uint32_t)b.val);
+  }
+  items[2 * w] = i0; items[2 * w + 1] = i1;
+}
+
+__global__ void __launch_bounds__(256)
+k_sw_list(const Rec16 *__restrict__ sorted, uint32_t first, uint32_t count, uint32_t *__restrict__ list) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) list[i] = (uint32_t)sorted[first + i].val;
+}
+
+__global__ void __launch_bounds__(256)
+k_sw_none(const SwTask *__restrict__ tasks, uint32_t n, SwRes *__restrict__ res) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (((tasks[i].flags >> 8) & 0xffu) == SWC_NONE) {
+    SwRes o; o.score = 0; o.ref_end = -1; o.read_end = 0; o.ref_begin = -1; o.read_begin = 0; o.flags = 0; o.pad0 = o.pad1 = 0;
+    res[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_sw_cells(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, uint32_t n, unsigned long long *out) {
+  unsigned long long fw = 0, rv = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    fw += (unsigned long long)tasks[i].m * tasks[i].n;
+    if (res[i].score > 0) rv += (unsigned long long)(res[i].read_end + 1) * (unsigned long long)(res[i].ref_end + 1);
+  }
+  for (int d = 16; d; d >>= 1) { fw += __shfl_xor_sync(0xffffffffu, fw, d); rv += __shfl_xor_sync(0xffffffffu, rv, d); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, fw); atomicAdd(out + 1, rv); }
+}
+
+// ---------------------------------------------------------------- host orchestration
+static SwScore make_score(const kslam_ctx *c) {
+  SwScore s;
+  s.match = c->prm.match; s.mismatch = c->prm.mismatch; s.gap_open = c->prm.gap_open; s.gap_extend = c->prm.gap_extend;
+  s.score_threshold = c->prm.score_threshold; s.report_cigar = c->prm.report_cigar; s.cigar_cap = c->prm.max_cigar_ops;
+  return s;
+}
+
+static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *ov, uint32_t *cig, int unflip) {
+  SwWorkspace *w = c->sw;
+  cudaStream_t st = c->stream;
+  const SwScore sc = make_score(c);
+  SwTask *tasks = w->tasks.as<SwTask>();
+  SwRes *res = w->res.as<SwRes>();
+  Rec16 *keys = w->keys.as<Rec16>(), *keys2 = w->keys2.as<Rec16>();
+  uint32_t *d_counts = c->counters.as<uint32_t>() + 32;      // 16 u32 counters
+  uint32_t *h_counts = c->h_counters.as<uint32_t>() + 32;
+  const unsigned nb = (n + 255) / 256;
+
+  cudaEvent_t e0 = tm_mark(c);
+  CUDA_TRY(cudaMemcpyAsync(h_counts, d_counts, 64, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const uint32_t n_fast = h_counts[SWC_FAST8], n_slow = h_counts[SWC_SLOW];
+  c->tm.n_sw_fast = n_fast; c->tm.n_sw_slow = n_slow;
+  // bucket by (class, columns): class is the high word so fast tasks come first
+  uint64_t passes = 0;
+  Rec16 *sorted = radix_sort(c, keys, keys2, n, 0, 0, 40, &passes);
+  Rec16 *other = sorted == keys ? keys2 : keys;
+  k_sw_none<<<nb, 256, 0, st>>>(tasks, n, res);
+  c->launches++;
+  cudaEvent_t e1 = tm_mark(c);
+  uint2 *items = w->items.as<uint2>();
+  if (n_fast) {
+    const uint32_t n_items = 2 * ((n_fast + 1) / 2);
+    k_sw_make_items<<<(n_items / 2 + 255) / 256, 256, 0, st>>>(sorted, n_fast, items);
+    constexpr int GROUPS = SW_BLOCK / 8;
+    k_sw_fast<8, false><<<(n_items + GROUPS - 1) / GROUPS, SW_BLOCK, 0, st>>>(tasks, items, n_items, pl, sc, res);
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+  }
+  cudaEvent_t e2 = tm_mark(c);
+  if (n_fast) {
+    CUDA_TRY(cudaMemsetAsync(d_counts + 8, 0, 4, st));
+    k_sw_rev_keys<<<nb, 256, 0, st>>>(tasks, res, n, other, d_counts);
+    c->launches++;
+    CUDA_TRY(cudaMemcpyAsync(h_counts + 8, d_counts + 8, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const uint32_t n_rev = h_counts[8];
+    // `sorted` (forward buckets) is still needed for the slow list: sort the reverse keys in a third buffer pair
+    w->items.reserve((size_t)(2 * ((n + 1) / 2)) * sizeof(uint2) + (size_t)n * sizeof(Rec16) + 64);
+    items = w->items.as<uint2>();
+    Rec16 *tmp = reinterpret_cast<Rec16 *>(reinterpret_cast<char *>(items) + (size_t)(2 * ((n + 1) / 2)) * sizeof(uint2));
+    Rec16 *rs = radix_sort(c, other, tmp, n, 0, 0, 41, &passes);
+    if (n_rev) {
+      const uint32_t n_items = 2 * ((n_rev + 1) / 2);
+      k_sw_make_items<<<(n_items / 2 + 255) / 256, 256, 0, st>>>(rs, n_rev, items);
+      constexpr int GROUPS = SW_BLOCK / 8;
+      k_sw_fast<8, true><<<(n_items + GROUPS - 1) / GROUPS, SW_BLOCK, 0, st>>>(tasks, items, n_items, pl, sc, res);
+      c->launches += 2;
+      CUDA_TRY(cudaGetLastError());
+    }
+  }
+  cudaEvent_t e3 = tm_mark(c);
+  if (n_slow) {
+    uint32_t *list = reinterpret_cast<uint32_t *>(w->items.p);
+    k_sw_list<<<(n_slow + 255) / 256, 256, 0, st>>>(sorted, n_fast, n_slow, list);
+    uint32_t max_rows = c->reads_loaded ? c->reads.max_len : 0;
+    if (c->sw_loaded && c->swq.max_len > max_rows) max_rows = c->swq.max_len;
+    uint32_t blocks = (n_slow + 127) / 128; if (blocks > (uint32_t)c->num_sms * 4) blocks = c->num_sms * 4;
+    w->tb_scratch.reserve((size_t)blocks * 128 * max_rows * 8 + 64);
+    k_sw_slow<<<blocks, 128, 0, st>>>(tasks, list, n_slow, pl, sc, res, w->tb_scratch.as<int32_t>(), max_rows);
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+  }
+  cudaEvent_t e4 = tm_mark(c);
+  {
+    // traceback + finalize
+    uint32_t *retry_count = d_counts + 9;
+    CUDA_TRY(cudaMemsetAsync(retry_count, 0, 4, st));
+    uint32_t *retry_list = reinterpret_cast<uint32_t *>(w->keys.p);   // keys are dead by now
+    uint32_t blocks = (n + 127) / 128;
+    k_sw_traceback<<<blocks, 128, 0, st>>>(tasks, res, n, nullptr, pl, sc, ov, cig, unflip, 0, retry_list, retry_count, nullptr, 0);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h_counts + 9, retry_count, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const uint32_t n_retry = h_counts[9];
+    if (n_retry) {
+      // big-scratch path: up to 1 MiB per thread covers band 512 x 640 rows; few threads
+      const size_t per_thread = 1u << 20;
+      uint32_t threads = n_retry < 2048 ? n_retry : 2048;
+      uint32_t rblocks = (threads + 127) / 128;
+      w->tb_scratch.reserve((size_t)rblocks * 128 * per_thread);
+      k_sw_traceback<<<rblocks, 128, 0, st>>>(tasks, res, n_retry, retry_list, pl, sc, ov, cig, unflip, 1, nullptr, nullptr,
+                                               w->tb_scratch.as<uint8_t>(), per_thread);
+      c->launches++;
+      CUDA_TRY(cudaGetLastError());
+    }
+  }
+  cudaEvent_t e5 = tm_mark(c);
+  unsigned long long *d_cells = c->counters.as<unsigned long long>() + 8;
+  CUDA_TRY(cudaMemsetAsync(d_cells, 0, 16, st));
+  k_sw_cells<<<c->num_sms * 2, 256, 0, st>>>(tasks, res, n, d_cells);
+  c->launches++;
+  unsigned long long *h_cells = c->h_counters.as<unsigned long long>() + 8;
+  CUDA_TRY(cudaMemcpyAsync(h_cells, d_cells, 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  c->tm.sw_cells_forward = h_cells[0]; c->tm.sw_cells_reverse = h_cells[1];
+  c->tm.ms_sw_prepare += tm_ms(e0, e1);
+  c->tm.ms_sw_forward = tm_ms(e1, e2);
+  c->tm.ms_sw_reverse = tm_ms(e2, e3);
+  c->tm.ms_sw_slow = tm_ms(e3, e4);
+  c->tm.ms_sw_traceback = tm_ms(e4, e5);
+}
+
+static void sw_reserve(kslam_ctx *c, uint32_t n) {
+  if (!c->sw) c->sw = new SwWorkspace();
+  SwWorkspace *w = c->sw;
+  w->tasks.reserve((size_t)n * sizeof(SwTask) + 64);
+  w->res.reserve((size_t)n * sizeof(SwRes) + 64);
+  w->keys.reserve((size_t)n * sizeof(Rec16) + 64);
+  w->keys2.reserve((size_t)n * sizeof(Rec16) + 64);
+  w->items.reserve((size_t)(2 * ((n + 1) / 2)) * sizeof(uint2) + (size_t)n * sizeof(Rec16) + 64);
+  c->counters.reserve(64 * 8); c->h_counters.reserve(64 * 8);
+  w->n = n;
+}
+
+void sw_align_seeds(kslam_ctx *c) {
+  const uint32_t n = (uint32_t)c->n_seeds;
+  c->tm.ms_sw_prepare = c->tm.ms_sw_forward = c->tm.ms_sw_reverse = c->tm.ms_sw_slow = c->tm.ms_sw_traceback = 0;
+  c->tm.sw_cells_forward = c->tm.sw_cells_reverse = 0; c->tm.n_sw_fast = c->tm.n_sw_slow = 0;
+  if (!n) return;
+  sw_reserve(c, n);
+  cudaStream_t st = c->stream;
+  const uint32_t cap = c->prm.max_cigar_ops;
+  if (c->prm.report_cigar) c->cig.reserve((size_t)n * cap * 4 + 64);
+  uint32_t *d_counts = c->counters.as<uint32_t>() + 32;
+  cudaEvent_t e0 = tm_mark(c);
+  CUDA_TRY(cudaMemsetAsync(d_counts, 0, 64, st));
+  k_sw_prepare_seeds<<<(n + 255) / 256, 256, 0, st>>>(c->seeds.as<kslam_seed>(), n, c->reads.offs.as<uint64_t>(),
+      c->reads.word_off.as<uint64_t>(), c->genomes.offs.as<uint64_t>(), c->genomes.word_off.as<uint64_t>(),
+      make_score(c), c->sw->tasks.as<SwTask>(), c->sw->keys.as<Rec16>(), d_counts);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  cudaEvent_t e1 = tm_mark(c);
+  SwPlanes pl{c->reads.sbits.as<uint64_t>(), c->reads.nmask.as<uint32_t>(), c->genomes.sbits.as<uint64_t>(),
+              c->genomes.nmask.as<uint32_t>(), c->genomes.xmask.as<uint32_t>()};
+  sw_run(c, n, pl, c->ov.as<kslam_overlap>(), c->prm.report_cigar ? c->cig.as<uint32_t>() : nullptr, 1);
+  c->tm.ms_sw_prepare += tm_ms(e0, e1);
+}
+
+void sw_align_pairs(kslam_ctx *c, uint64_t n64, kslam_overlap *out_dev, uint32_t *cig_dev) {
+  const uint32_t n = (uint32_t)n64;
+  c->tm.ms_sw_prepare = c->tm.ms_sw_forward = c->tm.ms_sw_reverse = c->tm.ms_sw_slow = c->tm.ms_sw_traceback = 0;
+  c->tm.sw_cells_forward = c->tm.sw_cells_reverse = 0; c->tm.n_sw_fast = c->tm.n_sw_slow = 0;
+  if (!n) return;
+  sw_reserve(c, n);
+  cudaStream_t st = c->stream;
+  uint32_t *d_counts = c->counters.as<uint32_t>() + 32;
+  cudaEvent_t e0 = tm_mark(c);
+  CUDA_TRY(cudaMemsetAsync(d_counts, 0, 64, st));
+  CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)n * sizeof(kslam_overlap), st));
+  k_sw_prepare_pairs<<<(n + 255) / 256, 256, 0, st>>>(n, c->swq.offs.as<uint64_t>(), c->swq.word_off.as<uint64_t>(),
+      c->swr.offs.as<uint64_t>(), c->swr.word_off.as<uint64_t>(), make_score(c), c->sw->tasks.as<SwTask>(),
+      c->sw->keys.as<Rec16>(), d_counts);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  cudaEvent_t e1 = tm_mark(c);
+  SwPlanes pl{c->swq.sbits.as<uint64_t>(), c->swq.nmask.as<uint32_t>(), c->swr.sbits.as<uint64_t>(),
+              c->swr.nmask.as<uint32_t>(), c->swr.xmask.as<uint32_t>()};
+  sw_run(c, n, pl, out_dev, cig_dev, 0);
+  c->tm.ms_sw_prepare += tm_ms(e0, e1);
+}
+
+void sw_workspace_free(kslam_ctx *c) {
+  if (!c->sw) return;
+  c->sw->tasks.release(); c->sw->res.release(); c->sw->keys.release(); c->sw->keys2.release();
+  c->sw->items.release(); c->sw->tb_scratch.release();
+  delete c->sw; c->sw = nullptr;
+}

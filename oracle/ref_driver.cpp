@@ -1,0 +1,242 @@
+// oracle/_ref harness — TEST INFRASTRUCTURE ONLY (never linked into the product).
+//
+// This translation unit is OUR code. It #includes the reference's headers where they
+// lie under /root/reference/src (nothing is copied into this repo) and exposes the
+// reference's own matching path through a small C interface so that tests and the
+// CPU-baseline leg of bench.py can run the UNMODIFIED reference implementation:
+//
+//   getKMersFromReads            /root/reference/src/KMer.h:373-381
+//   GenbankIndex::getKMers       /root/reference/src/GenbankTools.h:211-219
+//   sortKMers                    /root/reference/src/KMer.h:388-398
+//   findOverlaps[_parallel]      /root/reference/src/Overlap.h:230-246,277-295
+//   alignToDatabase              /root/reference/src/SLAM.h:60-79
+//   screenOverlapsByScoreThreshold /root/reference/src/Overlap.h:329-341
+//   getPairedOverlaps            /root/reference/src/PairedOverlap.h:243-272
+//   StripedSmithWaterman::Aligner::Align  /root/reference/src/ssw_cpp.cpp:234-283
+//
+// Built by oracle/Makefile into oracle/_ref/libkslam_ref.so (git-ignored, travels to the
+// GPU box as a prebuilt binary). Boost is absent from this image; oracle/ref_shim/
+// holds six no-op stand-in headers so the reference headers compile.
+// The reference headers rely on transitive includes (normally via Boost); pre-include them.
+#include <vector>
+#include <string>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <algorithm>
+#include <stdexcept>
+#include <limits>
+#include <memory>
+#include <set>
+#include <climits>
+#include <cmath>
+#include <numeric>
+#include <unordered_map>
+#include <array>
+#include <map>
+#include <tuple>
+#include <cstring>
+#include <cstdint>
+#include <omp.h>
+#include "SLAM.h"
+
+using namespace SLAM;
+
+namespace {
+
+typedef KMerAndData<KMerInt, k> KM;
+
+struct KrefCtx {
+  GenbankIndex idx;
+  std::vector<MetagenomicFASTQSequence> reads;
+  std::vector<KM> kmers;
+  std::vector<OverlapTemp> seeds;
+  std::vector<Overlap> overlaps;
+  std::vector<PairedOverlap> pairs;
+};
+
+// Records shared with oracle/kslam_oracle.h and include/kslam.h (same layout).
+struct KmerRec { uint64_t kmer; uint32_t id_flags; uint32_t offset; };
+struct SeedRec { uint32_t read; uint32_t entry; int32_t rel; uint32_t rev_comp; };
+struct OverlapRec {
+  uint32_t read, entry; int32_t rel; uint32_t rev_comp;
+  int32_t ref_begin, ref_end, query_begin, query_end;
+  uint32_t sw_score, cigar_off, cigar_len, pad;
+};
+struct PairRec {
+  uint32_t combined_score, entry; int32_t ref_start, ref_end;
+  uint32_t insert_size; int32_t r1_idx, r2_idx; uint32_t pad;
+};
+
+void fill_overlap(OverlapRec &o, const Overlap &v, uint32_t cigar_off) {
+  o.read = v.readPosInArray; o.entry = v.entryPosInArray; o.rel = v.relativePosition;
+  o.rev_comp = v.revComp;
+  o.ref_begin = v.alignment.ref_begin; o.ref_end = v.alignment.ref_end;
+  o.query_begin = v.alignment.query_begin; o.query_end = v.alignment.query_end;
+  o.sw_score = v.alignment.sw_score; o.cigar_off = cigar_off;
+  o.cigar_len = v.alignment.cigar ? (uint32_t)v.alignment.cigarLen : 0; o.pad = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void *kref_create() { forceParallel(); return new KrefCtx(); }
+void kref_destroy(void *h) { delete (KrefCtx *)h; }
+int kref_num_threads() { return omp_get_max_threads(); }
+
+// Globals.h:27-42 — main.cpp:36-58 normally fills these.
+void kref_set_params(uint32_t m, uint32_t x, uint32_t go, uint32_t ge, uint32_t thr,
+                     int report_cigar) {
+  match = m; misMatch = x; gapOpen = go; gapExtend = ge; scoreThreshold = thr;
+  reportCigar = report_cigar != 0;
+}
+
+void kref_set_genomes(void *h, uint64_t n, const char *bases, const uint64_t *offs) {
+  KrefCtx *c = (KrefCtx *)h;
+  c->idx.entries.clear();
+  c->idx.entries.resize(n);
+  for (uint64_t i = 0; i < n; i++) {
+    c->idx.entries[i].bases.assign(bases + offs[i], bases + offs[i + 1]);
+    c->idx.entries[i].locusTag = "g" + std::to_string(i);
+  }
+}
+
+void kref_set_reads(void *h, uint64_t n, const char *bases, const uint64_t *offs) {
+  KrefCtx *c = (KrefCtx *)h;
+  c->reads.clear();
+  c->reads.reserve(n);
+  for (uint64_t i = 0; i < n; i++) {
+    std::string b(bases + offs[i], bases + offs[i + 1]);
+    std::string q(b.size(), 'I');
+    c->reads.emplace_back("@r" + std::to_string(i), b, q);
+  }
+}
+
+// which: 1 = reads only, 2 = genomes only (gap k/2), 3 = both, in alignToDatabase order.
+uint64_t kref_extract_kmers(void *h, int which) {
+  KrefCtx *c = (KrefCtx *)h;
+  c->kmers.clear();
+  if (which & 1) getKMersFromReads(c->reads, c->kmers);
+  if (which & 2) c->idx.getKMers<KMerInt, k>(c->kmers, k / 2);
+  return c->kmers.size();
+}
+void kref_sort_kmers(void *h) { sortKMers(((KrefCtx *)h)->kmers); }
+void kref_get_kmers(void *h, void *out) {
+  KrefCtx *c = (KrefCtx *)h;
+  KmerRec *o = (KmerRec *)out;
+  for (size_t i = 0; i < c->kmers.size(); i++) {
+    o[i].kmer = c->kmers[i].kMerInt;
+    o[i].id_flags = c->kmers[i].kMerData.ID_isFromGB_RC;
+    o[i].offset = c->kmers[i].kMerData.offset;
+  }
+}
+
+// Raw pile walk over the whole sorted list as one chunk (Overlap.h:230-246).
+uint64_t kref_find_seeds_raw(void *h) {
+  KrefCtx *c = (KrefCtx *)h;
+  // findOverlaps may peek at *last (Overlap.h:243); keep one spare element past the end.
+  c->kmers.reserve(c->kmers.size() + 1);
+  c->seeds = findOverlaps(c->kmers.begin(), c->kmers.end(), c->reads);
+  return c->seeds.size();
+}
+// Chunked walk + sort + fuzzy unique (Overlap.h:277-295).
+uint64_t kref_find_seeds(void *h) {
+  KrefCtx *c = (KrefCtx *)h;
+  c->kmers.reserve(c->kmers.size() + 1);
+  c->seeds = findOverlaps_parallel(c->kmers.begin(), c->kmers.end(), c->reads);
+  return c->seeds.size();
+}
+void kref_get_seeds(void *h, void *out) {
+  KrefCtx *c = (KrefCtx *)h;
+  SeedRec *o = (SeedRec *)out;
+  for (size_t i = 0; i < c->seeds.size(); i++) {
+    o[i].read = c->seeds[i].readPosInArray; o[i].entry = c->seeds[i].entryPosInArray;
+    o[i].rel = c->seeds[i].relativePosition; o[i].rev_comp = c->seeds[i].revComp;
+  }
+}
+
+uint64_t kref_align_to_database(void *h) {
+  KrefCtx *c = (KrefCtx *)h;
+  c->overlaps = alignToDatabase(c->reads, c->idx);
+  return c->overlaps.size();
+}
+uint64_t kref_screen(void *h) {
+  KrefCtx *c = (KrefCtx *)h;
+  screenOverlapsByScoreThreshold(c->overlaps, scoreThreshold);
+  return c->overlaps.size();
+}
+uint64_t kref_num_overlaps(void *h) { return ((KrefCtx *)h)->overlaps.size(); }
+uint64_t kref_cigar_total(void *h) {
+  KrefCtx *c = (KrefCtx *)h;
+  uint64_t t = 0;
+  for (auto &o : c->overlaps) if (o.alignment.cigar) t += o.alignment.cigarLen;
+  return t;
+}
+void kref_get_overlaps(void *h, void *out, uint32_t *cigar_pool) {
+  KrefCtx *c = (KrefCtx *)h;
+  OverlapRec *o = (OverlapRec *)out;
+  uint32_t off = 0;
+  for (size_t i = 0; i < c->overlaps.size(); i++) {
+    fill_overlap(o[i], c->overlaps[i], off);
+    for (uint32_t j = 0; j < o[i].cigar_len; j++) cigar_pool[off + j] = c->overlaps[i].alignment.cigar[j];
+    off += o[i].cigar_len;
+  }
+}
+
+// getPairedOverlaps sorts c->overlaps in place; r1_idx/r2_idx index that sorted order.
+uint64_t kref_pair(void *h) {
+  KrefCtx *c = (KrefCtx *)h;
+  c->pairs = getPairedOverlaps(c->overlaps.begin(), c->overlaps.end(), c->reads);
+  return c->pairs.size();
+}
+void kref_get_pairs(void *h, void *out) {
+  KrefCtx *c = (KrefCtx *)h;
+  PairRec *o = (PairRec *)out;
+  std::map<std::tuple<uint32_t, uint32_t, int32_t>, int32_t> where;
+  for (size_t i = 0; i < c->overlaps.size(); i++)
+    where[std::make_tuple(c->overlaps[i].readPosInArray, c->overlaps[i].entryPosInArray,
+                          c->overlaps[i].relativePosition)] = (int32_t)i;
+  for (size_t i = 0; i < c->pairs.size(); i++) {
+    const PairedOverlap &p = c->pairs[i];
+    o[i].combined_score = p.combinedScore; o[i].entry = p.entryPosInArray;
+    o[i].ref_start = p.refStart; o[i].ref_end = p.refEnd; o[i].insert_size = p.insertSize;
+    o[i].r1_idx = p.hasR1 ? where[std::make_tuple(p.r1Overlap.readPosInArray, p.r1Overlap.entryPosInArray,
+                                                  p.r1Overlap.relativePosition)] : -1;
+    o[i].r2_idx = p.hasR2 ? where[std::make_tuple(p.r2Overlap.readPosInArray, p.r2Overlap.entryPosInArray,
+                                                  p.r2Overlap.relativePosition)] : -1;
+    o[i].pad = 0;
+  }
+}
+
+// Direct batched Aligner::Align (ssw_cpp.cpp:234-283) over n (query, ref) pairs, all host
+// threads. Output coordinates are SSW's own (no un-flip, no refStart offset). cigar_pool
+// has cigar_cap u32 per alignment. Returns number of alignments.
+uint64_t kref_ssw_batch(uint64_t n, const char *q, const uint64_t *qoffs, const char *r,
+                        const uint64_t *roffs, int report_cigar, uint32_t score_filter,
+                        void *out, uint32_t *cigar_pool, uint32_t cigar_cap, int threads) {
+  OverlapRec *o = (OverlapRec *)out;
+  if (threads <= 0) threads = omp_get_max_threads();
+#pragma omp parallel num_threads(threads)
+  {
+    const StripedSmithWaterman::Aligner aligner(match, misMatch, gapOpen, gapExtend);
+    StripedSmithWaterman::Filter filter;
+    filter.report_begin_position = true;
+    filter.report_cigar = report_cigar != 0;
+    filter.score_filter = score_filter;
+#pragma omp for schedule(dynamic, 256)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+      std::string qs(q + qoffs[i], q + qoffs[i + 1]);
+      std::string rs(r + roffs[i], r + roffs[i + 1]);
+      Overlap ov;
+      aligner.Align(qs.c_str(), rs.c_str(), (int)rs.size(), filter, &ov.alignment);
+      fill_overlap(o[i], ov, (uint32_t)(i * cigar_cap));
+      if (o[i].cigar_len > cigar_cap) o[i].cigar_len = cigar_cap | 0x80000000u;
+      for (uint32_t j = 0; j < (o[i].cigar_len & 0x7fffffffu) && j < cigar_cap; j++)
+        cigar_pool[i * (uint64_t)cigar_cap + j] = ov.alignment.cigar[j];
+    }
+  }
+  return n;
+}
+
+}  // extern "C"

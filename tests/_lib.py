@@ -1,0 +1,290 @@
+"""ctypes bindings for the CHECKERS (oracle/ and oracle/_ref) and shared test helpers.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module: the product path (k-slam_b200/) never touches oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+KMER_DT = np.dtype([("kmer", "<u8"), ("id_flags", "<u4"), ("offset", "<u4")])
+SEED_DT = np.dtype([("read", "<u4"), ("entry", "<u4"), ("rel", "<i4"), ("rev_comp", "<u4")])
+OVERLAP_DT = np.dtype([("read", "<u4"), ("entry", "<u4"), ("rel", "<i4"), ("rev_comp", "<u4"),
+                       ("ref_begin", "<i4"), ("ref_end", "<i4"), ("query_begin", "<i4"), ("query_end", "<i4"),
+                       ("sw_score", "<u4"), ("cigar_off", "<u4"), ("cigar_len", "<u4"), ("flags", "<u4")])
+PAIR_DT = np.dtype([("combined_score", "<u4"), ("entry", "<u4"), ("ref_start", "<i4"), ("ref_end", "<i4"),
+                    ("insert_size", "<u4"), ("r1_idx", "<i4"), ("r2_idx", "<i4"), ("pad", "<u4")])
+assert KMER_DT.itemsize == 16 and SEED_DT.itemsize == 16 and OVERLAP_DT.itemsize == 48 and PAIR_DT.itemsize == 32
+
+
+class KoParams(C.Structure):
+    _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open", C.c_int32),
+                ("gap_extend", C.c_int32), ("score_threshold", C.c_uint32), ("report_cigar", C.c_int32)]
+
+
+def default_params(report_cigar=1, score_threshold=0, match=2, mismatch=3, gap_open=5, gap_extend=2):
+    return KoParams(match, mismatch, gap_open, gap_extend, score_threshold, report_cigar)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def u8(a):
+    return np.ascontiguousarray(np.frombuffer(a, dtype=np.uint8) if isinstance(a, (bytes, bytearray)) else a, dtype=np.uint8)
+
+
+def offsets_of(seqs):
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(s) for s in seqs])
+    return offs
+
+
+def concat(seqs):
+    if not seqs:
+        return np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64)
+    return np.concatenate([u8(s) for s in seqs]) if sum(len(s) for s in seqs) else np.zeros(0, np.uint8), offsets_of(seqs)
+
+
+def build_oracle():
+    """Compile oracle/libkslam_oracle.so (and oracle/_ref when /root/reference exists)."""
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR, "all"], check=True, stdout=subprocess.DEVNULL)
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ORACLE_DIR, "libkslam_oracle.so")
+        if not os.path.exists(path):
+            build_oracle()
+        L = C.CDLL(path)
+        L.ko_extract_kmers.restype = C.c_uint64
+        L.ko_extract_kmers.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_void_p]
+        L.ko_sort_kmers.argtypes = [C.c_void_p, C.c_uint64]
+        L.ko_find_seeds_raw.restype = C.c_uint64
+        L.ko_find_seeds_raw.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.ko_sort_unique_seeds.restype = C.c_uint64
+        L.ko_sort_unique_seeds.argtypes = [C.c_void_p, C.c_uint64]
+        L.ko_ssw_batch.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.POINTER(KoParams), C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
+        L.ko_align_seeds.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.POINTER(KoParams), C.c_void_p, C.c_uint32, C.c_int]
+        L.ko_sort_for_pairing.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+        L.ko_pair_overlaps.restype = C.c_uint64
+        L.ko_pair_overlaps.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
+        _oracle = L
+    return _oracle
+
+
+def have_ref():
+    return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libkslam_ref.so"))
+
+
+def ref():
+    """The reference's own code (oracle/_ref/libkslam_ref.so). It writes log.txt into the CWD
+    (sequenceTools.h:176), so the first call happens inside a scratch directory."""
+    global _ref
+    if _ref is None:
+        L = C.CDLL(os.path.join(ORACLE_DIR, "_ref", "libkslam_ref.so"))
+        L.kref_create.restype = C.c_void_p
+        for name in ("kref_extract_kmers", "kref_find_seeds_raw", "kref_find_seeds", "kref_align_to_database",
+                     "kref_screen", "kref_num_overlaps", "kref_cigar_total", "kref_pair", "kref_ssw_batch"):
+            getattr(L, name).restype = C.c_uint64
+        L.kref_destroy.argtypes = [C.c_void_p]
+        L.kref_set_params.argtypes = [C.c_uint32] * 5 + [C.c_int]
+        L.kref_set_genomes.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.kref_set_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.kref_extract_kmers.argtypes = [C.c_void_p, C.c_int]
+        for name in ("kref_sort_kmers", "kref_find_seeds_raw", "kref_find_seeds", "kref_align_to_database",
+                     "kref_screen", "kref_num_overlaps", "kref_cigar_total", "kref_pair"):
+            getattr(L, name).argtypes = [C.c_void_p]
+        for name in ("kref_get_kmers", "kref_get_seeds", "kref_get_pairs"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_void_p]
+        L.kref_get_overlaps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kref_ssw_batch.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
+        cwd = os.getcwd()
+        scratch = tempfile.mkdtemp(prefix="kref_")
+        os.chdir(scratch)
+        try:
+            h = L.kref_create()
+            L.kref_set_params(2, 3, 5, 2, 0, 0)
+            z = np.zeros(1, dtype=np.uint64)
+            L.kref_set_reads(h, 0, None, _p(z))
+            L.kref_extract_kmers(h, 1)  # first log() call opens log.txt here
+            L.kref_destroy(h)
+        finally:
+            os.chdir(cwd)
+        _ref = L
+    return _ref
+
+
+# ---------------------------------------------------------------- oracle wrappers
+
+def ko_extract(bases, offs, is_gb, gap):
+    L = oracle()
+    bases = u8(bases); offs = np.ascontiguousarray(offs, dtype=np.uint64)
+    n = len(offs) - 1
+    cnt = L.ko_extract_kmers(n, _p(bases), _p(offs), int(is_gb), gap, None)
+    out = np.zeros(cnt, dtype=KMER_DT)
+    L.ko_extract_kmers(n, _p(bases), _p(offs), int(is_gb), gap, _p(out))
+    return out
+
+
+def ko_sort_kmers(recs):
+    recs = recs.copy()
+    oracle().ko_sort_kmers(_p(recs), len(recs))
+    return recs
+
+
+def ko_seeds_raw(sorted_recs, read_lens):
+    L = oracle()
+    read_lens = np.ascontiguousarray(read_lens, dtype=np.uint32)
+    cnt = L.ko_find_seeds_raw(_p(sorted_recs), len(sorted_recs), _p(read_lens), None)
+    out = np.zeros(cnt, dtype=SEED_DT)
+    L.ko_find_seeds_raw(_p(sorted_recs), len(sorted_recs), _p(read_lens), _p(out))
+    return out
+
+
+def ko_sort_unique(seeds):
+    seeds = seeds.copy()
+    n = oracle().ko_sort_unique_seeds(_p(seeds), len(seeds))
+    return seeds[:n].copy()
+
+
+def ko_ssw_batch(q, qoffs, r, roffs, params, cigar_cap=64, threads=8):
+    L = oracle()
+    q = u8(q); r = u8(r)
+    qoffs = np.ascontiguousarray(qoffs, dtype=np.uint64); roffs = np.ascontiguousarray(roffs, dtype=np.uint64)
+    n = len(qoffs) - 1
+    out = np.zeros(n, dtype=OVERLAP_DT)
+    pool = np.zeros(n * cigar_cap, dtype=np.uint32)
+    L.ko_ssw_batch(n, _p(q), _p(qoffs), _p(r), _p(roffs), C.byref(params), _p(out), _p(pool), cigar_cap, threads)
+    return out, pool
+
+
+def ko_pipeline(gen_bases, gen_offs, read_bases, read_offs, params, cigar_cap=64, threads=8, paired=True):
+    """Oracle restatement of alignToDatabase (+ screen + getPairedOverlaps). Returns a dict of every stage."""
+    L = oracle()
+    gen_bases = u8(gen_bases); read_bases = u8(read_bases)
+    gen_offs = np.ascontiguousarray(gen_offs, dtype=np.uint64); read_offs = np.ascontiguousarray(read_offs, dtype=np.uint64)
+    read_lens = (read_offs[1:] - read_offs[:-1]).astype(np.uint32)
+    rk = ko_extract(read_bases, read_offs, False, 1)
+    gk = ko_extract(gen_bases, gen_offs, True, 16)
+    allk = ko_sort_kmers(np.concatenate([rk, gk]))
+    raw = ko_seeds_raw(allk, read_lens)
+    seeds = ko_sort_unique(raw)
+    ov = np.zeros(len(seeds), dtype=OVERLAP_DT)
+    for f in ("read", "entry", "rel", "rev_comp"):
+        ov[f] = seeds[f]
+    pool = np.zeros(max(1, len(ov) * cigar_cap), dtype=np.uint32)
+    L.ko_align_seeds(len(ov), _p(ov), _p(read_bases), _p(read_offs), _p(gen_bases), _p(gen_offs),
+                     C.byref(params), _p(pool), cigar_cap, threads)
+    res = dict(read_kmers=rk, genome_kmers=gk, sorted_kmers=allk, raw_seeds=raw, seeds=seeds,
+               overlaps=ov, cigar_pool=pool, cigar_cap=cigar_cap)
+    if paired:
+        mid = (len(read_offs) - 1) // 2
+        kept = ov[ov["sw_score"] >= params.score_threshold].copy()  # Overlap.h:329-341
+        L.ko_sort_for_pairing(_p(kept), len(kept), mid)
+        cnt = L.ko_pair_overlaps(_p(kept), len(kept), mid, _p(read_lens), None)
+        pairs = np.zeros(cnt, dtype=PAIR_DT)
+        L.ko_pair_overlaps(_p(kept), len(kept), mid, _p(read_lens), _p(pairs))
+        res.update(pair_sorted_overlaps=kept, pairs=pairs)
+    return res
+
+
+def cigars_of(ov, pool):
+    """List of tuples of cigar words per overlap (pool indexed by cigar_off)."""
+    return [tuple(pool[o["cigar_off"]:o["cigar_off"] + o["cigar_len"]].tolist()) for o in ov]
+
+
+# ---------------------------------------------------------------- reference (_ref) wrappers
+
+class Ref:
+    """One reference context (GenbankIndex + reads) driving the reference's own functions."""
+
+    def __init__(self, gen_bases, gen_offs, read_bases, read_offs, params):
+        self.L = ref()
+        self.h = self.L.kref_create()
+        self.L.kref_set_params(params.match, params.mismatch, params.gap_open, params.gap_extend,
+                               params.score_threshold, params.report_cigar)
+        gb = u8(gen_bases); go = np.ascontiguousarray(gen_offs, dtype=np.uint64)
+        rb = u8(read_bases); ro = np.ascontiguousarray(read_offs, dtype=np.uint64)
+        self.L.kref_set_genomes(self.h, len(go) - 1, _p(gb), _p(go))
+        self.L.kref_set_reads(self.h, len(ro) - 1, _p(rb), _p(ro))
+
+    def close(self):
+        if self.h:
+            self.L.kref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def kmers(self, which, sort=False):
+        n = self.L.kref_extract_kmers(self.h, which)
+        if sort:
+            self.L.kref_sort_kmers(self.h)
+        out = np.zeros(n, dtype=KMER_DT)
+        self.L.kref_get_kmers(self.h, _p(out))
+        return out
+
+    def seeds(self, raw):
+        """Needs kmers(3, sort=True) first."""
+        n = self.L.kref_find_seeds_raw(self.h) if raw else self.L.kref_find_seeds(self.h)
+        out = np.zeros(n, dtype=SEED_DT)
+        self.L.kref_get_seeds(self.h, _p(out))
+        return out
+
+    def _overlaps(self):
+        n = self.L.kref_num_overlaps(self.h)
+        out = np.zeros(n, dtype=OVERLAP_DT)
+        pool = np.zeros(max(1, self.L.kref_cigar_total(self.h)), dtype=np.uint32)
+        self.L.kref_get_overlaps(self.h, _p(out), _p(pool))
+        return out, pool
+
+    def align_to_database(self):
+        self.L.kref_align_to_database(self.h)
+        return self._overlaps()
+
+    def screen_and_pair(self):
+        self.L.kref_screen(self.h)
+        n = self.L.kref_pair(self.h)
+        pairs = np.zeros(n, dtype=PAIR_DT)
+        self.L.kref_get_pairs(self.h, _p(pairs))
+        ov, pool = self._overlaps()
+        return ov, pool, pairs
+
+
+def ref_ssw_batch(q, qoffs, r, roffs, params, cigar_cap=64, threads=0):
+    L = ref()
+    L.kref_set_params(params.match, params.mismatch, params.gap_open, params.gap_extend,
+                      params.score_threshold, params.report_cigar)
+    q = u8(q); r = u8(r)
+    qoffs = np.ascontiguousarray(qoffs, dtype=np.uint64); roffs = np.ascontiguousarray(roffs, dtype=np.uint64)
+    n = len(qoffs) - 1
+    out = np.zeros(n, dtype=OVERLAP_DT)
+    pool = np.zeros(n * cigar_cap, dtype=np.uint32)
+    L.kref_ssw_batch(n, _p(q), _p(qoffs), _p(r), _p(roffs), params.report_cigar, params.score_threshold,
+                     _p(out), _p(pool), cigar_cap, threads)
+    return out, pool
+
+
+def load_pkg():
+    """Import the product package (directory name has a hyphen, so go through __graft_entry__)."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    return ge.load_pkg()

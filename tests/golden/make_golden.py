@@ -1,0 +1,67 @@
+"""Generate tests/golden/*.npz from the reference's own code (oracle/_ref/libkslam_ref.so).
+
+Run here (the container that has /root/reference): `python tests/golden/make_golden.py`.
+The reference ships no golden vectors for this path, so these fixtures — inputs plus
+the outputs of the UNMODIFIED reference functions — are what pins the oracle and the CUDA path on
+machines where the reference sources are absent. Inputs are seeded (k-slam_b200/synth.py).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import _lib as T  # noqa: E402
+
+synth = T.load_pkg().synth
+
+
+def pipeline_fixture(name, gb, go, rb, ro, params):
+    R = T.Ref(gb, go, rb, ro, params)
+    read_k = R.kmers(1)
+    gen_k = R.kmers(2)
+    R.kmers(3, sort=True)
+    raw = R.seeds(raw=True)
+    raw = np.sort(raw, order=["read", "entry", "rel", "rev_comp"])  # multiset: order is not contractual
+    seeds = R.seeds(raw=False)
+    ov, pool = R.align_to_database()
+    ovs, pools, pairs = R.screen_and_pair()
+    np.savez_compressed(
+        os.path.join(HERE, name), gen_bases=gb, gen_offs=go, read_bases=rb, read_offs=ro,
+        params=np.array([params.match, params.mismatch, params.gap_open, params.gap_extend,
+                         params.score_threshold, params.report_cigar], dtype=np.int64),
+        read_kmers=read_k, genome_kmers=gen_k, raw_seeds_sorted=raw, seeds=seeds, overlaps=ov,
+        cigar_pool=pool, pair_sorted_overlaps=ovs, pair_sorted_cigar_pool=pools, pairs=pairs)
+    print(name, "reads", len(ro) - 1, "kmers", len(read_k), len(gen_k), "raw", len(raw), "seeds", len(seeds),
+          "pairs", len(pairs))
+
+
+def ssw_fixture(name, q, qo, r, ro, params):
+    a, pool = T.ref_ssw_batch(q, qo, r, ro, params, cigar_cap=32)
+    assert (a["cigar_len"] <= 32).all()
+    np.savez_compressed(os.path.join(HERE, name), q=q, qoffs=qo, r=r, roffs=ro,
+                        params=np.array([params.match, params.mismatch, params.gap_open, params.gap_extend,
+                                         params.score_threshold, params.report_cigar], dtype=np.int64),
+                        expect=a, cigar_pool=pool)
+    print(name, len(a), "alignments; score range", a["sw_score"].min(), a["sw_score"].max())
+
+
+def main():
+    gb, go, rb, ro = synth.adversarial_set(seed=7, n_genomes=8, glen=6000, n_pairs=400)
+    pipeline_fixture("pipeline_adversarial_cigar.npz", gb, go, rb, ro, T.default_params(report_cigar=1))
+    pipeline_fixture("pipeline_adversarial_thr60.npz", gb, go, rb, ro,
+                     T.default_params(report_cigar=0, score_threshold=60))
+    gb, go = synth.random_genomes(4, 30_000, seed=1)
+    rb, ro, _ = synth.paired_reads(gb, go, 600, seed=2)
+    pipeline_fixture("pipeline_config1_mini.npz", gb, go, rb, ro, T.default_params(report_cigar=1))
+    q, qo, r, ro2 = synth.sw_pairs(1500, 150, 150, seed=21)
+    ssw_fixture("ssw_150x150.npz", q, qo, r, ro2, T.default_params(report_cigar=1))
+    q, qo, r, ro2 = synth.sw_pairs(1000, 150, 300, seed=22)
+    ssw_fixture("ssw_150x300.npz", q, qo, r, ro2, T.default_params(report_cigar=1))
+    q, qo, r, ro2 = synth.sw_pairs(800, 101, 140, seed=23)
+    ssw_fixture("ssw_101x140_nocigar.npz", q, qo, r, ro2, T.default_params(report_cigar=0))
+
+
+if __name__ == "__main__":
+    main()

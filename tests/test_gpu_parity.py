@@ -1,0 +1,236 @@
+"""GPU tier: the CUDA path (through the C ABI) against the oracle and the committed golden vectors."""
+import numpy as np
+import pytest
+
+import _lib as T
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ["read", "entry", "rel", "rev_comp", "ref_begin", "ref_end", "query_begin", "query_end", "sw_score", "cigar_len"]
+
+
+def canon(a):
+    return np.sort(a, order=list(a.dtype.names))
+
+
+def check_overlaps(got, gpool, want, wpool, fields=FIELDS, cigars=True):
+    assert len(got) == len(want)
+    undefined = ((want["flags"] | got["flags"]) & 1) != 0
+    for f in fields:
+        bad = (got[f] != want[f]) & ~undefined
+        assert not bad.any(), (f, int(bad.sum()), got[bad][:3], want[bad][:3])
+    if cigars:
+        a, b = T.cigars_of(got, gpool), T.cigars_of(want, wpool)
+        bad = [i for i in range(len(a)) if a[i] != b[i] and not undefined[i]]
+        assert not bad, (len(bad), [(a[i], b[i]) for i in bad[:3]])
+
+
+def run_pipeline(pkg, gb, go, rb, ro, P):
+    with pkg.Aligner(match=P.match, mismatch=P.mismatch, gap_open=P.gap_open, gap_extend=P.gap_extend,
+                     score_threshold=P.score_threshold, report_cigar=bool(P.report_cigar)) as al:
+        al.load_genomes(gb, go)
+        res = al.align_batch(rb, ro)
+        taps = dict(genome_kmers=al.genome_kmers(), read_kmers=al.read_kmers(), raw_seeds=al.raw_seeds(), seeds=al.seeds())
+        pairs = al.pair_batch()
+        tm = al.timings()
+    return res, taps, pairs, tm
+
+
+def check_pipeline(pkg, gb, go, rb, ro, P, want=None):
+    want = want or T.ko_pipeline(gb, go, rb, ro, P)
+    res, taps, pairs, tm = run_pipeline(pkg, gb, go, rb, ro, P)
+    # K1/K2: genome list in the reference's order (kmer asc, id_flags desc); read list sorted by k-mer, same multiset
+    wg = T.ko_sort_kmers(want["genome_kmers"])
+    assert np.array_equal(taps["genome_kmers"]["kmer"], wg["kmer"])
+    assert np.array_equal(taps["genome_kmers"]["id_flags"], wg["id_flags"])
+    assert np.array_equal(canon(taps["genome_kmers"]), canon(wg))
+    rk = taps["read_kmers"]
+    assert (np.diff(rk["kmer"].astype(np.uint64)) >= 0).all() if len(rk) > 1 else True
+    assert np.array_equal(canon(rk), canon(want["read_kmers"]))
+    # K3: raw seed multiset; K4: exact de-duplicated sequence
+    assert np.array_equal(canon(taps["raw_seeds"]), canon(want["raw_seeds"]))
+    assert np.array_equal(taps["seeds"], want["seeds"])
+    # K5-K8
+    check_overlaps(res.overlaps, res.cigar_pool, want["overlaps"], want["cigar_pool"], cigars=bool(P.report_cigar))
+    # K9
+    check_overlaps(pairs.sorted_overlaps, pairs.cigar_pool, want["pair_sorted_overlaps"], want["cigar_pool"],
+                   cigars=bool(P.report_cigar))
+    assert np.array_equal(pairs.pairs, want["pairs"])
+    assert tm["kernel_launches"] > 10
+    return res, tm
+
+
+def params_of(g):
+    p = g["params"]
+    return T.default_params(match=int(p[0]), mismatch=int(p[1]), gap_open=int(p[2]), gap_extend=int(p[3]),
+                            score_threshold=int(p[4]), report_cigar=int(p[5]))
+
+
+@pytest.mark.parametrize("name", ["pipeline_adversarial_cigar.npz", "pipeline_adversarial_thr60.npz",
+                                  "pipeline_config1_mini.npz"])
+def test_pipeline_golden(pkg, golden, name):
+    """Against the reference's own outputs (fixtures made by tests/golden/make_golden.py)."""
+    g = golden(name)
+    want = dict(read_kmers=g["read_kmers"], genome_kmers=g["genome_kmers"], raw_seeds=g["raw_seeds_sorted"],
+                seeds=g["seeds"], overlaps=g["overlaps"], cigar_pool=g["cigar_pool"],
+                pair_sorted_overlaps=g["pair_sorted_overlaps"], pairs=g["pairs"])
+    want["overlaps"] = want["overlaps"].copy()
+    check_pipeline(pkg, g["gen_bases"], g["gen_offs"], g["read_bases"], g["read_offs"], params_of(g), want)
+
+
+@pytest.mark.parametrize("seed,cigar,thr", [(11, 1, 0), (12, 0, 0), (13, 1, 80)])
+def test_pipeline_adversarial(pkg, seed, cigar, thr):
+    gb, go, rb, ro = pkg.synth.adversarial_set(seed=seed, n_genomes=10, glen=15_000, n_pairs=2500)
+    check_pipeline(pkg, gb, go, rb, ro, T.default_params(report_cigar=cigar, score_threshold=thr))
+
+
+def test_pipeline_config1_shape(pkg):
+    """Config 1 shape, scaled to what the oracle finishes in seconds: 8 x 250 kbp genomes, 20 k pairs."""
+    gb, go = pkg.synth.random_genomes(8, 250_000, seed=1)
+    rb, ro, truth = pkg.synth.paired_reads(gb, go, 20_000, seed=2)
+    res, tm = check_pipeline(pkg, gb, go, rb, ro, T.default_params(report_cigar=1))
+    assert tm["n_read_kmers"] == 2 * 20_000 * 119
+    assert tm["n_sw_slow"] == 0
+
+
+def test_pipeline_related_genomes_multi_hit(pkg):
+    """Config 2 shape in small: related genomes -> multi-genome piles and several seeds per read."""
+    gb, go = pkg.synth.related_genomes(12, 60_000, seed=3, n_roots=3, divergence=0.02)
+    rb, ro, _ = pkg.synth.paired_reads(gb, go, 5000, seed=4)
+    check_pipeline(pkg, gb, go, rb, ro, T.default_params(report_cigar=1))
+
+
+def test_empty_and_ragged_inputs(pkg):
+    P = T.default_params(report_cigar=1)
+    gb, go = pkg.synth.random_genomes(2, 5000, seed=5)
+    with pkg.Aligner(report_cigar=True) as al:
+        al.load_genomes(gb, go)
+        # no reads at all
+        res = al.align_batch(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+        assert len(res.overlaps) == 0
+        assert len(al.pair_batch().pairs) == 0
+        # reads all shorter than k, plus empty reads
+        seqs = [b"ACGT" * 5, b"", b"ACGTT" * 6, b""]
+        rb, ro = T.concat([np.frombuffer(s, np.uint8) for s in seqs])
+        res = al.align_batch(rb, ro)
+        assert len(res.overlaps) == 0 and len(al.read_kmers()) == 0
+    # a genome set with no k-mers
+    with pkg.Aligner(report_cigar=True) as al:
+        al.load_genomes(np.frombuffer(b"ACGT" * 5, np.uint8), np.array([0, 20], np.uint64))
+        rb, ro, _ = pkg.synth.paired_reads(gb, go, 10, seed=1)
+        assert len(al.align_batch(rb, ro).overlaps) == 0
+
+
+def test_long_reads_take_the_slow_kernel(pkg):
+    """Reads beyond the fast kernel's 160 rows are still aligned on the GPU (exact scalar kernel)."""
+    gb, go = pkg.synth.random_genomes(3, 40_000, seed=8)
+    rb, ro, _ = pkg.synth.paired_reads(gb, go, 300, read_len=251, seed=9, frag_mean=500, frag_sd=30)
+    res, tm = check_pipeline(pkg, gb, go, rb, ro, T.default_params(report_cigar=1))
+    assert tm["n_sw_slow"] > 0
+
+
+@pytest.mark.parametrize("name", ["ssw_150x150.npz", "ssw_150x300.npz", "ssw_101x140_nocigar.npz"])
+def test_ssw_golden(pkg, golden, name):
+    g = golden(name)
+    P = params_of(g)
+    with pkg.Aligner(report_cigar=bool(P.report_cigar)) as al:
+        out, pool = al.ssw_batch(g["q"], g["qoffs"], g["r"], g["roffs"])
+    want = g["expect"].copy()
+    check_overlaps(out, pool, want, g["cigar_pool"], fields=FIELDS[4:], cigars=bool(P.report_cigar))
+
+
+@pytest.mark.parametrize("shape", [(150, 150), (150, 300), (100, 130), (40, 64), (160, 160)])
+@pytest.mark.parametrize("cigar", [0, 1])
+def test_ssw_vs_oracle(pkg, shape, cigar):
+    q, qo, r, ro = pkg.synth.sw_pairs(20_000, shape[0], shape[1], seed=100 + shape[0] + cigar)
+    P = T.default_params(report_cigar=cigar)
+    want, wpool = T.ko_ssw_batch(q, qo, r, ro, P, cigar_cap=32)
+    with pkg.Aligner(report_cigar=bool(cigar)) as al:
+        out, pool = al.ssw_batch(q, qo, r, ro)
+        tm = al.timings()
+    check_overlaps(out, pool, want, wpool, fields=FIELDS[4:], cigars=bool(cigar))
+    assert tm["n_sw_slow"] == 0 and tm["n_sw_fast"] == 20_000
+
+
+def test_ssw_ragged_lengths_and_repeats(pkg):
+    rng = np.random.default_rng(5)
+    ACGT = pkg.synth.ACGT
+    qs, rs = [], []
+    for _ in range(6000):
+        per = int(rng.integers(2, 25)); unit = ACGT[rng.integers(0, 4, size=per)]
+        L = int(rng.integers(20, 181)); w = np.tile(unit, L // per + 2)[:L].copy()
+        m = rng.random(L) < 0.03; w[m] = ACGT[rng.integers(0, 4, size=int(m.sum()))]
+        ql = int(rng.integers(1, 161)); st = int(rng.integers(0, max(1, L - ql))); qq = w[st:st + ql].copy()
+        if len(qq) == 0:
+            qq = ACGT[rng.integers(0, 4, size=5)]
+        m = rng.random(len(qq)) < 0.03; qq[m] = ACGT[rng.integers(0, 4, size=int(m.sum()))]
+        if rng.random() < 0.1:
+            qq[rng.integers(0, len(qq))] = ord("N")
+        if rng.random() < 0.1:
+            w[rng.integers(0, len(w))] = ord("n")
+        qs.append(qq); rs.append(w)
+    q, qo = T.concat(qs); r, ro = T.concat(rs)
+    P = T.default_params(report_cigar=1)
+    want, wpool = T.ko_ssw_batch(q, qo, r, ro, P, cigar_cap=32)
+    with pkg.Aligner(report_cigar=True) as al:
+        out, pool = al.ssw_batch(q, qo, r, ro)
+    assert ((want["flags"] & 1) != 0).mean() < 0.01
+    check_overlaps(out, pool, want, wpool, fields=FIELDS[4:])
+
+
+def test_radix_sort_matches_numpy(pkg):
+    rng = np.random.default_rng(3)
+    with pkg.Aligner() as al:
+        for n, lo, hi in [(1, 0, 64), (5000, 0, 64), (300_000, 0, 64), (100_000, 8, 40), (70_000, 0, 13)]:
+            recs = np.zeros(n, dtype=pkg.KMER_DT)
+            recs["kmer"] = rng.integers(0, 2**63, size=n, dtype=np.uint64) * 2 + rng.integers(0, 2, size=n, dtype=np.uint64)
+            recs["id_flags"] = np.arange(n, dtype=np.uint32)       # arrival order: checks stability
+            recs["offset"] = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+            got, ms = al.sort_records(recs, lo, hi)
+            mask = np.uint64(((1 << (hi - lo)) - 1) if hi - lo < 64 else 0xFFFFFFFFFFFFFFFF)
+            key = (recs["kmer"] >> np.uint64(lo)) & mask
+            order = np.argsort(key, kind="stable")
+            assert np.array_equal(got, recs[order]), (n, lo, hi)
+
+
+def test_full_size_properties_config1_slice(pkg):
+    """Size-independent properties at a larger scale than the oracle can check quickly: planted position is
+    recovered (Tests.h:161-264), perfect reads score 2 x length (Tests.h:136,323), results are identical when
+    the same batch is split in two (seeds are per-read), and the record counts obey KMer.h:202."""
+    gb, go = pkg.synth.random_genomes(20, 1_000_000, seed=1)
+    n_pairs = 200_000
+    rb, ro, truth = pkg.synth.paired_reads(gb, go, n_pairs, seed=2, sub_rate=0.0, indel_frac=0.0)
+    with pkg.Aligner(report_cigar=False) as al:
+        al.load_genomes(gb, go)
+        res = al.align_batch(rb, ro)
+        tm = al.timings()
+        ov = res.overlaps
+        assert tm["n_read_kmers"] == 2 * n_pairs * 119
+        assert tm["n_genome_kmers"] == 20 * ((1_000_000 - 32) // 16 + 1)
+        # error-free reads: every read has a seed on its own genome scoring exactly 300
+        best = np.zeros(2 * n_pairs, dtype=np.uint32)
+        np.maximum.at(best, ov["read"], ov["sw_score"])
+        assert (best == 300).mean() > 0.999
+        # planted genome and position are recovered for the left mate (forward strand, rel == pos)
+        r1_is_left = truth["swapped"] == 0
+        left_read = np.where(r1_is_left, np.arange(n_pairs), np.arange(n_pairs) + n_pairs)
+        sel = (ov["sw_score"] == 300) & (ov["rev_comp"] == 0)
+        hit = {}
+        for rd, en, rel in zip(ov["read"][sel], ov["entry"][sel], ov["rel"][sel]):
+            hit[int(rd)] = (int(en), int(rel))
+        ok = sum(1 for i in range(0, n_pairs, 97) if hit.get(int(left_read[i])) == (int(truth["genome"][i]), int(truth["pos"][i])))
+        assert ok >= 0.99 * len(range(0, n_pairs, 97))
+        # sorted, de-duplicated order
+        key = (ov["read"].astype(np.int64) << 32) | ov["entry"].astype(np.int64)
+        assert (np.diff(key) >= 0).all()
+        # splitting the batch changes nothing for the reads of the first half
+        half = n_pairs // 2
+        sub = np.concatenate([np.arange(half), np.arange(n_pairs, n_pairs + half)])
+        L = 150
+        rb2 = rb.reshape(-1, L)[sub].reshape(-1)
+        ro2 = np.arange(len(sub) + 1, dtype=np.uint64) * np.uint64(L)
+        res2 = al.align_batch(rb2, ro2)
+        a = ov[ov["read"] < half]
+        b = res2.overlaps[res2.overlaps["read"] < half]
+        for f in FIELDS[1:9]:
+            assert np.array_equal(a[f], b[f]), f
