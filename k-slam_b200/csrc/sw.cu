@@ -81,6 +81,14 @@ __device__ __forceinline__ uint32_t w_code(const SwPlanes &p, const SwTask &t, u
 
 __device__ __forceinline__ uint32_t pack2(int v) { return ((uint32_t)v & 0xffffu) * 0x10001u; }
 
+// prmt.b32 in its generic form: selector nibble bit 3 replicates the sign of the chosen byte over the target
+// byte (the __byte_perm intrinsic masks that bit away, so the PTX instruction is used directly)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
 // ---------------------------------------------------------------- fast kernel
 template <int LANES, bool REVERSE>
 __global__ void __launch_bounds__(SW_BLOCK, 4)
@@ -155,7 +163,7 @@ k_sw_fast(const SwTask *__restrict__ tasks, const uint2 *__restrict__ items, uin
         const uint32_t cm = ((selw & 0x10000u) ? 0u : 0xffffu) | ((selw & 0x20000u) ? 0u : 0xffff0000u);
 #pragma unroll
         for (int r = 0; r < SW_R; r++) {
-          uint32_t s = __byte_perm(PA[r], PB[r], sel) & cm;
+          uint32_t s = prmt(PA[r], PB[r], sel) & cm;
           uint32_t h = __viaddmax_s16x2_relu(hd, s, E[r]);
           h = __vimax3_s16x2(h, f, f);
           hd = H[r]; H[r] = h;
@@ -167,7 +175,7 @@ k_sw_fast(const SwTask *__restrict__ tasks, const uint2 *__restrict__ items, uin
       } else {
 #pragma unroll
         for (int r = 0; r < SW_R; r++) {
-          uint32_t s = __byte_perm(PA[r], PB[r], sel);
+          uint32_t s = prmt(PA[r], PB[r], sel);
           uint32_t h = __viaddmax_s16x2_relu(hd, s, E[r]);       // max(H[i-1][j-1] + s, E, 0)
           h = __vimax3_s16x2(h, f, f);                            // ... and F
           hd = H[r]; H[r] = h;
