@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py — the matching path's headline metric on N B200s of one node.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2|config1|config3] [--pairs P]
+  python bench.py --impl reference ...      # the reference's own CPU implementation (oracle/_ref), rank 0 only
+
+A step = one pass of the hot path (alignToDatabase + score screen + getPairedOverlaps, SLAM.h:209-214) over
+one batch of synthetic read pairs. `value` is measured with the batch already packed-resident in HBM
+(kslam_align_resident + kslam_pair_batch, no result copy); `e2e` goes through the reference-facing C-ABI call
+with HOST buffers (kslam_align_batch + kslam_pair_batch with results copied back), host<->device copies inside
+the timed region. Ranks shard read pairs (weak scaling: every rank owns a full batch, the genome index is
+replicated, no collective on the data path); the timed region is bracketed by barrier + synchronize and the
+MAX over ranks is taken. One JSON line on stdout from rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+METRIC = "M read-pairs/min end-to-end at 1/2/4/8 B200; SW GCUPS; k-mer join GB/s"
+UNIT = "M read-pairs/min"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(pkg, name, pairs, seed_shift=0):
+    synth = pkg.synth
+    t0 = time.time()
+    if name == "config1":
+        gb, go = synth.random_genomes(50, 3_000_000, seed=1)
+        desc = f"config1-shape: {pairs} x 150bp FR pairs from 50 x 3 Mbp random genomes"
+    elif name == "config2":
+        gb, go = synth.tree_genomes(500, 2_000_000, seed=1)
+        desc = (f"config2-shape (metagenomic): {pairs} x 150bp FR pairs vs 500 x 2 Mbp genomes in a 5/25/100/500 "
+                "phylogeny (multi-genome piles)")
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    rb, ro, _ = synth.paired_reads(gb, go, pairs, seed=2 + seed_shift)
+    log(f"[bench] generated {desc} in {time.time() - t0:.1f}s")
+    return gb, go, rb, ro, desc
+
+
+def cpu_reference_sample(pkg, gb, go, n_pairs_sample, report_cigar, threshold):
+    """The reference's own alignToDatabase + screen + getPairedOverlaps (oracle/_ref, all host threads) on a
+    bounded sample of the same workload. Returns (pairs/min in millions, seconds, cores, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _lib as T
+    rb, ro, _ = pkg.synth.paired_reads(gb, go, n_pairs_sample, seed=99)
+    P = T.default_params(report_cigar=int(report_cigar), score_threshold=threshold)
+    if T.have_ref():
+        R = T.Ref(gb, go, rb, ro, P)
+        cores = T.ref().kref_num_threads()
+        t0 = time.time()
+        R.align_to_database()
+        R.screen_and_pair()
+        dt = time.time() - t0
+        R.close()
+        kind = "reference"
+    else:
+        cores = os.cpu_count() or 1
+        t0 = time.time()
+        T.ko_pipeline(gb, go, rb, ro, P, threads=cores)
+        dt = time.time() - t0
+        kind = "port"
+    return n_pairs_sample / dt * 60 / 1e6, dt, cores, kind
+
+
+def run_reference_arm(args, pkg):
+    """--impl reference: the reference's CPU path on this box's host cores, same config/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pairs = args.pairs or DEFAULT_PAIRS[args.workload]
+    sample = args.ref_sample
+    gb, go, _, _, desc = make_workload(pkg, args.workload, 1000)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt, cores, kind = cpu_reference_sample(pkg, gb, go, sample, False, 0)
+        log(f"[bench/reference] step {i}: {sample} pairs in {dt:.2f}s -> {v:.3f} M pairs/min on {cores} threads")
+        if i >= args.warmup:
+            vals.append((v, dt))
+    v = float(np.mean([x[0] for x in vals])); dt = float(np.mean([x[1] for x in vals]))
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "int16/int32/u64", "data": "synthetic",
+           "config": {"workload": desc.replace("1000 x", f"{pairs} x"), "batch_pairs_per_gpu": pairs},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                            "sample": f"{sample} pairs of the workload per step (same genomes), alignToDatabase+screen+getPairedOverlaps"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+DEFAULT_PAIRS = {"config1": 1_000_000, "config2": 10_000_000}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="kslam", choices=["kslam", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("KSLAM_BENCH_WORKLOAD", "config2"), choices=["config1", "config2"])
+    ap.add_argument("--pairs", type=int, default=0, help="read pairs per batch per GPU (default: the config's)")
+    ap.add_argument("--ref-sample", type=int, default=20_000, help="pairs per step for the CPU reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=20_000, help="pairs for the cpu_baseline leg (rank 0, N=1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    pkg = ge.load_pkg()
+    if args.impl == "reference":
+        return run_reference_arm(args, pkg)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the matching path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pairs = args.pairs or DEFAULT_PAIRS[args.workload]
+    gb, go, rb, ro, desc = make_workload(pkg, args.workload, pairs, seed_shift=rank)
+    # pinned host staging for the e2e leg (the C ABI takes plain host pointers)
+    rb_pin = torch.from_numpy(rb).pin_memory()
+    rb_host = rb_pin.numpy()
+    al = pkg.Aligner(report_cigar=False, device=local)
+    al.set_debug_taps(False)
+    t0 = time.time()
+    al.load_genomes(gb, go)
+    t_load = time.time() - t0
+    log(f"[bench r{rank}] genome index built in {t_load:.2f}s")
+
+    # ---- value: inputs resident in HBM -------------------------------------------------------
+    al.upload_reads(rb_host, ro)
+    for _ in range(args.warmup):
+        al.align_resident(fetch=False); al.pair_batch(fetch=False)
+    launches0 = al.timings()["kernel_launches"]
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
+    stage = {}
+    for _ in range(args.steps):
+        al.align_resident(fetch=False); al.pair_batch(fetch=False)
+        tm = al.timings()
+        for k, v in tm.items():
+            if k.startswith("ms_"):
+                stage[k] = stage.get(k, 0.0) + v
+    barrier()
+    t_res = time.perf_counter() - tw0          # library calls are synchronous: wall == device time of the chain
+    clocks = sampler.stop() if rank == 0 else None
+    tm = al.timings()
+    launches = (tm["kernel_launches"] - launches0) // max(1, args.steps)
+
+    # ---- e2e: host buffers in, results back on the host ------------------------------------------
+    for _ in range(max(1, args.warmup - 1)):
+        res = al.align_batch(rb_host, ro, copy=False); pr = al.pair_batch(fetch=True, copy=False)
+    barrier()
+    tw0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = al.align_batch(rb_host, ro, copy=False); pr = al.pair_batch(fetch=True, copy=False)
+    barrier()
+    t_e2e = time.perf_counter() - tw0
+    h2d = int(rb_host.nbytes + 3 * ro.nbytes)
+    d2h = int(res.overlaps.nbytes + pr.sorted_overlaps.nbytes + pr.pairs.nbytes)
+
+    t_max = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    t_res, t_e2e = float(t_max[0]), float(t_max[1])
+    total_pairs = pairs * world * args.steps
+    value = total_pairs / t_res * 60 / 1e6
+    e2e = total_pairs / t_e2e * 60 / 1e6
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        ms = {k: v / args.steps for k, v in stage.items()}
+        n_rk, n_raw = tm["n_read_kmers"], tm["n_raw_seeds"]
+        passes_kmer = 8
+        sort_s = ms["ms_sort"] / 1e3
+        # dominant HBM-bound kernel: k_rs_onesweep of the read k-mer sort. algorithmic bytes per launch = 32 B x records
+        # (one read + one write of every 16 B record per pass); duration = sort time / passes (histogram charged too)
+        per_launch_s = sort_s / passes_kmer if sort_s > 0 else float("nan")
+        achieved = 32.0 * n_rk / per_launch_s / 1e9 if sort_s > 0 else 0.0
+        join_gbs = (32.0 * n_rk + 16.0 * n_rk + 16.0 * n_raw) / ((ms["ms_sort"] + ms["ms_join"]) / 1e3) / 1e9
+        sw_s = (ms["ms_sw_forward"] + ms["ms_sw_reverse"] + ms["ms_sw_traceback"] + ms["ms_sw_slow"] + ms["ms_sw_prepare"]) / 1e3
+        gcups = tm["sw_cells_forward"] / sw_s / 1e9 if sw_s > 0 else 0.0
+        gcups_kernel = (tm["sw_cells_forward"] + tm["sw_cells_reverse"]) / ((ms["ms_sw_forward"] + ms["ms_sw_reverse"]) / 1e3) / 1e9 \
+            if ms["ms_sw_forward"] + ms["ms_sw_reverse"] > 0 else 0.0
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "int16x2 (SW) / u64 (k-mers)", "data": "synthetic",
+               "config": {"workload": desc, "batch_pairs_per_gpu": pairs, "sharding": f"read pairs, {world} ranks, no collective",
+                          "l2": "inputs larger than L2 (3.8 GB+ of k-mer records per step)", "report_cigar": False},
+               "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "gpu_launches": int(launches),
+               "clocks": clocks,
+               "roofline": {"bound": "hbm", "kernel": "k_rs_onesweep (read k-mer LSD pass)", "achieved": achieved, "peak": peak,
+                            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                            "note": "algorithmic 32 B/record/pass; duration = (sort stage incl. histogram)/8 passes, CUDA events on the ctx stream"},
+               "kmer_join_gbs": join_gbs, "sw_gcups": gcups, "sw_kernel_gcups_fwd_plus_rev": gcups_kernel,
+               "stage_ms": ms,
+               "counts": {k: tm[k] for k in ("n_read_kmers", "n_genome_kmers", "n_raw_seeds", "n_seeds", "n_pairs", "n_sw_fast",
+                                             "n_sw_slow", "sw_cells_forward", "sw_cells_reverse", "n_sort_passes")},
+               "genome_index_build_s": t_load}
+        if world == 1 and not args.no_cpu_baseline:
+            v, dt, cores, kind = cpu_reference_sample(pkg, gb, go, args.cpu_sample, False, 0)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                                   "sample": f"{args.cpu_sample} pairs of the same workload in {dt:.1f}s (alignToDatabase+screen+getPairedOverlaps, genome k-mers re-extracted and re-sorted per batch as the reference does)"}
+        print(json.dumps(out), flush=True)
+    al.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -511,19 +511,22 @@ k_sw_rev_keys(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, u
   if (run) atomicAdd(&counts[8], 1u);
 }
 
-// sorted (by class, columns) task ids -> work items: two alignments with the same column count share a group;
-// an unequal neighbour pair becomes two single items (both halves run the same alignment)
+// sorted (by class, columns) task ids -> work items: two alignments with the same column count share a group.
+// Item w < W = ceil(n/2) is dense; the second member of an unequal neighbour pair becomes a single item appended
+// after W through an atomic counter (slots [W, 2W) are pre-filled with SW_INVALID and exit immediately).
 __global__ void __launch_bounds__(256)
-k_sw_make_items(const Rec16 *__restrict__ sorted, uint32_t n_fast, uint2 *__restrict__ items) {
+k_sw_make_items(const Rec16 *__restrict__ sorted, uint32_t n_fast, uint2 *__restrict__ items, uint32_t *__restrict__ extra) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
   if (2 * w >= n_fast) return;
+  const uint32_t W = (n_fast + 1) / 2;
   const Rec16 a = sorted[2 * w];
-  uint2 i0 = make_uint2((uint32_t)a.val, (uint32_t)a.val), i1 = make_uint2(SW_INVALID, SW_INVALID);
+  uint2 i0 = make_uint2((uint32_t)a.val, (uint32_t)a.val);
   if (2 * w + 1 < n_fast) {
     const Rec16 b = sorted[2 * w + 1];
-    if (b.key == a.key) i0.y = (uint32_t)b.val; else i1 = make_uint2((uint32_t)b.val, (uint32_t)b.val);
+    if (b.key == a.key) i0.y = (uint32_t)b.val;
+    else items[W + atomicAdd(extra, 1u)] = make_uint2((uint32_t)b.val, (uint32_t)b.val);
   }
-  items[2 * w] = i0; items[2 * w + 1] = i1;
+  items[w] = i0;
 }
 
 __global__ void __launch_bounds__(256)
@@ -587,7 +590,9 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
   uint2 *items = w->items.as<uint2>();
   if (n_fast) {
     const uint32_t n_items = 2 * ((n_fast + 1) / 2);
-    k_sw_make_items<<<(n_items / 2 + 255) / 256, 256, 0, st>>>(sorted, n_fast, items);
+    CUDA_TRY(cudaMemsetAsync(items, 0xff, (size_t)n_items * sizeof(uint2), st));
+    CUDA_TRY(cudaMemsetAsync(d_counts + 10, 0, 4, st));
+    k_sw_make_items<<<(n_items / 2 + 255) / 256, 256, 0, st>>>(sorted, n_fast, items, d_counts + 10);
     constexpr int GROUPS = SW_BLOCK / 8;
     k_sw_fast<8, false><<<(n_items + GROUPS - 1) / GROUPS, SW_BLOCK, 0, st>>>(tasks, items, n_items, pl, sc, res);
     c->launches += 2;
@@ -608,7 +613,9 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
     Rec16 *rs = radix_sort(c, other, tmp, n, 0, 0, 41, &passes);
     if (n_rev) {
       const uint32_t n_items = 2 * ((n_rev + 1) / 2);
-      k_sw_make_items<<<(n_items / 2 + 255) / 256, 256, 0, st>>>(rs, n_rev, items);
+      CUDA_TRY(cudaMemsetAsync(items, 0xff, (size_t)n_items * sizeof(uint2), st));
+      CUDA_TRY(cudaMemsetAsync(d_counts + 10, 0, 4, st));
+      k_sw_make_items<<<(n_items / 2 + 255) / 256, 256, 0, st>>>(rs, n_rev, items, d_counts + 10);
       constexpr int GROUPS = SW_BLOCK / 8;
       k_sw_fast<8, true><<<(n_items + GROUPS - 1) / GROUPS, SW_BLOCK, 0, st>>>(tasks, items, n_items, pl, sc, res);
       c->launches += 2;

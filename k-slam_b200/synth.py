@@ -41,6 +41,31 @@ def related_genomes(n_genomes: int, length: int, seed: int = 1, n_roots: int = 5
     return out.reshape(-1), offs
 
 
+def tree_genomes(n_strains: int = 500, length: int = 2_000_000, seed: int = 1,
+                 divergence=(0.25, 0.15, 0.05, 0.01)):
+    """Config 2: strains in a synthetic phylogeny root -> 5 phyla -> 25 genera -> 100 species ->
+    `n_strains` strains; every child is its parent with a fraction of positions redrawn (per-level `divergence`),
+    so conserved 32-mers give multi-genome piles and reads seed on several related strains."""
+    rng = np.random.default_rng(seed)
+
+    def mutate(parent, d):
+        child = parent.copy()
+        m = rng.random(length) < d
+        child[m] = ACGT[rng.integers(0, 4, size=int(m.sum()), dtype=np.uint8)]
+        return child
+
+    root = ACGT[rng.integers(0, 4, size=length, dtype=np.uint8)]
+    n_species = max(1, n_strains // 5); n_genera = max(1, n_species // 4); n_phyla = max(1, n_genera // 5)
+    phyla = [mutate(root, divergence[0]) for _ in range(n_phyla)]
+    genera = [mutate(phyla[i % n_phyla], divergence[1]) for i in range(n_genera)]
+    species = [mutate(genera[i % n_genera], divergence[2]) for i in range(n_species)]
+    out = np.empty((n_strains, length), dtype=np.uint8)
+    for i in range(n_strains):
+        out[i] = mutate(species[i % n_species], divergence[3])
+    offs = np.arange(n_strains + 1, dtype=np.uint64) * np.uint64(length)
+    return out.reshape(-1), offs
+
+
 def paired_reads(gen_bases: np.ndarray, gen_offs: np.ndarray, n_pairs: int, read_len: int = 150,
                  seed: int = 2, sub_rate: float = 0.01, indel_frac: float = 0.05,
                  frag_mean: float = 350.0, frag_sd: float = 35.0, chunk: int = 200_000):
