@@ -253,7 +253,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peaks()
         ms = {k: v / args.steps for k, v in stage.items()}
-        n_rk, n_raw = tm["n_read_kmers"], tm["n_raw_seeds"]
+        n_rk, n_raw = tm["n_sorted_kmers"], tm["n_raw_seeds"]     # records actually sorted (after the prefilter)
         passes_kmer = 8
         sort_s = ms["ms_sort"] / 1e3
         # dominant HBM-bound kernel: k_rs_onesweep of the read k-mer sort. algorithmic bytes per launch = 32 B x records
@@ -278,7 +278,7 @@ def main():
                             "note": "algorithmic 32 B/record/pass; duration = (sort stage incl. histogram)/8 passes, CUDA events on the ctx stream"},
                "kmer_join_gbs": join_gbs, "sw_gcups": gcups, "sw_kernel_gcups_fwd_plus_rev": gcups_kernel,
                "stage_ms": ms,
-               "counts": {k: tm[k] for k in ("n_read_kmers", "n_genome_kmers", "n_raw_seeds", "n_seeds", "n_pairs", "n_sw_fast",
+               "counts": {k: tm[k] for k in ("n_read_kmers", "n_sorted_kmers", "n_genome_kmers", "n_raw_seeds", "n_seeds", "n_pairs", "n_sw_fast",
                                              "n_sw_slow", "sw_cells_forward", "sw_cells_reverse", "n_sort_passes")},
                "genome_index_build_s": t_load}
         if world == 1 and not args.no_cpu_baseline:

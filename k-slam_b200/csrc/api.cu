@@ -98,7 +98,7 @@ void kslam_destroy(kslam_ctx *c) {
   c->genomes.release(); c->reads.release(); c->swq.release(); c->swr.release();
   DevBuf *bufs[] = {&c->g_keys, &c->g_vals, &c->recA, &c->recB, &c->sort_hist, &c->scan_tmp, &c->counters,
                     &c->raw_seeds, &c->seedA, &c->seedB, &c->seed_keep, &c->seeds, &c->ov, &c->cig, &c->pair_keys,
-                    &c->pair_keys2, &c->ov_sorted, &c->cig_sorted, &c->pair_cnt, &c->pairs};
+                    &c->pair_keys2, &c->ov_sorted, &c->cig_sorted, &c->pair_cnt, &c->pairs, &c->bitmap};
   for (DevBuf *b : bufs) b->release();
   HostBuf *hb[] = {&c->h_counters, &c->h_ov, &c->h_cig, &c->h_ov_sorted, &c->h_cig_sorted, &c->h_pairs};
   for (HostBuf *b : hb) b->release();
@@ -106,6 +106,12 @@ void kslam_destroy(kslam_ctx *c) {
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
+}
+
+int kslam_set_prefilter(kslam_ctx *ctx, int on) {
+  if (!ctx) return KSLAM_ERR_ARG;
+  ctx->prefilter = on != 0;
+  return KSLAM_OK;
 }
 
 int kslam_set_debug_taps(kslam_ctx *ctx, int keep) {
@@ -163,6 +169,8 @@ int kslam_load_genomes(kslam_ctx *c, uint64_t n, const char *bases, const uint64
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     a.release(); b.release();
   }
+  build_prefilter(c);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->tm.n_genome_kmers = c->n_gk;
   c->genomes_loaded = true;
   return KSLAM_OK;
@@ -198,9 +206,14 @@ static void align_device(kslam_ctx *c) {
   c->tm.n_read_kmers = c->n_rk; c->tm.n_sort_passes = 0;
   c->sorted_rk = nullptr;
   if (c->n_rk) {
-    c->recA.reserve((size_t)c->n_rk * sizeof(Rec16)); c->recB.reserve((size_t)c->n_rk * sizeof(Rec16));
-    extract_kmers(c, c->reads, false, 1, c->recA.as<Rec16>());
+    c->recA.reserve((size_t)c->n_rk * sizeof(Rec16));
+    if (c->prefilter && c->filter_bits) {
+      // fused extract + prefilter: n_rk becomes the number of records that can still match a genome k-mer
+      c->n_rk = extract_read_kmers_filtered(c, c->reads, c->recA.as<Rec16>());
+    } else extract_kmers(c, c->reads, false, 1, c->recA.as<Rec16>());
+    c->recB.reserve((size_t)c->n_rk * sizeof(Rec16) + 64);
   }
+  c->tm.n_sorted_kmers = c->n_rk;
   cudaEvent_t e1 = tm_mark(c);
   if (c->n_rk) {
     uint64_t passes = 0;

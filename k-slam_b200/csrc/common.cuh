@@ -92,6 +92,9 @@ struct kslam_ctx {
   DevBuf g_keys;   // u64 sorted genome k-mers
   DevBuf g_vals;   // u64 id_flags | offset<<32, same order
   uint64_t n_gk = 0;
+  DevBuf bitmap;   // prefilter: 2^filter_bits bits over hashed genome k-mers (kmer.cu)
+  uint32_t filter_bits = 0;
+  bool prefilter = true;
   uint32_t max_genome_len = 0;
 
   DevBuf recA, recB;        // Rec16 ping-pong (read k-mers, then seeds)
@@ -133,6 +136,8 @@ void pack_sequences(kslam_ctx *c, PackedSeqs &s, uint64_t n, const char *bases, 
                     uint32_t kmer_gap, bool keep_raw);
 // kmer.cu
 void extract_kmers(kslam_ctx *c, const PackedSeqs &s, bool is_gb, uint32_t gap, Rec16 *out);
+void build_prefilter(kslam_ctx *c);
+uint64_t extract_read_kmers_filtered(kslam_ctx *c, const PackedSeqs &s, Rec16 *out);
 // radix_sort.cu
 // Sorts n records by bits [lo_bit, hi_bit) of their .key (word 0) or .val (word 1); stable.
 // Returns the buffer (a or b) holding the result; *passes_done is incremented per executed pass.

@@ -78,6 +78,114 @@ k_extract_flat(const uint64_t *__restrict__ kbits, const uint64_t *__restrict__ 
   }
 }
 
+// ---- prefilter: a bitmap over hashed genome k-mers ---------------------------------------------------
+// Only read k-mers that equal some genome k-mer can ever seed (Overlap.h:157: a pile must start with a genome
+// record), and zero k-mers never do (Overlap.h:236-239). A read record whose hashed k-mer misses the bitmap of
+// genome k-mers therefore cannot contribute to any pile and is dropped before it is ever written to HBM; false
+// positives are harmless (the join drops them). The seed multiset is unchanged; the sort shrinks ~10x.
+__device__ __forceinline__ uint64_t kmer_hash(uint64_t k, uint32_t bits) {
+  return (k * 0x9E3779B97F4A7C15ull) >> (64 - bits);
+}
+
+__global__ void __launch_bounds__(256)
+k_bitmap_build(const uint64_t *__restrict__ gkeys, uint64_t n, uint32_t bits, uint32_t *__restrict__ bitmap) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    uint64_t k = __ldg(&gkeys[i]);
+    if (k == 0) continue;
+    uint64_t h = kmer_hash(k, bits);
+    atomicOr(&bitmap[h >> 5], 1u << (h & 31));
+  }
+}
+
+#define XF_WBUF 160   // per-warp staging records (flushed with one global atomic once > 128 are pending)
+
+// Reads (gap 1) with the prefilter fused in: one warp per read; survivors are staged per warp in shared memory
+// and appended to the output in contiguous bursts. Record order is arbitrary (they are sorted next).
+__global__ void __launch_bounds__(256)
+k_extract_reads_filtered(const uint64_t *__restrict__ kbits, const uint64_t *__restrict__ offs,
+                         const uint64_t *__restrict__ word_off, uint64_t n_seqs, const uint32_t *__restrict__ bitmap,
+                         uint32_t bits, Rec16 *__restrict__ out, unsigned long long *__restrict__ counter) {
+  __shared__ __align__(16) Rec16 s_buf[8][XF_WBUF];
+  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  Rec16 *buf = s_buf[wib];
+  uint32_t pending = 0;   // warp-uniform
+  for (uint64_t seq = warp; seq < n_seqs; seq += nwarps) {
+    uint64_t len64 = __ldg(&offs[seq + 1]) - __ldg(&offs[seq]);
+    if (len64 < KSLAM_K) continue;
+    uint32_t len = (uint32_t)len64;
+    uint64_t woff = __ldg(&word_off[seq]);
+    uint32_t nk = len - KSLAM_K + 1;
+    for (uint32_t p0 = 0; p0 < nk; p0 += 32) {
+      uint32_t p = p0 + lane;
+      bool keep = false;
+      uint64_t key = 0, val = 0;
+      if (p < nk) {
+        uint64_t f = kmer_at(kbits, woff, p), rc = revcomp32(f);
+        uint32_t flags = (uint32_t)seq & 0x3FFFFFFFu;
+        if (f < rc) { key = f; val = (uint64_t)flags | ((uint64_t)p << 32); }
+        else { key = rc; val = (uint64_t)(flags | 0x40000000u) | ((uint64_t)(len - KSLAM_K - p) << 32); }
+        if (key != 0) { uint64_t h = kmer_hash(key, bits); keep = (__ldg(&bitmap[h >> 5]) >> (h & 31)) & 1; }
+      }
+      uint32_t m = __ballot_sync(0xffffffffu, keep);
+      if (keep) *reinterpret_cast<ulonglong2 *>(&buf[pending + __popc(m & ((1u << lane) - 1))]) = make_ulonglong2(key, val);
+      pending += __popc(m);
+      if (pending > XF_WBUF - 32) {
+        __syncwarp();
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)pending);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (uint32_t i = lane; i < pending; i += 32)
+          *reinterpret_cast<ulonglong2 *>(out + base + i) = *reinterpret_cast<const ulonglong2 *>(&buf[i]);
+        __syncwarp();
+        pending = 0;
+      }
+    }
+  }
+  if (pending) {
+    __syncwarp();
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(counter, (unsigned long long)pending);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t i = lane; i < pending; i += 32)
+      *reinterpret_cast<ulonglong2 *>(out + base + i) = *reinterpret_cast<const ulonglong2 *>(&buf[i]);
+  }
+}
+
+void build_prefilter(kslam_ctx *c) {
+  c->filter_bits = 0;
+  if (!c->n_gk) return;
+  uint32_t bits = ceil_log2_u64(c->n_gk * 16);
+  if (bits < 26) bits = 26;
+  if (bits > 34) bits = 34;
+  c->bitmap.reserve((size_t)1 << (bits - 3));
+  CUDA_TRY(cudaMemsetAsync(c->bitmap.p, 0, (size_t)1 << (bits - 3), c->stream));
+  uint64_t blocks = (c->n_gk + 255) / 256, maxb = (uint64_t)c->num_sms * 16;
+  if (blocks > maxb) blocks = maxb;
+  k_bitmap_build<<<(unsigned)blocks, 256, 0, c->stream>>>(c->g_keys.as<uint64_t>(), c->n_gk, bits, c->bitmap.as<uint32_t>());
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  c->filter_bits = bits;
+}
+
+// returns the number of records written (== s.n_kmers without the filter)
+uint64_t extract_read_kmers_filtered(kslam_ctx *c, const PackedSeqs &s, Rec16 *out) {
+  if (!s.n_kmers) return 0;
+  unsigned long long *d_cnt = c->counters.as<unsigned long long>() + 2;
+  unsigned long long *h_cnt = c->h_counters.as<unsigned long long>() + 2;
+  CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 8, c->stream));
+  uint64_t blocks = (s.n * 32 + 255) / 256, maxb = (uint64_t)c->num_sms * 8;
+  if (blocks > maxb) blocks = maxb;
+  k_extract_reads_filtered<<<(unsigned)blocks, 256, 0, c->stream>>>(s.kbits.as<uint64_t>(), s.offs.as<uint64_t>(),
+      s.word_off.as<uint64_t>(), s.n, c->bitmap.as<uint32_t>(), c->filter_bits, out, d_cnt);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return h_cnt[0];
+}
+
 void extract_kmers(kslam_ctx *c, const PackedSeqs &s, bool is_gb, uint32_t gap, Rec16 *out) {
   if (!s.n_kmers) return;
   if (!is_gb && gap == 1) {

@@ -11,11 +11,9 @@
 //
 // Roofline: HBM. Algorithmic bytes per record = 32 B x passes (+16 B for the histogram read).
 #include "common.cuh"
+#include <stdlib.h>
 
-#define RS_THREADS 256
-#define RS_WARPS (RS_THREADS / 32)
-#define RS_IPT 16
-#define RS_TILE (RS_THREADS * RS_IPT)
+#define RS_TILE 4096        // records per tile (64 KB staged in shared memory)
 #define RS_MAX_PASSES 8
 
 #define RS_FLAG_AGG (1ull << 62)
@@ -69,12 +67,15 @@ k_rs_scan_hist(unsigned long long *__restrict__ ghist, uint32_t n_passes, uint64
 }
 
 // ---- one LSD pass ------------------------------------------------------------------------------
+template <int RS_THREADS, int RS_IPT>
 __global__ void __launch_bounds__(RS_THREADS, 2)
 k_rs_onesweep(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n, uint32_t shift, uint32_t mask,
               uint32_t word,                                       // 0: sort by .key, 1: sort by .val
               const unsigned long long *__restrict__ digit_base,  // [256] exclusive global offsets
               volatile unsigned long long *tile_state,            // [tiles][256], zero-initialised
               uint32_t *__restrict__ ticket) {
+  constexpr int RS_WARPS = RS_THREADS / 32;
+  static_assert(RS_THREADS * RS_IPT == RS_TILE, "tile shape");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Rec16 *stage = reinterpret_cast<Rec16 *>(smem_raw);                               // RS_TILE records
   uint32_t *whist = reinterpret_cast<uint32_t *>(smem_raw + RS_TILE * sizeof(Rec16)); // [RS_WARPS][256]
@@ -113,54 +114,56 @@ k_rs_onesweep(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n,
     uint32_t idx = wbase + i * 32 + lane;
     uint32_t d = idx < count ? ((uint32_t)((word ? val[i] : key[i]) >> shift) & mask) : 255u;
     uint32_t peers = __match_any_sync(0xffffffffu, d);
-    uint32_t leader = __ffs(peers) - 1;
-    uint32_t old = 0;
-    if (lane == leader) { old = myhist[d]; myhist[d] = old + __popc(peers); }
-    old = __shfl_sync(0xffffffffu, old, leader);
-    rank[i] = old + __popc(peers & lt_mask);
+    uint32_t old = myhist[d];                    // every peer reads the warp's running count (broadcast)
     __syncwarp();
+    if ((peers & lt_mask) == 0) myhist[d] = old + __popc(peers);   // lowest peer publishes the new count
+    __syncwarp();
+    rank[i] = old + __popc(peers & lt_mask);
   }
   __syncthreads();
 
-  // 3. thread d owns digit d: exclusive offsets over warps, tile count
+  // 3. thread d (< 256) owns digit d: exclusive offsets over warps, tile count
   uint32_t cnt_d = 0;
+  if (tid < 256) {
 #pragma unroll
-  for (int w = 0; w < RS_WARPS; w++) { uint32_t t = whist[w * 256 + tid]; whist[w * 256 + tid] = cnt_d; cnt_d += t; }
-  uint32_t real_d = cnt_d;
-  if (tid == 255) real_d -= (RS_TILE - count);   // padding records were counted in digit 255
+    for (int w = 0; w < RS_WARPS; w++) { uint32_t t = whist[w * 256 + tid]; whist[w * 256 + tid] = cnt_d; cnt_d += t; }
+    uint32_t real_d = cnt_d;
+    if (tid == 255) real_d -= (RS_TILE - count);   // padding records were counted in digit 255
 
-  // 4. publish, then look back for the exclusive prefix over earlier tiles
-  volatile unsigned long long *my_state = tile_state + tile * 256 + tid;
-  if (tile == 0) *my_state = RS_FLAG_INCL | real_d; else *my_state = RS_FLAG_AGG | real_d;
-  unsigned long long excl = 0;
-  if (tile > 0) {
-    for (int64_t t = (int64_t)tile - 1; t >= 0; t--) {
-      volatile unsigned long long *ps = tile_state + (uint64_t)t * 256 + tid;
-      unsigned long long s;
-      do { s = *ps; } while ((s >> 62) == 0);
-      excl += s & RS_VAL_MASK;
-      if ((s >> 62) == 2) break;
+    // 4. publish, then look back for the exclusive prefix over earlier tiles
+    volatile unsigned long long *my_state = tile_state + tile * 256 + tid;
+    if (tile == 0) *my_state = RS_FLAG_INCL | real_d; else *my_state = RS_FLAG_AGG | real_d;
+    unsigned long long excl = 0;
+    if (tile > 0) {
+      for (int64_t t = (int64_t)tile - 1; t >= 0; t--) {
+        volatile unsigned long long *ps = tile_state + (uint64_t)t * 256 + tid;
+        unsigned long long s;
+        do { s = *ps; } while ((s >> 62) == 0);
+        excl += s & RS_VAL_MASK;
+        if ((s >> 62) == 2) break;
+      }
+      *my_state = RS_FLAG_INCL | (excl + real_d);
     }
-    *my_state = RS_FLAG_INCL | (excl + real_d);
+    s_gbase[tid] = digit_base[tid] + excl;
   }
-  s_gbase[tid] = digit_base[tid] + excl;
 
   // 5. tile-local exclusive scan over digits (counts include padding so positions cover the tile)
-  {
+  if (tid < 256) {
     uint32_t inc = cnt_d;
 #pragma unroll
     for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, dlt); if (lane >= dlt) inc += t; }
     if (lane == 31) s_scan[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = lane < RS_WARPS ? s_scan[lane] : 0, winc = w;
-#pragma unroll
-      for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, winc, dlt); if (lane >= dlt) winc += t; }
-      s_scan[lane] = winc - w;
-    }
-    __syncthreads();
-    s_dexcl[tid] = s_scan[warp] + inc - cnt_d;
+    s_dexcl[tid] = inc - cnt_d;                  // exclusive within the owning warp (8 warps x 32 digits)
   }
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < 8 ? s_scan[lane] : 0, winc = w;
+#pragma unroll
+    for (int dlt = 1; dlt < 8; dlt <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, winc, dlt); if (lane >= dlt) winc += t; }
+    if (lane < 8) s_scan[lane] = winc - w;
+  }
+  __syncthreads();
+  if (tid < 256) s_dexcl[tid] += s_scan[warp];
   __syncthreads();
 
   // 6. stage in digit order
@@ -181,7 +184,17 @@ k_rs_onesweep(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n,
   }
 }
 
-static const size_t RS_SMEM = RS_TILE * sizeof(Rec16) + RS_WARPS * 256 * sizeof(uint32_t);
+template <int T, int I>
+static void launch_onesweep(kslam_ctx *c, uint64_t tiles, const Rec16 *in, Rec16 *out, uint64_t n, uint32_t shift, uint32_t mask,
+                            uint32_t word, const unsigned long long *base, unsigned long long *state, uint32_t *ticket) {
+  constexpr size_t smem = RS_TILE * sizeof(Rec16) + (T / 32) * 256 * sizeof(uint32_t);
+  static bool attr_set[64] = {false};
+  if (!(c->device < 64 && attr_set[c->device])) {
+    CUDA_TRY(cudaFuncSetAttribute(k_rs_onesweep<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (c->device < 64) attr_set[c->device] = true;
+  }
+  k_rs_onesweep<T, I><<<(unsigned)tiles, T, smem, c->stream>>>(in, out, n, shift, mask, word, base, state, ticket);
+}
 
 Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, uint32_t lo_bit, uint32_t hi_bit,
                   uint64_t *passes_done) {
@@ -190,11 +203,8 @@ Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, u
   cudaStream_t st = c->stream;
   // a wide key range is sorted in groups of <= 8 passes
   Rec16 *cur = a, *alt = b;
-  static bool attr_set[64] = {false};
-  if (!(c->device < 64 && attr_set[c->device])) {
-    CUDA_TRY(cudaFuncSetAttribute(k_rs_onesweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS_SMEM));
-    if (c->device < 64) attr_set[c->device] = true;
-  }
+  static int cfg = -1;
+  if (cfg < 0) { const char *e = getenv("KSLAM_RS_CFG"); cfg = e ? atoi(e) : 0; }
   PassPlan plan;
   plan.n_passes = 0;
   for (uint32_t s = lo_bit; s < hi_bit && plan.n_passes < RS_MAX_PASSES; s += 8) {
@@ -224,8 +234,8 @@ Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, u
   for (uint32_t p = 0; p < plan.n_passes; p++) {
     if (h_trivial[p]) continue;   // every record has the same digit: the pass would be the identity
     CUDA_TRY(cudaMemsetAsync(state, 0, tiles * 256 * 8, st));
-    k_rs_onesweep<<<(unsigned)tiles, RS_THREADS, RS_SMEM, st>>>(cur, alt, n, plan.shift[p], plan.mask[p], word,
-                                                                 ghist + p * 256, state, tickets + p);
+    if (cfg == 1) launch_onesweep<512, 8>(c, tiles, cur, alt, n, plan.shift[p], plan.mask[p], word, ghist + p * 256, state, tickets + p);
+    else launch_onesweep<256, 16>(c, tiles, cur, alt, n, plan.shift[p], plan.mask[p], word, ghist + p * 256, state, tickets + p);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     Rec16 *t = cur; cur = alt; alt = t;

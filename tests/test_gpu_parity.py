@@ -13,6 +13,13 @@ def canon(a):
     return np.sort(a, order=list(a.dtype.names))
 
 
+def rec_hash(r):
+    """64-bit fingerprint of a 16-byte k-mer record (set algebra on millions of records with np.isin)."""
+    with np.errstate(over="ignore"):
+        lo = r["id_flags"].astype(np.uint64) | (r["offset"].astype(np.uint64) << np.uint64(32))
+        return r["kmer"] * np.uint64(0x9E3779B97F4A7C15) ^ (lo + np.uint64(0x632BE59BD9B4E019)) * np.uint64(0xC2B2AE3D27D4EB4F)
+
+
 def check_overlaps(got, gpool, want, wpool, fields=FIELDS, cigars=True):
     assert len(got) == len(want)
     undefined = (want["flags"] & 1) != 0      # only where the ORACLE says the reference is undefined
@@ -26,9 +33,10 @@ def check_overlaps(got, gpool, want, wpool, fields=FIELDS, cigars=True):
         assert not bad, (len(bad), [(a[i], b[i]) for i in bad[:3]])
 
 
-def run_pipeline(pkg, gb, go, rb, ro, P):
+def run_pipeline(pkg, gb, go, rb, ro, P, prefilter=True):
     with pkg.Aligner(match=P.match, mismatch=P.mismatch, gap_open=P.gap_open, gap_extend=P.gap_extend,
                      score_threshold=P.score_threshold, report_cigar=bool(P.report_cigar)) as al:
+        al.set_prefilter(prefilter)
         al.load_genomes(gb, go)
         res = al.align_batch(rb, ro)
         taps = dict(genome_kmers=al.genome_kmers(), read_kmers=al.read_kmers(), raw_seeds=al.raw_seeds(), seeds=al.seeds())
@@ -38,16 +46,34 @@ def run_pipeline(pkg, gb, go, rb, ro, P):
 
 
 def check_pipeline(pkg, gb, go, rb, ro, P, want=None):
+    """Runs the CUDA path twice — prefilter off (every k-mer record is materialised, so K1/K2 can be compared
+    record for record) and on (the production setting) — and checks every stage of both against `want`."""
     want = want or T.ko_pipeline(gb, go, rb, ro, P)
-    res, taps, pairs, tm = run_pipeline(pkg, gb, go, rb, ro, P)
-    # K1/K2: genome list in the reference's order (kmer asc, id_flags desc); read list sorted by k-mer, same multiset
+    for prefilter in (False, True):
+        out = check_pipeline_mode(pkg, gb, go, rb, ro, P, want, prefilter)
+    return out
+
+
+def check_pipeline_mode(pkg, gb, go, rb, ro, P, want, prefilter):
+    res, taps, pairs, tm = run_pipeline(pkg, gb, go, rb, ro, P, prefilter)
+    # K1/K2: genome list in the reference's order (kmer asc, id_flags desc); read list sorted by k-mer
     wg = T.ko_sort_kmers(want["genome_kmers"])
     assert np.array_equal(taps["genome_kmers"]["kmer"], wg["kmer"])
     assert np.array_equal(taps["genome_kmers"]["id_flags"], wg["id_flags"])
     assert np.array_equal(canon(taps["genome_kmers"]), canon(wg))
     rk = taps["read_kmers"]
     assert (np.diff(rk["kmer"].astype(np.uint64)) >= 0).all() if len(rk) > 1 else True
-    assert np.array_equal(canon(rk), canon(want["read_kmers"]))
+    wr = want["read_kmers"]
+    if not prefilter:
+        assert np.array_equal(canon(rk), canon(wr))           # same multiset as KMer.h:160-181 produces
+    else:
+        # survivors: a subset of the reference's records that still holds every record able to seed
+        gset = np.unique(wg["kmer"][wg["kmer"] != 0])
+        must = wr[np.isin(wr["kmer"], gset)]
+        assert np.isin(rec_hash(rk), rec_hash(wr)).all()
+        assert np.isin(rec_hash(must), rec_hash(rk)).all()
+        assert len(np.unique(rec_hash(rk))) == len(rk)
+        assert tm["n_sorted_kmers"] == len(rk) <= tm["n_read_kmers"] == len(wr)
     # K3: raw seed multiset; K4: exact de-duplicated sequence
     assert np.array_equal(canon(taps["raw_seeds"]), canon(want["raw_seeds"]))
     assert np.array_equal(taps["seeds"], want["seeds"])
