@@ -66,9 +66,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summarise the samples that arrived inside [t_begin, t_end] (the timed region)."""
         if self.proc:
             self.proc.terminate()
             try:
@@ -77,7 +78,10 @@ class ClockSampler:
                 self.proc.kill()
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for t, r in self.rows if (t_begin is None or t >= t_begin) and (t_end is None or t <= t_end + 0.05)]
+        if not rows:   # region shorter than one sampling period: fall back to the samples taken under warm-up load
+            rows = [r for _, r in self.rows[-5:]]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -140,7 +144,7 @@ def run_reference_arm(args, pkg):
     if rank != 0:
         return
     pairs = args.pairs or DEFAULT_PAIRS[args.workload]
-    sample = args.ref_sample
+    sample = args.ref_sample or CPU_SAMPLE[args.workload]
     gb, go, _, _, desc = make_workload(pkg, args.workload, 1000)
     vals = []
     for i in range(args.warmup + args.steps):
@@ -160,6 +164,8 @@ def run_reference_arm(args, pkg):
 
 
 DEFAULT_PAIRS = {"config1": 1_000_000, "config2": 10_000_000}
+# bounded CPU samples (pairs): sized for roughly 10-20 s of host work per step on a 16-core box
+CPU_SAMPLE = {"config1": 400_000, "config2": 150_000}
 
 
 def main():
@@ -170,8 +176,8 @@ def main():
     ap.add_argument("--impl", default="kslam", choices=["kslam", "reference"])
     ap.add_argument("--workload", default=os.environ.get("KSLAM_BENCH_WORKLOAD", "config2"), choices=["config1", "config2"])
     ap.add_argument("--pairs", type=int, default=0, help="read pairs per batch per GPU (default: the config's)")
-    ap.add_argument("--ref-sample", type=int, default=20_000, help="pairs per step for the CPU reference arm")
-    ap.add_argument("--cpu-sample", type=int, default=20_000, help="pairs for the cpu_baseline leg (rank 0, N=1)")
+    ap.add_argument("--ref-sample", type=int, default=0, help="pairs per step for the CPU reference arm (0 = per workload)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="pairs for the cpu_baseline leg (rank 0, N=1; 0 = per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -208,15 +214,15 @@ def main():
 
     # ---- value: inputs resident in HBM -------------------------------------------------------
     al.upload_reads(rb_host, ro)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         al.align_resident(fetch=False); al.pair_batch(fetch=False)
     launches0 = al.timings()["kernel_launches"]
-    sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
-        sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.perf_counter()
+    tw_first = tw0
     stage = {}
     for _ in range(args.steps):
         al.align_resident(fetch=False); al.pair_batch(fetch=False)
@@ -225,8 +231,8 @@ def main():
             if k.startswith("ms_"):
                 stage[k] = stage.get(k, 0.0) + v
     barrier()
-    t_res = time.perf_counter() - tw0          # library calls are synchronous: wall == device time of the chain
-    clocks = sampler.stop() if rank == 0 else None
+    tw1 = time.perf_counter()
+    t_res = tw1 - tw0                           # library calls are synchronous: wall == device time of the chain
     tm = al.timings()
     launches = (tm["kernel_launches"] - launches0) // max(1, args.steps)
 
@@ -238,7 +244,9 @@ def main():
     for _ in range(args.steps):
         res = al.align_batch(rb_host, ro, copy=False); pr = al.pair_batch(fetch=True, copy=False)
     barrier()
-    t_e2e = time.perf_counter() - tw0
+    tw3 = time.perf_counter()
+    t_e2e = tw3 - tw0
+    clocks = sampler.stop(tw_first, tw3) if rank == 0 else None
     h2d = int(rb_host.nbytes + 3 * ro.nbytes)
     d2h = int(res.overlaps.nbytes + pr.sorted_overlaps.nbytes + pr.pairs.nbytes)
 
@@ -282,9 +290,10 @@ def main():
                                              "n_sw_slow", "sw_cells_forward", "sw_cells_reverse", "n_sort_passes")},
                "genome_index_build_s": t_load}
         if world == 1 and not args.no_cpu_baseline:
-            v, dt, cores, kind = cpu_reference_sample(pkg, gb, go, args.cpu_sample, False, 0)
+            cs = args.cpu_sample or CPU_SAMPLE[args.workload]
+            v, dt, cores, kind = cpu_reference_sample(pkg, gb, go, cs, False, 0)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-                                   "sample": f"{args.cpu_sample} pairs of the same workload in {dt:.1f}s (alignToDatabase+screen+getPairedOverlaps, genome k-mers re-extracted and re-sorted per batch as the reference does)"}
+                                   "sample": f"{cs} pairs of the same workload in {dt:.1f}s (alignToDatabase+screen+getPairedOverlaps, genome k-mers re-extracted and re-sorted per batch as the reference does)"}
         print(json.dumps(out), flush=True)
     al.close()
     if world > 1:

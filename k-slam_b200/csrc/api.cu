@@ -100,7 +100,7 @@ void kslam_destroy(kslam_ctx *c) {
                     &c->raw_seeds, &c->seedA, &c->seedB, &c->seed_keep, &c->seeds, &c->ov, &c->cig, &c->pair_keys,
                     &c->pair_keys2, &c->ov_sorted, &c->cig_sorted, &c->pair_cnt, &c->pairs, &c->bitmap};
   for (DevBuf *b : bufs) b->release();
-  HostBuf *hb[] = {&c->h_counters, &c->h_ov, &c->h_cig, &c->h_ov_sorted, &c->h_cig_sorted, &c->h_pairs};
+  HostBuf *hb[] = {&c->h_stage, &c->h_counters, &c->h_ov, &c->h_cig, &c->h_ov_sorted, &c->h_cig_sorted, &c->h_pairs};
   for (HostBuf *b : hb) b->release();
   sw_workspace_free(c);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -239,7 +239,7 @@ int kslam_upload_reads(kslam_ctx *c, uint64_t n, const char *bases, const uint64
   c->reads_loaded = false; c->aligned = false;
   c->ev_used = 0;
   cudaEvent_t e0 = tm_mark(c);
-  pack_sequences(c, c->reads, n, bases, offs, 1, false);
+  pack_sequences(c, c->reads, n, bases, offs, 1, true);
   cudaEvent_t e1 = tm_mark(c);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->tm.ms_h2d = 0; c->tm.ms_pack = tm_ms(e0, e1);   // copy + pack (the copy is inside pack_sequences)
@@ -306,8 +306,8 @@ int kslam_ssw_upload(kslam_ctx *c, uint64_t n, const char *q, const uint64_t *qo
   if (!qoffs || !roffs) return fail(c, KSLAM_ERR_ARG, "null offsets");
   if (n >= (1ull << 31)) return fail(c, KSLAM_ERR_ARG, "too many pairs");
   c->sw_loaded = false;
-  pack_sequences(c, c->swq, n, q, qoffs, 1, false);
-  pack_sequences(c, c->swr, n, r, roffs, 1, false);
+  pack_sequences(c, c->swq, n, q, qoffs, 1, true);
+  pack_sequences(c, c->swr, n, r, roffs, 1, true);
   c->sw_loaded = true;
   return KSLAM_OK;
   API_END(c)

@@ -72,7 +72,6 @@ struct PackedSeqs {
   DevBuf kmer_off;         // u64 n+1: first k-mer record index of each sequence
   uint64_t n_kmers = 0;
   uint32_t max_len = 0;
-  std::vector<uint64_t> h_offs;  // host copy of raw offsets
   void release() { raw.release(); offs.release(); word_off.release(); kbits.release(); sbits.release();
                    nmask.release(); xmask.release(); kmer_off.release(); }
 };
@@ -102,6 +101,8 @@ struct kslam_ctx {
   DevBuf scan_tmp;
   DevBuf counters;          // small u64 counter block
   HostBuf h_counters;
+  HostBuf h_stage;          // pinned staging for ragged-batch offset tables
+  bool keep_raw_reads = true;  // keep the raw-byte device buffer between batches (avoids a cudaMalloc per batch)
   uint64_t n_rk = 0;        // read k-mer records
   Rec16 *sorted_rk = nullptr;  // points into recA/recB
 

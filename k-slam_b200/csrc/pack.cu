@@ -66,35 +66,56 @@ k_pack(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ offs,
   }
 }
 
+// offsets of a batch in which every sequence has the same length: generated on the device, nothing to upload
+__global__ void __launch_bounds__(256)
+k_uniform_offsets(uint64_t n, uint64_t len, uint64_t wpl, uint64_t kpl, uint64_t *__restrict__ offs,
+                  uint64_t *__restrict__ word_off, uint64_t *__restrict__ kmer_off) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x) {
+    offs[i] = i * len; word_off[i] = i * wpl; kmer_off[i] = i * kpl;
+  }
+}
+
 void pack_sequences(kslam_ctx *c, PackedSeqs &s, uint64_t n, const char *bases, const uint64_t *offs,
                     uint32_t kmer_gap, bool keep_raw) {
   ensure_tables(c->device);
+  cudaStream_t st = c->stream;
   s.n = n;
-  s.h_offs.assign(offs, offs + n + 1);
   s.n_bases = offs[n] - offs[0];
-  std::vector<uint64_t> wo(n + 1), ko(n + 1);
-  uint64_t w = 0, k = 0; uint32_t max_len = 0;
-  for (uint64_t i = 0; i < n; i++) {
-    uint64_t len = offs[i + 1] - offs[i];
-    wo[i] = w; ko[i] = k;
-    w += (len + 31) / 32;
-    if (len >= KSLAM_K) k += (len - KSLAM_K) / kmer_gap + 1;  // KMer.h:202
-    if (len > max_len) max_len = (uint32_t)(len > 0xffffffffull ? 0xffffffffull : len);
-  }
-  wo[n] = w; ko[n] = k;
-  s.n_words = w; s.n_kmers = k; s.max_len = max_len;
-  // rebase raw offsets to 0
-  std::vector<uint64_t> ro(n + 1);
-  for (uint64_t i = 0; i <= n; i++) ro[i] = offs[i] - offs[0];
-  s.raw.reserve(s.n_bases + 16);
+  // one pass over the offsets: uniform-length batches (the usual FASTQ case) need no per-sequence tables from the host
+  const uint64_t len0 = n ? offs[1] - offs[0] : 0;
+  bool uniform = n > 0;
+  for (uint64_t i = 0; i < n && uniform; i++) uniform = (offs[i + 1] - offs[i]) == len0;
   s.offs.reserve((n + 1) * 8); s.word_off.reserve((n + 1) * 8); s.kmer_off.reserve((n + 1) * 8);
+  uint64_t w = 0, k = 0; uint32_t max_len = 0;
+  if (uniform) {
+    const uint64_t wpl = (len0 + 31) / 32, kpl = len0 >= KSLAM_K ? (len0 - KSLAM_K) / kmer_gap + 1 : 0;
+    w = wpl * n; k = kpl * n; max_len = (uint32_t)len0;
+    uint64_t blocks = (n + 256) / 256, maxb = (uint64_t)c->num_sms * 8;
+    if (blocks > maxb) blocks = maxb;
+    k_uniform_offsets<<<(unsigned)blocks, 256, 0, st>>>(n, len0, wpl, kpl, s.offs.as<uint64_t>(), s.word_off.as<uint64_t>(),
+                                                        s.kmer_off.as<uint64_t>());
+    c->launches++;
+  } else {
+    // ragged batch: build the three tables in pinned staging memory owned by the ctx, then copy asynchronously
+    c->h_stage.reserve((n + 1) * 24);
+    uint64_t *ro = c->h_stage.as<uint64_t>(), *wo = ro + (n + 1), *ko = wo + (n + 1);
+    for (uint64_t i = 0; i < n; i++) {
+      uint64_t len = offs[i + 1] - offs[i];
+      ro[i] = offs[i] - offs[0]; wo[i] = w; ko[i] = k;
+      w += (len + 31) / 32;
+      if (len >= KSLAM_K) k += (len - KSLAM_K) / kmer_gap + 1;  // KMer.h:202
+      if (len > max_len) max_len = (uint32_t)(len > 0xffffffffull ? 0xffffffffull : len);
+    }
+    ro[n] = offs[n] - offs[0]; wo[n] = w; ko[n] = k;
+    CUDA_TRY(cudaMemcpyAsync(s.offs.p, ro, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s.word_off.p, wo, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s.kmer_off.p, ko, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  }
+  s.n_words = w; s.n_kmers = k; s.max_len = max_len;
+  s.raw.reserve(s.n_bases + 16);
   s.kbits.reserve((w + 2) * 8); s.sbits.reserve((w + 2) * 8); s.nmask.reserve((w + 2) * 4);
   s.xmask.reserve((w + 2) * 4);
-  cudaStream_t st = c->stream;
   if (s.n_bases) CUDA_TRY(cudaMemcpyAsync(s.raw.p, bases + offs[0], s.n_bases, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(s.offs.p, ro.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(s.word_off.p, wo.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaMemcpyAsync(s.kmer_off.p, ko.data(), (n + 1) * 8, cudaMemcpyHostToDevice, st));
   // two guard words past the end so funnel shifts / window gathers may read one word ahead
   CUDA_TRY(cudaMemsetAsync((char *)s.kbits.p + w * 8, 0, 16, st));
   CUDA_TRY(cudaMemsetAsync((char *)s.sbits.p + w * 8, 0, 16, st));
@@ -110,7 +131,7 @@ void pack_sequences(kslam_ctx *c, PackedSeqs &s, uint64_t n, const char *bases, 
     c->launches++;
     CUDA_TRY(cudaGetLastError());
   }
-  // the host staging vectors (ro/wo/ko) must outlive the async copies
+  // the caller's buffers and the pinned staging tables must stay untouched until the copies have landed
   CUDA_TRY(cudaStreamSynchronize(st));
-  if (!keep_raw) s.raw.release();
+  if (!keep_raw) s.raw.release();   // genomes: bytes are not needed again; reads: keep the allocation for the next batch
 }
