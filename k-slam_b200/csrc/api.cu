@@ -114,6 +114,12 @@ int kslam_set_prefilter(kslam_ctx *ctx, int on) {
   return KSLAM_OK;
 }
 
+int kslam_set_sw_band(kslam_ctx *ctx, int on) {
+  if (!ctx) return KSLAM_ERR_ARG;
+  ctx->sw_band = on != 0;
+  return KSLAM_OK;
+}
+
 int kslam_set_debug_taps(kslam_ctx *ctx, int keep) {
   if (!ctx) return KSLAM_ERR_ARG;
   ctx->keep_taps = keep != 0;

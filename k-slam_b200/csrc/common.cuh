@@ -94,6 +94,7 @@ struct kslam_ctx {
   DevBuf bitmap;   // prefilter: 2^filter_bits bits over hashed genome k-mers (kmer.cu)
   uint32_t filter_bits = 0;
   bool prefilter = true;
+  bool sw_band = true;     // banded SW kernel with exactness proof + full-matrix fallback (sw_band.cuh)
   uint32_t max_genome_len = 0;
 
   DevBuf recA, recB;        // Rec16 ping-pong (read k-mers, then seeds)

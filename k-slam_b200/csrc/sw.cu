@@ -38,6 +38,7 @@ struct __align__(16) SwTask {
   uint32_t flags;    // bit0: window is reverse-complemented; bits 8-15: class
 };
 #define SWT_REV 1u
+#define SWT_BAND 2u   // shape allows the banded kernel (rows <= 160, no code-4 base in the window)
 #define SWC_FAST8 0u
 #define SWC_SLOW 3u
 #define SWC_NONE 4u   // empty query or window: score 0, nothing to run
@@ -58,7 +59,7 @@ struct SwScore {
 };
 
 struct SwWorkspace {
-  DevBuf tasks, res, keys, keys2, items, tb_scratch;
+  DevBuf tasks, res, keys, keys2, items, lists, tb_scratch;
   uint64_t n = 0;
 };
 
@@ -89,7 +90,9 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return d;
 }
 
-// ---------------------------------------------------------------- fast kernel
+#include "sw_band.cuh"
+
+// ---------------------------------------------------------------- fast (full-matrix) kernel
 template <int LANES, bool REVERSE>
 __global__ void __launch_bounds__(SW_BLOCK, 4)
 k_sw_fast(const SwTask *__restrict__ tasks, const uint2 *__restrict__ items, uint32_t n_items, SwPlanes pl,
@@ -448,22 +451,54 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
   }
 }
 
-// ---------------------------------------------------------------- task preparation and bucketing
+// ---------------------------------------------------------------- task preparation and work lists
+// counters (u32) in c->counters + 32: [0] band list, [1] full-kernel keys, [2] slow list, [3] band fallbacks,
+// [4] traceback retries, [5] make_items extras
+#define CNT_BAND 0
+#define CNT_FULL 1
+#define CNT_SLOW 2
+#define CNT_RETRY 4
+#define CNT_EXTRA 5
+
 __device__ __forceinline__ uint32_t classify(uint32_t m, uint32_t n, const SwScore &sc) {
   if (m == 0 || n == 0) return SWC_NONE;
   const uint32_t mn = m < n ? m : n;
-  const bool score_ok = sc.match * 32 <= 127 && sc.mismatch * 32 <= 128 && (uint32_t)sc.match * mn <= 1000u &&
+  const bool score_ok = sc.match >= 1 && sc.match * 32 <= 127 && sc.mismatch * 32 <= 128 && (uint32_t)sc.match * mn <= 1000u &&
                         sc.gap_open * 32 <= 30000 && sc.gap_extend * 32 <= 30000;
   if (score_ok && m <= 8 * SW_R && n <= SW_MAXCOLS) return SWC_FAST8;
   return SWC_SLOW;
+}
+
+// true when no base of the window [w_start, w_start + n) has SSW code 4
+__device__ __forceinline__ bool window_clean(const uint32_t *__restrict__ nmask, uint64_t w_word, uint32_t w_start, uint32_t n) {
+  const uint32_t first = w_start >> 5, last = (w_start + n - 1) >> 5;
+  for (uint32_t w = first; w <= last; w++) {
+    uint32_t m = __ldg(&nmask[w_word + w]);
+    if (w == first) m &= 0xffffffffu << (w_start & 31);
+    if (w == last) { const uint32_t e = (w_start + n - 1) & 31; if (e < 31) m &= (2u << e) - 1u; }
+    if (m) return false;
+  }
+  return true;
+}
+
+__device__ __forceinline__ void enlist(const SwTask &t, uint32_t i, uint32_t cls, SwRes *__restrict__ res,
+                                       uint32_t *__restrict__ band_list, Rec16 *__restrict__ full_keys,
+                                       uint32_t *__restrict__ slow_list, uint32_t *__restrict__ counts) {
+  if (cls == SWC_NONE) {
+    SwRes o; o.score = 0; o.ref_end = -1; o.read_end = 0; o.ref_begin = -1; o.read_begin = 0; o.flags = 0; o.pad0 = o.pad1 = 0;
+    res[i] = o;
+  } else if (cls == SWC_SLOW) slow_list[atomicAdd(&counts[CNT_SLOW], 1u)] = i;
+  else if (t.flags & SWT_BAND) band_list[atomicAdd(&counts[CNT_BAND], 1u)] = i;
+  else { const uint32_t k = atomicAdd(&counts[CNT_FULL], 1u); full_keys[k].key = t.n; full_keys[k].val = i; }
 }
 
 // pipeline mode: one task per seed (SmithWaterman.h:199-211)
 __global__ void __launch_bounds__(256)
 k_sw_prepare_seeds(const kslam_seed *__restrict__ seeds, uint32_t n, const uint64_t *__restrict__ r_offs,
                    const uint64_t *__restrict__ r_word, const uint64_t *__restrict__ g_offs,
-                   const uint64_t *__restrict__ g_word, SwScore sc, SwTask *__restrict__ tasks,
-                   Rec16 *__restrict__ keys, uint32_t *__restrict__ counts) {
+                   const uint64_t *__restrict__ g_word, const uint32_t *__restrict__ g_nmask, SwScore sc, uint32_t use_band,
+                   SwTask *__restrict__ tasks, SwRes *__restrict__ res, uint32_t *__restrict__ band_list,
+                   Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list, uint32_t *__restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const kslam_seed s = seeds[i];
@@ -475,16 +510,19 @@ k_sw_prepare_seeds(const kslam_seed *__restrict__ seeds, uint32_t n, const uint6
   t.m = (uint32_t)qlen; t.n = (uint32_t)wlen; t.w_start = (uint32_t)start;
   const uint32_t cls = classify(t.m, t.n, sc);
   t.flags = (s.rev_comp ? SWT_REV : 0u) | (cls << 8);
+  if (use_band && cls == SWC_FAST8 && t.m <= SWB_MAXROWS && window_clean(g_nmask, t.w_word, t.w_start, t.n)) t.flags |= SWT_BAND;
   tasks[i] = t;
-  keys[i].key = ((uint64_t)cls << 32) | t.n; keys[i].val = i;
-  atomicAdd(&counts[cls], 1u);
+  enlist(t, i, cls, res, band_list, full_keys, slow_list, counts);
 }
 
 // Aligner::Align batch mode: query i against ref i, whole sequences
 __global__ void __launch_bounds__(256)
 k_sw_prepare_pairs(uint32_t n, const uint64_t *__restrict__ q_offs, const uint64_t *__restrict__ q_word,
-                   const uint64_t *__restrict__ r_offs, const uint64_t *__restrict__ r_word, SwScore sc,
-                   SwTask *__restrict__ tasks, Rec16 *__restrict__ keys, uint32_t *__restrict__ counts) {
+                   const uint64_t *__restrict__ r_offs, const uint64_t *__restrict__ r_word,
+                   const uint32_t *__restrict__ r_nmask, SwScore sc, uint32_t use_band, SwTask *__restrict__ tasks,
+                   SwRes *__restrict__ res,
+                   uint32_t *__restrict__ band_list, Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list,
+                   uint32_t *__restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   SwTask t;
@@ -492,28 +530,30 @@ k_sw_prepare_pairs(uint32_t n, const uint64_t *__restrict__ q_offs, const uint64
   t.m = (uint32_t)(q_offs[i + 1] - q_offs[i]); t.n = (uint32_t)(r_offs[i + 1] - r_offs[i]); t.w_start = 0;
   const uint32_t cls = classify(t.m, t.n, sc);
   t.flags = cls << 8;
+  if (use_band && cls == SWC_FAST8 && t.m <= SWB_MAXROWS && window_clean(r_nmask, t.w_word, 0, t.n)) t.flags |= SWT_BAND;
   tasks[i] = t;
-  keys[i].key = ((uint64_t)cls << 32) | t.n; keys[i].val = i;
-  atomicAdd(&counts[cls], 1u);
+  enlist(t, i, cls, res, band_list, full_keys, slow_list, counts);
 }
 
-// keys for the reverse pass: bucket by the number of columns it sweeps (ref_end + 1); alignments with
-// score 0 have no reverse pass (ssw.c:903 is reached with an empty range)
+// reverse pass work lists: score 0 has no reverse pass (ssw.c:903 is reached with an empty range). The band holds
+// every alignment that scores S when rows + cols - 2 * ceil(S / match) + 1 <= 32 (sw_band.cuh).
 __global__ void __launch_bounds__(256)
-k_sw_rev_keys(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, uint32_t n, Rec16 *__restrict__ keys,
-              uint32_t *__restrict__ counts) {
+k_sw_rev_lists(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, uint32_t n, SwScore sc,
+               uint32_t *__restrict__ band_list, Rec16 *__restrict__ full_keys, uint32_t *__restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t cls = (tasks[i].flags >> 8) & 0xffu;
-  const bool run = cls == SWC_FAST8 && res[i].score > 0;
-  keys[i].key = run ? (uint64_t)(res[i].ref_end + 1) : (1ull << 40);
-  keys[i].val = i;
-  if (run) atomicAdd(&counts[8], 1u);
+  const SwTask t = tasks[i];
+  if (((t.flags >> 8) & 0xffu) != SWC_FAST8) return;
+  const SwRes r = res[i];
+  if (r.score <= 0) return;
+  const int32_t rows = r.read_end + 1, cols = r.ref_end + 1, a = ceil_div_pos(r.score, sc.match);
+  if ((t.flags & SWT_BAND) && rows + cols - 2 * a + 1 <= SWB_W) band_list[atomicAdd(&counts[CNT_BAND], 1u)] = i;
+  else { const uint32_t k = atomicAdd(&counts[CNT_FULL], 1u); full_keys[k].key = (uint64_t)cols; full_keys[k].val = i; }
 }
 
-// sorted (by class, columns) task ids -> work items: two alignments with the same column count share a group.
-// Item w < W = ceil(n/2) is dense; the second member of an unequal neighbour pair becomes a single item appended
-// after W through an atomic counter (slots [W, 2W) are pre-filled with SW_INVALID and exit immediately).
+// sorted (by columns) task ids -> work items of the full-matrix kernel: two alignments with the same column count
+// share a group. Item w < W = ceil(n/2) is dense; the second member of an unequal neighbour pair becomes a single
+// item appended after W through an atomic counter (slots [W, 2W) are pre-filled with SW_INVALID and exit at once).
 __global__ void __launch_bounds__(256)
 k_sw_make_items(const Rec16 *__restrict__ sorted, uint32_t n_fast, uint2 *__restrict__ items, uint32_t *__restrict__ extra) {
   const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -527,22 +567,6 @@ k_sw_make_items(const Rec16 *__restrict__ sorted, uint32_t n_fast, uint2 *__rest
     else items[W + atomicAdd(extra, 1u)] = make_uint2((uint32_t)b.val, (uint32_t)b.val);
   }
   items[w] = i0;
-}
-
-__global__ void __launch_bounds__(256)
-k_sw_list(const Rec16 *__restrict__ sorted, uint32_t first, uint32_t count, uint32_t *__restrict__ list) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) list[i] = (uint32_t)sorted[first + i].val;
-}
-
-__global__ void __launch_bounds__(256)
-k_sw_none(const SwTask *__restrict__ tasks, uint32_t n, SwRes *__restrict__ res) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (((tasks[i].flags >> 8) & 0xffu) == SWC_NONE) {
-    SwRes o; o.score = 0; o.ref_end = -1; o.read_end = 0; o.ref_begin = -1; o.read_begin = 0; o.flags = 0; o.pad0 = o.pad1 = 0;
-    res[i] = o;
-  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -564,89 +588,101 @@ static SwScore make_score(const kslam_ctx *c) {
   return s;
 }
 
+static uint32_t read_count(kslam_ctx *c, uint32_t *d_counts, uint32_t *h_counts, int which) {
+  CUDA_TRY(cudaMemcpyAsync(h_counts + which, d_counts + which, 4, cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return h_counts[which];
+}
+
+// one direction (forward or reverse) over the prepared lists: banded kernel first, its fallbacks join the
+// full-matrix list, which is bucketed by column count and run by k_sw_fast
+template <bool REVERSE>
+static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore &sc, uint32_t n_band, uint32_t *d_counts,
+                    uint32_t *h_counts, uint64_t *n_band_done, uint64_t *n_full_done) {
+  SwWorkspace *w = c->sw;
+  cudaStream_t st = c->stream;
+  SwTask *tasks = w->tasks.as<SwTask>();
+  SwRes *res = w->res.as<SwRes>();
+  uint32_t *band_list = w->lists.as<uint32_t>();
+  Rec16 *keys = w->keys.as<Rec16>(), *keys2 = w->keys2.as<Rec16>();
+  if (n_band) {
+    const uint32_t pairs = (n_band + 1) / 2;
+    const size_t smem = (size_t)2 * SWB_COLS * SWB_BLOCK;
+    k_sw_band<REVERSE><<<(pairs + SWB_BLOCK - 1) / SWB_BLOCK, SWB_BLOCK, smem, st>>>(tasks, band_list, n_band, pl, sc, res, keys,
+                                                                                        d_counts + CNT_FULL);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  const uint32_t n_full = read_count(c, d_counts, h_counts, CNT_FULL);
+  *n_band_done += n_band; *n_full_done += n_full;
+  if (n_full) {
+    uint64_t passes = 0;
+    Rec16 *sorted = radix_sort(c, keys, keys2, n_full, 0, 0, 16, &passes);
+    uint2 *items = w->items.as<uint2>();
+    const uint32_t n_items = 2 * ((n_full + 1) / 2);
+    CUDA_TRY(cudaMemsetAsync(items, 0xff, (size_t)n_items * sizeof(uint2), st));
+    CUDA_TRY(cudaMemsetAsync(d_counts + CNT_EXTRA, 0, 4, st));
+    k_sw_make_items<<<(n_items / 2 + 255) / 256, 256, 0, st>>>(sorted, n_full, items, d_counts + CNT_EXTRA);
+    constexpr int GROUPS = SW_BLOCK / 8;
+    k_sw_fast<8, REVERSE><<<(n_items + GROUPS - 1) / GROUPS, SW_BLOCK, 0, st>>>(tasks, items, n_items, pl, sc, res);
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+  }
+}
+
 static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *ov, uint32_t *cig, int unflip) {
   SwWorkspace *w = c->sw;
   cudaStream_t st = c->stream;
   const SwScore sc = make_score(c);
   SwTask *tasks = w->tasks.as<SwTask>();
   SwRes *res = w->res.as<SwRes>();
-  Rec16 *keys = w->keys.as<Rec16>(), *keys2 = w->keys2.as<Rec16>();
   uint32_t *d_counts = c->counters.as<uint32_t>() + 32;      // 16 u32 counters
   uint32_t *h_counts = c->h_counters.as<uint32_t>() + 32;
   const unsigned nb = (n + 255) / 256;
+  uint32_t *band_list = w->lists.as<uint32_t>(), *slow_list = band_list + n;
 
-  cudaEvent_t e0 = tm_mark(c);
+  // ---- forward
+  cudaEvent_t e1 = tm_mark(c);
   CUDA_TRY(cudaMemcpyAsync(h_counts, d_counts, 64, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  const uint32_t n_fast = h_counts[SWC_FAST8], n_slow = h_counts[SWC_SLOW];
-  c->tm.n_sw_fast = n_fast; c->tm.n_sw_slow = n_slow;
-  // bucket by (class, columns): class is the high word so fast tasks come first
-  uint64_t passes = 0;
-  Rec16 *sorted = radix_sort(c, keys, keys2, n, 0, 0, 40, &passes);
-  Rec16 *other = sorted == keys ? keys2 : keys;
-  k_sw_none<<<nb, 256, 0, st>>>(tasks, n, res);
-  c->launches++;
-  cudaEvent_t e1 = tm_mark(c);
-  uint2 *items = w->items.as<uint2>();
-  if (n_fast) {
-    const uint32_t n_items = 2 * ((n_fast + 1) / 2);
-    CUDA_TRY(cudaMemsetAsync(items, 0xff, (size_t)n_items * sizeof(uint2), st));
-    CUDA_TRY(cudaMemsetAsync(d_counts + 10, 0, 4, st));
-    k_sw_make_items<<<(n_items / 2 + 255) / 256, 256, 0, st>>>(sorted, n_fast, items, d_counts + 10);
-    constexpr int GROUPS = SW_BLOCK / 8;
-    k_sw_fast<8, false><<<(n_items + GROUPS - 1) / GROUPS, SW_BLOCK, 0, st>>>(tasks, items, n_items, pl, sc, res);
-    c->launches += 2;
-    CUDA_TRY(cudaGetLastError());
-  }
+  uint32_t n_band = h_counts[CNT_BAND];
+  const uint32_t n_slow = h_counts[CNT_SLOW];
+  uint64_t band_done = 0, full_done = 0;
+  sw_pass<false>(c, n, pl, sc, n_band, d_counts, h_counts, &band_done, &full_done);
+  c->tm.n_sw_fast = full_done; c->tm.n_sw_band = band_done; c->tm.n_sw_slow = n_slow;
   cudaEvent_t e2 = tm_mark(c);
-  if (n_fast) {
-    CUDA_TRY(cudaMemsetAsync(d_counts + 8, 0, 4, st));
-    k_sw_rev_keys<<<nb, 256, 0, st>>>(tasks, res, n, other, d_counts);
-    c->launches++;
-    CUDA_TRY(cudaMemcpyAsync(h_counts + 8, d_counts + 8, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    const uint32_t n_rev = h_counts[8];
-    // `sorted` (forward buckets) is still needed for the slow list: sort the reverse keys in a third buffer pair
-    w->items.reserve((size_t)(2 * ((n + 1) / 2)) * sizeof(uint2) + (size_t)n * sizeof(Rec16) + 64);
-    items = w->items.as<uint2>();
-    Rec16 *tmp = reinterpret_cast<Rec16 *>(reinterpret_cast<char *>(items) + (size_t)(2 * ((n + 1) / 2)) * sizeof(uint2));
-    Rec16 *rs = radix_sort(c, other, tmp, n, 0, 0, 41, &passes);
-    if (n_rev) {
-      const uint32_t n_items = 2 * ((n_rev + 1) / 2);
-      CUDA_TRY(cudaMemsetAsync(items, 0xff, (size_t)n_items * sizeof(uint2), st));
-      CUDA_TRY(cudaMemsetAsync(d_counts + 10, 0, 4, st));
-      k_sw_make_items<<<(n_items / 2 + 255) / 256, 256, 0, st>>>(rs, n_rev, items, d_counts + 10);
-      constexpr int GROUPS = SW_BLOCK / 8;
-      k_sw_fast<8, true><<<(n_items + GROUPS - 1) / GROUPS, SW_BLOCK, 0, st>>>(tasks, items, n_items, pl, sc, res);
-      c->launches += 2;
-      CUDA_TRY(cudaGetLastError());
-    }
-  }
+
+  // ---- reverse
+  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_BAND, 0, 8, st));   // band + full counters
+  k_sw_rev_lists<<<nb, 256, 0, st>>>(tasks, res, n, sc, band_list, w->keys.as<Rec16>(), d_counts);
+  c->launches++;
+  n_band = read_count(c, d_counts, h_counts, CNT_BAND);
+  uint64_t band_rev = 0, full_rev = 0;
+  sw_pass<true>(c, n, pl, sc, n_band, d_counts, h_counts, &band_rev, &full_rev);
+  c->tm.n_sw_band_rev = band_rev;
   cudaEvent_t e3 = tm_mark(c);
+
+  // ---- exact scalar fallback for shapes outside the fast kernels
   if (n_slow) {
-    uint32_t *list = reinterpret_cast<uint32_t *>(w->items.p);
-    k_sw_list<<<(n_slow + 255) / 256, 256, 0, st>>>(sorted, n_fast, n_slow, list);
     uint32_t max_rows = c->reads_loaded ? c->reads.max_len : 0;
     if (c->sw_loaded && c->swq.max_len > max_rows) max_rows = c->swq.max_len;
     uint32_t blocks = (n_slow + 127) / 128; if (blocks > (uint32_t)c->num_sms * 4) blocks = c->num_sms * 4;
     w->tb_scratch.reserve((size_t)blocks * 128 * max_rows * 8 + 64);
-    k_sw_slow<<<blocks, 128, 0, st>>>(tasks, list, n_slow, pl, sc, res, w->tb_scratch.as<int32_t>(), max_rows);
-    c->launches += 2;
+    k_sw_slow<<<blocks, 128, 0, st>>>(tasks, slow_list, n_slow, pl, sc, res, w->tb_scratch.as<int32_t>(), max_rows);
+    c->launches++;
     CUDA_TRY(cudaGetLastError());
   }
   cudaEvent_t e4 = tm_mark(c);
   {
     // traceback + finalize
-    uint32_t *retry_count = d_counts + 9;
+    uint32_t *retry_count = d_counts + CNT_RETRY;
     CUDA_TRY(cudaMemsetAsync(retry_count, 0, 4, st));
     uint32_t *retry_list = reinterpret_cast<uint32_t *>(w->keys.p);   // keys are dead by now
     uint32_t blocks = (n + 127) / 128;
     k_sw_traceback<<<blocks, 128, 0, st>>>(tasks, res, n, nullptr, pl, sc, ov, cig, unflip, 0, retry_list, retry_count, nullptr, 0);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(h_counts + 9, retry_count, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    const uint32_t n_retry = h_counts[9];
+    const uint32_t n_retry = read_count(c, d_counts, h_counts, CNT_RETRY);
     if (n_retry) {
       // big-scratch path: up to 1 MiB per thread covers band 512 x 640 rows; few threads
       const size_t per_thread = 1u << 20;
@@ -668,7 +704,6 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
   CUDA_TRY(cudaMemcpyAsync(h_cells, d_cells, 16, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   c->tm.sw_cells_forward = h_cells[0]; c->tm.sw_cells_reverse = h_cells[1];
-  c->tm.ms_sw_prepare += tm_ms(e0, e1);
   c->tm.ms_sw_forward = tm_ms(e1, e2);
   c->tm.ms_sw_reverse = tm_ms(e2, e3);
   c->tm.ms_sw_slow = tm_ms(e3, e4);
@@ -682,61 +717,69 @@ static void sw_reserve(kslam_ctx *c, uint32_t n) {
   w->res.reserve((size_t)n * sizeof(SwRes) + 64);
   w->keys.reserve((size_t)n * sizeof(Rec16) + 64);
   w->keys2.reserve((size_t)n * sizeof(Rec16) + 64);
-  w->items.reserve((size_t)(2 * ((n + 1) / 2)) * sizeof(uint2) + (size_t)n * sizeof(Rec16) + 64);
+  w->items.reserve((size_t)(2 * ((n + 1) / 2)) * sizeof(uint2) + 64);
+  w->lists.reserve((size_t)n * 8 + 64);
   c->counters.reserve(64 * 8); c->h_counters.reserve(64 * 8);
   w->n = n;
 }
 
+static void sw_reset_timers(kslam_ctx *c) {
+  c->tm.ms_sw_prepare = c->tm.ms_sw_forward = c->tm.ms_sw_reverse = c->tm.ms_sw_slow = c->tm.ms_sw_traceback = 0;
+  c->tm.sw_cells_forward = c->tm.sw_cells_reverse = 0;
+  c->tm.n_sw_fast = c->tm.n_sw_slow = c->tm.n_sw_band = c->tm.n_sw_band_rev = 0;
+}
+
 void sw_align_seeds(kslam_ctx *c) {
   const uint32_t n = (uint32_t)c->n_seeds;
-  c->tm.ms_sw_prepare = c->tm.ms_sw_forward = c->tm.ms_sw_reverse = c->tm.ms_sw_slow = c->tm.ms_sw_traceback = 0;
-  c->tm.sw_cells_forward = c->tm.sw_cells_reverse = 0; c->tm.n_sw_fast = c->tm.n_sw_slow = 0;
+  sw_reset_timers(c);
   if (!n) return;
   sw_reserve(c, n);
   cudaStream_t st = c->stream;
   const uint32_t cap = c->prm.max_cigar_ops;
   if (c->prm.report_cigar) c->cig.reserve((size_t)n * cap * 4 + 64);
   uint32_t *d_counts = c->counters.as<uint32_t>() + 32;
+  SwWorkspace *w = c->sw;
   cudaEvent_t e0 = tm_mark(c);
   CUDA_TRY(cudaMemsetAsync(d_counts, 0, 64, st));
   k_sw_prepare_seeds<<<(n + 255) / 256, 256, 0, st>>>(c->seeds.as<kslam_seed>(), n, c->reads.offs.as<uint64_t>(),
       c->reads.word_off.as<uint64_t>(), c->genomes.offs.as<uint64_t>(), c->genomes.word_off.as<uint64_t>(),
-      make_score(c), c->sw->tasks.as<SwTask>(), c->sw->keys.as<Rec16>(), d_counts);
+      c->genomes.nmask.as<uint32_t>(), make_score(c), c->sw_band ? 1u : 0u, w->tasks.as<SwTask>(), w->res.as<SwRes>(), w->lists.as<uint32_t>(),
+      w->keys.as<Rec16>(), w->lists.as<uint32_t>() + n, d_counts);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   cudaEvent_t e1 = tm_mark(c);
   SwPlanes pl{c->reads.sbits.as<uint64_t>(), c->reads.nmask.as<uint32_t>(), c->genomes.sbits.as<uint64_t>(),
               c->genomes.nmask.as<uint32_t>(), c->genomes.xmask.as<uint32_t>()};
   sw_run(c, n, pl, c->ov.as<kslam_overlap>(), c->prm.report_cigar ? c->cig.as<uint32_t>() : nullptr, 1);
-  c->tm.ms_sw_prepare += tm_ms(e0, e1);
+  c->tm.ms_sw_prepare = tm_ms(e0, e1);
 }
 
 void sw_align_pairs(kslam_ctx *c, uint64_t n64, kslam_overlap *out_dev, uint32_t *cig_dev) {
   const uint32_t n = (uint32_t)n64;
-  c->tm.ms_sw_prepare = c->tm.ms_sw_forward = c->tm.ms_sw_reverse = c->tm.ms_sw_slow = c->tm.ms_sw_traceback = 0;
-  c->tm.sw_cells_forward = c->tm.sw_cells_reverse = 0; c->tm.n_sw_fast = c->tm.n_sw_slow = 0;
+  sw_reset_timers(c);
   if (!n) return;
   sw_reserve(c, n);
   cudaStream_t st = c->stream;
   uint32_t *d_counts = c->counters.as<uint32_t>() + 32;
+  SwWorkspace *w = c->sw;
   cudaEvent_t e0 = tm_mark(c);
   CUDA_TRY(cudaMemsetAsync(d_counts, 0, 64, st));
   CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)n * sizeof(kslam_overlap), st));
   k_sw_prepare_pairs<<<(n + 255) / 256, 256, 0, st>>>(n, c->swq.offs.as<uint64_t>(), c->swq.word_off.as<uint64_t>(),
-      c->swr.offs.as<uint64_t>(), c->swr.word_off.as<uint64_t>(), make_score(c), c->sw->tasks.as<SwTask>(),
-      c->sw->keys.as<Rec16>(), d_counts);
+      c->swr.offs.as<uint64_t>(), c->swr.word_off.as<uint64_t>(), c->swr.nmask.as<uint32_t>(), make_score(c), c->sw_band ? 1u : 0u,
+      w->tasks.as<SwTask>(), w->res.as<SwRes>(), w->lists.as<uint32_t>(), w->keys.as<Rec16>(), w->lists.as<uint32_t>() + n, d_counts);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   cudaEvent_t e1 = tm_mark(c);
   SwPlanes pl{c->swq.sbits.as<uint64_t>(), c->swq.nmask.as<uint32_t>(), c->swr.sbits.as<uint64_t>(),
               c->swr.nmask.as<uint32_t>(), c->swr.xmask.as<uint32_t>()};
   sw_run(c, n, pl, out_dev, cig_dev, 0);
-  c->tm.ms_sw_prepare += tm_ms(e0, e1);
+  c->tm.ms_sw_prepare = tm_ms(e0, e1);
 }
 
 void sw_workspace_free(kslam_ctx *c) {
   if (!c->sw) return;
   c->sw->tasks.release(); c->sw->res.release(); c->sw->keys.release(); c->sw->keys2.release();
-  c->sw->items.release(); c->sw->tb_scratch.release();
+  c->sw->items.release(); c->sw->lists.release(); c->sw->tb_scratch.release();
   delete c->sw; c->sw = nullptr;
 }

@@ -33,10 +33,11 @@ def check_overlaps(got, gpool, want, wpool, fields=FIELDS, cigars=True):
         assert not bad, (len(bad), [(a[i], b[i]) for i in bad[:3]])
 
 
-def run_pipeline(pkg, gb, go, rb, ro, P, prefilter=True):
+def run_pipeline(pkg, gb, go, rb, ro, P, prefilter=True, band=True):
     with pkg.Aligner(match=P.match, mismatch=P.mismatch, gap_open=P.gap_open, gap_extend=P.gap_extend,
                      score_threshold=P.score_threshold, report_cigar=bool(P.report_cigar)) as al:
         al.set_prefilter(prefilter)
+        al.set_sw_band(band)
         al.load_genomes(gb, go)
         res = al.align_batch(rb, ro)
         taps = dict(genome_kmers=al.genome_kmers(), read_kmers=al.read_kmers(), raw_seeds=al.raw_seeds(), seeds=al.seeds())
@@ -49,13 +50,15 @@ def check_pipeline(pkg, gb, go, rb, ro, P, want=None):
     """Runs the CUDA path twice — prefilter off (every k-mer record is materialised, so K1/K2 can be compared
     record for record) and on (the production setting) — and checks every stage of both against `want`."""
     want = want or T.ko_pipeline(gb, go, rb, ro, P)
-    for prefilter in (False, True):
-        out = check_pipeline_mode(pkg, gb, go, rb, ro, P, want, prefilter)
+    for prefilter, band in ((False, False), (True, True)):
+        out = check_pipeline_mode(pkg, gb, go, rb, ro, P, want, prefilter, band)
     return out
 
 
-def check_pipeline_mode(pkg, gb, go, rb, ro, P, want, prefilter):
-    res, taps, pairs, tm = run_pipeline(pkg, gb, go, rb, ro, P, prefilter)
+def check_pipeline_mode(pkg, gb, go, rb, ro, P, want, prefilter, band):
+    res, taps, pairs, tm = run_pipeline(pkg, gb, go, rb, ro, P, prefilter, band)
+    if not band:
+        assert tm["n_sw_band"] == 0 and tm["n_sw_band_rev"] == 0
     # K1/K2: genome list in the reference's order (kmer asc, id_flags desc); read list sorted by k-mer
     wg = T.ko_sort_kmers(want["genome_kmers"])
     assert np.array_equal(taps["genome_kmers"]["kmer"], wg["kmer"])
@@ -169,15 +172,23 @@ def test_ssw_golden(pkg, golden, name):
 
 @pytest.mark.parametrize("shape", [(150, 150), (150, 300), (100, 130), (40, 64), (160, 160)])
 @pytest.mark.parametrize("cigar", [0, 1])
-def test_ssw_vs_oracle(pkg, shape, cigar):
+@pytest.mark.parametrize("band", [False, True])
+def test_ssw_vs_oracle(pkg, shape, cigar, band):
     q, qo, r, ro = pkg.synth.sw_pairs(20_000, shape[0], shape[1], seed=100 + shape[0] + cigar)
     P = T.default_params(report_cigar=cigar)
     want, wpool = T.ko_ssw_batch(q, qo, r, ro, P, cigar_cap=32)
     with pkg.Aligner(report_cigar=bool(cigar)) as al:
+        al.set_sw_band(band)
         out, pool = al.ssw_batch(q, qo, r, ro)
         tm = al.timings()
     check_overlaps(out, pool, want, wpool, fields=FIELDS[4:], cigars=bool(cigar))
-    assert tm["n_sw_slow"] == 0 and tm["n_sw_fast"] == 20_000
+    assert tm["n_sw_slow"] == 0
+    if band:
+        assert tm["n_sw_band"] > 15_000                    # every clean window tries the band first ...
+        if shape[1] - shape[0] < 16:
+            assert tm["n_sw_fast"] < 10_000                # ... and most are proven there; the rest fall back
+    else:
+        assert tm["n_sw_band"] == 0 and tm["n_sw_fast"] == 20_000
 
 
 def test_ssw_ragged_lengths_and_repeats(pkg):
@@ -200,10 +211,12 @@ def test_ssw_ragged_lengths_and_repeats(pkg):
     q, qo = T.concat(qs); r, ro = T.concat(rs)
     P = T.default_params(report_cigar=1)
     want, wpool = T.ko_ssw_batch(q, qo, r, ro, P, cigar_cap=32)
-    with pkg.Aligner(report_cigar=True) as al:
-        out, pool = al.ssw_batch(q, qo, r, ro)
     assert ((want["flags"] & 1) != 0).mean() < 0.01
-    check_overlaps(out, pool, want, wpool, fields=FIELDS[4:])
+    for band in (False, True):
+        with pkg.Aligner(report_cigar=True) as al:
+            al.set_sw_band(band)
+            out, pool = al.ssw_batch(q, qo, r, ro)
+        check_overlaps(out, pool, want, wpool, fields=FIELDS[4:])
 
 
 def test_radix_sort_matches_numpy(pkg):
