@@ -95,7 +95,7 @@ typedef struct {
   float ms_h2d, ms_pack, ms_extract, ms_sort, ms_join, ms_seed_sort, ms_unique;
   float ms_sw_prepare, ms_sw_forward, ms_sw_reverse, ms_sw_traceback, ms_sw_slow, ms_d2h, ms_pair, ms_total;
   uint64_t n_read_kmers, n_sorted_kmers, n_genome_kmers, n_raw_seeds, n_seeds, n_sort_passes;
-  uint64_t sw_cells_forward, sw_cells_reverse, n_sw_fast, n_sw_slow, n_sw_band, n_sw_band_rev, n_pairs;
+  uint64_t sw_cells_forward, sw_cells_reverse, n_sw_fast, n_sw_slow, n_sw_band, n_sw_band_rev, n_traceback_dp, n_pairs;
   uint64_t kernel_launches;
 } kslam_timings;
 

@@ -68,7 +68,7 @@ class Timings(C.Structure):
                                          "ms_sw_traceback", "ms_sw_slow", "ms_d2h", "ms_pair", "ms_total")] + \
                [("_pad", C.c_float)] + \
                [(n, C.c_uint64) for n in ("n_read_kmers", "n_sorted_kmers", "n_genome_kmers", "n_raw_seeds", "n_seeds", "n_sort_passes",
-                                          "sw_cells_forward", "sw_cells_reverse", "n_sw_fast", "n_sw_slow", "n_sw_band", "n_sw_band_rev", "n_pairs",
+                                          "sw_cells_forward", "sw_cells_reverse", "n_sw_fast", "n_sw_slow", "n_sw_band", "n_sw_band_rev", "n_traceback_dp", "n_pairs",
                                           "kernel_launches")]
 
     def as_dict(self):

@@ -21,6 +21,7 @@
 //    alignment, then the reverse-complement un-flip and refStart offset (SmithWaterman.h:212-229).
 // Roofline: integer (ALU) pipe; cells/s reported as GCUPS next to the counted ops/cell.
 #include "common.cuh"
+#include <stdlib.h>
 
 #define SW_R 20
 #define SW_MAXCOLS 512
@@ -59,7 +60,7 @@ struct SwScore {
 };
 
 struct SwWorkspace {
-  DevBuf tasks, res, keys, keys2, items, lists, tb_scratch;
+  DevBuf tasks, res, keys, keys2, items, lists, bandbytes, tb_scratch;
   uint64_t n = 0;
 };
 
@@ -390,10 +391,27 @@ __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const S
   return l;
 }
 
+// Score of the gap-free alignment of read'[0..len) against ref'[0..len) (the sub-rectangle's main diagonal).
+__device__ __forceinline__ int32_t diagonal_score(const SwPlanes &pl, const SwTask &t, const SwScore &sc, int32_t ref0,
+                                                  int32_t read0, int32_t len) {
+  int32_t d = 0;
+  for (int32_t i = 0; i < len; i++) {
+    const uint32_t qc = q_code(pl, t, (uint32_t)(read0 + i)), wc = w_code(pl, t, (uint32_t)(ref0 + i));
+    d += (wc == 4 || qc == 4) ? 0 : (wc == qc ? sc.match : -sc.mismatch);
+  }
+  return d;
+}
+
 // Finishes every alignment: cigar (if requested and score >= threshold, ssw.c:924-927), un-flip for
 // reverse-complement seeds and + refStart (SmithWaterman.h:212-229), and writes the kslam_overlap fields.
-// mode 0: first attempt with per-thread local arrays (band <= SW_TB_MAXBAND, rows <= SW_TB_MAXROWS); tasks that
-// need more are appended to retry_list. mode 1: retry path with global scratch (one thread per alignment).
+//  mode 0 (all alignments, no DP): when the sub-rectangle is square and its main diagonal already scores `score`,
+//         banded_sw's first band (width 1) reaches the score, every diagonal cell has direction 1 (a gap path into
+//         a diagonal cell scoring more than the diagonal prefix would lift the corner above the global maximum; all
+//         prefix sums are positive or the reverse pass would have started later) and the traceback yields exactly
+//         `len M` — emitted directly. Everything else is appended to retry_list.
+//  mode 1 (retry_list): literal banded_sw with per-thread local arrays (band <= SW_TB_MAXBAND, rows <= SW_TB_MAXROWS);
+//         larger cases are appended to the next retry list.
+//  mode 2: same with a big global scratch per thread.
 __global__ void __launch_bounds__(128)
 k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, uint32_t n, const uint32_t *list,
                SwPlanes pl, SwScore sc, kslam_overlap *__restrict__ ov, uint32_t *__restrict__ cigs, int unflip,
@@ -419,7 +437,11 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
       else {
         const int32_t refLen = r.ref_end - r.ref_begin + 1, readLen = r.read_end - r.read_begin + 1;
         uint32_t overflow = 0; int32_t len;
-        if (mode == 0)
+        if (mode == 0) {
+          if (refLen == readLen && sc.cigar_cap >= 1 && diagonal_score(pl, t, sc, r.ref_begin, r.read_begin, readLen) == r.score) {
+            cig[0] = (uint32_t)readLen << 4; len = 1;
+          } else len = -3;
+        } else if (mode == 1)
           len = banded_traceback(pl, t, sc, r.ref_begin, r.read_begin, refLen, readLen, r.score, l_hb, l_eb, l_hc,
                                  SW_TB_MAXBAND * 2 + 3, l_dir, sizeof(l_dir), 1, cig, sc.cigar_cap, rev && unflip, &overflow);
         else {
@@ -431,7 +453,7 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
                                  big_per_thread - (size_t)arr_cap * 12, 1, cig, sc.cigar_cap, rev && unflip, &overflow);
         }
         if (len == -3) {
-          if (mode == 0) { deferred = true; retry_list[atomicAdd(retry_count, 1u)] = idx; }
+          if (mode < 2) { deferred = true; retry_list[atomicAdd(retry_count, 1u)] = idx; }
           else o.flags |= KSLAM_FLAG_UNDEFINED;   // beyond even the big scratch: report, never guess
         } else if (len == -2) { o.cigar_len = 0; o.sw_score = 0; }           // ssw.c:941-944
         else if (len == -1) o.flags |= KSLAM_FLAG_UNDEFINED;
@@ -606,12 +628,26 @@ static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore 
   uint32_t *band_list = w->lists.as<uint32_t>();
   Rec16 *keys = w->keys.as<Rec16>(), *keys2 = w->keys2.as<Rec16>();
   if (n_band) {
-    const uint32_t pairs = (n_band + 1) / 2;
-    const size_t smem = (size_t)2 * SWB_COLS * SWB_BLOCK;
-    k_sw_band<REVERSE><<<(pairs + SWB_BLOCK - 1) / SWB_BLOCK, SWB_BLOCK, smem, st>>>(tasks, band_list, n_band, pl, sc, res, keys,
-                                                                                        d_counts + CNT_FULL);
-    c->launches++;
-    CUDA_TRY(cudaGetLastError());
+    static int variant = -1;
+    if (variant < 0) { const char *e = getenv("KSLAM_SWB_VARIANT"); variant = e ? atoi(e) : 0; }
+    const uint32_t CHUNK = 4u << 20;                      // alignments per band-byte plane (768 MB)
+    const uint32_t cmax = n_band < CHUNK ? n_band : CHUNK;
+    const uint32_t stride = (cmax + 1) & ~1u;
+    w->bandbytes.reserve((size_t)stride * SWB_COLS + 64);
+    uint8_t *bytes = w->bandbytes.as<uint8_t>();
+    for (uint32_t c0 = 0; c0 < n_band; c0 += CHUNK) {
+      const uint32_t cn = n_band - c0 < CHUNK ? n_band - c0 : CHUNK;
+      const uint32_t *lst = band_list + c0;
+      dim3 gridb((cn + 255) / 256, SWB_COLS / 32);
+      k_band_bytes<REVERSE><<<gridb, 256, 0, st>>>(tasks, lst, cn, pl, sc, res, bytes, stride);
+      const uint32_t pairs = (cn + 1) / 2, blocks = (pairs + SWB_BLOCK - 1) / SWB_BLOCK;
+      if (variant == 1 && sc.gap_open >= sc.gap_extend)
+        k_sw_band<REVERSE, true><<<blocks, SWB_BLOCK, 0, st>>>(tasks, lst, cn, sc, res, bytes, stride, keys, d_counts + CNT_FULL);
+      else
+        k_sw_band<REVERSE, false><<<blocks, SWB_BLOCK, 0, st>>>(tasks, lst, cn, sc, res, bytes, stride, keys, d_counts + CNT_FULL);
+      c->launches += 2;
+      CUDA_TRY(cudaGetLastError());
+    }
   }
   const uint32_t n_full = read_count(c, d_counts, h_counts, CNT_FULL);
   *n_band_done += n_band; *n_full_done += n_full;
@@ -674,25 +710,32 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
   }
   cudaEvent_t e4 = tm_mark(c);
   {
-    // traceback + finalize
+    // finalize (+ diagonal fast path), then the literal banded_sw on what is left, then the big-scratch retry
     uint32_t *retry_count = d_counts + CNT_RETRY;
+    uint32_t *list1 = reinterpret_cast<uint32_t *>(w->keys.p), *list2 = reinterpret_cast<uint32_t *>(w->keys2.p);   // keys are dead by now
     CUDA_TRY(cudaMemsetAsync(retry_count, 0, 4, st));
-    uint32_t *retry_list = reinterpret_cast<uint32_t *>(w->keys.p);   // keys are dead by now
-    uint32_t blocks = (n + 127) / 128;
-    k_sw_traceback<<<blocks, 128, 0, st>>>(tasks, res, n, nullptr, pl, sc, ov, cig, unflip, 0, retry_list, retry_count, nullptr, 0);
+    k_sw_traceback<<<(n + 127) / 128, 128, 0, st>>>(tasks, res, n, nullptr, pl, sc, ov, cig, unflip, 0, list1, retry_count, nullptr, 0);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
-    const uint32_t n_retry = read_count(c, d_counts, h_counts, CNT_RETRY);
-    if (n_retry) {
-      // big-scratch path: up to 1 MiB per thread covers band 512 x 640 rows; few threads
-      const size_t per_thread = 1u << 20;
-      uint32_t threads = n_retry < 2048 ? n_retry : 2048;
-      uint32_t rblocks = (threads + 127) / 128;
-      w->tb_scratch.reserve((size_t)rblocks * 128 * per_thread);
-      k_sw_traceback<<<rblocks, 128, 0, st>>>(tasks, res, n_retry, retry_list, pl, sc, ov, cig, unflip, 1, nullptr, nullptr,
-                                               w->tb_scratch.as<uint8_t>(), per_thread);
+    const uint32_t n_dp = read_count(c, d_counts, h_counts, CNT_RETRY);
+    c->tm.n_traceback_dp = n_dp;
+    if (n_dp) {
+      CUDA_TRY(cudaMemsetAsync(retry_count, 0, 4, st));
+      k_sw_traceback<<<(n_dp + 127) / 128, 128, 0, st>>>(tasks, res, n_dp, list1, pl, sc, ov, cig, unflip, 1, list2, retry_count, nullptr, 0);
       c->launches++;
       CUDA_TRY(cudaGetLastError());
+      const uint32_t n_big = read_count(c, d_counts, h_counts, CNT_RETRY);
+      if (n_big) {
+        // up to 1 MiB per thread covers band 512 x 640 rows; few threads
+        const size_t per_thread = 1u << 20;
+        uint32_t threads = n_big < 2048 ? n_big : 2048;
+        uint32_t rblocks = (threads + 127) / 128;
+        w->tb_scratch.reserve((size_t)rblocks * 128 * per_thread);
+        k_sw_traceback<<<rblocks, 128, 0, st>>>(tasks, res, n_big, list2, pl, sc, ov, cig, unflip, 2, nullptr, nullptr,
+                                                 w->tb_scratch.as<uint8_t>(), per_thread);
+        c->launches++;
+        CUDA_TRY(cudaGetLastError());
+      }
     }
   }
   cudaEvent_t e5 = tm_mark(c);
@@ -780,6 +823,6 @@ void sw_align_pairs(kslam_ctx *c, uint64_t n64, kslam_overlap *out_dev, uint32_t
 void sw_workspace_free(kslam_ctx *c) {
   if (!c->sw) return;
   c->sw->tasks.release(); c->sw->res.release(); c->sw->keys.release(); c->sw->keys2.release();
-  c->sw->items.release(); c->sw->lists.release(); c->sw->tb_scratch.release();
+  c->sw->items.release(); c->sw->lists.release(); c->sw->bandbytes.release(); c->sw->tb_scratch.release();
   delete c->sw; c->sw = nullptr;
 }

@@ -25,105 +25,147 @@
 
 __device__ __forceinline__ int32_t ceil_div_pos(int32_t a, int32_t b) { return (a + b - 1) / b; }
 
-// selector byte for one alignment's column: (copy byte w, replicate sign of byte w) of its profile register.
-// `second` selects the second PRMT source (alignment B). Out-of-matrix columns use two replicate nibbles.
-__device__ __forceinline__ uint32_t band_sel_byte(uint32_t w, bool in_range, bool second) {
-  const uint32_t base = second ? 4u : 0u;
-  if (!in_range) return (8u | base) | ((8u | base) << 4);
-  return (base + w) | ((8u | (base + w)) << 4);
-}
+// geometry of one alignment inside the band sweep
+struct BandGeo { int32_t rows, cols, c0; };
 
 template <bool REVERSE>
+__device__ __forceinline__ BandGeo band_geo(const SwTask &t, const SwRes &r, const SwScore &sc) {
+  BandGeo g;
+  if (REVERSE) {
+    g.rows = r.read_end + 1; g.cols = r.ref_end + 1;
+    g.c0 = -(g.rows - ceil_div_pos(r.score, sc.match));
+  } else {
+    g.rows = (int32_t)t.m; g.cols = (int32_t)t.n;
+    g.c0 = ((g.cols - g.rows) >> 1) - SWB_W / 2;   // centre of [-(m - a), n - a] is (n - m) / 2 whatever a is
+  }
+  return g;
+}
+
+// Band byte plane: bytes[k * stride + slot] for band index k in [0, SWB_COLS) of the alignment in list slot `slot`.
+// low nibble = selector of matrix column j = k + c0 (SSW code 0-3, or 8 = outside the matrix), high nibble = SSW
+// code of query row k (0-4, 5 = past the query). One thread fills 32 consecutive k of one alignment, so the packed
+// words are fetched once and consecutive lanes (slots) write consecutive bytes.
+template <bool REVERSE>
+__global__ void __launch_bounds__(256)
+k_band_bytes(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, uint32_t n_list, SwPlanes pl, SwScore sc,
+             const SwRes *__restrict__ res, uint8_t *__restrict__ bytes, uint32_t stride) {
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_list) return;
+  const int32_t k0 = (int32_t)blockIdx.y * 32;
+  const uint32_t idx = list[slot];
+  const SwTask t = tasks[idx];
+  SwRes r; if (REVERSE) r = res[idx];
+  const BandGeo g = band_geo<REVERSE>(t, r, sc);
+  const bool rev = (t.flags & SWT_REV) != 0;
+  // genome position of matrix column j is P0 + sg * j (window reversal and the reverse sweep both flip the sign)
+  int32_t P0, sg;
+  if (!REVERSE) { P0 = rev ? (int32_t)(t.w_start + t.n - 1) : (int32_t)t.w_start; sg = rev ? -1 : 1; }
+  else { P0 = rev ? (int32_t)(t.w_start + t.n - 1) - r.ref_end : (int32_t)t.w_start + r.ref_end; sg = rev ? 1 : -1; }
+  const uint64_t *wb = pl.w_sbits + t.w_word; const uint32_t *wx = pl.w_xmask + t.w_word;
+  const uint64_t *qb = pl.q_sbits + t.q_word; const uint32_t *qn = pl.q_nmask + t.q_word;
+  int32_t curw = -1, curq = -1; uint64_t bits = 0, qbits = 0; uint32_t xm = 0, qnm = 0;
+  uint8_t *dst = bytes + (size_t)k0 * stride + slot;
+#pragma unroll 4
+  for (int32_t kk = 0; kk < 32; kk++) {
+    const int32_t k = k0 + kk, j = k + g.c0;
+    uint32_t lo = 8u;
+    if (j >= 0 && j < g.cols) {
+      const int32_t pos = P0 + sg * j, wi = pos >> 5;
+      if (wi != curw) { curw = wi; bits = __ldg(wb + wi); xm = rev ? ~__ldg(wx + wi) : 0u; }
+      lo = (uint32_t)(bits >> (2 * (pos & 31))) & 3u;
+      if ((xm >> (pos & 31)) & 1u) lo ^= 3u;               // complement (3 - c) unless the base is a/c/g/t/U/u
+    }
+    uint32_t hi = 5u;
+    if (k < g.rows) {
+      const int32_t qi = REVERSE ? g.rows - 1 - k : k, wq = qi >> 5;
+      if (wq != curq) { curq = wq; qbits = __ldg(qb + wq); qnm = __ldg(qn + wq); }
+      hi = ((qnm >> (qi & 31)) & 1u) ? 4u : ((uint32_t)(qbits >> (2 * (qi & 31))) & 3u);
+    }
+    dst[(size_t)kk * stride] = (uint8_t)(lo | (hi << 4));
+  }
+}
+
+// `list`/`bytes` cover one chunk of the band list; slot pairs (2p, 2p+1) share a thread. stride is even, so the two
+// bytes of a pair are one aligned 16-bit load.
+template <bool REVERSE, bool SHORT_CHAIN>
 __global__ void __launch_bounds__(SWB_BLOCK, 3)
-k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, uint32_t n_list, SwPlanes pl, SwScore sc,
-          SwRes *__restrict__ res, Rec16 *__restrict__ fb_keys, uint32_t *__restrict__ fb_count) {
-  extern __shared__ uint8_t s_selb[];   // [2][SWB_COLS][SWB_BLOCK]
-  const uint32_t tid = threadIdx.x;
-  const uint32_t p = blockIdx.x * SWB_BLOCK + tid;
+k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, uint32_t n_list, SwScore sc,
+          SwRes *__restrict__ res, const uint8_t *__restrict__ bytes, uint32_t stride, Rec16 *__restrict__ fb_keys,
+          uint32_t *__restrict__ fb_count) {
+  const uint32_t p = blockIdx.x * SWB_BLOCK + threadIdx.x;
   if (2 * p >= n_list) return;
-  const uint32_t ia = list[2 * p], ib = (2 * p + 1 < n_list) ? list[2 * p + 1] : ia;
+  const bool single = 2 * p + 1 >= n_list;
+  const uint32_t ia = list[2 * p], ib = single ? ia : list[2 * p + 1];
   const SwTask ta = tasks[ia], tb = tasks[ib];
   SwRes ra, rb;
-  int32_t rows[2], cols[2], c0[2];
-  if (REVERSE) {
-    ra = res[ia]; rb = res[ib];
-    rows[0] = ra.read_end + 1; cols[0] = ra.ref_end + 1; rows[1] = rb.read_end + 1; cols[1] = rb.ref_end + 1;
-    c0[0] = -(rows[0] - ceil_div_pos(ra.score, sc.match)); c0[1] = -(rows[1] - ceil_div_pos(rb.score, sc.match));
-  } else {
-    rows[0] = (int32_t)ta.m; cols[0] = (int32_t)ta.n; rows[1] = (int32_t)tb.m; cols[1] = (int32_t)tb.n;
-    // centre of [-(m - a), n - a] is (n - m) / 2 whatever a is; band = [c0, c0 + 31]
-    c0[0] = ((cols[0] - rows[0]) >> 1) - SWB_W / 2; c0[1] = ((cols[1] - rows[1]) >> 1) - SWB_W / 2;
-  }
+  if (REVERSE) { ra = res[ia]; rb = res[ib]; }
+  const BandGeo ga = band_geo<REVERSE>(ta, ra, sc), gb = band_geo<REVERSE>(tb, rb, sc);
+  const int32_t rows[2] = {ga.rows, gb.rows}, cols[2] = {ga.cols, gb.cols}, c0[2] = {ga.c0, gb.c0};
   const int32_t rows_max = rows[0] > rows[1] ? rows[0] : rows[1];
-
-  // ---- column selector bytes for band column index k (matrix column j = k + c0), k in [0, rows_max + 32)
-#pragma unroll
-  for (int al = 0; al < 2; al++) {
-    const SwTask &t = al ? tb : ta;
-    const bool rev = (t.flags & SWT_REV) != 0;
-    const int32_t ref_end = REVERSE ? (al ? rb.ref_end : ra.ref_end) : 0;
-    uint64_t curw = ~0ull, bits = 0; uint32_t xm = 0;
-    uint8_t *dst = s_selb + (size_t)al * SWB_COLS * SWB_BLOCK + tid;
-    for (int32_t k = 0; k < rows_max + SWB_W; k++) {
-      const int32_t j = k + c0[al];
-      uint32_t byte;
-      if (j < 0 || j >= cols[al]) byte = band_sel_byte(0, false, al);
-      else {
-        const uint32_t x = REVERSE ? (uint32_t)(ref_end - j) : (uint32_t)j;
-        const uint32_t pos = rev ? t.w_start + t.n - 1 - x : t.w_start + x;
-        const uint64_t w = t.w_word + (pos >> 5);
-        if (w != curw) { curw = w; bits = __ldg(&pl.w_sbits[w]); xm = rev ? __ldg(&pl.w_xmask[w]) : 0u; }
-        uint32_t c = (uint32_t)(bits >> (2 * (pos & 31))) & 3u;
-        if (rev && !((xm >> (pos & 31)) & 1u)) c = 3u - c;
-        byte = band_sel_byte(c, true, al);
-      }
-      dst[(size_t)k * SWB_BLOCK] = (uint8_t)byte;
-    }
-  }
-  // (each thread reads back only what it wrote: no barrier needed)
+  const uint16_t *bp = reinterpret_cast<const uint16_t *>(bytes + 2 * (size_t)p);   // + k * stride bytes
+  // low byte = alignment A, high byte = alignment B (for an unpaired last slot the neighbour byte is ignored: the
+  // B half then mirrors A through ib == ia but its band bytes are whatever slot 2p+1 holds — results of B are dropped)
+  auto ld2 = [&](int32_t k) -> uint32_t { return __ldg(reinterpret_cast<const uint16_t *>(reinterpret_cast<const uint8_t *>(bp) + (size_t)k * stride)); };
 
   const uint32_t mis_b = (uint32_t)(-(sc.mismatch * 32)) & 0xffu, mat_b = (uint32_t)(sc.match * 32) & 0xffu;
   const uint32_t MIS4 = mis_b * 0x01010101u, DIFF = mis_b ^ mat_b;
   const uint32_t NEG_GO = pack2(-sc.gap_open * 32), NEG_GE = pack2(-sc.gap_extend * 32), MIN2 = 0x80008000u;
-  const uint8_t *selA = s_selb + tid, *selB = s_selb + (size_t)SWB_COLS * SWB_BLOCK + tid;
 
+  // selector halves: alignment A copies byte w of PA (sign-replicated into the high byte), B byte w of PB;
+  // outside the matrix both nibbles replicate a sign (score 0 or -1, never positive)
+  auto mk_sel = [](uint32_t ab) -> uint32_t {       // ab = byte A | byte B << 8
+    const uint32_t a = ab & 15u, b = (ab >> 8) & 15u;
+    return (a | ((a & 3u) << 4) | 0x80u) | ((b | ((b & 3u) << 4) | 0xC4u) << 8);
+  };
   uint32_t H[SWB_W], V[SWB_W], sel[SWB_W];
 #pragma unroll
   for (int t = 0; t < SWB_W; t++) {
     H[t] = 0; V[t] = 0;
-    sel[t] = (uint32_t)selA[(size_t)t * SWB_BLOCK] | ((uint32_t)selB[(size_t)t * SWB_BLOCK] << 8);
+    sel[t] = mk_sel(ld2(t));
   }
+  uint32_t rowbytes = ld2(0);                                // query codes of row 0 (prefetched one row ahead)
   // forward: key = score << 12 | (4095 - column); reverse: key = 4095 - scan column of the first hit (0 = none)
   uint32_t bestA = 0, bestB = 0, rowA = 0, rowB = 0;
   const uint32_t thrA = REVERSE ? (uint32_t)ra.score * 32u : 0u, thrB = REVERSE ? (uint32_t)rb.score * 32u : 0u;
 
   for (int32_t i = 0; i < rows_max; i++) {
     // row profiles [s(q,A) s(q,C) s(q,G) s(q,T)] x 32; code-4 rows score 0; rows past the query mismatch everything
-    uint32_t PA = MIS4, PB = MIS4;
-    if (i < rows[0]) { const uint32_t c = q_code(pl, ta, REVERSE ? (uint32_t)(rows[0] - 1 - i) : (uint32_t)i);
-                       PA = c == 4 ? 0u : (MIS4 ^ (DIFF << (8 * c))); }
-    if (i < rows[1]) { const uint32_t c = q_code(pl, tb, REVERSE ? (uint32_t)(rows[1] - 1 - i) : (uint32_t)i);
-                       PB = c == 4 ? 0u : (MIS4 ^ (DIFF << (8 * c))); }
+    const uint32_t qa = (rowbytes >> 4) & 15u, qb = rowbytes >> 12;
+    const uint32_t PA = qa == 4u ? 0u : (qa == 5u ? MIS4 : (MIS4 ^ (DIFF << (8 * qa))));
+    const uint32_t PB = qb == 4u ? 0u : (qb == 5u ? MIS4 : (MIS4 ^ (DIFF << (8 * qb))));
+    // issue next row's loads now; they complete under the 32-cell body (indices stay below SWB_COLS)
+    const uint32_t next = ld2(i + 1), ent = ld2(i + SWB_W);
     uint32_t e = 0, acc = 0;
 #pragma unroll
     for (int t = 0; t < SWB_W; t++) {
       const uint32_t s = prmt(PA, PB, sel[t]);
       const uint32_t v = V[t];
-      uint32_t h = __viaddmax_s16x2_relu(H[t], s, v);           // max(H[i-1][j-1] + s, vertical gap, 0)
-      h = __vimax3_s16x2(h, e, e);                                // ... and the horizontal gap
-      H[t] = h;
-      const uint32_t hgo = __viaddmax_s16x2(h, NEG_GO, MIN2);
-      e = __viaddmax_s16x2(e, NEG_GE, hgo);                      // horizontal gap into (i, j+1)
-      if (t > 0) V[t - 1] = __viaddmax_s16x2(v, NEG_GE, hgo);    // vertical gap into (i+1, j): band slot t-1 next row
-      acc = __viaddmax_s16x2(h, (uint32_t)(31 - t) * 0x10001u, acc);   // max of H*32 + (31 - t): smallest column wins ties
+      if (SHORT_CHAIN) {
+        // gap_open >= gap_extend (checked by the launcher): the horizontal gap into (i, j+1) is
+        // max(e - ge, T - go) with T = max(H[i-1][j-1] + s, vertical gap, 0) — e itself cannot open a better gap —
+        // so the loop-carried chain through e is ONE op per cell; h and the vertical state hang off it
+        const uint32_t T = __viaddmax_s16x2_relu(H[t], s, v);
+        const uint32_t tgo = __viaddmax_s16x2(T, NEG_GO, MIN2);
+        const uint32_t h = __vimax3_s16x2(T, e, e);
+        H[t] = h;
+        if (t > 0) V[t - 1] = __viaddmax_s16x2(v, NEG_GE, __viaddmax_s16x2(h, NEG_GO, MIN2));   // off the e-chain
+        e = __viaddmax_s16x2(e, NEG_GE, tgo);
+        acc = __viaddmax_s16x2(h, (uint32_t)(31 - t) * 0x10001u, acc);
+      } else {
+        uint32_t h = __viaddmax_s16x2_relu(H[t], s, v);           // max(H[i-1][j-1] + s, vertical gap, 0)
+        h = __vimax3_s16x2(h, e, e);                                // ... and the horizontal gap
+        H[t] = h;
+        const uint32_t hgo = __viaddmax_s16x2(h, NEG_GO, MIN2);
+        e = __viaddmax_s16x2(e, NEG_GE, hgo);                      // horizontal gap into (i, j+1)
+        if (t > 0) V[t - 1] = __viaddmax_s16x2(v, NEG_GE, hgo);    // vertical gap into (i+1, j): band slot t-1 next row
+        acc = __viaddmax_s16x2(h, (uint32_t)(31 - t) * 0x10001u, acc);   // max of H*32 + (31 - t): smallest column wins ties
+      }
     }
     // slide the column selectors: next row's slot t is this row's slot t+1; slot 31 takes the entering column
 #pragma unroll
     for (int t = 0; t < SWB_W - 1; t++) sel[t] = sel[t + 1];
-    {
-      const size_t k = (size_t)(i + SWB_W) * SWB_BLOCK;
-      sel[SWB_W - 1] = (uint32_t)selA[k] | ((uint32_t)selB[k] << 8);
-    }
+    sel[SWB_W - 1] = mk_sel(ent);
+    rowbytes = next;
     // row winners -> running best (first column, then smallest row: rows only grow, so ties keep the old one)
     const uint32_t aA = acc & 0xffffu, aB = acc >> 16;
     const uint32_t jA = (uint32_t)(i + (int32_t)(31u - (aA & 31u)) + c0[0]), jB = (uint32_t)(i + (int32_t)(31u - (aB & 31u)) + c0[1]);
@@ -140,7 +182,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
 
 #pragma unroll
   for (int al = 0; al < 2; al++) {
-    if (al == 1 && ib == ia) break;
+    if (al == 1 && single) break;
     const uint32_t idx = al ? ib : ia;
     const uint32_t best = al ? bestB : bestA, brow = al ? rowB : rowA;
     if (REVERSE) {
