@@ -121,6 +121,7 @@ def cpu_reference_sample(pkg, gb, go, n_pairs_sample, report_cigar, threshold):
     rb, ro, _ = pkg.synth.paired_reads(gb, go, n_pairs_sample, seed=99)
     P = T.default_params(report_cigar=int(report_cigar), score_threshold=threshold)
     if T.have_ref():
+        T.ref().kref_set_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1: ask for every core
         R = T.Ref(gb, go, rb, ro, P)
         cores = T.ref().kref_num_threads()
         t0 = time.time()

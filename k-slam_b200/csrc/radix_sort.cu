@@ -13,7 +13,6 @@
 #include "common.cuh"
 #include <stdlib.h>
 
-#define RS_TILE 4096        // records per tile (64 KB staged in shared memory)
 #define RS_MAX_PASSES 8
 
 #define RS_FLAG_AGG (1ull << 62)
@@ -68,14 +67,14 @@ k_rs_scan_hist(unsigned long long *__restrict__ ghist, uint32_t n_passes, uint64
 
 // ---- one LSD pass ------------------------------------------------------------------------------
 template <int RS_THREADS, int RS_IPT>
-__global__ void __launch_bounds__(RS_THREADS, 2)
+__global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_IPT > 4096 ? 1 : 2))
 k_rs_onesweep(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n, uint32_t shift, uint32_t mask,
               uint32_t word,                                       // 0: sort by .key, 1: sort by .val
               const unsigned long long *__restrict__ digit_base,  // [256] exclusive global offsets
               volatile unsigned long long *tile_state,            // [tiles][256], zero-initialised
               uint32_t *__restrict__ ticket) {
   constexpr int RS_WARPS = RS_THREADS / 32;
-  static_assert(RS_THREADS * RS_IPT == RS_TILE, "tile shape");
+  constexpr uint32_t RS_TILE = RS_THREADS * RS_IPT;     // records per tile, staged in shared memory
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Rec16 *stage = reinterpret_cast<Rec16 *>(smem_raw);                               // RS_TILE records
   uint32_t *whist = reinterpret_cast<uint32_t *>(smem_raw + RS_TILE * sizeof(Rec16)); // [RS_WARPS][256]
@@ -111,15 +110,16 @@ k_rs_onesweep(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n,
   const uint32_t lt_mask = (1u << lane) - 1;
 #pragma unroll
   for (int i = 0; i < RS_IPT; i++) {
-    uint32_t idx = wbase + i * 32 + lane;
-    uint32_t d = idx < count ? ((uint32_t)((word ? val[i] : key[i]) >> shift) & mask) : 255u;
-    uint32_t peers = __match_any_sync(0xffffffffu, d);
-    uint32_t old = myhist[d];                    // every peer reads the warp's running count (broadcast)
+    const uint32_t idx = wbase + i * 32 + lane;
+    const uint32_t d = idx < count ? ((uint32_t)((word ? val[i] : key[i]) >> shift) & mask) : 255u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t old = myhist[d];              // every peer reads the warp's running count (broadcast)
     __syncwarp();
     if ((peers & lt_mask) == 0) myhist[d] = old + __popc(peers);   // lowest peer publishes the new count
     __syncwarp();
     rank[i] = old + __popc(peers & lt_mask);
   }
+  // (a software-pipelined variant — all MATCH ops, then shared-memory atomics, then shuffles — measured 5 % slower)
   __syncthreads();
 
   // 3. thread d (< 256) owns digit d: exclusive offsets over warps, tile count
@@ -135,12 +135,26 @@ k_rs_onesweep(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n,
     if (tile == 0) *my_state = RS_FLAG_INCL | real_d; else *my_state = RS_FLAG_AGG | real_d;
     unsigned long long excl = 0;
     if (tile > 0) {
-      for (int64_t t = (int64_t)tile - 1; t >= 0; t--) {
-        volatile unsigned long long *ps = tile_state + (uint64_t)t * 256 + tid;
-        unsigned long long s;
-        do { s = *ps; } while ((s >> 62) == 0);
-        excl += s & RS_VAL_MASK;
-        if ((s >> 62) == 2) break;
+      // walk back over the predecessors' published counts until one with an inclusive prefix is met. The
+      // states of RS_LB predecessors are fetched together (independent loads in flight) and consumed in order;
+      // an unpublished one restarts the batch at that tile.
+      constexpr int RS_LB = 8;
+      int64_t t = (int64_t)tile - 1;
+      bool done = false;
+      while (!done) {
+        unsigned long long s[RS_LB];
+#pragma unroll
+        for (int k = 0; k < RS_LB; k++)
+          s[k] = (t - k >= 0) ? tile_state[(uint64_t)(t - k) * 256 + tid] : RS_FLAG_INCL;   // before tile 0: prefix 0
+        int used = 0;
+#pragma unroll
+        for (int k = 0; k < RS_LB; k++) {
+          if (!done && used == k) {
+            const unsigned long long f = s[k] >> 62;
+            if (f != 0) { excl += s[k] & RS_VAL_MASK; used = k + 1; if (f == 2) done = true; }
+          }
+        }
+        t -= used;
       }
       *my_state = RS_FLAG_INCL | (excl + real_d);
     }
@@ -185,9 +199,10 @@ k_rs_onesweep(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n,
 }
 
 template <int T, int I>
-static void launch_onesweep(kslam_ctx *c, uint64_t tiles, const Rec16 *in, Rec16 *out, uint64_t n, uint32_t shift, uint32_t mask,
+static void launch_onesweep(kslam_ctx *c, const Rec16 *in, Rec16 *out, uint64_t n, uint32_t shift, uint32_t mask,
                             uint32_t word, const unsigned long long *base, unsigned long long *state, uint32_t *ticket) {
-  constexpr size_t smem = RS_TILE * sizeof(Rec16) + (T / 32) * 256 * sizeof(uint32_t);
+  constexpr size_t smem = (size_t)T * I * sizeof(Rec16) + (T / 32) * 256 * sizeof(uint32_t);
+  const uint64_t tiles = (n + (uint64_t)T * I - 1) / ((uint64_t)T * I);
   static bool attr_set[64] = {false};
   if (!(c->device < 64 && attr_set[c->device])) {
     CUDA_TRY(cudaFuncSetAttribute(k_rs_onesweep<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -211,7 +226,8 @@ Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, u
     uint32_t bits = hi_bit - s < 8 ? hi_bit - s : 8;
     plan.shift[plan.n_passes] = s; plan.mask[plan.n_passes] = (1u << bits) - 1; plan.n_passes++;
   }
-  const uint64_t tiles = (n + RS_TILE - 1) / RS_TILE;
+  const uint64_t tile_recs = cfg == 2 ? 8192 : 4096;
+  const uint64_t tiles = (n + tile_recs - 1) / tile_recs;
   // layout of sort_hist: [8*256 u64 hist][8 u32 trivial][8 u32 tickets][pad][tiles*256 u64 state]
   const size_t hist_bytes = RS_MAX_PASSES * 256 * 8, misc_bytes = 128;
   c->sort_hist.reserve(hist_bytes + misc_bytes + tiles * 256 * 8);
@@ -234,8 +250,9 @@ Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, u
   for (uint32_t p = 0; p < plan.n_passes; p++) {
     if (h_trivial[p]) continue;   // every record has the same digit: the pass would be the identity
     CUDA_TRY(cudaMemsetAsync(state, 0, tiles * 256 * 8, st));
-    if (cfg == 1) launch_onesweep<512, 8>(c, tiles, cur, alt, n, plan.shift[p], plan.mask[p], word, ghist + p * 256, state, tickets + p);
-    else launch_onesweep<256, 16>(c, tiles, cur, alt, n, plan.shift[p], plan.mask[p], word, ghist + p * 256, state, tickets + p);
+    if (cfg == 1) launch_onesweep<512, 8>(c, cur, alt, n, plan.shift[p], plan.mask[p], word, ghist + p * 256, state, tickets + p);
+    else if (cfg == 2) launch_onesweep<512, 16>(c, cur, alt, n, plan.shift[p], plan.mask[p], word, ghist + p * 256, state, tickets + p);
+    else launch_onesweep<256, 16>(c, cur, alt, n, plan.shift[p], plan.mask[p], word, ghist + p * 256, state, tickets + p);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     Rec16 *t = cur; cur = alt; alt = t;

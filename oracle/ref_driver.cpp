@@ -84,6 +84,8 @@ extern "C" {
 void *kref_create() { forceParallel(); return new KrefCtx(); }
 void kref_destroy(void *h) { delete (KrefCtx *)h; }
 int kref_num_threads() { return omp_get_max_threads(); }
+// torchrun exports OMP_NUM_THREADS=1; the CPU baseline must be able to ask for every host core explicitly.
+void kref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 // Globals.h:27-42 — main.cpp:36-58 normally fills these.
 void kref_set_params(uint32_t m, uint32_t x, uint32_t go, uint32_t ge, uint32_t thr,

@@ -104,6 +104,7 @@ def ref():
                      "kref_screen", "kref_num_overlaps", "kref_cigar_total", "kref_pair", "kref_ssw_batch"):
             getattr(L, name).restype = C.c_uint64
         L.kref_destroy.argtypes = [C.c_void_p]
+        L.kref_set_threads.argtypes = [C.c_int]
         L.kref_set_params.argtypes = [C.c_uint32] * 5 + [C.c_int]
         L.kref_set_genomes.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         L.kref_set_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
