@@ -95,7 +95,7 @@ typedef struct {
   float ms_h2d, ms_pack, ms_extract, ms_sort, ms_join, ms_seed_sort, ms_unique;
   float ms_sw_prepare, ms_sw_forward, ms_sw_reverse, ms_sw_traceback, ms_sw_slow, ms_d2h, ms_pair, ms_total;
   uint64_t n_read_kmers, n_sorted_kmers, n_genome_kmers, n_raw_seeds, n_seeds, n_sort_passes;
-  uint64_t sw_cells_forward, sw_cells_reverse, n_sw_fast, n_sw_slow, n_sw_band, n_sw_band_rev, n_traceback_dp, n_pairs;
+  uint64_t sw_cells_forward, sw_cells_reverse, n_sw_fast, n_sw_slow, n_sw_band, n_sw_band64, n_sw_band_rev, n_traceback_dp, n_pairs;
   uint64_t kernel_launches;
 } kslam_timings;
 
@@ -147,10 +147,10 @@ int kslam_get_timings(const kslam_ctx *ctx, kslam_timings *out);
  * extracted — they cannot seed (Overlap.h:157,236-239) — so only the survivors are written, sorted and joined.
  * Results are identical either way; with the filter off the read k-mer tap holds every record (KMer.h:160-181). */
 int kslam_set_prefilter(kslam_ctx *ctx, int on);
-/* Banded Smith-Waterman (default on): alignments whose optimum is provably inside a 32-diagonal band are run by
- * the banded kernel, everything else (and every case the proof fails for) by the full-matrix kernel. Results are
- * identical either way (DESIGN.md §SW band). */
-int kslam_set_sw_band(kslam_ctx *ctx, int on);
+/* Banded Smith-Waterman tiers: 0 = full-matrix kernel only; 1 = alignments whose optimum is provably inside a
+ * 32-diagonal band run in the banded kernel; 2 (default) = additionally a 64-diagonal tier for the rest. Whatever
+ * cannot be proven falls through to the full-matrix kernel. Results are identical at every level. */
+int kslam_set_sw_band(kslam_ctx *ctx, int level);
 /* Keep (1, default) or drop (0) stage-tap buffers between stages; dropping saves HBM on big batches. */
 int kslam_set_debug_taps(kslam_ctx *ctx, int keep);
 

@@ -68,7 +68,7 @@ class Timings(C.Structure):
                                          "ms_sw_traceback", "ms_sw_slow", "ms_d2h", "ms_pair", "ms_total")] + \
                [("_pad", C.c_float)] + \
                [(n, C.c_uint64) for n in ("n_read_kmers", "n_sorted_kmers", "n_genome_kmers", "n_raw_seeds", "n_seeds", "n_sort_passes",
-                                          "sw_cells_forward", "sw_cells_reverse", "n_sw_fast", "n_sw_slow", "n_sw_band", "n_sw_band_rev", "n_traceback_dp", "n_pairs",
+                                          "sw_cells_forward", "sw_cells_reverse", "n_sw_fast", "n_sw_slow", "n_sw_band", "n_sw_band64", "n_sw_band_rev", "n_traceback_dp", "n_pairs",
                                           "kernel_launches")]
 
     def as_dict(self):
@@ -291,8 +291,9 @@ class Aligner:
     def set_prefilter(self, on: bool):
         self._check(self.L.kslam_set_prefilter(self.h, int(on)), "kslam_set_prefilter")
 
-    def set_sw_band(self, on: bool):
-        self._check(self.L.kslam_set_sw_band(self.h, int(on)), "kslam_set_sw_band")
+    def set_sw_band(self, level: int):
+        """0 = full-matrix kernel only, 1 = 32-diagonal band tier, 2 (default) = 32- and 64-diagonal tiers."""
+        self._check(self.L.kslam_set_sw_band(self.h, int(level)), "kslam_set_sw_band")
 
     def set_debug_taps(self, keep: bool):
         self._check(self.L.kslam_set_debug_taps(self.h, int(keep)), "kslam_set_debug_taps")

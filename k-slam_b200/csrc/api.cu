@@ -116,7 +116,8 @@ int kslam_set_prefilter(kslam_ctx *ctx, int on) {
 
 int kslam_set_sw_band(kslam_ctx *ctx, int on) {
   if (!ctx) return KSLAM_ERR_ARG;
-  ctx->sw_band = on != 0;
+  ctx->sw_band = on != 0;          // on = 1: 32-wide tier only; on >= 2 (default): 32- and 64-wide tiers
+  ctx->sw_band64 = on >= 2;
   return KSLAM_OK;
 }
 

@@ -94,6 +94,7 @@ struct kslam_ctx {
   DevBuf bitmap;   // prefilter: 2^filter_bits bits over hashed genome k-mers (kmer.cu)
   uint32_t filter_bits = 0;
   bool prefilter = true;
+  bool sw_band64 = true;   // second banded tier (64 diagonals) for what the 32-wide sweep cannot prove
   bool sw_band = true;     // banded SW kernel with exactness proof + full-matrix fallback (sw_band.cuh)
   uint32_t max_genome_len = 0;
 

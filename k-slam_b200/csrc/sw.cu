@@ -481,6 +481,7 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
 #define CNT_SLOW 2
 #define CNT_RETRY 4
 #define CNT_EXTRA 5
+#define CNT_BAND64 6
 
 __device__ __forceinline__ uint32_t classify(uint32_t m, uint32_t n, const SwScore &sc) {
   if (m == 0 || n == 0) return SWC_NONE;
@@ -561,7 +562,8 @@ k_sw_prepare_pairs(uint32_t n, const uint64_t *__restrict__ q_offs, const uint64
 // every alignment that scores S when rows + cols - 2 * ceil(S / match) + 1 <= 32 (sw_band.cuh).
 __global__ void __launch_bounds__(256)
 k_sw_rev_lists(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, uint32_t n, SwScore sc,
-               uint32_t *__restrict__ band_list, Rec16 *__restrict__ full_keys, uint32_t *__restrict__ counts) {
+               uint32_t *__restrict__ band_list, uint32_t *__restrict__ band64_list, uint32_t use64,
+               Rec16 *__restrict__ full_keys, uint32_t *__restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const SwTask t = tasks[i];
@@ -569,7 +571,9 @@ k_sw_rev_lists(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
   const SwRes r = res[i];
   if (r.score <= 0) return;
   const int32_t rows = r.read_end + 1, cols = r.ref_end + 1, a = ceil_div_pos(r.score, sc.match);
-  if ((t.flags & SWT_BAND) && rows + cols - 2 * a + 1 <= SWB_W) band_list[atomicAdd(&counts[CNT_BAND], 1u)] = i;
+  const int32_t width = rows + cols - 2 * a + 1;
+  if ((t.flags & SWT_BAND) && width <= 32) band_list[atomicAdd(&counts[CNT_BAND], 1u)] = i;
+  else if ((t.flags & SWT_BAND) && use64 && width <= SWB_MAXW) band64_list[atomicAdd(&counts[CNT_BAND64], 1u)] = i;
   else { const uint32_t k = atomicAdd(&counts[CNT_FULL], 1u); full_keys[k].key = (uint64_t)cols; full_keys[k].val = i; }
 }
 
@@ -616,38 +620,52 @@ static uint32_t read_count(kslam_ctx *c, uint32_t *d_counts, uint32_t *h_counts,
   return h_counts[which];
 }
 
-// one direction (forward or reverse) over the prepared lists: banded kernel first, its fallbacks join the
-// full-matrix list, which is bucketed by column count and run by k_sw_fast
+// one banded tier over a list, in chunks of CHUNK alignments (one band byte plane is reused)
+template <int MODE, int W>
+static void run_band(kslam_ctx *c, const SwPlanes &pl, const SwScore &sc, const uint32_t *list, uint32_t n_list,
+                     uint32_t *d_counts, uint32_t *next_list) {
+  if (!n_list) return;
+  SwWorkspace *w = c->sw;
+  cudaStream_t st = c->stream;
+  const uint32_t CHUNK = 4u << 20;                      // alignments per band-byte plane (<= 900 MB)
+  const uint32_t cmax = n_list < CHUNK ? n_list : CHUNK;
+  const uint32_t stride = (cmax + 1) & ~1u;
+  w->bandbytes.reserve((size_t)stride * SWB_PLANE_ROWS + 64);
+  uint8_t *bytes = w->bandbytes.as<uint8_t>();
+  for (uint32_t c0 = 0; c0 < n_list; c0 += CHUNK) {
+    const uint32_t cn = n_list - c0 < CHUNK ? n_list - c0 : CHUNK;
+    dim3 gridb((cn + 255) / 256, (SWB_MAXROWS + W) / 32);
+    k_band_bytes<MODE, W><<<gridb, 256, 0, st>>>(w->tasks.as<SwTask>(), list + c0, cn, pl, sc, w->res.as<SwRes>(), bytes, stride);
+    const uint32_t pairs = (cn + 1) / 2, blocks = (pairs + SWB_BLOCK - 1) / SWB_BLOCK;
+    k_sw_band<MODE, W><<<blocks, SWB_BLOCK, 0, st>>>(w->tasks.as<SwTask>(), list + c0, cn, sc, w->res.as<SwRes>(), bytes, stride,
+                                                      w->keys.as<Rec16>(), d_counts + CNT_FULL, next_list, d_counts + CNT_BAND64);
+    c->launches += 2;
+    CUDA_TRY(cudaGetLastError());
+  }
+}
+
+// one direction (forward or reverse) over the prepared lists: 32-wide band, then the 64-wide band for what it could
+// not prove (forward) / what needs it (reverse), then every remaining alignment through the full-matrix kernel,
+// bucketed by column count
 template <bool REVERSE>
 static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore &sc, uint32_t n_band, uint32_t *d_counts,
-                    uint32_t *h_counts, uint64_t *n_band_done, uint64_t *n_full_done) {
+                    uint32_t *h_counts, uint64_t *n_band_done, uint64_t *n_band64_done, uint64_t *n_full_done) {
   SwWorkspace *w = c->sw;
   cudaStream_t st = c->stream;
   SwTask *tasks = w->tasks.as<SwTask>();
   SwRes *res = w->res.as<SwRes>();
-  uint32_t *band_list = w->lists.as<uint32_t>();
+  uint32_t *list32 = w->lists.as<uint32_t>(), *list64 = list32 + 2 * (size_t)n;
   Rec16 *keys = w->keys.as<Rec16>(), *keys2 = w->keys2.as<Rec16>();
-  if (n_band) {
-    static int variant = -1;
-    if (variant < 0) { const char *e = getenv("KSLAM_SWB_VARIANT"); variant = e ? atoi(e) : 0; }
-    const uint32_t CHUNK = 4u << 20;                      // alignments per band-byte plane (768 MB)
-    const uint32_t cmax = n_band < CHUNK ? n_band : CHUNK;
-    const uint32_t stride = (cmax + 1) & ~1u;
-    w->bandbytes.reserve((size_t)stride * SWB_COLS + 64);
-    uint8_t *bytes = w->bandbytes.as<uint8_t>();
-    for (uint32_t c0 = 0; c0 < n_band; c0 += CHUNK) {
-      const uint32_t cn = n_band - c0 < CHUNK ? n_band - c0 : CHUNK;
-      const uint32_t *lst = band_list + c0;
-      dim3 gridb((cn + 255) / 256, SWB_COLS / 32);
-      k_band_bytes<REVERSE><<<gridb, 256, 0, st>>>(tasks, lst, cn, pl, sc, res, bytes, stride);
-      const uint32_t pairs = (cn + 1) / 2, blocks = (pairs + SWB_BLOCK - 1) / SWB_BLOCK;
-      if (variant == 1 && sc.gap_open >= sc.gap_extend)
-        k_sw_band<REVERSE, true><<<blocks, SWB_BLOCK, 0, st>>>(tasks, lst, cn, sc, res, bytes, stride, keys, d_counts + CNT_FULL);
-      else
-        k_sw_band<REVERSE, false><<<blocks, SWB_BLOCK, 0, st>>>(tasks, lst, cn, sc, res, bytes, stride, keys, d_counts + CNT_FULL);
-      c->launches += 2;
-      CUDA_TRY(cudaGetLastError());
-    }
+  if (REVERSE) {
+    run_band<1, 32>(c, pl, sc, list32, n_band, d_counts, nullptr);
+    const uint32_t n64 = read_count(c, d_counts, h_counts, CNT_BAND64);     // filled by k_sw_rev_lists
+    run_band<1, 64>(c, pl, sc, list64, n64, d_counts, nullptr);
+    *n_band64_done += n64;
+  } else {
+    run_band<0, 32>(c, pl, sc, list32, n_band, d_counts, c->sw_band64 ? list64 : nullptr);
+    const uint32_t n64 = read_count(c, d_counts, h_counts, CNT_BAND64);     // 32-wide failures that fit 64 diagonals
+    run_band<2, 64>(c, pl, sc, list64, n64, d_counts, nullptr);
+    *n_band64_done += n64;
   }
   const uint32_t n_full = read_count(c, d_counts, h_counts, CNT_FULL);
   *n_band_done += n_band; *n_full_done += n_full;
@@ -683,19 +701,21 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
   CUDA_TRY(cudaStreamSynchronize(st));
   uint32_t n_band = h_counts[CNT_BAND];
   const uint32_t n_slow = h_counts[CNT_SLOW];
-  uint64_t band_done = 0, full_done = 0;
-  sw_pass<false>(c, n, pl, sc, n_band, d_counts, h_counts, &band_done, &full_done);
-  c->tm.n_sw_fast = full_done; c->tm.n_sw_band = band_done; c->tm.n_sw_slow = n_slow;
+  uint64_t band_done = 0, band64_done = 0, full_done = 0;
+  sw_pass<false>(c, n, pl, sc, n_band, d_counts, h_counts, &band_done, &band64_done, &full_done);
+  c->tm.n_sw_fast = full_done; c->tm.n_sw_band = band_done; c->tm.n_sw_band64 = band64_done; c->tm.n_sw_slow = n_slow;
   cudaEvent_t e2 = tm_mark(c);
 
   // ---- reverse
   CUDA_TRY(cudaMemsetAsync(d_counts + CNT_BAND, 0, 8, st));   // band + full counters
-  k_sw_rev_lists<<<nb, 256, 0, st>>>(tasks, res, n, sc, band_list, w->keys.as<Rec16>(), d_counts);
+  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_BAND64, 0, 4, st));
+  k_sw_rev_lists<<<nb, 256, 0, st>>>(tasks, res, n, sc, band_list, band_list + 2 * (size_t)n, c->sw_band64 ? 1u : 0u,
+                                     w->keys.as<Rec16>(), d_counts);
   c->launches++;
   n_band = read_count(c, d_counts, h_counts, CNT_BAND);
-  uint64_t band_rev = 0, full_rev = 0;
-  sw_pass<true>(c, n, pl, sc, n_band, d_counts, h_counts, &band_rev, &full_rev);
-  c->tm.n_sw_band_rev = band_rev;
+  uint64_t band_rev = 0, band64_rev = 0, full_rev = 0;
+  sw_pass<true>(c, n, pl, sc, n_band, d_counts, h_counts, &band_rev, &band64_rev, &full_rev);
+  c->tm.n_sw_band_rev = band_rev + band64_rev;
   cudaEvent_t e3 = tm_mark(c);
 
   // ---- exact scalar fallback for shapes outside the fast kernels
@@ -761,7 +781,7 @@ static void sw_reserve(kslam_ctx *c, uint32_t n) {
   w->keys.reserve((size_t)n * sizeof(Rec16) + 64);
   w->keys2.reserve((size_t)n * sizeof(Rec16) + 64);
   w->items.reserve((size_t)(2 * ((n + 1) / 2)) * sizeof(uint2) + 64);
-  w->lists.reserve((size_t)n * 8 + 64);
+  w->lists.reserve((size_t)n * 12 + 64);      // band32 list | slow list | band64 list
   c->counters.reserve(64 * 8); c->h_counters.reserve(64 * 8);
   w->n = n;
 }
@@ -769,7 +789,7 @@ static void sw_reserve(kslam_ctx *c, uint32_t n) {
 static void sw_reset_timers(kslam_ctx *c) {
   c->tm.ms_sw_prepare = c->tm.ms_sw_forward = c->tm.ms_sw_reverse = c->tm.ms_sw_slow = c->tm.ms_sw_traceback = 0;
   c->tm.sw_cells_forward = c->tm.sw_cells_reverse = 0;
-  c->tm.n_sw_fast = c->tm.n_sw_slow = c->tm.n_sw_band = c->tm.n_sw_band_rev = 0;
+  c->tm.n_sw_fast = c->tm.n_sw_slow = c->tm.n_sw_band = c->tm.n_sw_band64 = c->tm.n_sw_band_rev = 0; c->tm.n_traceback_dp = 0;
 }
 
 void sw_align_seeds(kslam_ctx *c) {
