@@ -259,6 +259,7 @@ def main():
     value = total_pairs / t_res * 60 / 1e6
     e2e = total_pairs / t_e2e * 60 / 1e6
 
+    int_peak = al.measure_int_peak() if rank == 0 else 0.0
     if rank == 0:
         peak, peak_src = measured_peaks()
         ms = {k: v / args.steps for k, v in stage.items()}
@@ -274,6 +275,23 @@ def main():
         gcups = tm["sw_cells_forward"] / sw_s / 1e9 if sw_s > 0 else 0.0
         gcups_kernel = (tm["sw_cells_forward"] + tm["sw_cells_reverse"]) / ((ms["ms_sw_forward"] + ms["ms_sw_reverse"]) / 1e3) / 1e9 \
             if ms["ms_sw_forward"] + ms["ms_sw_reverse"] > 0 else 0.0
+        hbm_roof = {"bound": "hbm", "kernel": "k_rs_onesweep (read k-mer LSD pass)", "achieved": achieved, "peak": peak,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "share_of_step": ms["ms_sort"] / (t_res / args.steps * 1e3),
+                    "note": "algorithmic 32 B/record/pass; duration = (sort stage incl. histogram)/8 passes, CUDA events on the ctx stream"}
+        # SW sweeps (k_sw_band / k_sw_fast): integer-pipe bound. 7 ALU thread-ops (1 PRMT + 6 s16x2 DPX) per two cells;
+        # numerator = cells the sweep kernels actually computed (band cells, not matrix cells), denominator = the
+        # issue rate of VIADDMNMX.S16x2 measured on this GPU right now (kslam_measure_int_peak).
+        sweep_s = (ms["ms_sw_forward"] + ms["ms_sw_reverse"]) / 1e3
+        int_ops = 3.5 * tm["sw_cells_computed"]
+        int_ach = int_ops / sweep_s / 1e12 if sweep_s > 0 else 0.0
+        int_roof = {"bound": "int-pipe", "kernel": "k_sw_band / k_sw_fast (SW forward + reverse sweeps)", "achieved": int_ach,
+                    "peak": int_peak / 1e12, "unit": "T int16x2 thread-ops/s", "frac": int_ach / (int_peak / 1e12) if int_peak else None,
+                    "traffic": None, "peak_source": "measured live: dependency-free VIADDMNMX.S16x2 issue-rate microbenchmark (kslam_measure_int_peak)",
+                    "share_of_step": sweep_s * 1e3 / (t_res / args.steps * 1e3),
+                    "note": "3.5 ALU thread-ops per computed cell (1 PRMT + 6 DPX per s16x2 cell pair); cells computed = band cells "
+                            "(32 or 64 per row) or the full matrix for fallback alignments; CUDA events on the ctx stream"}
+        dominant = int_roof if sweep_s * 1e3 >= ms["ms_sort"] else hbm_roof
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "int16x2 (SW) / u64 (k-mers)", "data": "synthetic",
@@ -282,13 +300,12 @@ def main():
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                "gpu_launches": int(launches),
                "clocks": clocks,
-               "roofline": {"bound": "hbm", "kernel": "k_rs_onesweep (read k-mer LSD pass)", "achieved": achieved, "peak": peak,
-                            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                            "note": "algorithmic 32 B/record/pass; duration = (sort stage incl. histogram)/8 passes, CUDA events on the ctx stream"},
+               "roofline": dominant, "roofline_hbm": hbm_roof, "roofline_int": int_roof,
                "kmer_join_gbs": join_gbs, "sw_gcups": gcups, "sw_kernel_gcups_fwd_plus_rev": gcups_kernel,
                "stage_ms": ms,
-               "counts": {k: tm[k] for k in ("n_read_kmers", "n_sorted_kmers", "n_genome_kmers", "n_raw_seeds", "n_seeds", "n_pairs", "n_sw_fast",
-                                             "n_sw_slow", "sw_cells_forward", "sw_cells_reverse", "n_sort_passes")},
+               "counts": {k: tm[k] for k in ("n_read_kmers", "n_sorted_kmers", "n_genome_kmers", "n_raw_seeds", "n_seeds", "n_pairs",
+                                             "n_sw_band", "n_sw_band64", "n_sw_fast", "n_sw_slow", "n_sw_band_rev",
+                                             "sw_cells_forward", "sw_cells_reverse", "sw_cells_computed", "n_sort_passes")},
                "genome_index_build_s": t_load}
         if world == 1 and not args.no_cpu_baseline:
             cs = args.cpu_sample or CPU_SAMPLE[args.workload]

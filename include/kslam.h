@@ -95,7 +95,7 @@ typedef struct {
   float ms_h2d, ms_pack, ms_extract, ms_sort, ms_join, ms_seed_sort, ms_unique;
   float ms_sw_prepare, ms_sw_forward, ms_sw_reverse, ms_sw_traceback, ms_sw_slow, ms_d2h, ms_pair, ms_total;
   uint64_t n_read_kmers, n_sorted_kmers, n_genome_kmers, n_raw_seeds, n_seeds, n_sort_passes;
-  uint64_t sw_cells_forward, sw_cells_reverse, n_sw_fast, n_sw_slow, n_sw_band, n_sw_band64, n_sw_band_rev, n_traceback_dp, n_pairs;
+  uint64_t sw_cells_forward, sw_cells_reverse, sw_cells_computed, n_sw_fast, n_sw_slow, n_sw_band, n_sw_band64, n_sw_band_rev, n_traceback_dp, n_pairs;
   uint64_t kernel_launches;
 } kslam_timings;
 
@@ -143,6 +143,9 @@ int kslam_sort_records(kslam_ctx *ctx, kslam_kmer *recs, uint64_t n, uint32_t lo
                        float *device_ms /* may be NULL */);
 
 int kslam_get_timings(const kslam_ctx *ctx, kslam_timings *out);
+/* Issue-rate microbenchmark of the packed-int16 DPX op the SW sweeps are made of (VIADDMNMX.S16x2), in thread-ops
+ * per second: the denominator of the integer-pipe roofline. */
+int kslam_measure_int_peak(kslam_ctx *ctx, double *ops_per_s);
 /* Prefilter (default on): read k-mers whose hash misses a bitmap of the genome k-mers are dropped while they are
  * extracted — they cannot seed (Overlap.h:157,236-239) — so only the survivors are written, sorted and joined.
  * Results are identical either way; with the filter off the read k-mer tap holds every record (KMer.h:160-181). */

@@ -68,7 +68,7 @@ class Timings(C.Structure):
                                          "ms_sw_traceback", "ms_sw_slow", "ms_d2h", "ms_pair", "ms_total")] + \
                [("_pad", C.c_float)] + \
                [(n, C.c_uint64) for n in ("n_read_kmers", "n_sorted_kmers", "n_genome_kmers", "n_raw_seeds", "n_seeds", "n_sort_passes",
-                                          "sw_cells_forward", "sw_cells_reverse", "n_sw_fast", "n_sw_slow", "n_sw_band", "n_sw_band64", "n_sw_band_rev", "n_traceback_dp", "n_pairs",
+                                          "sw_cells_forward", "sw_cells_reverse", "sw_cells_computed", "n_sw_fast", "n_sw_slow", "n_sw_band", "n_sw_band64", "n_sw_band_rev", "n_traceback_dp", "n_pairs",
                                           "kernel_launches")]
 
     def as_dict(self):
@@ -119,6 +119,7 @@ def lib():
     L.kslam_sort_records.argtypes = [vp, vp, u64, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
     L.kslam_get_timings.argtypes = [vp, C.POINTER(Timings)]
     L.kslam_set_debug_taps.argtypes = [vp, i32]
+    L.kslam_measure_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.kslam_set_prefilter.argtypes = [vp, i32]
     L.kslam_set_sw_band.argtypes = [vp, i32]
     _lib = L
@@ -287,6 +288,11 @@ class Aligner:
         t = Timings()
         self._check(self.L.kslam_get_timings(self.h, C.byref(t)), "kslam_get_timings")
         return t.as_dict()
+
+    def measure_int_peak(self) -> float:
+        v = C.c_double()
+        self._check(self.L.kslam_measure_int_peak(self.h, C.byref(v)), "kslam_measure_int_peak")
+        return v.value
 
     def set_prefilter(self, on: bool):
         self._check(self.L.kslam_set_prefilter(self.h, int(on)), "kslam_set_prefilter")

@@ -127,6 +127,14 @@ int kslam_set_debug_taps(kslam_ctx *ctx, int keep) {
   return KSLAM_OK;
 }
 
+int kslam_measure_int_peak(kslam_ctx *c, double *ops_per_s) {
+  API_BEGIN(c)
+  if (!ops_per_s) return fail(c, KSLAM_ERR_ARG, "null output");
+  *ops_per_s = sw_measure_int_peak(c);
+  return KSLAM_OK;
+  API_END(c)
+}
+
 int kslam_get_timings(const kslam_ctx *ctx, kslam_timings *out) {
   if (!ctx || !out) return KSLAM_ERR_ARG;
   *out = ctx->tm;

@@ -154,6 +154,7 @@ void join_and_unique(kslam_ctx *c);
 void sw_align_seeds(kslam_ctx *c);
 void sw_align_pairs(kslam_ctx *c, uint64_t n, kslam_overlap *out_dev, uint32_t *cig_dev);
 void sw_workspace_free(kslam_ctx *c);
+double sw_measure_int_peak(kslam_ctx *c);
 // pair.cu
 void pair_overlaps(kslam_ctx *c);
 

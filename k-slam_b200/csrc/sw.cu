@@ -46,8 +46,10 @@ struct __align__(16) SwTask {
 
 struct __align__(16) SwRes {
   int32_t score, ref_end, read_end, ref_begin, read_begin;
-  uint32_t flags, pad0, pad1;
+  uint32_t flags, pad0, pad1;   // flags: low byte = KSLAM_FLAG_*, bits 8-9 forward tier, bits 10-11 reverse tier
 };
+#define SWR_FWD_TIER(t) ((uint32_t)(t) << 8)    // 0 = full-matrix / scalar kernel, 1 = 32-wide band, 2 = 64-wide band
+#define SWR_REV_TIER(t) ((uint32_t)(t) << 10)
 
 struct SwPlanes {
   const uint64_t *q_sbits; const uint32_t *q_nmask;
@@ -428,7 +430,7 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
     kslam_overlap o = ov[idx];
     o.sw_score = (uint32_t)r.score & 0xffffu;
     o.ref_begin = r.ref_begin; o.ref_end = r.ref_end; o.query_begin = r.read_begin; o.query_end = r.read_end;
-    o.cigar_len = 0; o.cigar_off = idx * sc.cigar_cap; o.flags = r.flags;
+    o.cigar_len = 0; o.cigar_off = idx * sc.cigar_cap; o.flags = r.flags & 0xffu;
     const bool rev = (t.flags & SWT_REV) != 0;
     uint32_t *cig = cigs ? cigs + (size_t)idx * sc.cigar_cap : nullptr;
     bool deferred = false;
@@ -595,15 +597,64 @@ k_sw_make_items(const Rec16 *__restrict__ sorted, uint32_t n_fast, uint2 *__rest
   items[w] = i0;
 }
 
+// out[0..1]: matrix cells (readLen x windowLen) of the forward / reverse sweeps — the GCUPS numerator.
+// out[2]: cells actually computed by the sweep kernels (every band-eligible task tries the 32-wide tier; tiers 2
+// and 0 add their own), the numerator of the integer-pipe roofline (7 ALU ops per two cells).
 __global__ void __launch_bounds__(256)
 k_sw_cells(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, uint32_t n, unsigned long long *out) {
-  unsigned long long fw = 0, rv = 0;
+  unsigned long long fw = 0, rv = 0, comp = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    fw += (unsigned long long)tasks[i].m * tasks[i].n;
-    if (res[i].score > 0) rv += (unsigned long long)(res[i].read_end + 1) * (unsigned long long)(res[i].ref_end + 1);
+    const SwTask t = tasks[i]; const SwRes r = res[i];
+    fw += (unsigned long long)t.m * t.n;
+    const uint32_t ft = (r.flags >> 8) & 3u, rt = (r.flags >> 10) & 3u;
+    if (t.flags & SWT_BAND) comp += 32ull * t.m;
+    if (ft == 2) comp += 64ull * t.m; else if (ft == 0) comp += (unsigned long long)t.m * t.n;
+    if (r.score > 0) {
+      const unsigned long long rows = (unsigned long long)(r.read_end + 1), cols = (unsigned long long)(r.ref_end + 1);
+      rv += rows * cols;
+      comp += rt == 1 ? 32ull * rows : (rt == 2 ? 64ull * rows : rows * cols);
+    }
   }
-  for (int d = 16; d; d >>= 1) { fw += __shfl_xor_sync(0xffffffffu, fw, d); rv += __shfl_xor_sync(0xffffffffu, rv, d); }
-  if ((threadIdx.x & 31) == 0) { atomicAdd(out, fw); atomicAdd(out + 1, rv); }
+  for (int d = 16; d; d >>= 1) {
+    fw += __shfl_xor_sync(0xffffffffu, fw, d); rv += __shfl_xor_sync(0xffffffffu, rv, d); comp += __shfl_xor_sync(0xffffffffu, comp, d);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, fw); atomicAdd(out + 1, rv); atomicAdd(out + 2, comp); }
+}
+
+// Integer-pipe issue-rate microbenchmark: dependency-free streams of the DPX op the sweeps are made of
+// (VIADDMNMX.S16x2). 8 independent chains per thread; the result is thread-ops per second.
+__global__ void __launch_bounds__(256)
+k_int_peak(uint32_t *__restrict__ out, uint32_t iters, uint32_t b, uint32_t c) {
+  uint32_t a[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) a[k] = threadIdx.x * 0x10001u + k;
+  for (uint32_t i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = __viaddmax_s16x2(a[k], b, c);
+  }
+  uint32_t x = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) x ^= a[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+
+double sw_measure_int_peak(kslam_ctx *c) {
+  const uint32_t blocks = (uint32_t)c->num_sms * 8, iters = 4096;
+  DevBuf buf; buf.reserve((size_t)blocks * 256 * 4);
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    CUDA_TRY(cudaEventRecord(e0, c->stream));
+    k_int_peak<<<blocks, 256, 0, c->stream>>>(buf.as<uint32_t>(), iters, 0x00010001u, 0x00020002u);
+    CUDA_TRY(cudaEventRecord(e1, c->stream));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms; CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  buf.release();
+  return (double)blocks * 256.0 * iters * 8.0 / (best * 1e-3);
 }
 
 // ---------------------------------------------------------------- host orchestration
@@ -760,13 +811,13 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
   }
   cudaEvent_t e5 = tm_mark(c);
   unsigned long long *d_cells = c->counters.as<unsigned long long>() + 8;
-  CUDA_TRY(cudaMemsetAsync(d_cells, 0, 16, st));
+  CUDA_TRY(cudaMemsetAsync(d_cells, 0, 24, st));
   k_sw_cells<<<c->num_sms * 2, 256, 0, st>>>(tasks, res, n, d_cells);
   c->launches++;
   unsigned long long *h_cells = c->h_counters.as<unsigned long long>() + 8;
-  CUDA_TRY(cudaMemcpyAsync(h_cells, d_cells, 16, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h_cells, d_cells, 24, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  c->tm.sw_cells_forward = h_cells[0]; c->tm.sw_cells_reverse = h_cells[1];
+  c->tm.sw_cells_forward = h_cells[0]; c->tm.sw_cells_reverse = h_cells[1]; c->tm.sw_cells_computed = h_cells[2];
   c->tm.ms_sw_forward = tm_ms(e1, e2);
   c->tm.ms_sw_reverse = tm_ms(e2, e3);
   c->tm.ms_sw_slow = tm_ms(e3, e4);

@@ -193,6 +193,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
       if (best) {
         res[idx].ref_begin = r0.ref_end - (int32_t)(4095u - best);
         res[idx].read_begin = r0.read_end - (int32_t)brow;
+        res[idx].flags = r0.flags | SWR_REV_TIER(W / 32);
       } else {                      // cannot happen when the bound holds; never guess: hand over to the full kernel
         const uint32_t k = atomicAdd(fb_count, 1u);
         fb_keys[k].key = (uint64_t)(r0.ref_end + 1); fb_keys[k].val = idx;
@@ -203,7 +204,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
       const bool proven = S > 0 && c0[al] <= -(rows[al] - a) && (cols[al] - a) <= c0[al] + (W - 1);
       if (proven) {
         SwRes o;
-        o.flags = 0; o.pad0 = o.pad1 = 0; o.ref_begin = -1; o.read_begin = 0;
+        o.flags = SWR_FWD_TIER(W / 32); o.pad0 = o.pad1 = 0; o.ref_begin = -1; o.read_begin = 0;
         o.score = S; o.ref_end = (int32_t)(4095u - (best & 4095u)); o.read_end = (int32_t)brow;
         res[idx] = o;
       } else if (MODE == 0 && next_list && S > 0 && rows[al] + cols[al] - 2 * a + 1 <= SWB_MAXW) {
