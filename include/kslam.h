@@ -131,6 +131,33 @@ int kslam_ssw_upload(kslam_ctx *ctx, uint64_t n, const char *q, const uint64_t *
                      const uint64_t *roffs);
 int kslam_ssw_resident(kslam_ctx *ctx, kslam_overlap *out /* may be NULL */, uint32_t *cigar_pool /* may be NULL */);
 
+/* ---- k-mer-range partitioned database (BASELINE config 4: the genome k-mer list exceeds one GPU) ----
+ * Rank `part` of `n_parts` keeps the packed genomes and the prefilter bitmap (replicated) plus the slice of the sorted
+ * genome k-mer list (KMer.h:388-398) whose kMerInt lies in [splitters[part], splitters[part+1]); splitters are the
+ * quantiles of a sorted sample of the genome k-mers, a pure function of the database, so every rank derives the same
+ * ones. Equal k-mers share an owner, so no pile (Overlap.h:153-199) is split — the invariant of Overlap.h:285-287.
+ * One batch then takes two exchanges of 16-byte records, carried by the caller (NCCL all-to-all in
+ * k-slam_b200/dist.py); the pointers handed out below are DEVICE pointers into ctx-owned buffers:
+ *   1. kslam_upload_reads, kslam_part_route_kmers: read k-mer records (job-global read id = read_id_base + index,
+ *      all ids < 2^30) grouped by key owner; counts[p] records go to rank p.
+ *   2. receiver: kslam_part_recv_buffer(total) -> fill it -> kslam_part_join: sort, merge-join against the local
+ *      range, raw matches {read record, genome record} grouped by read owner (id_bases[n_parts+1] = first global
+ *      read id of every rank); counts[p] matches go back to rank p.
+ *   3. read owner: kslam_part_match_buffer(total) -> fill it -> kslam_part_finish: match -> seed (Overlap.h:185-193
+ *      needs the read length), seed sort + fuzzy unique, Smith-Waterman. Results as kslam_align_batch, bit-identical
+ *      to the unpartitioned path on the same reads; kslam_pair_batch follows as usual. */
+int kslam_load_genomes_part(kslam_ctx *ctx, uint64_t n_entries, const char *bases, const uint64_t *offs,
+                            uint32_t part, uint32_t n_parts /* 1..64 */);
+int kslam_get_partition(const kslam_ctx *ctx, uint32_t *part, uint32_t *n_parts, uint64_t *splitters /* n_parts+1, may be NULL */,
+                        uint64_t *n_genome_kmers_total /* may be NULL */);
+int kslam_part_route_kmers(kslam_ctx *ctx, uint32_t read_id_base, const void **dev_records, uint64_t *counts /* n_parts */);
+int kslam_part_recv_buffer(kslam_ctx *ctx, uint64_t n_records, void **dev_ptr);
+int kslam_part_join(kslam_ctx *ctx, uint64_t n_records, const uint32_t *id_bases /* n_parts+1 */,
+                    const void **dev_matches, uint64_t *counts /* n_parts */);
+int kslam_part_match_buffer(kslam_ctx *ctx, uint64_t n_matches, void **dev_ptr);
+int kslam_part_finish(kslam_ctx *ctx, uint64_t n_matches, uint32_t read_id_base, int fetch_results,
+                      kslam_alignments *out /* may be NULL */);
+
 /* Stage taps for parity tests (results of the last batch; copy to caller buffers; pass NULL to query
  * the count). Returns the count or a negative error. */
 int64_t kslam_get_genome_kmers(kslam_ctx *ctx, kslam_kmer *out, uint64_t cap);      /* sorted, resident */

@@ -122,6 +122,14 @@ def lib():
     L.kslam_measure_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.kslam_set_prefilter.argtypes = [vp, i32]
     L.kslam_set_sw_band.argtypes = [vp, i32]
+    u32 = C.c_uint32
+    L.kslam_load_genomes_part.argtypes = [vp, u64, vp, vp, u32, u32]
+    L.kslam_get_partition.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), vp, C.POINTER(u64)]
+    L.kslam_part_route_kmers.argtypes = [vp, u32, C.POINTER(vp), vp]
+    L.kslam_part_recv_buffer.argtypes = [vp, u64, C.POINTER(vp)]
+    L.kslam_part_join.argtypes = [vp, u64, vp, C.POINTER(vp), vp]
+    L.kslam_part_match_buffer.argtypes = [vp, u64, C.POINTER(vp)]
+    L.kslam_part_finish.argtypes = [vp, u64, u32, i32, C.POINTER(_Alignments)]
     _lib = L
     return L
 
@@ -176,6 +184,7 @@ class Aligner:
             raise KslamError(f"kslam_create failed ({rc}): {self.L.kslam_last_error(None).decode()}")
         self.h = h
         self._keep = []
+        self.n_parts = 1
 
     # -- lifecycle
     def close(self):
@@ -208,6 +217,52 @@ class Aligner:
     def load_genomes(self, bases, offs):
         bases, offs = _u8(bases), _u64(offs)
         self._check(self.L.kslam_load_genomes(self.h, len(offs) - 1, _ptr(bases), _ptr(offs)), "kslam_load_genomes")
+        self.n_parts = 1
+
+    # -- k-mer-range partitioned database (include/kslam.h "partitioned"; protocol in dist.py)
+    def load_genomes_part(self, bases, offs, part, n_parts):
+        bases, offs = _u8(bases), _u64(offs)
+        self._check(self.L.kslam_load_genomes_part(self.h, len(offs) - 1, _ptr(bases), _ptr(offs), part, n_parts),
+                    "kslam_load_genomes_part")
+        self.n_parts = n_parts
+
+    def partition(self):
+        part, n_parts, total = C.c_uint32(), C.c_uint32(), C.c_uint64()
+        self._check(self.L.kslam_get_partition(self.h, C.byref(part), C.byref(n_parts), None, C.byref(total)), "kslam_get_partition")
+        spl = np.zeros(n_parts.value + 1, dtype=np.uint64)
+        self._check(self.L.kslam_get_partition(self.h, None, None, _ptr(spl), None), "kslam_get_partition")
+        return dict(part=part.value, n_parts=n_parts.value, splitters=spl, n_genome_kmers_total=total.value)
+
+    def part_route_kmers(self, read_id_base):
+        """-> (device pointer of the k-mer records grouped by key owner, counts per owner)"""
+        ptr = C.c_void_p()
+        counts = np.zeros(self.n_parts, dtype=np.uint64)
+        self._check(self.L.kslam_part_route_kmers(self.h, read_id_base, C.byref(ptr), _ptr(counts)), "kslam_part_route_kmers")
+        return ptr.value or 0, counts
+
+    def part_recv_buffer(self, n_records):
+        ptr = C.c_void_p()
+        self._check(self.L.kslam_part_recv_buffer(self.h, n_records, C.byref(ptr)), "kslam_part_recv_buffer")
+        return ptr.value or 0
+
+    def part_join(self, n_records, id_bases):
+        """-> (device pointer of the raw matches grouped by read owner, counts per owner)"""
+        ptr = C.c_void_p()
+        idb = np.ascontiguousarray(id_bases, dtype=np.uint32)
+        assert len(idb) == self.n_parts + 1
+        counts = np.zeros(self.n_parts, dtype=np.uint64)
+        self._check(self.L.kslam_part_join(self.h, n_records, _ptr(idb), C.byref(ptr), _ptr(counts)), "kslam_part_join")
+        return ptr.value or 0, counts
+
+    def part_match_buffer(self, n_matches):
+        ptr = C.c_void_p()
+        self._check(self.L.kslam_part_match_buffer(self.h, n_matches, C.byref(ptr)), "kslam_part_match_buffer")
+        return ptr.value or 0
+
+    def part_finish(self, n_matches, read_id_base, fetch=True, copy=True):
+        out = _Alignments()
+        self._check(self.L.kslam_part_finish(self.h, n_matches, read_id_base, int(fetch), C.byref(out)), "kslam_part_finish")
+        return self._alignments(out, copy) if fetch else int(out.n_overlaps)
 
     def align_batch(self, bases, offs, copy=True) -> Alignments:
         bases, offs = _u8(bases), _u64(offs)

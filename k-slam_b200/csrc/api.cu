@@ -24,22 +24,11 @@ float tm_ms(cudaEvent_t a, cudaEvent_t b) {
   return ms;
 }
 
-static int fail(kslam_ctx *c, int code, const std::string &msg) {
+int api_fail(kslam_ctx *c, int code, const std::string &msg) {
   if (c) c->err = msg; else g_create_err = msg;
   return code;
 }
-
-#define API_BEGIN(ctx)                                                                          \
-  if (!(ctx)) return KSLAM_ERR_ARG;                                                            \
-  try {                                                                                         \
-    if (cudaSetDevice((ctx)->device) != cudaSuccess) return fail((ctx), KSLAM_ERR_CUDA, "cudaSetDevice failed");
-#define API_END(ctx)                                                                            \
-  } catch (const CudaError &e) {                                                                \
-    char buf[512];                                                                              \
-    snprintf(buf, sizeof buf, "%s:%d: %s: %s", e.file, e.line, e.what, cudaGetErrorString(e.e)); \
-    cudaGetLastError();                                                                         \
-    return fail((ctx), e.e == cudaErrorMemoryAllocation ? KSLAM_ERR_NOMEM : KSLAM_ERR_CUDA, buf); \
-  } catch (const std::exception &e) { return fail((ctx), KSLAM_ERR_NOMEM, e.what()); }
+static int fail(kslam_ctx *c, int code, const std::string &msg) { return api_fail(c, code, msg); }
 
 extern "C" {
 
@@ -98,7 +87,8 @@ void kslam_destroy(kslam_ctx *c) {
   c->genomes.release(); c->reads.release(); c->swq.release(); c->swr.release();
   DevBuf *bufs[] = {&c->g_keys, &c->g_vals, &c->recA, &c->recB, &c->sort_hist, &c->scan_tmp, &c->counters,
                     &c->raw_seeds, &c->seedA, &c->seedB, &c->seed_keep, &c->seeds, &c->ov, &c->cig, &c->pair_keys,
-                    &c->pair_keys2, &c->ov_sorted, &c->cig_sorted, &c->pair_cnt, &c->pairs, &c->bitmap};
+                    &c->pair_keys2, &c->ov_sorted, &c->cig_sorted, &c->pair_cnt, &c->pairs, &c->bitmap, &c->d_bounds,
+                    &c->part_send, &c->part_recv, &c->part_tmp, &c->part_m, &c->part_msend, &c->part_mrecv};
   for (DevBuf *b : bufs) b->release();
   HostBuf *hb[] = {&c->h_stage, &c->h_counters, &c->h_ov, &c->h_cig, &c->h_ov_sorted, &c->h_cig_sorted, &c->h_pairs};
   for (HostBuf *b : hb) b->release();
@@ -156,6 +146,25 @@ __global__ void __launch_bounds__(256) k_flip_idflags(Rec16 *__restrict__ r, uin
     r[i].val ^= 0xffffffffull;
 }
 
+}  // extern "C"
+
+void finish_genome_index(kslam_ctx *c, DevBuf &a, DevBuf &b, uint64_t n) {
+  uint64_t blocks = (n + 255) / 256, maxb = (uint64_t)c->num_sms * 16;
+  if (blocks > maxb) blocks = maxb;
+  k_flip_idflags<<<(unsigned)blocks, 256, 0, c->stream>>>(a.as<Rec16>(), n);
+  uint64_t passes = 0;
+  Rec16 *cur = radix_sort(c, a.as<Rec16>(), b.as<Rec16>(), n, 1, 0, 32, &passes);   // ~id_flags ascending
+  cur = radix_sort(c, cur, cur == a.as<Rec16>() ? b.as<Rec16>() : a.as<Rec16>(), n, 0, 0, 64, &passes);
+  k_flip_idflags<<<(unsigned)blocks, 256, 0, c->stream>>>(cur, n);
+  c->g_keys.reserve((size_t)n * 8 + 64); c->g_vals.reserve((size_t)n * 8 + 64);
+  k_split_recs<<<(unsigned)blocks, 256, 0, c->stream>>>(cur, n, c->g_keys.as<uint64_t>(), c->g_vals.as<uint64_t>());
+  c->launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+}
+
+extern "C" {
+
 int kslam_load_genomes(kslam_ctx *c, uint64_t n, const char *bases, const uint64_t *offs) {
   API_BEGIN(c)
   if (!offs || (n && !bases && offs[n] != offs[0])) return fail(c, KSLAM_ERR_ARG, "null genome buffers");
@@ -170,20 +179,11 @@ int kslam_load_genomes(kslam_ctx *c, uint64_t n, const char *bases, const uint64
     DevBuf a, b;
     a.reserve((size_t)c->n_gk * sizeof(Rec16)); b.reserve((size_t)c->n_gk * sizeof(Rec16));
     extract_kmers(c, c->genomes, true, c->prm.genome_gap, a.as<Rec16>());
-    uint64_t blocks = (c->n_gk + 255) / 256, maxb = (uint64_t)c->num_sms * 16;
-    if (blocks > maxb) blocks = maxb;
-    k_flip_idflags<<<(unsigned)blocks, 256, 0, c->stream>>>(a.as<Rec16>(), c->n_gk);
-    uint64_t passes = 0;
-    Rec16 *cur = radix_sort(c, a.as<Rec16>(), b.as<Rec16>(), c->n_gk, 1, 0, 32, &passes);   // ~id_flags ascending
-    cur = radix_sort(c, cur, cur == a.as<Rec16>() ? b.as<Rec16>() : a.as<Rec16>(), c->n_gk, 0, 0, 64, &passes);
-    k_flip_idflags<<<(unsigned)blocks, 256, 0, c->stream>>>(cur, c->n_gk);
-    c->g_keys.reserve((size_t)c->n_gk * 8 + 64); c->g_vals.reserve((size_t)c->n_gk * 8 + 64);
-    k_split_recs<<<(unsigned)blocks, 256, 0, c->stream>>>(cur, c->n_gk, c->g_keys.as<uint64_t>(), c->g_vals.as<uint64_t>());
-    c->launches += 3;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    finish_genome_index(c, a, b, c->n_gk);
     a.release(); b.release();
   }
+  c->part = 0; c->n_parts = 1; c->n_gk_total = c->n_gk;
+  c->splitters.assign({0ull, ~0ull});
   build_prefilter(c);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->tm.n_genome_kmers = c->n_gk;
@@ -280,6 +280,25 @@ int kslam_align_batch(kslam_ctx *c, uint64_t n, const char *bases, const uint64_
   rc = kslam_align_resident(c, 1, out);
   c->tm.ms_pack = pack;
   return rc;
+}
+
+int kslam_part_finish(kslam_ctx *c, uint64_t n_matches, uint32_t read_id_base, int fetch, kslam_alignments *out) {
+  API_BEGIN(c)
+  if (!c->reads_loaded) return fail(c, KSLAM_ERR_STATE, "kslam_upload_reads first");
+  if (n_matches * sizeof(Rec16) > c->part_mrecv.cap) return fail(c, KSLAM_ERR_ARG, "more matches than kslam_part_match_buffer reserved");
+  c->ev_used = 0;
+  cudaEvent_t e0 = tm_mark(c);
+  part_matches_to_seeds(c, n_matches, read_id_base);
+  seed_sort_unique(c);
+  sw_align_seeds(c);
+  cudaEvent_t e3 = tm_mark(c);
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->tm.ms_total = tm_ms(e0, e3);
+  c->aligned = true;
+  if (fetch) fetch_alignments(c, out);
+  else if (out) { out->n_overlaps = c->n_seeds; out->overlaps = nullptr; out->n_cigar_words = 0; out->cigar_pool = nullptr; }
+  return KSLAM_OK;
+  API_END(c)
 }
 
 int kslam_pair_batch(kslam_ctx *c, int fetch, kslam_pairs *out) {

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <exception>
 #include <vector>
 #include "../../include/kslam.h"
 
@@ -123,6 +124,13 @@ struct kslam_ctx {
   HostBuf h_ov_sorted, h_cig_sorted, h_pairs;
   uint64_t n_sorted = 0, n_pairs = 0;
 
+  // k-mer-range partitioned database (dist.cu)
+  uint32_t part = 0, n_parts = 1;
+  std::vector<uint64_t> splitters;   // n_parts + 1 lower bounds; part p owns keys in [splitters[p], splitters[p+1])
+  DevBuf d_bounds;                   // u64[64] bucket bounds on the device (key splitters or read-id bases)
+  DevBuf part_send, part_recv, part_tmp, part_m, part_msend, part_mrecv;
+  uint64_t n_gk_total = 0;
+
   // microbench / Aligner::Align batch
   PackedSeqs swq, swr;
   bool sw_loaded = false;
@@ -140,7 +148,9 @@ void pack_sequences(kslam_ctx *c, PackedSeqs &s, uint64_t n, const char *bases, 
 // kmer.cu
 void extract_kmers(kslam_ctx *c, const PackedSeqs &s, bool is_gb, uint32_t gap, Rec16 *out);
 void build_prefilter(kslam_ctx *c);
-uint64_t extract_read_kmers_filtered(kslam_ctx *c, const PackedSeqs &s, Rec16 *out);
+uint64_t extract_read_kmers_filtered(kslam_ctx *c, const PackedSeqs &s, Rec16 *out, uint32_t id_base = 0);
+void extract_genome_kmers_range(kslam_ctx *c, const PackedSeqs &s, uint32_t gap, uint64_t i_begin, uint64_t i_stride,
+                                uint64_t n_out, Rec16 *out);
 // radix_sort.cu
 // Sorts n records by bits [lo_bit, hi_bit) of their .key (word 0) or .val (word 1); stable.
 // Returns the buffer (a or b) holding the result; *passes_done is incremented per executed pass.
@@ -150,17 +160,48 @@ Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, u
 void exclusive_scan_u32(kslam_ctx *c, const uint32_t *in, uint32_t *out, uint64_t n, uint64_t *total_dev);
 // join.cu
 void join_and_unique(kslam_ctx *c);
+void seed_sort_unique(kslam_ctx *c);
+uint64_t run_join(kslam_ctx *c, const Rec16 *R, uint64_t n_r, bool match, DevBuf &outbuf);
+void matches_to_seeds(kslam_ctx *c, const Rec16 *m, uint64_t n, uint32_t id_base);
+// api.cu: sort an extracted genome k-mer list into the reference's order and split it into g_keys / g_vals
+void finish_genome_index(kslam_ctx *c, DevBuf &a, DevBuf &b, uint64_t n);
 // sw.cu
 void sw_align_seeds(kslam_ctx *c);
 void sw_align_pairs(kslam_ctx *c, uint64_t n, kslam_overlap *out_dev, uint32_t *cig_dev);
 void sw_workspace_free(kslam_ctx *c);
 double sw_measure_int_peak(kslam_ctx *c);
+// dist.cu
+void part_matches_to_seeds(kslam_ctx *c, uint64_t n_matches, uint32_t read_id_base);
 // pair.cu
 void pair_overlaps(kslam_ctx *c);
+
+// api.cu: error plumbing of the C ABI (no exception crosses the boundary)
+int api_fail(kslam_ctx *c, int code, const std::string &msg);
+#define API_BEGIN(ctx)                                                                          \
+  if (!(ctx)) return KSLAM_ERR_ARG;                                                            \
+  try {                                                                                         \
+    if (cudaSetDevice((ctx)->device) != cudaSuccess) return api_fail((ctx), KSLAM_ERR_CUDA, "cudaSetDevice failed");
+#define API_END(ctx)                                                                            \
+  } catch (const CudaError &e) {                                                                \
+    char buf[512];                                                                              \
+    snprintf(buf, sizeof buf, "%s:%d: %s: %s", e.file, e.line, e.what, cudaGetErrorString(e.e)); \
+    cudaGetLastError();                                                                         \
+    return api_fail((ctx), e.e == cudaErrorMemoryAllocation ? KSLAM_ERR_NOMEM : KSLAM_ERR_CUDA, buf); \
+  } catch (const std::exception &e) { return api_fail((ctx), KSLAM_ERR_NOMEM, e.what()); }
 
 // event-based stage timing
 cudaEvent_t tm_mark(kslam_ctx *c);
 float tm_ms(cudaEvent_t a, cudaEvent_t b);
+
+// prefilter hash (kmer.cu): position of a k-mer in the 2^bits-bit bitmap of genome k-mers
+__device__ __forceinline__ uint64_t kmer_hash(uint64_t k, uint32_t bits) {
+  return (k * 0x9E3779B97F4A7C15ull) >> (64 - bits);
+}
+static inline uint32_t prefilter_bits(uint64_t n_genome_kmers) {
+  uint32_t b = 0;
+  while (b < 64 && (1ull << b) < n_genome_kmers * 16) b++;
+  return b < 26 ? 26 : (b > 34 ? 34 : b);
+}
 
 static inline uint32_t ceil_log2_u64(uint64_t x) {
   uint32_t b = 0;

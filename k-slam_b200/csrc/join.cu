@@ -54,6 +54,10 @@ __device__ __forceinline__ uint64_t warp_bound(const uint64_t *__restrict__ keys
   return lo + __popc(m);
 }
 
+// MATCH = false: emit packed seeds (needs the read lengths, i.e. the reads live on this GPU).
+// MATCH = true (k-mer-range partitioned database, dist.cu): emit the raw match {read record val, genome record val};
+// the GPU that owns the read turns it into a seed (k_matches_to_seeds) because only it knows the read length.
+template <bool MATCH>
 __global__ void __launch_bounds__(JN_THREADS)
 k_join(const Rec16 *__restrict__ R, uint64_t n_r, const uint64_t *__restrict__ gkeys,
        const uint64_t *__restrict__ gvals, uint64_t n_g, const uint64_t *__restrict__ read_offs,
@@ -120,9 +124,10 @@ k_join(const Rec16 *__restrict__ R, uint64_t n_r, const uint64_t *__restrict__ g
     if (cnt[i]) {
       uint32_t idf = (uint32_t)rval[i], r_off = (uint32_t)(rval[i] >> 32);
       uint32_t rid = idf & 0x3FFFFFFFu, r_rc = (idf >> 30) & 1;
-      uint32_t rlen = (uint32_t)(__ldg(&read_offs[rid + 1]) - __ldg(&read_offs[rid]));
+      uint32_t rlen = MATCH ? 0u : (uint32_t)(__ldg(&read_offs[rid + 1]) - __ldg(&read_offs[rid]));
       for (uint32_t j = 0; j < cnt[i]; j++) {
         uint64_t gv = __ldg(&gvals[g_lo + first[i] + j]);
+        if (MATCH) { *reinterpret_cast<ulonglong2 *>(out + o) = make_ulonglong2(rval[i], gv); o++; continue; }
         uint32_t gf = (uint32_t)gv, g_off = (uint32_t)(gv >> 32);
         uint32_t g_rc = (gf >> 30) & 1;
         uint32_t off = g_rc ? rlen - r_off - KSLAM_K : r_off;           // Overlap.h:185-189
@@ -172,37 +177,88 @@ k_unique_compact(const Rec16 *__restrict__ s, uint64_t n, const uint32_t *__rest
   }
 }
 
+// Owner side of the partitioned path: raw matches {read record val, genome record val} -> packed seeds, with the
+// batch-local read id (global id - id_base) and the read length only this GPU knows (Overlap.h:185-193).
+__global__ void __launch_bounds__(256)
+k_matches_to_seeds(const Rec16 *__restrict__ m, uint64_t n, uint32_t id_base, const uint64_t *__restrict__ read_offs,
+                   uint32_t bias, Rec16 *__restrict__ out) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const ulonglong2 r = __ldg(reinterpret_cast<const ulonglong2 *>(m + i));
+    const uint32_t idf = (uint32_t)r.x, r_off = (uint32_t)(r.x >> 32);
+    const uint32_t rid = (idf & 0x3FFFFFFFu) - id_base, r_rc = (idf >> 30) & 1;
+    const uint32_t gf = (uint32_t)r.y, g_off = (uint32_t)(r.y >> 32), g_rc = (gf >> 30) & 1;
+    const uint32_t rlen = (uint32_t)(__ldg(&read_offs[rid + 1]) - __ldg(&read_offs[rid]));
+    const uint32_t off = g_rc ? rlen - r_off - KSLAM_K : r_off;
+    const Rec16 s = pack_seed(rid, gf & 0x3FFFFFFFu, (int32_t)(g_off - off), g_rc != r_rc, bias);
+    *reinterpret_cast<ulonglong2 *>(out + i) = make_ulonglong2(s.key, s.val);
+  }
+}
+
+void matches_to_seeds(kslam_ctx *c, const Rec16 *m, uint64_t n, uint32_t id_base) {
+  c->n_raw = n;
+  if (!n) return;
+  c->seedA.reserve((size_t)n * sizeof(Rec16));
+  uint64_t blocks = (n + 255) / 256, maxb = (uint64_t)c->num_sms * 16;
+  if (blocks > maxb) blocks = maxb;
+  k_matches_to_seeds<<<(unsigned)blocks, 256, 0, c->stream>>>(m, n, id_base, c->reads.offs.as<uint64_t>(), c->reads.max_len,
+                                                              c->seedA.as<Rec16>());
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+}
+
+// merge-join of n_r sorted read records against the resident genome list; returns the number of records emitted
+// into `outbuf` (packed seeds, or raw matches when `match` is set). The buffer is regrown once on overflow.
+uint64_t run_join(kslam_ctx *c, const Rec16 *R, uint64_t n_r, bool match, DevBuf &outbuf) {
+  cudaStream_t st = c->stream;
+  unsigned long long *d_cnt = c->counters.as<unsigned long long>();
+  unsigned long long *h_cnt = c->h_counters.as<unsigned long long>();
+  const uint32_t bias = c->reads.max_len;
+  if (!n_r || !c->n_gk) return 0;
+  uint64_t cap = outbuf.cap / sizeof(Rec16);
+  if (cap < (1u << 20)) { outbuf.reserve((size_t)(n_r / 8 + (1u << 20)) * sizeof(Rec16)); cap = outbuf.cap / sizeof(Rec16); }
+  const uint64_t tiles = (n_r + JN_TILE - 1) / JN_TILE;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 8, st));
+    if (match)
+      k_join<true><<<(unsigned)tiles, JN_THREADS, 0, st>>>(R, n_r, c->g_keys.as<uint64_t>(), c->g_vals.as<uint64_t>(), c->n_gk,
+                                                           nullptr, outbuf.as<Rec16>(), cap, d_cnt, bias);
+    else
+      k_join<false><<<(unsigned)tiles, JN_THREADS, 0, st>>>(R, n_r, c->g_keys.as<uint64_t>(), c->g_vals.as<uint64_t>(), c->n_gk,
+                                                            c->reads.offs.as<uint64_t>(), outbuf.as<Rec16>(), cap, d_cnt, bias);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_cnt[0] <= cap) break;
+    if (attempt == 1) throw CudaError{cudaErrorMemoryAllocation, "seed buffer overflow after regrow", __FILE__, __LINE__};
+    outbuf.reserve((size_t)h_cnt[0] * sizeof(Rec16));   // exact size is now known: grow once and redo
+    cap = outbuf.cap / sizeof(Rec16);
+  }
+  return h_cnt[0];
+}
+
 void join_and_unique(kslam_ctx *c) {
+  c->counters.reserve(64 * 8);
+  c->h_counters.reserve(64 * 8);
+  c->n_raw = 0; c->n_seeds = 0;
+  cudaEvent_t e0 = tm_mark(c);
+  c->n_raw = run_join(c, c->sorted_rk, c->n_rk, false, c->seedA);
+  cudaEvent_t e1 = tm_mark(c);
+  seed_sort_unique(c);
+  c->tm.ms_join = tm_ms(e0, e1);
+}
+
+// seed sort + fuzzy unique (Overlap.h:277-295) over the c->n_raw packed seeds in c->seedA
+void seed_sort_unique(kslam_ctx *c) {
   cudaStream_t st = c->stream;
   c->counters.reserve(64 * 8);
   c->h_counters.reserve(64 * 8);
   unsigned long long *d_cnt = c->counters.as<unsigned long long>();
   unsigned long long *h_cnt = c->h_counters.as<unsigned long long>();
   const uint32_t bias = c->reads.max_len;
-  c->n_raw = 0; c->n_seeds = 0;
-  cudaEvent_t e0 = tm_mark(c);
-  if (c->n_rk && c->n_gk) {
-    uint64_t cap = c->seedA.cap / sizeof(Rec16);
-    if (cap < (1u << 20)) { c->seedA.reserve((size_t)(c->n_rk / 8 + (1u << 20)) * sizeof(Rec16)); cap = c->seedA.cap / sizeof(Rec16); }
-    const uint64_t tiles = (c->n_rk + JN_TILE - 1) / JN_TILE;
-    for (int attempt = 0; attempt < 2; attempt++) {
-      CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 8, st));
-      k_join<<<(unsigned)tiles, JN_THREADS, 0, st>>>(c->sorted_rk, c->n_rk, c->g_keys.as<uint64_t>(),
-                                                     c->g_vals.as<uint64_t>(), c->n_gk, c->reads.offs.as<uint64_t>(),
-                                                     c->seedA.as<Rec16>(), cap, d_cnt, bias);
-      c->launches++;
-      CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaStreamSynchronize(st));
-      if (h_cnt[0] <= cap) break;
-      if (attempt == 1) throw CudaError{cudaErrorMemoryAllocation, "seed buffer overflow after regrow", __FILE__, __LINE__};
-      c->seedA.reserve((size_t)h_cnt[0] * sizeof(Rec16));   // exact size is now known: grow once and redo
-      cap = c->seedA.cap / sizeof(Rec16);
-    }
-    c->n_raw = h_cnt[0];
-  }
+  c->n_seeds = 0;
   cudaEvent_t e1 = tm_mark(c);
-  c->tm.ms_join = 0; c->tm.n_raw_seeds = c->n_raw;
+  c->tm.n_raw_seeds = c->n_raw;
   cudaEvent_t e2 = e1, e3 = e1;
   if (c->n_raw) {
     c->seedB.reserve((size_t)c->n_raw * sizeof(Rec16));
@@ -245,7 +301,6 @@ void join_and_unique(kslam_ctx *c) {
     e3 = tm_mark(c);
   }
   CUDA_TRY(cudaStreamSynchronize(st));
-  c->tm.ms_join = tm_ms(e0, e1);
   c->tm.ms_seed_sort = tm_ms(e1, e2);
   c->tm.ms_unique = tm_ms(e2, e3);
   c->tm.n_seeds = c->n_seeds;

@@ -62,9 +62,12 @@ k_extract_reads(const uint64_t *__restrict__ kbits, const uint64_t *__restrict__
 __global__ void __launch_bounds__(256)
 k_extract_flat(const uint64_t *__restrict__ kbits, const uint64_t *__restrict__ offs,
                const uint64_t *__restrict__ word_off, const uint64_t *__restrict__ kmer_off,
-               uint64_t n_seqs, uint64_t n_recs, uint32_t gap, bool is_gb, Rec16 *__restrict__ out) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_recs;
-       i += (uint64_t)gridDim.x * blockDim.x) {
+               uint64_t n_seqs, uint64_t n_recs, uint32_t gap, bool is_gb, Rec16 *__restrict__ out,
+               uint64_t i_begin, uint64_t i_stride) {
+  // output slot t holds flat record i = i_begin + t * i_stride (whole list: 0 / 1; chunks and samples: dist path)
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n_recs;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = i_begin + t * i_stride;
     uint64_t lo = 0, hi = n_seqs;
     while (hi - lo > 1) {
       uint64_t mid = (lo + hi) >> 1;
@@ -73,7 +76,7 @@ k_extract_flat(const uint64_t *__restrict__ kbits, const uint64_t *__restrict__ 
     uint64_t seq = lo;
     uint64_t len = __ldg(&offs[seq + 1]) - __ldg(&offs[seq]);
     uint64_t p = (i - __ldg(&kmer_off[seq])) * gap;
-    emit_kmer(out + i, kmer_at(kbits, __ldg(&word_off[seq]), (uint32_t)p), (uint32_t)seq, (uint32_t)p,
+    emit_kmer(out + t, kmer_at(kbits, __ldg(&word_off[seq]), (uint32_t)p), (uint32_t)seq, (uint32_t)p,
               (uint32_t)len, is_gb);
   }
 }
@@ -83,9 +86,6 @@ k_extract_flat(const uint64_t *__restrict__ kbits, const uint64_t *__restrict__ 
 // record), and zero k-mers never do (Overlap.h:236-239). A read record whose hashed k-mer misses the bitmap of
 // genome k-mers therefore cannot contribute to any pile and is dropped before it is ever written to HBM; false
 // positives are harmless (the join drops them). The seed multiset is unchanged; the sort shrinks ~10x.
-__device__ __forceinline__ uint64_t kmer_hash(uint64_t k, uint32_t bits) {
-  return (k * 0x9E3779B97F4A7C15ull) >> (64 - bits);
-}
 
 __global__ void __launch_bounds__(256)
 k_bitmap_build(const uint64_t *__restrict__ gkeys, uint64_t n, uint32_t bits, uint32_t *__restrict__ bitmap) {
@@ -104,7 +104,8 @@ k_bitmap_build(const uint64_t *__restrict__ gkeys, uint64_t n, uint32_t bits, ui
 __global__ void __launch_bounds__(256)
 k_extract_reads_filtered(const uint64_t *__restrict__ kbits, const uint64_t *__restrict__ offs,
                          const uint64_t *__restrict__ word_off, uint64_t n_seqs, const uint32_t *__restrict__ bitmap,
-                         uint32_t bits, Rec16 *__restrict__ out, unsigned long long *__restrict__ counter) {
+                         uint32_t bits, Rec16 *__restrict__ out, unsigned long long *__restrict__ counter,
+                         uint32_t id_base) {
   __shared__ __align__(16) Rec16 s_buf[8][XF_WBUF];
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
@@ -123,7 +124,7 @@ k_extract_reads_filtered(const uint64_t *__restrict__ kbits, const uint64_t *__r
       uint64_t key = 0, val = 0;
       if (p < nk) {
         uint64_t f = kmer_at(kbits, woff, p), rc = revcomp32(f);
-        uint32_t flags = (uint32_t)seq & 0x3FFFFFFFu;
+        uint32_t flags = ((uint32_t)seq + id_base) & 0x3FFFFFFFu;   // id_base != 0: job-global read ids (dist.cu)
         if (f < rc) { key = f; val = (uint64_t)flags | ((uint64_t)p << 32); }
         else { key = rc; val = (uint64_t)(flags | 0x40000000u) | ((uint64_t)(len - KSLAM_K - p) << 32); }
         if (key != 0) { uint64_t h = kmer_hash(key, bits); keep = (__ldg(&bitmap[h >> 5]) >> (h & 31)) & 1; }
@@ -156,9 +157,7 @@ k_extract_reads_filtered(const uint64_t *__restrict__ kbits, const uint64_t *__r
 void build_prefilter(kslam_ctx *c) {
   c->filter_bits = 0;
   if (!c->n_gk) return;
-  uint32_t bits = ceil_log2_u64(c->n_gk * 16);
-  if (bits < 26) bits = 26;
-  if (bits > 34) bits = 34;
+  uint32_t bits = prefilter_bits(c->n_gk);
   c->bitmap.reserve((size_t)1 << (bits - 3));
   CUDA_TRY(cudaMemsetAsync(c->bitmap.p, 0, (size_t)1 << (bits - 3), c->stream));
   uint64_t blocks = (c->n_gk + 255) / 256, maxb = (uint64_t)c->num_sms * 16;
@@ -170,7 +169,7 @@ void build_prefilter(kslam_ctx *c) {
 }
 
 // returns the number of records written (== s.n_kmers without the filter)
-uint64_t extract_read_kmers_filtered(kslam_ctx *c, const PackedSeqs &s, Rec16 *out) {
+uint64_t extract_read_kmers_filtered(kslam_ctx *c, const PackedSeqs &s, Rec16 *out, uint32_t id_base) {
   if (!s.n_kmers) return 0;
   unsigned long long *d_cnt = c->counters.as<unsigned long long>() + 2;
   unsigned long long *h_cnt = c->h_counters.as<unsigned long long>() + 2;
@@ -178,7 +177,7 @@ uint64_t extract_read_kmers_filtered(kslam_ctx *c, const PackedSeqs &s, Rec16 *o
   uint64_t blocks = (s.n * 32 + 255) / 256, maxb = (uint64_t)c->num_sms * 8;
   if (blocks > maxb) blocks = maxb;
   k_extract_reads_filtered<<<(unsigned)blocks, 256, 0, c->stream>>>(s.kbits.as<uint64_t>(), s.offs.as<uint64_t>(),
-      s.word_off.as<uint64_t>(), s.n, c->bitmap.as<uint32_t>(), c->filter_bits, out, d_cnt);
+      s.word_off.as<uint64_t>(), s.n, c->bitmap.as<uint32_t>(), c->filter_bits, out, d_cnt, id_base);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -202,8 +201,21 @@ void extract_kmers(kslam_ctx *c, const PackedSeqs &s, bool is_gb, uint32_t gap, 
     if (blocks > maxb) blocks = maxb;
     k_extract_flat<<<(unsigned)blocks, 256, 0, c->stream>>>(s.kbits.as<uint64_t>(), s.offs.as<uint64_t>(),
                                                             s.word_off.as<uint64_t>(), s.kmer_off.as<uint64_t>(),
-                                                            s.n, s.n_kmers, gap, is_gb, out);
+                                                            s.n, s.n_kmers, gap, is_gb, out, 0, 1);
   }
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+}
+
+// n_out genome records starting at flat record i_begin, every i_stride-th one (chunked index build and splitter
+// sampling of the k-mer-range partitioned database, dist.cu)
+void extract_genome_kmers_range(kslam_ctx *c, const PackedSeqs &s, uint32_t gap, uint64_t i_begin, uint64_t i_stride,
+                                uint64_t n_out, Rec16 *out) {
+  if (!n_out) return;
+  uint64_t blocks = (n_out + 255) / 256, maxb = (uint64_t)c->num_sms * 16;
+  if (blocks > maxb) blocks = maxb;
+  k_extract_flat<<<(unsigned)blocks, 256, 0, c->stream>>>(s.kbits.as<uint64_t>(), s.offs.as<uint64_t>(), s.word_off.as<uint64_t>(),
+                                                          s.kmer_off.as<uint64_t>(), s.n, n_out, gap, true, out, i_begin, i_stride);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
 }

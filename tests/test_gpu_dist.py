@@ -1,0 +1,108 @@
+"""GPU tier: the k-mer-range partitioned path (include/kslam.h "partitioned") on ONE GPU.
+
+`world` logical ranks run as threads of this process, each with its own kslam_ctx holding one key range of the genome
+k-mer list; the two all-to-alls are device-to-device copies (LoopbackExchange). Every rank's alignments, CIGARs and
+pair records must be bit-identical to the oracle on that rank's reads, and the key ranges must tile the sorted
+genome k-mer list exactly."""
+import threading
+
+import numpy as np
+import pytest
+
+import _lib as T
+from test_gpu_parity import FIELDS, check_overlaps
+
+pytestmark = pytest.mark.gpu
+
+
+def run_partitioned(pkg, gb, go, reads, world, report_cigar=True):
+    """reads[r] = (bases, offs) of logical rank r. Returns per-rank (Alignments, Pairs, genome k-mer tap, partition, stats)."""
+    import torch
+    from kslam_b200 import dist as kd
+    grp = kd.LoopbackGroup(world)
+    out, errs = [None] * world, []
+
+    def run(rank):
+        try:
+            torch.cuda.set_device(0)
+            with pkg.Aligner(report_cigar=report_cigar) as al:
+                al.load_genomes_part(gb, go, rank, world)
+                sb, so = reads[rank]
+                al.upload_reads(sb, so)
+                res, stats = kd.align_partitioned(kd.CudaEngine(al, 0), grp.exchange(rank), len(so) - 1)
+                pairs = al.pair_batch()
+                out[rank] = (res, pairs, al.genome_kmers(), al.partition(), stats, al.seeds())
+        except Exception as e:   # noqa: BLE001
+            errs.append(e); grp.barrier.abort()
+
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert not errs, errs
+    return out
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_partitioned_matches_oracle(pkg, world):
+    from kslam_b200 import shard
+    n_pairs = 600
+    gb, go, rb, ro = pkg.synth.adversarial_set(seed=41, n_genomes=8, glen=8000, n_pairs=n_pairs)
+    reads = [shard.slice_reads(rb, ro, *shard.pair_range(n_pairs, world, r)) for r in range(world)]
+    out = run_partitioned(pkg, gb, go, reads, world)
+    P = T.default_params(report_cigar=1)
+    # the key ranges tile the reference's sorted genome list (KMer.h:388-398) exactly
+    gk_all = np.concatenate([o[2] for o in out])
+    want_gk = T.ko_sort_kmers(T.ko_extract(gb, go, True, 16))
+    assert np.array_equal(gk_all, want_gk)
+    spl = out[0][3]["splitters"]
+    for r, o in enumerate(out):
+        assert np.array_equal(o[3]["splitters"], spl), "ranks disagree on the splitters"
+        k = o[2]["kmer"]
+        assert (k >= spl[r]).all() and (r == world - 1 or (k < spl[r + 1]).all())
+    assert sum(o[4]["kmers_sent"] for o in out) == sum(o[4]["kmers_received"] for o in out)
+    for r, (res, pairs, _, _, stats, seeds) in enumerate(out):
+        sb, so = reads[r]
+        want = T.ko_pipeline(gb, go, sb, so, P)
+        assert np.array_equal(seeds, want["seeds"])
+        check_overlaps(res.overlaps, res.cigar_pool, want["overlaps"], want["cigar_pool"])
+        check_overlaps(pairs.sorted_overlaps, pairs.cigar_pool, want["pair_sorted_overlaps"], want["cigar_pool"], cigars=False)
+        assert np.array_equal(pairs.pairs, want["pairs"])
+
+
+def test_partitioned_equals_replicated_at_volume(pkg):
+    """20k pairs against 16 x 300 kbp genomes over 4 key ranges: identical to the replicated-index path."""
+    from kslam_b200 import shard
+    world, n_pairs = 4, 20000
+    gb, go = pkg.synth.random_genomes(16, 300_000, seed=5)
+    rb, ro, _ = pkg.synth.paired_reads(gb, go, n_pairs, seed=6)
+    reads = [shard.slice_reads(rb, ro, *shard.pair_range(n_pairs, world, r)) for r in range(world)]
+    out = run_partitioned(pkg, gb, go, reads, world, report_cigar=False)
+    sizes = [len(o[2]) for o in out]
+    assert max(sizes) < 1.2 * (sum(sizes) / world), f"unbalanced key ranges {sizes}"      # sampled quantiles balance
+    with pkg.Aligner(report_cigar=False) as al:
+        al.load_genomes(gb, go)
+        for r in range(world):
+            sb, so = reads[r]
+            want = al.align_batch(sb, so)
+            wp = al.pair_batch()
+            got, gp = out[r][0], out[r][1]
+            assert len(want.overlaps) > 1000
+            for f in FIELDS:
+                assert np.array_equal(got.overlaps[f], want.overlaps[f]), (r, f)
+            assert np.array_equal(gp.pairs, wp.pairs)
+
+
+def test_partitioned_empty_rank_and_errors(pkg):
+    gb, go, rb, ro = pkg.synth.adversarial_set(seed=42, n_genomes=6, glen=5000, n_pairs=100)
+    empty = (np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    out = run_partitioned(pkg, gb, go, [(rb, ro), empty], 2)
+    want = T.ko_pipeline(gb, go, rb, ro, T.default_params(report_cigar=1))
+    check_overlaps(out[0][0].overlaps, out[0][0].cigar_pool, want["overlaps"], want["cigar_pool"])
+    assert len(out[1][0].overlaps) == 0 and len(out[1][1].pairs) == 0
+    with pkg.Aligner() as al:
+        with pytest.raises(pkg.KslamError):
+            al.load_genomes_part(gb, go, 2, 2)          # part out of range
+        with pytest.raises(pkg.KslamError):
+            al.load_genomes_part(gb, go, 0, 65)         # more than 64 parts
+        al.load_genomes_part(gb, go, 0, 2)
+        with pytest.raises(pkg.KslamError):
+            al.part_route_kmers(0)                      # no reads uploaded
