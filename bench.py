@@ -32,6 +32,16 @@ METRIC = "M read-pairs/min end-to-end at 1/2/4/8 B200; SW GCUPS; k-mer join GB/s
 UNIT = "M read-pairs/min"
 
 
+# stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner ...) are sent to stderr
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _REAL_STDOUT.write(json.dumps(obj) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -106,6 +116,11 @@ def make_workload(pkg, name, pairs, seed_shift=0):
         gb, go = synth.tree_genomes(500, 2_000_000, seed=1)
         desc = (f"config2-shape (metagenomic): {pairs} x 150bp FR pairs vs 500 x 2 Mbp genomes in a 5/25/100/500 "
                 "phylogeny (multi-genome piles)")
+    elif name == "config4":
+        ng = int(os.environ.get("KSLAM_CONFIG4_GENOMES", "500"))
+        gb, go = synth.random_genomes(ng, 4_000_000, seed=1)
+        desc = (f"config4-shape (k-mer-range partitioned DB, scaled): {pairs} x 150bp FR pairs per GPU vs {ng} x 4 Mbp genomes "
+                f"({ng * 250_000 / 1e6:.0f} M genome k-mer records range-partitioned across the GPUs, NCCL all-to-all both ways)")
     else:
         raise SystemExit(f"unknown workload {name}")
     rb, ro, _ = synth.paired_reads(gb, go, pairs, seed=2 + seed_shift)
@@ -161,12 +176,12 @@ def run_reference_arm(args, pkg):
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                             "sample": f"{sample} pairs of the workload per step (same genomes), alignToDatabase+screen+getPairedOverlaps"},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
-DEFAULT_PAIRS = {"config1": 1_000_000, "config2": 10_000_000}
+DEFAULT_PAIRS = {"config1": 1_000_000, "config2": 10_000_000, "config4": 2_000_000}
 # bounded CPU samples (pairs): sized for roughly 10-20 s of host work per step on a 16-core box
-CPU_SAMPLE = {"config1": 400_000, "config2": 150_000}
+CPU_SAMPLE = {"config1": 400_000, "config2": 150_000, "config4": 100_000}
 
 
 def main():
@@ -175,7 +190,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kslam", choices=["kslam", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("KSLAM_BENCH_WORKLOAD", "config2"), choices=["config1", "config2"])
+    ap.add_argument("--workload", default=os.environ.get("KSLAM_BENCH_WORKLOAD", "config2"), choices=["config1", "config2", "config4"])
     ap.add_argument("--pairs", type=int, default=0, help="read pairs per batch per GPU (default: the config's)")
     ap.add_argument("--ref-sample", type=int, default=0, help="pairs per step for the CPU reference arm (0 = per workload)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs for the cpu_baseline leg (rank 0, N=1; 0 = per workload)")
@@ -208,8 +223,33 @@ def main():
     rb_host = rb_pin.numpy()
     al = pkg.Aligner(report_cigar=False, device=local)
     al.set_debug_taps(False)
+    partitioned = args.workload == "config4"
     t0 = time.time()
-    al.load_genomes(gb, go)
+    if partitioned:
+        from kslam_b200 import dist as kd
+        al.load_genomes_part(gb, go, rank, world)
+        engine = kd.CudaEngine(al, local)
+        exch = kd.TorchExchange(device=torch.device("cuda", local)) if world > 1 else kd.LoopbackGroup(1).exchange(0)
+        n_reads = len(ro) - 1
+        xstats = {}
+
+        def step_resident():
+            _, st = kd.align_partitioned(engine, exch, n_reads, fetch=False)
+            xstats.update(st)
+            al.pair_batch(fetch=False)
+
+        def step_e2e():
+            al.upload_reads(rb_host, ro)
+            res, _ = kd.align_partitioned(engine, exch, n_reads, fetch=True)
+            return res, al.pair_batch(fetch=True, copy=False)
+    else:
+        al.load_genomes(gb, go)
+
+        def step_resident():
+            al.align_resident(fetch=False); al.pair_batch(fetch=False)
+
+        def step_e2e():
+            return al.align_batch(rb_host, ro, copy=False), al.pair_batch(fetch=True, copy=False)
     t_load = time.time() - t0
     log(f"[bench r{rank}] genome index built in {t_load:.2f}s")
 
@@ -219,14 +259,14 @@ def main():
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
-        al.align_resident(fetch=False); al.pair_batch(fetch=False)
+        step_resident()
     launches0 = al.timings()["kernel_launches"]
     barrier()
     tw0 = time.perf_counter()
     tw_first = tw0
     stage = {}
     for _ in range(args.steps):
-        al.align_resident(fetch=False); al.pair_batch(fetch=False)
+        step_resident()
         tm = al.timings()
         for k, v in tm.items():
             if k.startswith("ms_"):
@@ -239,11 +279,11 @@ def main():
 
     # ---- e2e: host buffers in, results back on the host ------------------------------------------
     for _ in range(max(1, args.warmup - 1)):
-        res = al.align_batch(rb_host, ro, copy=False); pr = al.pair_batch(fetch=True, copy=False)
+        res, pr = step_e2e()
     barrier()
     tw0 = time.perf_counter()
     for _ in range(args.steps):
-        res = al.align_batch(rb_host, ro, copy=False); pr = al.pair_batch(fetch=True, copy=False)
+        res, pr = step_e2e()
     barrier()
     tw3 = time.perf_counter()
     t_e2e = tw3 - tw0
@@ -295,7 +335,8 @@ def main():
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": t_res / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "int16x2 (SW) / u64 (k-mers)", "data": "synthetic",
-               "config": {"workload": desc, "batch_pairs_per_gpu": pairs, "sharding": f"read pairs, {world} ranks, no collective",
+               "config": {"workload": desc, "batch_pairs_per_gpu": pairs, "sharding": (f"genome k-mer list range-partitioned over {world} ranks + read pairs per rank; all-to-all of k-mer records "
+                                       f"and of raw matches (NCCL)" if partitioned else f"read pairs, {world} ranks, no collective"),
                           "l2": "inputs larger than L2 (3.8 GB+ of k-mer records per step)", "report_cigar": False},
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                "gpu_launches": int(launches),
@@ -307,12 +348,15 @@ def main():
                                              "n_sw_band", "n_sw_band64", "n_sw_fast", "n_sw_slow", "n_sw_band_rev",
                                              "sw_cells_forward", "sw_cells_reverse", "sw_cells_computed", "n_sort_passes")},
                "genome_index_build_s": t_load}
+        if partitioned:
+            out["exchange"] = {"rank0_records_per_step": xstats, "record_bytes": 16,
+                               "partition": {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in al.partition().items() if k != "splitters"}}
         if world == 1 and not args.no_cpu_baseline:
             cs = args.cpu_sample or CPU_SAMPLE[args.workload]
             v, dt, cores, kind = cpu_reference_sample(pkg, gb, go, cs, False, 0)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                    "sample": f"{cs} pairs of the same workload in {dt:.1f}s (alignToDatabase+screen+getPairedOverlaps, genome k-mers re-extracted and re-sorted per batch as the reference does)"}
-        print(json.dumps(out), flush=True)
+        emit(out)
     al.close()
     if world > 1:
         dist.destroy_process_group()

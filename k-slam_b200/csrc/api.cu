@@ -106,8 +106,9 @@ int kslam_set_prefilter(kslam_ctx *ctx, int on) {
 
 int kslam_set_sw_band(kslam_ctx *ctx, int on) {
   if (!ctx) return KSLAM_ERR_ARG;
-  ctx->sw_band = on != 0;          // on = 1: 32-wide tier only; on >= 2 (default): 32- and 64-wide tiers
+  ctx->sw_band = on != 0;          // 1: 32-wide sweep tier only; 2: + 64-wide tier; >= 3 (default): + direct tiers
   ctx->sw_band64 = on >= 2;
+  ctx->sw_tiers = on >= 3;
   return KSLAM_OK;
 }
 

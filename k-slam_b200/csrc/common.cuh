@@ -96,6 +96,7 @@ struct kslam_ctx {
   uint32_t filter_bits = 0;
   bool prefilter = true;
   bool sw_band64 = true;   // second banded tier (64 diagonals) for what the 32-wide sweep cannot prove
+  bool sw_tiers = true;    // direct tiers (8 / 16 / 32 / 64 diagonals) picked from the seed-diagonal lower bound
   bool sw_band = true;     // banded SW kernel with exactness proof + full-matrix fallback (sw_band.cuh)
   uint32_t max_genome_len = 0;
 

@@ -46,10 +46,17 @@ struct __align__(16) SwTask {
 
 struct __align__(16) SwRes {
   int32_t score, ref_end, read_end, ref_begin, read_begin;
-  uint32_t flags, pad0, pad1;   // flags: low byte = KSLAM_FLAG_*, bits 8-9 forward tier, bits 10-11 reverse tier
+  uint32_t flags, pad0, pad1;   // flags: low byte = KSLAM_FLAG_*, bits 8-10 forward tier, bits 11-13 reverse tier
 };
-#define SWR_FWD_TIER(t) ((uint32_t)(t) << 8)    // 0 = full-matrix / scalar kernel, 1 = 32-wide band, 2 = 64-wide band
-#define SWR_REV_TIER(t) ((uint32_t)(t) << 10)
+// tier code of the sweep that produced the result: 0 = full-matrix / scalar kernel, 1..4 = band of 8 / 16 / 32 / 64 diagonals
+#define SWR_TIER_OF_W(W) ((W) == 8 ? 1u : (W) == 16 ? 2u : (W) == 32 ? 3u : 4u)
+#define SWR_FWD_TIER(t) ((uint32_t)(t) << 8)
+#define SWR_REV_TIER(t) ((uint32_t)(t) << 11)
+// work-list tier of an alignment (byte arrays tier_f / tier_r): 0..3 = band of 8 / 16 / 32 / 64 diagonals placed exactly
+// on the interval a known score bound allows (no verification needed), 4 = 32 diagonals centred, sweep-and-verify,
+// 255 = not in a band list
+#define SWT_TIER_SWEEP 4u
+#define SWT_TIER_NONE 255u
 
 struct SwPlanes {
   const uint64_t *q_sbits; const uint32_t *q_nmask;
@@ -62,7 +69,7 @@ struct SwScore {
 };
 
 struct SwWorkspace {
-  DevBuf tasks, res, keys, keys2, items, lists, bandbytes, tb_scratch;
+  DevBuf tasks, res, keys, keys2, items, lists, bandbytes, tb_scratch, tier;
   uint64_t n = 0;
 };
 
@@ -484,6 +491,88 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
 #define CNT_RETRY 4
 #define CNT_EXTRA 5
 #define CNT_BAND64 6
+#define CNT_TIER 16    // 5 counters: alignments per work-list tier
+#define CNT_CUR 24     // 5 cursors of k_tier_scatter
+#define CNT_WORDS 32
+
+// ---- lower bound of the optimal score from the seed's own diagonal ------------------------------------------
+// 32 two-bit codes of `plane` starting at base p of the sequence that begins at word w_word (p may be negative or run
+// past the window: those lanes are masked by the caller; guard words keep the reads inside the allocation)
+__device__ __forceinline__ uint64_t bits_at(const uint64_t *__restrict__ plane, uint64_t w_word, int32_t p) {
+  const int32_t wi = p >> 5; const uint32_t sh = (uint32_t)p & 31u;
+  const uint64_t lo = wi >= 0 ? __ldg(&plane[w_word + wi]) : 0ull;
+  if (sh == 0) return lo;
+  const uint64_t hi = wi + 1 >= 0 ? __ldg(&plane[w_word + wi + 1]) : 0ull;
+  return (lo >> (2 * sh)) | (hi << (64 - 2 * sh));
+}
+__device__ __forceinline__ uint32_t mask_at(const uint32_t *__restrict__ plane, uint64_t w_word, int32_t p) {
+  const int32_t wi = p >> 5; const uint32_t sh = (uint32_t)p & 31u;
+  const uint32_t lo = wi >= 0 ? __ldg(&plane[w_word + wi]) : 0u, hi = wi + 1 >= 0 ? __ldg(&plane[w_word + wi + 1]) : 0u;
+  return __funnelshift_r(lo, hi, sh);
+}
+__device__ __forceinline__ uint64_t pair_mask(uint32_t m) {     // bit b -> bits 2b and 2b+1
+  uint64_t x = m;
+  x = (x | (x << 16)) & 0x0000FFFF0000FFFFull; x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+  x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full; x = (x | (x << 2)) & 0x3333333333333333ull;
+  x = (x | (x << 1)) & 0x5555555555555555ull;
+  return x * 3ull;
+}
+// Best ungapped local segment (Kadane) along matrix diagonal j = i + d0, in the orientation Align sees. It is the score
+// of a real local alignment, hence a LOWER BOUND L of the optimum: every alignment scoring >= L lies inside the offsets
+// [-(m - a), n - a] with a = ceil(L / match) (sw_band.cuh), which picks the band tier without a trial sweep. Only
+// called for windows without code-4 bases; code-4 query bases score 0 (ssw_cpp.cpp:43-48).
+__device__ int32_t diag_lower_bound(const SwPlanes &pl, const SwTask &t, int32_t d0, const SwScore &sc) {
+  const int32_t m = (int32_t)t.m, n = (int32_t)t.n;
+  const int32_t i_lo = d0 < 0 ? -d0 : 0, i_hi = (n - d0) < m ? (n - d0) : m;
+  if (i_lo >= i_hi) return 0;
+  const bool rev = (t.flags & SWT_REV) != 0;
+  int32_t run = 0, best = 0;
+  for (int32_t qw = i_lo >> 5; qw <= (i_hi - 1) >> 5; qw++) {
+    const uint64_t Q = __ldg(&pl.q_sbits[t.q_word + qw]);
+    const uint32_t qn = __ldg(&pl.q_nmask[t.q_word + qw]);
+    uint64_t W;
+    if (!rev) W = bits_at(pl.w_sbits, t.w_word, (int32_t)t.w_start + 32 * qw + d0);
+    else {
+      const int32_t p0 = (int32_t)t.w_start + n - 1 - 32 * qw - d0 - 31;     // column 32qw + d0 + b <-> base p0 + 31 - b
+      uint64_t e = __brevll(bits_at(pl.w_sbits, t.w_word, p0));
+      e = ((e >> 1) & 0x5555555555555555ull) | ((e & 0x5555555555555555ull) << 1);
+      W = e ^ pair_mask(~__brev(mask_at(pl.w_xmask, t.w_word, p0)));         // complement unless a/c/g/t/U/u
+    }
+    const uint64_t x = Q ^ W;
+    const uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;              // bit 2b set: base b mismatches
+    const int32_t b_lo = i_lo - 32 * qw > 0 ? i_lo - 32 * qw : 0, b_hi = i_hi - 32 * qw < 32 ? i_hi - 32 * qw : 32;
+    if (qn == 0) {
+      int32_t b = b_lo;
+      while (b < b_hi) {
+        const uint64_t rest = mm >> (2 * b);
+        int32_t z = rest ? (__ffsll((long long)rest) - 1) >> 1 : 32;         // matches before the next mismatch
+        if (b + z > b_hi) z = b_hi - b;
+        run += sc.match * z; if (run > best) best = run;
+        b += z;
+        if (b < b_hi) { run -= sc.mismatch; if (run < 0) run = 0; b++; }
+      }
+    } else {
+      for (int32_t b = b_lo; b < b_hi; b++) {
+        const int32_t sco = ((qn >> b) & 1u) ? 0 : (((mm >> (2 * b)) & 1ull) ? -sc.mismatch : sc.match);
+        run += sco; if (run < 0) run = 0; if (run > best) best = run;
+      }
+    }
+  }
+  return best;
+}
+// smallest direct tier (0..3 = 8 / 16 / 32 / 64 diagonals) whose band holds [-(rows - a), cols - a], a = ceil(score / match);
+// SWT_TIER_NONE when the interval is wider than 64 or the score says nothing
+__device__ __forceinline__ uint32_t tier_of_width(int32_t rows, int32_t cols, int32_t score, const SwScore &sc, uint32_t max_tier) {
+  if (score <= 0) return SWT_TIER_NONE;
+  const int32_t width = rows + cols - 2 * ceil_div_pos(score, sc.match) + 1;
+  const uint32_t t = width <= 8 ? 0u : width <= 16 ? 1u : width <= 32 ? 2u : width <= 64 ? 3u : SWT_TIER_NONE;
+  return (t != SWT_TIER_NONE && t > max_tier) ? SWT_TIER_NONE : t;
+}
+// one counter per tier, one atomic per (warp, tier)
+__device__ __forceinline__ void count_tier(uint32_t tier, uint32_t *__restrict__ counts) {
+  const uint32_t peers = __match_any_sync(__activemask(), tier);
+  if (tier != SWT_TIER_NONE && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&counts[CNT_TIER + tier], (uint32_t)__popc(peers));
+}
 
 __device__ __forceinline__ uint32_t classify(uint32_t m, uint32_t n, const SwScore &sc) {
   if (m == 0 || n == 0) return SWC_NONE;
@@ -506,15 +595,45 @@ __device__ __forceinline__ bool window_clean(const uint32_t *__restrict__ nmask,
   return true;
 }
 
-__device__ __forceinline__ void enlist(const SwTask &t, uint32_t i, uint32_t cls, SwRes *__restrict__ res,
-                                       uint32_t *__restrict__ band_list, Rec16 *__restrict__ full_keys,
-                                       uint32_t *__restrict__ slow_list, uint32_t *__restrict__ counts) {
+// Forward work lists. Band-eligible alignments get a tier (written to tier_f, listed later by k_tier_scatter): with
+// `tiers` on, the seed-diagonal lower bound L picks the narrowest band that provably holds every optimal alignment
+// (res[].score = L is what MODE 2 of k_sw_band places the band with); otherwise, or when L allows nothing <= 64
+// diagonals (e.g. an indel splits the read over two diagonals), the 32-wide sweep-and-verify tier.
+__device__ __forceinline__ void enlist(const SwPlanes &pl, const SwTask &t, uint32_t i, uint32_t cls, int32_t d0, uint32_t tiers,
+                                       uint32_t max_tier, const SwScore &sc, SwRes *__restrict__ res, uint8_t *__restrict__ tier_f,
+                                       Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list, uint32_t *__restrict__ counts) {
+  uint32_t tier = SWT_TIER_NONE;
   if (cls == SWC_NONE) {
     SwRes o; o.score = 0; o.ref_end = -1; o.read_end = 0; o.ref_begin = -1; o.read_begin = 0; o.flags = 0; o.pad0 = o.pad1 = 0;
     res[i] = o;
   } else if (cls == SWC_SLOW) slow_list[atomicAdd(&counts[CNT_SLOW], 1u)] = i;
-  else if (t.flags & SWT_BAND) band_list[atomicAdd(&counts[CNT_BAND], 1u)] = i;
-  else { const uint32_t k = atomicAdd(&counts[CNT_FULL], 1u); full_keys[k].key = t.n; full_keys[k].val = i; }
+  else if (t.flags & SWT_BAND) {
+    tier = SWT_TIER_SWEEP;
+    if (tiers) {
+      const int32_t L = diag_lower_bound(pl, t, d0, sc);
+      const uint32_t tt = tier_of_width((int32_t)t.m, (int32_t)t.n, L, sc, max_tier);
+      if (tt != SWT_TIER_NONE) { tier = tt; res[i].score = L; }
+    }
+  } else { const uint32_t k = atomicAdd(&counts[CNT_FULL], 1u); full_keys[k].key = t.n; full_keys[k].val = i; }
+  tier_f[i] = (uint8_t)tier;
+  count_tier(tier, counts);
+}
+
+// tier byte array -> one list per tier inside `list` (tier t starts at offs[t]); order inside a list is arbitrary
+__global__ void __launch_bounds__(256)
+k_tier_scatter(const uint8_t *__restrict__ tier, uint32_t n, const uint32_t *__restrict__ counts, uint32_t *__restrict__ cursors,
+               uint32_t *__restrict__ list) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = i < n ? tier[i] : SWT_TIER_NONE;
+  const uint32_t peers = __match_any_sync(0xffffffffu, t);
+  if (t == SWT_TIER_NONE) return;
+  const uint32_t lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(&cursors[t], (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  uint32_t off = 0;
+  for (uint32_t k = 0; k < t; k++) off += counts[CNT_TIER + k];
+  list[off + base + __popc(peers & ((1u << lane) - 1u))] = i;
 }
 
 // pipeline mode: one task per seed (SmithWaterman.h:199-211)
@@ -522,7 +641,7 @@ __global__ void __launch_bounds__(256)
 k_sw_prepare_seeds(const kslam_seed *__restrict__ seeds, uint32_t n, const uint64_t *__restrict__ r_offs,
                    const uint64_t *__restrict__ r_word, const uint64_t *__restrict__ g_offs,
                    const uint64_t *__restrict__ g_word, const uint32_t *__restrict__ g_nmask, SwScore sc, uint32_t use_band,
-                   SwTask *__restrict__ tasks, SwRes *__restrict__ res, uint32_t *__restrict__ band_list,
+                   SwPlanes pl, SwTask *__restrict__ tasks, SwRes *__restrict__ res, uint8_t *__restrict__ tier_f,
                    Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list, uint32_t *__restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -537,16 +656,19 @@ k_sw_prepare_seeds(const kslam_seed *__restrict__ seeds, uint32_t n, const uint6
   t.flags = (s.rev_comp ? SWT_REV : 0u) | (cls << 8);
   if (use_band && cls == SWC_FAST8 && t.m <= SWB_MAXROWS && window_clean(g_nmask, t.w_word, t.w_start, t.n)) t.flags |= SWT_BAND;
   tasks[i] = t;
-  enlist(t, i, cls, res, band_list, full_keys, slow_list, counts);
+  // matrix diagonal of the seed's exact 32-mer match: forward seeds put read base i on genome base rel + i; reverse-
+  // complement seeds put rc(read) base i there and Align sees the window reversed (SmithWaterman.h:205-208)
+  const int32_t d0 = s.rev_comp ? (int32_t)t.w_start + (int32_t)t.n - s.rel - (int32_t)t.m : s.rel - (int32_t)t.w_start;
+  enlist(pl, t, i, cls, d0, use_band >= 3, use_band >= 2 ? 3u : 2u, sc, res, tier_f, full_keys, slow_list, counts);
 }
 
 // Aligner::Align batch mode: query i against ref i, whole sequences
 __global__ void __launch_bounds__(256)
 k_sw_prepare_pairs(uint32_t n, const uint64_t *__restrict__ q_offs, const uint64_t *__restrict__ q_word,
                    const uint64_t *__restrict__ r_offs, const uint64_t *__restrict__ r_word,
-                   const uint32_t *__restrict__ r_nmask, SwScore sc, uint32_t use_band, SwTask *__restrict__ tasks,
+                   const uint32_t *__restrict__ r_nmask, SwScore sc, uint32_t use_band, SwPlanes pl, SwTask *__restrict__ tasks,
                    SwRes *__restrict__ res,
-                   uint32_t *__restrict__ band_list, Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list,
+                   uint8_t *__restrict__ tier_f, Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list,
                    uint32_t *__restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -557,26 +679,28 @@ k_sw_prepare_pairs(uint32_t n, const uint64_t *__restrict__ q_offs, const uint64
   t.flags = cls << 8;
   if (use_band && cls == SWC_FAST8 && t.m <= SWB_MAXROWS && window_clean(r_nmask, t.w_word, 0, t.n)) t.flags |= SWT_BAND;
   tasks[i] = t;
-  enlist(t, i, cls, res, band_list, full_keys, slow_list, counts);
+  enlist(pl, t, i, cls, 0, use_band >= 3, use_band >= 2 ? 3u : 2u, sc, res, tier_f, full_keys, slow_list, counts);   // no seed: try the main diagonal
 }
 
-// reverse pass work lists: score 0 has no reverse pass (ssw.c:903 is reached with an empty range). The band holds
-// every alignment that scores S when rows + cols - 2 * ceil(S / match) + 1 <= 32 (sw_band.cuh).
+// reverse pass work lists: score 0 has no reverse pass (ssw.c:903 is reached with an empty range). The forward score S
+// is known, so the band [-(rows - a), cols - a] (sw_band.cuh) is exact and its width picks the tier directly.
 __global__ void __launch_bounds__(256)
 k_sw_rev_lists(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, uint32_t n, SwScore sc,
-               uint32_t *__restrict__ band_list, uint32_t *__restrict__ band64_list, uint32_t use64,
+               uint8_t *__restrict__ tier_r, uint32_t min_tier, uint32_t max_tier,
                Rec16 *__restrict__ full_keys, uint32_t *__restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const SwTask t = tasks[i];
-  if (((t.flags >> 8) & 0xffu) != SWC_FAST8) return;
+  uint32_t tier = SWT_TIER_NONE;
   const SwRes r = res[i];
-  if (r.score <= 0) return;
-  const int32_t rows = r.read_end + 1, cols = r.ref_end + 1, a = ceil_div_pos(r.score, sc.match);
-  const int32_t width = rows + cols - 2 * a + 1;
-  if ((t.flags & SWT_BAND) && width <= 32) band_list[atomicAdd(&counts[CNT_BAND], 1u)] = i;
-  else if ((t.flags & SWT_BAND) && use64 && width <= SWB_MAXW) band64_list[atomicAdd(&counts[CNT_BAND64], 1u)] = i;
-  else { const uint32_t k = atomicAdd(&counts[CNT_FULL], 1u); full_keys[k].key = (uint64_t)cols; full_keys[k].val = i; }
+  if (((t.flags >> 8) & 0xffu) == SWC_FAST8 && r.score > 0) {
+    const int32_t rows = r.read_end + 1, cols = r.ref_end + 1;
+    if (t.flags & SWT_BAND) tier = tier_of_width(rows, cols, r.score, sc, max_tier);
+    if (tier != SWT_TIER_NONE && tier < min_tier) tier = min_tier;
+    if (tier == SWT_TIER_NONE) { const uint32_t k = atomicAdd(&counts[CNT_FULL], 1u); full_keys[k].key = (uint64_t)cols; full_keys[k].val = i; }
+  }
+  tier_r[i] = (uint8_t)tier;
+  count_tier(tier, counts);
 }
 
 // sorted (by columns) task ids -> work items of the full-matrix kernel: two alignments with the same column count
@@ -598,21 +722,24 @@ k_sw_make_items(const Rec16 *__restrict__ sorted, uint32_t n_fast, uint2 *__rest
 }
 
 // out[0..1]: matrix cells (readLen x windowLen) of the forward / reverse sweeps — the GCUPS numerator.
-// out[2]: cells actually computed by the sweep kernels (every band-eligible task tries the 32-wide tier; tiers 2
-// and 0 add their own), the numerator of the integer-pipe roofline (7 ALU ops per two cells).
+// out[2]: cells actually computed by the sweep kernels (band cells of every tier an alignment went through, the whole
+// matrix for the full-matrix kernel), the numerator of the integer-pipe roofline (7 ALU ops per two cells).
 __global__ void __launch_bounds__(256)
-k_sw_cells(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, uint32_t n, unsigned long long *out) {
+k_sw_cells(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, const uint8_t *__restrict__ tier_f,
+           const uint8_t *__restrict__ tier_r, uint32_t n, unsigned long long *out) {
   unsigned long long fw = 0, rv = 0, comp = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const SwTask t = tasks[i]; const SwRes r = res[i];
+    if (((t.flags >> 8) & 0xffu) != SWC_FAST8) continue;
     fw += (unsigned long long)t.m * t.n;
-    const uint32_t ft = (r.flags >> 8) & 3u, rt = (r.flags >> 10) & 3u;
-    if (t.flags & SWT_BAND) comp += 32ull * t.m;
-    if (ft == 2) comp += 64ull * t.m; else if (ft == 0) comp += (unsigned long long)t.m * t.n;
+    const uint32_t tf = tier_f[i], tr = tier_r[i], ft = (r.flags >> 8) & 7u;
+    if (tf <= 3u) comp += (unsigned long long)(8u << tf) * t.m;
+    if (tf == SWT_TIER_SWEEP) { comp += 32ull * t.m; if (ft == 4u) comp += 64ull * t.m; }
+    if (ft == 0u) comp += (unsigned long long)t.m * t.n;
     if (r.score > 0) {
       const unsigned long long rows = (unsigned long long)(r.read_end + 1), cols = (unsigned long long)(r.ref_end + 1);
       rv += rows * cols;
-      comp += rt == 1 ? 32ull * rows : (rt == 2 ? 64ull * rows : rows * cols);
+      comp += tr <= 3u ? (unsigned long long)(8u << tr) * rows : rows * cols;
     }
   }
   for (int d = 16; d; d >>= 1) {
@@ -685,7 +812,7 @@ static void run_band(kslam_ctx *c, const SwPlanes &pl, const SwScore &sc, const 
   uint8_t *bytes = w->bandbytes.as<uint8_t>();
   for (uint32_t c0 = 0; c0 < n_list; c0 += CHUNK) {
     const uint32_t cn = n_list - c0 < CHUNK ? n_list - c0 : CHUNK;
-    dim3 gridb((cn + 255) / 256, (SWB_MAXROWS + W) / 32);
+    dim3 gridb((cn + 255) / 256, (SWB_MAXROWS + W + 31) / 32);
     k_band_bytes<MODE, W><<<gridb, 256, 0, st>>>(w->tasks.as<SwTask>(), list + c0, cn, pl, sc, w->res.as<SwRes>(), bytes, stride);
     const uint32_t pairs = (cn + 1) / 2, blocks = (pairs + SWB_BLOCK - 1) / SWB_BLOCK;
     k_sw_band<MODE, W><<<blocks, SWB_BLOCK, 0, st>>>(w->tasks.as<SwTask>(), list + c0, cn, sc, w->res.as<SwRes>(), bytes, stride,
@@ -695,31 +822,45 @@ static void run_band(kslam_ctx *c, const SwPlanes &pl, const SwScore &sc, const 
   }
 }
 
-// one direction (forward or reverse) over the prepared lists: 32-wide band, then the 64-wide band for what it could
-// not prove (forward) / what needs it (reverse), then every remaining alignment through the full-matrix kernel,
-// bucketed by column count
+// tier byte array -> per-tier lists at the front of w->lists; returns the five list sizes
+static void make_tier_lists(kslam_ctx *c, uint32_t n, const uint8_t *tier, uint32_t *d_counts, uint32_t *h_counts, uint32_t cnt[5]) {
+  cudaStream_t st = c->stream;
+  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_CUR, 0, 5 * 4, st));
+  k_tier_scatter<<<(n + 255) / 256, 256, 0, st>>>(tier, n, d_counts, d_counts + CNT_CUR, c->sw->lists.as<uint32_t>());
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(h_counts + CNT_TIER, d_counts + CNT_TIER, 5 * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (int t = 0; t < 5; t++) cnt[t] = h_counts[CNT_TIER + t];
+}
+
+// one direction (forward or reverse) over the tier lists: the direct tiers (band placed exactly, 8 / 16 / 32 / 64
+// diagonals), forward only: the 32-wide sweep-and-verify tier and the 64-wide tier for what it could not prove but
+// bounded; then every remaining alignment through the full-matrix kernel, bucketed by column count
 template <bool REVERSE>
-static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore &sc, uint32_t n_band, uint32_t *d_counts,
-                    uint32_t *h_counts, uint64_t *n_band_done, uint64_t *n_band64_done, uint64_t *n_full_done) {
+static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore &sc, const uint32_t cnt[5], uint32_t *d_counts,
+                    uint32_t *h_counts, uint64_t *n_band64_via_sweep, uint64_t *n_full_done) {
   SwWorkspace *w = c->sw;
   cudaStream_t st = c->stream;
   SwTask *tasks = w->tasks.as<SwTask>();
   SwRes *res = w->res.as<SwRes>();
-  uint32_t *list32 = w->lists.as<uint32_t>(), *list64 = list32 + 2 * (size_t)n;
+  uint32_t *lists = w->lists.as<uint32_t>(), *list64 = lists + 2 * (size_t)n;
   Rec16 *keys = w->keys.as<Rec16>(), *keys2 = w->keys2.as<Rec16>();
-  if (REVERSE) {
-    run_band<1, 32>(c, pl, sc, list32, n_band, d_counts, nullptr);
-    const uint32_t n64 = read_count(c, d_counts, h_counts, CNT_BAND64);     // filled by k_sw_rev_lists
-    run_band<1, 64>(c, pl, sc, list64, n64, d_counts, nullptr);
-    *n_band64_done += n64;
-  } else {
-    run_band<0, 32>(c, pl, sc, list32, n_band, d_counts, c->sw_band64 ? list64 : nullptr);
+  uint32_t off[5] = {0, 0, 0, 0, 0};
+  for (int t = 1; t < 5; t++) off[t] = off[t - 1] + cnt[t - 1];
+  constexpr int DM = REVERSE ? 1 : 2;
+  run_band<DM, 8>(c, pl, sc, lists + off[0], cnt[0], d_counts, nullptr);
+  run_band<DM, 16>(c, pl, sc, lists + off[1], cnt[1], d_counts, nullptr);
+  run_band<DM, 32>(c, pl, sc, lists + off[2], cnt[2], d_counts, nullptr);
+  run_band<DM, 64>(c, pl, sc, lists + off[3], cnt[3], d_counts, nullptr);
+  if (!REVERSE && cnt[4]) {
+    run_band<0, 32>(c, pl, sc, lists + off[4], cnt[4], d_counts, c->sw_band64 ? list64 : nullptr);
     const uint32_t n64 = read_count(c, d_counts, h_counts, CNT_BAND64);     // 32-wide failures that fit 64 diagonals
     run_band<2, 64>(c, pl, sc, list64, n64, d_counts, nullptr);
-    *n_band64_done += n64;
+    *n_band64_via_sweep += n64;
   }
   const uint32_t n_full = read_count(c, d_counts, h_counts, CNT_FULL);
-  *n_band_done += n_band; *n_full_done += n_full;
+  *n_full_done += n_full;
   if (n_full) {
     uint64_t passes = 0;
     Rec16 *sorted = radix_sort(c, keys, keys2, n_full, 0, 0, 16, &passes);
@@ -741,32 +882,36 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
   const SwScore sc = make_score(c);
   SwTask *tasks = w->tasks.as<SwTask>();
   SwRes *res = w->res.as<SwRes>();
-  uint32_t *d_counts = c->counters.as<uint32_t>() + 32;      // 16 u32 counters
+  uint32_t *d_counts = c->counters.as<uint32_t>() + 32;      // CNT_WORDS u32 counters
   uint32_t *h_counts = c->h_counters.as<uint32_t>() + 32;
   const unsigned nb = (n + 255) / 256;
-  uint32_t *band_list = w->lists.as<uint32_t>(), *slow_list = band_list + n;
+  uint32_t *slow_list = w->lists.as<uint32_t>() + n;
+  uint8_t *tier_f = w->tier.as<uint8_t>(), *tier_r = tier_f + n;
 
   // ---- forward
   cudaEvent_t e1 = tm_mark(c);
-  CUDA_TRY(cudaMemcpyAsync(h_counts, d_counts, 64, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaStreamSynchronize(st));
-  uint32_t n_band = h_counts[CNT_BAND];
-  const uint32_t n_slow = h_counts[CNT_SLOW];
-  uint64_t band_done = 0, band64_done = 0, full_done = 0;
-  sw_pass<false>(c, n, pl, sc, n_band, d_counts, h_counts, &band_done, &band64_done, &full_done);
-  c->tm.n_sw_fast = full_done; c->tm.n_sw_band = band_done; c->tm.n_sw_band64 = band64_done; c->tm.n_sw_slow = n_slow;
+  uint32_t cnt[5];
+  make_tier_lists(c, n, tier_f, d_counts, h_counts, cnt);
+  const uint32_t n_slow = read_count(c, d_counts, h_counts, CNT_SLOW);
+  uint64_t band64_sweep = 0, full_done = 0;
+  sw_pass<false>(c, n, pl, sc, cnt, d_counts, h_counts, &band64_sweep, &full_done);
+  c->tm.n_sw_fast = full_done; c->tm.n_sw_slow = n_slow;
+  c->tm.n_sw_band = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4];
+  c->tm.n_sw_band64 = cnt[3] + band64_sweep;
+  c->tm.n_sw_tier8 = cnt[0]; c->tm.n_sw_tier16 = cnt[1]; c->tm.n_sw_tier32 = cnt[2]; c->tm.n_sw_tier64 = cnt[3]; c->tm.n_sw_sweep32 = cnt[4];
   cudaEvent_t e2 = tm_mark(c);
 
   // ---- reverse
   CUDA_TRY(cudaMemsetAsync(d_counts + CNT_BAND, 0, 8, st));   // band + full counters
   CUDA_TRY(cudaMemsetAsync(d_counts + CNT_BAND64, 0, 4, st));
-  k_sw_rev_lists<<<nb, 256, 0, st>>>(tasks, res, n, sc, band_list, band_list + 2 * (size_t)n, c->sw_band64 ? 1u : 0u,
-                                     w->keys.as<Rec16>(), d_counts);
+  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_TIER, 0, 5 * 4, st));
+  const uint32_t max_tier = !c->sw_band ? 0u : (c->sw_band64 ? 3u : 2u), min_tier = c->sw_tiers ? 0u : 2u;
+  k_sw_rev_lists<<<nb, 256, 0, st>>>(tasks, res, n, sc, tier_r, min_tier, max_tier, w->keys.as<Rec16>(), d_counts);
   c->launches++;
-  n_band = read_count(c, d_counts, h_counts, CNT_BAND);
-  uint64_t band_rev = 0, band64_rev = 0, full_rev = 0;
-  sw_pass<true>(c, n, pl, sc, n_band, d_counts, h_counts, &band_rev, &band64_rev, &full_rev);
-  c->tm.n_sw_band_rev = band_rev + band64_rev;
+  make_tier_lists(c, n, tier_r, d_counts, h_counts, cnt);
+  uint64_t dummy = 0, full_rev = 0;
+  sw_pass<true>(c, n, pl, sc, cnt, d_counts, h_counts, &dummy, &full_rev);
+  c->tm.n_sw_band_rev = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3];
   cudaEvent_t e3 = tm_mark(c);
 
   // ---- exact scalar fallback for shapes outside the fast kernels
@@ -812,7 +957,7 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
   cudaEvent_t e5 = tm_mark(c);
   unsigned long long *d_cells = c->counters.as<unsigned long long>() + 8;
   CUDA_TRY(cudaMemsetAsync(d_cells, 0, 24, st));
-  k_sw_cells<<<c->num_sms * 2, 256, 0, st>>>(tasks, res, n, d_cells);
+  k_sw_cells<<<c->num_sms * 2, 256, 0, st>>>(tasks, res, tier_f, tier_r, n, d_cells);
   c->launches++;
   unsigned long long *h_cells = c->h_counters.as<unsigned long long>() + 8;
   CUDA_TRY(cudaMemcpyAsync(h_cells, d_cells, 24, cudaMemcpyDeviceToHost, st));
@@ -824,6 +969,9 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
   c->tm.ms_sw_traceback = tm_ms(e4, e5);
 }
 
+// 0 = full-matrix only, 1 = 32-wide sweep tier, 2 = + 64-wide tier, 3 = + direct tiers from the seed-diagonal bound
+static uint32_t sw_level(const kslam_ctx *c) { return !c->sw_band ? 0u : (!c->sw_band64 ? 1u : (c->sw_tiers ? 3u : 2u)); }
+
 static void sw_reserve(kslam_ctx *c, uint32_t n) {
   if (!c->sw) c->sw = new SwWorkspace();
   SwWorkspace *w = c->sw;
@@ -832,7 +980,8 @@ static void sw_reserve(kslam_ctx *c, uint32_t n) {
   w->keys.reserve((size_t)n * sizeof(Rec16) + 64);
   w->keys2.reserve((size_t)n * sizeof(Rec16) + 64);
   w->items.reserve((size_t)(2 * ((n + 1) / 2)) * sizeof(uint2) + 64);
-  w->lists.reserve((size_t)n * 12 + 64);      // band32 list | slow list | band64 list
+  w->lists.reserve((size_t)n * 12 + 64);      // tier lists | slow list | 64-wide list of the sweep tier's failures
+  w->tier.reserve((size_t)n * 2 + 64);        // work-list tier of every alignment: forward | reverse
   c->counters.reserve(64 * 8); c->h_counters.reserve(64 * 8);
   w->n = n;
 }
@@ -841,6 +990,7 @@ static void sw_reset_timers(kslam_ctx *c) {
   c->tm.ms_sw_prepare = c->tm.ms_sw_forward = c->tm.ms_sw_reverse = c->tm.ms_sw_slow = c->tm.ms_sw_traceback = 0;
   c->tm.sw_cells_forward = c->tm.sw_cells_reverse = 0;
   c->tm.n_sw_fast = c->tm.n_sw_slow = c->tm.n_sw_band = c->tm.n_sw_band64 = c->tm.n_sw_band_rev = 0; c->tm.n_traceback_dp = 0;
+  c->tm.n_sw_tier8 = c->tm.n_sw_tier16 = c->tm.n_sw_tier32 = c->tm.n_sw_tier64 = c->tm.n_sw_sweep32 = 0; c->tm.sw_cells_computed = 0;
 }
 
 void sw_align_seeds(kslam_ctx *c) {
@@ -854,16 +1004,16 @@ void sw_align_seeds(kslam_ctx *c) {
   uint32_t *d_counts = c->counters.as<uint32_t>() + 32;
   SwWorkspace *w = c->sw;
   cudaEvent_t e0 = tm_mark(c);
-  CUDA_TRY(cudaMemsetAsync(d_counts, 0, 64, st));
+  CUDA_TRY(cudaMemsetAsync(d_counts, 0, CNT_WORDS * 4, st));
+  SwPlanes pl{c->reads.sbits.as<uint64_t>(), c->reads.nmask.as<uint32_t>(), c->genomes.sbits.as<uint64_t>(),
+              c->genomes.nmask.as<uint32_t>(), c->genomes.xmask.as<uint32_t>()};
   k_sw_prepare_seeds<<<(n + 255) / 256, 256, 0, st>>>(c->seeds.as<kslam_seed>(), n, c->reads.offs.as<uint64_t>(),
       c->reads.word_off.as<uint64_t>(), c->genomes.offs.as<uint64_t>(), c->genomes.word_off.as<uint64_t>(),
-      c->genomes.nmask.as<uint32_t>(), make_score(c), c->sw_band ? 1u : 0u, w->tasks.as<SwTask>(), w->res.as<SwRes>(), w->lists.as<uint32_t>(),
+      c->genomes.nmask.as<uint32_t>(), make_score(c), sw_level(c), pl, w->tasks.as<SwTask>(), w->res.as<SwRes>(), w->tier.as<uint8_t>(),
       w->keys.as<Rec16>(), w->lists.as<uint32_t>() + n, d_counts);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   cudaEvent_t e1 = tm_mark(c);
-  SwPlanes pl{c->reads.sbits.as<uint64_t>(), c->reads.nmask.as<uint32_t>(), c->genomes.sbits.as<uint64_t>(),
-              c->genomes.nmask.as<uint32_t>(), c->genomes.xmask.as<uint32_t>()};
   sw_run(c, n, pl, c->ov.as<kslam_overlap>(), c->prm.report_cigar ? c->cig.as<uint32_t>() : nullptr, 1);
   c->tm.ms_sw_prepare = tm_ms(e0, e1);
 }
@@ -877,16 +1027,16 @@ void sw_align_pairs(kslam_ctx *c, uint64_t n64, kslam_overlap *out_dev, uint32_t
   uint32_t *d_counts = c->counters.as<uint32_t>() + 32;
   SwWorkspace *w = c->sw;
   cudaEvent_t e0 = tm_mark(c);
-  CUDA_TRY(cudaMemsetAsync(d_counts, 0, 64, st));
+  CUDA_TRY(cudaMemsetAsync(d_counts, 0, CNT_WORDS * 4, st));
   CUDA_TRY(cudaMemsetAsync(out_dev, 0, (size_t)n * sizeof(kslam_overlap), st));
+  SwPlanes pl{c->swq.sbits.as<uint64_t>(), c->swq.nmask.as<uint32_t>(), c->swr.sbits.as<uint64_t>(),
+              c->swr.nmask.as<uint32_t>(), c->swr.xmask.as<uint32_t>()};
   k_sw_prepare_pairs<<<(n + 255) / 256, 256, 0, st>>>(n, c->swq.offs.as<uint64_t>(), c->swq.word_off.as<uint64_t>(),
-      c->swr.offs.as<uint64_t>(), c->swr.word_off.as<uint64_t>(), c->swr.nmask.as<uint32_t>(), make_score(c), c->sw_band ? 1u : 0u,
-      w->tasks.as<SwTask>(), w->res.as<SwRes>(), w->lists.as<uint32_t>(), w->keys.as<Rec16>(), w->lists.as<uint32_t>() + n, d_counts);
+      c->swr.offs.as<uint64_t>(), c->swr.word_off.as<uint64_t>(), c->swr.nmask.as<uint32_t>(), make_score(c), sw_level(c), pl,
+      w->tasks.as<SwTask>(), w->res.as<SwRes>(), w->tier.as<uint8_t>(), w->keys.as<Rec16>(), w->lists.as<uint32_t>() + n, d_counts);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   cudaEvent_t e1 = tm_mark(c);
-  SwPlanes pl{c->swq.sbits.as<uint64_t>(), c->swq.nmask.as<uint32_t>(), c->swr.sbits.as<uint64_t>(),
-              c->swr.nmask.as<uint32_t>(), c->swr.xmask.as<uint32_t>()};
   sw_run(c, n, pl, out_dev, cig_dev, 0);
   c->tm.ms_sw_prepare = tm_ms(e0, e1);
 }
@@ -894,6 +1044,6 @@ void sw_align_pairs(kslam_ctx *c, uint64_t n64, kslam_overlap *out_dev, uint32_t
 void sw_workspace_free(kslam_ctx *c) {
   if (!c->sw) return;
   c->sw->tasks.release(); c->sw->res.release(); c->sw->keys.release(); c->sw->keys2.release();
-  c->sw->items.release(); c->sw->lists.release(); c->sw->bandbytes.release(); c->sw->tb_scratch.release();
+  c->sw->items.release(); c->sw->lists.release(); c->sw->bandbytes.release(); c->sw->tb_scratch.release(); c->sw->tier.release();
   delete c->sw; c->sw = nullptr;
 }

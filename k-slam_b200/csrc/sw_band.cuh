@@ -96,7 +96,7 @@ k_band_bytes(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list
 // bytes of a pair are one aligned 16-bit load. Failures go to next_list (the 64-wide tier; score lower bound left in
 // res[].score) when the interval they need is <= SWB_MAXW wide, else to fb_keys (full-matrix kernel, key = columns).
 template <int MODE, int W>
-__global__ void __launch_bounds__(SWB_BLOCK, (W > 32 ? 2 : 3))
+__global__ void __launch_bounds__(SWB_BLOCK, (W > 32 ? 2 : (W == 32 ? 3 : 6)))
 k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, uint32_t n_list, SwScore sc,
           SwRes *__restrict__ res, const uint8_t *__restrict__ bytes, uint32_t stride, Rec16 *__restrict__ fb_keys,
           uint32_t *__restrict__ fb_count, uint32_t *__restrict__ next_list, uint32_t *__restrict__ next_count) {
@@ -145,9 +145,10 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
     const uint32_t PB = qb == 4u ? 0u : (qb == 5u ? MIS4 : (MIS4 ^ (DIFF << (8 * qb))));
     // issue next row's loads now; they complete under the cell body (indices stay below rows_max + W)
     const uint32_t next = ld2(i + 1), ent = ld2(i + W);
-    uint32_t e = 0, acc[W / 32];
+    constexpr int NH = W > 32 ? W / 32 : 1;      // tracking keys per 32-slot half
+    uint32_t e = 0, acc[NH];
 #pragma unroll
-    for (int h = 0; h < W / 32; h++) acc[h] = 0;
+    for (int h = 0; h < NH; h++) acc[h] = 0;
 #pragma unroll
     for (int t = 0; t < W; t++) {
       const uint32_t s = prmt(PA, PB, sel[t]);
@@ -167,7 +168,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
     rowbytes = next;
     // row winners -> running best (first column, then smallest row: rows only grow, so ties keep the old one)
 #pragma unroll
-    for (int h = 0; h < W / 32; h++) {
+    for (int h = 0; h < NH; h++) {
       const uint32_t aA = acc[h] & 0xffffu, aB = acc[h] >> 16;
       const uint32_t jA = (uint32_t)(i + 32 * h + (int32_t)(31u - (aA & 31u)) + c0[0]);
       const uint32_t jB = (uint32_t)(i + 32 * h + (int32_t)(31u - (aB & 31u)) + c0[1]);
@@ -193,7 +194,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
       if (best) {
         res[idx].ref_begin = r0.ref_end - (int32_t)(4095u - best);
         res[idx].read_begin = r0.read_end - (int32_t)brow;
-        res[idx].flags = r0.flags | SWR_REV_TIER(W / 32);
+        res[idx].flags = r0.flags | SWR_REV_TIER(SWR_TIER_OF_W(W));
       } else {                      // cannot happen when the bound holds; never guess: hand over to the full kernel
         const uint32_t k = atomicAdd(fb_count, 1u);
         fb_keys[k].key = (uint64_t)(r0.ref_end + 1); fb_keys[k].val = idx;
@@ -204,7 +205,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
       const bool proven = S > 0 && c0[al] <= -(rows[al] - a) && (cols[al] - a) <= c0[al] + (W - 1);
       if (proven) {
         SwRes o;
-        o.flags = SWR_FWD_TIER(W / 32); o.pad0 = o.pad1 = 0; o.ref_begin = -1; o.read_begin = 0;
+        o.flags = SWR_FWD_TIER(SWR_TIER_OF_W(W)); o.pad0 = o.pad1 = 0; o.ref_begin = -1; o.read_begin = 0;
         o.score = S; o.ref_end = (int32_t)(4095u - (best & 4095u)); o.read_end = (int32_t)brow;
         res[idx] = o;
       } else if (MODE == 0 && next_list && S > 0 && rows[al] + cols[al] - 2 * a + 1 <= SWB_MAXW) {

@@ -106,3 +106,16 @@ def test_partitioned_empty_rank_and_errors(pkg):
         al.load_genomes_part(gb, go, 0, 2)
         with pytest.raises(pkg.KslamError):
             al.part_route_kmers(0)                      # no reads uploaded
+
+
+def test_partitioned_nccl_two_gpus():
+    """Real exchange: one process per GPU, NCCL all_to_all_single over NVLink (skipped on a single-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_dist_nccl_worker.py")
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                    "--master-addr", "127.0.0.1", "--master-port", "29651", worker], check=True, timeout=900)

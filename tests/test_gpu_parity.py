@@ -33,7 +33,7 @@ def check_overlaps(got, gpool, want, wpool, fields=FIELDS, cigars=True):
         assert not bad, (len(bad), [(a[i], b[i]) for i in bad[:3]])
 
 
-def run_pipeline(pkg, gb, go, rb, ro, P, prefilter=True, band=True):
+def run_pipeline(pkg, gb, go, rb, ro, P, prefilter=True, band=3):
     with pkg.Aligner(match=P.match, mismatch=P.mismatch, gap_open=P.gap_open, gap_extend=P.gap_extend,
                      score_threshold=P.score_threshold, report_cigar=bool(P.report_cigar)) as al:
         al.set_prefilter(prefilter)
@@ -50,7 +50,7 @@ def check_pipeline(pkg, gb, go, rb, ro, P, want=None):
     """Runs the CUDA path twice — prefilter off (every k-mer record is materialised, so K1/K2 can be compared
     record for record) and on (the production setting) — and checks every stage of both against `want`."""
     want = want or T.ko_pipeline(gb, go, rb, ro, P)
-    for prefilter, band in ((False, 0), (True, 2)):
+    for prefilter, band in ((False, 0), (True, 2), (True, 3)):
         out = check_pipeline_mode(pkg, gb, go, rb, ro, P, want, prefilter, band)
     return out
 
@@ -172,7 +172,7 @@ def test_ssw_golden(pkg, golden, name):
 
 @pytest.mark.parametrize("shape", [(150, 150), (150, 300), (100, 130), (40, 64), (160, 160)])
 @pytest.mark.parametrize("cigar", [0, 1])
-@pytest.mark.parametrize("band", [0, 1, 2])
+@pytest.mark.parametrize("band", [0, 1, 2, 3])
 def test_ssw_vs_oracle(pkg, shape, cigar, band):
     q, qo, r, ro = pkg.synth.sw_pairs(20_000, shape[0], shape[1], seed=100 + shape[0] + cigar)
     P = T.default_params(report_cigar=cigar)
@@ -212,7 +212,7 @@ def test_ssw_ragged_lengths_and_repeats(pkg):
     P = T.default_params(report_cigar=1)
     want, wpool = T.ko_ssw_batch(q, qo, r, ro, P, cigar_cap=32)
     assert ((want["flags"] & 1) != 0).mean() < 0.01
-    for band in (0, 1, 2):
+    for band in (0, 1, 2, 3):
         with pkg.Aligner(report_cigar=True) as al:
             al.set_sw_band(band)
             out, pool = al.ssw_batch(q, qo, r, ro)
@@ -275,3 +275,28 @@ def test_full_size_properties_config1_slice(pkg):
         b = res2.overlaps[res2.overlaps["read"] < half]
         for f in FIELDS[1:9]:
             assert np.array_equal(a[f], b[f]), f
+
+
+def test_direct_tiers_match_full_matrix_at_volume(pkg):
+    """The tier an alignment runs in never changes its result: 60k config-1-like pairs (1 % substitutions, 5 % reads with
+    an indel) and 40k pairs against a diverged phylogeny give identical alignments at level 3 (direct tiers from the
+    seed-diagonal bound) and level 0 (full matrix only); the narrow tiers must actually carry the bulk of the work."""
+    cases = [(pkg.synth.random_genomes(20, 500_000, seed=3), 60_000, 0.8),
+             (pkg.synth.tree_genomes(40, 300_000, seed=4), 40_000, 0.2)]
+    for (gb, go), n_pairs, min_narrow in cases:
+        rb, ro, _ = pkg.synth.paired_reads(gb, go, n_pairs, seed=9)
+        outs = {}
+        for level in (0, 3):
+            with pkg.Aligner(report_cigar=True) as al:
+                al.set_sw_band(level)
+                al.load_genomes(gb, go)
+                outs[level] = (al.align_batch(rb, ro), al.timings())
+        (a, ta), (b, tb) = outs[0], outs[3]
+        assert len(a.overlaps) > n_pairs
+        for f in FIELDS:
+            assert np.array_equal(a.overlaps[f], b.overlaps[f]), f
+        assert T.cigars_of(a.overlaps[:5000], a.cigar_pool) == T.cigars_of(b.overlaps[:5000], b.cigar_pool)
+        assert ta["n_sw_band"] == 0
+        narrow = tb["n_sw_tier8"] + tb["n_sw_tier16"]
+        assert narrow >= min_narrow * tb["n_seeds"], (narrow, tb["n_seeds"])
+        assert tb["sw_cells_computed"] < ta["sw_cells_computed"]
