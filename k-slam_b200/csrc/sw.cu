@@ -496,27 +496,6 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
 #define CNT_WORDS 32
 
 // ---- lower bound of the optimal score from the seed's own diagonal ------------------------------------------
-// 32 two-bit codes of `plane` starting at base p of the sequence that begins at word w_word (p may be negative or run
-// past the window: those lanes are masked by the caller; guard words keep the reads inside the allocation)
-__device__ __forceinline__ uint64_t bits_at(const uint64_t *__restrict__ plane, uint64_t w_word, int32_t p) {
-  const int32_t wi = p >> 5; const uint32_t sh = (uint32_t)p & 31u;
-  const uint64_t lo = wi >= 0 ? __ldg(&plane[w_word + wi]) : 0ull;
-  if (sh == 0) return lo;
-  const uint64_t hi = wi + 1 >= 0 ? __ldg(&plane[w_word + wi + 1]) : 0ull;
-  return (lo >> (2 * sh)) | (hi << (64 - 2 * sh));
-}
-__device__ __forceinline__ uint32_t mask_at(const uint32_t *__restrict__ plane, uint64_t w_word, int32_t p) {
-  const int32_t wi = p >> 5; const uint32_t sh = (uint32_t)p & 31u;
-  const uint32_t lo = wi >= 0 ? __ldg(&plane[w_word + wi]) : 0u, hi = wi + 1 >= 0 ? __ldg(&plane[w_word + wi + 1]) : 0u;
-  return __funnelshift_r(lo, hi, sh);
-}
-__device__ __forceinline__ uint64_t pair_mask(uint32_t m) {     // bit b -> bits 2b and 2b+1
-  uint64_t x = m;
-  x = (x | (x << 16)) & 0x0000FFFF0000FFFFull; x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
-  x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full; x = (x | (x << 2)) & 0x3333333333333333ull;
-  x = (x | (x << 1)) & 0x5555555555555555ull;
-  return x * 3ull;
-}
 // Best ungapped local segment (Kadane) along matrix diagonal j = i + d0, in the orientation Align sees. It is the score
 // of a real local alignment, hence a LOWER BOUND L of the optimum: every alignment scoring >= L lies inside the offsets
 // [-(m - a), n - a] with a = ceil(L / match) (sw_band.cuh), which picks the band tier without a trial sweep. Only
@@ -798,28 +777,17 @@ static uint32_t read_count(kslam_ctx *c, uint32_t *d_counts, uint32_t *h_counts,
   return h_counts[which];
 }
 
-// one banded tier over a list, in chunks of CHUNK alignments (one band byte plane is reused)
+// one banded tier over a list: the sweep kernel unpacks its own selector streams into shared memory
 template <int MODE, int W>
 static void run_band(kslam_ctx *c, const SwPlanes &pl, const SwScore &sc, const uint32_t *list, uint32_t n_list,
                      uint32_t *d_counts, uint32_t *next_list) {
   if (!n_list) return;
   SwWorkspace *w = c->sw;
-  cudaStream_t st = c->stream;
-  const uint32_t CHUNK = 4u << 20;                      // alignments per band-byte plane (<= 900 MB)
-  const uint32_t cmax = n_list < CHUNK ? n_list : CHUNK;
-  const uint32_t stride = (cmax + 1) & ~1u;
-  w->bandbytes.reserve((size_t)stride * SWB_PLANE_ROWS + 64);
-  uint8_t *bytes = w->bandbytes.as<uint8_t>();
-  for (uint32_t c0 = 0; c0 < n_list; c0 += CHUNK) {
-    const uint32_t cn = n_list - c0 < CHUNK ? n_list - c0 : CHUNK;
-    dim3 gridb((cn + 255) / 256, (SWB_MAXROWS + W + 31) / 32);
-    k_band_bytes<MODE, W><<<gridb, 256, 0, st>>>(w->tasks.as<SwTask>(), list + c0, cn, pl, sc, w->res.as<SwRes>(), bytes, stride);
-    const uint32_t pairs = (cn + 1) / 2, blocks = (pairs + SWB_BLOCK - 1) / SWB_BLOCK;
-    k_sw_band<MODE, W><<<blocks, SWB_BLOCK, 0, st>>>(w->tasks.as<SwTask>(), list + c0, cn, sc, w->res.as<SwRes>(), bytes, stride,
-                                                      w->keys.as<Rec16>(), d_counts + CNT_FULL, next_list, d_counts + CNT_BAND64);
-    c->launches += 2;
-    CUDA_TRY(cudaGetLastError());
-  }
+  const uint32_t pairs = (n_list + 1) / 2, blocks = (pairs + SWB_BLOCK - 1) / SWB_BLOCK;
+  k_sw_band<MODE, W><<<blocks, SWB_BLOCK, BandSmem<W>::BYTES, c->stream>>>(w->tasks.as<SwTask>(), list, n_list, pl, sc, w->res.as<SwRes>(),
+      w->keys.as<Rec16>(), d_counts + CNT_FULL, next_list, d_counts + CNT_BAND64);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
 }
 
 // tier byte array -> per-tier lists at the front of w->lists; returns the five list sizes

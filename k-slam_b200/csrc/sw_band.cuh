@@ -20,15 +20,50 @@
 // register per row (moves go to the FMA pipe; the ALU pipe only sees the recurrences). Band cells that fall
 // outside the matrix use "replicate-sign" selectors that can only produce 0 or -1, so they stay at H = 0 on the
 // left and can never reach a maximum on the right. Per-alignment inputs (column selectors and query codes) come
-// from a byte plane written by k_band_bytes, one coalesced 16-bit load per row and pair.
+// from two planes written by k_band_bytes as ready-made PRMT selectors, one coalesced load each per row and pair, so
+// the per-row overhead next to the W x 7 cell ops is two PRMTs, the row-winner compare and the selector slide.
 #pragma once
 
 #define SWB_MAXROWS 160
-#define SWB_BLOCK 128
+#define SWB_BLOCK 64
 #define SWB_MAXW 64
-#define SWB_PLANE_ROWS (SWB_MAXROWS + SWB_MAXW)   // band indices k of one plane (multiple of 32)
+
+// shared-memory selector streams of one CTA, word w of thread t at [w * SWB_BLOCK + t] (conflict-free): per alignment
+// (SWB_MAXROWS + W + 4) column-selector bytes, plus one byte per query row holding both alignments' row codes
+template <int W> struct BandSmem {
+  static constexpr int COLW = (SWB_MAXROWS + W + 4 + 3) / 4;
+  static constexpr int QW = (SWB_MAXROWS + 4 + 3) / 4;
+  static constexpr int WORDS = 2 * COLW + QW;
+  static constexpr size_t BYTES = (size_t)WORDS * SWB_BLOCK * 4;
+};
 
 __device__ __forceinline__ int32_t ceil_div_pos(int32_t a, int32_t b) { return (a + b - 1) / b; }
+
+// 32 two-bit codes of `plane` starting at base p of the sequence that begins at word w_word (p may be negative or run
+// past the window: those lanes are masked by the caller; guard words keep the reads inside the allocation)
+__device__ __forceinline__ uint64_t bits_at(const uint64_t *__restrict__ plane, uint64_t w_word, int32_t p) {
+  const int32_t wi = p >> 5; const uint32_t sh = (uint32_t)p & 31u;
+  const uint64_t lo = wi >= 0 ? __ldg(&plane[w_word + wi]) : 0ull;
+  if (sh == 0) return lo;
+  const uint64_t hi = wi + 1 >= 0 ? __ldg(&plane[w_word + wi + 1]) : 0ull;
+  return (lo >> (2 * sh)) | (hi << (64 - 2 * sh));
+}
+__device__ __forceinline__ uint32_t mask_at(const uint32_t *__restrict__ plane, uint64_t w_word, int32_t p) {
+  const int32_t wi = p >> 5; const uint32_t sh = (uint32_t)p & 31u;
+  const uint32_t lo = wi >= 0 ? __ldg(&plane[w_word + wi]) : 0u, hi = wi + 1 >= 0 ? __ldg(&plane[w_word + wi + 1]) : 0u;
+  return __funnelshift_r(lo, hi, sh);
+}
+__device__ __forceinline__ uint64_t pair_mask(uint32_t m) {     // bit b -> bits 2b and 2b+1
+  uint64_t x = m;
+  x = (x | (x << 16)) & 0x0000FFFF0000FFFFull; x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+  x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full; x = (x | (x << 2)) & 0x3333333333333333ull;
+  x = (x | (x << 1)) & 0x5555555555555555ull;
+  return x * 3ull;
+}
+__device__ __forceinline__ uint64_t reverse_pairs(uint64_t e) {     // 2-bit group g -> group 31 - g
+  e = __brevll(e);
+  return ((e >> 1) & 0x5555555555555555ull) | ((e & 0x5555555555555555ull) << 1);
+}
 
 // geometry of one alignment inside the band sweep
 struct BandGeo { int32_t rows, cols, c0; };
@@ -47,60 +82,95 @@ __device__ __forceinline__ BandGeo band_geo(const SwTask &t, const SwRes &r, con
   return g;
 }
 
-// Band byte plane: bytes[k * stride + slot] for band index k in [0, rows + W) of the alignment in list slot `slot`.
-// low nibble = selector of matrix column j = k + c0 (SSW code 0-3, or 8 = outside the matrix), high nibble = SSW
-// code of query row k (0-4, 5 = past the query). One thread fills 32 consecutive k of one alignment, so the packed
-// words are fetched once and consecutive lanes (slots) write consecutive bytes. gridDim.y = (SWB_MAXROWS + W) / 32.
-template <int MODE, int W>
-__global__ void __launch_bounds__(256)
-k_band_bytes(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, uint32_t n_list, SwPlanes pl, SwScore sc,
-             const SwRes *__restrict__ res, uint8_t *__restrict__ bytes, uint32_t stride) {
+// ---- selector streams ------------------------------------------------------------------------------------
+// Column stream of one alignment: byte k = PRMT selector byte of matrix column j = k + c0 in the sweep's orientation —
+// for alignment A (low half of the s16x2 registers) nibbles {w, 8|w}: copy byte w of profile A and replicate its sign;
+// for B nibbles {4|w, 12|w} on profile B; columns outside the matrix replicate the sign of byte 0 (score 0 or -1, never
+// positive). 32 columns are fetched as one oriented 2-bit word and turned into bytes four at a time by one PRMT.
+template <int MODE>
+__device__ __forceinline__ void fill_col_stream(const SwPlanes &pl, const SwTask &t, const SwRes &r, const BandGeo &g, bool is_b,
+                                                int32_t kmax, uint32_t *__restrict__ col) {
   constexpr bool REVERSE = MODE == 1;
-  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= n_list) return;
-  const int32_t k0 = (int32_t)blockIdx.y * 32;
-  const uint32_t idx = list[slot];
-  const SwTask t = tasks[idx];
-  SwRes r; if (MODE != 0) r = res[idx];
-  const BandGeo g = band_geo<MODE, W>(t, r, sc);
   const bool rev = (t.flags & SWT_REV) != 0;
   // genome position of matrix column j is P0 + sg * j (window reversal and the reverse sweep both flip the sign)
   int32_t P0, sg;
   if (!REVERSE) { P0 = rev ? (int32_t)(t.w_start + t.n - 1) : (int32_t)t.w_start; sg = rev ? -1 : 1; }
   else { P0 = rev ? (int32_t)(t.w_start + t.n - 1) - r.ref_end : (int32_t)t.w_start + r.ref_end; sg = rev ? 1 : -1; }
-  const uint64_t *wb = pl.w_sbits + t.w_word; const uint32_t *wx = pl.w_xmask + t.w_word;
-  const uint64_t *qb = pl.q_sbits + t.q_word; const uint32_t *qn = pl.q_nmask + t.q_word;
-  int32_t curw = -1, curq = -1; uint64_t bits = 0, qbits = 0; uint32_t xm = 0, qnm = 0;
-  uint8_t *dst = bytes + (size_t)k0 * stride + slot;
-#pragma unroll 4
-  for (int32_t kk = 0; kk < 32; kk++) {
-    const int32_t k = k0 + kk, j = k + g.c0;
-    uint32_t lo = 8u;
-    if (j >= 0 && j < g.cols) {
-      const int32_t pos = P0 + sg * j, wi = pos >> 5;
-      if (wi != curw) { curw = wi; bits = __ldg(wb + wi); xm = rev ? ~__ldg(wx + wi) : 0u; }
-      lo = (uint32_t)(bits >> (2 * (pos & 31))) & 3u;
-      if ((xm >> (pos & 31)) & 1u) lo ^= 3u;               // complement (3 - c) unless the base is a/c/g/t/U/u
+  const uint32_t LUT = is_b ? 0xF7E6D5C4u : 0xB3A29180u, OUT = is_b ? 0xCCu : 0x88u;
+  for (int32_t k0 = 0; k0 < kmax; k0 += 32) {
+    const int32_t j0 = g.c0 + k0;
+    const int32_t lo = j0 < 0 ? -j0 : 0, hi = g.cols - j0 < 32 ? g.cols - j0 : 32;
+    uint32_t valid = 0;
+    uint64_t codes = 0;
+    if (hi > lo) {
+      valid = (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u) << lo);
+      if (sg > 0) {
+        const int32_t p = P0 + j0;
+        codes = bits_at(pl.w_sbits, t.w_word, p);
+        if (rev) codes ^= pair_mask(~mask_at(pl.w_xmask, t.w_word, p));          // complement unless a/c/g/t/U/u
+      } else {
+        const int32_t p = P0 - j0 - 31;                                            // column j0 + b <-> base p + 31 - b
+        codes = reverse_pairs(bits_at(pl.w_sbits, t.w_word, p));
+        if (rev) codes ^= pair_mask(~__brev(mask_at(pl.w_xmask, t.w_word, p)));
+      }
     }
-    uint32_t hi = 5u;
-    if (k < g.rows) {
-      const int32_t qi = REVERSE ? g.rows - 1 - k : k, wq = qi >> 5;
-      if (wq != curq) { curq = wq; qbits = __ldg(qb + wq); qnm = __ldg(qn + wq); }
-      hi = ((qnm >> (qi & 31)) & 1u) ? 4u : ((uint32_t)(qbits >> (2 * (qi & 31))) & 3u);
+#pragma unroll
+    for (int grp = 0; grp < 8; grp++) {
+      if (k0 + 4 * grp >= kmax) break;
+      const uint32_t x8 = (uint32_t)(codes >> (8 * grp)) & 0xffu;
+      uint32_t nib = (x8 | (x8 << 4)) & 0x0f0fu; nib = (nib | (nib << 2)) & 0x3333u;      // nibble b = code of column b
+      uint32_t bytes = prmt(LUT, 0u, nib);
+      const uint32_t v4 = (valid >> (4 * grp)) & 15u;
+      if (v4 != 15u) {
+#pragma unroll
+        for (int b = 0; b < 4; b++) if (!((v4 >> b) & 1u)) bytes = (bytes & ~(0xffu << (8 * b))) | (OUT << (8 * b));
+      }
+      col[(size_t)(k0 / 4 + grp) * SWB_BLOCK] = bytes;
     }
-    dst[(size_t)kk * stride] = (uint8_t)(lo | (hi << 4));
   }
 }
 
-// `list`/`bytes` cover one chunk of a band list; slot pairs (2p, 2p+1) share a thread. stride is even, so the two
-// bytes of a pair are one aligned 16-bit load. Failures go to next_list (the 64-wide tier; score lower bound left in
+// row codes of one alignment for rows 32g .. 32g+31 of the sweep as bytes in four-row words: 0-3 = base, 4 = code-4
+// base (scores 0 against everything, ssw_cpp.cpp:43-48), 5 = past the query end (mismatches everything)
+template <int MODE>
+__device__ __forceinline__ void q_group(const SwPlanes &pl, const SwTask &t, int32_t rows, int32_t g, uint32_t out[8]) {
+  uint64_t codes; uint32_t nm;
+  if (MODE != 1) {
+    const bool in = 32 * g < rows;
+    codes = in ? __ldg(&pl.q_sbits[t.q_word + g]) : 0ull; nm = in ? __ldg(&pl.q_nmask[t.q_word + g]) : 0u;
+  } else {
+    const int32_t p = rows - 1 - 32 * g - 31;                                       // sweep row 32g + b <-> query base p + 31 - b
+    codes = reverse_pairs(bits_at(pl.q_sbits, t.q_word, p)); nm = __brev(mask_at(pl.q_nmask, t.q_word, p));
+  }
+  const int32_t nv = rows - 32 * g;                                                // rows of this group inside the query
+#pragma unroll
+  for (int grp = 0; grp < 8; grp++) {
+    const uint32_t x8 = (uint32_t)(codes >> (8 * grp)) & 0xffu;
+    uint32_t y = (x8 | (x8 << 12)) & 0x000f000fu; y = (y | (y << 6)) & 0x03030303u;  // byte b = code of row 4 grp + b
+    const uint32_t n4 = (nm >> (4 * grp)) & 15u;
+    if (n4 | (uint32_t)(nv < 4 * grp + 4)) {
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        if ((n4 >> b) & 1u) y = (y & ~(0xffu << (8 * b))) | (4u << (8 * b));
+        if (4 * grp + b >= nv) y = (y & ~(0xffu << (8 * b))) | (5u << (8 * b));
+      }
+    }
+    out[grp] = y;
+  }
+}
+
+// Slot pairs (2p, 2p+1) of `list` share a thread. Failures go to next_list (the 64-wide tier; score lower bound left in
 // res[].score) when the interval they need is <= SWB_MAXW wide, else to fb_keys (full-matrix kernel, key = columns).
 template <int MODE, int W>
-__global__ void __launch_bounds__(SWB_BLOCK, (W > 32 ? 2 : (W == 32 ? 3 : 6)))
-k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, uint32_t n_list, SwScore sc,
-          SwRes *__restrict__ res, const uint8_t *__restrict__ bytes, uint32_t stride, Rec16 *__restrict__ fb_keys,
-          uint32_t *__restrict__ fb_count, uint32_t *__restrict__ next_list, uint32_t *__restrict__ next_count) {
+__global__ void __launch_bounds__(SWB_BLOCK, (W > 32 ? 4 : 6))
+k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, uint32_t n_list, SwPlanes pl, SwScore sc,
+          SwRes *__restrict__ res, Rec16 *__restrict__ fb_keys, uint32_t *__restrict__ fb_count,
+          uint32_t *__restrict__ next_list, uint32_t *__restrict__ next_count) {
   constexpr bool REVERSE = MODE == 1;
+  constexpr int NH = W > 32 ? W / 32 : 1;      // tracking keys per 32-slot half
+  constexpr int COLW = BandSmem<W>::COLW;
+  extern __shared__ uint32_t smem[];
+  uint32_t *colA = smem + threadIdx.x, *colB = colA + COLW * SWB_BLOCK, *qAB = colB + COLW * SWB_BLOCK;
   const uint32_t p = blockIdx.x * SWB_BLOCK + threadIdx.x;
   if (2 * p >= n_list) return;
   const bool single = 2 * p + 1 >= n_list;
@@ -111,75 +181,86 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
   const BandGeo ga = band_geo<MODE, W>(ta, ra, sc), gb = band_geo<MODE, W>(tb, rb, sc);
   const int32_t rows[2] = {ga.rows, gb.rows}, cols[2] = {ga.cols, gb.cols}, c0[2] = {ga.c0, gb.c0};
   const int32_t rows_max = rows[0] > rows[1] ? rows[0] : rows[1];
-  const uint8_t *bp = bytes + 2 * (size_t)p;
-  // low byte = alignment A, high byte = alignment B (for an unpaired last slot the B half computes on whatever the
-  // neighbour byte holds and its result is dropped)
-  auto ld2 = [&](int32_t k) -> uint32_t { return __ldg(reinterpret_cast<const uint16_t *>(bp + (size_t)k * stride)); };
+  const int32_t rows4 = (rows_max + 3) & ~3;                   // the sweep runs whole groups of four rows
+
+  // ---- unpack this thread's selector streams (low half = alignment A, high half = B; an unpaired last slot runs the
+  // same alignment in both halves and drops the second result)
+  fill_col_stream<MODE>(pl, ta, ra, ga, false, rows4 + W, colA);
+  fill_col_stream<MODE>(pl, tb, rb, gb, true, rows4 + W, colB);
+  for (int32_t g = 0; 32 * g < rows4 + 4; g++) {
+    uint32_t qa[8], qb[8];
+    q_group<MODE>(pl, ta, rows[0], g, qa);
+    q_group<MODE>(pl, tb, rows[1], g, qb);
+#pragma unroll
+    for (int grp = 0; grp < 8; grp++)
+      if (32 * g + 4 * grp < rows4 + 4) qAB[(size_t)(8 * g + grp) * SWB_BLOCK] = qa[grp] | (qb[grp] << 4);
+  }
 
   const uint32_t mis_b = (uint32_t)(-(sc.mismatch * 32)) & 0xffu, mat_b = (uint32_t)(sc.match * 32) & 0xffu;
-  const uint32_t MIS4 = mis_b * 0x01010101u, DIFF = mis_b ^ mat_b;
+  const uint32_t PSRC = mis_b | (mat_b << 8);                 // bytes {mismatch, match, 0, 0}: source of every row profile
+  const uint32_t QLUT0 = 0x20100201u, QLUT1 = 0x00000033u;    // row code 0-5 -> the byte naming its profile selector ...
+  const uint32_t QSRC = 0x22100100u;                          // ... whose nibbles pick the selector's two bytes here
   const uint32_t NEG_GO = pack2(-sc.gap_open * 32), NEG_GE = pack2(-sc.gap_extend * 32), MIN2 = 0x80008000u;
 
-  // selector halves: alignment A copies byte w of PA (sign-replicated into the high byte), B byte w of PB;
-  // outside the matrix both nibbles replicate a sign (score 0 or -1, never positive)
-  auto mk_sel = [](uint32_t ab) -> uint32_t {       // ab = byte A | byte B << 8
-    const uint32_t a = ab & 15u, b = (ab >> 8) & 15u;
-    return (a | ((a & 3u) << 4) | 0x80u) | ((b | ((b & 3u) << 4) | 0xC4u) << 8);
-  };
   uint32_t H[W], V[W], sel[W];
 #pragma unroll
-  for (int t = 0; t < W; t++) {
-    H[t] = 0; V[t] = 0;
-    sel[t] = mk_sel(ld2(t));
+  for (int t = 0; t < W; t += 4) {
+    const uint32_t wa = colA[(size_t)(t / 4) * SWB_BLOCK], wb = colB[(size_t)(t / 4) * SWB_BLOCK];
+#pragma unroll
+    for (int r = 0; r < 4; r++) { H[t + r] = 0; V[t + r] = 0; sel[t + r] = prmt(wa, wb, (uint32_t)(((4 + r) << 4) | r)); }
   }
-  uint32_t rowbytes = ld2(0);                                // query codes of row 0 (prefetched one row ahead)
-  // forward: key = score << 12 | (4095 - column); reverse: key = 4095 - scan column of the first hit (0 = none)
-  uint32_t bestA = 0, bestB = 0, rowA = 0, rowB = 0;
+  // forward: key = score * 32 | 31 of the best cell so far, info = row << 8 | band slot of that cell;
+  // reverse: (rcol, info) = first (smallest scan column, then smallest row) cell reaching the forward score
+  uint32_t keyA = 31u, keyB = 31u, infoA = 0, infoB = 0;
+  uint32_t rcolA = 0xffffffffu, rcolB = 0xffffffffu;
   const uint32_t thrA = REVERSE ? (uint32_t)ra.score * 32u : 0u, thrB = REVERSE ? (uint32_t)rb.score * 32u : 0u;
-  // tracking keys carry (31 - slot) in the low bits; scores are scaled by 32 (5 free bits) so for W = 64 the key is
-  // kept per 32-slot half and the halves are compared explicitly
-  for (int32_t i = 0; i < rows_max; i++) {
-    // row profiles [s(q,A) s(q,C) s(q,G) s(q,T)] x 32; code-4 rows score 0; rows past the query mismatch everything
-    const uint32_t qa = (rowbytes >> 4) & 15u, qb = rowbytes >> 12;
-    const uint32_t PA = qa == 4u ? 0u : (qa == 5u ? MIS4 : (MIS4 ^ (DIFF << (8 * qa))));
-    const uint32_t PB = qb == 4u ? 0u : (qb == 5u ? MIS4 : (MIS4 ^ (DIFF << (8 * qb))));
-    // issue next row's loads now; they complete under the cell body (indices stay below rows_max + W)
-    const uint32_t next = ld2(i + 1), ent = ld2(i + W);
-    constexpr int NH = W > 32 ? W / 32 : 1;      // tracking keys per 32-slot half
-    uint32_t e = 0, acc[NH];
+  for (int32_t i0 = 0; i0 < rows4; i0 += 4) {
+    const uint32_t qword = qAB[(size_t)(i0 / 4) * SWB_BLOCK];
+    const uint32_t ewa = colA[(size_t)((i0 + W) / 4) * SWB_BLOCK], ewb = colB[(size_t)((i0 + W) / 4) * SWB_BLOCK];
 #pragma unroll
-    for (int h = 0; h < NH; h++) acc[h] = 0;
+    for (int r = 0; r < 4; r++) {
+      const int32_t i = i0 + r;
+      // row profiles [s(q,A) s(q,C) s(q,G) s(q,T)] x 32 of both alignments from the row's code byte, PRMTs only
+      const uint32_t codes = prmt(qword, 0u, 0x4440u | (uint32_t)r);
+      const uint32_t q32 = prmt(QSRC, 0u, prmt(QLUT0, QLUT1, codes));
+      const uint32_t PA = prmt(PSRC, 0u, q32), PB = prmt(PSRC, 0u, q32 >> 16);
+      uint32_t e = 0, acc[NH];
 #pragma unroll
-    for (int t = 0; t < W; t++) {
-      const uint32_t s = prmt(PA, PB, sel[t]);
-      const uint32_t v = V[t];
-      uint32_t h = __viaddmax_s16x2_relu(H[t], s, v);           // max(H[i-1][j-1] + s, vertical gap, 0)
-      h = __vimax3_s16x2(h, e, e);                                // ... and the horizontal gap
-      H[t] = h;
-      const uint32_t hgo = __viaddmax_s16x2(h, NEG_GO, MIN2);
-      e = __viaddmax_s16x2(e, NEG_GE, hgo);                      // horizontal gap into (i, j+1)
-      if (t > 0) V[t - 1] = __viaddmax_s16x2(v, NEG_GE, hgo);    // vertical gap into (i+1, j): band slot t-1 next row
-      acc[t / 32] = __viaddmax_s16x2(h, (uint32_t)(31 - (t & 31)) * 0x10001u, acc[t / 32]);   // H*32 + (31 - slot): smallest column wins ties
-    }
-    // slide the column selectors: next row's slot t is this row's slot t+1; the last slot takes the entering column
+      for (int h = 0; h < NH; h++) acc[h] = 0;
 #pragma unroll
-    for (int t = 0; t < W - 1; t++) sel[t] = sel[t + 1];
-    sel[W - 1] = mk_sel(ent);
-    rowbytes = next;
-    // row winners -> running best (first column, then smallest row: rows only grow, so ties keep the old one)
+      for (int t = 0; t < W; t++) {
+        const uint32_t s = prmt(PA, PB, sel[t]);
+        const uint32_t v = V[t];
+        uint32_t h = __viaddmax_s16x2_relu(H[t], s, v);           // max(H[i-1][j-1] + s, vertical gap, 0)
+        h = __vimax3_s16x2(h, e, e);                                // ... and the horizontal gap
+        H[t] = h;
+        const uint32_t hgo = __viaddmax_s16x2(h, NEG_GO, MIN2);
+        e = __viaddmax_s16x2(e, NEG_GE, hgo);                      // horizontal gap into (i, j+1)
+        if (t > 0) V[t - 1] = __viaddmax_s16x2(v, NEG_GE, hgo);    // vertical gap into (i+1, j): band slot t-1 next row
+        acc[t / 32] = __viaddmax_s16x2(h, (uint32_t)(31 - (t & 31)) * 0x10001u, acc[t / 32]);   // H*32 + (31 - slot): smallest column wins ties
+      }
+      // slide the column selectors: next row's slot t is this row's slot t+1; the last slot takes the entering column
 #pragma unroll
-    for (int h = 0; h < NH; h++) {
-      const uint32_t aA = acc[h] & 0xffffu, aB = acc[h] >> 16;
-      const uint32_t jA = (uint32_t)(i + 32 * h + (int32_t)(31u - (aA & 31u)) + c0[0]);
-      const uint32_t jB = (uint32_t)(i + 32 * h + (int32_t)(31u - (aB & 31u)) + c0[1]);
-      if (REVERSE) {
-        const uint32_t kA = 4095u - jA, kB = 4095u - jB;
-        if (aA >= thrA && kA > bestA && jA < 4096u) { bestA = kA; rowA = (uint32_t)i; }
-        if (aB >= thrB && kB > bestB && jB < 4096u) { bestB = kB; rowB = (uint32_t)i; }
-      } else {
-        const uint32_t kA = ((aA >> 5) << 12) | (4095u - (jA & 4095u)), kB = ((aB >> 5) << 12) | (4095u - (jB & 4095u));
-        if (aA >= 32u && kA > bestA) { bestA = kA; rowA = (uint32_t)i; }
-        if (aB >= 32u && kB > bestB) { bestB = kB; rowB = (uint32_t)i; }
+      for (int t = 0; t < W - 1; t++) sel[t] = sel[t + 1];
+      sel[W - 1] = prmt(ewa, ewb, (uint32_t)(((4 + r) << 4) | r));
+      // row winners -> running best. SSW's rule: first column attaining the maximum, then the smallest row
+      // (ssw.c:316-342). Rows only grow, so a strictly larger score always wins (the common, branch-free path) and an
+      // equal score wins only with a strictly smaller column.
+#pragma unroll
+      for (int h = 0; h < NH; h++) {
+        const uint32_t aA = acc[h] & 0xffffu, aB = acc[h] >> 16;
+        if (REVERSE) {
+          if (aA >= thrA) { const uint32_t j = (uint32_t)(i + 32 * h + (int32_t)(31u - (aA & 31u)) + c0[0]);
+                            if (j < rcolA && j < 4096u) { rcolA = j; infoA = (uint32_t)i; } }
+          if (aB >= thrB) { const uint32_t j = (uint32_t)(i + 32 * h + (int32_t)(31u - (aB & 31u)) + c0[1]);
+                            if (j < rcolB && j < 4096u) { rcolB = j; infoB = (uint32_t)i; } }
+        } else {
+          const uint32_t nA = ((uint32_t)i << 8) | ((uint32_t)(32 * h + 31) - (aA & 31u)), nB = ((uint32_t)i << 8) | ((uint32_t)(32 * h + 31) - (aB & 31u));
+          if (aA > keyA) { keyA = aA | 31u; infoA = nA; }
+          else if ((aA | 31u) == keyA && aA > 31u && (nA >> 8) + (nA & 255u) < (infoA >> 8) + (infoA & 255u)) infoA = nA;
+          if (aB > keyB) { keyB = aB | 31u; infoB = nB; }
+          else if ((aB | 31u) == keyB && aB > 31u && (nB >> 8) + (nB & 255u) < (infoB >> 8) + (infoB & 255u)) infoB = nB;
+        }
       }
     }
   }
@@ -188,25 +269,27 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
   for (int al = 0; al < 2; al++) {
     if (al == 1 && single) break;
     const uint32_t idx = al ? ib : ia;
-    const uint32_t best = al ? bestB : bestA, brow = al ? rowB : rowA;
     if (REVERSE) {
       const SwRes &r0 = al ? rb : ra;
-      if (best) {
-        res[idx].ref_begin = r0.ref_end - (int32_t)(4095u - best);
-        res[idx].read_begin = r0.read_end - (int32_t)brow;
+      const uint32_t rcol = al ? rcolB : rcolA, rrow = al ? infoB : infoA;
+      if (rcol != 0xffffffffu) {
+        res[idx].ref_begin = r0.ref_end - (int32_t)rcol;
+        res[idx].read_begin = r0.read_end - (int32_t)rrow;
         res[idx].flags = r0.flags | SWR_REV_TIER(SWR_TIER_OF_W(W));
       } else {                      // cannot happen when the bound holds; never guess: hand over to the full kernel
         const uint32_t k = atomicAdd(fb_count, 1u);
         fb_keys[k].key = (uint64_t)(r0.ref_end + 1); fb_keys[k].val = idx;
       }
     } else {
-      const int32_t S = (int32_t)(best >> 12);
+      const uint32_t key = al ? keyB : keyA, info = al ? infoB : infoA;
+      const int32_t S = (int32_t)(key >> 5);
+      const int32_t brow = (int32_t)(info >> 8), bcol = brow + (int32_t)(info & 255u) + c0[al];
       const int32_t a = ceil_div_pos(S, sc.match);
       const bool proven = S > 0 && c0[al] <= -(rows[al] - a) && (cols[al] - a) <= c0[al] + (W - 1);
       if (proven) {
         SwRes o;
         o.flags = SWR_FWD_TIER(SWR_TIER_OF_W(W)); o.pad0 = o.pad1 = 0; o.ref_begin = -1; o.read_begin = 0;
-        o.score = S; o.ref_end = (int32_t)(4095u - (best & 4095u)); o.read_end = (int32_t)brow;
+        o.score = S; o.ref_end = bcol; o.read_end = brow;
         res[idx] = o;
       } else if (MODE == 0 && next_list && S > 0 && rows[al] + cols[al] - 2 * a + 1 <= SWB_MAXW) {
         res[idx].score = S;         // lower bound: every alignment scoring >= S lies in [-(m - a), n - a]
