@@ -240,8 +240,8 @@ def main():
 
         def step_e2e():
             al.upload_reads(rb_host, ro)
-            res, _ = kd.align_partitioned(engine, exch, n_reads, fetch=True)
-            return res, al.pair_batch(fetch=True, copy=False)
+            kd.align_partitioned(engine, exch, n_reads, fetch=False)
+            return None, al.pair_batch(fetch=True, copy=False)
     else:
         al.load_genomes(gb, go)
 
@@ -249,7 +249,7 @@ def main():
             al.align_resident(fetch=False); al.pair_batch(fetch=False)
 
         def step_e2e():
-            return al.align_batch(rb_host, ro, copy=False), al.pair_batch(fetch=True, copy=False)
+            return None, al.align_pair_batch(rb_host, ro, copy=False)
     t_load = time.time() - t0
     log(f"[bench r{rank}] genome index built in {t_load:.2f}s")
 
@@ -278,18 +278,52 @@ def main():
     launches = (tm["kernel_launches"] - launches0) // max(1, args.steps)
 
     # ---- e2e: host buffers in, results back on the host ------------------------------------------
-    for _ in range(max(1, args.warmup - 1)):
-        res, pr = step_e2e()
+    # The reference-facing call with HOST buffers: kslam_align_pair_batch = the body of the batch loop (SLAM.h:209-214),
+    # H2D of the reads and D2H of everything the loop keeps inside the timed region. Batches are streamed through TWO
+    # contexts on the same GPU (include/kslam.h: "two per GPU to double-buffer"), each driven by its own host thread, so
+    # one batch's PCIe copies overlap the other's kernels. The partitioned workload runs one context (its NCCL
+    # collectives are issued in program order).
+    depth = 1 if partitioned else 2
+    ctxs = [al]
+    if depth == 2:
+        al2 = pkg.Aligner(report_cigar=False, device=local)
+        al2.set_debug_taps(False)
+        al2.load_genomes(gb, go)
+        ctxs.append(al2)
+    last = [None] * depth
+
+    def run_e2e(n_batches):
+        if depth == 1:
+            for _ in range(n_batches):
+                last[0] = step_e2e()[1]
+            return
+        errs = []
+
+        def worker(k):
+            try:
+                torch.cuda.set_device(local)
+                for _b in range(k, n_batches, depth):
+                    last[k] = ctxs[k].align_pair_batch(rb_host, ro, copy=False)
+            except Exception as e:   # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=worker, args=(k,)) for k in range(depth)]
+        [t.start() for t in th]; [t.join() for t in th]
+        if errs:
+            raise errs[0]
+
+    run_e2e(max(2, args.warmup - 1))
     barrier()
     tw0 = time.perf_counter()
-    for _ in range(args.steps):
-        res, pr = step_e2e()
+    run_e2e(args.steps)
     barrier()
     tw3 = time.perf_counter()
     t_e2e = tw3 - tw0
     clocks = sampler.stop(tw_first, tw3) if rank == 0 else None
+    pr = last[0]
     h2d = int(rb_host.nbytes + 3 * ro.nbytes)
-    d2h = int(res.overlaps.nbytes + pr.sorted_overlaps.nbytes + pr.pairs.nbytes)
+    d2h = int(pr.sorted_overlaps.nbytes + pr.cigar_pool.nbytes + pr.pairs.nbytes)
+    if depth == 2:
+        al2.close()
 
     t_max = torch.tensor([t_res, t_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -338,7 +372,9 @@ def main():
                "config": {"workload": desc, "batch_pairs_per_gpu": pairs, "sharding": (f"genome k-mer list range-partitioned over {world} ranks + read pairs per rank; all-to-all of k-mer records "
                                        f"and of raw matches (NCCL)" if partitioned else f"read pairs, {world} ranks, no collective"),
                           "l2": "inputs larger than L2 (3.8 GB+ of k-mer records per step)", "report_cigar": False},
-               "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+               "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "call": "kslam_align_pair_batch (host buffers in, pair-sorted overlaps + pairs back on the host)",
+                       "contexts_per_gpu": depth},
                "gpu_launches": int(launches),
                "clocks": clocks,
                "roofline": dominant, "roofline_hbm": hbm_roof, "roofline_int": int_roof,
@@ -346,6 +382,7 @@ def main():
                "stage_ms": ms,
                "counts": {k: tm[k] for k in ("n_read_kmers", "n_sorted_kmers", "n_genome_kmers", "n_raw_seeds", "n_seeds", "n_pairs",
                                              "n_sw_band", "n_sw_band64", "n_sw_fast", "n_sw_slow", "n_sw_band_rev",
+                                             "n_sw_tier8", "n_sw_tier16", "n_sw_tier32", "n_sw_tier64", "n_sw_sweep32",
                                              "sw_cells_forward", "sw_cells_reverse", "sw_cells_computed", "n_sort_passes")},
                "genome_index_build_s": t_load}
         if partitioned:

@@ -124,6 +124,11 @@ int kslam_align_resident(kslam_ctx *ctx, int fetch_results, kslam_alignments *ou
  * the alignments of the last batch (device-resident). */
 int kslam_pair_batch(kslam_ctx *ctx, int fetch_results, kslam_pairs *out /* may be NULL */);
 
+/* The body of the reference's batch loop in one call (SLAM.h:209-214: alignToDatabase, score screen, getPairedOverlaps):
+ * same results as kslam_align_batch + kslam_pair_batch, but the unsorted alignment vector — which the loop discards
+ * once it is sorted — is never copied to the host. */
+int kslam_align_pair_batch(kslam_ctx *ctx, uint64_t n_reads, const char *bases, const uint64_t *offs, kslam_pairs *out);
+
 /* Aligner::Align (ssw_cpp.cpp:234-283) for n independent (query, ref) pairs, SSW's own coordinates
  * (no window un-flip). out[n] and cigar_pool[n * max_cigar_ops] are caller buffers (host). */
 int kslam_ssw_batch(kslam_ctx *ctx, uint64_t n, const char *q, const uint64_t *qoffs, const char *r,
@@ -178,6 +183,12 @@ int kslam_measure_int_peak(kslam_ctx *ctx, double *ops_per_s);
  * extracted — they cannot seed (Overlap.h:157,236-239) — so only the survivors are written, sorted and joined.
  * Results are identical either way; with the filter off the read k-mer tap holds every record (KMer.h:160-181). */
 int kslam_set_prefilter(kslam_ctx *ctx, int on);
+/* Read k-mer records are radix-sorted on their leading `bits` bits only before the merge-join (it binary-searches each
+ * record inside its tile's genome sub-range, so a total order is not needed): 0 (default) = log2(genome k-mers) + 2
+ * rounded up to whole 8-bit digits, 64 = total order as KMer.h:388-398. The seed multiset is identical either way;
+ * the read k-mer tap is ordered on those bits. */
+int kslam_set_kmer_sort_bits(kslam_ctx *ctx, uint32_t bits);
+int kslam_get_kmer_sort_bits(const kslam_ctx *ctx);
 /* Banded Smith-Waterman tiers: 0 = full-matrix kernel only; 1 = alignments whose optimum is provably inside a
  * 32-diagonal band run in the banded kernel (sweep, then verify); 2 = additionally a 64-diagonal tier for what that
  * sweep bounded but could not prove; 3 (default) = additionally bands of 8 / 16 / 32 / 64 diagonals placed directly

@@ -109,6 +109,7 @@ def lib():
     L.kslam_load_genomes.argtypes = [vp, u64, vp, vp]
     L.kslam_align_batch.argtypes = [vp, u64, vp, vp, C.POINTER(_Alignments)]
     L.kslam_upload_reads.argtypes = [vp, u64, vp, vp]
+    L.kslam_align_pair_batch.argtypes = [vp, u64, vp, vp, C.POINTER(_Pairs)]
     L.kslam_align_resident.argtypes = [vp, i32, C.POINTER(_Alignments)]
     L.kslam_pair_batch.argtypes = [vp, i32, C.POINTER(_Pairs)]
     L.kslam_ssw_batch.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
@@ -124,6 +125,8 @@ def lib():
     L.kslam_set_prefilter.argtypes = [vp, i32]
     L.kslam_set_sw_band.argtypes = [vp, i32]
     u32 = C.c_uint32
+    L.kslam_set_kmer_sort_bits.argtypes = [vp, u32]
+    L.kslam_get_kmer_sort_bits.argtypes = [vp]
     L.kslam_load_genomes_part.argtypes = [vp, u64, vp, vp, u32, u32]
     L.kslam_get_partition.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), vp, C.POINTER(u64)]
     L.kslam_part_route_kmers.argtypes = [vp, u32, C.POINTER(vp), vp]
@@ -286,11 +289,23 @@ class Aligner:
         cg = _view(out.cigar_pool, out.n_cigar_words, np.dtype("<u4"))
         return Alignments(ov.copy() if copy else ov, cg.copy() if copy else cg)
 
+    def align_pair_batch(self, bases, offs, copy=True) -> "Pairs":
+        """alignToDatabase + screen + getPairedOverlaps (SLAM.h:209-214) in one call; only the pair-stage results
+        (what the reference's loop keeps) are copied back."""
+        bases, offs = _u8(bases), _u64(offs)
+        out = _Pairs()
+        self._check(self.L.kslam_align_pair_batch(self.h, len(offs) - 1, _ptr(bases), _ptr(offs), C.byref(out)),
+                    "kslam_align_pair_batch")
+        return self._pairs(out, copy)
+
     def pair_batch(self, fetch=True, copy=True):
         out = _Pairs()
         self._check(self.L.kslam_pair_batch(self.h, int(fetch), C.byref(out)), "kslam_pair_batch")
         if not fetch:
             return int(out.n_pairs)
+        return self._pairs(out, copy)
+
+    def _pairs(self, out, copy):
         so = _view(out.sorted_overlaps, out.n_sorted, OVERLAP_DT)
         cg = _view(out.cigar_pool, out.n_cigar_words, np.dtype("<u4"))
         pr = _view(out.pairs, out.n_pairs, PAIR_DT)
@@ -356,6 +371,13 @@ class Aligner:
     def set_sw_band(self, level: int):
         """0 = full-matrix kernel only, 1 = 32-diagonal sweep tier, 2 = + 64-diagonal tier, 3 (default) = + direct tiers."""
         self._check(self.L.kslam_set_sw_band(self.h, int(level)), "kslam_set_sw_band")
+
+    def set_kmer_sort_bits(self, bits: int):
+        """Leading k-mer bits the read records are sorted on before the join (0 = auto, 64 = total order)."""
+        self._check(self.L.kslam_set_kmer_sort_bits(self.h, int(bits)), "kslam_set_kmer_sort_bits")
+
+    def kmer_sort_bits(self) -> int:
+        return self._check(self.L.kslam_get_kmer_sort_bits(self.h), "kslam_get_kmer_sort_bits")
 
     def set_debug_taps(self, keep: bool):
         self._check(self.L.kslam_set_debug_taps(self.h, int(keep)), "kslam_set_debug_taps")

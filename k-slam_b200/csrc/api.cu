@@ -112,6 +112,14 @@ int kslam_set_sw_band(kslam_ctx *ctx, int on) {
   return KSLAM_OK;
 }
 
+int kslam_set_kmer_sort_bits(kslam_ctx *ctx, uint32_t bits) {
+  if (!ctx || bits > 64) return KSLAM_ERR_ARG;
+  ctx->sort_bits = bits;
+  return KSLAM_OK;
+}
+
+int kslam_get_kmer_sort_bits(const kslam_ctx *ctx) { return ctx ? (int)kmer_sort_bits(ctx) : KSLAM_ERR_ARG; }
+
 int kslam_set_debug_taps(kslam_ctx *ctx, int keep) {
   if (!ctx) return KSLAM_ERR_ARG;
   ctx->keep_taps = keep != 0;
@@ -222,18 +230,20 @@ static void align_device(kslam_ctx *c) {
   c->tm.n_read_kmers = c->n_rk; c->tm.n_sort_passes = 0;
   c->sorted_rk = nullptr;
   if (c->n_rk) {
-    c->recA.reserve((size_t)c->n_rk * sizeof(Rec16));
     if (c->prefilter && c->filter_bits) {
       // fused extract + prefilter: n_rk becomes the number of records that can still match a genome k-mer
-      c->n_rk = extract_read_kmers_filtered(c, c->reads, c->recA.as<Rec16>());
-    } else extract_kmers(c, c->reads, false, 1, c->recA.as<Rec16>());
+      c->n_rk = extract_read_kmers_filtered(c, c->reads, c->recA);
+    } else {
+      c->recA.reserve((size_t)c->n_rk * sizeof(Rec16));
+      extract_kmers(c, c->reads, false, 1, c->recA.as<Rec16>());
+    }
     c->recB.reserve((size_t)c->n_rk * sizeof(Rec16) + 64);
   }
   c->tm.n_sorted_kmers = c->n_rk;
   cudaEvent_t e1 = tm_mark(c);
   if (c->n_rk) {
     uint64_t passes = 0;
-    c->sorted_rk = radix_sort(c, c->recA.as<Rec16>(), c->recB.as<Rec16>(), c->n_rk, 0, 0, 64, &passes);
+    c->sorted_rk = radix_sort(c, c->recA.as<Rec16>(), c->recB.as<Rec16>(), c->n_rk, 0, 64 - kmer_sort_bits(c), 64, &passes);
     c->tm.n_sort_passes += passes;
   }
   cudaEvent_t e2 = tm_mark(c);
@@ -333,6 +343,18 @@ int kslam_pair_batch(kslam_ctx *c, int fetch, kslam_pairs *out) {
   }
   return KSLAM_OK;
   API_END(c)
+}
+
+// alignToDatabase + screen + getPairedOverlaps in one call (the body of the reference's batch loop, SLAM.h:209-214):
+// the unsorted alignment vector never leaves the GPU, only what the loop keeps (pair-sorted overlaps, CIGARs, pairs).
+int kslam_align_pair_batch(kslam_ctx *c, uint64_t n, const char *bases, const uint64_t *offs, kslam_pairs *out) {
+  int rc = kslam_upload_reads(c, n, bases, offs);
+  if (rc != KSLAM_OK) return rc;
+  const float pack = c->tm.ms_pack;
+  rc = kslam_align_resident(c, 0, nullptr);
+  c->tm.ms_pack = pack;
+  if (rc != KSLAM_OK) return rc;
+  return kslam_pair_batch(c, 1, out);
 }
 
 // ---- Aligner::Align batch ------------------------------------------------------------------------

@@ -96,6 +96,7 @@ struct kslam_ctx {
   uint32_t filter_bits = 0;
   bool prefilter = true;
   bool sw_band64 = true;   // second banded tier (64 diagonals) for what the 32-wide sweep cannot prove
+  uint32_t sort_bits = 0;  // leading k-mer bits the read records are sorted on before the join; 0 = auto
   bool sw_tiers = true;    // direct tiers (8 / 16 / 32 / 64 diagonals) picked from the seed-diagonal lower bound
   bool sw_band = true;     // banded SW kernel with exactness proof + full-matrix fallback (sw_band.cuh)
   uint32_t max_genome_len = 0;
@@ -149,7 +150,7 @@ void pack_sequences(kslam_ctx *c, PackedSeqs &s, uint64_t n, const char *bases, 
 // kmer.cu
 void extract_kmers(kslam_ctx *c, const PackedSeqs &s, bool is_gb, uint32_t gap, Rec16 *out);
 void build_prefilter(kslam_ctx *c);
-uint64_t extract_read_kmers_filtered(kslam_ctx *c, const PackedSeqs &s, Rec16 *out, uint32_t id_base = 0);
+uint64_t extract_read_kmers_filtered(kslam_ctx *c, const PackedSeqs &s, DevBuf &outbuf, uint32_t id_base = 0);
 void extract_genome_kmers_range(kslam_ctx *c, const PackedSeqs &s, uint32_t gap, uint64_t i_begin, uint64_t i_stride,
                                 uint64_t n_out, Rec16 *out);
 // radix_sort.cu
@@ -202,6 +203,16 @@ static inline uint32_t prefilter_bits(uint64_t n_genome_kmers) {
   uint32_t b = 0;
   while (b < 64 && (1ull << b) < n_genome_kmers * 16) b++;
   return b < 26 ? 26 : (b > 34 ? 34 : b);
+}
+
+static inline uint32_t ceil_log2_u64_(uint64_t x) { uint32_t b = 0; while (b < 64 && (1ull << b) < x) b++; return b; }
+// The merge-join binary-searches every read record inside the genome sub-range its tile covers, so read records only
+// have to be GROUPED finely enough for that sub-range to stay small: sorting on the leading log2(genome k-mers) + 2
+// bits (rounded up to whole 8-bit digits) leaves < 1 genome key per bucket and halves the radix passes.
+static inline uint32_t kmer_sort_bits(const kslam_ctx *c) {
+  if (c->sort_bits) return c->sort_bits > 64 ? 64 : c->sort_bits;
+  uint32_t b = (ceil_log2_u64_(c->n_gk_total ? c->n_gk_total : 1) + 2 + 7) & ~7u;
+  return b < 16 ? 16 : (b > 64 ? 64 : b);
 }
 
 static inline uint32_t ceil_log2_u64(uint64_t x) {

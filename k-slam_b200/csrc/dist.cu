@@ -227,8 +227,7 @@ int kslam_part_route_kmers(kslam_ctx *c, uint32_t read_id_base, const void **dev
   uint64_t n = 0;
   c->tm.n_read_kmers = c->reads.n_kmers; c->tm.n_sort_passes = 0;
   if (c->reads.n_kmers && c->filter_bits) {
-    c->recA.reserve((size_t)c->reads.n_kmers * sizeof(Rec16));
-    n = extract_read_kmers_filtered(c, c->reads, c->recA.as<Rec16>(), read_id_base);
+    n = extract_read_kmers_filtered(c, c->reads, c->recA, read_id_base);
   }
   c->part_send.reserve((size_t)n * sizeof(Rec16) + 64);
   bucket_records<0>(c, c->recA.as<Rec16>(), n, c->splitters.data(), c->part_send.as<Rec16>(), counts);
@@ -260,7 +259,7 @@ int kslam_part_join(kslam_ctx *c, uint64_t n_records, const uint32_t *id_bases, 
   cudaEvent_t e0 = tm_mark(c);
   uint64_t passes = 0;
   const Rec16 *sorted = nullptr;
-  if (n_records) sorted = radix_sort(c, c->part_recv.as<Rec16>(), c->part_tmp.as<Rec16>(), n_records, 0, 0, 64, &passes);
+  if (n_records) sorted = radix_sort(c, c->part_recv.as<Rec16>(), c->part_tmp.as<Rec16>(), n_records, 0, 64 - kmer_sort_bits(c), 64, &passes);
   cudaEvent_t e1 = tm_mark(c);
   const uint64_t n_m = run_join(c, sorted, n_records, true, c->part_m);
   c->part_msend.reserve((size_t)n_m * sizeof(Rec16) + 64);

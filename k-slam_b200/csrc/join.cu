@@ -61,7 +61,9 @@ template <bool MATCH>
 __global__ void __launch_bounds__(JN_THREADS)
 k_join(const Rec16 *__restrict__ R, uint64_t n_r, const uint64_t *__restrict__ gkeys,
        const uint64_t *__restrict__ gvals, uint64_t n_g, const uint64_t *__restrict__ read_offs,
-       Rec16 *__restrict__ out, uint64_t cap, unsigned long long *__restrict__ counter, uint32_t bias) {
+       Rec16 *__restrict__ out, uint64_t cap, unsigned long long *__restrict__ counter, uint32_t bias, uint64_t low_mask) {
+  // R is ordered on the key bits above low_mask only (the radix sort stops there: the binary search below does not
+  // need more), so the tile's key range is widened by the unsorted low bits
   __shared__ uint64_t s_g[JN_GCAP];
   __shared__ uint64_t s_range[2];
   __shared__ uint32_t s_warp[32];
@@ -70,8 +72,8 @@ k_join(const Rec16 *__restrict__ R, uint64_t n_r, const uint64_t *__restrict__ g
   const uint32_t tid = threadIdx.x, warp = tid >> 5;
   const uint64_t t0 = (uint64_t)blockIdx.x * JN_TILE;
   const uint64_t t1 = t0 + JN_TILE < n_r ? t0 + JN_TILE : n_r;
-  if (warp == 0) { uint64_t v = warp_bound(gkeys, n_g, R[t0].key, false); if (tid == 0) s_range[0] = v; }
-  if (warp == 1) { uint64_t v = warp_bound(gkeys, n_g, R[t1 - 1].key, true); if ((tid & 31) == 0) s_range[1] = v; }
+  if (warp == 0) { uint64_t v = warp_bound(gkeys, n_g, R[t0].key & ~low_mask, false); if (tid == 0) s_range[0] = v; }
+  if (warp == 1) { uint64_t v = warp_bound(gkeys, n_g, R[t1 - 1].key | low_mask, true); if ((tid & 31) == 0) s_range[1] = v; }
   __syncthreads();
   const uint64_t g_lo = s_range[0], g_hi = s_range[1];
   const uint64_t ng = g_hi - g_lo;
@@ -213,6 +215,8 @@ uint64_t run_join(kslam_ctx *c, const Rec16 *R, uint64_t n_r, bool match, DevBuf
   unsigned long long *d_cnt = c->counters.as<unsigned long long>();
   unsigned long long *h_cnt = c->h_counters.as<unsigned long long>();
   const uint32_t bias = c->reads.max_len;
+  const uint32_t sb = kmer_sort_bits(c);
+  const uint64_t low_mask = sb >= 64 ? 0ull : (~0ull >> sb);
   if (!n_r || !c->n_gk) return 0;
   uint64_t cap = outbuf.cap / sizeof(Rec16);
   if (cap < (1u << 20)) { outbuf.reserve((size_t)(n_r / 8 + (1u << 20)) * sizeof(Rec16)); cap = outbuf.cap / sizeof(Rec16); }
@@ -221,10 +225,10 @@ uint64_t run_join(kslam_ctx *c, const Rec16 *R, uint64_t n_r, bool match, DevBuf
     CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 8, st));
     if (match)
       k_join<true><<<(unsigned)tiles, JN_THREADS, 0, st>>>(R, n_r, c->g_keys.as<uint64_t>(), c->g_vals.as<uint64_t>(), c->n_gk,
-                                                           nullptr, outbuf.as<Rec16>(), cap, d_cnt, bias);
+                                                           nullptr, outbuf.as<Rec16>(), cap, d_cnt, bias, low_mask);
     else
       k_join<false><<<(unsigned)tiles, JN_THREADS, 0, st>>>(R, n_r, c->g_keys.as<uint64_t>(), c->g_vals.as<uint64_t>(), c->n_gk,
-                                                            c->reads.offs.as<uint64_t>(), outbuf.as<Rec16>(), cap, d_cnt, bias);
+                                                            c->reads.offs.as<uint64_t>(), outbuf.as<Rec16>(), cap, d_cnt, bias, low_mask);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));

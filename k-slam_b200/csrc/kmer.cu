@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256)
 k_extract_reads_filtered(const uint64_t *__restrict__ kbits, const uint64_t *__restrict__ offs,
                          const uint64_t *__restrict__ word_off, uint64_t n_seqs, const uint32_t *__restrict__ bitmap,
                          uint32_t bits, Rec16 *__restrict__ out, unsigned long long *__restrict__ counter,
-                         uint32_t id_base) {
+                         uint32_t id_base, uint64_t cap) {
   __shared__ __align__(16) Rec16 s_buf[8][XF_WBUF];
   const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
@@ -137,8 +137,9 @@ k_extract_reads_filtered(const uint64_t *__restrict__ kbits, const uint64_t *__r
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(counter, (unsigned long long)pending);
         base = __shfl_sync(0xffffffffu, base, 0);
-        for (uint32_t i = lane; i < pending; i += 32)
-          *reinterpret_cast<ulonglong2 *>(out + base + i) = *reinterpret_cast<const ulonglong2 *>(&buf[i]);
+        if (base + pending <= cap)       // overflow: the counter still ends at the exact total and the host re-runs
+          for (uint32_t i = lane; i < pending; i += 32)
+            *reinterpret_cast<ulonglong2 *>(out + base + i) = *reinterpret_cast<const ulonglong2 *>(&buf[i]);
         __syncwarp();
         pending = 0;
       }
@@ -149,8 +150,9 @@ k_extract_reads_filtered(const uint64_t *__restrict__ kbits, const uint64_t *__r
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(counter, (unsigned long long)pending);
     base = __shfl_sync(0xffffffffu, base, 0);
-    for (uint32_t i = lane; i < pending; i += 32)
-      *reinterpret_cast<ulonglong2 *>(out + base + i) = *reinterpret_cast<const ulonglong2 *>(&buf[i]);
+    if (base + pending <= cap)
+      for (uint32_t i = lane; i < pending; i += 32)
+        *reinterpret_cast<ulonglong2 *>(out + base + i) = *reinterpret_cast<const ulonglong2 *>(&buf[i]);
   }
 }
 
@@ -168,20 +170,31 @@ void build_prefilter(kslam_ctx *c) {
   c->filter_bits = bits;
 }
 
-// returns the number of records written (== s.n_kmers without the filter)
-uint64_t extract_read_kmers_filtered(kslam_ctx *c, const PackedSeqs &s, Rec16 *out, uint32_t id_base) {
+// Extracts the read k-mers that pass the prefilter into `outbuf` and returns their number. The buffer starts at an
+// eighth of the worst case (the filter keeps ~7 % on unrelated data) and is regrown to the exact size — the kernel's
+// counter keeps counting past the capacity — if a batch needs more.
+uint64_t extract_read_kmers_filtered(kslam_ctx *c, const PackedSeqs &s, DevBuf &outbuf, uint32_t id_base) {
   if (!s.n_kmers) return 0;
   unsigned long long *d_cnt = c->counters.as<unsigned long long>() + 2;
   unsigned long long *h_cnt = c->h_counters.as<unsigned long long>() + 2;
-  CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 8, c->stream));
+  uint64_t want = s.n_kmers / 8 + (1u << 20);
+  if (want > s.n_kmers) want = s.n_kmers;
+  if (outbuf.cap < want * sizeof(Rec16)) outbuf.reserve((size_t)want * sizeof(Rec16));
   uint64_t blocks = (s.n * 32 + 255) / 256, maxb = (uint64_t)c->num_sms * 8;
   if (blocks > maxb) blocks = maxb;
-  k_extract_reads_filtered<<<(unsigned)blocks, 256, 0, c->stream>>>(s.kbits.as<uint64_t>(), s.offs.as<uint64_t>(),
-      s.word_off.as<uint64_t>(), s.n, c->bitmap.as<uint32_t>(), c->filter_bits, out, d_cnt, id_base);
-  c->launches++;
-  CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (int attempt = 0; attempt < 2; attempt++) {
+    const uint64_t cap = outbuf.cap / sizeof(Rec16);
+    CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 8, c->stream));
+    k_extract_reads_filtered<<<(unsigned)blocks, 256, 0, c->stream>>>(s.kbits.as<uint64_t>(), s.offs.as<uint64_t>(),
+        s.word_off.as<uint64_t>(), s.n, c->bitmap.as<uint32_t>(), c->filter_bits, outbuf.as<Rec16>(), d_cnt, id_base, cap);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (h_cnt[0] <= cap) break;
+    if (attempt == 1) throw CudaError{cudaErrorMemoryAllocation, "read k-mer buffer overflow after regrow", __FILE__, __LINE__};
+    outbuf.reserve((size_t)h_cnt[0] * sizeof(Rec16));
+  }
   return h_cnt[0];
 }
 

@@ -578,7 +578,7 @@ __device__ __forceinline__ bool window_clean(const uint32_t *__restrict__ nmask,
 // `tiers` on, the seed-diagonal lower bound L picks the narrowest band that provably holds every optimal alignment
 // (res[].score = L is what MODE 2 of k_sw_band places the band with); otherwise, or when L allows nothing <= 64
 // diagonals (e.g. an indel splits the read over two diagonals), the 32-wide sweep-and-verify tier.
-__device__ __forceinline__ void enlist(const SwPlanes &pl, const SwTask &t, uint32_t i, uint32_t cls, int32_t d0, uint32_t tiers,
+__device__ __forceinline__ void enlist(const SwPlanes &pl, const SwTask &t, uint32_t i, uint32_t cls, int32_t d0, bool seeded, uint32_t tiers,
                                        uint32_t max_tier, const SwScore &sc, SwRes *__restrict__ res, uint8_t *__restrict__ tier_f,
                                        Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list, uint32_t *__restrict__ counts) {
   uint32_t tier = SWT_TIER_NONE;
@@ -638,7 +638,7 @@ k_sw_prepare_seeds(const kslam_seed *__restrict__ seeds, uint32_t n, const uint6
   // matrix diagonal of the seed's exact 32-mer match: forward seeds put read base i on genome base rel + i; reverse-
   // complement seeds put rc(read) base i there and Align sees the window reversed (SmithWaterman.h:205-208)
   const int32_t d0 = s.rev_comp ? (int32_t)t.w_start + (int32_t)t.n - s.rel - (int32_t)t.m : s.rel - (int32_t)t.w_start;
-  enlist(pl, t, i, cls, d0, use_band >= 3, use_band >= 2 ? 3u : 2u, sc, res, tier_f, full_keys, slow_list, counts);
+  enlist(pl, t, i, cls, d0, true, use_band >= 3, use_band >= 2 ? 3u : 2u, sc, res, tier_f, full_keys, slow_list, counts);
 }
 
 // Aligner::Align batch mode: query i against ref i, whole sequences
@@ -658,7 +658,7 @@ k_sw_prepare_pairs(uint32_t n, const uint64_t *__restrict__ q_offs, const uint64
   t.flags = cls << 8;
   if (use_band && cls == SWC_FAST8 && t.m <= SWB_MAXROWS && window_clean(r_nmask, t.w_word, 0, t.n)) t.flags |= SWT_BAND;
   tasks[i] = t;
-  enlist(pl, t, i, cls, 0, use_band >= 3, use_band >= 2 ? 3u : 2u, sc, res, tier_f, full_keys, slow_list, counts);   // no seed: try the main diagonal
+  enlist(pl, t, i, cls, 0, false, use_band >= 3, use_band >= 2 ? 3u : 2u, sc, res, tier_f, full_keys, slow_list, counts);   // no seed: try the main diagonal
 }
 
 // reverse pass work lists: score 0 has no reverse pass (ssw.c:903 is reached with an empty range). The forward score S

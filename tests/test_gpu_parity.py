@@ -33,16 +33,18 @@ def check_overlaps(got, gpool, want, wpool, fields=FIELDS, cigars=True):
         assert not bad, (len(bad), [(a[i], b[i]) for i in bad[:3]])
 
 
-def run_pipeline(pkg, gb, go, rb, ro, P, prefilter=True, band=3):
+def run_pipeline(pkg, gb, go, rb, ro, P, prefilter=True, band=3, sort_bits=0):
     with pkg.Aligner(match=P.match, mismatch=P.mismatch, gap_open=P.gap_open, gap_extend=P.gap_extend,
                      score_threshold=P.score_threshold, report_cigar=bool(P.report_cigar)) as al:
         al.set_prefilter(prefilter)
         al.set_sw_band(band)
+        al.set_kmer_sort_bits(sort_bits)
         al.load_genomes(gb, go)
         res = al.align_batch(rb, ro)
         taps = dict(genome_kmers=al.genome_kmers(), read_kmers=al.read_kmers(), raw_seeds=al.raw_seeds(), seeds=al.seeds())
         pairs = al.pair_batch()
         tm = al.timings()
+        tm["kmer_sort_bits"] = al.kmer_sort_bits()
     return res, taps, pairs, tm
 
 
@@ -56,7 +58,9 @@ def check_pipeline(pkg, gb, go, rb, ro, P, want=None):
 
 
 def check_pipeline_mode(pkg, gb, go, rb, ro, P, want, prefilter, band):
-    res, taps, pairs, tm = run_pipeline(pkg, gb, go, rb, ro, P, prefilter, band)
+    # without the prefilter the read list is also sorted in full (KMer.h:388-398); with it, on the leading bits only
+    res, taps, pairs, tm = run_pipeline(pkg, gb, go, rb, ro, P, prefilter, band, sort_bits=0 if prefilter else 64)
+    assert tm["kmer_sort_bits"] == (64 if not prefilter else tm["kmer_sort_bits"]) and 16 <= tm["kmer_sort_bits"] <= 64
     if not band:
         assert tm["n_sw_band"] == 0 and tm["n_sw_band_rev"] == 0
     # K1/K2: genome list in the reference's order (kmer asc, id_flags desc); read list sorted by k-mer
@@ -65,7 +69,8 @@ def check_pipeline_mode(pkg, gb, go, rb, ro, P, want, prefilter, band):
     assert np.array_equal(taps["genome_kmers"]["id_flags"], wg["id_flags"])
     assert np.array_equal(canon(taps["genome_kmers"]), canon(wg))
     rk = taps["read_kmers"]
-    assert (np.diff(rk["kmer"].astype(np.uint64)) >= 0).all() if len(rk) > 1 else True
+    top = rk["kmer"].astype(np.uint64) >> np.uint64(64 - tm["kmer_sort_bits"])
+    assert (top[1:] >= top[:-1]).all()
     wr = want["read_kmers"]
     if not prefilter:
         assert np.array_equal(canon(rk), canon(wr))           # same multiset as KMer.h:160-181 produces
@@ -300,3 +305,27 @@ def test_direct_tiers_match_full_matrix_at_volume(pkg):
         narrow = tb["n_sw_tier8"] + tb["n_sw_tier16"]
         assert narrow >= min_narrow * tb["n_seeds"], (narrow, tb["n_seeds"])
         assert tb["sw_cells_computed"] < ta["sw_cells_computed"]
+
+
+def test_align_pair_batch_equals_two_calls(pkg):
+    """kslam_align_pair_batch (the batch-loop body in one call, no copy of the unsorted vector) returns exactly what
+    kslam_align_batch + kslam_pair_batch return; two contexts on one GPU driven from two threads do not disturb each other."""
+    import threading
+    gb, go, rb, ro = pkg.synth.adversarial_set(seed=51, n_genomes=8, glen=8000, n_pairs=700)
+    with pkg.Aligner(report_cigar=True) as al:
+        al.load_genomes(gb, go)
+        al.align_batch(rb, ro)
+        want = al.pair_batch()
+    got = [None, None]
+
+    def run(k):
+        with pkg.Aligner(report_cigar=True) as a2:
+            a2.load_genomes(gb, go)
+            for _ in range(3):
+                got[k] = a2.align_pair_batch(rb, ro)
+    th = [threading.Thread(target=run, args=(k,)) for k in range(2)]
+    [t.start() for t in th]; [t.join() for t in th]
+    for g in got:
+        assert np.array_equal(g.sorted_overlaps, want.sorted_overlaps)
+        assert np.array_equal(g.pairs, want.pairs)
+        assert T.cigars_of(g.sorted_overlaps, g.cigar_pool) == T.cigars_of(want.sorted_overlaps, want.cigar_pool)
