@@ -154,6 +154,59 @@ def cpu_reference_sample(pkg, gb, go, n_pairs_sample, report_cigar, threshold):
     return n_pairs_sample / dt * 60 / 1e6, dt, cores, kind
 
 
+def sw_pairs_chunked(pkg, n, read_len, window_len, seed):
+    parts = [pkg.synth.sw_pairs(min(500_000, n - i), read_len, window_len, seed=seed + i // 500_000) for i in range(0, n, 500_000)]
+    q = np.concatenate([p[0] for p in parts]); r = np.concatenate([p[2] for p in parts])
+    return (q, np.arange(n + 1, dtype=np.uint64) * np.uint64(read_len), r, np.arange(n + 1, dtype=np.uint64) * np.uint64(window_len))
+
+
+def run_config3(args, pkg):
+    """Config 3, the Smith-Waterman microbenchmark: (read 150, window) pairs through the batched Aligner::Align entry
+    point (kslam_ssw_batch), both shapes SURVEY.md §8d names (the live reference window of 150 and the 300-wide one),
+    with and without CIGAR, next to ssw.c (oracle/_ref) on the host cores. GCUPS = read x window cells / all SW time."""
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the matching path has no CPU fallback")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _lib as T
+    n = args.pairs or 2_000_000
+    shapes = []
+    for window in (150, 300):
+        q, qo, r, ro = sw_pairs_chunked(pkg, n, 150, window, seed=300 + window)
+        row = {"read_len": 150, "window_len": window, "pairs": n}
+        for cigar in (False, True):
+            with pkg.Aligner(report_cigar=cigar) as al:
+                al.ssw_upload(q, qo, r, ro)
+                for _ in range(args.warmup):
+                    al.ssw_resident()
+                ms = []
+                for _ in range(args.steps):
+                    al.ssw_resident(); ms.append(al.timings()["ms_total"])
+                tm = al.timings()
+                if not cigar:
+                    int_peak = al.measure_int_peak()
+            t = float(np.mean(ms)) / 1e3
+            key = "cigar" if cigar else "score_only"
+            row[key] = {"gcups": 150.0 * window * n / t / 1e9, "ms": t * 1e3, "M_pairs_per_min": n / t * 60 / 1e6,
+                        "tiers": {k: tm[k] for k in ("n_sw_tier8", "n_sw_tier16", "n_sw_tier32", "n_sw_tier64", "n_sw_sweep32", "n_sw_fast", "n_sw_slow")},
+                        "int_pipe_frac": 3.5 * tm["sw_cells_computed"] / ((tm["ms_sw_forward"] + tm["ms_sw_reverse"]) / 1e3) / int_peak}
+        if not args.no_cpu_baseline and T.have_ref():
+            cs = args.cpu_sample or 200_000
+            P = T.default_params(report_cigar=1)
+            t0 = time.time(); T.ref_ssw_batch(q[:cs * 150], qo[:cs + 1], r[:cs * window], ro[:cs + 1], P, cigar_cap=32, threads=os.cpu_count() or 1)
+            dt = time.time() - t0
+            row["ssw_c_reference"] = {"gcups": 150.0 * window * cs / dt / 1e9, "cores": os.cpu_count() or 1, "sample_pairs": cs, "with_cigar": True}
+        shapes.append(row)
+        log(f"[bench/config3] {row}")
+    live = shapes[0]["score_only"]
+    emit({"metric": METRIC, "value": live["M_pairs_per_min"], "unit": "M read/window pairs per min (SW microbench, 150 x 150, score + coordinates)",
+          "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": live["ms"], "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "int16x2", "data": "synthetic",
+          "config": {"workload": f"config3 (SW microbench): {n} read/window pairs per shape, scoring 2/3/5/2; mix 70 % 1 % subs, 20 % one 1-5 bp indel, "
+                                 "5 % unrelated, 5 % with N runs", "l2": "inputs larger than L2"},
+          "sw_gcups": live["gcups"], "shapes": shapes, "int_peak_thread_ops_per_s": int_peak})
+
+
 def run_reference_arm(args, pkg):
     """--impl reference: the reference's CPU path on this box's host cores, same config/metric/unit."""
     rank = int(os.environ.get("RANK", "0"))
@@ -164,7 +217,7 @@ def run_reference_arm(args, pkg):
     gb, go, _, _, desc = make_workload(pkg, args.workload, 1000)
     vals = []
     for i in range(args.warmup + args.steps):
-        v, dt, cores, kind = cpu_reference_sample(pkg, gb, go, sample, False, 0)
+        v, dt, cores, kind = cpu_reference_sample(pkg, gb, go, sample, args.workload == "config1", 0)
         log(f"[bench/reference] step {i}: {sample} pairs in {dt:.2f}s -> {v:.3f} M pairs/min on {cores} threads")
         if i >= args.warmup:
             vals.append((v, dt))
@@ -190,7 +243,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kslam", choices=["kslam", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("KSLAM_BENCH_WORKLOAD", "config2"), choices=["config1", "config2", "config4"])
+    ap.add_argument("--workload", default=os.environ.get("KSLAM_BENCH_WORKLOAD", "config2"), choices=["config1", "config2", "config3", "config4"])
     ap.add_argument("--pairs", type=int, default=0, help="read pairs per batch per GPU (default: the config's)")
     ap.add_argument("--ref-sample", type=int, default=0, help="pairs per step for the CPU reference arm (0 = per workload)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs for the cpu_baseline leg (rank 0, N=1; 0 = per workload)")
@@ -198,6 +251,8 @@ def main():
     args = ap.parse_args()
 
     pkg = ge.load_pkg()
+    if args.workload == "config3":
+        return run_config3(args, pkg)
     if args.impl == "reference":
         return run_reference_arm(args, pkg)
 
@@ -221,7 +276,9 @@ def main():
     # pinned host staging for the e2e leg (the C ABI takes plain host pointers)
     rb_pin = torch.from_numpy(rb).pin_memory()
     rb_host = rb_pin.numpy()
-    al = pkg.Aligner(report_cigar=False, device=local)
+    # config 1 is the --just-align / --sam-file run: reportCigar is on there (SLAM.h:169); configs 2 and 4 write XML only
+    want_cigar = args.workload == "config1"
+    al = pkg.Aligner(report_cigar=want_cigar, device=local)
     al.set_debug_taps(False)
     partitioned = args.workload == "config4"
     t0 = time.time()
@@ -286,7 +343,7 @@ def main():
     depth = 1 if partitioned else 2
     ctxs = [al]
     if depth == 2:
-        al2 = pkg.Aligner(report_cigar=False, device=local)
+        al2 = pkg.Aligner(report_cigar=want_cigar, device=local)
         al2.set_debug_taps(False)
         al2.load_genomes(gb, go)
         ctxs.append(al2)
@@ -338,7 +395,7 @@ def main():
         peak, peak_src = measured_peaks()
         ms = {k: v / args.steps for k, v in stage.items()}
         n_rk, n_raw = tm["n_sorted_kmers"], tm["n_raw_seeds"]     # records actually sorted (after the prefilter)
-        passes_kmer = 8
+        passes_kmer = max(1, al.kmer_sort_bits() // 8)     # 8-bit digits over the leading bits the join needs
         sort_s = ms["ms_sort"] / 1e3
         # dominant HBM-bound kernel: k_rs_onesweep of the read k-mer sort. algorithmic bytes per launch = 32 B x records
         # (one read + one write of every 16 B record per pass); duration = sort time / passes (histogram charged too)
@@ -350,9 +407,13 @@ def main():
         gcups_kernel = (tm["sw_cells_forward"] + tm["sw_cells_reverse"]) / ((ms["ms_sw_forward"] + ms["ms_sw_reverse"]) / 1e3) / 1e9 \
             if ms["ms_sw_forward"] + ms["ms_sw_reverse"] > 0 else 0.0
         hbm_roof = {"bound": "hbm", "kernel": "k_rs_onesweep (read k-mer LSD pass)", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": achieved / peak,
+                    # ncu --set full of this kernel on 64 M records (profiles/r1_ncu_summaries.txt, prof_sort_r1b): dram read
+                    # 1.037 GB + write 1.015 GB per launch = 32.07 B per record, i.e. no re-reads beyond the algorithmic bytes
+                    "traffic": 32.07 * n_rk, "traffic_source": "ncu dram__bytes_read+write per record (64 M-record capture) x records per launch",
+                    "peak_source": peak_src,
                     "share_of_step": ms["ms_sort"] / (t_res / args.steps * 1e3),
-                    "note": "algorithmic 32 B/record/pass; duration = (sort stage incl. histogram)/8 passes, CUDA events on the ctx stream"}
+                    "note": f"algorithmic 32 B/record/pass; duration = (sort stage incl. histogram)/{passes_kmer} passes, CUDA events on the ctx stream"}
         # SW sweeps (k_sw_band / k_sw_fast): integer-pipe bound. 7 ALU thread-ops (1 PRMT + 6 s16x2 DPX) per two cells;
         # numerator = cells the sweep kernels actually computed (band cells, not matrix cells), denominator = the
         # issue rate of VIADDMNMX.S16x2 measured on this GPU right now (kslam_measure_int_peak).
@@ -371,7 +432,7 @@ def main():
                "dtype": "int16x2 (SW) / u64 (k-mers)", "data": "synthetic",
                "config": {"workload": desc, "batch_pairs_per_gpu": pairs, "sharding": (f"genome k-mer list range-partitioned over {world} ranks + read pairs per rank; all-to-all of k-mer records "
                                        f"and of raw matches (NCCL)" if partitioned else f"read pairs, {world} ranks, no collective"),
-                          "l2": "inputs larger than L2 (3.8 GB+ of k-mer records per step)", "report_cigar": False},
+                          "l2": "inputs larger than L2 (3.8 GB+ of k-mer records per step)", "report_cigar": want_cigar},
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "call": "kslam_align_pair_batch (host buffers in, pair-sorted overlaps + pairs back on the host)",
                        "contexts_per_gpu": depth},
@@ -390,7 +451,7 @@ def main():
                                "partition": {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in al.partition().items() if k != "splitters"}}
         if world == 1 and not args.no_cpu_baseline:
             cs = args.cpu_sample or CPU_SAMPLE[args.workload]
-            v, dt, cores, kind = cpu_reference_sample(pkg, gb, go, cs, False, 0)
+            v, dt, cores, kind = cpu_reference_sample(pkg, gb, go, cs, want_cigar, 0)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                    "sample": f"{cs} pairs of the same workload in {dt:.1f}s (alignToDatabase+screen+getPairedOverlaps, genome k-mers re-extracted and re-sorted per batch as the reference does)"}
         emit(out)

@@ -86,7 +86,7 @@ void kslam_destroy(kslam_ctx *c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   c->genomes.release(); c->reads.release(); c->swq.release(); c->swr.release();
   DevBuf *bufs[] = {&c->g_keys, &c->g_vals, &c->recA, &c->recB, &c->sort_hist, &c->scan_tmp, &c->counters,
-                    &c->raw_seeds, &c->seedA, &c->seedB, &c->seed_keep, &c->seeds, &c->ov, &c->cig, &c->pair_keys,
+                    &c->raw_seeds, &c->seedA, &c->seedB, &c->seed_keep, &c->seeds, &c->ov, &c->cig, &c->cig_dense, &c->pair_keys,
                     &c->pair_keys2, &c->ov_sorted, &c->cig_sorted, &c->pair_cnt, &c->pairs, &c->bitmap, &c->d_bounds,
                     &c->part_send, &c->part_recv, &c->part_tmp, &c->part_m, &c->part_msend, &c->part_mrecv};
   for (DevBuf *b : bufs) b->release();
@@ -203,21 +203,20 @@ int kslam_load_genomes(kslam_ctx *c, uint64_t n, const char *bases, const uint64
 
 static void fetch_alignments(kslam_ctx *c, kslam_alignments *out) {
   const uint64_t n = c->n_seeds;
-  const uint32_t cap = c->prm.max_cigar_ops;
   cudaEvent_t e0 = tm_mark(c);
   c->h_ov.reserve((size_t)n * sizeof(kslam_overlap) + 64);
   if (n) CUDA_TRY(cudaMemcpyAsync(c->h_ov.p, c->ov.p, (size_t)n * sizeof(kslam_overlap), cudaMemcpyDeviceToHost, c->stream));
   const bool with_cig = c->prm.report_cigar && n;
   if (with_cig) {
-    c->h_cig.reserve((size_t)n * cap * 4 + 64);
-    CUDA_TRY(cudaMemcpyAsync(c->h_cig.p, c->cig.p, (size_t)n * cap * 4, cudaMemcpyDeviceToHost, c->stream));
+    c->h_cig.reserve((size_t)c->n_cig_words * 4 + 64);
+    if (c->n_cig_words) CUDA_TRY(cudaMemcpyAsync(c->h_cig.p, c->cig_dense.p, (size_t)c->n_cig_words * 4, cudaMemcpyDeviceToHost, c->stream));
   }
   cudaEvent_t e1 = tm_mark(c);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->tm.ms_d2h = tm_ms(e0, e1);
   if (out) {
     out->n_overlaps = n; out->overlaps = c->h_ov.as<kslam_overlap>();
-    out->n_cigar_words = with_cig ? n * cap : 0; out->cigar_pool = with_cig ? c->h_cig.as<uint32_t>() : nullptr;
+    out->n_cigar_words = with_cig ? c->n_cig_words : 0; out->cigar_pool = with_cig ? c->h_cig.as<uint32_t>() : nullptr;
   }
 }
 
@@ -319,16 +318,15 @@ int kslam_pair_batch(kslam_ctx *c, int fetch, kslam_pairs *out) {
   cudaEvent_t e0 = tm_mark(c);
   pair_overlaps(c);
   cudaEvent_t e1 = tm_mark(c);
-  const uint32_t cap = c->prm.max_cigar_ops;
-  const bool with_cig = c->prm.report_cigar && c->n_sorted && c->cig_sorted.p;
+  const bool with_cig = c->prm.report_cigar && c->n_sorted && c->cig_dense.p;
   if (fetch) {
     c->h_ov_sorted.reserve((size_t)c->n_sorted * sizeof(kslam_overlap) + 64);
     c->h_pairs.reserve((size_t)c->n_pairs * sizeof(kslam_pair) + 64);
     if (c->n_sorted) CUDA_TRY(cudaMemcpyAsync(c->h_ov_sorted.p, c->ov_sorted.p, (size_t)c->n_sorted * sizeof(kslam_overlap), cudaMemcpyDeviceToHost, c->stream));
     if (c->n_pairs) CUDA_TRY(cudaMemcpyAsync(c->h_pairs.p, c->pairs.p, (size_t)c->n_pairs * sizeof(kslam_pair), cudaMemcpyDeviceToHost, c->stream));
     if (with_cig) {
-      c->h_cig_sorted.reserve((size_t)c->n_sorted * cap * 4 + 64);
-      CUDA_TRY(cudaMemcpyAsync(c->h_cig_sorted.p, c->cig_sorted.p, (size_t)c->n_sorted * cap * 4, cudaMemcpyDeviceToHost, c->stream));
+      c->h_cig_sorted.reserve((size_t)c->n_cig_words * 4 + 64);
+      if (c->n_cig_words) CUDA_TRY(cudaMemcpyAsync(c->h_cig_sorted.p, c->cig_dense.p, (size_t)c->n_cig_words * 4, cudaMemcpyDeviceToHost, c->stream));
     }
   }
   CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -338,7 +336,7 @@ int kslam_pair_batch(kslam_ctx *c, int fetch, kslam_pairs *out) {
     out->n_sorted = c->n_sorted; out->n_pairs = c->n_pairs;
     out->sorted_overlaps = fetch ? c->h_ov_sorted.as<kslam_overlap>() : nullptr;
     out->pairs = fetch ? c->h_pairs.as<kslam_pair>() : nullptr;
-    out->n_cigar_words = (fetch && with_cig) ? c->n_sorted * cap : 0;
+    out->n_cigar_words = (fetch && with_cig) ? c->n_cig_words : 0;
     out->cigar_pool = (fetch && with_cig) ? c->h_cig_sorted.as<uint32_t>() : nullptr;
   }
   return KSLAM_OK;

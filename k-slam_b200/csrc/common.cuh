@@ -118,7 +118,9 @@ struct kslam_ctx {
   uint64_t n_raw = 0, n_seeds = 0;
 
   DevBuf ov;                // kslam_overlap[n_seeds]
-  DevBuf cig;               // u32[n_seeds * max_cigar_ops]
+  DevBuf cig;               // u32[n_seeds * max_cigar_ops]: traceback scratch, fixed stride
+  DevBuf cig_dense;         // u32[n_cig_words]: the CIGAR pool that leaves the GPU (dense; cigar_off indexes it)
+  uint64_t n_cig_words = 0;
   SwWorkspace *sw = nullptr;
   HostBuf h_ov, h_cig;
 

@@ -26,17 +26,10 @@ k_pair_keys(const kslam_overlap *__restrict__ ov, uint32_t n, uint32_t mid, uint
 
 __global__ void __launch_bounds__(256)
 k_pair_gather(const Rec16 *__restrict__ sorted, uint32_t n_sorted, const kslam_overlap *__restrict__ ov,
-              const uint32_t *__restrict__ cig, uint32_t cap, kslam_overlap *__restrict__ ov_out,
-              uint32_t *__restrict__ cig_out) {
+              kslam_overlap *__restrict__ ov_out) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_sorted) return;
-  const uint32_t src = (uint32_t)sorted[k].val;
-  kslam_overlap o = ov[src];
-  if (cig && cig_out) {
-    for (uint32_t j = 0; j < o.cigar_len; j++) cig_out[(size_t)k * cap + j] = cig[(size_t)src * cap + j];
-    o.cigar_off = k * cap;
-  }
-  ov_out[k] = o;
+  ov_out[k] = ov[(uint32_t)sorted[k].val];      // cigar_off keeps pointing into the batch's dense CIGAR pool
 }
 
 // getPairsFromRead over the run starting at `first`; emits into out (or only counts when out == nullptr)
@@ -128,7 +121,6 @@ void pair_overlaps(kslam_ctx *c) {
   if (!n) return;
   const uint32_t mid = (uint32_t)(c->reads.n / 2);
   if (mid == 0) return;
-  const uint32_t cap = c->prm.max_cigar_ops;
   uint32_t *d_cnt = c->counters.as<uint32_t>() + 48;
   uint32_t *h_cnt = c->h_counters.as<uint32_t>() + 48;
   c->pair_keys.reserve((size_t)n * sizeof(Rec16) + 64);
@@ -148,11 +140,8 @@ void pair_overlaps(kslam_ctx *c) {
   c->n_sorted = ns;
   if (!ns) return;
   c->ov_sorted.reserve((size_t)ns * sizeof(kslam_overlap) + 64);
-  const bool with_cig = c->prm.report_cigar && c->cig.p;
-  if (with_cig) c->cig_sorted.reserve((size_t)ns * cap * 4 + 64);
   const unsigned nbs = (ns + 255) / 256;
-  k_pair_gather<<<nbs, 256, 0, st>>>(cur, ns, c->ov.as<kslam_overlap>(), with_cig ? c->cig.as<uint32_t>() : nullptr, cap,
-                                     c->ov_sorted.as<kslam_overlap>(), with_cig ? c->cig_sorted.as<uint32_t>() : nullptr);
+  k_pair_gather<<<nbs, 256, 0, st>>>(cur, ns, c->ov.as<kslam_overlap>(), c->ov_sorted.as<kslam_overlap>());
   c->pair_cnt.reserve((size_t)ns * 8 + 64);
   uint32_t *cnt = c->pair_cnt.as<uint32_t>(), *pos = cnt + ns;
   k_pair_count<<<nbs, 256, 0, st>>>(c->ov_sorted.as<kslam_overlap>(), ns, mid, c->reads.offs.as<uint64_t>(), cnt);

@@ -40,6 +40,7 @@ struct __align__(16) SwTask {
 };
 #define SWT_REV 1u
 #define SWT_BAND 2u   // shape allows the banded kernel (rows <= 160, no code-4 base in the window)
+#define SWT_CLEAN 4u  // no code-4 base in the window
 #define SWC_FAST8 0u
 #define SWC_SLOW 3u
 #define SWC_NONE 4u   // empty query or window: score 0, nothing to run
@@ -400,8 +401,35 @@ __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const S
   return l;
 }
 
+__device__ __forceinline__ int32_t diagonal_score_slow(const SwPlanes &pl, const SwTask &t, const SwScore &sc, int32_t ref0,
+                                                       int32_t read0, int32_t len);
+// 2-bit codes of the 32 window columns j = 32 qw + d0 + b (b = 0..31) in the orientation Align sees; windows without
+// code-4 bases only (the caller checks SWT_CLEAN)
+__device__ __forceinline__ uint64_t window_word_on_diagonal(const SwPlanes &pl, const SwTask &t, int32_t qw, int32_t d0) {
+  if (!(t.flags & SWT_REV)) return bits_at(pl.w_sbits, t.w_word, (int32_t)t.w_start + 32 * qw + d0);
+  const int32_t p0 = (int32_t)t.w_start + (int32_t)t.n - 1 - 32 * qw - d0 - 31;   // column 32qw + d0 + b <-> base p0 + 31 - b
+  return reverse_pairs(bits_at(pl.w_sbits, t.w_word, p0)) ^ pair_mask(~__brev(mask_at(pl.w_xmask, t.w_word, p0)));   // complement unless a/c/g/t/U/u
+}
+
 // Score of the gap-free alignment of read'[0..len) against ref'[0..len) (the sub-rectangle's main diagonal).
+// Word-parallel when the window has no code-4 base: XOR of the 2-bit planes, population counts.
 __device__ __forceinline__ int32_t diagonal_score(const SwPlanes &pl, const SwTask &t, const SwScore &sc, int32_t ref0,
+                                                  int32_t read0, int32_t len) {
+  if (!(t.flags & SWT_CLEAN)) return diagonal_score_slow(pl, t, sc, ref0, read0, len);
+  const int32_t d0 = ref0 - read0, i_lo = read0, i_hi = read0 + len;
+  int32_t matches = 0, mism = 0;
+  for (int32_t qw = i_lo >> 5; qw <= (i_hi - 1) >> 5; qw++) {
+    const uint64_t x = __ldg(&pl.q_sbits[t.q_word + qw]) ^ window_word_on_diagonal(pl, t, qw, d0);
+    const uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;
+    const int32_t b_lo = i_lo - 32 * qw > 0 ? i_lo - 32 * qw : 0, b_hi = i_hi - 32 * qw < 32 ? i_hi - 32 * qw : 32;
+    const uint32_t span = (b_hi - b_lo >= 32 ? 0xffffffffu : ((1u << (b_hi - b_lo)) - 1u) << b_lo);
+    const uint64_t live = pair_mask(span & ~__ldg(&pl.q_nmask[t.q_word + qw])) & 0x5555555555555555ull;   // code-4 query bases score 0
+    mism += __popcll(mm & live); matches += __popcll(~mm & live);
+  }
+  return sc.match * matches - sc.mismatch * mism;
+}
+
+__device__ __forceinline__ int32_t diagonal_score_slow(const SwPlanes &pl, const SwTask &t, const SwScore &sc, int32_t ref0,
                                                   int32_t read0, int32_t len) {
   int32_t d = 0;
   for (int32_t i = 0; i < len; i++) {
@@ -504,19 +532,11 @@ __device__ int32_t diag_lower_bound(const SwPlanes &pl, const SwTask &t, int32_t
   const int32_t m = (int32_t)t.m, n = (int32_t)t.n;
   const int32_t i_lo = d0 < 0 ? -d0 : 0, i_hi = (n - d0) < m ? (n - d0) : m;
   if (i_lo >= i_hi) return 0;
-  const bool rev = (t.flags & SWT_REV) != 0;
   int32_t run = 0, best = 0;
   for (int32_t qw = i_lo >> 5; qw <= (i_hi - 1) >> 5; qw++) {
     const uint64_t Q = __ldg(&pl.q_sbits[t.q_word + qw]);
     const uint32_t qn = __ldg(&pl.q_nmask[t.q_word + qw]);
-    uint64_t W;
-    if (!rev) W = bits_at(pl.w_sbits, t.w_word, (int32_t)t.w_start + 32 * qw + d0);
-    else {
-      const int32_t p0 = (int32_t)t.w_start + n - 1 - 32 * qw - d0 - 31;     // column 32qw + d0 + b <-> base p0 + 31 - b
-      uint64_t e = __brevll(bits_at(pl.w_sbits, t.w_word, p0));
-      e = ((e >> 1) & 0x5555555555555555ull) | ((e & 0x5555555555555555ull) << 1);
-      W = e ^ pair_mask(~__brev(mask_at(pl.w_xmask, t.w_word, p0)));         // complement unless a/c/g/t/U/u
-    }
+    const uint64_t W = window_word_on_diagonal(pl, t, qw, d0);
     const uint64_t x = Q ^ W;
     const uint64_t mm = (x | (x >> 1)) & 0x5555555555555555ull;              // bit 2b set: base b mismatches
     const int32_t b_lo = i_lo - 32 * qw > 0 ? i_lo - 32 * qw : 0, b_hi = i_hi - 32 * qw < 32 ? i_hi - 32 * qw : 32;
@@ -560,6 +580,14 @@ __device__ __forceinline__ uint32_t classify(uint32_t m, uint32_t n, const SwSco
                         sc.gap_open * 32 <= 30000 && sc.gap_extend * 32 <= 30000;
   if (score_ok && m <= 8 * SW_R && n <= SW_MAXCOLS) return SWC_FAST8;
   return SWC_SLOW;
+}
+
+// A band can only ever hold [-(m - a), n - a] (sw_band.cuh) when that interval's minimum width |n - m| + 1 (reached at
+// a = min(m, n)) fits the widest tier; wider shapes (e.g. a 150-base read in a 300-base window) go straight to the
+// full-matrix kernel instead of paying for a sweep that cannot prove anything.
+__device__ __forceinline__ bool band_shape_ok(uint32_t m, uint32_t n) {
+  const uint32_t d = m > n ? m - n : n - m;
+  return m <= SWB_MAXROWS && d + 1 <= SWB_MAXW;
 }
 
 // true when no base of the window [w_start, w_start + n) has SSW code 4
@@ -633,7 +661,8 @@ k_sw_prepare_seeds(const kslam_seed *__restrict__ seeds, uint32_t n, const uint6
   t.m = (uint32_t)qlen; t.n = (uint32_t)wlen; t.w_start = (uint32_t)start;
   const uint32_t cls = classify(t.m, t.n, sc);
   t.flags = (s.rev_comp ? SWT_REV : 0u) | (cls << 8);
-  if (use_band && cls == SWC_FAST8 && t.m <= SWB_MAXROWS && window_clean(g_nmask, t.w_word, t.w_start, t.n)) t.flags |= SWT_BAND;
+  if (cls != SWC_NONE && window_clean(g_nmask, t.w_word, t.w_start, t.n)) t.flags |= SWT_CLEAN;
+  if (use_band && cls == SWC_FAST8 && band_shape_ok(t.m, t.n) && (t.flags & SWT_CLEAN)) t.flags |= SWT_BAND;
   tasks[i] = t;
   // matrix diagonal of the seed's exact 32-mer match: forward seeds put read base i on genome base rel + i; reverse-
   // complement seeds put rc(read) base i there and Align sees the window reversed (SmithWaterman.h:205-208)
@@ -656,7 +685,8 @@ k_sw_prepare_pairs(uint32_t n, const uint64_t *__restrict__ q_offs, const uint64
   t.m = (uint32_t)(q_offs[i + 1] - q_offs[i]); t.n = (uint32_t)(r_offs[i + 1] - r_offs[i]); t.w_start = 0;
   const uint32_t cls = classify(t.m, t.n, sc);
   t.flags = cls << 8;
-  if (use_band && cls == SWC_FAST8 && t.m <= SWB_MAXROWS && window_clean(r_nmask, t.w_word, 0, t.n)) t.flags |= SWT_BAND;
+  if (cls != SWC_NONE && window_clean(r_nmask, t.w_word, 0, t.n)) t.flags |= SWT_CLEAN;
+  if (use_band && cls == SWC_FAST8 && band_shape_ok(t.m, t.n) && (t.flags & SWT_CLEAN)) t.flags |= SWT_BAND;
   tasks[i] = t;
   enlist(pl, t, i, cls, 0, false, use_band >= 3, use_band >= 2 ? 3u : 2u, sc, res, tier_f, full_keys, slow_list, counts);   // no seed: try the main diagonal
 }
@@ -961,6 +991,39 @@ static void sw_reset_timers(kslam_ctx *c) {
   c->tm.n_sw_tier8 = c->tm.n_sw_tier16 = c->tm.n_sw_tier32 = c->tm.n_sw_tier64 = c->tm.n_sw_sweep32 = 0; c->tm.sw_cells_computed = 0;
 }
 
+// ---- CIGAR pool compaction: the traceback writes alignment i's ops at the fixed stride i * cigar_cap; almost every
+// CIGAR is one or three ops, so the pool that leaves the GPU is the dense concatenation and cigar_off indexes into it
+__global__ void __launch_bounds__(256) k_cigar_lens(const kslam_overlap *__restrict__ ov, uint32_t n, uint32_t *__restrict__ lens) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) lens[i] = ov[i].cigar_len;
+}
+__global__ void __launch_bounds__(256) k_cigar_compact(kslam_overlap *__restrict__ ov, uint32_t n, const uint32_t *__restrict__ offs,
+                                                       const uint32_t *__restrict__ strided, uint32_t *__restrict__ dense) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t len = ov[i].cigar_len, src = ov[i].cigar_off, dst = offs[i];
+  for (uint32_t j = 0; j < len; j++) dense[dst + j] = strided[src + j];
+  ov[i].cigar_off = dst;
+}
+
+static void compact_cigars(kslam_ctx *c, uint32_t n) {
+  cudaStream_t st = c->stream;
+  c->n_cig_words = 0;
+  if (!n || !c->prm.report_cigar) return;
+  c->seed_keep.reserve((size_t)n * 8 + 64);                 // free again by now: lens | offsets
+  uint32_t *lens = c->seed_keep.as<uint32_t>(), *offs = lens + n;
+  unsigned long long *d_cnt = c->counters.as<unsigned long long>() + 3, *h_cnt = c->h_counters.as<unsigned long long>() + 3;
+  k_cigar_lens<<<(n + 255) / 256, 256, 0, st>>>(c->ov.as<kslam_overlap>(), n, lens);
+  exclusive_scan_u32(c, lens, offs, n, (uint64_t *)d_cnt);
+  CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  c->n_cig_words = h_cnt[0];
+  c->cig_dense.reserve((size_t)c->n_cig_words * 4 + 64);
+  k_cigar_compact<<<(n + 255) / 256, 256, 0, st>>>(c->ov.as<kslam_overlap>(), n, offs, c->cig.as<uint32_t>(), c->cig_dense.as<uint32_t>());
+  c->launches += 2;
+  CUDA_TRY(cudaGetLastError());
+}
+
 void sw_align_seeds(kslam_ctx *c) {
   const uint32_t n = (uint32_t)c->n_seeds;
   sw_reset_timers(c);
@@ -983,6 +1046,11 @@ void sw_align_seeds(kslam_ctx *c) {
   CUDA_TRY(cudaGetLastError());
   cudaEvent_t e1 = tm_mark(c);
   sw_run(c, n, pl, c->ov.as<kslam_overlap>(), c->prm.report_cigar ? c->cig.as<uint32_t>() : nullptr, 1);
+  cudaEvent_t e2 = tm_mark(c);
+  compact_cigars(c, n);
+  cudaEvent_t e3 = tm_mark(c);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  c->tm.ms_sw_traceback += tm_ms(e2, e3);
   c->tm.ms_sw_prepare = tm_ms(e0, e1);
 }
 

@@ -49,7 +49,7 @@ def merge_alignments(parts, ranges, n_pairs: int, cigar_cap: int = 0):
     Global order is (read, entry, rel) with all R1 reads before all R2 reads, so the R1 segments of every rank
     come first (rank order), then the R2 segments."""
     mid = n_pairs
-    segs_ov, segs_cg = [], []
+    segs_ov, segs_cg, base = [], [], 0
     for want_r2 in (False, True):
         for (ov, pool), (lo, hi) in zip(parts, ranges):
             cnt = hi - lo
@@ -57,16 +57,17 @@ def merge_alignments(parts, ranges, n_pairs: int, cigar_cap: int = 0):
             seg = ov[split:] if want_r2 else ov[:split]
             seg = seg.copy()
             seg["read"] = globalize_reads(seg["read"], lo, cnt, mid)
+            if len(pool) and len(seg):
+                # gather every CIGAR of the segment (cigar_off / cigar_len index the rank's pool, strided or dense)
+                lens = seg["cigar_len"].astype(np.int64)
+                starts = np.cumsum(lens) - lens
+                idx = np.repeat(seg["cigar_off"].astype(np.int64) - starts, lens) + np.arange(int(lens.sum()), dtype=np.int64)
+                segs_cg.append(pool[idx])
+                seg["cigar_off"] = (starts + base).astype(np.uint32)
+                base += int(lens.sum())
             segs_ov.append(seg)
-            if cigar_cap and len(pool):
-                a = split if want_r2 else 0
-                segs_cg.append(pool[a * cigar_cap:(a + len(seg)) * cigar_cap])
     ov = np.concatenate(segs_ov) if segs_ov else np.zeros(0, dtype=parts[0][0].dtype)
-    if cigar_cap and segs_cg:
-        pool = np.concatenate(segs_cg)
-        ov["cigar_off"] = np.arange(len(ov), dtype=np.uint32) * np.uint32(cigar_cap)
-    else:
-        pool = np.zeros(0, dtype=np.uint32)
+    pool = np.concatenate(segs_cg) if segs_cg else np.zeros(0, dtype=np.uint32)
     return ov, pool
 
 
