@@ -164,6 +164,27 @@ int kslam_part_match_buffer(kslam_ctx *ctx, uint64_t n_matches, void **dev_ptr);
 int kslam_part_finish(kslam_ctx *ctx, uint64_t n_matches, uint32_t read_id_base, int fetch_results,
                       kslam_alignments *out /* may be NULL */);
 
+/* ---- FASTQ ingest (host side) ------------------------------------------------------------------
+ * Chunk-parallel restatement of the reference's reader: getSequencesFromFASTQFile / getPairedSequencesFromFASTQFiles
+ * (FASTQsequence.h:110-165) over safeGetline (sequenceTools.h:45-73: "\n", "\r\n" and lone "\r" end a line) with the
+ * read-id rule of FASTQsequence.h:61-71 (drop '@', cut at the first space, then at the first '/'). Records are four
+ * lines, never validated, exactly like the reference. One call returns the next max_reads records of R1 followed by
+ * the next max_reads records of R2 (R1 block then R2 block, the layout kslam_align_batch expects;
+ * --num-reads-at-once, SLAM.h:194-208); n_reads == 0 at end of input. Buffers are owned by the reader, valid until the
+ * next call, page-locked when a CUDA device is present. KSLAM_ERR_STATE = the reference's "mismatch in R1 and R2 size". */
+typedef struct kslam_fastq kslam_fastq;
+typedef struct {
+  uint64_t n_reads, n_r1;          /* reads in this batch; how many of them came from R1 */
+  const char *bases; const uint64_t *offs;         /* read i = bases[offs[i] .. offs[i+1]) */
+  const char *quals; const uint64_t *qual_offs;    /* quality line i, stored as is */
+  const char *ids; const uint64_t *id_offs;        /* sequenceIdentifier i */
+} kslam_read_batch;
+int kslam_fastq_open(const char *r1_path, const char *r2_path /* NULL: single-end */, uint32_t threads /* 0: all cores */,
+                     kslam_fastq **out);
+int kslam_fastq_next(kslam_fastq *reader, uint64_t max_reads, kslam_read_batch *out);
+const char *kslam_fastq_error(const kslam_fastq *reader);
+void kslam_fastq_close(kslam_fastq *reader);
+
 /* Stage taps for parity tests (results of the last batch; copy to caller buffers; pass NULL to query
  * the count). Returns the count or a negative error. */
 int64_t kslam_get_genome_kmers(kslam_ctx *ctx, kslam_kmer *out, uint64_t cap);      /* sorted, resident */

@@ -76,6 +76,11 @@ class Timings(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "_pad"}
 
 
+class _ReadBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_uint64), ("n_r1", C.c_uint64), ("bases", C.c_void_p), ("offs", C.c_void_p),
+                ("quals", C.c_void_p), ("qual_offs", C.c_void_p), ("ids", C.c_void_p), ("id_offs", C.c_void_p)]
+
+
 def declared_symbols():
     """Every function the public header declares (used by the CPU-tier symbol test)."""
     text = open(HEADER).read()
@@ -125,6 +130,12 @@ def lib():
     L.kslam_set_prefilter.argtypes = [vp, i32]
     L.kslam_set_sw_band.argtypes = [vp, i32]
     u32 = C.c_uint32
+    L.kslam_fastq_open.argtypes = [C.c_char_p, C.c_char_p, u32, C.POINTER(vp)]
+    L.kslam_fastq_next.argtypes = [vp, u64, C.POINTER(_ReadBatch)]
+    L.kslam_fastq_error.argtypes = [vp]
+    L.kslam_fastq_error.restype = C.c_char_p
+    L.kslam_fastq_close.argtypes = [vp]
+    L.kslam_fastq_close.restype = None
     L.kslam_set_kmer_sort_bits.argtypes = [vp, u32]
     L.kslam_get_kmer_sort_bits.argtypes = [vp]
     L.kslam_load_genomes_part.argtypes = [vp, u64, vp, vp, u32, u32]
@@ -381,3 +392,61 @@ class Aligner:
 
     def set_debug_taps(self, keep: bool):
         self._check(self.L.kslam_set_debug_taps(self.h, int(keep)), "kslam_set_debug_taps")
+
+
+@dataclass
+class ReadBatch:
+    """One batch of the FASTQ reader: R1 block then R2 block, the layout Aligner.align_batch takes."""
+    n_r1: int
+    bases: np.ndarray
+    offs: np.ndarray
+    quals: np.ndarray
+    qual_offs: np.ndarray
+    ids: np.ndarray
+    id_offs: np.ndarray
+
+    def __len__(self):
+        return len(self.offs) - 1
+
+    def records(self):
+        b, q, i = self.bases.tobytes(), self.quals.tobytes(), self.ids.tobytes()
+        return [(i[int(self.id_offs[k]):int(self.id_offs[k + 1])], b[int(self.offs[k]):int(self.offs[k + 1])],
+                 q[int(self.qual_offs[k]):int(self.qual_offs[k + 1])]) for k in range(len(self))]
+
+
+class FastqReader:
+    """kslam_fastq_*: chunk-parallel FASTQ ingest with the reference reader's exact semantics (FASTQsequence.h:110-165)."""
+
+    def __init__(self, r1, r2=None, threads=0):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.kslam_fastq_open(os.fsencode(r1), os.fsencode(r2) if r2 else None, threads, C.byref(h))
+        if rc != 0:
+            raise KslamError(f"kslam_fastq_open failed ({rc}): {self.L.kslam_last_error(None).decode()}")
+        self.h = h
+
+    def next(self, max_reads, copy=True):
+        """Next batch (None at end of input). Raises KslamError on the reference's R1/R2 size mismatch."""
+        out = _ReadBatch()
+        rc = self.L.kslam_fastq_next(self.h, max_reads, C.byref(out))
+        if rc != 0:
+            raise KslamError(f"kslam_fastq_next failed ({rc}): {self.L.kslam_fastq_error(self.h).decode()}")
+        n = out.n_reads
+        if n == 0:
+            return None
+        offs = _view(out.offs, n + 1, np.dtype("<u8")); qo = _view(out.qual_offs, n + 1, np.dtype("<u8"))
+        io = _view(out.id_offs, n + 1, np.dtype("<u8"))
+        f = (lambda a: a.copy()) if copy else (lambda a: a)
+        return ReadBatch(int(out.n_r1), f(_view(out.bases, int(offs[-1]), np.dtype("u1"))), f(offs),
+                         f(_view(out.quals, int(qo[-1]), np.dtype("u1"))), f(qo), f(_view(out.ids, int(io[-1]), np.dtype("u1"))), f(io))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.kslam_fastq_close(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -241,4 +241,38 @@ uint64_t kref_ssw_batch(uint64_t n, const char *q, const uint64_t *qoffs, const 
   return n;
 }
 
+// ---- the reference's own FASTQ reader (FASTQsequence.h:110-165) over real files, batch by batch ------------------
+// Streams stay open across calls like the ifstreams of the batch loop (SLAM.h:194-208). Returns the number of reads
+// of the batch, or (uint64_t)-1 when the reference throws ("mismatch in R1 and R2 size").
+struct KrefFastq { std::ifstream r1, r2; bool paired; std::vector<MetagenomicFASTQSequence> reads; };
+void *kref_fastq_open(const char *r1, const char *r2) {
+  KrefFastq *f = new KrefFastq();
+  f->r1.open(r1); f->paired = r2 != nullptr;
+  if (f->paired) f->r2.open(r2);
+  return f;
+}
+uint64_t kref_fastq_next(void *h, unsigned max_reads) {
+  KrefFastq *f = (KrefFastq *)h;
+  f->reads.clear();
+  try {
+    if (f->paired) getPairedSequencesFromFASTQFiles(f->r1, f->r2, f->reads, max_reads);
+    else getSequencesFromFASTQFile(f->r1, f->reads, max_reads);
+  } catch (const std::runtime_error &) { return (uint64_t)-1; }
+  return f->reads.size();
+}
+// which: 0 = bases, 1 = quality, 2 = sequenceIdentifier. offs gets n+1 entries; buf may be NULL to size it.
+uint64_t kref_fastq_get(void *h, int which, char *buf, uint64_t *offs) {
+  KrefFastq *f = (KrefFastq *)h;
+  uint64_t pos = 0;
+  for (size_t i = 0; i < f->reads.size(); i++) {
+    const std::string &s = which == 0 ? f->reads[i].bases : (which == 1 ? f->reads[i].quality : f->reads[i].sequenceIdentifier);
+    if (offs) offs[i] = pos;
+    if (buf) memcpy(buf + pos, s.data(), s.size());
+    pos += s.size();
+  }
+  if (offs) offs[f->reads.size()] = pos;
+  return pos;
+}
+void kref_fastq_close(void *h) { delete (KrefFastq *)h; }
+
 }  // extern "C"

@@ -117,6 +117,13 @@ def ref():
         L.kref_get_overlaps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.kref_ssw_batch.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
+        L.kref_fastq_open.restype = C.c_void_p
+        L.kref_fastq_open.argtypes = [C.c_char_p, C.c_char_p]
+        L.kref_fastq_next.restype = C.c_uint64
+        L.kref_fastq_next.argtypes = [C.c_void_p, C.c_uint]
+        L.kref_fastq_get.restype = C.c_uint64
+        L.kref_fastq_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.kref_fastq_close.argtypes = [C.c_void_p]
         cwd = os.getcwd()
         scratch = tempfile.mkdtemp(prefix="kref_")
         os.chdir(scratch)
@@ -282,6 +289,32 @@ def ref_ssw_batch(q, qoffs, r, roffs, params, cigar_cap=64, threads=0):
     L.kref_ssw_batch(n, _p(q), _p(qoffs), _p(r), _p(roffs), params.report_cigar, params.score_threshold,
                      _p(out), _p(pool), cigar_cap, threads)
     return out, pool
+
+
+def ref_read_fastq(r1, r2, max_reads):
+    """The reference's own reader (FASTQsequence.h:110-165) over files, batch by batch. Yields per batch a list of
+    (id, bases, quality) byte strings, or the string "mismatch" when the reference throws."""
+    L = ref()
+    h = L.kref_fastq_open(r1.encode(), r2.encode() if r2 else None)
+    out = []
+    try:
+        while True:
+            n = L.kref_fastq_next(h, max_reads)
+            if n == 2**64 - 1:
+                out.append("mismatch"); break
+            if n == 0:
+                break
+            fields = []
+            for which in (2, 0, 1):
+                offs = np.zeros(n + 1, dtype=np.uint64)
+                size = L.kref_fastq_get(h, which, None, _p(offs))
+                buf = np.zeros(max(1, size), dtype=np.uint8)
+                L.kref_fastq_get(h, which, _p(buf), _p(offs))
+                fields.append([bytes(buf[int(offs[i]):int(offs[i + 1])]) for i in range(n)])
+            out.append(list(zip(*fields)))
+    finally:
+        L.kref_fastq_close(h)
+    return out
 
 
 def load_pkg():

@@ -47,7 +47,25 @@ def ssw_fixture(name, q, qo, r, ro, params):
     print(name, len(a), "alignments; score range", a["sw_score"].min(), a["sw_score"].max())
 
 
+def fastq_fixture(name):
+    """A small paired FASTQ (CRLF and LF mixed, tricky ids, '@' quality lines, no final newline) and what the
+    reference's own reader (FASTQsequence.h:110-165) returns for it in batches of 11."""
+    import tempfile
+    from test_fastq_ingest import fastq_bytes
+    r1 = fastq_bytes(40, 5, b"\n", final_newline=False); r2 = fastq_bytes(40, 6, b"\r\n")
+    d = tempfile.mkdtemp()
+    p1, p2 = os.path.join(d, "R1.fq"), os.path.join(d, "R2.fq")
+    open(p1, "wb").write(r1); open(p2, "wb").write(r2)
+    batches = T.ref_read_fastq(p1, p2, 11)
+    fields = [f for b in batches for rec in b for f in rec]
+    np.savez_compressed(os.path.join(HERE, name), r1=np.frombuffer(r1, np.uint8), r2=np.frombuffer(r2, np.uint8), max_reads=11,
+                        fields=np.frombuffer(b"".join(fields), np.uint8), field_lens=np.array([len(f) for f in fields], np.int64),
+                        batch_sizes=np.array([len(b) for b in batches], np.int64))
+
+
 def main():
+    sys.path.insert(0, os.path.dirname(HERE))
+    fastq_fixture("fastq_reader.npz")
     gb, go, rb, ro = synth.adversarial_set(seed=7, n_genomes=8, glen=6000, n_pairs=400)
     pipeline_fixture("pipeline_adversarial_cigar.npz", gb, go, rb, ro, T.default_params(report_cigar=1))
     pipeline_fixture("pipeline_adversarial_thr60.npz", gb, go, rb, ro,
