@@ -111,11 +111,19 @@ static uint64_t index_lines(MappedFile &mf, uint64_t max_reads, uint32_t threads
   std::vector<uint64_t> cnt(threads + 1);
   size_t end = begin;
   uint64_t total = 0;
+  bool has_cr = false;      // Unix files (no '\r') take the vectorised path: count / find '\n' only
   for (;;) {
     end = begin + win;
+    std::vector<uint8_t> cr(threads + 1, 0);
+    parallel_for(threads, win, [&](uint32_t t, uint64_t lo, uint64_t hi) {
+      cr[t] = memchr(p + begin + lo, '\r', hi - lo) != nullptr;
+    });
+    has_cr = false;
+    for (uint8_t v : cr) has_cr |= v != 0;
     parallel_for(threads, win, [&](uint32_t t, uint64_t lo, uint64_t hi) {
       uint64_t c = 0;
-      for (size_t i = begin + lo; i < begin + hi; i++) c += line_end_at(p, i);
+      if (has_cr) for (size_t i = begin + lo; i < begin + hi; i++) c += line_end_at(p, i);
+      else { const char *q = p + begin; for (size_t i = lo; i < hi; i++) c += q[i] == '\n'; }
       cnt[t + 1] = c;
     });
     cnt[0] = 0; total = 0;
@@ -140,6 +148,11 @@ static uint64_t index_lines(MappedFile &mf, uint64_t max_reads, uint32_t threads
   const uint32_t nt = (threads > 1 && win >= 2) ? threads : 1;
   parallel_for(nt, win, [&](uint32_t t, uint64_t lo, uint64_t hi) {
     uint64_t k = cnt[t];
+    if (!has_cr) {
+      const char *q = p + begin + lo, *e = p + begin + hi;
+      while (k < n_lines && q < e && (q = (const char *)memchr(q, '\n', (size_t)(e - q))) != nullptr) { q++; k++; starts[k] = (uint64_t)(q - p); }
+      return;
+    }
     for (size_t i = begin + lo; i < begin + hi && k < n_lines; i++)   // k counts real line ends; virtual lines are patched below
       if (line_end_at(p, i)) {
         size_t nxt = i + 1;

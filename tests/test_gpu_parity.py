@@ -331,3 +331,31 @@ def test_align_pair_batch_equals_two_calls(pkg):
         assert np.array_equal(g.sorted_overlaps, want.sorted_overlaps)
         assert np.array_equal(g.pairs, want.pairs)
         assert T.cigars_of(g.sorted_overlaps, g.cigar_pool) == T.cigars_of(want.sorted_overlaps, want.cigar_pool)
+
+
+def test_fastq_to_alignments(pkg, tmp_path):
+    """FASTQ files -> kslam_fastq_next (pinned batch, R1 block then R2 block) -> kslam_align_pair_batch: same pairs as
+    handing the arrays over directly, batch by batch (--num-reads-at-once)."""
+    gb, go, rb, ro = pkg.synth.adversarial_set(seed=61, n_genomes=8, glen=8000, n_pairs=500)
+    n = len(ro) - 1; mid = n // 2
+    seqs = [bytes(rb[int(ro[i]):int(ro[i + 1])]) for i in range(n)]
+    for k, (lo, hi) in enumerate(((0, mid), (mid, n))):
+        with open(tmp_path / f"R{k + 1}.fq", "wb") as f:
+            for i in range(lo, hi):
+                f.write(b"@r%d/%d\n" % (i - lo, k + 1) + seqs[i] + b"\n+\n" + b"I" * len(seqs[i]) + b"\n")
+    with pkg.Aligner(report_cigar=True) as al, pkg.FastqReader(str(tmp_path / "R1.fq"), str(tmp_path / "R2.fq")) as rd:
+        al.load_genomes(gb, go)
+        done = 0
+        while True:
+            b = rd.next(200, copy=False)
+            if b is None:
+                break
+            cnt = b.n_r1
+            got = al.align_pair_batch(b.bases, b.offs)
+            sub = [seqs[done + i] for i in range(cnt)] + [seqs[mid + done + i] for i in range(cnt)]
+            sb, so = T.concat([np.frombuffer(s, np.uint8) for s in sub])
+            want = al.align_pair_batch(sb, so)
+            assert len(want.pairs) > 0 and np.array_equal(got.pairs, want.pairs)
+            assert np.array_equal(got.sorted_overlaps, want.sorted_overlaps)
+            done += cnt
+        assert done == mid
