@@ -185,6 +185,31 @@ int kslam_fastq_next(kslam_fastq *reader, uint64_t max_reads, kslam_read_batch *
 const char *kslam_fastq_error(const kslam_fastq *reader);
 void kslam_fastq_close(kslam_fastq *reader);
 
+/* ---- host stages after pairing, up to the SAM text (host code, no GPU involved) -----------
+ * kslam_sam_batch restates, literally and with the same std::sort calls so that ties fall as in the reference:
+ * getPerReadOverlaps, getMaxAllowedInsertSize, screenPairedAlignmentsByInsertSize(replace), screenPairedAlignmentsByScore,
+ * pseudoAssembly (+ second score screen) and writeSAMOutputPairs (PairedOverlap.h:314-576, SAM.h:101-517) — the rest
+ * of the reference's batch loop for a --sam-file run (SLAM.h:215-239) — on the output of kslam_pair_batch. Paired data
+ * only. Gene annotations (XG/XP/XR of GenBank databases) are not carried by this interface. */
+typedef struct {
+  uint32_t num_alignments;          /* --num-alignments (numSAMAlignments), default 10 */
+  uint8_t pseudo_assembly;          /* 1 unless --no-pseudo-assembly (Globals.h:36) */
+  uint8_t report_cigar;             /* reportCigar: cigar + MD columns */
+  uint8_t sam_xa;                   /* --sam-xa: primary line only */
+  uint8_t reserved;
+  double score_fraction_threshold;  /* --score-fraction-threshold, default 0.95 */
+} kslam_sam_params;
+typedef struct {
+  uint64_t n_entries;
+  const char *bases; const uint64_t *offs;             /* GenbankEntry::bases, as given to kslam_load_genomes */
+  const char *locus_tags; const uint64_t *locus_offs;  /* GenbankEntry::locusTag of entry e = locus_tags[locus_offs[e] .. locus_offs[e+1]) */
+  const uint32_t *taxonomy_ids;                        /* GenbankEntry::taxonomyID, may be NULL (all 0) */
+} kslam_sam_db;
+int kslam_sam_header(const kslam_sam_db *db, const char *command_line, char **text, uint64_t *len);   /* getHeader, SAM.h:518-531 */
+int kslam_sam_batch(const kslam_sam_params *params, const kslam_sam_db *db, const kslam_read_batch *reads,
+                    const kslam_pairs *pairs, char **text, uint64_t *len, uint32_t *max_insert_size /* may be NULL */);
+void kslam_sam_free(char *text);
+
 /* Stage taps for parity tests (results of the last batch; copy to caller buffers; pass NULL to query
  * the count). Returns the count or a negative error. */
 int64_t kslam_get_genome_kmers(kslam_ctx *ctx, kslam_kmer *out, uint64_t cap);      /* sorted, resident */

@@ -81,6 +81,16 @@ class _ReadBatch(C.Structure):
                 ("quals", C.c_void_p), ("qual_offs", C.c_void_p), ("ids", C.c_void_p), ("id_offs", C.c_void_p)]
 
 
+class SamParams(C.Structure):
+    _fields_ = [("num_alignments", C.c_uint32), ("pseudo_assembly", C.c_uint8), ("report_cigar", C.c_uint8),
+                ("sam_xa", C.c_uint8), ("reserved", C.c_uint8), ("score_fraction_threshold", C.c_double)]
+
+
+class _SamDb(C.Structure):
+    _fields_ = [("n_entries", C.c_uint64), ("bases", C.c_void_p), ("offs", C.c_void_p), ("locus_tags", C.c_void_p),
+                ("locus_offs", C.c_void_p), ("taxonomy_ids", C.c_void_p)]
+
+
 def declared_symbols():
     """Every function the public header declares (used by the CPU-tier symbol test)."""
     text = open(HEADER).read()
@@ -136,6 +146,11 @@ def lib():
     L.kslam_fastq_error.restype = C.c_char_p
     L.kslam_fastq_close.argtypes = [vp]
     L.kslam_fastq_close.restype = None
+    L.kslam_sam_header.argtypes = [C.POINTER(_SamDb), C.c_char_p, C.POINTER(vp), C.POINTER(u64)]
+    L.kslam_sam_batch.argtypes = [C.POINTER(SamParams), C.POINTER(_SamDb), C.POINTER(_ReadBatch), C.POINTER(_Pairs), C.POINTER(vp),
+                                  C.POINTER(u64), C.POINTER(u32)]
+    L.kslam_sam_free.argtypes = [vp]
+    L.kslam_sam_free.restype = None
     L.kslam_set_kmer_sort_bits.argtypes = [vp, u32]
     L.kslam_get_kmer_sort_bits.argtypes = [vp]
     L.kslam_load_genomes_part.argtypes = [vp, u64, vp, vp, u32, u32]
@@ -450,3 +465,55 @@ class FastqReader:
 
     def __exit__(self, *a):
         self.close()
+
+
+def _cat(strings):
+    offs = np.zeros(len(strings) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(x) for x in strings])
+    buf = np.frombuffer(b"".join(strings), dtype=np.uint8).copy() if offs[-1] else np.zeros(1, np.uint8)
+    return buf, offs
+
+
+class SamWriter:
+    """kslam_sam_header / kslam_sam_batch: the reference's host stages after pairing up to the SAM text
+    (PairedOverlap.h:314-576, SAM.h). Host code: works without a GPU on any (sorted_overlaps, cigar_pool, pairs)."""
+
+    def __init__(self, gen_bases, gen_offs, locus_tags, taxonomy_ids=None, num_alignments=10, score_fraction_threshold=0.95,
+                 pseudo_assembly=True, report_cigar=True, sam_xa=False):
+        self.L = lib()
+        self.gb, self.go = _u8(gen_bases), _u64(gen_offs)
+        self.lt, self.lo = _cat([t if isinstance(t, bytes) else t.encode() for t in locus_tags])
+        self.tax = None if taxonomy_ids is None else np.ascontiguousarray(taxonomy_ids, dtype=np.uint32)
+        self.db = _SamDb(len(self.go) - 1, self.gb.ctypes.data, self.go.ctypes.data, self.lt.ctypes.data, self.lo.ctypes.data,
+                         None if self.tax is None else self.tax.ctypes.data)
+        self.prm = SamParams(num_alignments, int(pseudo_assembly), int(report_cigar), int(sam_xa), 0, score_fraction_threshold)
+
+    def _take(self, ptr, n):
+        try:
+            return C.string_at(ptr, n.value)
+        finally:
+            self.L.kslam_sam_free(ptr)
+
+    def header(self, command_line=""):
+        ptr, n = C.c_void_p(), C.c_uint64()
+        rc = self.L.kslam_sam_header(C.byref(self.db), command_line.encode(), C.byref(ptr), C.byref(n))
+        if rc != 0:
+            raise KslamError(f"kslam_sam_header failed ({rc})")
+        return self._take(ptr, n)
+
+    def batch(self, read_bases, read_offs, quals, qual_offs, ids, id_offs, sorted_overlaps, cigar_pool, pairs):
+        """-> (SAM text of the batch, max allowed insert size)"""
+        rb, ro, q, qo, i, io = _u8(read_bases), _u64(read_offs), _u8(quals), _u64(qual_offs), _u8(ids), _u64(id_offs)
+        n = len(ro) - 1
+        reads = _ReadBatch(n, n // 2, rb.ctypes.data, ro.ctypes.data, q.ctypes.data, qo.ctypes.data, i.ctypes.data, io.ctypes.data)
+        so = np.ascontiguousarray(sorted_overlaps, dtype=OVERLAP_DT); pr = np.ascontiguousarray(pairs, dtype=PAIR_DT)
+        cg = np.ascontiguousarray(cigar_pool, dtype=np.uint32)
+        p = _Pairs()
+        p.n_sorted = len(so); p.sorted_overlaps = so.ctypes.data if len(so) else None
+        p.n_cigar_words = len(cg); p.cigar_pool = cg.ctypes.data if len(cg) else None
+        p.n_pairs = len(pr); p.pairs = pr.ctypes.data if len(pr) else None
+        ptr, ln, mi = C.c_void_p(), C.c_uint64(), C.c_uint32()
+        rc = self.L.kslam_sam_batch(C.byref(self.prm), C.byref(self.db), C.byref(reads), C.byref(p), C.byref(ptr), C.byref(ln), C.byref(mi))
+        if rc != 0:
+            raise KslamError(f"kslam_sam_batch failed ({rc})")
+        return self._take(ptr, ln), mi.value

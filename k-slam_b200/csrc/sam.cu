@@ -1,0 +1,447 @@
+// sam.cu — host stages after pairing, up to the SAM text (host code).
+//
+// north_star keeps these stages on the host; they are restated here so that the library is a drop-in from FASTQ to SAM
+// for the --sam-file run. Every step follows the reference literally, including the order of its (unstable) std::sort
+// calls — the same libstdc++ std::sort over the same sequence with the same comparator yields the same permutation,
+// which is what makes ties come out as in the reference:
+//   getPerReadOverlaps                   /root/reference/src/PairedOverlap.h:437-471
+//   getMaxAllowedInsertSize              PairedOverlap.h:314-360   (double arithmetic, same expressions)
+//   screenPairedAlignmentsByInsertSize   PairedOverlap.h:396-436   (replace = true: a far pair splits into two singles)
+//   screenPairedAlignmentsByScore        PairedOverlap.h:361-390
+//   pseudoAssembly                       PairedOverlap.h:480-576   (optional, on by default as in Globals.h:36)
+//   getCigarAndMD / SAMEntry / getSAMFromPair / writeSAMOutputPairs / getHeader    SAM.h:101-237,240-534
+// Input is exactly what kslam_pair_batch returns plus the batch's reads (ids, bases, qualities: kslam_read_batch) and
+// the database entries' bases / locus tags / taxonomy ids. Gene annotations (XG / XP / XR, GenBank databases) are not
+// carried by this interface yet: FASTA databases have none.
+#include "common.cuh"
+#include <algorithm>
+#include <cmath>
+#include <climits>
+#include <numeric>
+#include <string.h>
+#include <unordered_map>
+
+namespace {
+
+struct POv {                       // PairedOverlap, PairedOverlap.h:32-58, overlaps held as indices
+  uint32_t combinedScore = 0, entry = 0;
+  int refStart = 0, refEnd = 0;
+  uint32_t insertSize = 0;
+  bool hasR1 = false, hasR2 = false;
+  int32_t r1 = -1, r2 = -1;        // index into sorted_overlaps
+};
+struct ReadPair { uint32_t r1Pos = 0, r2Pos = 0; std::vector<POv> pairs; };
+
+struct Ctx {
+  const kslam_sam_params *prm; const kslam_sam_db *db; const kslam_read_batch *reads; const kslam_pairs *in;
+  std::string read_bases(uint32_t i) const { return std::string(reads->bases + reads->offs[i], reads->bases + reads->offs[i + 1]); }
+  std::string read_qual(uint32_t i) const { return std::string(reads->quals + reads->qual_offs[i], reads->quals + reads->qual_offs[i + 1]); }
+  std::string read_id(uint32_t i) const { return std::string(reads->ids + reads->id_offs[i], reads->ids + reads->id_offs[i + 1]); }
+  std::string locus(uint32_t e) const { return std::string(db->locus_tags + db->locus_offs[e], db->locus_tags + db->locus_offs[e + 1]); }
+};
+
+// sequenceTools.h:83-116: reverse, then complement upper-case A/C/G/T only
+std::string reverse_complement(const std::string &f) {
+  std::string rc = f;
+  std::reverse(rc.begin(), rc.end());
+  for (char &c : rc) {
+    switch (c) { case 'A': c = 'T'; break; case 'T': c = 'A'; break; case 'C': c = 'G'; break; case 'G': c = 'C'; break; default: break; }
+  }
+  return rc;
+}
+
+std::vector<ReadPair> per_read(const kslam_pairs *in, uint32_t midpoint) {          // PairedOverlap.h:437-471
+  std::vector<ReadPair> out;
+  ReadPair cur;
+  uint32_t readPos = 0;
+  for (uint64_t i = 0; i < in->n_pairs; i++) {
+    const kslam_pair &k = in->pairs[i];
+    POv p;
+    p.combinedScore = k.combined_score; p.entry = k.entry; p.refStart = k.ref_start; p.refEnd = k.ref_end;
+    p.insertSize = k.insert_size; p.hasR1 = k.r1_idx >= 0; p.hasR2 = k.r2_idx >= 0; p.r1 = k.r1_idx; p.r2 = k.r2_idx;
+    const uint32_t thisReadPos = p.hasR1 ? in->sorted_overlaps[p.r1].read : in->sorted_overlaps[p.r2].read - midpoint;
+    if (thisReadPos != readPos) {
+      if (cur.pairs.size()) { out.push_back(std::move(cur)); cur.pairs.clear(); }
+      readPos = thisReadPos;
+    }
+    cur.pairs.push_back(p);
+    cur.r1Pos = thisReadPos; cur.r2Pos = thisReadPos + midpoint;
+  }
+  if (cur.pairs.size()) out.push_back(cur);
+  return out;
+}
+
+uint32_t max_allowed_insert_size(const std::vector<ReadPair> &reads) {               // PairedOverlap.h:314-360
+  std::vector<int32_t> insertSizes;
+  for (auto &read : reads)
+    for (auto &p : read.pairs)
+      if (p.insertSize != 0) insertSizes.push_back(p.insertSize);
+  if (insertSizes.size() == 0) return UINT32_MAX;
+  std::sort(insertSizes.begin(), insertSizes.end());
+  int32_t limit = 0;
+  for (int i = 0; i < 99; i++) {
+    if ((insertSizes[floor(insertSizes.size() * (i + 1) / 100.0)] - insertSizes[floor(insertSizes.size() * (i) / 100.0)]) > 1000) {
+      limit = insertSizes[floor(insertSizes.size() * (i) / 100)];
+      break;
+    }
+  }
+  int32_t LQ = insertSizes[floor(insertSizes.size() * 0.25)];
+  int32_t UQ = insertSizes[floor(insertSizes.size() * 0.75)];
+  int32_t lowerLimit = 0;
+  int32_t upperLimit = UQ + 2 * (UQ - LQ);
+  if (limit) upperLimit = limit;
+  if (upperLimit == 0) upperLimit = INT32_MAX;
+  auto endPos = std::remove_if(insertSizes.begin(), insertSizes.end(), [&](const int32_t i) { return i < lowerLimit || i > upperLimit; });
+  insertSizes.resize(std::distance(insertSizes.begin(), endPos));
+  double sum = std::accumulate(insertSizes.begin(), insertSizes.end(), 0.0);
+  double mean = sum / insertSizes.size();
+  double sqSum = std::inner_product(insertSizes.begin(), insertSizes.end(), insertSizes.begin(), 0.0);
+  double stdDev = std::sqrt(sqSum / insertSizes.size() - mean * mean);
+  auto result = floor(mean + 6 * stdDev);
+  return std::isnan(result) ? UINT_MAX : result;
+}
+
+void screen_by_insert_size(std::vector<ReadPair> &reads, const kslam_overlap *ov, const uint32_t insertSize) {   // :396-436, replace = true
+  for (auto &read : reads) {
+    std::sort(read.pairs.begin(), read.pairs.end(), [](const POv &i, const POv &j) { return i.insertSize < j.insertSize; });
+    auto cutoff = std::find_if(read.pairs.begin(), read.pairs.end(), [&](const POv &i) { return i.insertSize > insertSize; });
+    auto cutoffPos = std::distance(read.pairs.begin(), cutoff);
+    read.pairs.reserve(read.pairs.size() + std::distance(cutoff, read.pairs.end()));
+    const size_t oldEnd = read.pairs.size();
+    for (size_t cur = (size_t)cutoffPos; cur < oldEnd; cur++) {
+      POv single;                                            // the R1 half becomes a pair record of its own
+      const kslam_overlap &o1 = ov[read.pairs[cur].r1];
+      single.combinedScore = (uint16_t)o1.sw_score; single.entry = read.pairs[cur].entry;
+      single.refStart = o1.ref_begin; single.refEnd = o1.ref_end; single.insertSize = 0;
+      single.hasR1 = true; single.hasR2 = false; single.r1 = read.pairs[cur].r1; single.r2 = -1;
+      read.pairs.push_back(single);
+      POv &c = read.pairs[cur];                              // ... and the record itself keeps R2 only
+      const kslam_overlap &o2 = ov[c.r2];
+      c.combinedScore = (uint16_t)o2.sw_score; c.hasR1 = false; c.insertSize = 0; c.r1 = -1;
+      c.refStart = o2.ref_begin; c.refEnd = o2.ref_end;
+    }
+  }
+}
+
+void screen_by_score(std::vector<ReadPair> &reads, double fraction) {                 // PairedOverlap.h:361-390
+  for (auto &read : reads) {
+    if (read.pairs.size() == 0) continue;
+    std::sort(read.pairs.begin(), read.pairs.end(), [](const POv &i, const POv &j) { return i.combinedScore > j.combinedScore; });
+    unsigned topScore = read.pairs[0].combinedScore;
+    auto cutoff = std::find_if(read.pairs.begin(), read.pairs.end(), [&](const POv &i) { return i.combinedScore < topScore * fraction; });
+    read.pairs.erase(cutoff, read.pairs.end());
+  }
+}
+
+void pseudo_assembly(std::vector<ReadPair> &pairedAlignments) {                       // PairedOverlap.h:480-576
+  struct coverage { int start = 0; int stop = 0; };
+  struct entryAndOverlaps { uint32_t entryPos = 0; std::vector<std::pair<coverage, POv *>> reads; };
+  std::unordered_map<uint32_t, entryAndOverlaps> entriesAndOverlaps;
+  for (auto &read : pairedAlignments)
+    for (auto &overlap : read.pairs) {
+      coverage c; c.start = overlap.refStart; c.stop = overlap.refEnd;
+      auto &e = entriesAndOverlaps[overlap.entry];
+      e.entryPos = overlap.entry;
+      e.reads.push_back({c, &overlap});
+    }
+  for (auto &entry : entriesAndOverlaps) {
+    std::sort(entry.second.reads.begin(), entry.second.reads.end(),
+              [](const std::pair<coverage, POv *> &i, const std::pair<coverage, POv *> &j) { return i.first.start < j.first.start; });
+    auto chainStart = entry.second.reads.begin();
+    int highestPos = -1000000;
+    uint32_t score = 0;
+    uint32_t numBases = 0;
+    double perBaseScore = 0;
+    for (auto overlap = entry.second.reads.begin(); overlap != entry.second.reads.end(); overlap++) {
+      if (overlap->first.start > highestPos - 20) {
+        auto chainLength = std::distance(chainStart, overlap);
+        if (chainLength > 1) {
+          double length = highestPos - chainStart->first.start;
+          double coverage = numBases / length;
+          double avgScorePerBase = perBaseScore / chainLength;
+          double score = coverage * avgScorePerBase * length;
+          for (auto overlap2 = chainStart; overlap2 != overlap; overlap2++) overlap2->second->combinedScore = score;
+        }
+        chainStart = overlap;
+        highestPos = overlap->first.stop;
+        score = overlap->second->combinedScore;
+        perBaseScore = overlap->second->combinedScore * 1.0 / abs(overlap->second->refEnd - overlap->second->refStart);
+        numBases = abs(overlap->second->refEnd - overlap->second->refStart);
+      } else {
+        if (overlap->first.stop > highestPos) highestPos = overlap->first.stop;
+        score += overlap->second->combinedScore;
+        perBaseScore += overlap->second->combinedScore * 1.0 / abs(overlap->second->refEnd - overlap->second->refStart);
+        numBases += abs(overlap->second->refEnd - overlap->second->refStart);
+      }
+    }
+    auto chainLength = std::distance(chainStart, entry.second.reads.end());
+    if (chainLength > 1) {
+      double length = highestPos - chainStart->first.start;
+      double coverage = numBases / length;
+      double avgScorePerBase = perBaseScore / chainLength;
+      double score = coverage * avgScorePerBase * length;
+      for (auto overlap2 = chainStart; overlap2 != entry.second.reads.end(); overlap2++) overlap2->second->combinedScore = score;
+    }
+    (void)score;
+  }
+}
+
+// ---- SAM.h ---------------------------------------------------------------------------------------------------
+struct SequenceDifference { std::string cigar, MD; uint32_t NM = 0; double logProbability = 0; };
+
+const std::vector<double> &log_match_table() {           // SAM.h:33-40
+  static std::vector<double> table = [] {
+    std::vector<double> t;
+    t.push_back(std::log10(1.0 - std::pow(10.0, 1.0 / -10.0)));
+    for (int i = 1; i < 100; i++) t.push_back(std::log10(1.0 - std::pow(10.0, i / -10.0)));
+    return t;
+  }();
+  return table;
+}
+const std::vector<double> &log_mismatch_table() {        // SAM.h:41-48
+  static std::vector<double> table = [] {
+    std::vector<double> t;
+    t.push_back(1 / -10.0);
+    for (int i = 1; i < 100; i++) t.push_back(i / -10.0);
+    return t;
+  }();
+  return table;
+}
+
+SequenceDifference cigar_and_md(const Ctx &c, const kslam_overlap &overlap) {          // SAM.h:101-237
+  const auto &matchTable = log_match_table();
+  const auto &misMatchTable = log_mismatch_table();
+  SequenceDifference sd;
+  std::vector<std::string> MDcomponents;
+  const char *ref = c.db->bases + c.db->offs[overlap.entry];
+  std::string query = overlap.rev_comp ? reverse_complement(c.read_bases(overlap.read)) : c.read_bases(overlap.read);
+  std::string quality = c.read_qual(overlap.read);
+  if (overlap.rev_comp) std::reverse(quality.begin(), quality.end());
+  if (!overlap.cigar_len || !c.in->cigar_pool) return sd;            // Alignment::cigar == nullptr
+  const uint32_t *cig = c.in->cigar_pool + overlap.cigar_off;
+  int refPos = overlap.ref_begin;
+  int queryPos = 0;
+  if (overlap.query_begin > 0) {
+    auto length = overlap.query_begin;
+    sd.cigar.append(std::to_string(length)); sd.cigar.push_back('S');
+    queryPos += length;
+  }
+  for (uint32_t e = 0; e < overlap.cigar_len; e++) {
+    int numMatch = 0;
+    uint32_t length = cig[e] >> 4;
+    sd.cigar.append(std::to_string(length));
+    uint32_t operation = cig[e] & 0xf;
+    std::string temp;
+    switch (operation) {
+      case 0:
+        sd.cigar.push_back('M');
+        for (int i = 0; i < (int)length; i++) {
+          if (ref[refPos] == query[queryPos]) { numMatch++; sd.logProbability += matchTable[quality[queryPos] - 33]; }
+          else {
+            sd.NM++;
+            if (numMatch) MDcomponents.push_back(std::to_string(numMatch));
+            MDcomponents.push_back(std::string(1, ref[refPos]));
+            sd.logProbability += misMatchTable[quality[queryPos] - 33];
+            numMatch = 0;
+          }
+          refPos++; queryPos++;
+        }
+        if (numMatch) MDcomponents.push_back(std::to_string(numMatch));
+        break;
+      case 1:
+        sd.cigar.push_back('I'); sd.NM += length; queryPos += length;
+        break;
+      case 2:
+        sd.cigar.push_back('D');
+        MDcomponents.push_back("^");
+        for (int i = 0; i < (int)length; i++) { temp.push_back(ref[refPos]); sd.NM++; refPos++; }
+        MDcomponents.push_back(temp);
+        break;
+      default: break;
+    }
+  }
+  int end = (int)query.size() - overlap.query_end - 1;
+  if (end > 0) { sd.cigar.append(std::to_string(end)); sd.cigar.push_back('S'); }
+  bool ambiguous = false;
+  for (auto it = MDcomponents.begin(); it != MDcomponents.end();) {
+    if (*it == "^") { sd.MD.append(*it); it++; sd.MD.append(*it); ambiguous = true; it++; }
+    else if (isdigit((*it)[0])) {
+      int runningTotal = 0;
+      while (it != MDcomponents.end() && isdigit((*it)[0])) { runningTotal += std::stoi(*it); it++; }
+      sd.MD.append(std::to_string(runningTotal));
+      ambiguous = false;
+    } else {
+      if (ambiguous) { sd.MD.append("0"); ambiguous = false; }
+      sd.MD.append(*it);
+      it++;
+    }
+    if (it == MDcomponents.end()) break;
+  }
+  return sd;
+}
+
+struct SAMEntry {                                        // SAM.h:240-281
+  std::string qname, rname;
+  uint32_t pos = 0; uint8_t mapq = 255;
+  std::string cigar = "*", rnext = "=";
+  uint32_t pnext = 0; int32_t tlen = 0;
+  bool multipleSegments = false, allSegmentsAligned = false, thisSegmentUnmapped = false, nextSegmentUnmapped = false;
+  bool revComp = false, nextRevComp = false, first = false, secondary = true;
+  std::string MD; uint16_t AS = 0; uint32_t NM = 0; uint16_t XS = 0; uint32_t XO = 0, XT = 0;
+  double prob = 0;
+};
+
+uint16_t sam_flag(const SAMEntry &e) {                   // SAM.h:309-326 (pairedData = true)
+  uint16_t flag = 0;
+  if (e.multipleSegments) flag |= 0x1;
+  if (e.allSegmentsAligned) flag |= 0x2;
+  if (e.thisSegmentUnmapped) flag |= 0x4;
+  if (e.nextSegmentUnmapped) flag |= 0x8;
+  if (e.revComp) flag |= 0x10;
+  if (e.nextRevComp) flag |= 0x20;
+  flag |= e.first ? 0x40 : 0x80;
+  if (e.secondary) flag |= 0x100;
+  return flag;
+}
+
+std::string sam_line(const SAMEntry &e, bool reportCigar) {   // SAM.h:282-308
+  std::string out;
+  out += e.qname + '\t' + std::to_string(sam_flag(e)) + '\t' + e.rname + '\t' + std::to_string(e.pos) + '\t' + std::to_string(e.mapq) + '\t' +
+         (reportCigar ? e.cigar : "*") + '\t' + e.rnext + '\t' + std::to_string(e.pnext) + '\t' + std::to_string(e.tlen) + '\t' + '*' + '\t' + '*';
+  if (e.thisSegmentUnmapped) return out;
+  if (reportCigar) { out.append("\tMD:Z:"); out += e.MD; }
+  out.append("\tAS:i:");
+  out += std::to_string(e.AS) + '\t' + "XS:i:" + std::to_string(e.XS) + '\t' + "NM:i:" + std::to_string(e.NM) + '\t' + "X0:i:" + std::to_string(e.XO);
+  if (e.XT != 0) out += "\tXT:i:" + std::to_string(e.XT);
+  return out;
+}
+
+void sam_init(SAMEntry &s, const Ctx &c, const kslam_overlap &overlap) {              // SAM.h:344-356
+  auto sd = cigar_and_md(c, overlap);
+  s.cigar = sd.cigar; s.MD = sd.MD; s.NM = sd.NM;
+  s.prob = std::pow(10, sd.logProbability);
+  s.rname = c.locus(overlap.entry);
+  s.pos = overlap.ref_begin + 1;
+  s.AS = (uint16_t)overlap.sw_score;
+}
+
+std::pair<SAMEntry, SAMEntry> sam_from_pair(const Ctx &c, const POv &ap) {             // SAM.h:357-441
+  const kslam_overlap *ov = c.in->sorted_overlaps;
+  SAMEntry r1, r2;
+  r1.first = true; r2.first = false;
+  const uint32_t tax = c.db->taxonomy_ids ? c.db->taxonomy_ids[ap.entry] : 0;
+  r1.XT = tax; r2.XT = tax;
+  bool conventionalSequence = true;
+  bool bothAligned = ap.hasR1 && ap.hasR2;
+  r1.multipleSegments = true; r2.multipleSegments = true;
+  if (bothAligned) {
+    r1.allSegmentsAligned = true; r2.allSegmentsAligned = true;
+    conventionalSequence = ov[ap.r1].ref_begin < ov[ap.r2].ref_begin;
+    if (ov[ap.r1].rev_comp) { r1.revComp = true; r2.nextRevComp = true; }
+    if (ov[ap.r2].rev_comp) { r2.revComp = true; r1.nextRevComp = true; }
+  } else if (ap.hasR1) {
+    r1.nextSegmentUnmapped = true; r2.thisSegmentUnmapped = true;
+    if (ov[ap.r1].rev_comp) r1.revComp = true;
+  } else if (ap.hasR2) {
+    r2.nextSegmentUnmapped = true; r1.thisSegmentUnmapped = true;
+    if (ov[ap.r2].rev_comp) r2.revComp = true;
+  }
+  if (ap.hasR1) sam_init(r1, c, ov[ap.r1]);
+  if (ap.hasR2) sam_init(r2, c, ov[ap.r2]);
+  r1.pnext = r2.pos; r2.pnext = r1.pos;
+  if (!ap.hasR1) { r1.rname = r2.rname; r1.pos = r2.pos; r2.pnext = r2.pos; r1.pnext = r2.pos; }
+  if (!ap.hasR2) { r2.rname = r1.rname; r2.pos = r1.pos; r1.pnext = r1.pos; r2.pnext = r1.pos; }
+  int32_t tlen = ap.refEnd - ap.refStart + 1;
+  if (!(ap.hasR1 || ap.hasR2)) tlen = 0;
+  if (!conventionalSequence) tlen *= -1;
+  r1.tlen = tlen; r2.tlen = tlen * -1;
+  r1.XS = ap.combinedScore; r2.XS = ap.combinedScore;
+  return {r1, r2};
+}
+
+void write_pairs(std::string &out, const Ctx &c, ReadPair &read) {                    // SAM.h:451-517
+  std::sort(read.pairs.begin(), read.pairs.end(), [](const POv &i, const POv &j) { return i.combinedScore > j.combinedScore; });
+  std::vector<std::pair<SAMEntry, SAMEntry>> SAMPairs;
+  uint32_t r1NumHits = 0, r2NumHits = 0;
+  for (auto &ap : read.pairs) {
+    if (ap.hasR1) r1NumHits++;
+    if (ap.hasR2) r2NumHits++;
+    SAMPairs.push_back(sam_from_pair(c, ap));
+    if (SAMPairs.size() >= c.prm->num_alignments) break;
+  }
+  if (SAMPairs.empty()) return;                          // the reference would dereference begin() here; nothing to write
+  auto primary = SAMPairs.begin();
+  double r1SumProb = 0, r2SumProb = 0;
+  const std::string q1 = c.read_id(read.r1Pos), q2 = c.read_id(read.r2Pos);
+  for (auto sp = SAMPairs.begin(); sp != SAMPairs.end(); sp++) {
+    sp->first.qname = q1; sp->second.qname = q2;
+    r1SumProb += sp->first.prob; r2SumProb += sp->second.prob;
+    sp->first.XO = r1NumHits; sp->second.XO = r2NumHits;
+  }
+  primary->first.secondary = false; primary->second.secondary = false;
+  for (auto sp = SAMPairs.begin(); sp != SAMPairs.end(); sp++) {
+    double temp = 1.0 - sp->first.prob / r1SumProb;
+    if (temp <= 0.00001) temp = 0.00001;
+    double temp2 = 1.0 - sp->second.prob / r2SumProb;
+    if (temp2 <= 0.00001) temp2 = 0.00001;
+    sp->first.mapq = ceil(-10.0 * std::log10(temp));
+    sp->second.mapq = ceil(-10.0 * std::log10(temp2));
+    out += sam_line(sp->first, c.prm->report_cigar != 0); out += "\n";
+    out += sam_line(sp->second, c.prm->report_cigar != 0); out += "\n";
+    if (c.prm->sam_xa) break;
+  }
+}
+
+char *dup_text(const std::string &s) {
+  char *p = (char *)malloc(s.size() + 1);
+  if (!p) return nullptr;
+  memcpy(p, s.data(), s.size()); p[s.size()] = 0;
+  return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kslam_sam_header(const kslam_sam_db *db, const char *command_line, char **text, uint64_t *len) {   // SAM.h:518-531
+  if (!db || !text) return KSLAM_ERR_ARG;
+  std::string h = "@HD\tVN:1.0\tSO:unsorted\n";
+  for (uint64_t e = 0; e < db->n_entries; e++) {
+    h += "@SQ\tSN:";
+    h.append(db->locus_tags + db->locus_offs[e], db->locus_tags + db->locus_offs[e + 1]);
+    h += "\tLN:";
+    h += std::to_string(db->offs[e + 1] - db->offs[e]);
+    if (db->taxonomy_ids && db->taxonomy_ids[e]) { h += "\tSP:"; h += std::to_string(db->taxonomy_ids[e]); }
+    h += "\n";
+  }
+  h += "@PG\tID:SLAM\tPN:SLAM\tVN:1.0\tCL:\"";
+  h += command_line ? command_line : "";
+  h += "\"\n";
+  *text = dup_text(h);
+  if (len) *len = h.size();
+  return *text ? KSLAM_OK : KSLAM_ERR_NOMEM;
+}
+
+int kslam_sam_batch(const kslam_sam_params *prm, const kslam_sam_db *db, const kslam_read_batch *reads, const kslam_pairs *pairs,
+                    char **text, uint64_t *len, uint32_t *max_insert_size) {
+  if (!prm || !db || !reads || !pairs || !text) return KSLAM_ERR_ARG;
+  if (pairs->n_pairs && (!pairs->pairs || !pairs->sorted_overlaps)) return KSLAM_ERR_ARG;
+  try {
+    Ctx c{prm, db, reads, pairs};
+    auto rp = per_read(pairs, (uint32_t)(reads->n_reads / 2));
+    const uint32_t maxInsert = max_allowed_insert_size(rp);
+    if (max_insert_size) *max_insert_size = maxInsert;
+    screen_by_insert_size(rp, pairs->sorted_overlaps, maxInsert);
+    screen_by_score(rp, prm->score_fraction_threshold);
+    if (prm->pseudo_assembly) { pseudo_assembly(rp); screen_by_score(rp, prm->score_fraction_threshold); }
+    std::string out;
+    for (auto &read : rp) write_pairs(out, c, read);
+    *text = dup_text(out);
+    if (len) *len = out.size();
+    return *text ? KSLAM_OK : KSLAM_ERR_NOMEM;
+  } catch (const std::exception &) { return KSLAM_ERR_NOMEM; }
+}
+
+void kslam_sam_free(char *text) { free(text); }
+
+}  // extern "C"

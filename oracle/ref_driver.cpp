@@ -241,6 +241,45 @@ uint64_t kref_ssw_batch(uint64_t n, const char *q, const uint64_t *qoffs, const 
   return n;
 }
 
+// Replace the qualities of the reads set by kref_set_reads (same lengths as the bases).
+void kref_set_read_quals(void *h, const char *quals, const uint64_t *offs) {
+  KrefCtx *c = (KrefCtx *)h;
+  for (size_t i = 0; i < c->reads.size(); i++) c->reads[i].quality.assign(quals + offs[i], quals + offs[i + 1]);
+}
+// The rest of the batch loop for a --sam-file run, SLAM.h:215-239, on the pairs kref_pair left in the ctx:
+// getPerReadOverlaps, getMaxAllowedInsertSize, both screens, pseudoAssembly (optional), writeSAMOutputPairs.
+// Returns the SAM text length; the text is copied into buf when it is large enough.
+uint64_t kref_sam(void *h, uint32_t num_alignments, double fraction, int pseudo, int sam_xa, const char *tmp_path,
+                  char *buf, uint64_t cap, uint32_t *max_insert) {
+  KrefCtx *c = (KrefCtx *)h;
+  numSAMAlignments = num_alignments; scoreFractionThreshold = fraction; SAMXA = sam_xa != 0; pairedData = true;
+  auto rp = getPerReadOverlaps(c->pairs.begin(), c->pairs.end(), c->reads.size() / 2);
+  c->pairs.clear();
+  uint32_t maxInsertSize = getMaxAllowedInsertSize(rp);
+  if (max_insert) *max_insert = maxInsertSize;
+  screenPairedAlignmentsByInsertSize(rp, maxInsertSize, true);
+  screenPairedAlignmentsByScore(rp, scoreFractionThreshold);
+  if (pseudo) {
+    pseudoAssembly(rp, c->reads, c->idx);
+    screenPairedAlignmentsByScore(rp, scoreFractionThreshold);
+  }
+  {
+    std::ofstream sam(tmp_path);
+    for (auto &read : rp) writeSAMOutputPairs(sam, read, c->reads, c->idx);
+  }
+  std::ifstream in(tmp_path, std::ios::binary);
+  std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  if (buf && cap >= text.size()) memcpy(buf, text.data(), text.size());
+  return text.size();
+}
+uint64_t kref_sam_header(void *h, const char *cmd, char *buf, uint64_t cap) {
+  KrefCtx *c = (KrefCtx *)h;
+  commandLine = cmd;
+  std::string t = getHeader(c->idx);
+  if (buf && cap >= t.size()) memcpy(buf, t.data(), t.size());
+  return t.size();
+}
+
 // ---- the reference's own FASTQ reader (FASTQsequence.h:110-165) over real files, batch by batch ------------------
 // Streams stay open across calls like the ifstreams of the batch loop (SLAM.h:194-208). Returns the number of reads
 // of the batch, or (uint64_t)-1 when the reference throws ("mismatch in R1 and R2 size").

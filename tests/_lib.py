@@ -117,6 +117,11 @@ def ref():
         L.kref_get_overlaps.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.kref_ssw_batch.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
+        L.kref_set_read_quals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kref_sam.restype = C.c_uint64
+        L.kref_sam.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
+        L.kref_sam_header.restype = C.c_uint64
+        L.kref_sam_header.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64]
         L.kref_fastq_open.restype = C.c_void_p
         L.kref_fastq_open.argtypes = [C.c_char_p, C.c_char_p]
         L.kref_fastq_next.restype = C.c_uint64
@@ -275,6 +280,28 @@ class Ref:
         self.L.kref_get_pairs(self.h, _p(pairs))
         ov, pool = self._overlaps()
         return ov, pool, pairs
+
+
+def ref_sam(R, quals=None, qual_offs=None, num_alignments=10, fraction=0.95, pseudo=True, sam_xa=False):
+    """The reference's host stages after kref_pair up to the SAM text (SLAM.h:215-239) on a Ref context that has run
+    align_to_database() and screen_and_pair(). Returns (text, max insert size). Consumes the context's pairs."""
+    L = R.L
+    if quals is not None:
+        q = u8(quals); qo = np.ascontiguousarray(qual_offs, dtype=np.uint64)
+        L.kref_set_read_quals(R.h, _p(q), _p(qo))
+    tmp = tempfile.NamedTemporaryFile(suffix=".sam", delete=False); tmp.close()
+    mi = C.c_uint32()
+    buf = np.zeros(1 << 26, dtype=np.uint8)
+    n = L.kref_sam(R.h, num_alignments, fraction, int(pseudo), int(sam_xa), tmp.name.encode(), _p(buf), len(buf), C.byref(mi))
+    os.unlink(tmp.name)
+    assert n <= len(buf)
+    return bytes(buf[:n]), mi.value
+
+
+def ref_sam_header(R, cmd=""):
+    buf = np.zeros(1 << 20, dtype=np.uint8)
+    n = R.L.kref_sam_header(R.h, cmd.encode(), _p(buf), len(buf))
+    return bytes(buf[:n])
 
 
 def ref_ssw_batch(q, qoffs, r, roffs, params, cigar_cap=64, threads=0):

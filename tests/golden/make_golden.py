@@ -63,9 +63,20 @@ def fastq_fixture(name):
                         batch_sizes=np.array([len(b) for b in batches], np.int64))
 
 
+def sam_fixture(name):
+    """Reference SAM text (SLAM.h:215-239 chain + SAM.h) for a small config-1-like batch, with its inputs."""
+    from test_sam_host import make_inputs, reference_side
+    gb, go, rb, ro, quals, idb, ido = make_inputs(T.load_pkg(), 5, n_pairs=300, kind="config1")
+    ov, pool, pairs, text, mi, _ = reference_side(gb, go, rb, ro, quals, 1)
+    R = T.Ref(gb, go, rb[:0], ro[:1], T.default_params()); hdr = T.ref_sam_header(R, "SLAM golden"); R.close()
+    np.savez_compressed(os.path.join(HERE, name), gb=gb, go=go, rb=rb, ro=ro, quals=quals, ids=idb, id_offs=ido, ov=ov, pool=pool, pairs=pairs,
+                        sam=np.frombuffer(text, np.uint8), max_insert=mi, header=np.frombuffer(hdr, np.uint8))
+
+
 def main():
     sys.path.insert(0, os.path.dirname(HERE))
     fastq_fixture("fastq_reader.npz")
+    sam_fixture("sam_config1_mini.npz")
     gb, go, rb, ro = synth.adversarial_set(seed=7, n_genomes=8, glen=6000, n_pairs=400)
     pipeline_fixture("pipeline_adversarial_cigar.npz", gb, go, rb, ro, T.default_params(report_cigar=1))
     pipeline_fixture("pipeline_adversarial_thr60.npz", gb, go, rb, ro,

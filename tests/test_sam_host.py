@@ -1,0 +1,72 @@
+"""CPU tier: the host stages after pairing (kslam_sam_batch: per-read grouping, insert-size limit, both screens,
+pseudo-assembly, SAM records with CIGAR / MD / NM / MAPQ) against the reference's OWN functions run here
+(oracle/_ref: SLAM.h:215-239 chain, PairedOverlap.h:314-576, SAM.h), byte for byte, and against a golden SAM file."""
+import numpy as np
+import pytest
+
+import _lib as T
+
+
+def make_inputs(pkg, seed, n_pairs=400, kind="adversarial"):
+    if kind == "adversarial":
+        gb, go, rb, ro = pkg.synth.adversarial_set(seed=seed, n_genomes=8, glen=6000, n_pairs=n_pairs)
+    elif kind == "related":
+        gb, go = pkg.synth.related_genomes(12, 20_000, seed=seed)          # multi-genome hits: ties, chains, far pairs
+        rb, ro, _ = pkg.synth.paired_reads(gb, go, n_pairs, seed=seed + 1)
+    else:
+        gb, go = pkg.synth.random_genomes(4, 30_000, seed=seed)
+        rb, ro, _ = pkg.synth.paired_reads(gb, go, n_pairs, seed=seed + 1)
+    rng = np.random.default_rng(seed)
+    quals = rng.integers(35, 75, size=len(rb), dtype=np.uint8)
+    n = len(ro) - 1
+    ids = [b"r%d" % i for i in range(n)]            # what "@r<i>" becomes (FASTQsequence.h:61-71)
+    idb = np.frombuffer(b"".join(ids), np.uint8); ido = np.zeros(n + 1, np.uint64); ido[1:] = np.cumsum([len(x) for x in ids])
+    return gb, go, rb, ro, quals, idb, ido
+
+
+def reference_side(gb, go, rb, ro, quals, cigar, **kw):
+    R = T.Ref(gb, go, rb, ro, T.default_params(report_cigar=int(cigar)))
+    R.align_to_database()
+    ov, pool, pairs = R.screen_and_pair()
+    hdr = T.ref_sam_header(R, "SLAM --db x")
+    text, mi = T.ref_sam(R, quals, ro, **kw)
+    R.close()
+    return ov, pool, pairs, text, mi, hdr
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="needs oracle/_ref (built where /root/reference exists)")
+@pytest.mark.parametrize("kind,seed", [("adversarial", 71), ("related", 72), ("config1", 73)])
+@pytest.mark.parametrize("cigar", [1, 0])
+def test_sam_text_equals_reference(pkg, kind, seed, cigar):
+    gb, go, rb, ro, quals, idb, ido = make_inputs(pkg, seed, kind=kind)
+    tags = [f"g{i}" for i in range(len(go) - 1)]
+    for kw in (dict(), dict(pseudo=False), dict(num_alignments=1), dict(sam_xa=True, fraction=0.5), dict(num_alignments=3, fraction=0.0)):
+        ov, pool, pairs, want, want_mi, want_hdr = reference_side(gb, go, rb, ro, quals, cigar, **kw)
+        assert len(pairs) > 50 and len(want) > 1000
+        w = pkg.SamWriter(gb, go, tags, num_alignments=kw.get("num_alignments", 10), score_fraction_threshold=kw.get("fraction", 0.95),
+                          pseudo_assembly=kw.get("pseudo", True), report_cigar=bool(cigar), sam_xa=kw.get("sam_xa", False))
+        got, mi = w.batch(rb, ro, quals, ro, idb, ido, ov, pool, pairs)
+        assert mi == want_mi
+        if got != want:
+            a, b = got.split(b"\n"), want.split(b"\n")
+            bad = [(i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y][:3]
+            raise AssertionError((kw, len(a), len(b), bad))
+        assert w.header("SLAM --db x") == want_hdr
+
+
+def test_sam_golden(pkg, golden):
+    """Inputs and the reference's SAM text from tests/golden/make_golden.py: travels to boxes without /root/reference."""
+    g = golden("sam_config1_mini.npz")
+    tags = [f"g{i}" for i in range(len(g["go"]) - 1)]
+    w = pkg.SamWriter(g["gb"], g["go"], tags, report_cigar=True)
+    got, mi = w.batch(g["rb"], g["ro"], g["quals"], g["ro"], g["ids"], g["id_offs"], g["ov"], g["pool"], g["pairs"])
+    assert got == g["sam"].tobytes() and mi == int(g["max_insert"])
+    assert w.header("SLAM golden") == g["header"].tobytes()
+
+
+def test_sam_empty_batch(pkg):
+    gb, go = pkg.synth.random_genomes(2, 1000, seed=1)
+    w = pkg.SamWriter(gb, go, ["a", "b"])
+    z8, z1 = np.zeros(0, np.uint8), np.zeros(1, np.uint64)
+    got, mi = w.batch(z8, z1, z8, z1, z8, z1, np.zeros(0, pkg.OVERLAP_DT), np.zeros(0, np.uint32), np.zeros(0, pkg.PAIR_DT))
+    assert got == b"" and mi == 2**32 - 1
