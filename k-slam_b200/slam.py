@@ -1,0 +1,72 @@
+"""FASTQ + FASTA -> SAM through the library, batch by batch: the --just-align / --sam-file run of the reference
+(`SLAM --db DB --just-align --sam-file out.sam R1 R2`, SLAM.h:159-268) with every stage of its batch loop taken from
+libkslam.so: kslam_fastq_next (reader), kslam_align_pair_batch (alignToDatabase + screen + getPairedOverlaps on the GPU)
+and kslam_sam_batch (insert-size / score screens, pseudo-assembly, SAM records). The database is given as FASTA files
+and parsed the way --parse-fasta does (GenbankTools.h:224-260: locus tag = header up to the first space, bases
+upper-cased); the Boost text archive the reference stores in --db is not read here."""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+
+def parse_fasta(paths):
+    """createIndexFromFASTA, GenbankTools.h:224-260. Returns (bases u8, offs u64, locus tags)."""
+    entries, tags = [], []
+    for path in paths:
+        cur, tag, have = [], b"", False
+        with open(path, "rb") as f:
+            data = f.read()
+        for line in data.replace(b"\r\n", b"\n").replace(b"\r", b"\n").split(b"\n"):
+            if not line:
+                continue
+            if line[:1] == b">":
+                if sum(len(x) for x in cur):
+                    entries.append(b"".join(cur)); tags.append(tag)
+                cur, tag = [], b""
+                sp = line.find(b" ")
+                if sp not in (-1, 0):
+                    tag = line[1:sp]
+            else:
+                cur.append(line)
+        if sum(len(x) for x in cur):
+            entries.append(b"".join(cur)); tags.append(tag)
+    entries = [e.upper() for e in entries]            # inPlaceConvertToUpperCase
+    offs = np.zeros(len(entries) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(e) for e in entries])
+    bases = np.frombuffer(b"".join(entries), dtype=np.uint8).copy() if entries else np.zeros(0, np.uint8)
+    return bases, offs, tags
+
+
+def align_to_sam(pkg, fasta_paths, r1, r2, sam_path, reads_at_once=10_000_000, num_alignments=10, score_fraction_threshold=0.95,
+                 pseudo_assembly=True, sam_xa=False, min_alignment_score=0, command_line="", device=0, log=None):
+    """Returns a dict of counts and wall times per stage."""
+    t = {"ingest": 0.0, "gpu": 0.0, "sam": 0.0, "write": 0.0}
+    gb, go, tags = parse_fasta(fasta_paths)
+    stats = {"pairs": 0, "batches": 0, "sam_bytes": 0}
+    with pkg.Aligner(report_cigar=True, score_threshold=min_alignment_score, device=device) as al, \
+            pkg.FastqReader(r1, r2) as rd, open(sam_path, "wb") as out:
+        al.set_debug_taps(False)
+        al.load_genomes(gb, go)
+        w = pkg.SamWriter(gb, go, tags, num_alignments=num_alignments, score_fraction_threshold=score_fraction_threshold,
+                          pseudo_assembly=pseudo_assembly, report_cigar=True, sam_xa=sam_xa)
+        out.write(w.header(command_line))
+        while True:
+            t0 = time.perf_counter()
+            b = rd.next(reads_at_once, copy=False)
+            t1 = time.perf_counter()
+            if b is None:
+                break
+            p = al.align_pair_batch(b.bases, b.offs, copy=False)
+            t2 = time.perf_counter()
+            text, _ = w.batch(b.bases, b.offs, b.quals, b.qual_offs, b.ids, b.id_offs, p.sorted_overlaps, p.cigar_pool, p.pairs)
+            t3 = time.perf_counter()
+            out.write(text)
+            t4 = time.perf_counter()
+            t["ingest"] += t1 - t0; t["gpu"] += t2 - t1; t["sam"] += t3 - t2; t["write"] += t4 - t3
+            stats["pairs"] += b.n_r1; stats["batches"] += 1; stats["sam_bytes"] += len(text)
+            if log:
+                log(f"batch {stats['batches']}: {b.n_r1} pairs, ingest {t1 - t0:.2f}s gpu {t2 - t1:.2f}s sam {t3 - t2:.2f}s")
+    stats["seconds"] = t
+    return stats

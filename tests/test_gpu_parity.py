@@ -359,3 +359,44 @@ def test_fastq_to_alignments(pkg, tmp_path):
             assert np.array_equal(got.sorted_overlaps, want.sorted_overlaps)
             done += cnt
         assert done == mid
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="needs the prebuilt oracle/_ref")
+@pytest.mark.parametrize("kind,seed", [("related", 81), ("config1", 82)])
+def test_fastq_to_sam_equals_reference(pkg, tmp_path, kind, seed):
+    """The whole --sam-file run — FASTQ files -> reader -> GPU matching path -> host stages -> SAM text — against the
+    reference's own chain (alignToDatabase ... writeSAMOutputPairs, oracle/_ref) on the same reads, byte for byte, in one
+    batch and in three (--num-reads-at-once)."""
+    from kslam_b200 import slam
+    from test_sam_host import make_inputs
+    gb, go, rb, ro, quals, idb, ido = make_inputs(pkg, seed, n_pairs=600, kind=kind)
+    n = len(ro) - 1; mid = n // 2
+    fa = tmp_path / "db.fa"
+    with open(fa, "wb") as f:
+        for i in range(len(go) - 1):
+            f.write(b">g%d synthetic entry\n" % i + bytes(gb[int(go[i]):int(go[i + 1])]) + b"\n")
+    for k, (lo, hi) in enumerate(((0, mid), (mid, n))):
+        with open(tmp_path / f"R{k + 1}.fq", "wb") as f:
+            for i in range(lo, hi):
+                f.write(b"@r%d\n" % i + bytes(rb[int(ro[i]):int(ro[i + 1])]) + b"\n+\n" + bytes(quals[int(ro[i]):int(ro[i + 1])]) + b"\n")
+
+    def reference(lo, hi):
+        sel = list(range(lo, hi)) + list(range(mid + lo, mid + hi))
+        sb, so = T.concat([rb[int(ro[i]):int(ro[i + 1])] for i in sel])
+        sq, _ = T.concat([quals[int(ro[i]):int(ro[i + 1])] for i in sel])
+        R = T.Ref(gb, go, sb, so, T.default_params(report_cigar=1))
+        R.align_to_database(); R.screen_and_pair()
+        text, _ = T.ref_sam(R, sq, so)
+        R.close()
+        # the harness names reads r<local index>; the files name them r<global index>
+        for j in sorted(range(len(sel)), reverse=True):
+            text = text.replace(b"r%d\t" % j, b"R%d\t" % sel[j])
+        return text.replace(b"R", b"r")
+
+    for at_once in (mid, 200):
+        sam = tmp_path / f"out_{at_once}.sam"
+        st = slam.align_to_sam(pkg, [str(fa)], str(tmp_path / "R1.fq"), str(tmp_path / "R2.fq"), str(sam), reads_at_once=at_once, command_line="x")
+        body = b"".join(l for l in open(sam, "rb").read().splitlines(keepends=True) if not l.startswith(b"@"))
+        want = b"".join(reference(lo, min(lo + at_once, mid)) for lo in range(0, mid, at_once))
+        assert st["pairs"] == mid and len(want) > 10_000
+        assert body == want
