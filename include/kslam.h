@@ -196,7 +196,7 @@ typedef struct {
   uint8_t pseudo_assembly;          /* 1 unless --no-pseudo-assembly (Globals.h:36) */
   uint8_t report_cigar;             /* reportCigar: cigar + MD columns */
   uint8_t sam_xa;                   /* --sam-xa: primary line only */
-  uint8_t reserved;
+  uint8_t threads;                  /* host threads (stages are independent per read pair / per entry); 0 = all cores */
   double score_fraction_threshold;  /* --score-fraction-threshold, default 0.95 */
 } kslam_sam_params;
 typedef struct {

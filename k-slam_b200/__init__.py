@@ -83,7 +83,7 @@ class _ReadBatch(C.Structure):
 
 class SamParams(C.Structure):
     _fields_ = [("num_alignments", C.c_uint32), ("pseudo_assembly", C.c_uint8), ("report_cigar", C.c_uint8),
-                ("sam_xa", C.c_uint8), ("reserved", C.c_uint8), ("score_fraction_threshold", C.c_double)]
+                ("sam_xa", C.c_uint8), ("threads", C.c_uint8), ("score_fraction_threshold", C.c_double)]
 
 
 class _SamDb(C.Structure):
@@ -479,14 +479,14 @@ class SamWriter:
     (PairedOverlap.h:314-576, SAM.h). Host code: works without a GPU on any (sorted_overlaps, cigar_pool, pairs)."""
 
     def __init__(self, gen_bases, gen_offs, locus_tags, taxonomy_ids=None, num_alignments=10, score_fraction_threshold=0.95,
-                 pseudo_assembly=True, report_cigar=True, sam_xa=False):
+                 pseudo_assembly=True, report_cigar=True, sam_xa=False, threads=0):
         self.L = lib()
         self.gb, self.go = _u8(gen_bases), _u64(gen_offs)
         self.lt, self.lo = _cat([t if isinstance(t, bytes) else t.encode() for t in locus_tags])
         self.tax = None if taxonomy_ids is None else np.ascontiguousarray(taxonomy_ids, dtype=np.uint32)
         self.db = _SamDb(len(self.go) - 1, self.gb.ctypes.data, self.go.ctypes.data, self.lt.ctypes.data, self.lo.ctypes.data,
                          None if self.tax is None else self.tax.ctypes.data)
-        self.prm = SamParams(num_alignments, int(pseudo_assembly), int(report_cigar), int(sam_xa), 0, score_fraction_threshold)
+        self.prm = SamParams(num_alignments, int(pseudo_assembly), int(report_cigar), int(sam_xa), threads, score_fraction_threshold)
 
     def _take(self, ptr, n):
         try:

@@ -19,6 +19,7 @@
 #include <climits>
 #include <numeric>
 #include <string.h>
+#include <thread>
 #include <unordered_map>
 
 namespace {
@@ -31,6 +32,14 @@ struct POv {                       // PairedOverlap, PairedOverlap.h:32-58, over
   int32_t r1 = -1, r2 = -1;        // index into sorted_overlaps
 };
 struct ReadPair { uint32_t r1Pos = 0, r2Pos = 0; std::vector<POv> pairs; };
+
+// contiguous ranges of [0, n) on `threads` host threads (every stage below is independent per read pair or per entry)
+template <class F> void parallel_ranges(uint32_t threads, size_t n, F f) {
+  if (threads <= 1 || n < 2 * (size_t)threads) { f(0, (size_t)0, n); return; }
+  std::vector<std::thread> th;
+  for (uint32_t t = 0; t < threads; t++) th.emplace_back([=] { f(t, n * t / threads, n * (t + 1) / threads); });
+  for (auto &x : th) x.join();
+}
 
 struct Ctx {
   const kslam_sam_params *prm; const kslam_sam_db *db; const kslam_read_batch *reads; const kslam_pairs *in;
@@ -101,8 +110,10 @@ uint32_t max_allowed_insert_size(const std::vector<ReadPair> &reads) {          
   return std::isnan(result) ? UINT_MAX : result;
 }
 
-void screen_by_insert_size(std::vector<ReadPair> &reads, const kslam_overlap *ov, const uint32_t insertSize) {   // :396-436, replace = true
-  for (auto &read : reads) {
+void screen_by_insert_size(std::vector<ReadPair> &reads, const kslam_overlap *ov, const uint32_t insertSize, uint32_t threads) {   // :396-436, replace = true
+  parallel_ranges(threads, reads.size(), [&](uint32_t, size_t lo, size_t hi) {
+  for (size_t ri = lo; ri < hi; ri++) {
+    ReadPair &read = reads[ri];
     std::sort(read.pairs.begin(), read.pairs.end(), [](const POv &i, const POv &j) { return i.insertSize < j.insertSize; });
     auto cutoff = std::find_if(read.pairs.begin(), read.pairs.end(), [&](const POv &i) { return i.insertSize > insertSize; });
     auto cutoffPos = std::distance(read.pairs.begin(), cutoff);
@@ -121,19 +132,23 @@ void screen_by_insert_size(std::vector<ReadPair> &reads, const kslam_overlap *ov
       c.refStart = o2.ref_begin; c.refEnd = o2.ref_end;
     }
   }
+  });
 }
 
-void screen_by_score(std::vector<ReadPair> &reads, double fraction) {                 // PairedOverlap.h:361-390
-  for (auto &read : reads) {
+void screen_by_score(std::vector<ReadPair> &reads, double fraction, uint32_t threads) {   // PairedOverlap.h:361-390
+  parallel_ranges(threads, reads.size(), [&](uint32_t, size_t lo, size_t hi) {
+  for (size_t ri = lo; ri < hi; ri++) {
+    ReadPair &read = reads[ri];
     if (read.pairs.size() == 0) continue;
     std::sort(read.pairs.begin(), read.pairs.end(), [](const POv &i, const POv &j) { return i.combinedScore > j.combinedScore; });
     unsigned topScore = read.pairs[0].combinedScore;
     auto cutoff = std::find_if(read.pairs.begin(), read.pairs.end(), [&](const POv &i) { return i.combinedScore < topScore * fraction; });
     read.pairs.erase(cutoff, read.pairs.end());
   }
+  });
 }
 
-void pseudo_assembly(std::vector<ReadPair> &pairedAlignments) {                       // PairedOverlap.h:480-576
+void pseudo_assembly(std::vector<ReadPair> &pairedAlignments, uint32_t threads) {     // PairedOverlap.h:480-576
   struct coverage { int start = 0; int stop = 0; };
   struct entryAndOverlaps { uint32_t entryPos = 0; std::vector<std::pair<coverage, POv *>> reads; };
   std::unordered_map<uint32_t, entryAndOverlaps> entriesAndOverlaps;
@@ -144,7 +159,11 @@ void pseudo_assembly(std::vector<ReadPair> &pairedAlignments) {                 
       e.entryPos = overlap.entry;
       e.reads.push_back({c, &overlap});
     }
-  for (auto &entry : entriesAndOverlaps) {
+  std::vector<entryAndOverlaps *> entries;            // chains never cross entries: one entry per task
+  for (auto &entry : entriesAndOverlaps) entries.push_back(&entry.second);
+  parallel_ranges(threads, entries.size(), [&](uint32_t, size_t elo, size_t ehi) {
+  for (size_t ei = elo; ei < ehi; ei++) {
+    struct { entryAndOverlaps &second; } entry{*entries[ei]};
     std::sort(entry.second.reads.begin(), entry.second.reads.end(),
               [](const std::pair<coverage, POv *> &i, const std::pair<coverage, POv *> &j) { return i.first.start < j.first.start; });
     auto chainStart = entry.second.reads.begin();
@@ -184,6 +203,7 @@ void pseudo_assembly(std::vector<ReadPair> &pairedAlignments) {                 
     }
     (void)score;
   }
+  });
 }
 
 // ---- SAM.h ---------------------------------------------------------------------------------------------------
@@ -431,11 +451,20 @@ int kslam_sam_batch(const kslam_sam_params *prm, const kslam_sam_db *db, const k
     auto rp = per_read(pairs, (uint32_t)(reads->n_reads / 2));
     const uint32_t maxInsert = max_allowed_insert_size(rp);
     if (max_insert_size) *max_insert_size = maxInsert;
-    screen_by_insert_size(rp, pairs->sorted_overlaps, maxInsert);
-    screen_by_score(rp, prm->score_fraction_threshold);
-    if (prm->pseudo_assembly) { pseudo_assembly(rp); screen_by_score(rp, prm->score_fraction_threshold); }
+    uint32_t threads = prm->threads ? prm->threads : std::max(1u, std::thread::hardware_concurrency());
+    if (threads > 64) threads = 64;
+    screen_by_insert_size(rp, pairs->sorted_overlaps, maxInsert, threads);
+    screen_by_score(rp, prm->score_fraction_threshold, threads);
+    if (prm->pseudo_assembly) { pseudo_assembly(rp, threads); screen_by_score(rp, prm->score_fraction_threshold, threads); }
+    std::vector<std::string> parts(threads);
+    parallel_ranges(threads, rp.size(), [&](uint32_t t, size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; i++) write_pairs(parts[t], c, rp[i]);
+    });
     std::string out;
-    for (auto &read : rp) write_pairs(out, c, read);
+    size_t total = 0;
+    for (auto &p : parts) total += p.size();
+    out.reserve(total);
+    for (auto &p : parts) out += p;
     *text = dup_text(out);
     if (len) *len = out.size();
     return *text ? KSLAM_OK : KSLAM_ERR_NOMEM;
