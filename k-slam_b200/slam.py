@@ -41,10 +41,48 @@ def parse_fasta(paths):
 
 def align_to_sam(pkg, fasta_paths, r1, r2, sam_path, reads_at_once=10_000_000, num_alignments=10, score_fraction_threshold=0.95,
                  pseudo_assembly=True, sam_xa=False, min_alignment_score=0, command_line="", device=0, log=None):
-    """Returns a dict of counts and wall times per stage."""
+    """The batch loop as a three-stage pipeline, one host thread per stage (every heavy call is a C call that releases the
+    GIL): FASTQ ingest of batch i+2 | GPU matching of batch i+1 | host stages + SAM text + file write of batch i.
+    Batches are handed over as copies, so each stage owns its data. Returns counts and per-stage busy times."""
+    import queue
+    import threading
     t = {"ingest": 0.0, "gpu": 0.0, "sam": 0.0, "write": 0.0}
     gb, go, tags = parse_fasta(fasta_paths)
     stats = {"pairs": 0, "batches": 0, "sam_bytes": 0}
+    errs = []
+    q_reads, q_pairs = queue.Queue(maxsize=1), queue.Queue(maxsize=1)
+
+    def stage_ingest(rd):
+        try:
+            while not errs:
+                t0 = time.perf_counter()
+                b = rd.next(reads_at_once, copy=True)
+                t["ingest"] += time.perf_counter() - t0
+                q_reads.put(b)
+                if b is None:
+                    return
+        except Exception as e:   # noqa: BLE001
+            errs.append(e); q_reads.put(None)
+
+    def stage_gpu(al):
+        try:
+            import torch
+            torch.cuda.set_device(device)
+        except Exception:   # noqa: BLE001
+            pass
+        try:
+            while True:
+                b = q_reads.get()
+                if b is None or errs:
+                    q_pairs.put(None)
+                    return
+                t0 = time.perf_counter()
+                p = al.align_pair_batch(b.bases, b.offs, copy=True)
+                t["gpu"] += time.perf_counter() - t0
+                q_pairs.put((b, p))
+        except Exception as e:   # noqa: BLE001
+            errs.append(e); q_pairs.put(None)
+
     with pkg.Aligner(report_cigar=True, score_threshold=min_alignment_score, device=device) as al, \
             pkg.FastqReader(r1, r2) as rd, open(sam_path, "wb") as out:
         al.set_debug_taps(False)
@@ -52,21 +90,23 @@ def align_to_sam(pkg, fasta_paths, r1, r2, sam_path, reads_at_once=10_000_000, n
         w = pkg.SamWriter(gb, go, tags, num_alignments=num_alignments, score_fraction_threshold=score_fraction_threshold,
                           pseudo_assembly=pseudo_assembly, report_cigar=True, sam_xa=sam_xa)
         out.write(w.header(command_line))
+        th = [threading.Thread(target=stage_ingest, args=(rd,)), threading.Thread(target=stage_gpu, args=(al,))]
+        [x.start() for x in th]
         while True:
-            t0 = time.perf_counter()
-            b = rd.next(reads_at_once, copy=False)
-            t1 = time.perf_counter()
-            if b is None:
+            item = q_pairs.get()
+            if item is None:
                 break
-            p = al.align_pair_batch(b.bases, b.offs, copy=False)
-            t2 = time.perf_counter()
+            b, p = item
+            t0 = time.perf_counter()
             text, _ = w.batch(b.bases, b.offs, b.quals, b.qual_offs, b.ids, b.id_offs, p.sorted_overlaps, p.cigar_pool, p.pairs)
-            t3 = time.perf_counter()
+            t1 = time.perf_counter()
             out.write(text)
-            t4 = time.perf_counter()
-            t["ingest"] += t1 - t0; t["gpu"] += t2 - t1; t["sam"] += t3 - t2; t["write"] += t4 - t3
+            t["sam"] += t1 - t0; t["write"] += time.perf_counter() - t1
             stats["pairs"] += b.n_r1; stats["batches"] += 1; stats["sam_bytes"] += len(text)
             if log:
-                log(f"batch {stats['batches']}: {b.n_r1} pairs, ingest {t1 - t0:.2f}s gpu {t2 - t1:.2f}s sam {t3 - t2:.2f}s")
+                log(f"batch {stats['batches']}: {b.n_r1} pairs done")
+        [x.join() for x in th]
+    if errs:
+        raise errs[0]
     stats["seconds"] = t
     return stats

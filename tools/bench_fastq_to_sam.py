@@ -29,4 +29,4 @@ for rep in range(2):
     t0 = time.time()
     st = slam.align_to_sam(pkg, [fa], paths[0], paths[1], os.path.join(d, "out.sam"), reads_at_once=at_once)
     dt = time.time() - t0
-    print(f"run {rep}: {pairs} pairs in {dt:.2f}s ({pairs / dt * 60 / 1e6:.1f} M pairs/min incl. FASTA parse + index build) stages {st}")
+    print(f"run {rep}: {pairs} pairs in {dt:.2f}s ({pairs / dt * 60 / 1e6:.1f} M pairs/min incl. FASTA parse + index build), {st['batches']} batches, stage busy times {st['seconds']}")
