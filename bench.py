@@ -337,13 +337,15 @@ def main():
     # ---- e2e: host buffers in, results back on the host ------------------------------------------
     # The reference-facing call with HOST buffers: kslam_align_pair_batch = the body of the batch loop (SLAM.h:209-214),
     # H2D of the reads and D2H of everything the loop keeps inside the timed region. Batches are streamed through TWO
-    # contexts on the same GPU (include/kslam.h: "two per GPU to double-buffer"), each driven by its own host thread, so
-    # one batch's PCIe copies overlap the other's kernels. The partitioned workload runs one context (its NCCL
-    # collectives are issued in program order).
+    # contexts on the same GPU (include/kslam.h: "two per GPU to double-buffer"), each driven by its own host thread. A
+    # batch is kslam_upload_reads (H2D) | kslam_align_resident + kslam_pair_batch (kernels) | kslam_fetch_pairs (D2H), and
+    # a host mutex around the kernel phase hands the GPU from one context to the other, so the copies of one batch always
+    # run under the kernels of the other. The partitioned workload runs one context (its NCCL collectives are issued in
+    # program order).
     depth = 1 if partitioned else 2
     ctxs = [al]
     if depth == 2:
-        al2 = pkg.Aligner(report_cigar=want_cigar, device=local)
+        al2 = pkg.Aligner(report_cigar=want_cigar, device=local, )
         al2.set_debug_taps(False)
         al2.load_genomes(gb, go)
         ctxs.append(al2)
@@ -355,12 +357,23 @@ def main():
                 last[0] = step_e2e()[1]
             return
         errs = []
+        gpu_turn = threading.Lock()
+        trace = bool(os.environ.get("KSLAM_BENCH_TRACE"))
 
         def worker(k):
             try:
                 torch.cuda.set_device(local)
                 for _b in range(k, n_batches, depth):
-                    last[k] = ctxs[k].align_pair_batch(rb_host, ro, copy=False)
+                    t0 = time.perf_counter()
+                    ctxs[k].upload_reads(rb_host, ro)
+                    t1 = time.perf_counter()
+                    with gpu_turn:
+                        t2 = time.perf_counter()
+                        ctxs[k].align_resident(fetch=False); ctxs[k].pair_batch(fetch=False)
+                        t3 = time.perf_counter()
+                    last[k] = ctxs[k].fetch_pairs(copy=False)
+                    if trace:
+                        log(f"[e2e ctx{k} batch{_b}] upload {t1 - t0:.3f}s wait {t2 - t1:.3f}s kernels {t3 - t2:.3f}s fetch {time.perf_counter() - t3:.3f}s")
             except Exception as e:   # noqa: BLE001
                 errs.append(e)
         th = [threading.Thread(target=worker, args=(k,)) for k in range(depth)]
@@ -434,7 +447,7 @@ def main():
                                        f"and of raw matches (NCCL)" if partitioned else f"read pairs, {world} ranks, no collective"),
                           "l2": "inputs larger than L2 (3.8 GB+ of k-mer records per step)", "report_cigar": want_cigar},
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "call": "kslam_align_pair_batch (host buffers in, pair-sorted overlaps + pairs back on the host)",
+                       "call": "kslam_upload_reads + kslam_align_resident + kslam_pair_batch + kslam_fetch_pairs (host buffers in, pair-sorted overlaps + pairs back on the host)",
                        "contexts_per_gpu": depth},
                "gpu_launches": int(launches),
                "clocks": clocks,

@@ -50,7 +50,9 @@ typedef struct {
   int32_t device;                                /* CUDA device ordinal */
   uint32_t genome_gap;                           /* k/2 = 16 (SLAM.h:65); 0 = default */
   uint32_t max_cigar_ops;                        /* per-alignment cigar capacity, 0 = default 32 */
-  uint32_t reserved1;
+  uint32_t stream_priority;                      /* 0 = default; 1 = the ctx stream gets the highest CUDA stream priority: of two
+                                                    contexts double-buffering on one GPU, give it to one so that its kernels run
+                                                    first and the other fills the gaps its PCIe copies leave */
 } kslam_params;
 
 /* KMerAndData, KMer.h:58-116. id_flags: bits 0-29 id, bit 30 revComp, bit 31 isFromGB. */
@@ -123,6 +125,12 @@ int kslam_align_resident(kslam_ctx *ctx, int fetch_results, kslam_alignments *ou
 /* screenOverlapsByScoreThreshold (Overlap.h:329-341) + getPairedOverlaps (PairedOverlap.h:243-272) on
  * the alignments of the last batch (device-resident). */
 int kslam_pair_batch(kslam_ctx *ctx, int fetch_results, kslam_pairs *out /* may be NULL */);
+
+/* Copy the results of the last kslam_pair_batch(fetch_results = 0) to the host. Splitting a batch into kslam_upload_reads
+ * (H2D), kslam_align_resident + kslam_pair_batch (kernels) and kslam_fetch_pairs (D2H) lets a caller that double-buffers
+ * with two contexts hand the GPU from one to the other with a host mutex around the kernel phase, so that the copies
+ * of one batch always run under the kernels of the other (bench.py's e2e leg does exactly that). */
+int kslam_fetch_pairs(kslam_ctx *ctx, kslam_pairs *out);
 
 /* The body of the reference's batch loop in one call (SLAM.h:209-214: alignToDatabase, score screen, getPairedOverlaps):
  * same results as kslam_align_batch + kslam_pair_batch, but the unsorted alignment vector — which the loop discards

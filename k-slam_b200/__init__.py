@@ -49,7 +49,7 @@ class Params(C.Structure):
     _fields_ = [("match", C.c_uint8), ("mismatch", C.c_uint8), ("gap_open", C.c_uint8), ("gap_extend", C.c_uint8),
                 ("score_threshold", C.c_uint16), ("report_cigar", C.c_uint8), ("reserved0", C.c_uint8),
                 ("device", C.c_int32), ("genome_gap", C.c_uint32), ("max_cigar_ops", C.c_uint32),
-                ("reserved1", C.c_uint32)]
+                ("stream_priority", C.c_uint32)]
 
 
 class _Alignments(C.Structure):
@@ -127,6 +127,7 @@ def lib():
     L.kslam_align_pair_batch.argtypes = [vp, u64, vp, vp, C.POINTER(_Pairs)]
     L.kslam_align_resident.argtypes = [vp, i32, C.POINTER(_Alignments)]
     L.kslam_pair_batch.argtypes = [vp, i32, C.POINTER(_Pairs)]
+    L.kslam_fetch_pairs.argtypes = [vp, C.POINTER(_Pairs)]
     L.kslam_ssw_batch.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
     L.kslam_ssw_upload.argtypes = [vp, u64, vp, vp, vp, vp]
     L.kslam_ssw_resident.argtypes = [vp, vp, vp]
@@ -204,10 +205,10 @@ class Aligner:
     """One matching context on one GPU (one kslam_ctx)."""
 
     def __init__(self, match=2, mismatch=3, gap_open=5, gap_extend=2, score_threshold=0, report_cigar=False,
-                 device=0, genome_gap=16, max_cigar_ops=32):
+                 device=0, genome_gap=16, max_cigar_ops=32, stream_priority=0):
         self.L = lib()
         self.params = Params(match, mismatch, gap_open, gap_extend, score_threshold, int(bool(report_cigar)), 0,
-                             device, genome_gap, max_cigar_ops, 0)
+                             device, genome_gap, max_cigar_ops, stream_priority)
         h = C.c_void_p()
         rc = self.L.kslam_create(C.byref(self.params), C.byref(h))
         if rc != 0:
@@ -329,6 +330,12 @@ class Aligner:
         self._check(self.L.kslam_pair_batch(self.h, int(fetch), C.byref(out)), "kslam_pair_batch")
         if not fetch:
             return int(out.n_pairs)
+        return self._pairs(out, copy)
+
+    def fetch_pairs(self, copy=True) -> "Pairs":
+        """D2H of the last pair_batch(fetch=False)."""
+        out = _Pairs()
+        self._check(self.L.kslam_fetch_pairs(self.h, C.byref(out)), "kslam_fetch_pairs")
         return self._pairs(out, copy)
 
     def _pairs(self, out, copy):

@@ -24,6 +24,15 @@ float tm_ms(cudaEvent_t a, cudaEvent_t b) {
   return ms;
 }
 
+__global__ void k_read_small(uint32_t *__restrict__ dst_host, const uint32_t *__restrict__ src, uint32_t n_words) {
+  for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) dst_host[i] = src[i];
+  __threadfence_system();
+}
+void read_small(kslam_ctx *c, void *host_pinned, const void *dev, size_t bytes) {
+  k_read_small<<<1, 32, 0, c->stream>>>((uint32_t *)host_pinned, (const uint32_t *)dev, (uint32_t)(bytes / 4));
+  CUDA_TRY(cudaGetLastError());
+}
+
 int api_fail(kslam_ctx *c, int code, const std::string &msg) {
   if (c) c->err = msg; else g_create_err = msg;
   return code;
@@ -69,7 +78,11 @@ int kslam_create(const kslam_params *params, kslam_ctx **out) {
     c->num_sms = prop.multiProcessorCount;
     memset(&c->tm, 0, sizeof c->tm);
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    if (params->stream_priority) {
+      int lo = 0, hi = 0;
+      CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));     // numerically lower = higher priority
+      CUDA_TRY(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+    } else CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     c->counters.reserve(64 * 8);
     c->h_counters.reserve(64 * 8);
   } catch (const CudaError &e) {
@@ -261,7 +274,7 @@ int kslam_upload_reads(kslam_ctx *c, uint64_t n, const char *bases, const uint64
   if (!c->genomes_loaded) return fail(c, KSLAM_ERR_STATE, "kslam_load_genomes first");
   if (!offs || (n && !bases && offs[n] != offs[0])) return fail(c, KSLAM_ERR_ARG, "null read buffers");
   if (n >= (1ull << 30)) return fail(c, KSLAM_ERR_ARG, "more than 2^30 reads (KMer.h:65-66)");
-  c->reads_loaded = false; c->aligned = false;
+  c->reads_loaded = false; c->aligned = false; c->paired = false;
   c->ev_used = 0;
   cudaEvent_t e0 = tm_mark(c);
   pack_sequences(c, c->reads, n, bases, offs, 1, true);
@@ -311,34 +324,51 @@ int kslam_part_finish(kslam_ctx *c, uint64_t n_matches, uint32_t read_id_base, i
   API_END(c)
 }
 
+// D2H of the pair stage's results (pair-sorted overlaps, dense CIGAR pool, pairs) into the ctx's pinned buffers
+static void fetch_pairs(kslam_ctx *c, kslam_pairs *out) {
+  const bool with_cig = c->prm.report_cigar && c->n_sorted && c->cig_dense.p;
+  c->h_ov_sorted.reserve((size_t)c->n_sorted * sizeof(kslam_overlap) + 64);
+  c->h_pairs.reserve((size_t)c->n_pairs * sizeof(kslam_pair) + 64);
+  if (c->n_sorted) CUDA_TRY(cudaMemcpyAsync(c->h_ov_sorted.p, c->ov_sorted.p, (size_t)c->n_sorted * sizeof(kslam_overlap), cudaMemcpyDeviceToHost, c->stream));
+  if (c->n_pairs) CUDA_TRY(cudaMemcpyAsync(c->h_pairs.p, c->pairs.p, (size_t)c->n_pairs * sizeof(kslam_pair), cudaMemcpyDeviceToHost, c->stream));
+  if (with_cig) {
+    c->h_cig_sorted.reserve((size_t)c->n_cig_words * 4 + 64);
+    if (c->n_cig_words) CUDA_TRY(cudaMemcpyAsync(c->h_cig_sorted.p, c->cig_dense.p, (size_t)c->n_cig_words * 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (out) {
+    out->n_sorted = c->n_sorted; out->n_pairs = c->n_pairs;
+    out->sorted_overlaps = c->h_ov_sorted.as<kslam_overlap>(); out->pairs = c->h_pairs.as<kslam_pair>();
+    out->n_cigar_words = with_cig ? c->n_cig_words : 0;
+    out->cigar_pool = with_cig ? c->h_cig_sorted.as<uint32_t>() : nullptr;
+  }
+}
+
 int kslam_pair_batch(kslam_ctx *c, int fetch, kslam_pairs *out) {
   API_BEGIN(c)
   if (!c->aligned) return fail(c, KSLAM_ERR_STATE, "kslam_align_batch first");
   c->ev_used = 0;
+  c->paired = false;
   cudaEvent_t e0 = tm_mark(c);
   pair_overlaps(c);
   cudaEvent_t e1 = tm_mark(c);
-  const bool with_cig = c->prm.report_cigar && c->n_sorted && c->cig_dense.p;
-  if (fetch) {
-    c->h_ov_sorted.reserve((size_t)c->n_sorted * sizeof(kslam_overlap) + 64);
-    c->h_pairs.reserve((size_t)c->n_pairs * sizeof(kslam_pair) + 64);
-    if (c->n_sorted) CUDA_TRY(cudaMemcpyAsync(c->h_ov_sorted.p, c->ov_sorted.p, (size_t)c->n_sorted * sizeof(kslam_overlap), cudaMemcpyDeviceToHost, c->stream));
-    if (c->n_pairs) CUDA_TRY(cudaMemcpyAsync(c->h_pairs.p, c->pairs.p, (size_t)c->n_pairs * sizeof(kslam_pair), cudaMemcpyDeviceToHost, c->stream));
-    if (with_cig) {
-      c->h_cig_sorted.reserve((size_t)c->n_cig_words * 4 + 64);
-      if (c->n_cig_words) CUDA_TRY(cudaMemcpyAsync(c->h_cig_sorted.p, c->cig_dense.p, (size_t)c->n_cig_words * 4, cudaMemcpyDeviceToHost, c->stream));
-    }
-  }
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->tm.ms_pair = tm_ms(e0, e1);
   c->tm.n_pairs = c->n_pairs;
-  if (out) {
-    out->n_sorted = c->n_sorted; out->n_pairs = c->n_pairs;
-    out->sorted_overlaps = fetch ? c->h_ov_sorted.as<kslam_overlap>() : nullptr;
-    out->pairs = fetch ? c->h_pairs.as<kslam_pair>() : nullptr;
-    out->n_cigar_words = (fetch && with_cig) ? c->n_cig_words : 0;
-    out->cigar_pool = (fetch && with_cig) ? c->h_cig_sorted.as<uint32_t>() : nullptr;
+  c->paired = true;
+  if (fetch) fetch_pairs(c, out);
+  else if (out) {
+    out->n_sorted = c->n_sorted; out->n_pairs = c->n_pairs; out->sorted_overlaps = nullptr; out->pairs = nullptr;
+    out->n_cigar_words = 0; out->cigar_pool = nullptr;
   }
+  return KSLAM_OK;
+  API_END(c)
+}
+
+int kslam_fetch_pairs(kslam_ctx *c, kslam_pairs *out) {
+  API_BEGIN(c)
+  if (!c->paired) return fail(c, KSLAM_ERR_STATE, "kslam_pair_batch first");
+  fetch_pairs(c, out);
   return KSLAM_OK;
   API_END(c)
 }

@@ -88,7 +88,7 @@ struct kslam_ctx {
   bool keep_taps = true;
 
   PackedSeqs genomes, reads;
-  bool genomes_loaded = false, reads_loaded = false, aligned = false;
+  bool genomes_loaded = false, reads_loaded = false, aligned = false, paired = false;
   DevBuf g_keys;   // u64 sorted genome k-mers
   DevBuf g_vals;   // u64 id_flags | offset<<32, same order
   uint64_t n_gk = 0;
@@ -192,6 +192,12 @@ int api_fail(kslam_ctx *c, int code, const std::string &msg);
     cudaGetLastError();                                                                         \
     return api_fail((ctx), e.e == cudaErrorMemoryAllocation ? KSLAM_ERR_NOMEM : KSLAM_ERR_CUDA, buf); \
   } catch (const std::exception &e) { return api_fail((ctx), KSLAM_ERR_NOMEM, e.what()); }
+
+// api.cu: read a few words of device memory into PINNED host memory without the copy engine — a one-warp kernel
+// stores them through the PCIe mapping of the pinned allocation (UVA). The D2H copy engine is a FIFO: while another
+// context on the same GPU drains an 8 GB result buffer, a 4-byte cudaMemcpyAsync counter read waits behind it (measured:
+// +0.2 s per config-2 batch when two contexts double-buffer). Enqueues only; the caller synchronises the stream.
+void read_small(kslam_ctx *c, void *host_pinned, const void *dev, size_t bytes);
 
 // event-based stage timing
 cudaEvent_t tm_mark(kslam_ctx *c);

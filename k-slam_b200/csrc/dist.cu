@@ -89,7 +89,7 @@ static void bucket_records(kslam_ctx *c, const Rec16 *in, uint64_t n, const uint
   if (blocks > maxb) blocks = maxb;
   if (n) { k_bucket_count<MODE><<<(unsigned)blocks, 256, 0, st>>>(in, n, d_bounds, P, d_counts); c->launches++; }
   uint64_t *h_counts = h + DIST_MAX_PARTS;
-  CUDA_TRY(cudaMemcpyAsync(h_counts, d_counts, P * 8, cudaMemcpyDeviceToHost, st));
+  read_small(c, h_counts, d_counts, P * 8);
   CUDA_TRY(cudaStreamSynchronize(st));
   uint64_t *h_cur = h + 2 * DIST_MAX_PARTS, run = 0;
   for (uint32_t p = 0; p < P; p++) { counts_host[p] = h_counts[p]; h_cur[p] = run; run += h_counts[p]; }
@@ -188,7 +188,7 @@ int kslam_load_genomes_part(kslam_ctx *c, uint64_t n, const char *bases, const u
         CUDA_TRY(cudaGetLastError());
       }
       if (pass == 0) {
-        CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+        read_small(c, h_cnt, d_cnt, 8);
         CUDA_TRY(cudaStreamSynchronize(st));
         c->n_gk = h_cnt[0];
         if (!c->n_gk) break;

@@ -231,7 +231,7 @@ uint64_t run_join(kslam_ctx *c, const Rec16 *R, uint64_t n_r, bool match, DevBuf
                                                             c->reads.offs.as<uint64_t>(), outbuf.as<Rec16>(), cap, d_cnt, bias, low_mask);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+    read_small(c, h_cnt, d_cnt, 8);
     CUDA_TRY(cudaStreamSynchronize(st));
     if (h_cnt[0] <= cap) break;
     if (attempt == 1) throw CudaError{cudaErrorMemoryAllocation, "seed buffer overflow after regrow", __FILE__, __LINE__};
@@ -293,7 +293,7 @@ void seed_sort_unique(kslam_ctx *c) {
     k_unique_flags<<<(unsigned)blocks, 256, 0, st>>>(cur, c->n_raw, keep);
     c->launches++;
     exclusive_scan_u32(c, keep, pos, c->n_raw, (uint64_t *)(d_cnt + 1));
-    CUDA_TRY(cudaMemcpyAsync(h_cnt + 1, d_cnt + 1, 8, cudaMemcpyDeviceToHost, st));
+    read_small(c, h_cnt + 1, d_cnt + 1, 8);
     CUDA_TRY(cudaStreamSynchronize(st));
     c->n_seeds = h_cnt[1];
     c->seeds.reserve((size_t)c->n_seeds * sizeof(kslam_seed) + 64);

@@ -189,7 +189,7 @@ uint64_t extract_read_kmers_filtered(kslam_ctx *c, const PackedSeqs &s, DevBuf &
         s.word_off.as<uint64_t>(), s.n, c->bitmap.as<uint32_t>(), c->filter_bits, outbuf.as<Rec16>(), d_cnt, id_base, cap);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, c->stream));
+    read_small(c, h_cnt, d_cnt, 8);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (h_cnt[0] <= cap) break;
     if (attempt == 1) throw CudaError{cudaErrorMemoryAllocation, "read k-mer buffer overflow after regrow", __FILE__, __LINE__};

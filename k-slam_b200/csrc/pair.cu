@@ -13,15 +13,19 @@ __global__ void __launch_bounds__(256)
 k_pair_keys(const kslam_overlap *__restrict__ ov, uint32_t n, uint32_t mid, uint32_t thr, uint32_t bias,
             Rec16 *__restrict__ keys, uint32_t *__restrict__ n_pass) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const kslam_overlap o = ov[i];
-  Rec16 k;
-  if (o.sw_score >= thr) {              // Overlap.h:335: removed when sw_score < scoreThreshold
-    k.key = ((uint64_t)(o.read % mid) << 32) | o.entry;
-    k.val = ((uint64_t)(uint32_t)(o.rel + (int32_t)bias) << 32) | i;
-    atomicAdd(n_pass, 1u);
-  } else { k.key = ~0ull; k.val = ((uint64_t)0xffffffffu << 32) | i; }
-  keys[i] = k;
+  bool pass = false;
+  if (i < n) {
+    const kslam_overlap o = ov[i];
+    Rec16 k;
+    pass = o.sw_score >= thr;           // Overlap.h:335: removed when sw_score < scoreThreshold
+    if (pass) {
+      k.key = ((uint64_t)(o.read % mid) << 32) | o.entry;
+      k.val = ((uint64_t)(uint32_t)(o.rel + (int32_t)bias) << 32) | i;
+    } else { k.key = ~0ull; k.val = ((uint64_t)0xffffffffu << 32) | i; }
+    keys[i] = k;
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, pass);     // one atomic per warp
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_pass, (uint32_t)__popc(m));
 }
 
 __global__ void __launch_bounds__(256)
@@ -134,7 +138,7 @@ void pair_overlaps(kslam_ctx *c) {
   Rec16 *a = c->pair_keys.as<Rec16>(), *b = c->pair_keys2.as<Rec16>();
   Rec16 *cur = radix_sort(c, a, b, n, 1, 32, 64, &passes);       // rel (stable: index order kept on ties)
   cur = radix_sort(c, cur, cur == a ? b : a, n, 0, 0, 64, &passes);  // entry, then pair id
-  CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, st));
+  read_small(c, h_cnt, d_cnt, 4);
   CUDA_TRY(cudaStreamSynchronize(st));
   const uint32_t ns = h_cnt[0];
   c->n_sorted = ns;
@@ -149,7 +153,7 @@ void pair_overlaps(kslam_ctx *c) {
   unsigned long long *d_tot = c->counters.as<unsigned long long>() + 30;
   exclusive_scan_u32(c, cnt, pos, ns, (uint64_t *)d_tot);
   unsigned long long *h_tot = c->h_counters.as<unsigned long long>() + 30;
-  CUDA_TRY(cudaMemcpyAsync(h_tot, d_tot, 8, cudaMemcpyDeviceToHost, st));
+  read_small(c, h_tot, d_tot, 8);
   CUDA_TRY(cudaStreamSynchronize(st));
   c->n_pairs = h_tot[0];
   if (c->n_pairs) {

@@ -244,8 +244,9 @@ Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, u
     k_rs_scan_hist<<<1, 256, 0, st>>>(ghist, plan.n_passes, n, trivial);
     c->launches += 2;
   }
-  uint32_t h_trivial[8];
-  CUDA_TRY(cudaMemcpyAsync(h_trivial, trivial, sizeof(h_trivial), cudaMemcpyDeviceToHost, st));
+  c->h_counters.reserve(64 * 8);
+  uint32_t *h_trivial = c->h_counters.as<uint32_t>() + 112;     // 8 words of the ctx's pinned block
+  read_small(c, h_trivial, trivial, 8 * sizeof(uint32_t));
   CUDA_TRY(cudaStreamSynchronize(st));
   for (uint32_t p = 0; p < plan.n_passes; p++) {
     if (h_trivial[p]) continue;   // every record has the same digit: the pass would be the identity

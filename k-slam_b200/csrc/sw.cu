@@ -490,7 +490,7 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
                                  big_per_thread - (size_t)arr_cap * 12, 1, cig, sc.cigar_cap, rev && unflip, &overflow);
         }
         if (len == -3) {
-          if (mode < 2) { deferred = true; retry_list[atomicAdd(retry_count, 1u)] = idx; }
+          if (mode < 2) { deferred = true; retry_list[list_slot(retry_count)] = idx; }
           else o.flags |= KSLAM_FLAG_UNDEFINED;   // beyond even the big scratch: report, never guess
         } else if (len == -2) { o.cigar_len = 0; o.sw_score = 0; }           // ssw.c:941-944
         else if (len == -1) o.flags |= KSLAM_FLAG_UNDEFINED;
@@ -613,7 +613,7 @@ __device__ __forceinline__ void enlist(const SwPlanes &pl, const SwTask &t, uint
   if (cls == SWC_NONE) {
     SwRes o; o.score = 0; o.ref_end = -1; o.read_end = 0; o.ref_begin = -1; o.read_begin = 0; o.flags = 0; o.pad0 = o.pad1 = 0;
     res[i] = o;
-  } else if (cls == SWC_SLOW) slow_list[atomicAdd(&counts[CNT_SLOW], 1u)] = i;
+  } else if (cls == SWC_SLOW) slow_list[list_slot(&counts[CNT_SLOW])] = i;
   else if (t.flags & SWT_BAND) {
     tier = SWT_TIER_SWEEP;
     if (tiers) {
@@ -621,7 +621,7 @@ __device__ __forceinline__ void enlist(const SwPlanes &pl, const SwTask &t, uint
       const uint32_t tt = tier_of_width((int32_t)t.m, (int32_t)t.n, L, sc, max_tier);
       if (tt != SWT_TIER_NONE) { tier = tt; res[i].score = L; }
     }
-  } else { const uint32_t k = atomicAdd(&counts[CNT_FULL], 1u); full_keys[k].key = t.n; full_keys[k].val = i; }
+  } else { const uint32_t k = list_slot(&counts[CNT_FULL]); full_keys[k].key = t.n; full_keys[k].val = i; }
   tier_f[i] = (uint8_t)tier;
   count_tier(tier, counts);
 }
@@ -706,7 +706,7 @@ k_sw_rev_lists(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
     const int32_t rows = r.read_end + 1, cols = r.ref_end + 1;
     if (t.flags & SWT_BAND) tier = tier_of_width(rows, cols, r.score, sc, max_tier);
     if (tier != SWT_TIER_NONE && tier < min_tier) tier = min_tier;
-    if (tier == SWT_TIER_NONE) { const uint32_t k = atomicAdd(&counts[CNT_FULL], 1u); full_keys[k].key = (uint64_t)cols; full_keys[k].val = i; }
+    if (tier == SWT_TIER_NONE) { const uint32_t k = list_slot(&counts[CNT_FULL]); full_keys[k].key = (uint64_t)cols; full_keys[k].val = i; }
   }
   tier_r[i] = (uint8_t)tier;
   count_tier(tier, counts);
@@ -725,7 +725,7 @@ k_sw_make_items(const Rec16 *__restrict__ sorted, uint32_t n_fast, uint2 *__rest
   if (2 * w + 1 < n_fast) {
     const Rec16 b = sorted[2 * w + 1];
     if (b.key == a.key) i0.y = (uint32_t)b.val;
-    else items[W + atomicAdd(extra, 1u)] = make_uint2((uint32_t)b.val, (uint32_t)b.val);
+    else items[W + list_slot(extra)] = make_uint2((uint32_t)b.val, (uint32_t)b.val);
   }
   items[w] = i0;
 }
@@ -802,7 +802,7 @@ static SwScore make_score(const kslam_ctx *c) {
 }
 
 static uint32_t read_count(kslam_ctx *c, uint32_t *d_counts, uint32_t *h_counts, int which) {
-  CUDA_TRY(cudaMemcpyAsync(h_counts + which, d_counts + which, 4, cudaMemcpyDeviceToHost, c->stream));
+  read_small(c, h_counts + which, d_counts + which, 4);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return h_counts[which];
 }
@@ -827,7 +827,7 @@ static void make_tier_lists(kslam_ctx *c, uint32_t n, const uint8_t *tier, uint3
   k_tier_scatter<<<(n + 255) / 256, 256, 0, st>>>(tier, n, d_counts, d_counts + CNT_CUR, c->sw->lists.as<uint32_t>());
   c->launches++;
   CUDA_TRY(cudaGetLastError());
-  CUDA_TRY(cudaMemcpyAsync(h_counts + CNT_TIER, d_counts + CNT_TIER, 5 * 4, cudaMemcpyDeviceToHost, st));
+  read_small(c, h_counts + CNT_TIER, d_counts + CNT_TIER, 5 * 4);
   CUDA_TRY(cudaStreamSynchronize(st));
   for (int t = 0; t < 5; t++) cnt[t] = h_counts[CNT_TIER + t];
 }
@@ -958,7 +958,7 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
   k_sw_cells<<<c->num_sms * 2, 256, 0, st>>>(tasks, res, tier_f, tier_r, n, d_cells);
   c->launches++;
   unsigned long long *h_cells = c->h_counters.as<unsigned long long>() + 8;
-  CUDA_TRY(cudaMemcpyAsync(h_cells, d_cells, 24, cudaMemcpyDeviceToHost, st));
+  read_small(c, h_cells, d_cells, 24);
   CUDA_TRY(cudaStreamSynchronize(st));
   c->tm.sw_cells_forward = h_cells[0]; c->tm.sw_cells_reverse = h_cells[1]; c->tm.sw_cells_computed = h_cells[2];
   c->tm.ms_sw_forward = tm_ms(e1, e2);
@@ -1015,7 +1015,7 @@ static void compact_cigars(kslam_ctx *c, uint32_t n) {
   unsigned long long *d_cnt = c->counters.as<unsigned long long>() + 3, *h_cnt = c->h_counters.as<unsigned long long>() + 3;
   k_cigar_lens<<<(n + 255) / 256, 256, 0, st>>>(c->ov.as<kslam_overlap>(), n, lens);
   exclusive_scan_u32(c, lens, offs, n, (uint64_t *)d_cnt);
-  CUDA_TRY(cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+  read_small(c, h_cnt, d_cnt, 8);
   CUDA_TRY(cudaStreamSynchronize(st));
   c->n_cig_words = h_cnt[0];
   c->cig_dense.reserve((size_t)c->n_cig_words * 4 + 64);

@@ -39,6 +39,16 @@ template <int W> struct BandSmem {
 
 __device__ __forceinline__ int32_t ceil_div_pos(int32_t a, int32_t b) { return (a + b - 1) / b; }
 
+// Slot reservation in an append-only work list from divergent code: the lanes that are here together take one atomic
+// (millions of single-lane atomics on ONE counter serialise in L2: 12 ms for the 25 M full-matrix fallbacks of config 2).
+__device__ __forceinline__ uint32_t list_slot(uint32_t *counter) {
+  const uint32_t peers = __activemask(), lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  return base + __popc(peers & ((1u << lane) - 1u));
+}
+
 // 32 two-bit codes of `plane` starting at base p of the sequence that begins at word w_word (p may be negative or run
 // past the window: those lanes are masked by the caller; guard words keep the reads inside the allocation)
 __device__ __forceinline__ uint64_t bits_at(const uint64_t *__restrict__ plane, uint64_t w_word, int32_t p) {
@@ -277,7 +287,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
         res[idx].read_begin = r0.read_end - (int32_t)rrow;
         res[idx].flags = r0.flags | SWR_REV_TIER(SWR_TIER_OF_W(W));
       } else {                      // cannot happen when the bound holds; never guess: hand over to the full kernel
-        const uint32_t k = atomicAdd(fb_count, 1u);
+        const uint32_t k = list_slot(fb_count);
         fb_keys[k].key = (uint64_t)(r0.ref_end + 1); fb_keys[k].val = idx;
       }
     } else {
@@ -293,9 +303,9 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
         res[idx] = o;
       } else if (MODE == 0 && next_list && S > 0 && rows[al] + cols[al] - 2 * a + 1 <= SWB_MAXW) {
         res[idx].score = S;         // lower bound: every alignment scoring >= S lies in [-(m - a), n - a]
-        next_list[atomicAdd(next_count, 1u)] = idx;
+        next_list[list_slot(next_count)] = idx;
       } else {
-        const uint32_t k = atomicAdd(fb_count, 1u);
+        const uint32_t k = list_slot(fb_count);
         fb_keys[k].key = (uint64_t)(al ? tb.n : ta.n); fb_keys[k].val = idx;
       }
     }
