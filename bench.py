@@ -189,7 +189,7 @@ def run_config3(args, pkg):
             key = "cigar" if cigar else "score_only"
             row[key] = {"gcups": 150.0 * window * n / t / 1e9, "ms": t * 1e3, "M_pairs_per_min": n / t * 60 / 1e6,
                         "tiers": {k: tm[k] for k in ("n_sw_tier8", "n_sw_tier16", "n_sw_tier32", "n_sw_tier64", "n_sw_sweep32", "n_sw_fast", "n_sw_slow")},
-                        "int_pipe_frac": 3.5 * tm["sw_cells_computed"] / ((tm["ms_sw_forward"] + tm["ms_sw_reverse"]) / 1e3) / int_peak}
+                        "int_pipe_frac": 3.0 * tm["sw_cells_computed"] / ((tm["ms_sw_forward"] + tm["ms_sw_reverse"]) / 1e3) / int_peak}
         if not args.no_cpu_baseline and T.have_ref():
             cs = args.cpu_sample or 200_000
             P = T.default_params(report_cigar=1)
@@ -427,17 +427,18 @@ def main():
                     "peak_source": peak_src,
                     "share_of_step": ms["ms_sort"] / (t_res / args.steps * 1e3),
                     "note": f"algorithmic 32 B/record/pass; duration = (sort stage incl. histogram)/{passes_kmer} passes, CUDA events on the ctx stream"}
-        # SW sweeps (k_sw_band / k_sw_fast): integer-pipe bound. 7 ALU thread-ops (1 PRMT + 6 s16x2 DPX) per two cells;
+        # SW sweeps (k_sw_band / k_sw_fast): integer-pipe bound. 6 ALU thread-ops (1 PRMT + 5 s16x2 DPX) per two cells
+        # (the seventh op of the recurrence, H - gapOpen, is an IMAD on the FMA pipe thanks to the biased cells);
         # numerator = cells the sweep kernels actually computed (band cells, not matrix cells), denominator = the
         # issue rate of VIADDMNMX.S16x2 measured on this GPU right now (kslam_measure_int_peak).
         sweep_s = (ms["ms_sw_forward"] + ms["ms_sw_reverse"]) / 1e3
-        int_ops = 3.5 * tm["sw_cells_computed"]
+        int_ops = 3.0 * tm["sw_cells_computed"]
         int_ach = int_ops / sweep_s / 1e12 if sweep_s > 0 else 0.0
         int_roof = {"bound": "int-pipe", "kernel": "k_sw_band / k_sw_fast (SW forward + reverse sweeps)", "achieved": int_ach,
                     "peak": int_peak / 1e12, "unit": "T int16x2 thread-ops/s", "frac": int_ach / (int_peak / 1e12) if int_peak else None,
                     "traffic": None, "peak_source": "measured live: dependency-free VIADDMNMX.S16x2 issue-rate microbenchmark (kslam_measure_int_peak)",
                     "share_of_step": sweep_s * 1e3 / (t_res / args.steps * 1e3),
-                    "note": "3.5 ALU thread-ops per computed cell (1 PRMT + 6 DPX per s16x2 cell pair); cells computed = band cells "
+                    "note": "3 ALU thread-ops per computed cell (1 PRMT + 5 DPX per s16x2 cell pair; H - gapOpen is an IMAD on the FMA pipe); cells computed = band cells "
                             "(32 or 64 per row) or the full matrix for fallback alignments; CUDA events on the ctx stream"}
         dominant = int_roof if sweep_s * 1e3 >= ms["ms_sort"] else hbm_roof
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -101,13 +101,24 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return d;
 }
 
+// bias added to every stored cell / gap value of the packed sweeps (see k_sw_band): a multiple of 32 larger than
+// (gapOpen + gapExtend) * 32, so that H - gapOpen and the gap recurrences stay positive in both 16-bit halves
+__host__ __device__ __forceinline__ uint32_t sw_bias(const SwScore &sc) { return 32u * (uint32_t)(sc.gap_open + sc.gap_extend + 2); }
+// a * one + c with `one` == 1 passed as a kernel argument: ptxas cannot fold the multiply away, so this is an IMAD and
+// issues on the FMA pipe, not on the ALU pipe that the DPX recurrences saturate
+__device__ __forceinline__ uint32_t mad_add(uint32_t a, uint32_t one, uint32_t c) {
+  uint32_t d;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(c));
+  return d;
+}
+
 #include "sw_band.cuh"
 
 // ---------------------------------------------------------------- fast (full-matrix) kernel
 template <int LANES, bool REVERSE>
 __global__ void __launch_bounds__(SW_BLOCK, 4)
 k_sw_fast(const SwTask *__restrict__ tasks, const uint2 *__restrict__ items, uint32_t n_items, SwPlanes pl,
-          SwScore sc, SwRes *__restrict__ res) {
+          SwScore sc, SwRes *__restrict__ res, uint32_t one /* == 1, opaque to ptxas */) {
   constexpr int GROUPS = SW_BLOCK / LANES;
   __shared__ uint32_t s_sel[GROUPS][SW_MAXCOLS];
   const uint32_t lane = threadIdx.x & 31;
@@ -151,22 +162,25 @@ k_sw_fast(const SwTask *__restrict__ tasks, const uint2 *__restrict__ items, uin
   }
   __syncwarp(gmask);
 
-  const uint32_t NEG_GO = pack2(-sc.gap_open * 32), NEG_GE = pack2(-sc.gap_extend * 32), MIN2 = 0x80008000u;
+  // biased cells, H - gapOpen as one IMAD on the FMA pipe: see k_sw_band
+  const uint32_t NEG_GE = pack2(-sc.gap_extend * 32);
+  const uint32_t KB = sw_bias(sc), K2 = KB * 0x10001u;
+  const uint32_t NEG_GO32 = (uint32_t)(-(int32_t)(sc.gap_open * 32) * 0x10001);
   uint32_t H[SW_R], E[SW_R];
 #pragma unroll
-  for (int r = 0; r < SW_R; r++) { H[r] = 0; E[r] = 0; }
-  uint32_t lastH = 0, lastF = 0, prevUpH = 0;
+  for (int r = 0; r < SW_R; r++) { H[r] = K2; E[r] = K2; }
+  uint32_t lastH = K2, lastF = K2, prevUpH = K2;
   // forward: best = (H*32 | 31) of the running maximum, info = step << 16 | key at the step it was set
   // reverse: thr = forward score * 32, info = first step whose lane maximum reaches it
-  uint32_t bestA = 31, bestB = 31, infoA = 0, infoB = 0;
-  const uint32_t thrA = REVERSE ? (uint32_t)ra.score * 32u : 0u, thrB = REVERSE ? (uint32_t)rb.score * 32u : 0u;
+  uint32_t bestA = KB + 31u, bestB = KB + 31u, infoA = 0, infoB = 0;
+  const uint32_t thrA = REVERSE ? (uint32_t)ra.score * 32u + KB : 0u, thrB = REVERSE ? (uint32_t)rb.score * 32u + KB : 0u;
   bool hitA = false, hitB = false;
 
   const uint32_t steps = ncols + LANES - 1;
   for (uint32_t t = 0; t < steps; t++) {
     uint32_t upH = __shfl_up_sync(gmask, lastH, 1, LANES);
     uint32_t upF = __shfl_up_sync(gmask, lastF, 1, LANES);
-    if (g == 0) { upH = 0; upF = 0; }
+    if (g == 0) { upH = K2; upF = K2; }
     const int32_t j = (int32_t)t - (int32_t)g;
     if (j >= 0 && j < (int32_t)ncols) {
       const uint32_t selw = s_sel[grp][j];
@@ -178,10 +192,10 @@ k_sw_fast(const SwTask *__restrict__ tasks, const uint2 *__restrict__ items, uin
 #pragma unroll
         for (int r = 0; r < SW_R; r++) {
           uint32_t s = prmt(PA[r], PB[r], sel) & cm;
-          uint32_t h = __viaddmax_s16x2_relu(hd, s, E[r]);
-          h = __vimax3_s16x2(h, f, f);
+          uint32_t h = __viaddmax_s16x2(hd, s, E[r]);
+          h = __vimax3_s16x2(h, f, K2);
           hd = H[r]; H[r] = h;
-          uint32_t hgo = __viaddmax_s16x2(h, NEG_GO, MIN2);
+          uint32_t hgo = mad_add(h, one, NEG_GO32);
           E[r] = __viaddmax_s16x2(E[r], NEG_GE, hgo);
           f = __viaddmax_s16x2(f, NEG_GE, hgo);
           acc = __viaddmax_s16x2(h, (uint32_t)(31 - r) * 0x10001u, acc);
@@ -190,10 +204,10 @@ k_sw_fast(const SwTask *__restrict__ tasks, const uint2 *__restrict__ items, uin
 #pragma unroll
         for (int r = 0; r < SW_R; r++) {
           uint32_t s = prmt(PA[r], PB[r], sel);
-          uint32_t h = __viaddmax_s16x2_relu(hd, s, E[r]);       // max(H[i-1][j-1] + s, E, 0)
-          h = __vimax3_s16x2(h, f, f);                            // ... and F
+          uint32_t h = __viaddmax_s16x2(hd, s, E[r]);            // max(H[i-1][j-1] + s, E)
+          h = __vimax3_s16x2(h, f, K2);                           // ... F and the floor (0, biased)
           hd = H[r]; H[r] = h;
-          uint32_t hgo = __viaddmax_s16x2(h, NEG_GO, MIN2);       // H - gapOpen
+          uint32_t hgo = mad_add(h, one, NEG_GO32);               // H - gapOpen, both halves, FMA pipe
           E[r] = __viaddmax_s16x2(E[r], NEG_GE, hgo);             // E for column j+1
           f = __viaddmax_s16x2(f, NEG_GE, hgo);                   // F for row i+1
           acc = __viaddmax_s16x2(h, (uint32_t)(31 - r) * 0x10001u, acc);  // max of H*32 + (31 - r)
@@ -221,8 +235,8 @@ k_sw_fast(const SwTask *__restrict__ tasks, const uint2 *__restrict__ items, uin
       keyA = hitA ? (((1023u - colA) << 10) | (1023u - rowA)) : 0u;
       keyB = hitB ? (((1023u - colB) << 10) | (1023u - rowB)) : 0u;
     } else {
-      keyA = bestA > 31u ? (((bestA >> 5) << 20) | ((1023u - colA) << 10) | (1023u - rowA)) : 0u;
-      keyB = bestB > 31u ? (((bestB >> 5) << 20) | ((1023u - colB) << 10) | (1023u - rowB)) : 0u;
+      keyA = bestA > KB + 31u ? ((((bestA - KB) >> 5) << 20) | ((1023u - colA) << 10) | (1023u - rowA)) : 0u;
+      keyB = bestB > KB + 31u ? ((((bestB - KB) >> 5) << 20) | ((1023u - colB) << 10) | (1023u - rowB)) : 0u;
     }
   }
 #pragma unroll
@@ -576,8 +590,9 @@ __device__ __forceinline__ void count_tier(uint32_t tier, uint32_t *__restrict__
 __device__ __forceinline__ uint32_t classify(uint32_t m, uint32_t n, const SwScore &sc) {
   if (m == 0 || n == 0) return SWC_NONE;
   const uint32_t mn = m < n ? m : n;
-  const bool score_ok = sc.match >= 1 && sc.match * 32 <= 127 && sc.mismatch * 32 <= 128 && (uint32_t)sc.match * mn <= 1000u &&
-                        sc.gap_open * 32 <= 30000 && sc.gap_extend * 32 <= 30000;
+  // 16-bit cells: the largest possible score, scaled by 32 and biased (sw_bias), must stay below 2^15
+  const bool score_ok = sc.match >= 1 && sc.match * 32 <= 127 && sc.mismatch * 32 <= 128 && sc.gap_open <= 100 && sc.gap_extend <= 100 &&
+                        (uint32_t)sc.match * mn * 32u + sw_bias(sc) + 64u <= 32767u;
   if (score_ok && m <= 8 * SW_R && n <= SW_MAXCOLS) return SWC_FAST8;
   return SWC_SLOW;
 }
@@ -815,7 +830,7 @@ static void run_band(kslam_ctx *c, const SwPlanes &pl, const SwScore &sc, const 
   SwWorkspace *w = c->sw;
   const uint32_t pairs = (n_list + 1) / 2, blocks = (pairs + SWB_BLOCK - 1) / SWB_BLOCK;
   k_sw_band<MODE, W><<<blocks, SWB_BLOCK, BandSmem<W>::BYTES, c->stream>>>(w->tasks.as<SwTask>(), list, n_list, pl, sc, w->res.as<SwRes>(),
-      w->keys.as<Rec16>(), d_counts + CNT_FULL, next_list, d_counts + CNT_BAND64);
+      w->keys.as<Rec16>(), d_counts + CNT_FULL, next_list, d_counts + CNT_BAND64, 1u);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
 }
@@ -868,7 +883,7 @@ static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore 
     CUDA_TRY(cudaMemsetAsync(d_counts + CNT_EXTRA, 0, 4, st));
     k_sw_make_items<<<(n_items / 2 + 255) / 256, 256, 0, st>>>(sorted, n_full, items, d_counts + CNT_EXTRA);
     constexpr int GROUPS = SW_BLOCK / 8;
-    k_sw_fast<8, REVERSE><<<(n_items + GROUPS - 1) / GROUPS, SW_BLOCK, 0, st>>>(tasks, items, n_items, pl, sc, res);
+    k_sw_fast<8, REVERSE><<<(n_items + GROUPS - 1) / GROUPS, SW_BLOCK, 0, st>>>(tasks, items, n_items, pl, sc, res, 1u);
     c->launches += 2;
     CUDA_TRY(cudaGetLastError());
   }

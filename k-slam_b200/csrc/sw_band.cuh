@@ -175,7 +175,7 @@ template <int MODE, int W>
 __global__ void __launch_bounds__(SWB_BLOCK, (W > 32 ? 4 : 6))
 k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, uint32_t n_list, SwPlanes pl, SwScore sc,
           SwRes *__restrict__ res, Rec16 *__restrict__ fb_keys, uint32_t *__restrict__ fb_count,
-          uint32_t *__restrict__ next_list, uint32_t *__restrict__ next_count) {
+          uint32_t *__restrict__ next_list, uint32_t *__restrict__ next_count, uint32_t one /* == 1, opaque to ptxas */) {
   constexpr bool REVERSE = MODE == 1;
   constexpr int NH = W > 32 ? W / 32 : 1;      // tracking keys per 32-slot half
   constexpr int COLW = BandSmem<W>::COLW;
@@ -210,20 +210,26 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
   const uint32_t PSRC = mis_b | (mat_b << 8);                 // bytes {mismatch, match, 0, 0}: source of every row profile
   const uint32_t QLUT0 = 0x20100201u, QLUT1 = 0x00000033u;    // row code 0-5 -> the byte naming its profile selector ...
   const uint32_t QSRC = 0x22100100u;                          // ... whose nibbles pick the selector's two bytes here
-  const uint32_t NEG_GO = pack2(-sc.gap_open * 32), NEG_GE = pack2(-sc.gap_extend * 32), MIN2 = 0x80008000u;
+  const uint32_t NEG_GE = pack2(-sc.gap_extend * 32);
+  // Biased cells: every H / gap value is stored + KB (sw_bias), so nothing the recurrences produce is ever negative: the
+  // floor of a cell is KB instead of 0, gap states are bounded below by KB - gapOpen > 0 by their own recurrence (no
+  // clamp needed), and "H - gapOpen" for both halves is ONE plain 32-bit add of -gapOpen * 0x10001 (no borrow can cross
+  // the halves) — issued as an IMAD on the FMA pipe (mad_add), which leaves 6 ALU-pipe ops per cell pair instead of 7.
+  const uint32_t KB = sw_bias(sc), K2 = KB * 0x10001u;
+  const uint32_t NEG_GO32 = (uint32_t)(-(int32_t)(sc.gap_open * 32) * 0x10001);
 
   uint32_t H[W], V[W], sel[W];
 #pragma unroll
   for (int t = 0; t < W; t += 4) {
     const uint32_t wa = colA[(size_t)(t / 4) * SWB_BLOCK], wb = colB[(size_t)(t / 4) * SWB_BLOCK];
 #pragma unroll
-    for (int r = 0; r < 4; r++) { H[t + r] = 0; V[t + r] = 0; sel[t + r] = prmt(wa, wb, (uint32_t)(((4 + r) << 4) | r)); }
+    for (int r = 0; r < 4; r++) { H[t + r] = K2; V[t + r] = K2; sel[t + r] = prmt(wa, wb, (uint32_t)(((4 + r) << 4) | r)); }
   }
   // forward: key = score * 32 | 31 of the best cell so far, info = row << 8 | band slot of that cell;
   // reverse: (rcol, info) = first (smallest scan column, then smallest row) cell reaching the forward score
-  uint32_t keyA = 31u, keyB = 31u, infoA = 0, infoB = 0;
+  uint32_t keyA = KB + 31u, keyB = KB + 31u, infoA = 0, infoB = 0;
   uint32_t rcolA = 0xffffffffu, rcolB = 0xffffffffu;
-  const uint32_t thrA = REVERSE ? (uint32_t)ra.score * 32u : 0u, thrB = REVERSE ? (uint32_t)rb.score * 32u : 0u;
+  const uint32_t thrA = REVERSE ? (uint32_t)ra.score * 32u + KB : 0u, thrB = REVERSE ? (uint32_t)rb.score * 32u + KB : 0u;
   for (int32_t i0 = 0; i0 < rows4; i0 += 4) {
     const uint32_t qword = qAB[(size_t)(i0 / 4) * SWB_BLOCK];
     const uint32_t ewa = colA[(size_t)((i0 + W) / 4) * SWB_BLOCK], ewb = colB[(size_t)((i0 + W) / 4) * SWB_BLOCK];
@@ -234,17 +240,17 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
       const uint32_t codes = prmt(qword, 0u, 0x4440u | (uint32_t)r);
       const uint32_t q32 = prmt(QSRC, 0u, prmt(QLUT0, QLUT1, codes));
       const uint32_t PA = prmt(PSRC, 0u, q32), PB = prmt(PSRC, 0u, q32 >> 16);
-      uint32_t e = 0, acc[NH];
+      uint32_t e = K2, acc[NH];
 #pragma unroll
       for (int h = 0; h < NH; h++) acc[h] = 0;
 #pragma unroll
       for (int t = 0; t < W; t++) {
         const uint32_t s = prmt(PA, PB, sel[t]);
         const uint32_t v = V[t];
-        uint32_t h = __viaddmax_s16x2_relu(H[t], s, v);           // max(H[i-1][j-1] + s, vertical gap, 0)
-        h = __vimax3_s16x2(h, e, e);                                // ... and the horizontal gap
+        uint32_t h = __viaddmax_s16x2(H[t], s, v);                // max(H[i-1][j-1] + s, vertical gap)
+        h = __vimax3_s16x2(h, e, K2);                               // ... the horizontal gap and the floor (0, biased)
         H[t] = h;
-        const uint32_t hgo = __viaddmax_s16x2(h, NEG_GO, MIN2);
+        const uint32_t hgo = mad_add(h, one, NEG_GO32);             // H - gapOpen in both halves, on the FMA pipe
         e = __viaddmax_s16x2(e, NEG_GE, hgo);                      // horizontal gap into (i, j+1)
         if (t > 0) V[t - 1] = __viaddmax_s16x2(v, NEG_GE, hgo);    // vertical gap into (i+1, j): band slot t-1 next row
         acc[t / 32] = __viaddmax_s16x2(h, (uint32_t)(31 - (t & 31)) * 0x10001u, acc[t / 32]);   // H*32 + (31 - slot): smallest column wins ties
@@ -267,9 +273,9 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
         } else {
           const uint32_t nA = ((uint32_t)i << 8) | ((uint32_t)(32 * h + 31) - (aA & 31u)), nB = ((uint32_t)i << 8) | ((uint32_t)(32 * h + 31) - (aB & 31u));
           if (aA > keyA) { keyA = aA | 31u; infoA = nA; }
-          else if ((aA | 31u) == keyA && aA > 31u && (nA >> 8) + (nA & 255u) < (infoA >> 8) + (infoA & 255u)) infoA = nA;
+          else if ((aA | 31u) == keyA && aA > KB + 31u && (nA >> 8) + (nA & 255u) < (infoA >> 8) + (infoA & 255u)) infoA = nA;
           if (aB > keyB) { keyB = aB | 31u; infoB = nB; }
-          else if ((aB | 31u) == keyB && aB > 31u && (nB >> 8) + (nB & 255u) < (infoB >> 8) + (infoB & 255u)) infoB = nB;
+          else if ((aB | 31u) == keyB && aB > KB + 31u && (nB >> 8) + (nB & 255u) < (infoB >> 8) + (infoB & 255u)) infoB = nB;
         }
       }
     }
@@ -292,7 +298,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
       }
     } else {
       const uint32_t key = al ? keyB : keyA, info = al ? infoB : infoA;
-      const int32_t S = (int32_t)(key >> 5);
+      const int32_t S = (int32_t)((key - KB) >> 5);
       const int32_t brow = (int32_t)(info >> 8), bcol = brow + (int32_t)(info & 255u) + c0[al];
       const int32_t a = ceil_div_pos(S, sc.match);
       const bool proven = S > 0 && c0[al] <= -(rows[al] - a) && (cols[al] - a) <= c0[al] + (W - 1);
