@@ -188,7 +188,7 @@ def run_config3(args, pkg):
             t = float(np.mean(ms)) / 1e3
             key = "cigar" if cigar else "score_only"
             row[key] = {"gcups": 150.0 * window * n / t / 1e9, "ms": t * 1e3, "M_pairs_per_min": n / t * 60 / 1e6,
-                        "tiers": {k: tm[k] for k in ("n_sw_tier8", "n_sw_tier16", "n_sw_tier32", "n_sw_tier64", "n_sw_sweep32", "n_sw_fast", "n_sw_slow")},
+                        "tiers": {k: tm[k] for k in ("n_sw_tier8", "n_sw_tier16", "n_sw_tier32", "n_sw_tier48", "n_sw_tier64", "n_sw_sweep32", "n_sw_fast", "n_sw_slow")},
                         "int_pipe_frac": 3.0 * tm["sw_cells_computed"] / ((tm["ms_sw_forward"] + tm["ms_sw_reverse"]) / 1e3) / int_peak}
         if not args.no_cpu_baseline and T.have_ref():
             cs = args.cpu_sample or 200_000
@@ -457,7 +457,7 @@ def main():
                "stage_ms": ms,
                "counts": {k: tm[k] for k in ("n_read_kmers", "n_sorted_kmers", "n_genome_kmers", "n_raw_seeds", "n_seeds", "n_pairs",
                                              "n_sw_band", "n_sw_band64", "n_sw_fast", "n_sw_slow", "n_sw_band_rev",
-                                             "n_sw_tier8", "n_sw_tier16", "n_sw_tier32", "n_sw_tier64", "n_sw_sweep32",
+                                             "n_sw_tier8", "n_sw_tier16", "n_sw_tier32", "n_sw_tier48", "n_sw_tier64", "n_sw_sweep32",
                                              "sw_cells_forward", "sw_cells_reverse", "sw_cells_computed", "n_sort_passes")},
                "genome_index_build_s": t_load}
         if partitioned:

@@ -98,7 +98,7 @@ typedef struct {
   float ms_sw_prepare, ms_sw_forward, ms_sw_reverse, ms_sw_traceback, ms_sw_slow, ms_d2h, ms_pair, ms_total;
   uint64_t n_read_kmers, n_sorted_kmers, n_genome_kmers, n_raw_seeds, n_seeds, n_sort_passes;
   uint64_t sw_cells_forward, sw_cells_reverse, sw_cells_computed, n_sw_fast, n_sw_slow, n_sw_band, n_sw_band64, n_sw_band_rev, n_traceback_dp, n_pairs;
-  uint64_t n_sw_tier8, n_sw_tier16, n_sw_tier32, n_sw_tier64, n_sw_sweep32; /* forward work-list tiers */
+  uint64_t n_sw_tier8, n_sw_tier16, n_sw_tier32, n_sw_tier48, n_sw_tier64, n_sw_sweep32; /* forward work-list tiers */
   uint64_t kernel_launches;
 } kslam_timings;
 
@@ -245,7 +245,7 @@ int kslam_set_kmer_sort_bits(kslam_ctx *ctx, uint32_t bits);
 int kslam_get_kmer_sort_bits(const kslam_ctx *ctx);
 /* Banded Smith-Waterman tiers: 0 = full-matrix kernel only; 1 = alignments whose optimum is provably inside a
  * 32-diagonal band run in the banded kernel (sweep, then verify); 2 = additionally a 64-diagonal tier for what that
- * sweep bounded but could not prove; 3 (default) = additionally bands of 8 / 16 / 32 / 64 diagonals placed directly
+ * sweep bounded but could not prove; 3 (default) = additionally bands of 8 / 16 / 32 / 48 / 64 diagonals placed directly
  * from a lower bound of the score (best ungapped segment on the seed's diagonal; the forward score for the reverse
  * pass). Whatever cannot be proven falls through to the full-matrix kernel. Results are identical at every level
  * (DESIGN.md §3.4). */

@@ -49,15 +49,19 @@ struct __align__(16) SwRes {
   int32_t score, ref_end, read_end, ref_begin, read_begin;
   uint32_t flags, pad0, pad1;   // flags: low byte = KSLAM_FLAG_*, bits 8-10 forward tier, bits 11-13 reverse tier
 };
-// tier code of the sweep that produced the result: 0 = full-matrix / scalar kernel, 1..4 = band of 8 / 16 / 32 / 64 diagonals
-#define SWR_TIER_OF_W(W) ((W) == 8 ? 1u : (W) == 16 ? 2u : (W) == 32 ? 3u : 4u)
+// tier code of the sweep that produced the result: 0 = full-matrix / scalar kernel, 1..4 = band of 8 / 16 / 32 / 64
+// diagonals, 5 = 48 diagonals
+#define SWR_TIER_OF_W(W) ((W) == 8 ? 1u : (W) == 16 ? 2u : (W) == 32 ? 3u : (W) == 64 ? 4u : 5u)
 #define SWR_FWD_TIER(t) ((uint32_t)(t) << 8)
 #define SWR_REV_TIER(t) ((uint32_t)(t) << 11)
-// work-list tier of an alignment (byte arrays tier_f / tier_r): 0..3 = band of 8 / 16 / 32 / 64 diagonals placed exactly
-// on the interval a known score bound allows (no verification needed), 4 = 32 diagonals centred, sweep-and-verify,
-// 255 = not in a band list
-#define SWT_TIER_SWEEP 4u
+// work-list tier of an alignment (byte arrays tier_f / tier_r): 0..4 = band of 8 / 16 / 32 / 48 / 64 diagonals placed
+// exactly on the interval a known score bound allows (no verification needed), 5 = 32 diagonals centred,
+// sweep-and-verify, 255 = not in a band list
+#define SWT_N_DIRECT 5u
+#define SWT_TIER_SWEEP 5u
+#define SWT_N_TIERS 6u
 #define SWT_TIER_NONE 255u
+__host__ __device__ __forceinline__ uint32_t tier_width(uint32_t t) { return t == 0 ? 8u : t == 1 ? 16u : t == 2 ? 32u : t == 3 ? 48u : 64u; }
 
 struct SwPlanes {
   const uint64_t *q_sbits; const uint32_t *q_nmask;
@@ -533,8 +537,8 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
 #define CNT_RETRY 4
 #define CNT_EXTRA 5
 #define CNT_BAND64 6
-#define CNT_TIER 16    // 5 counters: alignments per work-list tier
-#define CNT_CUR 24     // 5 cursors of k_tier_scatter
+#define CNT_TIER 16    // SWT_N_TIERS counters: alignments per work-list tier
+#define CNT_CUR 24     // SWT_N_TIERS cursors of k_tier_scatter
 #define CNT_WORDS 32
 
 // ---- lower bound of the optimal score from the seed's own diagonal ------------------------------------------
@@ -573,13 +577,15 @@ __device__ int32_t diag_lower_bound(const SwPlanes &pl, const SwTask &t, int32_t
   }
   return best;
 }
-// smallest direct tier (0..3 = 8 / 16 / 32 / 64 diagonals) whose band holds [-(rows - a), cols - a], a = ceil(score / match);
-// SWT_TIER_NONE when the interval is wider than 64 or the score says nothing
-__device__ __forceinline__ uint32_t tier_of_width(int32_t rows, int32_t cols, int32_t score, const SwScore &sc, uint32_t max_tier) {
+// smallest direct tier (0..4 = 8 / 16 / 32 / 48 / 64 diagonals) whose band holds [-(rows - a), cols - a],
+// a = ceil(score / match); SWT_TIER_NONE when the interval is wider than the widest tier allowed or the score says
+// nothing. level: 1 = 32 only, 2 = 32 and 64, 3 = all five widths.
+__device__ __forceinline__ uint32_t tier_of_width(int32_t rows, int32_t cols, int32_t score, const SwScore &sc, uint32_t level) {
   if (score <= 0) return SWT_TIER_NONE;
   const int32_t width = rows + cols - 2 * ceil_div_pos(score, sc.match) + 1;
-  const uint32_t t = width <= 8 ? 0u : width <= 16 ? 1u : width <= 32 ? 2u : width <= 64 ? 3u : SWT_TIER_NONE;
-  return (t != SWT_TIER_NONE && t > max_tier) ? SWT_TIER_NONE : t;
+  if (level >= 3) return width <= 8 ? 0u : width <= 16 ? 1u : width <= 32 ? 2u : width <= 48 ? 3u : width <= 64 ? 4u : SWT_TIER_NONE;
+  if (width <= 32) return 2u;
+  return (level >= 2 && width <= 64) ? 4u : SWT_TIER_NONE;
 }
 // one counter per tier, one atomic per (warp, tier)
 __device__ __forceinline__ void count_tier(uint32_t tier, uint32_t *__restrict__ counts) {
@@ -621,8 +627,8 @@ __device__ __forceinline__ bool window_clean(const uint32_t *__restrict__ nmask,
 // `tiers` on, the seed-diagonal lower bound L picks the narrowest band that provably holds every optimal alignment
 // (res[].score = L is what MODE 2 of k_sw_band places the band with); otherwise, or when L allows nothing <= 64
 // diagonals (e.g. an indel splits the read over two diagonals), the 32-wide sweep-and-verify tier.
-__device__ __forceinline__ void enlist(const SwPlanes &pl, const SwTask &t, uint32_t i, uint32_t cls, int32_t d0, bool seeded, uint32_t tiers,
-                                       uint32_t max_tier, const SwScore &sc, SwRes *__restrict__ res, uint8_t *__restrict__ tier_f,
+__device__ __forceinline__ void enlist(const SwPlanes &pl, const SwTask &t, uint32_t i, uint32_t cls, int32_t d0, bool seeded, uint32_t level,
+                                       const SwScore &sc, SwRes *__restrict__ res, uint8_t *__restrict__ tier_f,
                                        Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list, uint32_t *__restrict__ counts) {
   uint32_t tier = SWT_TIER_NONE;
   if (cls == SWC_NONE) {
@@ -631,9 +637,9 @@ __device__ __forceinline__ void enlist(const SwPlanes &pl, const SwTask &t, uint
   } else if (cls == SWC_SLOW) slow_list[list_slot(&counts[CNT_SLOW])] = i;
   else if (t.flags & SWT_BAND) {
     tier = SWT_TIER_SWEEP;
-    if (tiers) {
+    if (level >= 3) {
       const int32_t L = diag_lower_bound(pl, t, d0, sc);
-      const uint32_t tt = tier_of_width((int32_t)t.m, (int32_t)t.n, L, sc, max_tier);
+      const uint32_t tt = tier_of_width((int32_t)t.m, (int32_t)t.n, L, sc, level);
       if (tt != SWT_TIER_NONE) { tier = tt; res[i].score = L; }
     }
   } else { const uint32_t k = list_slot(&counts[CNT_FULL]); full_keys[k].key = t.n; full_keys[k].val = i; }
@@ -682,7 +688,7 @@ k_sw_prepare_seeds(const kslam_seed *__restrict__ seeds, uint32_t n, const uint6
   // matrix diagonal of the seed's exact 32-mer match: forward seeds put read base i on genome base rel + i; reverse-
   // complement seeds put rc(read) base i there and Align sees the window reversed (SmithWaterman.h:205-208)
   const int32_t d0 = s.rev_comp ? (int32_t)t.w_start + (int32_t)t.n - s.rel - (int32_t)t.m : s.rel - (int32_t)t.w_start;
-  enlist(pl, t, i, cls, d0, true, use_band >= 3, use_band >= 2 ? 3u : 2u, sc, res, tier_f, full_keys, slow_list, counts);
+  enlist(pl, t, i, cls, d0, true, use_band, sc, res, tier_f, full_keys, slow_list, counts);
 }
 
 // Aligner::Align batch mode: query i against ref i, whole sequences
@@ -703,14 +709,14 @@ k_sw_prepare_pairs(uint32_t n, const uint64_t *__restrict__ q_offs, const uint64
   if (cls != SWC_NONE && window_clean(r_nmask, t.w_word, 0, t.n)) t.flags |= SWT_CLEAN;
   if (use_band && cls == SWC_FAST8 && band_shape_ok(t.m, t.n) && (t.flags & SWT_CLEAN)) t.flags |= SWT_BAND;
   tasks[i] = t;
-  enlist(pl, t, i, cls, 0, false, use_band >= 3, use_band >= 2 ? 3u : 2u, sc, res, tier_f, full_keys, slow_list, counts);   // no seed: try the main diagonal
+  enlist(pl, t, i, cls, 0, false, use_band, sc, res, tier_f, full_keys, slow_list, counts);   // no seed: try the main diagonal
 }
 
 // reverse pass work lists: score 0 has no reverse pass (ssw.c:903 is reached with an empty range). The forward score S
 // is known, so the band [-(rows - a), cols - a] (sw_band.cuh) is exact and its width picks the tier directly.
 __global__ void __launch_bounds__(256)
 k_sw_rev_lists(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, uint32_t n, SwScore sc,
-               uint8_t *__restrict__ tier_r, uint32_t min_tier, uint32_t max_tier,
+               uint8_t *__restrict__ tier_r, uint32_t level,
                Rec16 *__restrict__ full_keys, uint32_t *__restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -719,8 +725,7 @@ k_sw_rev_lists(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
   const SwRes r = res[i];
   if (((t.flags >> 8) & 0xffu) == SWC_FAST8 && r.score > 0) {
     const int32_t rows = r.read_end + 1, cols = r.ref_end + 1;
-    if (t.flags & SWT_BAND) tier = tier_of_width(rows, cols, r.score, sc, max_tier);
-    if (tier != SWT_TIER_NONE && tier < min_tier) tier = min_tier;
+    if (t.flags & SWT_BAND) tier = tier_of_width(rows, cols, r.score, sc, level);
     if (tier == SWT_TIER_NONE) { const uint32_t k = list_slot(&counts[CNT_FULL]); full_keys[k].key = (uint64_t)cols; full_keys[k].val = i; }
   }
   tier_r[i] = (uint8_t)tier;
@@ -757,13 +762,13 @@ k_sw_cells(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, cons
     if (((t.flags >> 8) & 0xffu) != SWC_FAST8) continue;
     fw += (unsigned long long)t.m * t.n;
     const uint32_t tf = tier_f[i], tr = tier_r[i], ft = (r.flags >> 8) & 7u;
-    if (tf <= 3u) comp += (unsigned long long)(8u << tf) * t.m;
+    if (tf < SWT_N_DIRECT) comp += (unsigned long long)tier_width(tf) * t.m;
     if (tf == SWT_TIER_SWEEP) { comp += 32ull * t.m; if (ft == 4u) comp += 64ull * t.m; }
     if (ft == 0u) comp += (unsigned long long)t.m * t.n;
     if (r.score > 0) {
       const unsigned long long rows = (unsigned long long)(r.read_end + 1), cols = (unsigned long long)(r.ref_end + 1);
       rv += rows * cols;
-      comp += tr <= 3u ? (unsigned long long)(8u << tr) * rows : rows * cols;
+      comp += tr < SWT_N_DIRECT ? (unsigned long long)tier_width(tr) * rows : rows * cols;
     }
   }
   for (int d = 16; d; d >>= 1) {
@@ -835,23 +840,26 @@ static void run_band(kslam_ctx *c, const SwPlanes &pl, const SwScore &sc, const 
   CUDA_TRY(cudaGetLastError());
 }
 
-// tier byte array -> per-tier lists at the front of w->lists; returns the five list sizes
-static void make_tier_lists(kslam_ctx *c, uint32_t n, const uint8_t *tier, uint32_t *d_counts, uint32_t *h_counts, uint32_t cnt[5]) {
+// 0 = full-matrix only, 1 = 32-wide sweep tier, 2 = + 64-wide tier, 3 = + direct tiers from the seed-diagonal bound
+static uint32_t sw_level(const kslam_ctx *c) { return !c->sw_band ? 0u : (!c->sw_band64 ? 1u : (c->sw_tiers ? 3u : 2u)); }
+
+// tier byte array -> per-tier lists at the front of w->lists; returns the list sizes
+static void make_tier_lists(kslam_ctx *c, uint32_t n, const uint8_t *tier, uint32_t *d_counts, uint32_t *h_counts, uint32_t cnt[SWT_N_TIERS]) {
   cudaStream_t st = c->stream;
-  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_CUR, 0, 5 * 4, st));
+  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_CUR, 0, SWT_N_TIERS * 4, st));
   k_tier_scatter<<<(n + 255) / 256, 256, 0, st>>>(tier, n, d_counts, d_counts + CNT_CUR, c->sw->lists.as<uint32_t>());
   c->launches++;
   CUDA_TRY(cudaGetLastError());
-  read_small(c, h_counts + CNT_TIER, d_counts + CNT_TIER, 5 * 4);
+  read_small(c, h_counts + CNT_TIER, d_counts + CNT_TIER, SWT_N_TIERS * 4);
   CUDA_TRY(cudaStreamSynchronize(st));
-  for (int t = 0; t < 5; t++) cnt[t] = h_counts[CNT_TIER + t];
+  for (uint32_t t = 0; t < SWT_N_TIERS; t++) cnt[t] = h_counts[CNT_TIER + t];
 }
 
 // one direction (forward or reverse) over the tier lists: the direct tiers (band placed exactly, 8 / 16 / 32 / 64
 // diagonals), forward only: the 32-wide sweep-and-verify tier and the 64-wide tier for what it could not prove but
 // bounded; then every remaining alignment through the full-matrix kernel, bucketed by column count
 template <bool REVERSE>
-static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore &sc, const uint32_t cnt[5], uint32_t *d_counts,
+static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore &sc, const uint32_t cnt[SWT_N_TIERS], uint32_t *d_counts,
                     uint32_t *h_counts, uint64_t *n_band64_via_sweep, uint64_t *n_full_done) {
   SwWorkspace *w = c->sw;
   cudaStream_t st = c->stream;
@@ -859,15 +867,16 @@ static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore 
   SwRes *res = w->res.as<SwRes>();
   uint32_t *lists = w->lists.as<uint32_t>(), *list64 = lists + 2 * (size_t)n;
   Rec16 *keys = w->keys.as<Rec16>(), *keys2 = w->keys2.as<Rec16>();
-  uint32_t off[5] = {0, 0, 0, 0, 0};
-  for (int t = 1; t < 5; t++) off[t] = off[t - 1] + cnt[t - 1];
+  uint32_t off[SWT_N_TIERS] = {0, 0, 0, 0, 0, 0};
+  for (uint32_t t = 1; t < SWT_N_TIERS; t++) off[t] = off[t - 1] + cnt[t - 1];
   constexpr int DM = REVERSE ? 1 : 2;
   run_band<DM, 8>(c, pl, sc, lists + off[0], cnt[0], d_counts, nullptr);
   run_band<DM, 16>(c, pl, sc, lists + off[1], cnt[1], d_counts, nullptr);
   run_band<DM, 32>(c, pl, sc, lists + off[2], cnt[2], d_counts, nullptr);
-  run_band<DM, 64>(c, pl, sc, lists + off[3], cnt[3], d_counts, nullptr);
-  if (!REVERSE && cnt[4]) {
-    run_band<0, 32>(c, pl, sc, lists + off[4], cnt[4], d_counts, c->sw_band64 ? list64 : nullptr);
+  run_band<DM, 48>(c, pl, sc, lists + off[3], cnt[3], d_counts, nullptr);
+  run_band<DM, 64>(c, pl, sc, lists + off[4], cnt[4], d_counts, nullptr);
+  if (!REVERSE && cnt[SWT_TIER_SWEEP]) {
+    run_band<0, 32>(c, pl, sc, lists + off[SWT_TIER_SWEEP], cnt[SWT_TIER_SWEEP], d_counts, c->sw_band64 ? list64 : nullptr);
     const uint32_t n64 = read_count(c, d_counts, h_counts, CNT_BAND64);     // 32-wide failures that fit 64 diagonals
     run_band<2, 64>(c, pl, sc, list64, n64, d_counts, nullptr);
     *n_band64_via_sweep += n64;
@@ -903,28 +912,28 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
 
   // ---- forward
   cudaEvent_t e1 = tm_mark(c);
-  uint32_t cnt[5];
+  uint32_t cnt[SWT_N_TIERS];
   make_tier_lists(c, n, tier_f, d_counts, h_counts, cnt);
   const uint32_t n_slow = read_count(c, d_counts, h_counts, CNT_SLOW);
   uint64_t band64_sweep = 0, full_done = 0;
   sw_pass<false>(c, n, pl, sc, cnt, d_counts, h_counts, &band64_sweep, &full_done);
   c->tm.n_sw_fast = full_done; c->tm.n_sw_slow = n_slow;
-  c->tm.n_sw_band = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4];
-  c->tm.n_sw_band64 = cnt[3] + band64_sweep;
-  c->tm.n_sw_tier8 = cnt[0]; c->tm.n_sw_tier16 = cnt[1]; c->tm.n_sw_tier32 = cnt[2]; c->tm.n_sw_tier64 = cnt[3]; c->tm.n_sw_sweep32 = cnt[4];
+  c->tm.n_sw_band = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4] + cnt[5];
+  c->tm.n_sw_band64 = cnt[4] + band64_sweep;
+  c->tm.n_sw_tier8 = cnt[0]; c->tm.n_sw_tier16 = cnt[1]; c->tm.n_sw_tier32 = cnt[2]; c->tm.n_sw_tier48 = cnt[3]; c->tm.n_sw_tier64 = cnt[4];
+  c->tm.n_sw_sweep32 = cnt[SWT_TIER_SWEEP];
   cudaEvent_t e2 = tm_mark(c);
 
   // ---- reverse
   CUDA_TRY(cudaMemsetAsync(d_counts + CNT_BAND, 0, 8, st));   // band + full counters
   CUDA_TRY(cudaMemsetAsync(d_counts + CNT_BAND64, 0, 4, st));
-  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_TIER, 0, 5 * 4, st));
-  const uint32_t max_tier = !c->sw_band ? 0u : (c->sw_band64 ? 3u : 2u), min_tier = c->sw_tiers ? 0u : 2u;
-  k_sw_rev_lists<<<nb, 256, 0, st>>>(tasks, res, n, sc, tier_r, min_tier, max_tier, w->keys.as<Rec16>(), d_counts);
+  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_TIER, 0, SWT_N_TIERS * 4, st));
+  k_sw_rev_lists<<<nb, 256, 0, st>>>(tasks, res, n, sc, tier_r, sw_level(c), w->keys.as<Rec16>(), d_counts);
   c->launches++;
   make_tier_lists(c, n, tier_r, d_counts, h_counts, cnt);
   uint64_t dummy = 0, full_rev = 0;
   sw_pass<true>(c, n, pl, sc, cnt, d_counts, h_counts, &dummy, &full_rev);
-  c->tm.n_sw_band_rev = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3];
+  c->tm.n_sw_band_rev = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4];
   cudaEvent_t e3 = tm_mark(c);
 
   // ---- exact scalar fallback for shapes outside the fast kernels
@@ -982,8 +991,6 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
   c->tm.ms_sw_traceback = tm_ms(e4, e5);
 }
 
-// 0 = full-matrix only, 1 = 32-wide sweep tier, 2 = + 64-wide tier, 3 = + direct tiers from the seed-diagonal bound
-static uint32_t sw_level(const kslam_ctx *c) { return !c->sw_band ? 0u : (!c->sw_band64 ? 1u : (c->sw_tiers ? 3u : 2u)); }
 
 static void sw_reserve(kslam_ctx *c, uint32_t n) {
   if (!c->sw) c->sw = new SwWorkspace();
@@ -1003,7 +1010,7 @@ static void sw_reset_timers(kslam_ctx *c) {
   c->tm.ms_sw_prepare = c->tm.ms_sw_forward = c->tm.ms_sw_reverse = c->tm.ms_sw_slow = c->tm.ms_sw_traceback = 0;
   c->tm.sw_cells_forward = c->tm.sw_cells_reverse = 0;
   c->tm.n_sw_fast = c->tm.n_sw_slow = c->tm.n_sw_band = c->tm.n_sw_band64 = c->tm.n_sw_band_rev = 0; c->tm.n_traceback_dp = 0;
-  c->tm.n_sw_tier8 = c->tm.n_sw_tier16 = c->tm.n_sw_tier32 = c->tm.n_sw_tier64 = c->tm.n_sw_sweep32 = 0; c->tm.sw_cells_computed = 0;
+  c->tm.n_sw_tier8 = c->tm.n_sw_tier16 = c->tm.n_sw_tier32 = c->tm.n_sw_tier48 = c->tm.n_sw_tier64 = c->tm.n_sw_sweep32 = 0; c->tm.sw_cells_computed = 0;
 }
 
 // ---- CIGAR pool compaction: the traceback writes alignment i's ops at the fixed stride i * cigar_cap; almost every

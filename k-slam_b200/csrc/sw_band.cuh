@@ -177,7 +177,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
           SwRes *__restrict__ res, Rec16 *__restrict__ fb_keys, uint32_t *__restrict__ fb_count,
           uint32_t *__restrict__ next_list, uint32_t *__restrict__ next_count, uint32_t one /* == 1, opaque to ptxas */) {
   constexpr bool REVERSE = MODE == 1;
-  constexpr int NH = W > 32 ? W / 32 : 1;      // tracking keys per 32-slot half
+  constexpr int NH = (W + 31) / 32;            // tracking keys per 32-slot half
   constexpr int COLW = BandSmem<W>::COLW;
   extern __shared__ uint32_t smem[];
   uint32_t *colA = smem + threadIdx.x, *colB = colA + COLW * SWB_BLOCK, *qAB = colB + COLW * SWB_BLOCK;
