@@ -9,31 +9,101 @@
 // (SURVEY.md App. C H3). One thread walks one (pair, entry) run twice (count, then emit after a prefix sum).
 #include "common.cuh"
 
+// ---- pair order by MERGE ------------------------------------------------------------------------------------------
+// alignToDatabase's vector is ordered by (read, entry, rel) with every R1 read before every R2 read, so its R1 part and
+// its R2 part are each already ordered by (pair id, entry, rel): getPairedOverlaps' order is the stable merge of the two
+// (R1 first on exact ties) — one pass over the data instead of an 8-pass radix sort.
+//   k_pair_flags   pass[i] = sw_score >= threshold (Overlap.h:335)                -> exclusive scan -> compact index list
+//   k_pair_compact idx[pos[i]] = i for passing overlaps; the list keeps input order, its first n_a entries are R1
+//   k_pair_split   merge-path partition: for every tile of PM_TILE outputs, how many come from the R1 list
+//   k_pair_merge   one CTA per tile: keys of both sub-ranges staged in shared memory, every thread finds its own
+//                  diagonal by binary search and merges PM_IPT outputs, writing the merged overlap records
+#define PM_THREADS 128
+#define PM_IPT 8
+#define PM_TILE (PM_THREADS * PM_IPT)
+
+struct PairKey { uint64_t hi; uint32_t lo; };            // (pair id << 32 | entry, rel + bias)
+__device__ __forceinline__ PairKey pair_key(const kslam_overlap *__restrict__ ov, uint32_t i, uint32_t mid, uint32_t bias) {
+  const uint4 w = __ldg(reinterpret_cast<const uint4 *>(ov + i));     // read, entry, rel, rev_comp
+  PairKey k; k.hi = ((uint64_t)(w.x % mid) << 32) | w.y; k.lo = (uint32_t)((int32_t)w.z + (int32_t)bias);
+  return k;
+}
+// a strictly before b? (ties: the R1 list wins, which is what the callers' "<= / <" choice encodes)
+__device__ __forceinline__ bool key_less(const PairKey &a, const PairKey &b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+
 __global__ void __launch_bounds__(256)
-k_pair_keys(const kslam_overlap *__restrict__ ov, uint32_t n, uint32_t mid, uint32_t thr, uint32_t bias,
-            Rec16 *__restrict__ keys, uint32_t *__restrict__ n_pass) {
+k_pair_flags(const kslam_overlap *__restrict__ ov, uint32_t n, uint32_t mid, uint32_t thr, uint32_t *__restrict__ pass,
+             uint32_t *__restrict__ n_r1_pass) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool pass = false;
-  if (i < n) {
-    const kslam_overlap o = ov[i];
-    Rec16 k;
-    pass = o.sw_score >= thr;           // Overlap.h:335: removed when sw_score < scoreThreshold
-    if (pass) {
-      k.key = ((uint64_t)(o.read % mid) << 32) | o.entry;
-      k.val = ((uint64_t)(uint32_t)(o.rel + (int32_t)bias) << 32) | i;
-    } else { k.key = ~0ull; k.val = ((uint64_t)0xffffffffu << 32) | i; }
-    keys[i] = k;
-  }
-  const uint32_t m = __ballot_sync(0xffffffffu, pass);     // one atomic per warp
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_pass, (uint32_t)__popc(m));
+  bool p = false, r1 = false;
+  if (i < n) { p = ov[i].sw_score >= thr; r1 = p && ov[i].read < mid; pass[i] = p ? 1u : 0u; }
+  const uint32_t m = __ballot_sync(0xffffffffu, r1);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_r1_pass, (uint32_t)__popc(m));
 }
 
 __global__ void __launch_bounds__(256)
-k_pair_gather(const Rec16 *__restrict__ sorted, uint32_t n_sorted, const kslam_overlap *__restrict__ ov,
-              kslam_overlap *__restrict__ ov_out) {
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_sorted) return;
-  ov_out[k] = ov[(uint32_t)sorted[k].val];      // cigar_off keeps pointing into the batch's dense CIGAR pool
+k_pair_compact(const uint32_t *__restrict__ pass, const uint32_t *__restrict__ pos, uint32_t n, uint32_t *__restrict__ idx) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && pass[i]) idx[pos[i]] = i;
+}
+
+// number of R1-list elements among the first `diag` outputs of the merge of A = idx[0..na) and B = idx[na..na+nb)
+__device__ __forceinline__ uint32_t merge_split(const kslam_overlap *__restrict__ ov, const uint32_t *__restrict__ idx, uint32_t na,
+                                                uint32_t nb, uint32_t diag, uint32_t mid, uint32_t bias) {
+  uint32_t lo = diag > nb ? diag - nb : 0u, hi = diag < na ? diag : na;       // a in [lo, hi]
+  while (lo < hi) {
+    const uint32_t a = (lo + hi) >> 1, b = diag - 1 - a;                        // compare A[a] with B[b]
+    // A[a] goes before B[b] unless B[b] is strictly smaller (ties: A first)
+    if (!key_less(pair_key(ov, idx[na + b], mid, bias), pair_key(ov, idx[a], mid, bias))) lo = a + 1; else hi = a;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256)
+k_pair_split(const kslam_overlap *__restrict__ ov, const uint32_t *__restrict__ idx, uint32_t na, uint32_t nb, uint32_t mid,
+             uint32_t bias, uint32_t n_tiles, uint32_t *__restrict__ tile_a) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_tiles) return;
+  const uint64_t d = (uint64_t)t * PM_TILE;
+  const uint32_t diag = d < (uint64_t)na + nb ? (uint32_t)d : na + nb;
+  tile_a[t] = merge_split(ov, idx, na, nb, diag, mid, bias);
+}
+
+__global__ void __launch_bounds__(PM_THREADS)
+k_pair_merge(const kslam_overlap *__restrict__ ov, const uint32_t *__restrict__ idx, uint32_t na, uint32_t nb, uint32_t mid,
+             uint32_t bias, const uint32_t *__restrict__ tile_a, kslam_overlap *__restrict__ out) {
+  __shared__ uint64_t s_hi[PM_TILE + 2];
+  __shared__ uint32_t s_lo[PM_TILE + 2];
+  __shared__ uint32_t s_src[PM_TILE + 2];
+  const uint32_t tile = blockIdx.x, n = na + nb;
+  const uint32_t d0 = tile * PM_TILE, d1 = d0 + PM_TILE < n ? d0 + PM_TILE : n;
+  const uint32_t a0 = tile_a[tile], a1 = tile_a[tile + 1], b0 = d0 - a0, b1 = d1 - a1;
+  const uint32_t ca = a1 - a0, cb = b1 - b0;                     // ca + cb == d1 - d0; A keys at [0, ca), B keys at [ca, ca + cb)
+  for (uint32_t i = threadIdx.x; i < ca + cb; i += PM_THREADS) {
+    const uint32_t src = i < ca ? idx[a0 + i] : idx[na + b0 + (i - ca)];
+    const PairKey k = pair_key(ov, src, mid, bias);
+    s_hi[i] = k.hi; s_lo[i] = k.lo; s_src[i] = src;
+  }
+  __syncthreads();
+  auto less_ba = [&](uint32_t b, uint32_t a) {                   // B[b] strictly before A[a]?
+    return s_hi[ca + b] < s_hi[a] || (s_hi[ca + b] == s_hi[a] && s_lo[ca + b] < s_lo[a]);
+  };
+  const uint32_t diag = threadIdx.x * PM_IPT < ca + cb ? threadIdx.x * PM_IPT : ca + cb;
+  uint32_t lo = diag > cb ? diag - cb : 0u, hi = diag < ca ? diag : ca;
+  while (lo < hi) {
+    const uint32_t a = (lo + hi) >> 1, b = diag - 1 - a;
+    if (!less_ba(b, a)) lo = a + 1; else hi = a;
+  }
+  uint32_t a = lo, b = diag - lo;
+#pragma unroll
+  for (int k = 0; k < PM_IPT; k++) {
+    const uint32_t o = diag + k;
+    if (o >= ca + cb) break;
+    const bool take_b = a >= ca || (b < cb && less_ba(b, a));
+    const uint32_t src = take_b ? s_src[ca + b] : s_src[a];
+    if (take_b) b++; else a++;
+    out[d0 + o] = ov[src];                                        // cigar_off keeps pointing into the batch's dense CIGAR pool
+  }
 }
 
 // getPairsFromRead over the run starting at `first`; emits into out (or only counts when out == nullptr)
@@ -127,29 +197,35 @@ void pair_overlaps(kslam_ctx *c) {
   if (mid == 0) return;
   uint32_t *d_cnt = c->counters.as<uint32_t>() + 48;
   uint32_t *h_cnt = c->h_counters.as<uint32_t>() + 48;
-  c->pair_keys.reserve((size_t)n * sizeof(Rec16) + 64);
-  c->pair_keys2.reserve((size_t)n * sizeof(Rec16) + 64);
+  // pass flags | positions | compact index list | tile splits, all u32
+  const uint32_t max_tiles = n / PM_TILE + 2;
+  c->pair_keys.reserve(((size_t)n * 3 + max_tiles + 8) * 4 + 64);
+  uint32_t *pass = c->pair_keys.as<uint32_t>(), *ppos = pass + n, *idx = ppos + n, *tile_a = idx + n;
   CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 16, st));
   const unsigned nb = (n + 255) / 256;
-  k_pair_keys<<<nb, 256, 0, st>>>(c->ov.as<kslam_overlap>(), n, mid, c->prm.score_threshold, c->reads.max_len,
-                                  c->pair_keys.as<Rec16>(), d_cnt);
-  c->launches++;
-  uint64_t passes = 0;
-  Rec16 *a = c->pair_keys.as<Rec16>(), *b = c->pair_keys2.as<Rec16>();
-  Rec16 *cur = radix_sort(c, a, b, n, 1, 32, 64, &passes);       // rel (stable: index order kept on ties)
-  cur = radix_sort(c, cur, cur == a ? b : a, n, 0, 0, 64, &passes);  // entry, then pair id
+  k_pair_flags<<<nb, 256, 0, st>>>(c->ov.as<kslam_overlap>(), n, mid, c->prm.score_threshold, pass, d_cnt);
+  unsigned long long *d_ns = c->counters.as<unsigned long long>() + 31;
+  exclusive_scan_u32(c, pass, ppos, n, (uint64_t *)d_ns);
+  k_pair_compact<<<nb, 256, 0, st>>>(pass, ppos, n, idx);
+  c->launches += 2;
+  unsigned long long *h_ns = c->h_counters.as<unsigned long long>() + 31;
   read_small(c, h_cnt, d_cnt, 4);
+  read_small(c, h_ns, d_ns, 8);
   CUDA_TRY(cudaStreamSynchronize(st));
-  const uint32_t ns = h_cnt[0];
+  const uint32_t ns = (uint32_t)h_ns[0], na = h_cnt[0], nbb = ns - na;
   c->n_sorted = ns;
   if (!ns) return;
   c->ov_sorted.reserve((size_t)ns * sizeof(kslam_overlap) + 64);
+  const uint32_t n_tiles = (ns + PM_TILE - 1) / PM_TILE;
+  k_pair_split<<<(n_tiles + 1 + 255) / 256, 256, 0, st>>>(c->ov.as<kslam_overlap>(), idx, na, nbb, mid, c->reads.max_len, n_tiles, tile_a);
+  k_pair_merge<<<n_tiles, PM_THREADS, 0, st>>>(c->ov.as<kslam_overlap>(), idx, na, nbb, mid, c->reads.max_len, tile_a,
+                                                c->ov_sorted.as<kslam_overlap>());
+  c->launches += 2;
   const unsigned nbs = (ns + 255) / 256;
-  k_pair_gather<<<nbs, 256, 0, st>>>(cur, ns, c->ov.as<kslam_overlap>(), c->ov_sorted.as<kslam_overlap>());
   c->pair_cnt.reserve((size_t)ns * 8 + 64);
   uint32_t *cnt = c->pair_cnt.as<uint32_t>(), *pos = cnt + ns;
   k_pair_count<<<nbs, 256, 0, st>>>(c->ov_sorted.as<kslam_overlap>(), ns, mid, c->reads.offs.as<uint64_t>(), cnt);
-  c->launches += 2;
+  c->launches++;
   unsigned long long *d_tot = c->counters.as<unsigned long long>() + 30;
   exclusive_scan_u32(c, cnt, pos, ns, (uint64_t *)d_tot);
   unsigned long long *h_tot = c->h_counters.as<unsigned long long>() + 30;
