@@ -446,6 +446,17 @@ int kslam_sam_batch(const kslam_sam_params *prm, const kslam_sam_db *db, const k
                     char **text, uint64_t *len, uint32_t *max_insert_size) {
   if (!prm || !db || !reads || !pairs || !text) return KSLAM_ERR_ARG;
   if (pairs->n_pairs && (!pairs->pairs || !pairs->sorted_overlaps)) return KSLAM_ERR_ARG;
+  // the records index each other and the read / entry arrays: refuse anything out of range instead of reading past a buffer
+  for (uint64_t i = 0; i < pairs->n_sorted; i++) {
+    const kslam_overlap &o = pairs->sorted_overlaps[i];
+    if (o.read >= reads->n_reads || o.entry >= db->n_entries) return KSLAM_ERR_ARG;
+    if (o.cigar_len && pairs->cigar_pool && (uint64_t)o.cigar_off + o.cigar_len > pairs->n_cigar_words) return KSLAM_ERR_ARG;
+  }
+  for (uint64_t i = 0; i < pairs->n_pairs; i++) {
+    const kslam_pair &k = pairs->pairs[i];
+    if ((k.r1_idx < 0 && k.r2_idx < 0) || k.r1_idx >= (int64_t)pairs->n_sorted || k.r2_idx >= (int64_t)pairs->n_sorted ||
+        k.entry >= db->n_entries) return KSLAM_ERR_ARG;
+  }
   try {
     Ctx c{prm, db, reads, pairs};
     auto rp = per_read(pairs, (uint32_t)(reads->n_reads / 2));

@@ -5,20 +5,26 @@
 // striped forward pass, reverse pass and banded traceback (/root/reference/src/ssw.c:841-951, :143-592,
 // :594-792), then un-flips coordinates for reverse-complement seeds.
 //
-// Here (DESIGN.md §SW):
-//  * k_sw_fast<LANES, REVERSE>: a group of LANES threads owns TWO alignments packed in the halves of s16x2
-//    registers; each lane keeps SW_R=20 query rows (H, E and a 4-byte score profile per row) in registers and
-//    the group sweeps the columns as an anti-diagonal wavefront (lane g works on column t-g at step t,
-//    boundary H/F handed down with shuffles). One PRMT builds the packed substitution score from the two
-//    profiles, the recurrences are DPX VIADDMNMX/VIMNMX ops. Scores are scaled by 32 so the free low 5 bits
-//    of every cell carry (31 - row-in-lane): a single viaddmax per cell tracks "max score, then smallest row",
-//    which together with the step counter reproduces SSW's tie rules exactly (first column, then smallest row).
-//    REVERSE=true runs the same sweep over the reversed prefixes and records the first column reaching the
-//    forward score (ssw.c:905-923). No tensor cores: nothing here is a dense contraction.
-//  * k_sw_slow: exact scalar fallback (one thread per alignment) for shapes outside the fast kernel's range.
-//  * k_sw_traceback: literal restatement of banded_sw (ssw.c:594-792) — rolling h_b/e_b/h_c arrays with the
-//    reference's index maps (set_u/set_d), direction bytes, band doubling, traceback quirks — one thread per
-//    alignment, then the reverse-complement un-flip and refStart offset (SmithWaterman.h:212-229).
+// Here (DESIGN.md §3.4):
+//  * k_sw_band<MODE, W> (sw_band.cuh): one THREAD owns two alignments packed in the halves of s16x2 registers and sweeps a
+//    band of W = 8 / 16 / 32 / 48 / 64 diagonals that provably contains every optimal alignment (the bound comes from
+//    diag_lower_bound, from a first 32-wide sweep, or — reverse pass — from the forward score). Most alignments.
+//  * k_sw_fast<LANES, REVERSE>: a group of LANES threads owns two alignments; each lane keeps SW_R=20 query rows (H, E and a
+//    4-byte score profile per row) in registers and the group sweeps the columns as an anti-diagonal wavefront (lane g works
+//    on column t-g at step t, boundary H/F handed down with shuffles). The full matrix, for what no band can hold.
+//    Both kernels: one PRMT builds the packed substitution score from the two profiles, the recurrences are DPX
+//    VIADDMNMX/VIMNMX3 ops on BIASED cells (H - gapOpen is then a plain 32-bit add issued as an IMAD on the FMA pipe: six
+//    ALU-pipe ops per cell pair). Scores are scaled by 32 so the free low 5 bits of a tracking key carry (31 - row-in-lane)
+//    or (31 - band slot): one viaddmax per cell tracks "max score, then smallest row / column", which together with the
+//    step / row counter reproduces SSW's tie rules exactly (first column, then smallest row). REVERSE runs the same sweep
+//    over the reversed prefixes and records the first column reaching the forward score (ssw.c:905-923). No tensor cores:
+//    nothing here is a dense contraction.
+//  * k_sw_slow: exact scalar fallback (one thread per alignment) for shapes outside the packed kernels' range.
+//  * k_sw_traceback: pass 0 emits "len M" when the sub-rectangle's main diagonal already scores the alignment score
+//    (word-parallel XOR + popcount); the rest runs a literal restatement of banded_sw (ssw.c:594-792) — rolling h_b/e_b/h_c
+//    arrays with the reference's index maps (set_u/set_d), direction bytes, band doubling, traceback quirks — one thread
+//    per alignment; then the reverse-complement un-flip and refStart offset (SmithWaterman.h:212-229) and the compaction
+//    of the CIGAR pool.
 // Roofline: integer (ALU) pipe; cells/s reported as GCUPS next to the counted ops/cell.
 #include "common.cuh"
 #include <stdlib.h>

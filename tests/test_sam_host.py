@@ -70,3 +70,15 @@ def test_sam_empty_batch(pkg):
     z8, z1 = np.zeros(0, np.uint8), np.zeros(1, np.uint64)
     got, mi = w.batch(z8, z1, z8, z1, z8, z1, np.zeros(0, pkg.OVERLAP_DT), np.zeros(0, np.uint32), np.zeros(0, pkg.PAIR_DT))
     assert got == b"" and mi == 2**32 - 1
+
+
+def test_sam_rejects_out_of_range_records(pkg, golden):
+    g = golden("sam_config1_mini.npz")
+    tags = [f"g{i}" for i in range(len(g["go"]) - 1)]
+    w = pkg.SamWriter(g["gb"], g["go"], tags)
+    args = [g["rb"], g["ro"], g["quals"], g["ro"], g["ids"], g["id_offs"]]
+    for field, arr, bad in (("read", "ov", 10**9), ("entry", "ov", 10**6), ("r1_idx", "pairs", 10**9)):
+        ov, pairs = g["ov"].copy(), g["pairs"].copy()
+        (ov if arr == "ov" else pairs)[field][0] = bad
+        with pytest.raises(pkg.KslamError):
+            w.batch(*args, ov, g["pool"], pairs)
