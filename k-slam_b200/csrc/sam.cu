@@ -19,6 +19,8 @@
 #include <climits>
 #include <numeric>
 #include <string.h>
+#include <chrono>
+#include <stdlib.h>
 #include <thread>
 #include <unordered_map>
 
@@ -43,21 +45,9 @@ template <class F> void parallel_ranges(uint32_t threads, size_t n, F f) {
 
 struct Ctx {
   const kslam_sam_params *prm; const kslam_sam_db *db; const kslam_read_batch *reads; const kslam_pairs *in;
-  std::string read_bases(uint32_t i) const { return std::string(reads->bases + reads->offs[i], reads->bases + reads->offs[i + 1]); }
-  std::string read_qual(uint32_t i) const { return std::string(reads->quals + reads->qual_offs[i], reads->quals + reads->qual_offs[i + 1]); }
   std::string read_id(uint32_t i) const { return std::string(reads->ids + reads->id_offs[i], reads->ids + reads->id_offs[i + 1]); }
   std::string locus(uint32_t e) const { return std::string(db->locus_tags + db->locus_offs[e], db->locus_tags + db->locus_offs[e + 1]); }
 };
-
-// sequenceTools.h:83-116: reverse, then complement upper-case A/C/G/T only
-std::string reverse_complement(const std::string &f) {
-  std::string rc = f;
-  std::reverse(rc.begin(), rc.end());
-  for (char &c : rc) {
-    switch (c) { case 'A': c = 'T'; break; case 'T': c = 'A'; break; case 'C': c = 'G'; break; case 'G': c = 'C'; break; default: break; }
-  }
-  return rc;
-}
 
 std::vector<ReadPair> per_read(const kslam_pairs *in, uint32_t midpoint) {          // PairedOverlap.h:437-471
   std::vector<ReadPair> out;
@@ -228,75 +218,89 @@ const std::vector<double> &log_mismatch_table() {        // SAM.h:41-48
   return table;
 }
 
-SequenceDifference cigar_and_md(const Ctx &c, const kslam_overlap &overlap) {          // SAM.h:101-237
+// decimal digits of v appended to out (std::to_string without the temporary)
+inline void put_uint(std::string &out, uint64_t v) {
+  char buf[24]; int n = 0;
+  do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  while (n) out.push_back(buf[--n]);
+}
+inline void put_int(std::string &out, int64_t v) {
+  if (v < 0) { out.push_back('-'); put_uint(out, (uint64_t)(-v)); } else put_uint(out, (uint64_t)v);
+}
+
+// getCigarAndMD, SAM.h:101-237. Same walk, same order of the floating-point additions; the reference's temporaries
+// (reverse-complemented copy of the read, reversed copy of the qualities, the vector of MD components that is
+// concatenated afterwards) are replaced by index arithmetic and a streaming MD writer with the same merging rules:
+// consecutive numeric components are summed, a deleted block is "^" + bases, and a mismatch base directly after a
+// deleted block is preceded by "0".
+SequenceDifference cigar_and_md(const Ctx &c, const kslam_overlap &overlap) {
   const auto &matchTable = log_match_table();
   const auto &misMatchTable = log_mismatch_table();
   SequenceDifference sd;
-  std::vector<std::string> MDcomponents;
-  const char *ref = c.db->bases + c.db->offs[overlap.entry];
-  std::string query = overlap.rev_comp ? reverse_complement(c.read_bases(overlap.read)) : c.read_bases(overlap.read);
-  std::string quality = c.read_qual(overlap.read);
-  if (overlap.rev_comp) std::reverse(quality.begin(), quality.end());
   if (!overlap.cigar_len || !c.in->cigar_pool) return sd;            // Alignment::cigar == nullptr
+  const char *ref = c.db->bases + c.db->offs[overlap.entry];
+  const char *rb = c.reads->bases + c.reads->offs[overlap.read];
+  const int qlen = (int)(c.reads->offs[overlap.read + 1] - c.reads->offs[overlap.read]);
+  const char *qq = c.reads->quals + c.reads->qual_offs[overlap.read];
+  const int qqlen = (int)(c.reads->qual_offs[overlap.read + 1] - c.reads->qual_offs[overlap.read]);
+  const bool rc = overlap.rev_comp != 0;
+  // reverseComplement(bases)[p] (sequenceTools.h:83-116: only upper-case A/C/G/T are complemented) as a table walk from the
+  // read's end — no data-dependent branch on the base
+  static const struct CompTable { unsigned char t[256]; CompTable() { for (int i = 0; i < 256; i++) t[i] = (unsigned char)i; t['A'] = 'T'; t['T'] = 'A'; t['C'] = 'G'; t['G'] = 'C'; } } comp;
+  const int qstep = rc ? -1 : 1;
+  const char *qbase = rc ? rb + qlen - 1 : rb;                       // query[p] = f(qbase[p * qstep])
+  const char *qqbase = rc ? qq + qqlen - 1 : qq;
+  auto query_at = [&](int p) -> char { const unsigned char ch = (unsigned char)qbase[p * qstep]; return rc ? (char)comp.t[ch] : (char)ch; };
+  auto qual_at = [&](int p) -> int { return (unsigned char)qqbase[p * qstep]; };
   const uint32_t *cig = c.in->cigar_pool + overlap.cigar_off;
   int refPos = overlap.ref_begin;
   int queryPos = 0;
   if (overlap.query_begin > 0) {
-    auto length = overlap.query_begin;
-    sd.cigar.append(std::to_string(length)); sd.cigar.push_back('S');
-    queryPos += length;
+    put_int(sd.cigar, overlap.query_begin); sd.cigar.push_back('S');
+    queryPos += overlap.query_begin;
   }
+  long pending = -1;               // sum of the numeric MD components not yet written
+  bool ambiguous = false;
+  auto md_number = [&](int v) { pending = pending < 0 ? v : pending + v; };
+  auto md_flush = [&]() { if (pending >= 0) { put_uint(sd.MD, (uint64_t)pending); pending = -1; ambiguous = false; } };
   for (uint32_t e = 0; e < overlap.cigar_len; e++) {
     int numMatch = 0;
-    uint32_t length = cig[e] >> 4;
-    sd.cigar.append(std::to_string(length));
-    uint32_t operation = cig[e] & 0xf;
-    std::string temp;
+    const uint32_t length = cig[e] >> 4, operation = cig[e] & 0xf;
+    put_uint(sd.cigar, length);
     switch (operation) {
       case 0:
         sd.cigar.push_back('M');
         for (int i = 0; i < (int)length; i++) {
-          if (ref[refPos] == query[queryPos]) { numMatch++; sd.logProbability += matchTable[quality[queryPos] - 33]; }
+          if (ref[refPos] == query_at(queryPos)) { numMatch++; sd.logProbability += matchTable[qual_at(queryPos) - 33]; }
           else {
             sd.NM++;
-            if (numMatch) MDcomponents.push_back(std::to_string(numMatch));
-            MDcomponents.push_back(std::string(1, ref[refPos]));
-            sd.logProbability += misMatchTable[quality[queryPos] - 33];
+            if (numMatch) md_number(numMatch);
+            md_flush();
+            if (ambiguous) { sd.MD.push_back('0'); ambiguous = false; }
+            sd.MD.push_back(ref[refPos]);
+            sd.logProbability += misMatchTable[qual_at(queryPos) - 33];
             numMatch = 0;
           }
           refPos++; queryPos++;
         }
-        if (numMatch) MDcomponents.push_back(std::to_string(numMatch));
+        if (numMatch) md_number(numMatch);
         break;
       case 1:
         sd.cigar.push_back('I'); sd.NM += length; queryPos += length;
         break;
       case 2:
         sd.cigar.push_back('D');
-        MDcomponents.push_back("^");
-        for (int i = 0; i < (int)length; i++) { temp.push_back(ref[refPos]); sd.NM++; refPos++; }
-        MDcomponents.push_back(temp);
+        md_flush();
+        sd.MD.push_back('^');
+        for (int i = 0; i < (int)length; i++) { sd.MD.push_back(ref[refPos]); sd.NM++; refPos++; }
+        ambiguous = true;
         break;
       default: break;
     }
   }
-  int end = (int)query.size() - overlap.query_end - 1;
-  if (end > 0) { sd.cigar.append(std::to_string(end)); sd.cigar.push_back('S'); }
-  bool ambiguous = false;
-  for (auto it = MDcomponents.begin(); it != MDcomponents.end();) {
-    if (*it == "^") { sd.MD.append(*it); it++; sd.MD.append(*it); ambiguous = true; it++; }
-    else if (isdigit((*it)[0])) {
-      int runningTotal = 0;
-      while (it != MDcomponents.end() && isdigit((*it)[0])) { runningTotal += std::stoi(*it); it++; }
-      sd.MD.append(std::to_string(runningTotal));
-      ambiguous = false;
-    } else {
-      if (ambiguous) { sd.MD.append("0"); ambiguous = false; }
-      sd.MD.append(*it);
-      it++;
-    }
-    if (it == MDcomponents.end()) break;
-  }
+  md_flush();
+  const int end = qlen - overlap.query_end - 1;
+  if (end > 0) { put_int(sd.cigar, end); sd.cigar.push_back('S'); }
   return sd;
 }
 
@@ -324,21 +328,26 @@ uint16_t sam_flag(const SAMEntry &e) {                   // SAM.h:309-326 (paire
   return flag;
 }
 
-std::string sam_line(const SAMEntry &e, bool reportCigar) {   // SAM.h:282-308
-  std::string out;
-  out += e.qname + '\t' + std::to_string(sam_flag(e)) + '\t' + e.rname + '\t' + std::to_string(e.pos) + '\t' + std::to_string(e.mapq) + '\t' +
-         (reportCigar ? e.cigar : "*") + '\t' + e.rnext + '\t' + std::to_string(e.pnext) + '\t' + std::to_string(e.tlen) + '\t' + '*' + '\t' + '*';
-  if (e.thisSegmentUnmapped) return out;
-  if (reportCigar) { out.append("\tMD:Z:"); out += e.MD; }
-  out.append("\tAS:i:");
-  out += std::to_string(e.AS) + '\t' + "XS:i:" + std::to_string(e.XS) + '\t' + "NM:i:" + std::to_string(e.NM) + '\t' + "X0:i:" + std::to_string(e.XO);
-  if (e.XT != 0) out += "\tXT:i:" + std::to_string(e.XT);
-  return out;
+void sam_line(std::string &out, const SAMEntry &e, bool reportCigar) {   // SAMEntry::getEntry, SAM.h:282-308, + '\n'
+  out += e.qname; out.push_back('\t'); put_uint(out, sam_flag(e)); out.push_back('\t');
+  out += e.rname; out.push_back('\t'); put_uint(out, e.pos); out.push_back('\t'); put_uint(out, e.mapq); out.push_back('\t');
+  if (reportCigar) out += e.cigar; else out.push_back('*');
+  out.push_back('\t'); out += e.rnext; out.push_back('\t'); put_uint(out, e.pnext); out.push_back('\t'); put_int(out, e.tlen);
+  out += "\t*\t*";
+  if (!e.thisSegmentUnmapped) {
+    if (reportCigar) { out += "\tMD:Z:"; out += e.MD; }
+    out += "\tAS:i:"; put_uint(out, e.AS);
+    out += "\tXS:i:"; put_uint(out, e.XS);
+    out += "\tNM:i:"; put_uint(out, e.NM);
+    out += "\tX0:i:"; put_uint(out, e.XO);
+    if (e.XT != 0) { out += "\tXT:i:"; put_uint(out, e.XT); }
+  }
+  out.push_back('\n');
 }
 
 void sam_init(SAMEntry &s, const Ctx &c, const kslam_overlap &overlap) {              // SAM.h:344-356
   auto sd = cigar_and_md(c, overlap);
-  s.cigar = sd.cigar; s.MD = sd.MD; s.NM = sd.NM;
+  s.cigar = std::move(sd.cigar); s.MD = std::move(sd.MD); s.NM = sd.NM;
   s.prob = std::pow(10, sd.logProbability);
   s.rname = c.locus(overlap.entry);
   s.pos = overlap.ref_begin + 1;
@@ -382,6 +391,7 @@ std::pair<SAMEntry, SAMEntry> sam_from_pair(const Ctx &c, const POv &ap) {      
 void write_pairs(std::string &out, const Ctx &c, ReadPair &read) {                    // SAM.h:451-517
   std::sort(read.pairs.begin(), read.pairs.end(), [](const POv &i, const POv &j) { return i.combinedScore > j.combinedScore; });
   std::vector<std::pair<SAMEntry, SAMEntry>> SAMPairs;
+  SAMPairs.reserve(read.pairs.size() < c.prm->num_alignments ? read.pairs.size() : c.prm->num_alignments);
   uint32_t r1NumHits = 0, r2NumHits = 0;
   for (auto &ap : read.pairs) {
     if (ap.hasR1) r1NumHits++;
@@ -406,8 +416,8 @@ void write_pairs(std::string &out, const Ctx &c, ReadPair &read) {              
     if (temp2 <= 0.00001) temp2 = 0.00001;
     sp->first.mapq = ceil(-10.0 * std::log10(temp));
     sp->second.mapq = ceil(-10.0 * std::log10(temp2));
-    out += sam_line(sp->first, c.prm->report_cigar != 0); out += "\n";
-    out += sam_line(sp->second, c.prm->report_cigar != 0); out += "\n";
+    sam_line(out, sp->first, c.prm->report_cigar != 0);
+    sam_line(out, sp->second, c.prm->report_cigar != 0);
     if (c.prm->sam_xa) break;
   }
 }
@@ -459,14 +469,20 @@ int kslam_sam_batch(const kslam_sam_params *prm, const kslam_sam_db *db, const k
   }
   try {
     Ctx c{prm, db, reads, pairs};
+    const bool trace = getenv("KSLAM_SAM_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
     auto rp = per_read(pairs, (uint32_t)(reads->n_reads / 2));
+    double t1 = now();
     const uint32_t maxInsert = max_allowed_insert_size(rp);
+    double t2 = now();
     if (max_insert_size) *max_insert_size = maxInsert;
     uint32_t threads = prm->threads ? prm->threads : std::max(1u, std::thread::hardware_concurrency());
     if (threads > 64) threads = 64;
     screen_by_insert_size(rp, pairs->sorted_overlaps, maxInsert, threads);
     screen_by_score(rp, prm->score_fraction_threshold, threads);
     if (prm->pseudo_assembly) { pseudo_assembly(rp, threads); screen_by_score(rp, prm->score_fraction_threshold, threads); }
+    double t3 = now();
     std::vector<std::string> parts(threads);
     parallel_ranges(threads, rp.size(), [&](uint32_t t, size_t lo, size_t hi) {
       for (size_t i = lo; i < hi; i++) write_pairs(parts[t], c, rp[i]);
@@ -476,6 +492,8 @@ int kslam_sam_batch(const kslam_sam_params *prm, const kslam_sam_db *db, const k
     for (auto &p : parts) total += p.size();
     out.reserve(total);
     for (auto &p : parts) out += p;
+    if (trace) fprintf(stderr, "[kslam_sam] per_read %.1f ms, insert limit %.1f ms, screens + assembly %.1f ms, records %.1f ms (incl. concat), %u threads\n",
+                       (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (now() - t3) * 1e3, threads);
     *text = dup_text(out);
     if (len) *len = out.size();
     return *text ? KSLAM_OK : KSLAM_ERR_NOMEM;
