@@ -508,8 +508,9 @@ class SamWriter:
             raise KslamError(f"kslam_sam_header failed ({rc})")
         return self._take(ptr, n)
 
-    def batch(self, read_bases, read_offs, quals, qual_offs, ids, id_offs, sorted_overlaps, cigar_pool, pairs):
-        """-> (SAM text of the batch, max allowed insert size)"""
+    def batch(self, read_bases, read_offs, quals, qual_offs, ids, id_offs, sorted_overlaps, cigar_pool, pairs, out_file=None):
+        """-> (SAM text of the batch, max allowed insert size); with out_file the text is written to it straight from the
+        library's buffer and its length is returned instead."""
         rb, ro, q, qo, i, io = _u8(read_bases), _u64(read_offs), _u8(quals), _u64(qual_offs), _u8(ids), _u64(id_offs)
         n = len(ro) - 1
         reads = _ReadBatch(n, n // 2, rb.ctypes.data, ro.ctypes.data, q.ctypes.data, qo.ctypes.data, i.ctypes.data, io.ctypes.data)
@@ -523,4 +524,11 @@ class SamWriter:
         rc = self.L.kslam_sam_batch(C.byref(self.prm), C.byref(self.db), C.byref(reads), C.byref(p), C.byref(ptr), C.byref(ln), C.byref(mi))
         if rc != 0:
             raise KslamError(f"kslam_sam_batch failed ({rc})")
+        if out_file is not None:
+            try:
+                if ln.value:
+                    out_file.write(memoryview((C.c_char * ln.value).from_address(ptr.value)))
+            finally:
+                self.L.kslam_sam_free(ptr)
+            return ln.value, mi.value
         return self._take(ptr, ln), mi.value

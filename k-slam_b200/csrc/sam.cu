@@ -487,15 +487,20 @@ int kslam_sam_batch(const kslam_sam_params *prm, const kslam_sam_db *db, const k
     parallel_ranges(threads, rp.size(), [&](uint32_t t, size_t lo, size_t hi) {
       for (size_t i = lo; i < hi; i++) write_pairs(parts[t], c, rp[i]);
     });
-    std::string out;
     size_t total = 0;
-    for (auto &p : parts) total += p.size();
-    out.reserve(total);
-    for (auto &p : parts) out += p;
+    std::vector<size_t> at(threads + 1, 0);
+    for (uint32_t t = 0; t < threads; t++) { at[t] = total; total += parts[t].size(); }
+    char *buf = (char *)malloc(total + 1);                      // the threads' pieces go straight into the result buffer
+    if (buf) {
+      parallel_ranges(threads, threads, [&](uint32_t, size_t lo, size_t hi) {
+        for (size_t t = lo; t < hi; t++) memcpy(buf + at[t], parts[t].data(), parts[t].size());
+      });
+      buf[total] = 0;
+    }
+    *text = buf;
+    if (len) *len = total;
     if (trace) fprintf(stderr, "[kslam_sam] per_read %.1f ms, insert limit %.1f ms, screens + assembly %.1f ms, records %.1f ms (incl. concat), %u threads\n",
                        (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (now() - t3) * 1e3, threads);
-    *text = dup_text(out);
-    if (len) *len = out.size();
     return *text ? KSLAM_OK : KSLAM_ERR_NOMEM;
   } catch (const std::exception &) { return KSLAM_ERR_NOMEM; }
 }

@@ -98,11 +98,9 @@ def align_to_sam(pkg, fasta_paths, r1, r2, sam_path, reads_at_once=10_000_000, n
                 break
             b, p = item
             t0 = time.perf_counter()
-            text, _ = w.batch(b.bases, b.offs, b.quals, b.qual_offs, b.ids, b.id_offs, p.sorted_overlaps, p.cigar_pool, p.pairs)
-            t1 = time.perf_counter()
-            out.write(text)
-            t["sam"] += t1 - t0; t["write"] += time.perf_counter() - t1
-            stats["pairs"] += b.n_r1; stats["batches"] += 1; stats["sam_bytes"] += len(text)
+            n_text, _ = w.batch(b.bases, b.offs, b.quals, b.qual_offs, b.ids, b.id_offs, p.sorted_overlaps, p.cigar_pool, p.pairs, out_file=out)
+            t["sam"] += time.perf_counter() - t0
+            stats["pairs"] += b.n_r1; stats["batches"] += 1; stats["sam_bytes"] += n_text
             if log:
                 log(f"batch {stats['batches']}: {b.n_r1} pairs done")
         [x.join() for x in th]
