@@ -189,6 +189,9 @@ typedef struct {
 } kslam_read_batch;
 int kslam_fastq_open(const char *r1_path, const char *r2_path /* NULL: single-end */, uint32_t threads /* 0: all cores */,
                      kslam_fastq **out);
+/* Before the first batch: keep n buffer sets (1..16) and fill them round-robin, so a batch stays valid until n more
+ * batches have been read — a pipelined caller (ingest | GPU | SAM) needs no copies. Default 1. */
+int kslam_fastq_set_ring(kslam_fastq *reader, uint32_t n_buffer_sets);
 int kslam_fastq_next(kslam_fastq *reader, uint64_t max_reads, kslam_read_batch *out);
 const char *kslam_fastq_error(const kslam_fastq *reader);
 void kslam_fastq_close(kslam_fastq *reader);

@@ -143,6 +143,7 @@ def lib():
     u32 = C.c_uint32
     L.kslam_fastq_open.argtypes = [C.c_char_p, C.c_char_p, u32, C.POINTER(vp)]
     L.kslam_fastq_next.argtypes = [vp, u64, C.POINTER(_ReadBatch)]
+    L.kslam_fastq_set_ring.argtypes = [vp, u32]
     L.kslam_fastq_error.argtypes = [vp]
     L.kslam_fastq_error.restype = C.c_char_p
     L.kslam_fastq_close.argtypes = [vp]
@@ -439,13 +440,15 @@ class ReadBatch:
 class FastqReader:
     """kslam_fastq_*: chunk-parallel FASTQ ingest with the reference reader's exact semantics (FASTQsequence.h:110-165)."""
 
-    def __init__(self, r1, r2=None, threads=0):
+    def __init__(self, r1, r2=None, threads=0, ring=1):
         self.L = lib()
         h = C.c_void_p()
         rc = self.L.kslam_fastq_open(os.fsencode(r1), os.fsencode(r2) if r2 else None, threads, C.byref(h))
         if rc != 0:
             raise KslamError(f"kslam_fastq_open failed ({rc}): {self.L.kslam_last_error(None).decode()}")
         self.h = h
+        if ring != 1 and self.L.kslam_fastq_set_ring(self.h, ring) != 0:
+            raise KslamError("kslam_fastq_set_ring failed")
 
     def next(self, max_reads, copy=True):
         """Next batch (None at end of input). Raises KslamError on the reference's R1/R2 size mismatch."""

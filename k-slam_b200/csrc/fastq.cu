@@ -85,8 +85,12 @@ struct kslam_fastq {
   uint32_t threads = 1;
   bool pinned = false;
   std::string err;
-  IngestBuf bases, ids, quals;
-  std::vector<uint64_t> offs, id_offs, q_offs, line_start[2];
+  // ring of batch buffers: batch b lives in set b % ring, so a caller that pipelines (ingest | GPU | SAM) can keep the
+  // last ring - 1 batches alive without copying them (kslam_fastq_set_ring; default 1 = valid until the next call)
+  struct BufSet { IngestBuf bases, ids, quals; std::vector<uint64_t> offs, id_offs, q_offs; };
+  std::vector<BufSet> sets = std::vector<BufSet>(1);
+  uint64_t n_batches = 0;
+  std::vector<uint64_t> line_start[2];
   uint64_t n_file[2] = {0, 0};
 };
 
@@ -199,6 +203,12 @@ int kslam_fastq_open(const char *r1_path, const char *r2_path, uint32_t threads,
 
 const char *kslam_fastq_error(const kslam_fastq *rd) { return rd ? rd->err.c_str() : ""; }
 
+int kslam_fastq_set_ring(kslam_fastq *rd, uint32_t n_buffer_sets) {
+  if (!rd || n_buffer_sets < 1 || n_buffer_sets > 16 || rd->n_batches) return KSLAM_ERR_ARG;
+  rd->sets.resize(n_buffer_sets);
+  return KSLAM_OK;
+}
+
 int kslam_fastq_next(kslam_fastq *rd, uint64_t max_reads, kslam_read_batch *out) {
   if (!rd || !out) return KSLAM_ERR_ARG;
   try {
@@ -217,8 +227,10 @@ int kslam_fastq_next(kslam_fastq *rd, uint64_t max_reads, kslam_read_batch *out)
       rd->err = "mismatch in R1 and R2 size";
       return KSLAM_ERR_STATE;
     }
-    rd->offs.assign(n + 1, 0); rd->id_offs.assign(n + 1, 0); rd->q_offs.assign(n + 1, 0);
-    std::vector<uint64_t> &offs = rd->offs, &ioffs = rd->id_offs, &qoffs = rd->q_offs;
+    kslam_fastq::BufSet &bs = rd->sets[rd->n_batches % rd->sets.size()];
+    rd->n_batches++;
+    bs.offs.assign(n + 1, 0); bs.id_offs.assign(n + 1, 0); bs.q_offs.assign(n + 1, 0);
+    std::vector<uint64_t> &offs = bs.offs, &ioffs = bs.id_offs, &qoffs = bs.q_offs;
     // lengths, then prefix sums (ids are parsed twice: once for the length, once for the copy)
     auto rec = [&](uint64_t i, int *file, uint64_t *r) { if (i < n_rec[0]) { *file = 0; *r = i; } else { *file = 1; *r = i - n_rec[0]; } };
     auto id_span = [&](const char *p, uint64_t a, size_t len, size_t *from, size_t *cnt) {
@@ -243,22 +255,22 @@ int kslam_fastq_next(kslam_fastq *rd, uint64_t max_reads, kslam_read_batch *out)
       }
     });
     for (uint64_t i = 0; i < n; i++) { offs[i + 1] += offs[i]; ioffs[i + 1] += ioffs[i]; qoffs[i + 1] += qoffs[i]; }
-    rd->bases.reserve(offs[n] + 16, rd->pinned); rd->quals.reserve(qoffs[n] + 16, false); rd->ids.reserve(ioffs[n] + 16, false);
+    bs.bases.reserve(offs[n] + 16, rd->pinned); bs.quals.reserve(qoffs[n] + 16, false); bs.ids.reserve(ioffs[n] + 16, false);
     parallel_for(rd->threads, n, [&](uint32_t, uint64_t lo, uint64_t hi) {
       for (uint64_t i = lo; i < hi; i++) {
         int fl; uint64_t r; rec(i, &fl, &r);
         const char *p = rd->f[fl].p; const std::vector<uint64_t> &ls = rd->line_start[fl];
         const size_t bl = offs[i + 1] - offs[i];
-        memcpy(rd->bases.p + offs[i], p + ls[4 * r + 1], bl);
-        memcpy(rd->quals.p + qoffs[i], p + ls[4 * r + 3], qoffs[i + 1] - qoffs[i]);     // stored as is, whatever its length
+        memcpy(bs.bases.p + offs[i], p + ls[4 * r + 1], bl);
+        memcpy(bs.quals.p + qoffs[i], p + ls[4 * r + 3], qoffs[i + 1] - qoffs[i]);     // stored as is, whatever its length
         size_t from, cnt; id_span(p, ls[4 * r], line_len(p, ls[4 * r], ls[4 * r + 1]), &from, &cnt);
-        memcpy(rd->ids.p + ioffs[i], p + ls[4 * r] + from, cnt);
+        memcpy(bs.ids.p + ioffs[i], p + ls[4 * r] + from, cnt);
       }
     });
     out->n_reads = n; out->n_r1 = n_rec[0];
-    out->bases = rd->bases.p; out->offs = rd->offs.data();
-    out->quals = rd->quals.p; out->qual_offs = rd->q_offs.data();
-    out->ids = rd->ids.p; out->id_offs = rd->id_offs.data();
+    out->bases = bs.bases.p; out->offs = bs.offs.data();
+    out->quals = bs.quals.p; out->qual_offs = bs.q_offs.data();
+    out->ids = bs.ids.p; out->id_offs = bs.id_offs.data();
     rd->n_file[0] += n_rec[0]; rd->n_file[1] += n_rec[1];
     return KSLAM_OK;
   } catch (const std::exception &e) { rd->err = e.what(); return KSLAM_ERR_NOMEM; }
@@ -267,7 +279,7 @@ int kslam_fastq_next(kslam_fastq *rd, uint64_t max_reads, kslam_read_batch *out)
 void kslam_fastq_close(kslam_fastq *rd) {
   if (!rd) return;
   rd->f[0].close(); rd->f[1].close();
-  rd->bases.release(); rd->ids.release(); rd->quals.release();
+  for (auto &b : rd->sets) { b.bases.release(); b.ids.release(); b.quals.release(); }
   delete rd;
 }
 

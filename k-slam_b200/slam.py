@@ -43,7 +43,8 @@ def align_to_sam(pkg, fasta_paths, r1, r2, sam_path, reads_at_once=10_000_000, n
                  pseudo_assembly=True, sam_xa=False, min_alignment_score=0, command_line="", device=0, log=None):
     """The batch loop as a three-stage pipeline, one host thread per stage (every heavy call is a C call that releases the
     GIL): FASTQ ingest of batch i+2 | GPU matching of batch i+1 | host stages + SAM text + file write of batch i.
-    Batches are handed over as copies, so each stage owns its data. Returns counts and per-stage busy times."""
+    The reader fills a ring of six buffer sets (one being filled, one in each queue, one in each of the two later stages,
+    one spare), so batches are handed over without copies. Returns counts and per-stage busy times."""
     import queue
     import threading
     t = {"ingest": 0.0, "gpu": 0.0, "sam": 0.0, "write": 0.0}
@@ -56,7 +57,7 @@ def align_to_sam(pkg, fasta_paths, r1, r2, sam_path, reads_at_once=10_000_000, n
         try:
             while not errs:
                 t0 = time.perf_counter()
-                b = rd.next(reads_at_once, copy=True)
+                b = rd.next(reads_at_once, copy=False)     # ring of 6 buffer sets: at most 4 older batches are still in flight
                 t["ingest"] += time.perf_counter() - t0
                 q_reads.put(b)
                 if b is None:
@@ -84,7 +85,7 @@ def align_to_sam(pkg, fasta_paths, r1, r2, sam_path, reads_at_once=10_000_000, n
             errs.append(e); q_pairs.put(None)
 
     with pkg.Aligner(report_cigar=True, score_threshold=min_alignment_score, device=device) as al, \
-            pkg.FastqReader(r1, r2) as rd, open(sam_path, "wb") as out:
+            pkg.FastqReader(r1, r2, ring=6) as rd, open(sam_path, "wb") as out:
         al.set_debug_taps(False)
         al.load_genomes(gb, go)
         w = pkg.SamWriter(gb, go, tags, num_alignments=num_alignments, score_fraction_threshold=score_fraction_threshold,

@@ -110,3 +110,15 @@ def test_golden_records(pkg, golden, tmp_path):
     flat = [f for b in got for rec in b for f in rec]
     want = [bytes(x) for x in np.split(g["fields"], np.cumsum(g["field_lens"])[:-1])]
     assert flat == want and [len(b) for b in got] == g["batch_sizes"].tolist()
+
+
+def test_ring_keeps_older_batches_valid(pkg, tmp_path):
+    p = str(tmp_path / "ring.fq")
+    write(p, fastq_bytes(90, 3, tricky=False))
+    with pkg.FastqReader(p, None, threads=2, ring=3) as rd:
+        views = [rd.next(10, copy=False) for _ in range(3)]          # three batches alive at once, no copies
+        want = ours(pkg, p, None, 10, 2)
+        assert [v.records() for v in views] == want[:3]
+    with pkg.FastqReader(p, None) as rd:
+        rd.next(10)
+        assert rd.L.kslam_fastq_set_ring(rd.h, 2) != 0               # only before the first batch
