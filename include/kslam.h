@@ -200,8 +200,8 @@ void kslam_fastq_close(kslam_fastq *reader);
  * kslam_sam_batch restates, literally and with the same std::sort calls so that ties fall as in the reference:
  * getPerReadOverlaps, getMaxAllowedInsertSize, screenPairedAlignmentsByInsertSize(replace), screenPairedAlignmentsByScore,
  * pseudoAssembly (+ second score screen) and writeSAMOutputPairs (PairedOverlap.h:314-576, SAM.h:101-517) — the rest
- * of the reference's batch loop for a --sam-file run (SLAM.h:215-239) — on the output of kslam_pair_batch. Paired data
- * only. Gene annotations (XG/XP/XR of GenBank databases) are not carried by this interface. */
+ * of the reference's batch loop for a --sam-file run (SLAM.h:215-239) — on the output of kslam_pair_batch (paired
+ * data) or kslam_align_batch (kslam_sam_batch_single). Gene annotations (XG/XP/XR of GenBank databases) are not carried by this interface. */
 typedef struct {
   uint32_t num_alignments;          /* --num-alignments (numSAMAlignments), default 10 */
   uint8_t pseudo_assembly;          /* 1 unless --no-pseudo-assembly (Globals.h:36) */
@@ -219,6 +219,10 @@ typedef struct {
 int kslam_sam_header(const kslam_sam_db *db, const char *command_line, char **text, uint64_t *len);   /* getHeader, SAM.h:518-531 */
 int kslam_sam_batch(const kslam_sam_params *params, const kslam_sam_db *db, const kslam_read_batch *reads,
                     const kslam_pairs *pairs, char **text, uint64_t *len, uint32_t *max_insert_size /* may be NULL */);
+/* Single-end reads (SLAM.h:223-228): takes kslam_align_batch's output directly; score screen, per-read grouping, one
+ * R1-only record per alignment, score-fraction screen, pseudo-assembly, SAM lines without mate fields. */
+int kslam_sam_batch_single(const kslam_sam_params *params, const kslam_sam_db *db, const kslam_read_batch *reads,
+                           const kslam_alignments *alignments, uint32_t score_threshold, char **text, uint64_t *len);
 void kslam_sam_free(char *text);
 
 /* Stage taps for parity tests (results of the last batch; copy to caller buffers; pass NULL to query

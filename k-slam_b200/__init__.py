@@ -151,6 +151,8 @@ def lib():
     L.kslam_sam_header.argtypes = [C.POINTER(_SamDb), C.c_char_p, C.POINTER(vp), C.POINTER(u64)]
     L.kslam_sam_batch.argtypes = [C.POINTER(SamParams), C.POINTER(_SamDb), C.POINTER(_ReadBatch), C.POINTER(_Pairs), C.POINTER(vp),
                                   C.POINTER(u64), C.POINTER(u32)]
+    L.kslam_sam_batch_single.argtypes = [C.POINTER(SamParams), C.POINTER(_SamDb), C.POINTER(_ReadBatch), C.POINTER(_Alignments), u32,
+                                         C.POINTER(vp), C.POINTER(u64)]
     L.kslam_sam_free.argtypes = [vp]
     L.kslam_sam_free.restype = None
     L.kslam_set_kmer_sort_bits.argtypes = [vp, u32]
@@ -510,6 +512,21 @@ class SamWriter:
         if rc != 0:
             raise KslamError(f"kslam_sam_header failed ({rc})")
         return self._take(ptr, n)
+
+    def batch_single(self, read_bases, read_offs, quals, qual_offs, ids, id_offs, overlaps, cigar_pool, score_threshold=0):
+        """Single-end reads: SAM text from align_batch's output (kslam_sam_batch_single)."""
+        rb, ro, q, qo, i, io = _u8(read_bases), _u64(read_offs), _u8(quals), _u64(qual_offs), _u8(ids), _u64(id_offs)
+        n = len(ro) - 1
+        reads = _ReadBatch(n, n, rb.ctypes.data, ro.ctypes.data, q.ctypes.data, qo.ctypes.data, i.ctypes.data, io.ctypes.data)
+        ov = np.ascontiguousarray(overlaps, dtype=OVERLAP_DT); cg = np.ascontiguousarray(cigar_pool, dtype=np.uint32)
+        a = _Alignments()
+        a.n_overlaps = len(ov); a.overlaps = ov.ctypes.data if len(ov) else None
+        a.n_cigar_words = len(cg); a.cigar_pool = cg.ctypes.data if len(cg) else None
+        ptr, ln = C.c_void_p(), C.c_uint64()
+        rc = self.L.kslam_sam_batch_single(C.byref(self.prm), C.byref(self.db), C.byref(reads), C.byref(a), score_threshold, C.byref(ptr), C.byref(ln))
+        if rc != 0:
+            raise KslamError(f"kslam_sam_batch_single failed ({rc})")
+        return self._take(ptr, ln)
 
     def batch(self, read_bases, read_offs, quals, qual_offs, ids, id_offs, sorted_overlaps, cigar_pool, pairs, out_file=None):
         """-> (SAM text of the batch, max allowed insert size); with out_file the text is written to it straight from the

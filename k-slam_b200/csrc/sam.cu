@@ -45,6 +45,7 @@ template <class F> void parallel_ranges(uint32_t threads, size_t n, F f) {
 
 struct Ctx {
   const kslam_sam_params *prm; const kslam_sam_db *db; const kslam_read_batch *reads; const kslam_pairs *in;
+  bool paired;                     // Globals.h pairedData
   std::string read_id(uint32_t i) const { return std::string(reads->ids + reads->id_offs[i], reads->ids + reads->id_offs[i + 1]); }
   std::string locus(uint32_t e) const { return std::string(db->locus_tags + db->locus_offs[e], db->locus_tags + db->locus_offs[e + 1]); }
 };
@@ -315,7 +316,7 @@ struct SAMEntry {                                        // SAM.h:240-281
   double prob = 0;
 };
 
-uint16_t sam_flag(const SAMEntry &e) {                   // SAM.h:309-326 (pairedData = true)
+uint16_t sam_flag(const SAMEntry &e, bool pairedData) {  // SAM.h:309-326
   uint16_t flag = 0;
   if (e.multipleSegments) flag |= 0x1;
   if (e.allSegmentsAligned) flag |= 0x2;
@@ -323,13 +324,13 @@ uint16_t sam_flag(const SAMEntry &e) {                   // SAM.h:309-326 (paire
   if (e.nextSegmentUnmapped) flag |= 0x8;
   if (e.revComp) flag |= 0x10;
   if (e.nextRevComp) flag |= 0x20;
-  flag |= e.first ? 0x40 : 0x80;
+  if (pairedData) flag |= e.first ? 0x40 : 0x80;
   if (e.secondary) flag |= 0x100;
   return flag;
 }
 
-void sam_line(std::string &out, const SAMEntry &e, bool reportCigar) {   // SAMEntry::getEntry, SAM.h:282-308, + '\n'
-  out += e.qname; out.push_back('\t'); put_uint(out, sam_flag(e)); out.push_back('\t');
+void sam_line(std::string &out, const SAMEntry &e, bool reportCigar, bool pairedData) {   // SAMEntry::getEntry, SAM.h:282-308, + '\n'
+  out += e.qname; out.push_back('\t'); put_uint(out, sam_flag(e, pairedData)); out.push_back('\t');
   out += e.rname; out.push_back('\t'); put_uint(out, e.pos); out.push_back('\t'); put_uint(out, e.mapq); out.push_back('\t');
   if (reportCigar) out += e.cigar; else out.push_back('*');
   out.push_back('\t'); out += e.rnext; out.push_back('\t'); put_uint(out, e.pnext); out.push_back('\t'); put_int(out, e.tlen);
@@ -362,7 +363,7 @@ std::pair<SAMEntry, SAMEntry> sam_from_pair(const Ctx &c, const POv &ap) {      
   r1.XT = tax; r2.XT = tax;
   bool conventionalSequence = true;
   bool bothAligned = ap.hasR1 && ap.hasR2;
-  r1.multipleSegments = true; r2.multipleSegments = true;
+  if (c.paired) { r1.multipleSegments = true; r2.multipleSegments = true; }
   if (bothAligned) {
     r1.allSegmentsAligned = true; r2.allSegmentsAligned = true;
     conventionalSequence = ov[ap.r1].ref_begin < ov[ap.r2].ref_begin;
@@ -380,6 +381,7 @@ std::pair<SAMEntry, SAMEntry> sam_from_pair(const Ctx &c, const POv &ap) {      
   r1.pnext = r2.pos; r2.pnext = r1.pos;
   if (!ap.hasR1) { r1.rname = r2.rname; r1.pos = r2.pos; r2.pnext = r2.pos; r1.pnext = r2.pos; }
   if (!ap.hasR2) { r2.rname = r1.rname; r2.pos = r1.pos; r1.pnext = r1.pos; r2.pnext = r1.pos; }
+  if (!c.paired) { r1.rnext = "*"; r1.pnext = 0; r1.nextSegmentUnmapped = false; }     // SAM.h:425-429
   int32_t tlen = ap.refEnd - ap.refStart + 1;
   if (!(ap.hasR1 || ap.hasR2)) tlen = 0;
   if (!conventionalSequence) tlen *= -1;
@@ -416,8 +418,8 @@ void write_pairs(std::string &out, const Ctx &c, ReadPair &read) {              
     if (temp2 <= 0.00001) temp2 = 0.00001;
     sp->first.mapq = ceil(-10.0 * std::log10(temp));
     sp->second.mapq = ceil(-10.0 * std::log10(temp2));
-    sam_line(out, sp->first, c.prm->report_cigar != 0);
-    sam_line(out, sp->second, c.prm->report_cigar != 0);
+    sam_line(out, sp->first, c.prm->report_cigar != 0, c.paired);
+    if (c.paired) sam_line(out, sp->second, c.prm->report_cigar != 0, c.paired);
     if (c.prm->sam_xa) break;
   }
 }
@@ -452,56 +454,104 @@ int kslam_sam_header(const kslam_sam_db *db, const char *command_line, char **te
   return *text ? KSLAM_OK : KSLAM_ERR_NOMEM;
 }
 
+// everything after the per-read grouping: screens, pseudo-assembly, records, text (shared by paired and single-end input)
+static int sam_finish(Ctx &c, std::vector<ReadPair> &rp, bool insert_screen, char **text, uint64_t *len, uint32_t *max_insert_size) {
+  const kslam_sam_params *prm = c.prm;
+  const bool trace = getenv("KSLAM_SAM_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t1 = now();
+  uint32_t threads = prm->threads ? prm->threads : std::max(1u, std::thread::hardware_concurrency());
+  if (threads > 64) threads = 64;
+  if (insert_screen) {
+    const uint32_t maxInsert = max_allowed_insert_size(rp);
+    if (max_insert_size) *max_insert_size = maxInsert;
+    screen_by_insert_size(rp, c.in->sorted_overlaps, maxInsert, threads);
+  } else if (max_insert_size) *max_insert_size = UINT32_MAX;
+  double t2 = now();
+  screen_by_score(rp, prm->score_fraction_threshold, threads);
+  if (prm->pseudo_assembly) { pseudo_assembly(rp, threads); screen_by_score(rp, prm->score_fraction_threshold, threads); }
+  double t3 = now();
+  std::vector<std::string> parts(threads);
+  parallel_ranges(threads, rp.size(), [&](uint32_t t, size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; i++) write_pairs(parts[t], c, rp[i]);
+  });
+  size_t total = 0;
+  std::vector<size_t> at(threads + 1, 0);
+  for (uint32_t t = 0; t < threads; t++) { at[t] = total; total += parts[t].size(); }
+  char *buf = (char *)malloc(total + 1);                      // the threads' pieces go straight into the result buffer
+  if (buf) {
+    parallel_ranges(threads, threads, [&](uint32_t, size_t lo, size_t hi) {
+      for (size_t t = lo; t < hi; t++) memcpy(buf + at[t], parts[t].data(), parts[t].size());
+    });
+    buf[total] = 0;
+  }
+  *text = buf;
+  if (len) *len = total;
+  if (trace) fprintf(stderr, "[kslam_sam] insert limit + screen %.1f ms, score screens + assembly %.1f ms, records %.1f ms (incl. concat), %u threads\n",
+                     (t2 - t1) * 1e3, (t3 - t2) * 1e3, (now() - t3) * 1e3, threads);
+  return buf ? KSLAM_OK : KSLAM_ERR_NOMEM;
+}
+
+static int check_overlaps(const kslam_sam_db *db, const kslam_read_batch *reads, const kslam_overlap *ov, uint64_t n, const uint32_t *pool,
+                          uint64_t n_pool) {
+  // the records index each other and the read / entry arrays: refuse anything out of range instead of reading past a buffer
+  for (uint64_t i = 0; i < n; i++) {
+    const kslam_overlap &o = ov[i];
+    if (o.read >= reads->n_reads || o.entry >= db->n_entries) return KSLAM_ERR_ARG;
+    if (o.cigar_len && pool && (uint64_t)o.cigar_off + o.cigar_len > n_pool) return KSLAM_ERR_ARG;
+  }
+  return KSLAM_OK;
+}
+
 int kslam_sam_batch(const kslam_sam_params *prm, const kslam_sam_db *db, const kslam_read_batch *reads, const kslam_pairs *pairs,
                     char **text, uint64_t *len, uint32_t *max_insert_size) {
   if (!prm || !db || !reads || !pairs || !text) return KSLAM_ERR_ARG;
   if (pairs->n_pairs && (!pairs->pairs || !pairs->sorted_overlaps)) return KSLAM_ERR_ARG;
-  // the records index each other and the read / entry arrays: refuse anything out of range instead of reading past a buffer
-  for (uint64_t i = 0; i < pairs->n_sorted; i++) {
-    const kslam_overlap &o = pairs->sorted_overlaps[i];
-    if (o.read >= reads->n_reads || o.entry >= db->n_entries) return KSLAM_ERR_ARG;
-    if (o.cigar_len && pairs->cigar_pool && (uint64_t)o.cigar_off + o.cigar_len > pairs->n_cigar_words) return KSLAM_ERR_ARG;
-  }
+  if (check_overlaps(db, reads, pairs->sorted_overlaps, pairs->n_sorted, pairs->cigar_pool, pairs->n_cigar_words) != KSLAM_OK) return KSLAM_ERR_ARG;
   for (uint64_t i = 0; i < pairs->n_pairs; i++) {
     const kslam_pair &k = pairs->pairs[i];
     if ((k.r1_idx < 0 && k.r2_idx < 0) || k.r1_idx >= (int64_t)pairs->n_sorted || k.r2_idx >= (int64_t)pairs->n_sorted ||
         k.entry >= db->n_entries) return KSLAM_ERR_ARG;
   }
   try {
-    Ctx c{prm, db, reads, pairs};
-    const bool trace = getenv("KSLAM_SAM_TRACE") != nullptr;
-    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    double t0 = now();
+    Ctx c{prm, db, reads, pairs, true};
     auto rp = per_read(pairs, (uint32_t)(reads->n_reads / 2));
-    double t1 = now();
-    const uint32_t maxInsert = max_allowed_insert_size(rp);
-    double t2 = now();
-    if (max_insert_size) *max_insert_size = maxInsert;
-    uint32_t threads = prm->threads ? prm->threads : std::max(1u, std::thread::hardware_concurrency());
-    if (threads > 64) threads = 64;
-    screen_by_insert_size(rp, pairs->sorted_overlaps, maxInsert, threads);
-    screen_by_score(rp, prm->score_fraction_threshold, threads);
-    if (prm->pseudo_assembly) { pseudo_assembly(rp, threads); screen_by_score(rp, prm->score_fraction_threshold, threads); }
-    double t3 = now();
-    std::vector<std::string> parts(threads);
-    parallel_ranges(threads, rp.size(), [&](uint32_t t, size_t lo, size_t hi) {
-      for (size_t i = lo; i < hi; i++) write_pairs(parts[t], c, rp[i]);
-    });
-    size_t total = 0;
-    std::vector<size_t> at(threads + 1, 0);
-    for (uint32_t t = 0; t < threads; t++) { at[t] = total; total += parts[t].size(); }
-    char *buf = (char *)malloc(total + 1);                      // the threads' pieces go straight into the result buffer
-    if (buf) {
-      parallel_ranges(threads, threads, [&](uint32_t, size_t lo, size_t hi) {
-        for (size_t t = lo; t < hi; t++) memcpy(buf + at[t], parts[t].data(), parts[t].size());
-      });
-      buf[total] = 0;
+    return sam_finish(c, rp, true, text, len, max_insert_size);
+  } catch (const std::exception &) { return KSLAM_ERR_NOMEM; }
+}
+
+// Single-end reads (SLAM.h:223-228): alignToDatabase's vector, score screen (Overlap.h:329-341), getPerReadOverlaps
+// (Overlap.h:302-327), one R1-only dummy pair per overlap (getDummyAlignmentPairsFromSingleEndReads, PairedOverlap.h:280-298),
+// then the same screens / pseudo-assembly / records with pairedData = false (one line per alignment, no mate fields).
+int kslam_sam_batch_single(const kslam_sam_params *prm, const kslam_sam_db *db, const kslam_read_batch *reads,
+                           const kslam_alignments *al, uint32_t score_threshold, char **text, uint64_t *len) {
+  if (!prm || !db || !reads || !al || !text) return KSLAM_ERR_ARG;
+  if (al->n_overlaps && !al->overlaps) return KSLAM_ERR_ARG;
+  if (check_overlaps(db, reads, al->overlaps, al->n_overlaps, al->cigar_pool, al->n_cigar_words) != KSLAM_OK) return KSLAM_ERR_ARG;
+  try {
+    kslam_pairs view;
+    memset(&view, 0, sizeof view);
+    view.sorted_overlaps = al->overlaps; view.n_sorted = al->n_overlaps;
+    view.cigar_pool = al->cigar_pool; view.n_cigar_words = al->n_cigar_words;
+    Ctx c{prm, db, reads, &view, false};
+    std::vector<ReadPair> rp;
+    ReadPair cur;
+    uint32_t readPos = 0;
+    for (uint64_t i = 0; i < al->n_overlaps; i++) {
+      const kslam_overlap &o = al->overlaps[i];
+      if (o.sw_score < score_threshold) continue;             // screenOverlapsByScoreThreshold
+      if (o.read != readPos) {
+        if (cur.pairs.size()) { rp.push_back(std::move(cur)); cur.pairs.clear(); }
+        readPos = o.read;
+      }
+      POv p;
+      p.combinedScore = (uint16_t)o.sw_score; p.entry = o.entry; p.refStart = o.ref_begin; p.refEnd = o.ref_end;
+      p.insertSize = 0; p.hasR1 = true; p.hasR2 = false; p.r1 = (int32_t)i; p.r2 = -1;
+      cur.pairs.push_back(p);
+      cur.r1Pos = o.read; cur.r2Pos = 0;
     }
-    *text = buf;
-    if (len) *len = total;
-    if (trace) fprintf(stderr, "[kslam_sam] per_read %.1f ms, insert limit %.1f ms, screens + assembly %.1f ms, records %.1f ms (incl. concat), %u threads\n",
-                       (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (now() - t3) * 1e3, threads);
-    return *text ? KSLAM_OK : KSLAM_ERR_NOMEM;
+    if (cur.pairs.size()) rp.push_back(cur);
+    return sam_finish(c, rp, false, text, len, nullptr);
   } catch (const std::exception &) { return KSLAM_ERR_NOMEM; }
 }
 

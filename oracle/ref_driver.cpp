@@ -272,6 +272,28 @@ uint64_t kref_sam(void *h, uint32_t num_alignments, double fraction, int pseudo,
   if (buf && cap >= text.size()) memcpy(buf, text.data(), text.size());
   return text.size();
 }
+// single-end flavour of the same loop body (SLAM.h:223-228) on the overlaps kref_align_to_database + kref_screen left
+uint64_t kref_sam_single(void *h, uint32_t num_alignments, double fraction, int pseudo, int sam_xa, const char *tmp_path,
+                         char *buf, uint64_t cap) {
+  KrefCtx *c = (KrefCtx *)h;
+  numSAMAlignments = num_alignments; scoreFractionThreshold = fraction; SAMXA = sam_xa != 0; pairedData = false;
+  auto perRead = getPerReadOverlaps(c->overlaps.begin(), c->overlaps.end());
+  auto rp = getDummyAlignmentPairsFromSingleEndReads(perRead, c->reads);
+  screenPairedAlignmentsByScore(rp, scoreFractionThreshold);
+  if (pseudo) {
+    pseudoAssembly(rp, c->reads, c->idx);
+    screenPairedAlignmentsByScore(rp, scoreFractionThreshold);
+  }
+  {
+    std::ofstream sam(tmp_path);
+    for (auto &read : rp) writeSAMOutputPairs(sam, read, c->reads, c->idx);
+  }
+  pairedData = true;
+  std::ifstream in(tmp_path, std::ios::binary);
+  std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  if (buf && cap >= text.size()) memcpy(buf, text.data(), text.size());
+  return text.size();
+}
 uint64_t kref_sam_header(void *h, const char *cmd, char *buf, uint64_t cap) {
   KrefCtx *c = (KrefCtx *)h;
   commandLine = cmd;

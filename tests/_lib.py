@@ -120,6 +120,8 @@ def ref():
         L.kref_set_read_quals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.kref_sam.restype = C.c_uint64
         L.kref_sam.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
+        L.kref_sam_single.restype = C.c_uint64
+        L.kref_sam_single.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_int, C.c_int, C.c_char_p, C.c_void_p, C.c_uint64]
         L.kref_sam_header.restype = C.c_uint64
         L.kref_sam_header.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64]
         L.kref_fastq_open.restype = C.c_void_p
@@ -296,6 +298,19 @@ def ref_sam(R, quals=None, qual_offs=None, num_alignments=10, fraction=0.95, pse
     os.unlink(tmp.name)
     assert n <= len(buf)
     return bytes(buf[:n]), mi.value
+
+
+def ref_sam_single(R, quals=None, qual_offs=None, num_alignments=10, fraction=0.95, pseudo=True, sam_xa=False):
+    """Single-end flavour (SLAM.h:223-228) on a Ref context that has run align_to_database() and kref_screen."""
+    L = R.L
+    if quals is not None:
+        q = u8(quals); qo = np.ascontiguousarray(qual_offs, dtype=np.uint64)
+        L.kref_set_read_quals(R.h, _p(q), _p(qo))
+    tmp = tempfile.NamedTemporaryFile(suffix=".sam", delete=False); tmp.close()
+    buf = np.zeros(1 << 26, dtype=np.uint8)
+    n = L.kref_sam_single(R.h, num_alignments, fraction, int(pseudo), int(sam_xa), tmp.name.encode(), _p(buf), len(buf))
+    os.unlink(tmp.name)
+    return bytes(buf[:n])
 
 
 def ref_sam_header(R, cmd=""):

@@ -400,3 +400,19 @@ def test_fastq_to_sam_equals_reference(pkg, tmp_path, kind, seed):
         want = b"".join(reference(lo, min(lo + at_once, mid)) for lo in range(0, mid, at_once))
         assert st["pairs"] == mid and len(want) > 10_000
         assert body == want
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="needs the prebuilt oracle/_ref")
+def test_single_end_gpu_to_sam_equals_reference(pkg):
+    """Single-end reads: kslam_align_batch on the GPU -> kslam_sam_batch_single, against the reference's single-end chain."""
+    from test_sam_host import make_inputs
+    gb, go, rb, ro, quals, idb, ido = make_inputs(pkg, 95, n_pairs=500, kind="related")
+    R = T.Ref(gb, go, rb, ro, T.default_params(report_cigar=1))
+    R.align_to_database(); R.L.kref_screen(R.h)
+    want = T.ref_sam_single(R, quals, ro)
+    R.close()
+    with pkg.Aligner(report_cigar=True) as al:
+        al.load_genomes(gb, go)
+        res = al.align_batch(rb, ro)
+    w = pkg.SamWriter(gb, go, [f"g{i}" for i in range(len(go) - 1)], report_cigar=True)
+    assert w.batch_single(rb, ro, quals, ro, idb, ido, res.overlaps, res.cigar_pool) == want and len(want) > 10_000

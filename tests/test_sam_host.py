@@ -82,3 +82,25 @@ def test_sam_rejects_out_of_range_records(pkg, golden):
         (ov if arr == "ov" else pairs)[field][0] = bad
         with pytest.raises(pkg.KslamError):
             w.batch(*args, ov, g["pool"], pairs)
+
+
+@pytest.mark.skipif(not T.have_ref(), reason="needs oracle/_ref")
+@pytest.mark.parametrize("kind,seed,thr", [("adversarial", 91, 0), ("related", 92, 0), ("config1", 93, 120)])
+def test_single_end_sam_equals_reference(pkg, kind, seed, thr):
+    """Single-end reads (SLAM.h:223-228): the same reads treated as one unpaired set."""
+    gb, go, rb, ro, quals, idb, ido = make_inputs(pkg, seed, kind=kind)
+    tags = [f"g{i}" for i in range(len(go) - 1)]
+    for kw in (dict(), dict(pseudo=False, num_alignments=2), dict(sam_xa=True)):
+        R = T.Ref(gb, go, rb, ro, T.default_params(report_cigar=1, score_threshold=thr))
+        ov_all, pool_all = R.align_to_database()
+        R.L.kref_screen(R.h)
+        want = T.ref_sam_single(R, quals, ro, **kw)
+        R.close()
+        assert len(want) > 1000
+        w = pkg.SamWriter(gb, go, tags, num_alignments=kw.get("num_alignments", 10), pseudo_assembly=kw.get("pseudo", True),
+                          report_cigar=True, sam_xa=kw.get("sam_xa", False))
+        got = w.batch_single(rb, ro, quals, ro, idb, ido, ov_all, pool_all, score_threshold=thr)
+        if got != want:
+            a, b = got.split(b"\n"), want.split(b"\n")
+            bad = [(i, x, y) for i, (x, y) in enumerate(zip(a, b)) if x != y][:3]
+            raise AssertionError((kw, len(a), len(b), bad))
