@@ -39,8 +39,20 @@ def parse_fasta(paths):
     return bases, offs, tags
 
 
+def load_database(fasta_paths=None, db_dir=None):
+    """The genomes either from FASTA files (parsed as --parse-fasta does) or from a SLAM database directory (`--db DIR`:
+    DIR/database, database.py — format parity unpinned, see there). -> (bases, offs, locus tags, taxonomy ids or None)"""
+    if db_dir:
+        import os
+        from . import database
+        gb, go, tags, tax = database.flatten(database.read_database(os.path.join(db_dir, "database")))
+        return gb, go, tags, tax
+    gb, go, tags = parse_fasta(fasta_paths)
+    return gb, go, tags, None
+
+
 def align_to_sam(pkg, fasta_paths, r1, r2, sam_path, reads_at_once=10_000_000, num_alignments=10, score_fraction_threshold=0.95,
-                 pseudo_assembly=True, sam_xa=False, min_alignment_score=0, command_line="", device=0, log=None):
+                 pseudo_assembly=True, sam_xa=False, min_alignment_score=0, command_line="", device=0, log=None, db_dir=None):
     """The batch loop as a three-stage pipeline, one host thread per stage (every heavy call is a C call that releases the
     GIL): FASTQ ingest of batch i+2 | GPU matching of batch i+1 | host stages + SAM text + file write of batch i.
     The reader fills a ring of six buffer sets (one being filled, one in each queue, one in each of the two later stages,
@@ -48,7 +60,7 @@ def align_to_sam(pkg, fasta_paths, r1, r2, sam_path, reads_at_once=10_000_000, n
     import queue
     import threading
     t = {"ingest": 0.0, "gpu": 0.0, "sam": 0.0, "write": 0.0}
-    gb, go, tags = parse_fasta(fasta_paths)
+    gb, go, tags, tax = load_database(fasta_paths, db_dir)
     stats = {"pairs": 0, "batches": 0, "sam_bytes": 0}
     errs = []
     q_reads, q_pairs = queue.Queue(maxsize=1), queue.Queue(maxsize=1)
@@ -88,7 +100,7 @@ def align_to_sam(pkg, fasta_paths, r1, r2, sam_path, reads_at_once=10_000_000, n
             pkg.FastqReader(r1, r2, ring=6) as rd, open(sam_path, "wb") as out:
         al.set_debug_taps(False)
         al.load_genomes(gb, go)
-        w = pkg.SamWriter(gb, go, tags, num_alignments=num_alignments, score_fraction_threshold=score_fraction_threshold,
+        w = pkg.SamWriter(gb, go, tags, taxonomy_ids=tax, num_alignments=num_alignments, score_fraction_threshold=score_fraction_threshold,
                           pseudo_assembly=pseudo_assembly, report_cigar=True, sam_xa=sam_xa)
         out.write(w.header(command_line))
         th = [threading.Thread(target=stage_ingest, args=(rd,)), threading.Thread(target=stage_gpu, args=(al,))]
