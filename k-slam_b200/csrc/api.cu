@@ -30,6 +30,7 @@ __global__ void k_read_small(uint32_t *__restrict__ dst_host, const uint32_t *__
 }
 void read_small(kslam_ctx *c, void *host_pinned, const void *dev, size_t bytes) {
   k_read_small<<<1, 32, 0, c->stream>>>((uint32_t *)host_pinned, (const uint32_t *)dev, (uint32_t)(bytes / 4));
+  c->launches++;
   CUDA_TRY(cudaGetLastError());
 }
 
