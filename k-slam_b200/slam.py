@@ -12,26 +12,41 @@ import numpy as np
 
 
 def parse_fasta(paths):
-    """createIndexFromFASTA, GenbankTools.h:224-260. Returns (bases u8, offs u64, locus tags)."""
+    """createIndexFromFASTA, GenbankTools.h:224-260. Returns (bases u8, offs u64, locus tags).
+    A line is a header when it starts with '>' (locus tag = the text up to the first space, if there is one and it is not
+    the first character); every other non-empty line is appended to the current entry; entries without bases are dropped;
+    one GenbankEntry object is reused per file, so bases seen before the first header of a file form an entry too."""
     entries, tags = [], []
+
+    def close(cur, tag):
+        seq = b"".join(cur)
+        if seq:
+            entries.append(seq); tags.append(tag)
+
     for path in paths:
-        cur, tag, have = [], b"", False
         with open(path, "rb") as f:
             data = f.read()
-        for line in data.replace(b"\r\n", b"\n").replace(b"\r", b"\n").split(b"\n"):
-            if not line:
-                continue
-            if line[:1] == b">":
-                if sum(len(x) for x in cur):
-                    entries.append(b"".join(cur)); tags.append(tag)
+        if b"\r" in data:                       # safeGetline also ends lines at "\r\n" and lone "\r"
+            data = data.replace(b"\r\n", b"\n").replace(b"\r", b"\n")
+        cur, tag = [], b""
+        pos, n = 0, len(data)
+        while pos < n:
+            if data[pos:pos + 1] == b">":
+                close(cur, tag)
                 cur, tag = [], b""
+                end = data.find(b"\n", pos)
+                end = n if end < 0 else end
+                line = data[pos:end]
                 sp = line.find(b" ")
                 if sp not in (-1, 0):
                     tag = line[1:sp]
-            else:
-                cur.append(line)
-        if sum(len(x) for x in cur):
-            entries.append(b"".join(cur)); tags.append(tag)
+                pos = end + 1
+            else:                                  # a block of sequence lines up to the next header line
+                nxt = data.find(b"\n>", pos)
+                end = n if nxt < 0 else nxt + 1
+                cur.append(data[pos:end].translate(None, b"\n"))
+                pos = end
+        close(cur, tag)
     entries = [e.upper() for e in entries]            # inPlaceConvertToUpperCase
     offs = np.zeros(len(entries) + 1, dtype=np.uint64)
     offs[1:] = np.cumsum([len(e) for e in entries])
