@@ -207,6 +207,54 @@ def run_config3(args, pkg):
           "sw_gcups": live["gcups"], "shapes": shapes, "int_peak_thread_ops_per_s": int_peak})
 
 
+def run_fastq_to_sam(args, pkg):
+    """--workload sam: the --just-align --sam-file run end to end, FASTQ text + FASTA in, SAM text out (config-1 data),
+    through slam.align_to_sam (reader | GPU | host stages + SAM writer pipeline). Wall clock of the whole call, including
+    FASTA parsing, index build and pipeline fill; per-stage busy times alongside."""
+    import tempfile
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the matching path has no CPU fallback")
+    from kslam_b200 import slam
+    pairs = args.pairs or 4_000_000
+    at_once = 1_000_000
+    gb, go = pkg.synth.random_genomes(50, 3_000_000, seed=1)
+    rb, ro, _ = pkg.synth.paired_reads(gb, go, pairs, seed=2)
+    d = tempfile.mkdtemp(prefix="kslam_bench_")
+    fa = os.path.join(d, "db.fa")
+    with open(fa, "wb") as f:
+        for i in range(len(go) - 1):
+            f.write(b">g%02d synthetic\n" % i + gb[int(go[i]):int(go[i + 1])].tobytes() + b"\n")
+    paths = []
+    for k in range(2):
+        rows = rb.reshape(-1, 150)[k * pairs:(k + 1) * pairs]
+        p = os.path.join(d, f"R{k + 1}.fq"); paths.append(p)
+        with open(p, "wb") as f:
+            for lo in range(0, pairs, 100_000):
+                blk = rows[lo:lo + 100_000]
+                f.write(b"".join(b"@r%d/%d\n" % (lo + i, k + 1) + blk[i].tobytes() + b"\n+\n" + b"I" * 150 + b"\n" for i in range(len(blk))))
+    in_bytes = sum(os.path.getsize(p) for p in paths)
+    runs = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        st = slam.align_to_sam(pkg, [fa], paths[0], paths[1], os.path.join(d, "out.sam"), reads_at_once=at_once)
+        dt = time.perf_counter() - t0
+        log(f"[bench/sam] run {i}: {pairs} pairs in {dt:.2f}s, stage busy {st['seconds']}")
+        if i >= args.warmup:
+            runs.append((dt, st))
+    dt = float(np.mean([r[0] for r in runs])); st = runs[-1][1]
+    for p in paths + [fa, os.path.join(d, "out.sam")]:
+        os.unlink(p)
+    os.rmdir(d)
+    emit({"metric": METRIC, "value": pairs / dt * 60 / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+          "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16x2 (SW) / u64 (k-mers) / f64 (MAPQ)",
+          "data": "synthetic",
+          "config": {"workload": f"FASTQ -> SAM whole process: {pairs} x 150bp FR pairs (FASTQ text, {in_bytes / 1e9:.2f} GB) vs 50 x 3 Mbp genomes (FASTA), "
+                                 f"--num-reads-at-once {at_once}, pseudo-assembly on, 10 alignments per read, CIGAR/MD/NM/MAPQ",
+                     "includes": "FASTA parse, index build, FASTQ ingest, GPU matching path, host screens + pseudo-assembly + SAM text, file write"},
+          "stage_busy_s": st["seconds"], "sam_bytes": st["sam_bytes"], "batches": st["batches"]})
+
+
 def run_reference_arm(args, pkg):
     """--impl reference: the reference's CPU path on this box's host cores, same config/metric/unit."""
     rank = int(os.environ.get("RANK", "0"))
@@ -243,7 +291,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kslam", choices=["kslam", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("KSLAM_BENCH_WORKLOAD", "config2"), choices=["config1", "config2", "config3", "config4"])
+    ap.add_argument("--workload", default=os.environ.get("KSLAM_BENCH_WORKLOAD", "config2"), choices=["config1", "config2", "config3", "config4", "sam"])
     ap.add_argument("--pairs", type=int, default=0, help="read pairs per batch per GPU (default: the config's)")
     ap.add_argument("--ref-sample", type=int, default=0, help="pairs per step for the CPU reference arm (0 = per workload)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs for the cpu_baseline leg (rank 0, N=1; 0 = per workload)")
@@ -253,6 +301,8 @@ def main():
     pkg = ge.load_pkg()
     if args.workload == "config3":
         return run_config3(args, pkg)
+    if args.workload == "sam":
+        return run_fastq_to_sam(args, pkg)
     if args.impl == "reference":
         return run_reference_arm(args, pkg)
 
