@@ -201,7 +201,8 @@ void kslam_fastq_close(kslam_fastq *reader);
  * getPerReadOverlaps, getMaxAllowedInsertSize, screenPairedAlignmentsByInsertSize(replace), screenPairedAlignmentsByScore,
  * pseudoAssembly (+ second score screen) and writeSAMOutputPairs (PairedOverlap.h:314-576, SAM.h:101-517) — the rest
  * of the reference's batch loop for a --sam-file run (SLAM.h:215-239) — on the output of kslam_pair_batch (paired
- * data) or kslam_align_batch (kslam_sam_batch_single). Gene annotations (XG/XP/XR of GenBank databases) are not carried by this interface. */
+ * data) or kslam_align_batch (kslam_sam_batch_single). With a gene table in kslam_sam_db the records carry XG / XP / XR of the gene
+ * with the largest overlap (GenbankEntry::getGene, GenbankTools.h:170-185; SAM.h:361-370). */
 typedef struct {
   uint32_t num_alignments;          /* --num-alignments (numSAMAlignments), default 10 */
   uint8_t pseudo_assembly;          /* 1 unless --no-pseudo-assembly (Globals.h:36) */
@@ -210,11 +211,21 @@ typedef struct {
   uint8_t threads;                  /* host threads (stages are independent per read pair / per entry); 0 = all cores */
   double score_fraction_threshold;  /* --score-fraction-threshold, default 0.95 */
 } kslam_sam_params;
+/* Gene (GenbankTools.h:67-110): string i of {geneName, locusTag, proteinID, product, referenceSequence} =
+ * gene_strings[str_offs[i] .. str_offs[i+1]). */
+typedef struct kslam_gene {
+  uint32_t cds_start, cds_stop;     /* CDS::start / stop as parsed (GenbankTools.h:389-413) */
+  uint32_t gene_id, complement;
+  uint64_t str_offs[6];
+} kslam_gene;
 typedef struct {
   uint64_t n_entries;
   const char *bases; const uint64_t *offs;             /* GenbankEntry::bases, as given to kslam_load_genomes */
   const char *locus_tags; const uint64_t *locus_offs;  /* GenbankEntry::locusTag of entry e = locus_tags[locus_offs[e] .. locus_offs[e+1]) */
   const uint32_t *taxonomy_ids;                        /* GenbankEntry::taxonomyID, may be NULL (all 0) */
+  /* GenbankEntry::genes of GenBank databases (GenbankTools.h:67-110,149); all three NULL for FASTA databases.
+   * Entry e owns genes[gene_offs[e] .. gene_offs[e+1]), in the entry's stored order. */
+  const kslam_gene *genes; const uint64_t *gene_offs; const char *gene_strings;
 } kslam_sam_db;
 int kslam_sam_header(const kslam_sam_db *db, const char *command_line, char **text, uint64_t *len);   /* getHeader, SAM.h:518-531 */
 int kslam_sam_batch(const kslam_sam_params *params, const kslam_sam_db *db, const kslam_read_batch *reads,
@@ -224,6 +235,54 @@ int kslam_sam_batch(const kslam_sam_params *params, const kslam_sam_db *db, cons
 int kslam_sam_batch_single(const kslam_sam_params *params, const kslam_sam_db *db, const kslam_read_batch *reads,
                            const kslam_alignments *alignments, uint32_t score_threshold, char **text, uint64_t *len);
 void kslam_sam_free(char *text);
+
+/* ---- taxonomy and the metagenomic outputs (host side; the part of the batch loop after the SAM records, SLAM.h:243-265) --
+ * kslam_taxdb  = TaxonomyDB (TaxonomyDatabase.h:45-348): the `taxDB` file of a --db directory (four lines per node: id,
+ *                parent id, scientific name, rank — readTaxonomyIndex :166-183) or NCBI names.dmp / nodes.dmp
+ *                (--parse-taxonomy, writeTaxonomyIndex :153-164).
+ * kslam_taxa   = the run's std::vector<IdentifiedTaxonomy> (MetagenomicResults.h:32-42), grown batch by batch.
+ * kslam_batch_outputs = kslam_sam_batch (SAM text optional) followed by convertAlignmentsToIdentifiedTaxonomies_parallel
+ *                (MetagenomicResults.h:88-111,182-197) on the same per-read records: per read pair the LCA
+ *                (getLowestCommonAncestor, TaxonomyDatabase.h:185-223) of the entries it still aligns to, plus the best
+ *                gene of every alignment. db (bases, gene table) must stay valid until kslam_taxa_results.
+ * kslam_taxa_results  = writePerReadResults, combineTaxonomies, writeResults (XML) and writeAbbreviatedResultsFile
+ *                (MetagenomicResults.h:149-176,213-275,302-369,455-463): the texts of <out>_PerRead, <out> and
+ *                <out>_abbreviated. combineTaxonomies orders reads by taxon with the sequential std::sort, i.e. the
+ *                reference run with one OpenMP thread (its __gnu_parallel::sort is thread-count dependent on ties). */
+typedef struct kslam_taxdb kslam_taxdb;
+typedef struct kslam_taxa kslam_taxa;
+int kslam_taxdb_open(const char *taxdb_path, kslam_taxdb **out);
+int kslam_taxdb_build(const char *names_dmp, const char *nodes_dmp, const char *out_path);       /* --parse-taxonomy */
+uint64_t kslam_taxdb_size(const kslam_taxdb *db);
+uint32_t kslam_taxdb_lca(const kslam_taxdb *db, const uint32_t *tax_ids, uint64_t n);
+int kslam_taxdb_lineage(const kslam_taxdb *db, uint32_t tax_id, char **text, uint64_t *len);     /* getLineage :249-265; free with kslam_sam_free */
+int kslam_taxdb_name(const kslam_taxdb *db, uint32_t tax_id, char **text, uint64_t *len);        /* getScientificName :233-239 */
+void kslam_taxdb_close(kslam_taxdb *db);
+int kslam_taxa_create(kslam_taxa **out);
+void kslam_taxa_destroy(kslam_taxa *taxa);
+int kslam_batch_outputs(const kslam_sam_params *params, const kslam_sam_db *db, const kslam_read_batch *reads,
+                        const kslam_pairs *pairs, int want_sam, char **sam_text /* may be NULL when !want_sam */, uint64_t *sam_len,
+                        uint32_t *max_insert_size /* may be NULL */, const kslam_taxdb *taxdb, kslam_taxa *taxa);
+int kslam_batch_outputs_single(const kslam_sam_params *params, const kslam_sam_db *db, const kslam_read_batch *reads,
+                               const kslam_alignments *alignments, uint32_t score_threshold, int want_sam, char **sam_text,
+                               uint64_t *sam_len, const kslam_taxdb *taxdb, kslam_taxa *taxa);
+int kslam_taxa_results(kslam_taxa *taxa, const kslam_taxdb *taxdb, uint32_t num_reads, char **per_read, uint64_t *per_read_len,
+                       char **xml, uint64_t *xml_len, char **abbreviated, uint64_t *abbreviated_len);
+
+/* ---- database builders (host side): --parse-genbank / --parse-fasta / DIR/database ----------------------------------
+ * kslam_index = GenbankIndex (GenbankTools.h:189-207). kslam_index_parse_genbank = createIndexFromGBFF (:481-527) with
+ * parseSection (:348-476); kslam_index_parse_fasta = createIndexFromFASTA (:224-260); kslam_index_read / _write = the Boost
+ * text archive of getIndexFromBoostSerial / writeIndexToBoostSerial (:201-205,336-344; grammar in SURVEY.md App. B.1 —
+ * parity of the archive bytes is unpinned, no Boost in the build image). kslam_index_db fills a kslam_sam_db view whose
+ * pointers stay valid until kslam_index_free. */
+typedef struct kslam_index kslam_index;
+int kslam_index_parse_genbank(const char *const *paths, uint64_t n_paths, kslam_index **out);
+int kslam_index_parse_fasta(const char *const *paths, uint64_t n_paths, kslam_index **out);
+int kslam_index_read(const char *database_path, kslam_index **out);
+int kslam_index_write(const kslam_index *index, const char *database_path);
+int kslam_index_db(const kslam_index *index, kslam_sam_db *out);
+const char *kslam_index_error(void);
+void kslam_index_free(kslam_index *index);
 
 /* Stage taps for parity tests (results of the last batch; copy to caller buffers; pass NULL to query
  * the count). Returns the count or a negative error. */

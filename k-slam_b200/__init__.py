@@ -37,6 +37,8 @@ OVERLAP_DT = np.dtype([("read", "<u4"), ("entry", "<u4"), ("rel", "<i4"), ("rev_
                        ("sw_score", "<u4"), ("cigar_off", "<u4"), ("cigar_len", "<u4"), ("flags", "<u4")])
 PAIR_DT = np.dtype([("combined_score", "<u4"), ("entry", "<u4"), ("ref_start", "<i4"), ("ref_end", "<i4"),
                     ("insert_size", "<u4"), ("r1_idx", "<i4"), ("r2_idx", "<i4"), ("pad", "<u4")])
+GENE_DT = np.dtype([("cds_start", "<u4"), ("cds_stop", "<u4"), ("gene_id", "<u4"), ("complement", "<u4"), ("str_offs", "<u8", (6,))])
+GENE_STRINGS = ("gene_name", "locus_tag", "protein_id", "product", "reference_sequence")
 FLAG_UNDEFINED = 1
 FLAG_CIGAR_OVERFLOW = 2
 
@@ -88,7 +90,8 @@ class SamParams(C.Structure):
 
 class _SamDb(C.Structure):
     _fields_ = [("n_entries", C.c_uint64), ("bases", C.c_void_p), ("offs", C.c_void_p), ("locus_tags", C.c_void_p),
-                ("locus_offs", C.c_void_p), ("taxonomy_ids", C.c_void_p)]
+                ("locus_offs", C.c_void_p), ("taxonomy_ids", C.c_void_p),
+                ("genes", C.c_void_p), ("gene_offs", C.c_void_p), ("gene_strings", C.c_void_p)]
 
 
 def declared_symbols():
@@ -155,6 +158,32 @@ def lib():
                                          C.POINTER(vp), C.POINTER(u64)]
     L.kslam_sam_free.argtypes = [vp]
     L.kslam_sam_free.restype = None
+    L.kslam_taxdb_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.kslam_taxdb_build.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+    L.kslam_taxdb_size.argtypes = [vp]
+    L.kslam_taxdb_size.restype = u64
+    L.kslam_taxdb_lca.argtypes = [vp, vp, u64]
+    L.kslam_taxdb_lca.restype = u32
+    L.kslam_taxdb_lineage.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64)]
+    L.kslam_taxdb_name.argtypes = [vp, u32, C.POINTER(vp), C.POINTER(u64)]
+    L.kslam_taxdb_close.argtypes = [vp]
+    L.kslam_taxdb_close.restype = None
+    L.kslam_taxa_create.argtypes = [C.POINTER(vp)]
+    L.kslam_taxa_destroy.argtypes = [vp]
+    L.kslam_taxa_destroy.restype = None
+    L.kslam_batch_outputs.argtypes = [C.POINTER(SamParams), C.POINTER(_SamDb), C.POINTER(_ReadBatch), C.POINTER(_Pairs), i32, C.POINTER(vp),
+                                      C.POINTER(u64), C.POINTER(u32), vp, vp]
+    L.kslam_batch_outputs_single.argtypes = [C.POINTER(SamParams), C.POINTER(_SamDb), C.POINTER(_ReadBatch), C.POINTER(_Alignments), u32, i32,
+                                             C.POINTER(vp), C.POINTER(u64), vp, vp]
+    L.kslam_taxa_results.argtypes = [vp, vp, u32] + [C.POINTER(vp), C.POINTER(u64)] * 3
+    L.kslam_index_parse_genbank.argtypes = [C.POINTER(C.c_char_p), u64, C.POINTER(vp)]
+    L.kslam_index_parse_fasta.argtypes = [C.POINTER(C.c_char_p), u64, C.POINTER(vp)]
+    L.kslam_index_read.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.kslam_index_write.argtypes = [vp, C.c_char_p]
+    L.kslam_index_db.argtypes = [vp, C.POINTER(_SamDb)]
+    L.kslam_index_error.restype = C.c_char_p
+    L.kslam_index_free.argtypes = [vp]
+    L.kslam_index_free.restype = None
     L.kslam_set_kmer_sort_bits.argtypes = [vp, u32]
     L.kslam_get_kmer_sort_bits.argtypes = [vp]
     L.kslam_load_genomes_part.argtypes = [vp, u64, vp, vp, u32, u32]
@@ -490,14 +519,24 @@ class SamWriter:
     """kslam_sam_header / kslam_sam_batch: the reference's host stages after pairing up to the SAM text
     (PairedOverlap.h:314-576, SAM.h). Host code: works without a GPU on any (sorted_overlaps, cigar_pool, pairs)."""
 
-    def __init__(self, gen_bases, gen_offs, locus_tags, taxonomy_ids=None, num_alignments=10, score_fraction_threshold=0.95,
-                 pseudo_assembly=True, report_cigar=True, sam_xa=False, threads=0):
+    def __init__(self, gen_bases=None, gen_offs=None, locus_tags=None, taxonomy_ids=None, num_alignments=10, score_fraction_threshold=0.95,
+                 pseudo_assembly=True, report_cigar=True, sam_xa=False, threads=0, genes=None, index=None):
+        """The database either as arrays (genes = (GENE_DT records, gene_offs u64[n+1], gene string bytes) or None) or as an
+        Index (kslam_index_*), whose buffers are used in place."""
         self.L = lib()
-        self.gb, self.go = _u8(gen_bases), _u64(gen_offs)
-        self.lt, self.lo = _cat([t if isinstance(t, bytes) else t.encode() for t in locus_tags])
-        self.tax = None if taxonomy_ids is None else np.ascontiguousarray(taxonomy_ids, dtype=np.uint32)
-        self.db = _SamDb(len(self.go) - 1, self.gb.ctypes.data, self.go.ctypes.data, self.lt.ctypes.data, self.lo.ctypes.data,
-                         None if self.tax is None else self.tax.ctypes.data)
+        if index is not None:
+            self.index = index                              # keeps the buffers alive
+            self.db = index.db
+        else:
+            self.gb, self.go = _u8(gen_bases), _u64(gen_offs)
+            self.lt, self.lo = _cat([t if isinstance(t, bytes) else t.encode() for t in locus_tags])
+            self.tax = None if taxonomy_ids is None else np.ascontiguousarray(taxonomy_ids, dtype=np.uint32)
+            self.db = _SamDb(len(self.go) - 1, self.gb.ctypes.data, self.go.ctypes.data, self.lt.ctypes.data, self.lo.ctypes.data,
+                             None if self.tax is None else self.tax.ctypes.data)
+            if genes is not None:
+                self.genes = np.ascontiguousarray(genes[0], dtype=GENE_DT); self.gene_offs = _u64(genes[1])
+                self.gene_strings = _u8(genes[2]) if len(genes[2]) else np.zeros(1, np.uint8)
+                self.db.genes, self.db.gene_offs, self.db.gene_strings = self.genes.ctypes.data, self.gene_offs.ctypes.data, self.gene_strings.ctypes.data
         self.prm = SamParams(num_alignments, int(pseudo_assembly), int(report_cigar), int(sam_xa), threads, score_fraction_threshold)
 
     def _take(self, ptr, n):
@@ -513,8 +552,9 @@ class SamWriter:
             raise KslamError(f"kslam_sam_header failed ({rc})")
         return self._take(ptr, n)
 
-    def batch_single(self, read_bases, read_offs, quals, qual_offs, ids, id_offs, overlaps, cigar_pool, score_threshold=0):
-        """Single-end reads: SAM text from align_batch's output (kslam_sam_batch_single)."""
+    def batch_single(self, read_bases, read_offs, quals, qual_offs, ids, id_offs, overlaps, cigar_pool, score_threshold=0,
+                     want_sam=True, taxdb=None, taxa=None):
+        """Single-end reads: SAM text (and taxon assignments) from align_batch's output (kslam_batch_outputs_single)."""
         rb, ro, q, qo, i, io = _u8(read_bases), _u64(read_offs), _u8(quals), _u64(qual_offs), _u8(ids), _u64(id_offs)
         n = len(ro) - 1
         reads = _ReadBatch(n, n, rb.ctypes.data, ro.ctypes.data, q.ctypes.data, qo.ctypes.data, i.ctypes.data, io.ctypes.data)
@@ -523,14 +563,20 @@ class SamWriter:
         a.n_overlaps = len(ov); a.overlaps = ov.ctypes.data if len(ov) else None
         a.n_cigar_words = len(cg); a.cigar_pool = cg.ctypes.data if len(cg) else None
         ptr, ln = C.c_void_p(), C.c_uint64()
-        rc = self.L.kslam_sam_batch_single(C.byref(self.prm), C.byref(self.db), C.byref(reads), C.byref(a), score_threshold, C.byref(ptr), C.byref(ln))
+        rc = self.L.kslam_batch_outputs_single(C.byref(self.prm), C.byref(self.db), C.byref(reads), C.byref(a), score_threshold, int(want_sam),
+                                               C.byref(ptr), C.byref(ln), taxdb.h if taxdb is not None else None, taxa.h if taxa is not None else None)
         if rc != 0:
-            raise KslamError(f"kslam_sam_batch_single failed ({rc})")
+            raise KslamError(f"kslam_batch_outputs_single failed ({rc})")
+        if not want_sam:
+            return b""
         return self._take(ptr, ln)
 
-    def batch(self, read_bases, read_offs, quals, qual_offs, ids, id_offs, sorted_overlaps, cigar_pool, pairs, out_file=None):
+    def batch(self, read_bases, read_offs, quals, qual_offs, ids, id_offs, sorted_overlaps, cigar_pool, pairs, out_file=None,
+              want_sam=True, taxdb=None, taxa=None):
         """-> (SAM text of the batch, max allowed insert size); with out_file the text is written to it straight from the
-        library's buffer and its length is returned instead."""
+        library's buffer and its length is returned instead. With taxdb + taxa (TaxDb, Taxa) the batch's per-read taxon
+        assignments are appended to taxa (kslam_batch_outputs); want_sam=False skips the SAM records like a run without
+        --sam-file."""
         rb, ro, q, qo, i, io = _u8(read_bases), _u64(read_offs), _u8(quals), _u64(qual_offs), _u8(ids), _u64(id_offs)
         n = len(ro) - 1
         reads = _ReadBatch(n, n // 2, rb.ctypes.data, ro.ctypes.data, q.ctypes.data, qo.ctypes.data, i.ctypes.data, io.ctypes.data)
@@ -541,9 +587,12 @@ class SamWriter:
         p.n_cigar_words = len(cg); p.cigar_pool = cg.ctypes.data if len(cg) else None
         p.n_pairs = len(pr); p.pairs = pr.ctypes.data if len(pr) else None
         ptr, ln, mi = C.c_void_p(), C.c_uint64(), C.c_uint32()
-        rc = self.L.kslam_sam_batch(C.byref(self.prm), C.byref(self.db), C.byref(reads), C.byref(p), C.byref(ptr), C.byref(ln), C.byref(mi))
+        rc = self.L.kslam_batch_outputs(C.byref(self.prm), C.byref(self.db), C.byref(reads), C.byref(p), int(want_sam), C.byref(ptr), C.byref(ln),
+                                        C.byref(mi), taxdb.h if taxdb is not None else None, taxa.h if taxa is not None else None)
         if rc != 0:
-            raise KslamError(f"kslam_sam_batch failed ({rc})")
+            raise KslamError(f"kslam_batch_outputs failed ({rc})")
+        if not want_sam:
+            return (0 if out_file is not None else b""), mi.value
         if out_file is not None:
             try:
                 if ln.value:
@@ -552,3 +601,157 @@ class SamWriter:
                 self.L.kslam_sam_free(ptr)
             return ln.value, mi.value
         return self._take(ptr, ln), mi.value
+
+
+def _take_text(L, ptr, n):
+    try:
+        return C.string_at(ptr, n.value) if ptr.value else b""
+    finally:
+        L.kslam_sam_free(ptr)
+
+
+class TaxDb:
+    """kslam_taxdb_*: the reference's TaxonomyDB (TaxonomyDatabase.h) — DIR/taxDB, LCA, lineage."""
+
+    def __init__(self, path):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.kslam_taxdb_open(os.fsencode(path), C.byref(h))
+        if rc != 0:
+            raise KslamError(f"kslam_taxdb_open({path}) failed ({rc})")
+        self.h = h
+
+    @staticmethod
+    def build(names_dmp, nodes_dmp, out_path):
+        """--parse-taxonomy: names.dmp + nodes.dmp -> the taxDB file."""
+        rc = lib().kslam_taxdb_build(os.fsencode(names_dmp), os.fsencode(nodes_dmp), os.fsencode(out_path))
+        if rc != 0:
+            raise KslamError(f"kslam_taxdb_build failed ({rc})")
+
+    def __len__(self):
+        return int(self.L.kslam_taxdb_size(self.h))
+
+    def lca(self, tax_ids):
+        a = np.ascontiguousarray(tax_ids, dtype=np.uint32)
+        return int(self.L.kslam_taxdb_lca(self.h, a.ctypes.data if len(a) else None, len(a)))
+
+    def _text(self, fn, tax_id):
+        ptr, n = C.c_void_p(), C.c_uint64()
+        if fn(self.h, tax_id, C.byref(ptr), C.byref(n)) != 0:
+            raise KslamError("taxonomy query failed")
+        return _take_text(self.L, ptr, n)
+
+    def lineage(self, tax_id):
+        return self._text(self.L.kslam_taxdb_lineage, tax_id)
+
+    def name(self, tax_id):
+        return self._text(self.L.kslam_taxdb_name, tax_id)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.kslam_taxdb_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # noqa: BLE001
+            pass
+
+
+class Taxa:
+    """kslam_taxa_*: the run's per-read taxon assignments (std::vector<IdentifiedTaxonomy>), filled by SamWriter.batch."""
+
+    def __init__(self):
+        self.L = lib()
+        h = C.c_void_p()
+        if self.L.kslam_taxa_create(C.byref(h)) != 0:
+            raise KslamError("kslam_taxa_create failed")
+        self.h = h
+
+    def results(self, taxdb, num_reads):
+        """-> (text of <out>_PerRead, XML text of <out>, text of <out>_abbreviated), SLAM.h:256-265."""
+        p = [C.c_void_p() for _ in range(3)]; n = [C.c_uint64() for _ in range(3)]
+        rc = self.L.kslam_taxa_results(self.h, taxdb.h, num_reads, C.byref(p[0]), C.byref(n[0]), C.byref(p[1]), C.byref(n[1]), C.byref(p[2]), C.byref(n[2]))
+        if rc != 0:
+            raise KslamError(f"kslam_taxa_results failed ({rc})")
+        return tuple(_take_text(self.L, p[i], n[i]) for i in range(3))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.kslam_taxa_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # noqa: BLE001
+            pass
+
+
+class Index:
+    """kslam_index_*: GenbankIndex built from GenBank flat files / FASTA files or read from DIR/database, held flat."""
+
+    def __init__(self, h):
+        self.L = lib()
+        self.h = h
+        self.db = _SamDb()
+        if self.L.kslam_index_db(self.h, C.byref(self.db)) != 0:
+            raise KslamError("kslam_index_db failed")
+        n = self.n_entries = int(self.db.n_entries)
+        self.offs = _view(self.db.offs, n + 1, np.dtype("<u8"))
+        self.bases = _view(self.db.bases, int(self.offs[-1]), np.dtype("u1"))
+        lo = _view(self.db.locus_offs, n + 1, np.dtype("<u8"))
+        lt = _view(self.db.locus_tags, int(lo[-1]), np.dtype("u1")).tobytes()
+        self.locus_tags = [lt[int(lo[i]):int(lo[i + 1])] for i in range(n)]
+        self.taxonomy_ids = _view(self.db.taxonomy_ids, n, np.dtype("<u4"))
+        if self.db.genes:
+            self.gene_offs = _view(self.db.gene_offs, n + 1, np.dtype("<u8"))
+            self.genes = _view(self.db.genes, int(self.gene_offs[-1]), GENE_DT)
+            self.gene_strings = _view(self.db.gene_strings, int(self.genes["str_offs"][-1][5]) if len(self.genes) else 0, np.dtype("u1"))
+        else:
+            self.gene_offs, self.genes, self.gene_strings = np.zeros(n + 1, np.uint64), np.zeros(0, GENE_DT), np.zeros(0, np.uint8)
+
+    @classmethod
+    def _make(cls, fn, *args):
+        L = lib()
+        h = C.c_void_p()
+        rc = fn(*args, C.byref(h))
+        if rc != 0:
+            raise KslamError(f"building the index failed ({rc}): {L.kslam_index_error().decode()}")
+        return cls(h)
+
+    @classmethod
+    def parse_genbank(cls, paths):
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        return cls._make(lib().kslam_index_parse_genbank, arr, len(paths))
+
+    @classmethod
+    def parse_fasta(cls, paths):
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(p) for p in paths])
+        return cls._make(lib().kslam_index_parse_fasta, arr, len(paths))
+
+    @classmethod
+    def read(cls, database_path):
+        return cls._make(lib().kslam_index_read, os.fsencode(database_path))
+
+    def write(self, database_path):
+        rc = self.L.kslam_index_write(self.h, os.fsencode(database_path))
+        if rc != 0:
+            raise KslamError(f"kslam_index_write failed ({rc}): {self.L.kslam_index_error().decode()}")
+
+    def gene_records(self, entry):
+        """[(dict of the five strings + gene_id, start, stop)] of one entry."""
+        gs = self.gene_strings.tobytes()
+        out = []
+        for g in self.genes[int(self.gene_offs[entry]):int(self.gene_offs[entry + 1])]:
+            so = g["str_offs"]
+            d = {k: gs[int(so[i]):int(so[i + 1])] for i, k in enumerate(GENE_STRINGS)}
+            d.update(gene_id=int(g["gene_id"]), start=int(g["cds_start"]), stop=int(g["cds_stop"]), complement=int(g["complement"]))
+            out.append(d)
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.kslam_index_free(self.h)
+            self.h = None

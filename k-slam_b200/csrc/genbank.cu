@@ -1,0 +1,328 @@
+// genbank.cu — the database side of the drop-in (host code): building a GenbankIndex from GenBank flat files or FASTA
+// files and reading / writing DIR/database, the file `--db` points at.
+//   createIndexFromGBFF + parseSection      /root/reference/src/GenbankTools.h:348-527   (--parse-genbank)
+//   createIndexFromFASTA                    GenbankTools.h:224-260                       (--parse-fasta)
+//   writeIndexToBoostSerial / getIndexFromBoostSerial   GenbankTools.h:201-205,336-344   (Boost text archive)
+// The parsers follow the reference field by field, including what it does by accident (the taxon id is found because
+// stoul stops at the closing quote after an unsigned wrap-around of the substring length; a qualifier found anywhere in
+// a feature's text wins; every line of the ORIGIN block is a "section" of its own whose tag is the base counter).
+// The archive grammar is the one SURVEY.md App. B.1 spells out; this image has no Boost, so the bytes of a real
+// archive could not be compared ("parity unpinned" for the archive, pinned for the parsers: tests/test_genbank.py
+// runs the reference's own createIndexFromGBFF through oracle/_ref).
+#include "common.cuh"
+#include "host_stages.h"
+#include <algorithm>
+#include <ctype.h>
+#include <stdexcept>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace {
+
+struct Gene {                                              // Gene + CDS, GenbankTools.h:47-110
+  std::string geneName, locusTag, proteinID, product, referenceSequence;
+  uint32_t geneID = 0, start = 0, stop = 0;
+  bool complement = false;
+};
+struct Entry {                                             // GenbankEntry, GenbankTools.h:136-164 (serialised members + definition)
+  std::string bases, locusTag, definition;
+  uint32_t taxonomyID = 0, genbankID = 0;
+  bool isPlasmid = false, is16S = false;
+  std::vector<Gene> genes;
+};
+
+thread_local std::string g_error;
+
+bool read_file(const char *path, std::string &data) {
+  FILE *f = fopen(path, "rb");
+  if (!f) return false;
+  char buf[1 << 16];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof buf, f)) > 0) data.append(buf, n);
+  const bool ok = !ferror(f);
+  fclose(f);
+  return ok;
+}
+
+typedef std::string::const_iterator It;
+inline It skip_to(It from, It end, bool (*pred)(char)) { return std::find_if(from, end, pred); }
+bool is_space(char c) { return c == ' '; }
+bool not_space(char c) { return c != ' '; }
+bool is_digit(char c) { return isdigit((unsigned char)c) != 0; }
+bool not_digit(char c) { return isdigit((unsigned char)c) == 0; }
+
+// text between `key` and the next double quote, if both exist (the pattern of GenbankTools.h:415-468)
+bool qualifier(const std::string &field, size_t startPos, size_t keyLen, std::string &out) {
+  if (startPos == std::string::npos) return false;
+  startPos += keyLen;
+  const size_t endPos = field.find('"', startPos);
+  if (endPos == std::string::npos || startPos >= field.size()) return false;
+  out = field.substr(startPos, endPos - startPos);
+  return true;
+}
+
+void parse_section(const std::string &field, Entry &entry) {          // parseSection, GenbankTools.h:348-476
+  It start = skip_to(field.begin(), field.end(), not_space);
+  if (start == field.end()) return;
+  It stop = skip_to(start, field.end(), is_space);
+  const std::string tag(start, stop);
+  start = skip_to(stop, field.end(), not_space);
+  if (tag == "VERSION") {
+    stop = skip_to(start, field.end(), is_space);
+    entry.locusTag = std::string(start, stop);
+    start = skip_to(stop, field.end(), is_digit);
+    try { entry.genbankID = (uint32_t)stoul(std::string(start, field.end())); } catch (...) {}
+  } else if (tag == "DEFINITION") {
+    entry.definition = std::string(start, field.end());
+  } else if (tag == "source") {
+    size_t startPos = field.find("/db_xref=\"taxon:");
+    const size_t endPos = field.find('"', startPos);       // the OPENING quote: endPos < startPos + 16, the length below wraps
+    if (startPos != std::string::npos && endPos != std::string::npos) {
+      startPos += 16;
+      if (startPos < field.size()) try { entry.taxonomyID = (uint32_t)stoul(field.substr(startPos, endPos - startPos)); } catch (...) {}
+    }
+  } else if (tag == "CDS" || tag == "tRNA" || tag == "gene") {
+    Gene gene;
+    start = skip_to(start, field.end(), is_digit);
+    stop = skip_to(start, field.end(), not_digit);
+    try { gene.start = (uint32_t)stoul(std::string(start, stop)); } catch (...) {}
+    start = skip_to(stop, field.end(), is_digit);
+    stop = skip_to(start, field.end(), not_digit);
+    try { gene.stop = (uint32_t)stoul(std::string(start, stop)); } catch (...) {}
+    qualifier(field, field.find("/product=\""), 10, gene.product);
+    qualifier(field, field.rfind("/protein_id=\""), 13, gene.proteinID);
+    qualifier(field, field.find("/locus_tag=\""), 12, gene.locusTag);
+    std::string id;
+    if (qualifier(field, field.find("GeneID:"), 7, id)) gene.geneID = (uint32_t)std::stoul(id);   // not guarded in the reference either: throws
+    qualifier(field, field.find("/gene=\""), 7, gene.geneName);
+    gene.referenceSequence = entry.locusTag;
+    entry.genes.push_back(std::move(gene));
+  } else if (tag.size() && is_digit(tag[0])) {
+    for (; start != field.end(); ++start)
+      if (*start != ' ') entry.bases.push_back((char)toupper((unsigned char)*start));
+  }
+}
+
+}  // namespace
+
+// GenbankIndex held flat: what kslam_load_genomes, kslam_sam_db and the archive writer take without another copy.
+struct kslam_index {
+  std::string bases; std::vector<uint64_t> offs{0};
+  std::string locus; std::vector<uint64_t> locus_offs{0};
+  std::vector<uint32_t> taxonomy_ids, genbank_ids;
+  std::vector<uint8_t> is_plasmid, is_16s;
+  std::vector<kslam_gene> genes; std::vector<uint64_t> gene_offs{0}; std::string gene_strings;
+
+  void add(const Entry &e) {
+    bases += e.bases; offs.push_back(bases.size());
+    locus += e.locusTag; locus_offs.push_back(locus.size());
+    taxonomy_ids.push_back(e.taxonomyID); genbank_ids.push_back(e.genbankID);
+    is_plasmid.push_back(e.isPlasmid); is_16s.push_back(e.is16S);
+    for (const Gene &g : e.genes) {
+      kslam_gene k;
+      k.cds_start = g.start; k.cds_stop = g.stop; k.gene_id = g.geneID; k.complement = g.complement;
+      const std::string *s[5] = {&g.geneName, &g.locusTag, &g.proteinID, &g.product, &g.referenceSequence};
+      for (int i = 0; i < 5; i++) { k.str_offs[i] = gene_strings.size(); gene_strings += *s[i]; }
+      k.str_offs[5] = gene_strings.size();
+      genes.push_back(k);
+    }
+    gene_offs.push_back(genes.size());
+  }
+  uint64_t n() const { return offs.size() - 1; }
+};
+
+namespace {
+
+// ---- Boost text archive: space-separated tokens after "22 serialization::archive <libver>"; the FIRST
+// object of every class type is preceded by "<tracking> <version>" = "0 0"; a vector is "<count> <item_version>" then the
+// items; a string is "<len>", ONE space, then len raw bytes; bool is 0 / 1. Serialised members, in order:
+//   GenbankIndex{entries}  GenbankEntry{bases taxonomyID genbankID isPlasmid is16S locusTag genes}
+//   Gene{geneName locusTag proteinID product referenceSequence geneID codingSequence}  CDS{start stop complement}
+const char kArchiveHeader[] = "22 serialization::archive";
+
+struct ArchiveReader {
+  const std::string &d; size_t p; unsigned seen = 0;
+  uint64_t number() {
+    while (p < d.size() && (d[p] == ' ' || d[p] == '\n' || d[p] == '\r' || d[p] == '\t')) p++;
+    size_t q = p;
+    uint64_t v = 0;
+    while (q < d.size() && is_digit(d[q])) { v = v * 10 + (uint64_t)(d[q] - '0'); q++; }
+    if (q == p) throw std::runtime_error("expected a number at byte " + std::to_string(p));
+    p = q;
+    return v;
+  }
+  void string(std::string &out) {
+    const uint64_t n = number();
+    p += 1;                                                // exactly one separator, then n raw bytes (they may contain spaces)
+    if (p + n > d.size()) throw std::runtime_error("string runs past the end of the archive");
+    out.assign(d, p, n);
+    p += n;
+  }
+  void class_info(unsigned bit) { if (!(seen & bit)) { seen |= bit; number(); number(); } }
+  uint64_t vector(unsigned bit) { class_info(bit); const uint64_t count = number(); number(); return count; }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char *kslam_index_error(void) { return g_error.c_str(); }
+void kslam_index_free(kslam_index *index) { delete index; }
+
+int kslam_index_parse_genbank(const char *const *paths, uint64_t n_paths, kslam_index **out) {   // createIndexFromGBFF, :481-527
+  if (!paths || !out) return KSLAM_ERR_ARG;
+  kslam_index *index = nullptr;
+  try {
+    index = new kslam_index();
+    for (uint64_t f = 0; f < n_paths; f++) {
+      std::string data;
+      if (!read_file(paths[f], data)) throw std::runtime_error(std::string("unable to open index file ") + paths[f]);
+      std::string line, section;
+      Entry entry;
+      for (size_t pos = 0; pos < data.size();) {           // std::getline: '\n' ends a line, a '\r' stays in it
+        size_t nl = data.find('\n', pos);
+        if (nl == std::string::npos) nl = data.size();
+        line.assign(data, pos, nl - pos);
+        pos = nl + 1;
+        if (line.size() == 0) continue;
+        const size_t startPos = line.find_first_not_of(' ');
+        if (startPos < 12) {
+          parse_section(section, entry);
+          section = line;
+          if (line == "//") {
+            std::sort(entry.genes.begin(), entry.genes.end(), [](const Gene &i, const Gene &j) {
+              if (i.start == j.start) return i.proteinID.size() > j.proteinID.size();
+              return i.start < j.start;
+            });
+            auto it = std::unique(entry.genes.begin(), entry.genes.end(), [](const Gene &i, const Gene &j) { return i.start == j.start; });
+            entry.genes.resize(std::distance(entry.genes.begin(), it));
+            index->add(entry);
+            entry = Entry();
+          }
+        } else if (startPos == std::string::npos) continue;
+        else section.append(line.substr(startPos - 1));    // continuation line: one space + its text
+      }
+    }
+    *out = index;
+    return KSLAM_OK;
+  } catch (const std::exception &e) { g_error = e.what(); delete index; return KSLAM_ERR_ARG; }
+}
+
+int kslam_index_parse_fasta(const char *const *paths, uint64_t n_paths, kslam_index **out) {     // createIndexFromFASTA, :224-260
+  if (!paths || !out) return KSLAM_ERR_ARG;
+  kslam_index *index = nullptr;
+  try {
+    index = new kslam_index();
+    for (uint64_t f = 0; f < n_paths; f++) {
+      std::string data;
+      if (!read_file(paths[f], data)) throw std::runtime_error(std::string("unable to open FASTA file ") + paths[f]);
+      Entry cur;                                           // one object per file: bases before the first header form an entry too
+      auto close = [&]() {
+        if (cur.bases.size()) {
+          for (char &ch : cur.bases) ch = (char)toupper((unsigned char)ch);   // inPlaceConvertToUpperCase
+          index->add(cur);
+        }
+      };
+      for (size_t pos = 0; pos < data.size();) {           // safeGetline (sequenceTools.h:45-73): "\n", "\r\n" and lone "\r" end a line
+        size_t e = pos;
+        while (e < data.size() && data[e] != '\n' && data[e] != '\r') e++;
+        const char *line = data.data() + pos;
+        const size_t len = e - pos;
+        pos = e + ((e + 1 < data.size() && data[e] == '\r' && data[e + 1] == '\n') ? 2 : 1);
+        if (len == 0) continue;
+        if (line[0] == '>') {
+          close();
+          cur.bases.clear(); cur.locusTag.clear();
+          const void *sp = memchr(line, ' ', len);
+          if (sp && sp != line) cur.locusTag.assign(line + 1, (const char *)sp - line - 1);
+        } else cur.bases.append(line, len);
+      }
+      close();
+    }
+    *out = index;
+    return KSLAM_OK;
+  } catch (const std::exception &e) { g_error = e.what(); delete index; return KSLAM_ERR_ARG; }
+}
+
+int kslam_index_read(const char *path, kslam_index **out) {           // getIndexFromBoostSerial, :336-344
+  if (!path || !out) return KSLAM_ERR_ARG;
+  kslam_index *index = nullptr;
+  try {
+    std::string data;
+    if (!read_file(path, data)) throw std::runtime_error("unable to open index file");
+    if (data.compare(0, sizeof kArchiveHeader - 1, kArchiveHeader) != 0) throw std::runtime_error("not a Boost text archive (header missing)");
+    ArchiveReader r{data, sizeof kArchiveHeader - 1};
+    if (r.number() < 4) throw std::runtime_error("archive library version < 4 is not supported");
+    enum { INDEX = 1, ENTRIES = 2, ENTRY = 4, GENES = 8, GENE = 16, CDS = 32 };
+    index = new kslam_index();
+    r.class_info(INDEX);
+    const uint64_t n_entries = r.vector(ENTRIES);
+    for (uint64_t e = 0; e < n_entries; e++) {
+      r.class_info(ENTRY);
+      Entry en;
+      r.string(en.bases);
+      en.taxonomyID = (uint32_t)r.number(); en.genbankID = (uint32_t)r.number();
+      en.isPlasmid = r.number() != 0; en.is16S = r.number() != 0;
+      r.string(en.locusTag);
+      const uint64_t n_genes = r.vector(GENES);
+      for (uint64_t g = 0; g < n_genes; g++) {
+        r.class_info(GENE);
+        Gene ge;
+        r.string(ge.geneName); r.string(ge.locusTag); r.string(ge.proteinID); r.string(ge.product); r.string(ge.referenceSequence);
+        ge.geneID = (uint32_t)r.number();
+        r.class_info(CDS);
+        ge.start = (uint32_t)r.number(); ge.stop = (uint32_t)r.number(); ge.complement = r.number() != 0;
+        en.genes.push_back(std::move(ge));
+      }
+      index->add(en);
+    }
+    *out = index;
+    return KSLAM_OK;
+  } catch (const std::exception &e) { g_error = e.what(); delete index; return KSLAM_ERR_ARG; }
+}
+
+int kslam_index_write(const kslam_index *ix, const char *path) {      // writeIndexToBoostSerial, :201-205
+  if (!ix || !path) return KSLAM_ERR_ARG;
+  FILE *f = fopen(path, "wb");
+  if (!f) { g_error = "unable to open the database file for writing"; return KSLAM_ERR_ARG; }
+  unsigned seen = 0;
+  enum { INDEX = 1, ENTRIES = 2, ENTRY = 4, GENES = 8, GENE = 16, CDS = 32 };
+  auto info = [&](unsigned bit) { if (!(seen & bit)) { seen |= bit; fputs(" 0 0", f); } };
+  auto str = [&](const char *p, uint64_t n) { fprintf(f, " %llu ", (unsigned long long)n); fwrite(p, 1, n, f); };
+  fprintf(f, "%s 17", kArchiveHeader);
+  info(INDEX); info(ENTRIES);
+  fprintf(f, " %llu 0", (unsigned long long)ix->n());
+  for (uint64_t e = 0; e < ix->n(); e++) {
+    info(ENTRY);
+    str(ix->bases.data() + ix->offs[e], ix->offs[e + 1] - ix->offs[e]);
+    fprintf(f, " %u %u %u %u", ix->taxonomy_ids[e], ix->genbank_ids[e], (unsigned)ix->is_plasmid[e], (unsigned)ix->is_16s[e]);
+    str(ix->locus.data() + ix->locus_offs[e], ix->locus_offs[e + 1] - ix->locus_offs[e]);
+    info(GENES);
+    fprintf(f, " %llu 0", (unsigned long long)(ix->gene_offs[e + 1] - ix->gene_offs[e]));
+    for (uint64_t g = ix->gene_offs[e]; g < ix->gene_offs[e + 1]; g++) {
+      const kslam_gene &k = ix->genes[g];
+      info(GENE);
+      for (int i = 0; i < 5; i++) str(ix->gene_strings.data() + k.str_offs[i], k.str_offs[i + 1] - k.str_offs[i]);
+      fprintf(f, " %u", k.gene_id);
+      info(CDS);
+      fprintf(f, " %u %u %u", k.cds_start, k.cds_stop, k.complement ? 1u : 0u);
+    }
+  }
+  fputc('\n', f);
+  const bool ok = !ferror(f);
+  return (fclose(f) == 0 && ok) ? KSLAM_OK : KSLAM_ERR_STATE;
+}
+
+int kslam_index_db(const kslam_index *ix, kslam_sam_db *out) {
+  if (!ix || !out) return KSLAM_ERR_ARG;
+  memset(out, 0, sizeof *out);
+  out->n_entries = ix->n();
+  out->bases = ix->bases.data(); out->offs = ix->offs.data();
+  out->locus_tags = ix->locus.data(); out->locus_offs = ix->locus_offs.data();
+  out->taxonomy_ids = ix->taxonomy_ids.data();
+  if (!ix->genes.empty()) { out->genes = ix->genes.data(); out->gene_offs = ix->gene_offs.data(); out->gene_strings = ix->gene_strings.data(); }
+  return KSLAM_OK;
+}
+
+}  // extern "C"

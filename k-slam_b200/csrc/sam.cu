@@ -11,9 +11,10 @@
 //   pseudoAssembly                       PairedOverlap.h:480-576   (optional, on by default as in Globals.h:36)
 //   getCigarAndMD / SAMEntry / getSAMFromPair / writeSAMOutputPairs / getHeader    SAM.h:101-237,240-534
 // Input is exactly what kslam_pair_batch returns plus the batch's reads (ids, bases, qualities: kslam_read_batch) and
-// the database entries' bases / locus tags / taxonomy ids. Gene annotations (XG / XP / XR, GenBank databases) are not
-// carried by this interface yet: FASTA databases have none.
+// the database entries' bases / locus tags / taxonomy ids / gene tables (XG / XP / XR of GenBank databases).
+// kslam_batch_outputs runs the same chain and then hands the per-read records to taxon.cu (LCA, genes; SLAM.h:243-249).
 #include "common.cuh"
+#include "host_stages.h"
 #include <algorithm>
 #include <cmath>
 #include <climits>
@@ -24,31 +25,9 @@
 #include <thread>
 #include <unordered_map>
 
+using namespace kslam_host;
+
 namespace {
-
-struct POv {                       // PairedOverlap, PairedOverlap.h:32-58, overlaps held as indices
-  uint32_t combinedScore = 0, entry = 0;
-  int refStart = 0, refEnd = 0;
-  uint32_t insertSize = 0;
-  bool hasR1 = false, hasR2 = false;
-  int32_t r1 = -1, r2 = -1;        // index into sorted_overlaps
-};
-struct ReadPair { uint32_t r1Pos = 0, r2Pos = 0; std::vector<POv> pairs; };
-
-// contiguous ranges of [0, n) on `threads` host threads (every stage below is independent per read pair or per entry)
-template <class F> void parallel_ranges(uint32_t threads, size_t n, F f) {
-  if (threads <= 1 || n < 2 * (size_t)threads) { f(0, (size_t)0, n); return; }
-  std::vector<std::thread> th;
-  for (uint32_t t = 0; t < threads; t++) th.emplace_back([=] { f(t, n * t / threads, n * (t + 1) / threads); });
-  for (auto &x : th) x.join();
-}
-
-struct Ctx {
-  const kslam_sam_params *prm; const kslam_sam_db *db; const kslam_read_batch *reads; const kslam_pairs *in;
-  bool paired;                     // Globals.h pairedData
-  std::string read_id(uint32_t i) const { return std::string(reads->ids + reads->id_offs[i], reads->ids + reads->id_offs[i + 1]); }
-  std::string locus(uint32_t e) const { return std::string(db->locus_tags + db->locus_offs[e], db->locus_tags + db->locus_offs[e + 1]); }
-};
 
 std::vector<ReadPair> per_read(const kslam_pairs *in, uint32_t midpoint) {          // PairedOverlap.h:437-471
   std::vector<ReadPair> out;
@@ -313,6 +292,7 @@ struct SAMEntry {                                        // SAM.h:240-281
   bool multipleSegments = false, allSegmentsAligned = false, thisSegmentUnmapped = false, nextSegmentUnmapped = false;
   bool revComp = false, nextRevComp = false, first = false, secondary = true;
   std::string MD; uint16_t AS = 0; uint32_t NM = 0; uint16_t XS = 0; uint32_t XO = 0, XT = 0;
+  std::string_view XG, XP, XR;    // gene, protein id, product (views into the database's gene strings)
   double prob = 0;
 };
 
@@ -342,6 +322,9 @@ void sam_line(std::string &out, const SAMEntry &e, bool reportCigar, bool paired
     out += "\tNM:i:"; put_uint(out, e.NM);
     out += "\tX0:i:"; put_uint(out, e.XO);
     if (e.XT != 0) { out += "\tXT:i:"; put_uint(out, e.XT); }
+    if (e.XG.size()) { out += "\tXG:Z:"; out += e.XG; }
+    if (e.XP.size()) { out += "\tXP:Z:"; out += e.XP; }
+    if (e.XR.size()) { out += "\tXR:Z:\""; out += e.XR; out.push_back('"'); }
   }
   out.push_back('\n');
 }
@@ -359,6 +342,11 @@ std::pair<SAMEntry, SAMEntry> sam_from_pair(const Ctx &c, const POv &ap) {      
   const kslam_overlap *ov = c.in->sorted_overlaps;
   SAMEntry r1, r2;
   r1.first = true; r2.first = false;
+  if (const kslam_gene *gene = best_gene(c.db, ap.entry, ap.refStart, ap.refEnd)) {     // SAM.h:361-370
+    r1.XG = r2.XG = gene_str(c.db, gene, GENE_NAME);
+    r1.XP = r2.XP = gene_str(c.db, gene, GENE_PROTEIN);
+    r1.XR = r2.XR = gene_str(c.db, gene, GENE_PRODUCT);
+  }
   const uint32_t tax = c.db->taxonomy_ids ? c.db->taxonomy_ids[ap.entry] : 0;
   r1.XT = tax; r2.XT = tax;
   bool conventionalSequence = true;
@@ -424,14 +412,14 @@ void write_pairs(std::string &out, const Ctx &c, ReadPair &read) {              
   }
 }
 
-char *dup_text(const std::string &s) {
+}  // namespace
+
+char *kslam_host::dup_text(const std::string &s) {
   char *p = (char *)malloc(s.size() + 1);
   if (!p) return nullptr;
   memcpy(p, s.data(), s.size()); p[s.size()] = 0;
   return p;
 }
-
-}  // namespace
 
 extern "C" {
 
@@ -454,8 +442,11 @@ int kslam_sam_header(const kslam_sam_db *db, const char *command_line, char **te
   return *text ? KSLAM_OK : KSLAM_ERR_NOMEM;
 }
 
-// everything after the per-read grouping: screens, pseudo-assembly, records, text (shared by paired and single-end input)
-static int sam_finish(Ctx &c, std::vector<ReadPair> &rp, bool insert_screen, char **text, uint64_t *len, uint32_t *max_insert_size) {
+// everything after the per-read grouping: screens, pseudo-assembly, records, text (shared by paired and single-end input);
+// with a taxonomy database the per-read records then go to taxon.cu, after the SAM records exactly as in the batch loop
+// (writeSAMOutputPairs re-sorts every read's records in place before the taxonomy step sees them, SLAM.h:235-246)
+static int sam_finish(Ctx &c, std::vector<ReadPair> &rp, bool insert_screen, bool want_sam, char **text, uint64_t *len, uint32_t *max_insert_size,
+                      const kslam_taxdb *taxdb, kslam_taxa *taxa) {
   const kslam_sam_params *prm = c.prm;
   const bool trace = getenv("KSLAM_SAM_TRACE") != nullptr;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -471,25 +462,34 @@ static int sam_finish(Ctx &c, std::vector<ReadPair> &rp, bool insert_screen, cha
   screen_by_score(rp, prm->score_fraction_threshold, threads);
   if (prm->pseudo_assembly) { pseudo_assembly(rp, threads); screen_by_score(rp, prm->score_fraction_threshold, threads); }
   double t3 = now();
-  std::vector<std::string> parts(threads);
-  parallel_ranges(threads, rp.size(), [&](uint32_t t, size_t lo, size_t hi) {
-    for (size_t i = lo; i < hi; i++) write_pairs(parts[t], c, rp[i]);
-  });
-  size_t total = 0;
-  std::vector<size_t> at(threads + 1, 0);
-  for (uint32_t t = 0; t < threads; t++) { at[t] = total; total += parts[t].size(); }
-  char *buf = (char *)malloc(total + 1);                      // the threads' pieces go straight into the result buffer
-  if (buf) {
-    parallel_ranges(threads, threads, [&](uint32_t, size_t lo, size_t hi) {
-      for (size_t t = lo; t < hi; t++) memcpy(buf + at[t], parts[t].data(), parts[t].size());
+  int rc = KSLAM_OK;
+  if (want_sam) {
+    std::vector<std::string> parts(threads);
+    parallel_ranges(threads, rp.size(), [&](uint32_t t, size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; i++) write_pairs(parts[t], c, rp[i]);
     });
-    buf[total] = 0;
+    size_t total = 0;
+    std::vector<size_t> at(threads + 1, 0);
+    for (uint32_t t = 0; t < threads; t++) { at[t] = total; total += parts[t].size(); }
+    char *buf = (char *)malloc(total + 1);                      // the threads' pieces go straight into the result buffer
+    if (buf) {
+      parallel_ranges(threads, threads, [&](uint32_t, size_t lo, size_t hi) {
+        for (size_t t = lo; t < hi; t++) memcpy(buf + at[t], parts[t].data(), parts[t].size());
+      });
+      buf[total] = 0;
+    }
+    *text = buf;
+    if (len) *len = total;
+    if (!buf) rc = KSLAM_ERR_NOMEM;
+  } else {
+    if (text) *text = nullptr;
+    if (len) *len = 0;
   }
-  *text = buf;
-  if (len) *len = total;
-  if (trace) fprintf(stderr, "[kslam_sam] insert limit + screen %.1f ms, score screens + assembly %.1f ms, records %.1f ms (incl. concat), %u threads\n",
-                     (t2 - t1) * 1e3, (t3 - t2) * 1e3, (now() - t3) * 1e3, threads);
-  return buf ? KSLAM_OK : KSLAM_ERR_NOMEM;
+  double t4 = now();
+  if (rc == KSLAM_OK && taxdb && taxa) rc = taxa_add_batch(taxa, taxdb, c, rp, threads);
+  if (trace) fprintf(stderr, "[kslam_sam] insert limit + screen %.1f ms, score screens + assembly %.1f ms, records %.1f ms (incl. concat), taxonomy %.1f ms, %u threads\n",
+                     (t2 - t1) * 1e3, (t3 - t2) * 1e3, (t4 - t3) * 1e3, (now() - t4) * 1e3, threads);
+  return rc;
 }
 
 static int check_overlaps(const kslam_sam_db *db, const kslam_read_batch *reads, const kslam_overlap *ov, uint64_t n, const uint32_t *pool,
@@ -505,7 +505,13 @@ static int check_overlaps(const kslam_sam_db *db, const kslam_read_batch *reads,
 
 int kslam_sam_batch(const kslam_sam_params *prm, const kslam_sam_db *db, const kslam_read_batch *reads, const kslam_pairs *pairs,
                     char **text, uint64_t *len, uint32_t *max_insert_size) {
-  if (!prm || !db || !reads || !pairs || !text) return KSLAM_ERR_ARG;
+  return kslam_batch_outputs(prm, db, reads, pairs, 1, text, len, max_insert_size, nullptr, nullptr);
+}
+
+int kslam_batch_outputs(const kslam_sam_params *prm, const kslam_sam_db *db, const kslam_read_batch *reads, const kslam_pairs *pairs,
+                        int want_sam, char **text, uint64_t *len, uint32_t *max_insert_size, const kslam_taxdb *taxdb, kslam_taxa *taxa) {
+  if (!prm || !db || !reads || !pairs || (want_sam && !text) || ((taxdb != nullptr) != (taxa != nullptr))) return KSLAM_ERR_ARG;
+  if ((db->genes != nullptr) != (db->gene_offs != nullptr) || (db->genes && !db->gene_strings)) return KSLAM_ERR_ARG;
   if (pairs->n_pairs && (!pairs->pairs || !pairs->sorted_overlaps)) return KSLAM_ERR_ARG;
   if (check_overlaps(db, reads, pairs->sorted_overlaps, pairs->n_sorted, pairs->cigar_pool, pairs->n_cigar_words) != KSLAM_OK) return KSLAM_ERR_ARG;
   for (uint64_t i = 0; i < pairs->n_pairs; i++) {
@@ -516,7 +522,7 @@ int kslam_sam_batch(const kslam_sam_params *prm, const kslam_sam_db *db, const k
   try {
     Ctx c{prm, db, reads, pairs, true};
     auto rp = per_read(pairs, (uint32_t)(reads->n_reads / 2));
-    return sam_finish(c, rp, true, text, len, max_insert_size);
+    return sam_finish(c, rp, true, want_sam != 0, text, len, max_insert_size, taxdb, taxa);
   } catch (const std::exception &) { return KSLAM_ERR_NOMEM; }
 }
 
@@ -525,7 +531,13 @@ int kslam_sam_batch(const kslam_sam_params *prm, const kslam_sam_db *db, const k
 // then the same screens / pseudo-assembly / records with pairedData = false (one line per alignment, no mate fields).
 int kslam_sam_batch_single(const kslam_sam_params *prm, const kslam_sam_db *db, const kslam_read_batch *reads,
                            const kslam_alignments *al, uint32_t score_threshold, char **text, uint64_t *len) {
-  if (!prm || !db || !reads || !al || !text) return KSLAM_ERR_ARG;
+  return kslam_batch_outputs_single(prm, db, reads, al, score_threshold, 1, text, len, nullptr, nullptr);
+}
+
+int kslam_batch_outputs_single(const kslam_sam_params *prm, const kslam_sam_db *db, const kslam_read_batch *reads, const kslam_alignments *al,
+                               uint32_t score_threshold, int want_sam, char **text, uint64_t *len, const kslam_taxdb *taxdb, kslam_taxa *taxa) {
+  if (!prm || !db || !reads || !al || (want_sam && !text) || ((taxdb != nullptr) != (taxa != nullptr))) return KSLAM_ERR_ARG;
+  if ((db->genes != nullptr) != (db->gene_offs != nullptr) || (db->genes && !db->gene_strings)) return KSLAM_ERR_ARG;
   if (al->n_overlaps && !al->overlaps) return KSLAM_ERR_ARG;
   if (check_overlaps(db, reads, al->overlaps, al->n_overlaps, al->cigar_pool, al->n_cigar_words) != KSLAM_OK) return KSLAM_ERR_ARG;
   try {
@@ -551,7 +563,7 @@ int kslam_sam_batch_single(const kslam_sam_params *prm, const kslam_sam_db *db, 
       cur.r1Pos = o.read; cur.r2Pos = 0;
     }
     if (cur.pairs.size()) rp.push_back(cur);
-    return sam_finish(c, rp, false, text, len, nullptr);
+    return sam_finish(c, rp, false, want_sam != 0, text, len, nullptr, taxdb, taxa);
   } catch (const std::exception &) { return KSLAM_ERR_NOMEM; }
 }
 

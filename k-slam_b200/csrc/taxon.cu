@@ -1,0 +1,428 @@
+// taxon.cu — taxonomy database, lowest common ancestor, per-read taxon assignment and the metagenomic result files
+// (host code; the part of the reference's batch loop after the SAM records, /root/reference/src/SLAM.h:243-265).
+//
+// north_star keeps LCA assignment and output formatting on the host; they are restated here so the library carries a
+// run from FASTQ to the XML / _PerRead / _abbreviated files. Restated functions:
+//   TaxonomyDB: readTaxonomyIndex, parseNodesDump, parseNamesDump, writeTaxonomyIndex, getParentTaxID,
+//               getLowestCommonAncestor, getLineage, getScientificName, getRank     TaxonomyDatabase.h:95-265
+//   getResultFromPairedOverlaps, convertAlignmentsToIdentifiedTaxonomies_parallel        MetagenomicResults.h:88-111,182-197
+//   combineTaxonomies, combineRangeOfIdentifiedTaxonomy                                  MetagenomicResults.h:117-176
+//   sortResults, writeResults, getXML, correctXML, writeAbbreviatedResultsFile, writePerReadResults   :213-369,455-463
+//   Gene::operator==, geneSort                                                           GenbankTools.h:82-89,116-125
+// The reference decides ties with std::sort; the same std::sort calls are issued here over sequences that compare the
+// same way, so the permutations coincide. One exception is documented in include/kslam.h: combineTaxonomies uses
+// __gnu_parallel::sort, whose order among reads of one taxon depends on the OpenMP thread count; this file uses the
+// sequential std::sort (the reference with one thread). That order only shows when two genes compare equal
+// (same protein id and product) but differ in their other fields.
+#include "common.cuh"
+#include "host_stages.h"
+#include <algorithm>
+#include <fstream>
+#include <stdexcept>
+#include <stdio.h>
+#include <string.h>
+#include <unordered_map>
+
+using namespace kslam_host;
+
+namespace {
+
+struct TaxEntry {                                          // TaxonomyEntry, TaxonomyDatabase.h:24-43 (fields that are read)
+  uint32_t taxonomyID = 0, parentTaxonomyID = 0;
+  std::string scientificName, rank;
+};
+
+// tokenise, sequenceTools.h:117-133
+std::vector<std::string> tokenise(const std::string &line, const char *delimiters) {
+  std::vector<std::string> tokens;
+  std::string::size_type lastPos = line.find_first_not_of(delimiters, 0);
+  std::string::size_type pos = line.find_first_of(delimiters, lastPos);
+  while (pos != std::string::npos || lastPos != std::string::npos) {
+    tokens.push_back(line.substr(lastPos, pos - lastPos));
+    lastPos = line.find_first_not_of(delimiters, pos);
+    pos = line.find_first_of(delimiters, lastPos);
+  }
+  return tokens;
+}
+
+}  // namespace
+
+struct kslam_taxdb {
+  // the same container as the reference's taxIDsAndEntries filled by the same insert sequence, so that the iteration
+  // order writeTaxonomyIndex depends on is the same
+  std::unordered_map<uint32_t, TaxEntry> nodes;
+
+  void read_index(const char *path) {                      // readTaxonomyIndex, TaxonomyDatabase.h:166-183
+    std::ifstream in(path);
+    if (!in.is_open()) throw std::runtime_error("unable to open taxonomy index file");
+    for (std::string line; getline(in, line);) {
+      TaxEntry e;
+      e.taxonomyID = stoi(line);
+      getline(in, line); e.parentTaxonomyID = stoi(line);
+      getline(in, line); e.scientificName = line;
+      getline(in, line); e.rank = line;
+      nodes.insert({e.taxonomyID, e});
+    }
+  }
+  void parse_nodes(const char *path) {                     // parseNodesDump, :95-117
+    std::ifstream in(path);
+    if (!in.is_open()) throw std::runtime_error("unable to open nodes file");
+    std::string line;
+    while (in.good()) {
+      getline(in, line);
+      std::vector<std::string> tokens = tokenise(line, "\t|");
+      if (tokens.size() > 2) {
+        TaxEntry e;
+        e.taxonomyID = stoi(tokens[0]);
+        e.parentTaxonomyID = stoi(tokens[1]);
+        e.rank = tokens[2];
+        nodes.insert({e.taxonomyID, e});                   // a repeated id keeps its first parent and rank (:111-114)
+      }
+    }
+  }
+  void parse_names(const char *path) {                     // parseNamesDump, :118-151
+    std::ifstream in(path);
+    if (!in.is_open()) throw std::runtime_error("unable to open names file");
+    std::string line;
+    while (in.good()) {
+      getline(in, line);
+      std::vector<std::string> tokens = tokenise(line, "|");
+      for (auto &token : tokens)
+        if (token.size() > 1) {
+          if (token[0] == '\t') token.erase(0, 1);
+          if (token[token.size() - 1] == '\t') token.erase(token.size() - 1, 1);
+        }
+      if (tokens.size() > 3) {
+        TaxEntry e;
+        e.taxonomyID = stoi(tokens[0]);
+        if (tokens[3] != "scientific name") continue;
+        e.scientificName = tokens[1];
+        auto it = nodes.insert({e.taxonomyID, e});
+        if (!it.second) it.first->second.scientificName = e.scientificName;
+      }
+    }
+  }
+  uint32_t parent(uint32_t taxID) const {                  // getParentTaxID, :225-231: the root's children end the walk
+    auto it = nodes.find(taxID);
+    return (it != nodes.end() && it->second.parentTaxonomyID != 1) ? it->second.parentTaxonomyID : 0;
+  }
+  const std::string &name(uint32_t taxID) const {          // getScientificName, :233-239
+    static const std::string empty;
+    auto it = nodes.find(taxID);
+    return it != nodes.end() ? it->second.scientificName : empty;
+  }
+  const std::string &rank(uint32_t taxID) const {          // getRank, :241-247
+    static const std::string empty;
+    auto it = nodes.find(taxID);
+    return it != nodes.end() ? it->second.rank : empty;
+  }
+  // getLowestCommonAncestor, :185-223. Paths run from the node up to (not including) the root's child boundary, are
+  // reversed, ordered by length, and compared position by position over the shortest one. The reference walks parent
+  // links without a cycle check; a database with a cycle would hang it, here the walk stops after nodes.size() steps.
+  uint32_t lca(const uint32_t *taxIDs, uint64_t n) const {
+    if (n == 0) return 0;
+    std::vector<std::vector<uint32_t>> paths;
+    for (uint64_t k = 0; k < n; k++) {
+      std::vector<uint32_t> path;
+      uint32_t t = taxIDs[k];
+      while (t != 0 && path.size() <= nodes.size()) { path.push_back(t); t = parent(t); }
+      paths.push_back(std::move(path));
+    }
+    size_t shortest = paths[0].size();
+    for (auto &p : paths) { std::reverse(p.begin(), p.end()); shortest = std::min(shortest, p.size()); }
+    uint32_t consensus = 0;                                // the result does not depend on the order among equal lengths,
+    for (size_t i = 0; i < shortest; i++) {                // so the reference's sort by length reduces to "the shortest"
+      uint32_t temp = 0;
+      for (auto &p : paths) {
+        if (temp == 0) temp = p[i];
+        else if (temp != p[i]) return consensus;
+      }
+      consensus = temp;
+    }
+    return consensus;
+  }
+  std::string lineage(uint32_t taxonomyID) const {         // getLineage, :249-265 (131567 = cellular organisms, skipped)
+    std::string lineage;
+    for (size_t steps = 0; steps <= nodes.size() + 1; steps++) {
+      if (taxonomyID != 131567) {
+        if (lineage.size()) lineage.insert(0, "; ");
+        lineage.insert(0, name(taxonomyID));
+        if (rank(taxonomyID) == "species") lineage.clear();
+      }
+      taxonomyID = parent(taxonomyID);
+      if (taxonomyID == 0) {
+        if (lineage.size()) lineage.append(".");
+        break;
+      }
+    }
+    return lineage;
+  }
+};
+
+// ---- IdentifiedTaxonomy (MetagenomicResults.h:32-42), one per read pair, kept compact: the read id lives in an arena
+// (the batch's buffers are recycled), genes are references into the database's gene table + a count.
+namespace {
+struct GeneHit { const kslam_gene *g = nullptr; int count = 1; };
+struct PerRead { uint32_t taxonomyID = 0; uint32_t id_len = 0; uint64_t id_off = 0; uint64_t gene_off = 0; uint32_t n_genes = 0; uint32_t has_read = 0; };
+}
+
+struct kslam_taxa {
+  kslam_sam_db db{};                                       // gene strings are read through it until kslam_taxa_results
+  std::vector<PerRead> items;
+  std::string ids;
+  std::vector<GeneHit> genes;
+};
+
+namespace {
+
+struct GeneOps {
+  const kslam_sam_db *db;
+  std::string_view s(const kslam_gene *g, int w) const { return gene_str(db, g, w); }
+  bool equal(const GeneHit &a, const GeneHit &b) const {   // Gene::operator==, GenbankTools.h:82-89
+    if (s(a.g, GENE_PROTEIN).size() == 0 && s(b.g, GENE_PROTEIN).size() == 0) return s(a.g, GENE_NAME) == s(b.g, GENE_NAME);
+    if (s(a.g, GENE_PROTEIN) == s(b.g, GENE_PROTEIN)) return s(a.g, GENE_PRODUCT) == s(b.g, GENE_PRODUCT);
+    return false;
+  }
+  bool less(const GeneHit &a, const GeneHit &b) const {    // geneSort, GenbankTools.h:116-125
+    if (s(a.g, GENE_PROTEIN).size() == 0 && s(b.g, GENE_PROTEIN).size() == 0) return s(a.g, GENE_NAME) < s(b.g, GENE_NAME);
+    if (s(a.g, GENE_PROTEIN) == s(b.g, GENE_PROTEIN)) return s(a.g, GENE_PRODUCT) < s(b.g, GENE_PRODUCT);
+    return s(a.g, GENE_PROTEIN) < s(b.g, GENE_PROTEIN);
+  }
+};
+
+void xml_escape(std::string &out, std::string_view in) {   // correctXML, MetagenomicResults.h:276-301
+  for (char ch : in) switch (ch) {
+    case '<': out += "&lt;"; break;
+    case '>': out += "&gt;"; break;
+    case '&': out += "&amp;"; break;
+    case '\'': out += "&apos;"; break;
+    case '"': out += "&quot;"; break;
+    default: out.push_back(ch);
+  }
+}
+
+struct Combined { uint32_t taxonomyID = 0; std::vector<std::string_view> reads; std::vector<GeneHit> genes; };
+
+}  // namespace
+
+// getResultFromPairedOverlaps (MetagenomicResults.h:88-111) for every per-read record of the batch, in order
+int kslam_host::taxa_add_batch(kslam_taxa *taxa, const kslam_taxdb *taxdb, const Ctx &c, const std::vector<ReadPair> &rp, uint32_t threads) {
+  try {
+    if (taxa->items.empty()) taxa->db = *c.db;
+    else if (taxa->db.genes != c.db->genes || taxa->db.gene_strings != c.db->gene_strings) return KSLAM_ERR_STATE;   // one database per run
+    const GeneOps ops{c.db};
+    struct Part { std::vector<PerRead> items; std::string ids; std::vector<GeneHit> genes; };
+    std::vector<Part> parts(std::max(1u, threads));
+    parallel_ranges(threads, rp.size(), [&](uint32_t t, size_t lo, size_t hi) {
+      Part &part = parts[t];
+      std::vector<uint32_t> taxIDs;
+      std::vector<GeneHit> genes;
+      for (size_t i = lo; i < hi; i++) {
+        const ReadPair &read = rp[i];
+        PerRead r;
+        if (read.pairs.size()) {
+          taxIDs.clear(); genes.clear();
+          for (const POv &a : read.pairs) {
+            taxIDs.push_back(c.db->taxonomy_ids ? c.db->taxonomy_ids[a.entry] : 0);
+            if (const kslam_gene *g = best_gene(c.db, a.entry, a.refStart, a.refEnd)) genes.push_back(GeneHit{g, 1});
+          }
+          std::sort(genes.begin(), genes.end(), [&](const GeneHit &x, const GeneHit &y) { return ops.less(x, y); });
+          genes.erase(std::unique(genes.begin(), genes.end(), [&](const GeneHit &x, const GeneHit &y) { return ops.equal(x, y); }), genes.end());
+          r.has_read = 1;
+          r.id_off = part.ids.size();
+          r.id_len = (uint32_t)(c.reads->id_offs[read.r1Pos + 1] - c.reads->id_offs[read.r1Pos]);
+          part.ids.append(c.reads->ids + c.reads->id_offs[read.r1Pos], r.id_len);
+          r.gene_off = part.genes.size(); r.n_genes = (uint32_t)genes.size();
+          part.genes.insert(part.genes.end(), genes.begin(), genes.end());
+          r.taxonomyID = taxdb->lca(taxIDs.data(), taxIDs.size());
+        }
+        part.items.push_back(r);
+      }
+    });
+    for (Part &part : parts) {
+      const uint64_t id_base = taxa->ids.size(), gene_base = taxa->genes.size();
+      taxa->ids += part.ids;
+      taxa->genes.insert(taxa->genes.end(), part.genes.begin(), part.genes.end());
+      for (PerRead r : part.items) { r.id_off += id_base; r.gene_off += gene_base; taxa->items.push_back(r); }
+    }
+    return KSLAM_OK;
+  } catch (const std::exception &) { return KSLAM_ERR_NOMEM; }
+}
+
+extern "C" {
+
+int kslam_taxdb_open(const char *path, kslam_taxdb **out) {          // TaxonomyDB(inFileName), TaxonomyDatabase.h:87-93
+  if (!path || !out) return KSLAM_ERR_ARG;
+  kslam_taxdb *db = nullptr;
+  try {
+    db = new kslam_taxdb();
+    db->read_index(path);
+    *out = db;
+    return KSLAM_OK;
+  } catch (const std::exception &) { delete db; return KSLAM_ERR_ARG; }   // unreadable file or a line stoi rejects
+}
+
+int kslam_taxdb_build(const char *names_dmp, const char *nodes_dmp, const char *out_path) {   // writeTaxonomyIndex, :153-164
+  if (!names_dmp || !nodes_dmp || !out_path) return KSLAM_ERR_ARG;
+  try {
+    kslam_taxdb db;
+    db.parse_nodes(nodes_dmp);
+    db.parse_names(names_dmp);
+    std::ofstream out(out_path);
+    if (!out.is_open()) return KSLAM_ERR_ARG;
+    for (auto &e : db.nodes) out << e.first << "\n" << e.second.parentTaxonomyID << "\n" << e.second.scientificName << "\n" << e.second.rank << "\n";
+    out.close();
+    return out.fail() ? KSLAM_ERR_STATE : KSLAM_OK;
+  } catch (const std::exception &) { return KSLAM_ERR_ARG; }
+}
+
+uint64_t kslam_taxdb_size(const kslam_taxdb *db) { return db ? db->nodes.size() : 0; }
+uint32_t kslam_taxdb_lca(const kslam_taxdb *db, const uint32_t *tax_ids, uint64_t n) { return (db && (tax_ids || !n)) ? db->lca(tax_ids, n) : 0; }
+
+int kslam_taxdb_lineage(const kslam_taxdb *db, uint32_t tax_id, char **text, uint64_t *len) {
+  if (!db || !text) return KSLAM_ERR_ARG;
+  const std::string s = db->lineage(tax_id);
+  *text = dup_text(s);
+  if (len) *len = s.size();
+  return *text ? KSLAM_OK : KSLAM_ERR_NOMEM;
+}
+int kslam_taxdb_name(const kslam_taxdb *db, uint32_t tax_id, char **text, uint64_t *len) {
+  if (!db || !text) return KSLAM_ERR_ARG;
+  const std::string &s = db->name(tax_id);
+  *text = dup_text(s);
+  if (len) *len = s.size();
+  return *text ? KSLAM_OK : KSLAM_ERR_NOMEM;
+}
+void kslam_taxdb_close(kslam_taxdb *db) { delete db; }
+
+int kslam_taxa_create(kslam_taxa **out) {
+  if (!out) return KSLAM_ERR_ARG;
+  *out = new (std::nothrow) kslam_taxa();
+  return *out ? KSLAM_OK : KSLAM_ERR_NOMEM;
+}
+void kslam_taxa_destroy(kslam_taxa *taxa) { delete taxa; }
+
+// End of the run, SLAM.h:256-265: <out>_PerRead from the per-read results in batch order; then one record per taxon.
+int kslam_taxa_results(kslam_taxa *taxa, const kslam_taxdb *taxdb, uint32_t num_reads, char **per_read, uint64_t *per_read_len,
+                       char **xml, uint64_t *xml_len, char **abbreviated, uint64_t *abbreviated_len) {
+  if (!taxa || !taxdb) return KSLAM_ERR_ARG;
+  try {
+    const GeneOps ops{&taxa->db};
+    auto id_of = [&](const PerRead &r) { return std::string_view(taxa->ids.data() + r.id_off, r.id_len); };
+    if (per_read) {                                        // writePerReadResults, MetagenomicResults.h:455-463
+      std::string t;
+      for (const PerRead &r : taxa->items)
+        if (r.has_read) { t += id_of(r); t.push_back('\t'); t += std::to_string(r.taxonomyID); t.push_back('\n'); }
+      *per_read = dup_text(t);
+      if (per_read_len) *per_read_len = t.size();
+      if (!*per_read) return KSLAM_ERR_NOMEM;
+    }
+    if (!xml && !abbreviated) return KSLAM_OK;
+    // combineTaxonomies, :149-176. The loop skips the first element and starts with testTaxID = 0: reads without a taxon
+    // (id 0) sort first and are dropped, and when there are none the very first record of the sorted vector is left out
+    // of its range (or its taxon dropped, if it was alone) — kept as is.
+    std::vector<PerRead> sorted(taxa->items);
+    std::sort(sorted.begin(), sorted.end(), [](const PerRead &i, const PerRead &j) { return i.taxonomyID < j.taxonomyID; });
+    std::vector<Combined> results;
+    auto combine = [&](size_t begin, size_t end) {         // combineRangeOfIdentifiedTaxonomy, :117-143
+      Combined t;
+      t.taxonomyID = sorted[begin].taxonomyID;
+      for (size_t k = begin; k < end; k++) {
+        const PerRead &r = sorted[k];
+        t.genes.insert(t.genes.end(), taxa->genes.begin() + r.gene_off, taxa->genes.begin() + r.gene_off + r.n_genes);
+        if (r.has_read) t.reads.push_back(id_of(r));
+      }
+      std::sort(t.genes.begin(), t.genes.end(), [&](const GeneHit &x, const GeneHit &y) { return ops.less(x, y); });
+      auto first = t.genes.begin(), last = t.genes.end();
+      if (first != last) {
+        auto result = first;
+        while (++first != last) {
+          if (!ops.equal(*result, *first)) *(++result) = *first;
+          else result->count++;
+        }
+        t.genes.resize(std::distance(t.genes.begin(), ++result));
+      }
+      results.push_back(std::move(t));
+    };
+    if (!sorted.empty()) {
+      uint32_t testTaxID = 0;
+      size_t start = 0;
+      for (size_t tax = 1; tax < sorted.size(); tax++)
+        if (sorted[tax].taxonomyID != testTaxID) {
+          if (testTaxID != 0) combine(start, tax);
+          testTaxID = sorted[tax].taxonomyID;
+          start = tax;
+        }
+      if (sorted[start].taxonomyID != 0) combine(start, sorted.size());
+    }
+    auto sort_results = [&]() {                            // sortResults, :254-275
+      std::sort(results.begin(), results.end(), [](const Combined &i, const Combined &j) {
+        if (i.reads.size() == j.reads.size()) return i.taxonomyID < j.taxonomyID;
+        return i.reads.size() > j.reads.size();
+      });
+      for (auto &entry : results) {
+        std::sort(entry.reads.begin(), entry.reads.end());
+        std::sort(entry.genes.begin(), entry.genes.end(), [&](const GeneHit &i, const GeneHit &j) {
+          if (i.count == j.count) {
+            if (i.g->cds_start == j.g->cds_start) return ops.s(i.g, GENE_LOCUS) < ops.s(j.g, GENE_LOCUS);
+            return i.g->cds_start < j.g->cds_start;
+          }
+          return i.count > j.count;
+        });
+      }
+    };
+    sort_results();                                        // writeResults sorts, writeAbbreviatedResultsFile sorts again
+    if (xml) {                                             // getXML, :302-369
+      std::string o;
+      for (const Combined &entry : results) {
+        o += "<taxon>\n  <abundance numReads=\"";
+        o += std::to_string(entry.reads.size());
+        o += "\">";
+        o += std::to_string(entry.reads.size() * 100.0 / num_reads);
+        o += "</abundance>\n  <taxonomyID>";
+        o += std::to_string(entry.taxonomyID);
+        o += "</taxonomyID>\n  <lineage>";
+        xml_escape(o, taxdb->lineage(entry.taxonomyID));
+        o += "</lineage>\n  <name>";
+        xml_escape(o, taxdb->name(entry.taxonomyID));
+        o += "</name>\n  <genes>\n";
+        for (const GeneHit &gene : entry.genes) {
+          o += "    <gene protein=\""; xml_escape(o, ops.s(gene.g, GENE_PROTEIN));
+          o += "\" locus=\""; xml_escape(o, ops.s(gene.g, GENE_LOCUS));
+          o += "\" product=\""; xml_escape(o, ops.s(gene.g, GENE_PRODUCT));
+          o += "\" GeneID=\""; o += std::to_string(gene.g->gene_id);
+          o += "\" reference=\""; xml_escape(o, ops.s(gene.g, GENE_REFERENCE));
+          o += "\" numReads=\""; o += std::to_string(gene.count);
+          o += "\" cdsStart=\""; o += std::to_string(gene.g->cds_start);
+          o += "\" cdsEnd=\""; o += std::to_string(gene.g->cds_stop);
+          o += "\">"; xml_escape(o, ops.s(gene.g, GENE_NAME));
+          o += "</gene>\n";
+        }
+        o += "  </genes>\n  <reads>\n";
+        for (auto &read : entry.reads) { o += "    <read>"; xml_escape(o, read); o += "</read>\n"; }
+        o += "  </reads>\n</taxon>\n";
+      }
+      *xml = dup_text(o);
+      if (xml_len) *xml_len = o.size();
+      if (!*xml) return KSLAM_ERR_NOMEM;
+    }
+    if (abbreviated) {                                     // writeAbbreviatedResultsFile, :237-249 (ostream << double = %g)
+      sort_results();
+      std::string o;
+      char num[64];
+      for (const Combined &entry : results) {
+        o += taxdb->name(entry.taxonomyID);
+        o.push_back('\t');
+        snprintf(num, sizeof num, "%g", entry.reads.size() * 100.0 / num_reads);
+        o += num;
+        o.push_back('\n');
+      }
+      *abbreviated = dup_text(o);
+      if (abbreviated_len) *abbreviated_len = o.size();
+      if (!*abbreviated) return KSLAM_ERR_NOMEM;
+    }
+    return KSLAM_OK;
+  } catch (const std::exception &) { return KSLAM_ERR_NOMEM; }
+}
+
+}  // extern "C"

@@ -242,3 +242,83 @@ def adversarial_set(seed: int = 7, n_genomes: int = 12, glen: int = 20_000, n_pa
     offs = np.zeros(len(reads) + 1, dtype=np.uint64)
     offs[1:] = np.cumsum([len(r) for r in reads])
     return gen_bases, gen_offs, np.concatenate(reads), offs
+
+
+# ---------------------------------------------------------------- config 2: taxonomy + GenBank flat files
+
+def tree_taxonomy(n_strains: int):
+    """The NCBI-style taxonomy of tree_genomes(n_strains): root 1 -> superkingdom 2 -> phyla -> genera -> species -> one
+    strain node per genome (same index arithmetic as tree_genomes). -> (nodes [(id, parent, rank, name)], strain tax ids)."""
+    n_species = max(1, n_strains // 5); n_genera = max(1, n_species // 4); n_phyla = max(1, n_genera // 5)
+    nodes = [(1, 1, "no rank", "root"), (131567, 1, "no rank", "cellular organisms"), (2, 131567, "superkingdom", "Bacteria")]
+    ph = [1000 + i for i in range(n_phyla)]; ge = [2000 + i for i in range(n_genera)]; sp = [10000 + i for i in range(n_species)]
+    nodes += [(ph[i], 2, "phylum", f"Phylum{i} <synthetic>") for i in range(n_phyla)]
+    nodes += [(ge[i], ph[i % n_phyla], "genus", f"Genus{i}") for i in range(n_genera)]
+    nodes += [(sp[i], ge[i % n_genera], "species", f"Genus{i % n_genera} species{i}") for i in range(n_species)]
+    strains = [100000 + i for i in range(n_strains)]
+    nodes += [(strains[i], sp[i % n_species], "no rank", f"Genus{(i % n_species) % n_genera} species{i % n_species} str. S{i} & co") for i in range(n_strains)]
+    return nodes, np.array(strains, dtype=np.uint32)
+
+
+def write_taxonomy_dumps(nodes, names_path, nodes_path):
+    """names.dmp / nodes.dmp in NCBI's `\\t|\\t` layout (what --parse-taxonomy reads, TaxonomyDatabase.h:95-151); every node
+    also gets a synonym line, which the parser must skip."""
+    with open(nodes_path, "w") as f:
+        for tid, parent, rank, _ in nodes:
+            f.write(f"{tid}\t|\t{parent}\t|\t{rank}\t|\t\t|\t0\t|\t1\t|\t11\t|\t1\t|\t0\t|\t1\t|\t1\t|\t0\t|\t\t|\n")
+    with open(names_path, "w") as f:
+        for tid, _, _, name in nodes:
+            f.write(f"{tid}\t|\told name of {tid}\t|\t\t|\tsynonym\t|\n")
+            f.write(f"{tid}\t|\t{name}\t|\t\t|\tscientific name\t|\n")
+
+
+def genbank_text(bases: bytes, accession: str, gi: int, taxon: int, organism: str, strain_idx: int, species_idx: int, seed: int = 0,
+                 cds_every: int = 1000) -> bytes:
+    """One GenBank flat-file record: LOCUS / DEFINITION / VERSION ACC.1 GI:n / source with
+    /db_xref="taxon:T" / a gene + CDS feature about every `cds_every` bases (qualifiers /gene /locus_tag /product /protein_id
+    /db_xref="GeneID:n", some products wrapped over two lines, some CDS on the complement strand, a tRNA now and then) /
+    ORIGIN in 60-base lines / `//`. Protein ids are per SPECIES, so strains of one species share proteins."""
+    rng = np.random.default_rng(seed)
+    n = len(bases)
+    out = [f"LOCUS       {accession:<16} {n:>10} bp    DNA     circular BCT 01-JAN-2020",
+           f"DEFINITION  {organism}, complete genome.",
+           f"ACCESSION   {accession}",
+           f"VERSION     {accession}.1  GI:{gi}",
+           "KEYWORDS    .",
+           f"SOURCE      {organism}",
+           f"  ORGANISM  {organism}",
+           "            Bacteria; Synthetic.",
+           "FEATURES             Location/Qualifiers",
+           f"     source          1..{n}",
+           f"                     /organism=\"{organism}\"",
+           "                     /mol_type=\"genomic DNA\"",
+           f"                     /db_xref=\"taxon:{taxon}\""]
+    pos, k = 50, 0
+    while pos + 400 < n:
+        length = int(rng.integers(300, min(900, n - pos - 10)))
+        a, b = pos + 1, pos + length
+        loc = f"complement({a}..{b})" if k % 3 == 2 else f"{a}..{b}"
+        tag = f"S{strain_idx}_{k:04d}"
+        if k % 7 == 6:
+            out += [f"     tRNA            {loc}", f"                     /locus_tag=\"{tag}\"", f"                     /product=\"tRNA-Ala\""]
+        else:
+            gene = f"gen{k % 50}{'AB'[k % 2]}"
+            product = f"protein <{k}> of species {species_idx}"
+            out += [f"     gene            {loc}", f"                     /gene=\"{gene}\"", f"                     /locus_tag=\"{tag}\""]
+            out += [f"     CDS             {loc}", f"                     /gene=\"{gene}\"", f"                     /locus_tag=\"{tag}\""]
+            if k % 4:
+                out += [f"                     /product=\"{product}\""]
+            else:
+                out += [f"                     /product=\"very long hypothetical membrane transporter", f"                     component number {k} of species {species_idx}\""]
+            if k % 5:
+                out += [f"                     /protein_id=\"WP_{species_idx:03d}{k:05d}.1\""]
+            out += [f"                     /db_xref=\"GeneID:{5_000_000 + species_idx * 10_000 + k}\"",
+                    "                     /translation=\"MKVLAAGIVGLCAQEPTW\""]
+        pos += int(rng.integers(cds_every // 2, cds_every * 3 // 2)); k += 1
+    out.append("ORIGIN      ")
+    low = bases.lower().decode()
+    for i in range(0, n, 60):
+        chunk = low[i:i + 60]
+        out.append(f"{i + 1:>9} " + " ".join(chunk[j:j + 10] for j in range(0, len(chunk), 10)))
+    out.append("//")
+    return ("\n".join(out) + "\n").encode()

@@ -13,6 +13,8 @@
 //   screenOverlapsByScoreThreshold /root/reference/src/Overlap.h:329-341
 //   getPairedOverlaps            /root/reference/src/PairedOverlap.h:243-272
 //   StripedSmithWaterman::Aligner::Align  /root/reference/src/ssw_cpp.cpp:234-283
+//   host stages up to SAM / XML: PairedOverlap.h:314-576, SAM.h, MetagenomicResults.h, TaxonomyDatabase.h
+//   createIndexFromGBFF / createIndexFromFASTA   /root/reference/src/GenbankTools.h:224-260,481-527
 //
 // Built by oracle/Makefile into oracle/_ref/libkslam_ref.so (git-ignored, travels to the
 // GPU box as a prebuilt binary). Boost is absent from this image; oracle/ref_shim/
@@ -53,7 +55,10 @@ struct KrefCtx {
   std::vector<OverlapTemp> seeds;
   std::vector<Overlap> overlaps;
   std::vector<PairedOverlap> pairs;
+  std::vector<IdentifiedTaxonomy> taxa;   // grows batch by batch like SLAM.h:243-249
 };
+GenbankIndex g_parsed_index;              // what the reference's database builders handed to the (stub) archive
+void capture_index(const void *obj) { g_parsed_index = *(const GenbankIndex *)obj; }
 
 // Records shared with oracle/kslam_oracle.h and include/kslam.h (same layout).
 struct KmerRec { uint64_t kmer; uint32_t id_flags; uint32_t offset; };
@@ -335,5 +340,127 @@ uint64_t kref_fastq_get(void *h, int which, char *buf, uint64_t *offs) {
   return pos;
 }
 void kref_fastq_close(void *h) { delete (KrefFastq *)h; }
+
+// ---- genes / taxonomy ids / read ids of the in-memory index, the taxonomy database and the metagenomic outputs -----------
+void kref_set_read_ids(void *h, const char *ids, const uint64_t *offs) {
+  KrefCtx *c = (KrefCtx *)h;
+  for (size_t i = 0; i < c->reads.size(); i++) c->reads[i].sequenceIdentifier.assign(ids + offs[i], ids + offs[i + 1]);
+}
+void kref_set_entry_meta(void *h, uint64_t e, uint32_t taxonomy_id, const char *locus_tag) {
+  KrefCtx *c = (KrefCtx *)h;
+  c->idx.entries[e].taxonomyID = taxonomy_id;
+  if (locus_tag) c->idx.entries[e].locusTag = locus_tag;
+}
+void kref_add_gene(void *h, uint64_t e, const char *name, const char *locus, const char *protein, const char *product,
+                   const char *reference, uint32_t gene_id, uint32_t start, uint32_t stop) {
+  KrefCtx *c = (KrefCtx *)h;
+  Gene g(name, locus, protein, product, reference, CDS(start, stop, false));
+  g.geneID = gene_id;
+  c->idx.entries[e].genes.push_back(g);
+}
+void *kref_taxdb_open(const char *path) {
+  try { return new TaxonomyDB(path); } catch (...) { return nullptr; }
+}
+void kref_taxdb_close(void *t) { delete (TaxonomyDB *)t; }
+int kref_taxdb_build(const char *names, const char *nodes, const char *out) {       // --parse-taxonomy, main.cpp:131-141
+  try { TaxonomyDB t; t.writeTaxonomyIndex(out, names, nodes); return 0; } catch (...) { return -1; }
+}
+uint64_t kref_taxdb_size(void *t) { return ((TaxonomyDB *)t)->taxIDsAndEntries.size(); }
+uint32_t kref_lca(void *t, const uint32_t *ids, uint64_t n) {
+  return ((TaxonomyDB *)t)->getLowestCommonAncestor(std::vector<uint32_t>(ids, ids + n));
+}
+uint64_t kref_lineage(void *t, uint32_t id, int which, char *buf, uint64_t cap) {
+  std::string s = which == 0 ? ((TaxonomyDB *)t)->getLineage(id) : ((TaxonomyDB *)t)->getScientificName(id);
+  if (buf && cap >= s.size()) memcpy(buf, s.data(), s.size());
+  return s.size();
+}
+// One pass of the batch loop after pairing, SLAM.h:215-249, on what kref_pair (paired) or kref_align_to_database +
+// kref_screen (single-end) left in the ctx: screens, pseudo-assembly, SAM records if wanted, then
+// convertAlignmentsToIdentifiedTaxonomies_parallel appended to the run's results. Returns the SAM text length.
+uint64_t kref_meta_batch(void *h, void *taxdb, uint32_t num_alignments, double fraction, int pseudo, int sam_xa, int paired,
+                         int want_sam, const char *tmp_path, char *buf, uint64_t cap) {
+  KrefCtx *c = (KrefCtx *)h;
+  numSAMAlignments = num_alignments; scoreFractionThreshold = fraction; SAMXA = sam_xa != 0; pairedData = paired != 0;
+  std::vector<ReadPairAndOverlaps> rp;
+  if (paired) {
+    rp = getPerReadOverlaps(c->pairs.begin(), c->pairs.end(), c->reads.size() / 2);
+    c->pairs.clear();
+    uint32_t maxInsertSize = getMaxAllowedInsertSize(rp);
+    screenPairedAlignmentsByInsertSize(rp, maxInsertSize, true);
+    screenPairedAlignmentsByScore(rp, scoreFractionThreshold);
+  } else {
+    auto perRead = getPerReadOverlaps(c->overlaps.begin(), c->overlaps.end());
+    rp = getDummyAlignmentPairsFromSingleEndReads(perRead, c->reads);
+    screenPairedAlignmentsByScore(rp, scoreFractionThreshold);
+  }
+  if (pseudo) {
+    pseudoAssembly(rp, c->reads, c->idx);
+    screenPairedAlignmentsByScore(rp, scoreFractionThreshold);
+  }
+  std::string text;
+  if (want_sam) {
+    {
+      std::ofstream sam(tmp_path);
+      for (auto &read : rp) writeSAMOutputPairs(sam, read, c->reads, c->idx);
+    }
+    std::ifstream in(tmp_path, std::ios::binary);
+    text.assign((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+    if (buf && cap >= text.size()) memcpy(buf, text.data(), text.size());
+  }
+  if (taxdb) {
+    auto fresh = convertAlignmentsToIdentifiedTaxonomies_parallel(rp.begin(), rp.end(), c->reads, c->idx, *(TaxonomyDB *)taxdb);
+    c->taxa.insert(c->taxa.end(), fresh.begin(), fresh.end());
+  }
+  pairedData = true;
+  return text.size();
+}
+// End of the run, SLAM.h:256-265: <prefix>_PerRead, <prefix> (XML), <prefix>_abbreviated.
+void kref_meta_finish(void *h, void *taxdb, uint32_t num_reads, const char *prefix) {
+  KrefCtx *c = (KrefCtx *)h;
+  TaxonomyDB &taxDB = *(TaxonomyDB *)taxdb;
+  std::string outFileName(prefix);
+  std::ofstream perReadout(outFileName + "_PerRead");
+  writePerReadResults(c->taxa, perReadout);
+  c->taxa = combineTaxonomies(c->taxa);
+  std::ofstream outFile(outFileName);
+  writeResults(c->taxa, outFile, taxDB, num_reads);
+  writeAbbreviatedResultsFile(c->taxa, outFileName + "_abbreviated", taxDB, num_reads);
+  c->taxa.clear();
+}
+
+// ---- the reference's database builders; the GenbankIndex they build is captured from the stub archive -------------------
+// kind 0 = createIndexFromGBFF (needs a file "taxDB" in the CWD, GenbankTools.h:483), 1 = createIndexFromFASTA.
+// Returns the number of entries or -1 when the reference throws.
+int64_t kref_parse_index(int kind, const char *const *paths, uint64_t n, const char *out_path) {
+  std::vector<std::string> names(paths, paths + n);
+  g_parsed_index = GenbankIndex();
+  kref_shim::archive_hook() = capture_index;
+  int64_t rc;
+  try {
+    if (kind == 0) createIndexFromGBFF(names, out_path); else createIndexFromFASTA(names, out_path);
+    rc = (int64_t)g_parsed_index.entries.size();
+  } catch (...) { rc = -1; }
+  kref_shim::archive_hook() = nullptr;
+  return rc;
+}
+// Text dump of the captured index, fields separated by 0x1f, records by 0x1e:
+//   E locusTag taxonomyID genbankID isPlasmid is16S bases | G geneName locusTag proteinID product referenceSequence geneID start stop complement
+uint64_t kref_parsed_index_dump(char *buf, uint64_t cap) {
+  std::string t;
+  const char F = 0x1f, R = 0x1e;
+  for (auto &e : g_parsed_index.entries) {
+    t += "E"; t += F; t += e.locusTag; t += F; t += std::to_string(e.taxonomyID); t += F; t += std::to_string(e.genbankID); t += F;
+    t += std::to_string((int)e.isPlasmid); t += F; t += std::to_string((int)e.is16S); t += F; t += e.bases; t += R;
+    for (auto &g : e.genes) {
+      t += "G"; t += F; t += g.geneName; t += F; t += g.locusTag; t += F; t += g.proteinID; t += F; t += g.product; t += F;
+      t += g.referenceSequence; t += F; t += std::to_string(g.geneID); t += F; t += std::to_string(g.codingSequence.start); t += F;
+      t += std::to_string(g.codingSequence.stop); t += F; t += std::to_string((int)g.codingSequence.complement); t += R;
+    }
+  }
+  if (buf && cap >= t.size()) memcpy(buf, t.data(), t.size());
+  return t.size();
+}
+// Use the captured index as the ctx's database (so alignment, SAM gene tags and taxonomy run on what the reference parsed).
+void kref_use_parsed_index(void *h) { ((KrefCtx *)h)->idx = g_parsed_index; }
 
 }  // extern "C"

@@ -131,6 +131,28 @@ def ref():
         L.kref_fastq_get.restype = C.c_uint64
         L.kref_fastq_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.kref_fastq_close.argtypes = [C.c_void_p]
+        L.kref_set_read_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.kref_set_entry_meta.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_char_p]
+        L.kref_add_gene.argtypes = [C.c_void_p, C.c_uint64] + [C.c_char_p] * 5 + [C.c_uint32] * 3
+        L.kref_taxdb_open.restype = C.c_void_p
+        L.kref_taxdb_open.argtypes = [C.c_char_p]
+        L.kref_taxdb_close.argtypes = [C.c_void_p]
+        L.kref_taxdb_build.argtypes = [C.c_char_p] * 3
+        L.kref_taxdb_size.restype = C.c_uint64
+        L.kref_taxdb_size.argtypes = [C.c_void_p]
+        L.kref_lca.restype = C.c_uint32
+        L.kref_lca.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.kref_lineage.restype = C.c_uint64
+        L.kref_lineage.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64]
+        L.kref_meta_batch.restype = C.c_uint64
+        L.kref_meta_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                      C.c_void_p, C.c_uint64]
+        L.kref_meta_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_char_p]
+        L.kref_parse_index.restype = C.c_int64
+        L.kref_parse_index.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_uint64, C.c_char_p]
+        L.kref_parsed_index_dump.restype = C.c_uint64
+        L.kref_parsed_index_dump.argtypes = [C.c_void_p, C.c_uint64]
+        L.kref_use_parsed_index.argtypes = [C.c_void_p]
         cwd = os.getcwd()
         scratch = tempfile.mkdtemp(prefix="kref_")
         os.chdir(scratch)
@@ -364,3 +386,89 @@ def load_pkg():
     sys.path.insert(0, ROOT)
     import __graft_entry__ as ge
     return ge.load_pkg()
+
+
+# ---------------------------------------------------------------- reference: taxonomy, metagenomic outputs, database builders
+
+def ref_meta_batch(R, taxdb, quals=None, qual_offs=None, ids=None, id_offs=None, num_alignments=10, fraction=0.95, pseudo=True,
+                   sam_xa=False, paired=True, want_sam=True):
+    """SLAM.h:215-249 on a Ref context after screen_and_pair() (paired) or align_to_database() + kref_screen (single-end).
+    taxdb: handle from ref().kref_taxdb_open or None. Returns the SAM text (b"" when not wanted)."""
+    L = R.L
+    if quals is not None:
+        q = u8(quals); qo = np.ascontiguousarray(qual_offs, dtype=np.uint64)
+        L.kref_set_read_quals(R.h, _p(q), _p(qo))
+    if ids is not None:
+        i = u8(ids); io = np.ascontiguousarray(id_offs, dtype=np.uint64)
+        L.kref_set_read_ids(R.h, _p(i), _p(io))
+    tmp = tempfile.NamedTemporaryFile(suffix=".sam", delete=False); tmp.close()
+    buf = np.zeros(1 << 26, dtype=np.uint8)
+    n = L.kref_meta_batch(R.h, taxdb, num_alignments, fraction, int(pseudo), int(sam_xa), int(paired), int(want_sam), tmp.name.encode(),
+                          _p(buf), len(buf))
+    os.unlink(tmp.name)
+    assert n <= len(buf)
+    return bytes(buf[:n])
+
+
+def ref_meta_finish(R, taxdb, num_reads):
+    """SLAM.h:256-265 -> (text of _PerRead, XML, _abbreviated)."""
+    d = tempfile.mkdtemp(prefix="kref_meta_")
+    prefix = os.path.join(d, "out")
+    R.L.kref_meta_finish(R.h, taxdb, num_reads, prefix.encode())
+    res = []
+    for suffix in ("_PerRead", "", "_abbreviated"):
+        with open(prefix + suffix, "rb") as f:
+            res.append(f.read())
+        os.unlink(prefix + suffix)
+    os.rmdir(d)
+    return tuple(res)
+
+
+def ref_parse_index(kind, paths, taxdb_path=None):
+    """The reference's createIndexFromGBFF (kind 0; needs ./taxDB) or createIndexFromFASTA (kind 1) -> list of entries
+    (dicts like database.read_database's), decoded from the harness's dump of the GenbankIndex it built."""
+    L = ref()
+    cwd = os.getcwd()
+    d = tempfile.mkdtemp(prefix="kref_idx_")
+    try:
+        os.chdir(d)
+        if taxdb_path:
+            with open(taxdb_path, "rb") as f, open("taxDB", "wb") as g:
+                g.write(f.read())
+        arr = (C.c_char_p * len(paths))(*[os.fsencode(os.path.join(cwd, p) if not os.path.isabs(p) else p) for p in paths])
+        n = L.kref_parse_index(kind, arr, len(paths), b"database")
+    finally:
+        os.chdir(cwd)
+        for f in os.listdir(d):
+            os.unlink(os.path.join(d, f))
+        os.rmdir(d)
+    if n < 0:
+        return None
+    size = L.kref_parsed_index_dump(None, 0)
+    buf = np.zeros(max(1, size), dtype=np.uint8)
+    L.kref_parsed_index_dump(_p(buf), len(buf))
+    return decode_index_dump(bytes(buf[:size]))
+
+
+def decode_index_dump(text):
+    entries = []
+    for rec in text.split(b"\x1e"):
+        if not rec:
+            continue
+        f = rec.split(b"\x1f")
+        if f[0] == b"E":
+            entries.append(dict(locus_tag=f[1], taxonomy_id=int(f[2]), genbank_id=int(f[3]), is_plasmid=int(f[4]), is_16s=int(f[5]), bases=f[6], genes=[]))
+        else:
+            entries[-1]["genes"].append(dict(gene_name=f[1], locus_tag=f[2], protein_id=f[3], product=f[4], reference_sequence=f[5],
+                                             gene_id=int(f[6]), start=int(f[7]), stop=int(f[8]), complement=int(f[9])))
+    return entries
+
+
+def index_entries(ix):
+    """The same list-of-dicts view of a kslam_b200.Index."""
+    out = []
+    b = ix.bases.tobytes()
+    for e in range(ix.n_entries):
+        out.append(dict(locus_tag=ix.locus_tags[e], taxonomy_id=int(ix.taxonomy_ids[e]), bases=b[int(ix.offs[e]):int(ix.offs[e + 1])],
+                        genes=ix.gene_records(e)))
+    return out

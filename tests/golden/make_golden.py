@@ -73,8 +73,39 @@ def sam_fixture(name):
                         sam=np.frombuffer(text, np.uint8), max_insert=mi, header=np.frombuffer(hdr, np.uint8))
 
 
+def meta_fixture(name):
+    """Metagenomic run of the reference on a small GenBank database (its own createIndexFromGBFF, SLAM.h:209-265 with one
+    OpenMP thread): the GenBank text, the taxDB file, the batch's alignments and the four output texts."""
+    import pathlib
+    import tempfile
+    from test_taxon_host import make_db, make_reads
+    pkg = T.load_pkg()
+    tmp = pathlib.Path(tempfile.mkdtemp())
+    gb, go, _, _, _, _, taxdb, paths = make_db(pkg, tmp, n_strains=10, length=6000, files=1)
+    L = T.ref()
+    assert T.ref_parse_index(0, paths, taxdb) is not None
+    rt = L.kref_taxdb_open(taxdb.encode())
+    L.kref_set_threads(1)
+    rb, ro, quals, idb, ido = make_reads(pkg, gb, go, 200, seed=31)
+    R = T.Ref(gb, go, rb, ro, T.default_params(report_cigar=1))
+    L.kref_use_parsed_index(R.h)
+    R.align_to_database()
+    ov, pool, pairs = R.screen_and_pair()
+    sam = T.ref_meta_batch(R, rt, quals, ro, idb, ido)
+    per_read, xml, abbreviated = T.ref_meta_finish(R, rt, (len(ro) - 1) // 2)
+    R.close(); L.kref_taxdb_close(rt); L.kref_set_threads(os.cpu_count() or 1)
+    u = lambda b: np.frombuffer(b, np.uint8)   # noqa: E731
+    np.savez_compressed(os.path.join(HERE, name), gbff=u(open(paths[0], "rb").read()), taxdb=u(open(taxdb, "rb").read()), rb=rb, ro=ro,
+                        quals=quals, ids=idb, id_offs=ido, ov=ov, pool=pool, pairs=pairs, sam=u(sam), per_read=u(per_read), xml=u(xml),
+                        abbreviated=u(abbreviated))
+    print(name, "pairs", len(pairs), "sam", len(sam), "xml", len(xml), "taxa", xml.count(b"<taxon>"))
+
+
 def main():
     sys.path.insert(0, os.path.dirname(HERE))
+    if len(sys.argv) > 1 and sys.argv[1] == "meta":
+        return meta_fixture("meta_mini.npz")
+    meta_fixture("meta_mini.npz")
     fastq_fixture("fastq_reader.npz")
     sam_fixture("sam_config1_mini.npz")
     gb, go, rb, ro = synth.adversarial_set(seed=7, n_genomes=8, glen=6000, n_pairs=400)
