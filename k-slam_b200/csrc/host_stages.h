@@ -27,6 +27,14 @@ template <class F> void parallel_ranges(uint32_t threads, size_t n, F f) {
   for (auto &x : th) x.join();
 }
 
+// f(t) once on each of `threads` host threads
+template <class F> void parallel_threads(uint32_t threads, F f) {
+  if (threads <= 1) { f(0u); return; }
+  std::vector<std::thread> th;
+  for (uint32_t t = 0; t < threads; t++) th.emplace_back([=] { f(t); });
+  for (auto &x : th) x.join();
+}
+
 struct Ctx {
   const kslam_sam_params *prm; const kslam_sam_db *db; const kslam_read_batch *reads; const kslam_pairs *in;
   bool paired;                     // Globals.h pairedData

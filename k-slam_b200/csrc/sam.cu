@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "host_stages.h"
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <climits>
 #include <numeric>
@@ -29,11 +30,15 @@ using namespace kslam_host;
 
 namespace {
 
-std::vector<ReadPair> per_read(const kslam_pairs *in, uint32_t midpoint) {          // PairedOverlap.h:437-471
-  std::vector<ReadPair> out;
+// batches smaller than this take the single-threaded form of the stages below (KSLAM_HOST_PAR_MIN: test hook)
+size_t par_min() { const char *e = getenv("KSLAM_HOST_PAR_MIN"); return e ? (size_t)strtoull(e, nullptr, 10) : 65536; }
+
+// getPerReadOverlaps, PairedOverlap.h:437-471: consecutive records of one read pair become one ReadPair. The reference walks
+// the vector once; here every thread walks a range that starts and ends on a read boundary, the pieces are joined in order.
+void per_read_range(const kslam_pairs *in, uint32_t midpoint, uint64_t lo, uint64_t hi, std::vector<ReadPair> &out) {
   ReadPair cur;
   uint32_t readPos = 0;
-  for (uint64_t i = 0; i < in->n_pairs; i++) {
+  for (uint64_t i = lo; i < hi; i++) {
     const kslam_pair &k = in->pairs[i];
     POv p;
     p.combinedScore = k.combined_score; p.entry = k.entry; p.refStart = k.ref_start; p.refEnd = k.ref_end;
@@ -47,6 +52,28 @@ std::vector<ReadPair> per_read(const kslam_pairs *in, uint32_t midpoint) {      
     cur.r1Pos = thisReadPos; cur.r2Pos = thisReadPos + midpoint;
   }
   if (cur.pairs.size()) out.push_back(cur);
+}
+std::vector<ReadPair> per_read(const kslam_pairs *in, uint32_t midpoint, uint32_t threads) {
+  std::vector<ReadPair> out;
+  const uint64_t n = in->n_pairs;
+  if (threads <= 1 || n < par_min() || n < threads) { per_read_range(in, midpoint, 0, n, out); return out; }
+  auto read_of = [&](uint64_t i) {
+    const kslam_pair &k = in->pairs[i];
+    return k.r1_idx >= 0 ? in->sorted_overlaps[k.r1_idx].read : in->sorted_overlaps[k.r2_idx].read - midpoint;
+  };
+  std::vector<uint64_t> cut(threads + 1, n);
+  cut[0] = 0;
+  for (uint32_t t = 1; t < threads; t++) {
+    uint64_t b = std::max(cut[t - 1], n * t / threads);
+    while (b > 0 && b < n && read_of(b) == read_of(b - 1)) b++;      // move to the next read boundary
+    cut[t] = b;
+  }
+  std::vector<std::vector<ReadPair>> parts(threads);
+  parallel_threads(threads, [&](uint32_t t) { per_read_range(in, midpoint, cut[t], cut[t + 1], parts[t]); });
+  size_t total = 0;
+  for (auto &p : parts) total += p.size();
+  out.reserve(total);
+  for (auto &p : parts) for (auto &r : p) out.push_back(std::move(r));
   return out;
 }
 
@@ -56,7 +83,16 @@ uint32_t max_allowed_insert_size(const std::vector<ReadPair> &reads) {          
     for (auto &p : read.pairs)
       if (p.insertSize != 0) insertSizes.push_back(p.insertSize);
   if (insertSizes.size() == 0) return UINT32_MAX;
-  std::sort(insertSizes.begin(), insertSizes.end());
+  // std::sort in the reference; a sorted sequence of integers does not depend on the algorithm, so large batches of small
+  // values (the normal case: fragment lengths) take a counting sort
+  int32_t lo = insertSizes[0], hi = insertSizes[0];
+  for (int32_t v : insertSizes) { lo = std::min(lo, v); hi = std::max(hi, v); }
+  if (insertSizes.size() >= par_min() && lo >= 0 && hi < (1 << 22)) {
+    std::vector<uint32_t> count((size_t)hi + 1, 0);
+    for (int32_t v : insertSizes) count[v]++;
+    size_t at = 0;
+    for (int32_t v = lo; v <= hi; v++) { std::fill_n(insertSizes.begin() + at, count[v], v); at += count[v]; }
+  } else std::sort(insertSizes.begin(), insertSizes.end());
   int32_t limit = 0;
   for (int i = 0; i < 99; i++) {
     if ((insertSizes[floor(insertSizes.size() * (i + 1) / 100.0)] - insertSizes[floor(insertSizes.size() * (i) / 100.0)]) > 1000) {
@@ -118,21 +154,50 @@ void screen_by_score(std::vector<ReadPair> &reads, double fraction, uint32_t thr
   });
 }
 
-void pseudo_assembly(std::vector<ReadPair> &pairedAlignments, uint32_t threads) {     // PairedOverlap.h:480-576
+void pseudo_assembly(std::vector<ReadPair> &pairedAlignments, uint32_t threads, uint64_t n_entries) {     // PairedOverlap.h:480-576
   struct coverage { int start = 0; int stop = 0; };
   struct entryAndOverlaps { uint32_t entryPos = 0; std::vector<std::pair<coverage, POv *>> reads; };
+  // The reference appends every record to its entry's list while walking the reads in order (an unordered_map keyed by
+  // entry). The same lists, in the same order, are built here by all threads: count per (thread range, entry), prefix,
+  // fill. Chains never cross entries, so the map's iteration order does not matter.
+  std::vector<entryAndOverlaps> lists;
+  std::vector<entryAndOverlaps *> entries;
   std::unordered_map<uint32_t, entryAndOverlaps> entriesAndOverlaps;
-  for (auto &read : pairedAlignments)
-    for (auto &overlap : read.pairs) {
-      coverage c; c.start = overlap.refStart; c.stop = overlap.refEnd;
-      auto &e = entriesAndOverlaps[overlap.entry];
-      e.entryPos = overlap.entry;
-      e.reads.push_back({c, &overlap});
+  const size_t n_reads = pairedAlignments.size();
+  if (threads > 1 && n_reads >= par_min() && n_entries * threads <= (16u << 20)) {
+    std::vector<std::vector<uint32_t>> cnt(threads, std::vector<uint32_t>(n_entries, 0));
+    parallel_threads(threads, [&](uint32_t t) {
+      for (size_t r = n_reads * t / threads; r < n_reads * (t + 1) / threads; r++)
+        for (auto &overlap : pairedAlignments[r].pairs) cnt[t][overlap.entry]++;
+    });
+    lists.resize(n_entries);
+    for (uint64_t e = 0; e < n_entries; e++) {
+      uint32_t total = 0;
+      for (uint32_t t = 0; t < threads; t++) { const uint32_t c = cnt[t][e]; cnt[t][e] = total; total += c; }
+      lists[e].entryPos = (uint32_t)e;
+      lists[e].reads.resize(total);
     }
-  std::vector<entryAndOverlaps *> entries;            // chains never cross entries: one entry per task
-  for (auto &entry : entriesAndOverlaps) entries.push_back(&entry.second);
-  parallel_ranges(threads, entries.size(), [&](uint32_t, size_t elo, size_t ehi) {
-  for (size_t ei = elo; ei < ehi; ei++) {
+    parallel_threads(threads, [&](uint32_t t) {
+      for (size_t r = n_reads * t / threads; r < n_reads * (t + 1) / threads; r++)
+        for (auto &overlap : pairedAlignments[r].pairs) {
+          coverage c; c.start = overlap.refStart; c.stop = overlap.refEnd;
+          lists[overlap.entry].reads[cnt[t][overlap.entry]++] = {c, &overlap};
+        }
+    });
+    for (auto &l : lists) if (l.reads.size()) entries.push_back(&l);
+  } else {
+    for (auto &read : pairedAlignments)
+      for (auto &overlap : read.pairs) {
+        coverage c; c.start = overlap.refStart; c.stop = overlap.refEnd;
+        auto &e = entriesAndOverlaps[overlap.entry];
+        e.entryPos = overlap.entry;
+        e.reads.push_back({c, &overlap});
+      }
+    for (auto &entry : entriesAndOverlaps) entries.push_back(&entry.second);
+  }
+  std::atomic<size_t> next{0};                            // entries differ a lot in size: hand them out one at a time
+  parallel_threads(entries.size() < 2 ? 1u : threads, [&](uint32_t) {
+  for (size_t ei = next++; ei < entries.size(); ei = next++) {
     struct { entryAndOverlaps &second; } entry{*entries[ei]};
     std::sort(entry.second.reads.begin(), entry.second.reads.end(),
               [](const std::pair<coverage, POv *> &i, const std::pair<coverage, POv *> &j) { return i.first.start < j.first.start; });
@@ -460,7 +525,7 @@ static int sam_finish(Ctx &c, std::vector<ReadPair> &rp, bool insert_screen, boo
   } else if (max_insert_size) *max_insert_size = UINT32_MAX;
   double t2 = now();
   screen_by_score(rp, prm->score_fraction_threshold, threads);
-  if (prm->pseudo_assembly) { pseudo_assembly(rp, threads); screen_by_score(rp, prm->score_fraction_threshold, threads); }
+  if (prm->pseudo_assembly) { pseudo_assembly(rp, threads, c.db->n_entries); screen_by_score(rp, prm->score_fraction_threshold, threads); }
   double t3 = now();
   int rc = KSLAM_OK;
   if (want_sam) {
@@ -473,9 +538,7 @@ static int sam_finish(Ctx &c, std::vector<ReadPair> &rp, bool insert_screen, boo
     for (uint32_t t = 0; t < threads; t++) { at[t] = total; total += parts[t].size(); }
     char *buf = (char *)malloc(total + 1);                      // the threads' pieces go straight into the result buffer
     if (buf) {
-      parallel_ranges(threads, threads, [&](uint32_t, size_t lo, size_t hi) {
-        for (size_t t = lo; t < hi; t++) memcpy(buf + at[t], parts[t].data(), parts[t].size());
-      });
+      parallel_threads(threads, [&](uint32_t t) { memcpy(buf + at[t], parts[t].data(), parts[t].size()); });
       buf[total] = 0;
     }
     *text = buf;
@@ -521,7 +584,8 @@ int kslam_batch_outputs(const kslam_sam_params *prm, const kslam_sam_db *db, con
   }
   try {
     Ctx c{prm, db, reads, pairs, true};
-    auto rp = per_read(pairs, (uint32_t)(reads->n_reads / 2));
+    uint32_t threads = prm->threads ? prm->threads : std::max(1u, std::thread::hardware_concurrency());
+    auto rp = per_read(pairs, (uint32_t)(reads->n_reads / 2), std::min(threads, 64u));
     return sam_finish(c, rp, true, want_sam != 0, text, len, max_insert_size, taxdb, taxa);
   } catch (const std::exception &) { return KSLAM_ERR_NOMEM; }
 }

@@ -54,6 +54,20 @@ def test_sam_text_equals_reference(pkg, kind, seed, cigar):
         assert w.header("SLAM --db x") == want_hdr
 
 
+@pytest.mark.skipif(not T.have_ref(), reason="needs oracle/_ref")
+@pytest.mark.parametrize("kind,seed,threads", [("related", 81, 5), ("config1", 82, 3), ("adversarial", 83, 8)])
+def test_sam_parallel_host_stages_equal_reference(pkg, kind, seed, threads, monkeypatch):
+    """Large batches group the reads, sort the insert sizes and build the pseudo-assembly lists on all host threads
+    (ranges cut at read boundaries, counting sort, count / prefix / fill); forced on here for a small batch."""
+    monkeypatch.setenv("KSLAM_HOST_PAR_MIN", "1")
+    gb, go, rb, ro, quals, idb, ido = make_inputs(pkg, seed, n_pairs=700, kind=kind)
+    tags = [f"g{i}" for i in range(len(go) - 1)]
+    ov, pool, pairs, want, want_mi, _ = reference_side(gb, go, rb, ro, quals, 1)
+    w = pkg.SamWriter(gb, go, tags, report_cigar=True, threads=threads)
+    got, mi = w.batch(rb, ro, quals, ro, idb, ido, ov, pool, pairs)
+    assert mi == want_mi and got == want and len(want) > 10_000
+
+
 def test_sam_golden(pkg, golden):
     """Inputs and the reference's SAM text from tests/golden/make_golden.py: travels to boxes without /root/reference."""
     g = golden("sam_config1_mini.npz")
