@@ -255,6 +255,84 @@ def run_fastq_to_sam(args, pkg):
           "stage_busy_s": st["seconds"], "sam_bytes": st["sam_bytes"], "batches": st["batches"]})
 
 
+def run_cli(args, pkg, meta):
+    """--workload cli / cli-meta: the `SLAM` executable (k-slam_b200/csrc/slam_main.cpp, C++ host over the C ABI) as a user
+    runs it, wall clock of the whole process: database load, index build, FASTQ ingest, GPU matching path, host stages, output.
+    cli      = config-1 data, FASTA database (built with SLAM --parse-fasta), --just-align --sam-file   (configs 1 / 5)
+    cli-meta = config-2 data scaled down (strains in a phylogeny as GenBank flat files with genes + names.dmp / nodes.dmp,
+               built with SLAM --parse-genbank / --parse-taxonomy), SAM + LCA XML + _PerRead + _abbreviated   (config 2)."""
+    import shutil
+    import tempfile
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the matching path has no CPU fallback")
+    exe = os.path.join(ROOT, "k-slam_b200", "SLAM")
+    pairs = args.pairs or (2_000_000 if meta else 4_000_000)
+    at_once = 1_000_000
+    d = tempfile.mkdtemp(prefix="kslam_cli_")
+    db = os.path.join(d, "db"); os.mkdir(db)
+    t_build = time.perf_counter()
+    if meta:
+        n_strains, length = 100, 1_000_000
+        gb, go = pkg.synth.tree_genomes(n_strains, length, seed=1)
+        nodes, strain_tax = pkg.synth.tree_taxonomy(n_strains)
+        pkg.synth.write_taxonomy_dumps(nodes, os.path.join(d, "names.dmp"), os.path.join(d, "nodes.dmp"))
+        gbff = os.path.join(d, "all.gbff")
+        with open(gbff, "wb") as f:
+            for i in range(n_strains):
+                f.write(pkg.synth.genbank_text(gb[int(go[i]):int(go[i + 1])].tobytes(), f"NC_{i:06d}", 7_000_000 + i, int(strain_tax[i]),
+                                               f"Synthetic strain {i}", i, i % (n_strains // 5), seed=i % (n_strains // 5)))
+        subprocess.run([exe, "--parse-genbank", "--output-file", os.path.join(db, "database"), gbff], check=True, cwd=d)
+        subprocess.run([exe, "--parse-taxonomy", "--output-file", os.path.join(db, "taxDB"), os.path.join(d, "names.dmp"), os.path.join(d, "nodes.dmp")],
+                       check=True, cwd=d)
+        what = f"{n_strains} strains x {length} bp in a phylogeny (GenBank flat files, ~1 gene / kb)"
+    else:
+        gb, go = pkg.synth.random_genomes(50, 3_000_000, seed=1)
+        fa = os.path.join(d, "db.fa")
+        with open(fa, "wb") as f:
+            for i in range(len(go) - 1):
+                f.write(b">g%02d synthetic\n" % i + gb[int(go[i]):int(go[i + 1])].tobytes() + b"\n")
+        subprocess.run([exe, "--parse-fasta", "--output-file", os.path.join(db, "database"), fa], check=True, cwd=d)
+        what = "50 x 3 Mbp genomes (FASTA)"
+    t_build = time.perf_counter() - t_build
+    rb, ro, _ = pkg.synth.paired_reads(gb, go, pairs, seed=2)
+    paths = []
+    for k in range(2):
+        rows = rb.reshape(-1, 150)[k * pairs:(k + 1) * pairs]
+        p = os.path.join(d, f"R{k + 1}.fq"); paths.append(p)
+        with open(p, "wb") as f:
+            for lo in range(0, pairs, 100_000):
+                blk = rows[lo:lo + 100_000]
+                f.write(b"".join(b"@r%d/%d\n" % (lo + i, k + 1) + blk[i].tobytes() + b"\n+\n" + b"I" * 150 + b"\n" for i in range(len(blk))))
+    in_bytes = sum(os.path.getsize(p) for p in paths)
+    cmd = [exe, "--db", db, "--sam-file", os.path.join(d, "out.sam"), "--num-reads-at-once", str(at_once)]
+    cmd += ["--output-file", os.path.join(d, "out.xml")] if meta else ["--just-align"]
+    cmd += paths
+    runs = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = subprocess.run(cmd, cwd=d, capture_output=True)
+        dt = time.perf_counter() - t0
+        if r.returncode != 0:
+            raise SystemExit(f"SLAM failed ({r.returncode}): {r.stderr.decode()[-500:]}")
+        stages = open(os.path.join(d, "log.txt")).read().strip().splitlines()
+        log(f"[bench/cli] run {i}: {pairs} pairs in {dt:.2f}s; last log line: {stages[-1] if stages else ''}")
+        if i >= args.warmup:
+            runs.append(dt)
+    dt = float(np.mean(runs))
+    out_bytes = {n: os.path.getsize(os.path.join(d, n)) for n in os.listdir(d) if n.startswith("out.")}
+    shutil.rmtree(d, ignore_errors=True)
+    emit({"metric": METRIC, "value": pairs / dt * 60 / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+          "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16x2 (SW) / u64 (k-mers) / f64 (MAPQ)",
+          "data": "synthetic",
+          "config": {"workload": f"SLAM executable, whole process: {pairs} x 150bp FR pairs (FASTQ text, {in_bytes / 1e9:.2f} GB) vs {what}, "
+                                 f"--num-reads-at-once {at_once}, pseudo-assembly on, 10 alignments per read, "
+                                 + ("SAM + LCA XML + _PerRead + _abbreviated" if meta else "--just-align SAM"),
+                     "includes": "process start, CUDA context, DIR/database parse, index build, FASTQ ingest, GPU matching path, host stages, output files",
+                     "command": " ".join(os.path.basename(c) if os.sep in c else c for c in cmd)},
+          "output_bytes": out_bytes, "database_build_s": t_build})
+
+
 def run_reference_arm(args, pkg):
     """--impl reference: the reference's CPU path on this box's host cores, same config/metric/unit."""
     rank = int(os.environ.get("RANK", "0"))
@@ -291,7 +369,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kslam", choices=["kslam", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("KSLAM_BENCH_WORKLOAD", "config2"), choices=["config1", "config2", "config3", "config4", "sam"])
+    ap.add_argument("--workload", default=os.environ.get("KSLAM_BENCH_WORKLOAD", "config2"), choices=["config1", "config2", "config3", "config4", "sam", "cli", "cli-meta"])
     ap.add_argument("--pairs", type=int, default=0, help="read pairs per batch per GPU (default: the config's)")
     ap.add_argument("--ref-sample", type=int, default=0, help="pairs per step for the CPU reference arm (0 = per workload)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="pairs for the cpu_baseline leg (rank 0, N=1; 0 = per workload)")
@@ -303,6 +381,8 @@ def main():
         return run_config3(args, pkg)
     if args.workload == "sam":
         return run_fastq_to_sam(args, pkg)
+    if args.workload in ("cli", "cli-meta"):
+        return run_cli(args, pkg, args.workload == "cli-meta")
     if args.impl == "reference":
         return run_reference_arm(args, pkg)
 
