@@ -4,7 +4,7 @@
 // sorts (/root/reference/src/Overlap.h:289, /root/reference/src/PairedOverlap.h:248-257). Design
 // ("onesweep"): ONE histogram launch counts every 8-bit digit of every pass in shared memory; then each
 // pass is ONE launch in which a CTA ranks a 4096-record tile with warp-wide digit matching
-// (__match_any_sync + popc ballots, per-warp shared-memory histograms), learns its global digit offsets
+// (eight ballots per digit + popc, per-warp shared-memory histograms), learns its global digit offsets
 // by decoupled look-back over the previous tiles' published counts, stages the tile in shared memory in
 // digit order and writes it out in contiguous runs. Per pass every record is read once and written once
 // (32 B); passes whose digit is constant over the whole input are skipped. Stable, so LSD order holds.
@@ -65,9 +65,56 @@ k_rs_scan_hist(unsigned long long *__restrict__ ghist, uint32_t n_passes, uint64
   }
 }
 
+// lanes of the warp holding the same 8-bit digit. MATCH.ANY walks the distinct values of the warp one by one (32 of them
+// for random digits: the ADU pipe was the limiter of those passes, profiles/r1k); eight ballots cost the same for any
+// distribution.
+template <bool BALLOT> __device__ __forceinline__ uint32_t digit_peers(uint32_t d) {
+  if (!BALLOT) return __match_any_sync(0xffffffffu, d);
+  uint32_t peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 8; b++) {
+    const bool bit = (d >> b) & 1u;
+    const uint32_t v = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? v : ~v;
+  }
+  return peers;
+}
+
+// Decoupled look-back for digit `tid` of tile `tile`: publish this tile's count, sum the predecessors' published counts
+// back to the nearest one that already carries an inclusive prefix, publish the inclusive prefix, return the exclusive one.
+// The states of RS_LB predecessors are fetched together (independent loads in flight) and consumed in order; an
+// unpublished one restarts the batch at that tile.
+__device__ __forceinline__ unsigned long long publish_and_look_back(volatile unsigned long long *tile_state, uint64_t tile, uint32_t tid,
+                                                                    uint32_t real_d) {
+  volatile unsigned long long *my_state = tile_state + tile * 256 + tid;
+  if (tile == 0) { *my_state = RS_FLAG_INCL | real_d; return 0; }
+  *my_state = RS_FLAG_AGG | real_d;
+  unsigned long long excl = 0;
+  constexpr int RS_LB = 8;
+  int64_t t = (int64_t)tile - 1;
+  bool done = false;
+  while (!done) {
+    unsigned long long s[RS_LB];
+#pragma unroll
+    for (int k = 0; k < RS_LB; k++)
+      s[k] = (t - k >= 0) ? tile_state[(uint64_t)(t - k) * 256 + tid] : RS_FLAG_INCL;   // before tile 0: prefix 0
+    int used = 0;
+#pragma unroll
+    for (int k = 0; k < RS_LB; k++) {
+      if (!done && used == k) {
+        const unsigned long long f = s[k] >> 62;
+        if (f != 0) { excl += s[k] & RS_VAL_MASK; used = k + 1; if (f == 2) done = true; }
+      }
+    }
+    t -= used;
+  }
+  *my_state = RS_FLAG_INCL | (excl + real_d);
+  return excl;
+}
+
 // ---- one LSD pass ------------------------------------------------------------------------------
-template <int RS_THREADS, int RS_IPT>
-__global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_IPT > 4096 ? 1 : 2))
+template <int RS_THREADS, int RS_IPT, bool BALLOT>
+__global__ void __launch_bounds__(RS_THREADS, (RS_THREADS * RS_IPT > 4096 ? 1 : (RS_THREADS * RS_IPT > 3072 ? 2 : (RS_THREADS * RS_IPT > 2048 ? 3 : 4))))
 k_rs_onesweep(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n, uint32_t shift, uint32_t mask,
               uint32_t word,                                       // 0: sort by .key, 1: sort by .val
               const unsigned long long *__restrict__ digit_base,  // [256] exclusive global offsets
@@ -105,14 +152,14 @@ k_rs_onesweep(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n,
     } else { key[i] = ~0ull; val[i] = 0; }   // padding sorts to the very end of the tile
   }
 
-  // 2. per-warp digit ranks: peers with my digit via match_any, rank = earlier peers + warp running count
+  // 2. per-warp digit ranks: peers with my digit (digit_peers), rank = earlier peers + warp running count
   uint32_t *myhist = whist + warp * 256;
   const uint32_t lt_mask = (1u << lane) - 1;
 #pragma unroll
   for (int i = 0; i < RS_IPT; i++) {
     const uint32_t idx = wbase + i * 32 + lane;
     const uint32_t d = idx < count ? ((uint32_t)((word ? val[i] : key[i]) >> shift) & mask) : 255u;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t peers = digit_peers<BALLOT>(d);
     const uint32_t old = myhist[d];              // every peer reads the warp's running count (broadcast)
     __syncwarp();
     if ((peers & lt_mask) == 0) myhist[d] = old + __popc(peers);   // lowest peer publishes the new count
@@ -131,34 +178,7 @@ k_rs_onesweep(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n,
     if (tid == 255) real_d -= (RS_TILE - count);   // padding records were counted in digit 255
 
     // 4. publish, then look back for the exclusive prefix over earlier tiles
-    volatile unsigned long long *my_state = tile_state + tile * 256 + tid;
-    if (tile == 0) *my_state = RS_FLAG_INCL | real_d; else *my_state = RS_FLAG_AGG | real_d;
-    unsigned long long excl = 0;
-    if (tile > 0) {
-      // walk back over the predecessors' published counts until one with an inclusive prefix is met. The
-      // states of RS_LB predecessors are fetched together (independent loads in flight) and consumed in order;
-      // an unpublished one restarts the batch at that tile.
-      constexpr int RS_LB = 8;
-      int64_t t = (int64_t)tile - 1;
-      bool done = false;
-      while (!done) {
-        unsigned long long s[RS_LB];
-#pragma unroll
-        for (int k = 0; k < RS_LB; k++)
-          s[k] = (t - k >= 0) ? tile_state[(uint64_t)(t - k) * 256 + tid] : RS_FLAG_INCL;   // before tile 0: prefix 0
-        int used = 0;
-#pragma unroll
-        for (int k = 0; k < RS_LB; k++) {
-          if (!done && used == k) {
-            const unsigned long long f = s[k] >> 62;
-            if (f != 0) { excl += s[k] & RS_VAL_MASK; used = k + 1; if (f == 2) done = true; }
-          }
-        }
-        t -= used;
-      }
-      *my_state = RS_FLAG_INCL | (excl + real_d);
-    }
-    s_gbase[tid] = digit_base[tid] + excl;
+    s_gbase[tid] = digit_base[tid] + publish_and_look_back(tile_state, tile, tid, real_d);
   }
 
   // 5. tile-local exclusive scan over digits (counts include padding so positions cover the tile)
@@ -198,17 +218,17 @@ k_rs_onesweep(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n,
   }
 }
 
-template <int T, int I>
+template <int T, int I, bool B>
 static void launch_onesweep(kslam_ctx *c, const Rec16 *in, Rec16 *out, uint64_t n, uint32_t shift, uint32_t mask,
                             uint32_t word, const unsigned long long *base, unsigned long long *state, uint32_t *ticket) {
   constexpr size_t smem = (size_t)T * I * sizeof(Rec16) + (T / 32) * 256 * sizeof(uint32_t);
   const uint64_t tiles = (n + (uint64_t)T * I - 1) / ((uint64_t)T * I);
-  static bool attr_set[64] = {false};
+  static bool attr_set[64] = {false};   // per instantiation
   if (!(c->device < 64 && attr_set[c->device])) {
-    CUDA_TRY(cudaFuncSetAttribute(k_rs_onesweep<T, I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_rs_onesweep<T, I, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (c->device < 64) attr_set[c->device] = true;
   }
-  k_rs_onesweep<T, I><<<(unsigned)tiles, T, smem, c->stream>>>(in, out, n, shift, mask, word, base, state, ticket);
+  k_rs_onesweep<T, I, B><<<(unsigned)tiles, T, smem, c->stream>>>(in, out, n, shift, mask, word, base, state, ticket);
 }
 
 Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, uint32_t lo_bit, uint32_t hi_bit,
@@ -226,7 +246,7 @@ Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, u
     uint32_t bits = hi_bit - s < 8 ? hi_bit - s : 8;
     plan.shift[plan.n_passes] = s; plan.mask[plan.n_passes] = (1u << bits) - 1; plan.n_passes++;
   }
-  const uint64_t tile_recs = cfg == 2 ? 8192 : 4096;
+  const uint64_t tile_recs = cfg == 2 ? 8192 : (cfg == 5 ? 2048 : 4096);
   const uint64_t tiles = (n + tile_recs - 1) / tile_recs;
   // layout of sort_hist: [8*256 u64 hist][8 u32 trivial][8 u32 tickets][pad][tiles*256 u64 state]
   const size_t hist_bytes = RS_MAX_PASSES * 256 * 8, misc_bytes = 128;
@@ -251,9 +271,16 @@ Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, u
   for (uint32_t p = 0; p < plan.n_passes; p++) {
     if (h_trivial[p]) continue;   // every record has the same digit: the pass would be the identity
     CUDA_TRY(cudaMemsetAsync(state, 0, tiles * 256 * 8, st));
-    if (cfg == 1) launch_onesweep<512, 8>(c, cur, alt, n, plan.shift[p], plan.mask[p], word, ghist + p * 256, state, tickets + p);
-    else if (cfg == 2) launch_onesweep<512, 16>(c, cur, alt, n, plan.shift[p], plan.mask[p], word, ghist + p * 256, state, tickets + p);
-    else launch_onesweep<256, 16>(c, cur, alt, n, plan.shift[p], plan.mask[p], word, ghist + p * 256, state, tickets + p);
+#define RS_LAUNCH(T, I, B) launch_onesweep<T, I, B>(c, cur, alt, n, plan.shift[p], plan.mask[p], word, ghist + p * 256, state, tickets + p)
+    // KSLAM_RS_CFG picks an instance for experiments; measured on 32 M random records, 8 passes (gpurun, round 1):
+    //   0 ballots 256x16 3.05 ms (default) | 4 MATCH.ANY 256x16 3.46 | 1 ballots 512x8 3.16 | 5 ballots 256x8 (4 CTAs/SM) 3.55 |
+    //   2 MATCH.ANY 512x16 (one CTA/SM). 256x12 at 3 CTAs/SM (3.25) and look-back before the ranking (3.04) were tried and dropped.
+    if (cfg == 1) RS_LAUNCH(512, 8, true);
+    else if (cfg == 2) RS_LAUNCH(512, 16, false);
+    else if (cfg == 4) RS_LAUNCH(256, 16, false);
+    else if (cfg == 5) RS_LAUNCH(256, 8, true);
+    else RS_LAUNCH(256, 16, true);
+#undef RS_LAUNCH
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     Rec16 *t = cur; cur = alt; alt = t;

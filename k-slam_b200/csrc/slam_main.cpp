@@ -13,6 +13,7 @@
 // CPU fallback: without an sm_100 GPU the alignment modes stop with the library's error; the --parse-* modes are host-only.
 // Option names may be abbreviated to an unambiguous prefix, as boost::program_options allows.
 #include "../../include/kslam.h"
+#include <algorithm>
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -47,7 +48,7 @@ struct Options {                                           // main.cpp:36-82, de
   double scoreFractionThreshold = 0.95;
   bool help = false, version = false, samXA = false, justAlign = false, noPseudoAssembly = false;
   bool parseGenbank = false, parseFasta = false, parseTaxonomy = false;
-  int device = 0;                                          // extension: --device N (CUDA ordinal)
+  std::vector<int> devices{0};                             // extension: --device N / --devices N,M,... (CUDA ordinals, one context each)
   std::vector<std::string> inputs;
 };
 
@@ -56,7 +57,7 @@ const OptSpec kSpecs[] = {
     {"help", 0}, {"db", 1}, {"min-alignment-score", 1}, {"score-fraction-threshold", 1}, {"match-score", 1}, {"mismatch-penalty", 1},
     {"gap-open", 1}, {"gap-extend", 1}, {"num-reads", 1}, {"num-reads-at-once", 1}, {"output-file", 1}, {"sam-file", 1},
     {"num-alignments", 1}, {"sam-xa", 0}, {"version", 0}, {"just-align", 0}, {"no-pseudo-assembly", 0}, {"server", 0},
-    {"input-file", 1}, {"parse-genbank", 0}, {"parse-fasta", 0}, {"parse-taxonomy", 0}, {"alignment-only", 0}, {"device", 1}};
+    {"input-file", 1}, {"parse-genbank", 0}, {"parse-fasta", 0}, {"parse-taxonomy", 0}, {"alignment-only", 0}, {"device", 1}, {"devices", 1}};
 
 uint32_t to_u32(const std::string &name, const std::string &v) {
   size_t used = 0;
@@ -118,7 +119,15 @@ Options parse_options(int argc, char **argv) {
     else if (name == "parse-genbank") o.parseGenbank = true;
     else if (name == "parse-fasta") o.parseFasta = true;
     else if (name == "parse-taxonomy") o.parseTaxonomy = true;
-    else if (name == "device") o.device = (int)to_u32(name, value);
+    else if (name == "device") o.devices.assign(1, (int)to_u32(name, value));
+    else if (name == "devices") {
+      o.devices.clear();
+      for (size_t at = 0; at <= value.size();) {
+        const size_t comma = std::min(value.find(',', at), value.size());
+        o.devices.push_back((int)to_u32(name, value.substr(at, comma - at)));
+        at = comma + 1;
+      }
+    }
     // --server and --alignment-only are accepted and ignored, as in the reference (main.cpp never reads them)
   }
   return o;
@@ -147,7 +156,9 @@ void usage() {                                             // main.cpp:96-107
                "  --version                             print version number\n"
                "  --just-align                          only perform alignments, not metagenomics\n"
                "  --no-pseudo-assembly                  do not link alignments together\n"
-               "  --device arg (=0)                     CUDA device ordinal (this implementation)\n\n";
+               "  --device arg (=0)                     CUDA device ordinal (this implementation)\n"
+               "  --devices arg                         comma-separated CUDA ordinals: every batch is split into that many contiguous\n"
+               "                                        ranges of read pairs, one context per entry (this implementation)\n\n";
 }
 
 // bounded hand-over between two pipeline stages
@@ -168,6 +179,82 @@ bool write_file(const std::string &path, const char *text, uint64_t len) {
   if (!f) return false;
   const bool ok = fwrite(text, 1, len, f) == len;
   return fclose(f) == 0 && ok;
+}
+
+// Stage 2 for one batch. One context: the library call as is. Several: the batch is cut into contiguous ranges of read
+// pairs that keep mates together (R1 i and R2 i + mid), every context runs the whole path on its range, and the results are
+// joined in range order with read / overlap / cigar indices rebased — which is the order one context would have produced
+// (same rules as k-slam_b200/shard.py: pairing is per pair, seeds are per (read, genome)).
+void align_batch(const std::vector<kslam_ctx *> &ctxs, bool isPaired, Batch *b) {
+  const kslam_read_batch &r = b->reads;
+  const size_t G = ctxs.size();
+  if (G == 1) {
+    if (isPaired) {
+      kslam_pairs p;
+      if (kslam_align_pair_batch(ctxs[0], r.n_reads, r.bases, r.offs, &p) != KSLAM_OK) { b->error = kslam_last_error(ctxs[0]); return; }
+      b->overlaps.assign(p.sorted_overlaps, p.sorted_overlaps + p.n_sorted);
+      b->cigars.assign(p.cigar_pool, p.cigar_pool + p.n_cigar_words);
+      b->pairs.assign(p.pairs, p.pairs + p.n_pairs);
+    } else {
+      kslam_alignments a;
+      if (kslam_align_batch(ctxs[0], r.n_reads, r.bases, r.offs, &a) != KSLAM_OK) { b->error = kslam_last_error(ctxs[0]); return; }
+      b->overlaps.assign(a.overlaps, a.overlaps + a.n_overlaps);
+      b->cigars.assign(a.cigar_pool, a.cigar_pool + a.n_cigar_words);
+    }
+    return;
+  }
+  struct Shard { uint64_t lo = 0, hi = 0; std::vector<char> bases; std::vector<uint64_t> offs; kslam_pairs p{}; kslam_alignments a{}; std::string error; };
+  std::vector<Shard> shards(G);
+  const uint64_t units = isPaired ? r.n_reads / 2 : r.n_reads, mid = r.n_reads / 2;
+  std::vector<std::thread> th;
+  for (size_t g = 0; g < G; g++) {
+    Shard &s = shards[g];
+    s.lo = units * g / G; s.hi = units * (g + 1) / G;
+    if (s.hi == s.lo) continue;
+    th.emplace_back([&, g] {
+      Shard &s = shards[g];
+      const uint64_t cnt = s.hi - s.lo;
+      if (isPaired) {                                      // R1 block of the range, then its R2 block, in one array
+        const uint64_t a0 = r.offs[s.lo], a1 = r.offs[s.hi], b0 = r.offs[mid + s.lo], b1 = r.offs[mid + s.hi];
+        s.bases.resize((a1 - a0) + (b1 - b0));
+        memcpy(s.bases.data(), r.bases + a0, a1 - a0);
+        memcpy(s.bases.data() + (a1 - a0), r.bases + b0, b1 - b0);
+        s.offs.resize(2 * cnt + 1);
+        for (uint64_t i = 0; i <= cnt; i++) s.offs[i] = r.offs[s.lo + i] - a0;
+        for (uint64_t i = 1; i <= cnt; i++) s.offs[cnt + i] = (a1 - a0) + (r.offs[mid + s.lo + i] - b0);
+        if (kslam_align_pair_batch(ctxs[g], 2 * cnt, s.bases.data(), s.offs.data(), &s.p) != KSLAM_OK) s.error = kslam_last_error(ctxs[g]);
+      } else {                                             // a contiguous slice of the batch: only the offsets are rebased
+        s.offs.resize(cnt + 1);
+        for (uint64_t i = 0; i <= cnt; i++) s.offs[i] = r.offs[s.lo + i] - r.offs[s.lo];
+        if (kslam_align_batch(ctxs[g], cnt, r.bases + r.offs[s.lo], s.offs.data(), &s.a) != KSLAM_OK) s.error = kslam_last_error(ctxs[g]);
+      }
+    });
+  }
+  for (auto &t : th) t.join();
+  for (Shard &s : shards) if (!s.error.empty()) { b->error = s.error; return; }
+  for (Shard &s : shards) {
+    if (s.hi == s.lo) continue;
+    const uint64_t cnt = s.hi - s.lo, ov_base = b->overlaps.size(), cg_base = b->cigars.size();
+    const kslam_overlap *ov = isPaired ? s.p.sorted_overlaps : s.a.overlaps;
+    const uint64_t n_ov = isPaired ? s.p.n_sorted : s.a.n_overlaps;
+    const uint32_t *cg = isPaired ? s.p.cigar_pool : s.a.cigar_pool;
+    const uint64_t n_cg = isPaired ? s.p.n_cigar_words : s.a.n_cigar_words;
+    b->overlaps.insert(b->overlaps.end(), ov, ov + n_ov);
+    for (uint64_t i = ov_base; i < b->overlaps.size(); i++) {
+      kslam_overlap &o = b->overlaps[i];
+      o.read = isPaired ? (uint32_t)(o.read < cnt ? s.lo + o.read : mid + s.lo + (o.read - cnt)) : (uint32_t)(o.read + s.lo);
+      if (o.cigar_len) o.cigar_off += (uint32_t)cg_base;
+    }
+    if (n_cg) b->cigars.insert(b->cigars.end(), cg, cg + n_cg);
+    if (isPaired) {
+      const uint64_t pr_base = b->pairs.size();
+      b->pairs.insert(b->pairs.end(), s.p.pairs, s.p.pairs + s.p.n_pairs);
+      for (uint64_t i = pr_base; i < b->pairs.size(); i++) {
+        if (b->pairs[i].r1_idx >= 0) b->pairs[i].r1_idx += (int32_t)ov_base;
+        if (b->pairs[i].r2_idx >= 0) b->pairs[i].r2_idx += (int32_t)ov_base;
+      }
+    }
+  }
 }
 
 int run_alignment(const Options &o, const std::string &commandLine) {      // metagenomicAnalysis_Low_Mem, SLAM.h:159-268
@@ -191,13 +278,24 @@ int run_alignment(const Options &o, const std::string &commandLine) {      // me
   kslam_params prm;
   memset(&prm, 0, sizeof prm);
   prm.match = (uint8_t)o.match; prm.mismatch = (uint8_t)o.misMatch; prm.gap_open = (uint8_t)o.gapOpen; prm.gap_extend = (uint8_t)o.gapExtend;   // ssw_cpp.cpp:114-117
-  prm.score_threshold = (uint16_t)o.scoreThreshold; prm.report_cigar = wantSam ? 1 : 0; prm.device = o.device;
+  prm.score_threshold = (uint16_t)o.scoreThreshold; prm.report_cigar = wantSam ? 1 : 0; prm.device = o.devices[0];
   if (!kslam_params_exact(&prm))
     std::cerr << "SLAM: warning: scoring parameters outside the domain in which results are proven identical to SSW's (need gap-extend < gap-open and mismatch <= 2 * gap-extend)\n";
-  kslam_ctx *ctx = nullptr;
-  if (kslam_create(&prm, &ctx) != KSLAM_OK) { std::cerr << "SLAM: " << kslam_last_error(nullptr) << "\n"; return 3; }
+  // one context per entry of --devices, the genome index replicated in each (read pairs shard trivially)
+  const size_t G = o.devices.size();
+  std::vector<kslam_ctx *> ctxs(G, nullptr);
+  for (size_t g = 0; g < G; g++) {
+    prm.device = o.devices[g];
+    if (kslam_create(&prm, &ctxs[g]) != KSLAM_OK) { std::cerr << "SLAM: " << kslam_last_error(nullptr) << "\n"; return 3; }
+  }
   log("Getting k-mers from index");
-  if (kslam_load_genomes(ctx, db.n_entries, db.bases, db.offs) != KSLAM_OK) { std::cerr << "SLAM: " << kslam_last_error(ctx) << "\n"; return 3; }
+  {
+    std::vector<int> rc(G, 0);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; g++) th.emplace_back([&, g] { rc[g] = kslam_load_genomes(ctxs[g], db.n_entries, db.bases, db.offs); });
+    for (auto &t : th) t.join();
+    for (size_t g = 0; g < G; g++) if (rc[g] != KSLAM_OK) { std::cerr << "SLAM: " << kslam_last_error(ctxs[g]) << "\n"; return 3; }
+  }
 
   kslam_fastq *reader = nullptr;
   if (kslam_fastq_open(o.inputs[0].c_str(), isPaired ? o.inputs[1].c_str() : nullptr, 0, &reader) != KSLAM_OK) {
@@ -236,27 +334,10 @@ int run_alignment(const Options &o, const std::string &commandLine) {      // me
       if (last) return;
     }
   });
-  std::thread gpu([&] {                                    // stage 2: alignToDatabase + score screen + getPairedOverlaps on the GPU
+  std::thread gpu([&] {                                    // stage 2: alignToDatabase + score screen + getPairedOverlaps on the GPU(s)
     for (;;) {
       Batch *b = to_gpu.take();
-      if (b->reads.n_reads && b->error.empty()) {
-        if (isPaired) {
-          kslam_pairs p;
-          if (kslam_align_pair_batch(ctx, b->reads.n_reads, b->reads.bases, b->reads.offs, &p) != KSLAM_OK) b->error = kslam_last_error(ctx);
-          else {
-            b->overlaps.assign(p.sorted_overlaps, p.sorted_overlaps + p.n_sorted);
-            b->cigars.assign(p.cigar_pool, p.cigar_pool + p.n_cigar_words);
-            b->pairs.assign(p.pairs, p.pairs + p.n_pairs);
-          }
-        } else {
-          kslam_alignments a;
-          if (kslam_align_batch(ctx, b->reads.n_reads, b->reads.bases, b->reads.offs, &a) != KSLAM_OK) b->error = kslam_last_error(ctx);
-          else {
-            b->overlaps.assign(a.overlaps, a.overlaps + a.n_overlaps);
-            b->cigars.assign(a.cigar_pool, a.cigar_pool + a.n_cigar_words);
-          }
-        }
-      }
+      if (b->reads.n_reads && b->error.empty()) align_batch(ctxs, isPaired, b);
       const bool last = b->reads.n_reads == 0 || !b->error.empty();
       to_host.put(b);
       if (last) return;
@@ -320,7 +401,7 @@ int run_alignment(const Options &o, const std::string &commandLine) {      // me
   }
   log("Done");
   kslam_fastq_close(reader);
-  kslam_destroy(ctx);
+  for (kslam_ctx *c : ctxs) kslam_destroy(c);
   kslam_taxa_destroy(taxa);
   kslam_taxdb_close(taxdb);
   kslam_index_free(index);

@@ -80,6 +80,13 @@ def test_slam_executable_equals_reference(pkg, tmp_path):
         for suffix, want in zip(("_PerRead", "", "_abbreviated"), outs):
             assert (tmp_path / ("o.xml" + suffix)).read_bytes() == want, suffix
         assert outs[1].count(b"<taxon>") >= 3
+        # the same run with every batch split over three contexts (--devices; here all on GPU 0): identical files
+        r = run("--db", db, "--sam-file", "m.sam", "--output-file", "m.xml", "--num-reads-at-once", 150, "--devices", "0,0,0", r1, r2)
+        assert r.returncode == 0, r.stderr
+        body = lambda t: t[t.index(b"@PG"):].split(b"\n", 1)[1]   # noqa: E731
+        assert body((tmp_path / "m.sam").read_bytes()) == sam
+        for suffix, want in zip(("_PerRead", "", "_abbreviated"), outs):
+            assert (tmp_path / ("m.xml" + suffix)).read_bytes() == want, suffix
         # paired, taxonomy only (no SAM: the records are not re-sorted before the taxonomy step), XML to stdout, --num-reads cut
         r = run("--db=" + str(db), "--num-reads", 250, "--num-reads-at-once", 100, "--no-pseudo-assembly", "--score-fraction-threshold", 0.5, r1, r2)
         assert r.returncode == 0, r.stderr
@@ -99,6 +106,9 @@ def test_slam_executable_equals_reference(pkg, tmp_path):
         hdr, sam, _ = reference_run(L, rt, gb, go, s_rb, s_ro, quals[:len(s_rb)], ids[:n_pairs], n_pairs // 2, 300, False, True, False, num_alignments=3)
         got = (tmp_path / "s.sam").read_bytes()
         assert got[got.index(b"@PG"):].split(b"\n", 1)[1] == sam and len(sam) > 10_000
+        r = run("--db", db, "--just-align", "--sam-file", "s2.sam", "--num-reads-at-once", 300, "--num-alignments", 3, "--devices", "0,0", r1)
+        assert r.returncode == 0, r.stderr
+        assert body((tmp_path / "s2.sam").read_bytes()) == sam
     finally:
         L.kref_set_threads(os.cpu_count() or 1)
         L.kref_taxdb_close(rt)
