@@ -317,6 +317,8 @@ def run_cli(args, pkg, meta):
             raise SystemExit(f"SLAM failed ({r.returncode}): {r.stderr.decode()[-500:]}")
         stages = open(os.path.join(d, "log.txt")).read().strip().splitlines()
         log(f"[bench/cli] run {i}: {pairs} pairs in {dt:.2f}s; last log line: {stages[-1] if stages else ''}")
+        if i == args.warmup + args.steps - 1:
+            log("[bench/cli] log.txt of the last run (first / last lines):\n  " + "\n  ".join(stages[:8] + ["..."] + stages[-6:]))
         if i >= args.warmup:
             runs.append(dt)
     dt = float(np.mean(runs))

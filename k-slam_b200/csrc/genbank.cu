@@ -7,7 +7,7 @@
 // stoul stops at the closing quote after an unsigned wrap-around of the substring length; a qualifier found anywhere in
 // a feature's text wins; every line of the ORIGIN block is a "section" of its own whose tag is the base counter).
 // The archive grammar is the one SURVEY.md App. B.1 spells out; this image has no Boost, so the bytes of a real
-// archive could not be compared ("parity unpinned" for the archive, pinned for the parsers: tests/test_genbank.py
+// archive could not be compared ("parity unpinned" for the archive, pinned for the parsers: tests/test_taxon_host.py
 // runs the reference's own createIndexFromGBFF through oracle/_ref).
 #include "common.cuh"
 #include "host_stages.h"
@@ -37,7 +37,16 @@ thread_local std::string g_error;
 bool read_file(const char *path, std::string &data) {
   FILE *f = fopen(path, "rb");
   if (!f) return false;
-  char buf[1 << 16];
+  if (fseek(f, 0, SEEK_END) == 0) {                        // regular file: one allocation, one read
+    const long size = ftell(f);
+    rewind(f);
+    if (size > 0) {
+      data.resize((size_t)size);
+      const size_t got = fread(&data[0], 1, (size_t)size, f);
+      data.resize(got);
+    }
+  }
+  char buf[1 << 16];                                       // whatever is left (pipes, files that grew)
   size_t n;
   while ((n = fread(buf, 1, sizeof buf, f)) > 0) data.append(buf, n);
   const bool ok = !ferror(f);
@@ -114,8 +123,9 @@ struct kslam_index {
   std::vector<uint8_t> is_plasmid, is_16s;
   std::vector<kslam_gene> genes; std::vector<uint64_t> gene_offs{0}; std::string gene_strings;
 
-  void add(const Entry &e) {
-    bases += e.bases; offs.push_back(bases.size());
+  void add(const Entry &e) { add(e, e.bases); }
+  void add(const Entry &e, std::string_view entry_bases) {   // the bases may live elsewhere (the archive reader passes a view)
+    bases.append(entry_bases.data(), entry_bases.size()); offs.push_back(bases.size());
     locus += e.locusTag; locus_offs.push_back(locus.size());
     taxonomy_ids.push_back(e.taxonomyID); genbank_ids.push_back(e.genbankID);
     is_plasmid.push_back(e.isPlasmid); is_16s.push_back(e.is16S);
@@ -152,13 +162,15 @@ struct ArchiveReader {
     p = q;
     return v;
   }
-  void string(std::string &out) {
+  std::string_view view() {
     const uint64_t n = number();
     p += 1;                                                // exactly one separator, then n raw bytes (they may contain spaces)
     if (p + n > d.size()) throw std::runtime_error("string runs past the end of the archive");
-    out.assign(d, p, n);
+    const std::string_view v(d.data() + p, n);
     p += n;
+    return v;
   }
+  void string(std::string &out) { const std::string_view v = view(); out.assign(v.data(), v.size()); }
   void class_info(unsigned bit) { if (!(seen & bit)) { seen |= bit; number(); number(); } }
   uint64_t vector(unsigned bit) { class_info(bit); const uint64_t count = number(); number(); return count; }
 };
@@ -256,12 +268,13 @@ int kslam_index_read(const char *path, kslam_index **out) {           // getInde
     if (r.number() < 4) throw std::runtime_error("archive library version < 4 is not supported");
     enum { INDEX = 1, ENTRIES = 2, ENTRY = 4, GENES = 8, GENE = 16, CDS = 32 };
     index = new kslam_index();
+    index->bases.reserve(data.size());                     // the archive is almost all bases: no regrowth while appending
     r.class_info(INDEX);
     const uint64_t n_entries = r.vector(ENTRIES);
     for (uint64_t e = 0; e < n_entries; e++) {
       r.class_info(ENTRY);
       Entry en;
-      r.string(en.bases);
+      const std::string_view bases = r.view();
       en.taxonomyID = (uint32_t)r.number(); en.genbankID = (uint32_t)r.number();
       en.isPlasmid = r.number() != 0; en.is16S = r.number() != 0;
       r.string(en.locusTag);
@@ -275,7 +288,7 @@ int kslam_index_read(const char *path, kslam_index **out) {           // getInde
         ge.start = (uint32_t)r.number(); ge.stop = (uint32_t)r.number(); ge.complement = r.number() != 0;
         en.genes.push_back(std::move(ge));
       }
-      index->add(en);
+      index->add(en, bases);
     }
     *out = index;
     return KSLAM_OK;
