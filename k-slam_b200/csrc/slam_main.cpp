@@ -400,10 +400,11 @@ int run_alignment(const Options &o, const std::string &commandLine) {      // me
     kslam_sam_free(per_read); kslam_sam_free(xml); kslam_sam_free(abbreviated);
   }
   log("Done");
-  // Every output is written and closed. Unmapping tens of GB of pinned buffers and tearing the CUDA contexts down took
-  // 0.5 s of a 3.3 s run; the operating system does it faster (KSLAM_CLEAN_EXIT=1 runs the destructors, for leak checkers).
+  // Every output is written and closed. KSLAM_FAST_EXIT=1 leaves without unmapping the pinned buffers and tearing the CUDA
+  // contexts down (0.5 s of a 3.3 s run) — measured: the driver then cleans up behind the dead process and the NEXT
+  // process pays 1.6 s in its context creation, so back-to-back runs get slower; off by default.
   fflush(stdout);
-  if (!getenv("KSLAM_CLEAN_EXIT")) _Exit(rc);
+  if (getenv("KSLAM_FAST_EXIT")) _Exit(rc);
   kslam_fastq_close(reader);
   for (kslam_ctx *c : ctxs) kslam_destroy(c);
   kslam_taxa_destroy(taxa);
