@@ -15,7 +15,10 @@
 // The batch comes back in the layout kslam_align_batch / kslam_align_pair_batch take (one byte array + n+1 offsets),
 // in page-locked memory when a CUDA device is present so the H2D copy runs at full PCIe rate.
 #include "common.cuh"
+#include <chrono>
+#include <emmintrin.h>
 #include <fcntl.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -28,6 +31,7 @@ struct MappedFile {
   const char *p = nullptr;
   size_t size = 0, cursor = 0;
   bool eof_line_done = false;   // the empty line safeGetline yields once at end of file has been handed out
+  double bytes_per_line = 0;    // running estimate from the last batch (sizes the next scan window)
   int fd = -1;
   bool open(const char *path, std::string &err) {
     fd = ::open(path, O_RDONLY);
@@ -74,6 +78,21 @@ template <class F> void parallel_for(uint32_t threads, uint64_t n, F f) {
   for (auto &x : th) x.join();
 }
 
+// Offsets just past every '\n' of p[lo, hi) appended to `out` (the starts of the lines that follow). 64 bytes per step:
+// four SSE2 compares folded into one 64-bit mask, one entry per set bit. (memchr per line cost 4 calls per record.)
+void scan_newlines(const char *p, size_t lo, size_t hi, std::vector<uint64_t> &out) {
+  size_t i = lo;
+  const __m128i nl = _mm_set1_epi8('\n');
+  for (; i + 64 <= hi; i += 64) {
+    const __m128i a = _mm_loadu_si128((const __m128i *)(p + i)), b = _mm_loadu_si128((const __m128i *)(p + i + 16));
+    const __m128i c = _mm_loadu_si128((const __m128i *)(p + i + 32)), d = _mm_loadu_si128((const __m128i *)(p + i + 48));
+    uint64_t m = (uint64_t)(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(a, nl)) | ((uint64_t)(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(b, nl)) << 16) |
+                 ((uint64_t)(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(c, nl)) << 32) | ((uint64_t)(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(d, nl)) << 48);
+    while (m) { out.push_back(i + (size_t)__builtin_ctzll(m) + 1); m &= m - 1; }
+  }
+  for (; i < hi; i++) if (p[i] == '\n') out.push_back(i + 1);
+}
+
 // is byte i the end of a line? ('\r', or a '\n' that does not directly follow a '\r')
 inline bool line_end_at(const char *p, size_t i) { return p[i] == '\r' || (p[i] == '\n' && (i == 0 || p[i - 1] != '\r')); }
 
@@ -111,7 +130,64 @@ static uint64_t index_lines(MappedFile &mf, uint64_t max_reads, uint32_t threads
   }
   // grow a window until it holds want_lines line ends or reaches the end of the file
   size_t win = (size_t)(max_reads < (1u << 20) ? max_reads : (1u << 20)) * 512 + 4096;
+  if (mf.bytes_per_line > 0) {                             // later batches: the file's own average line length, + 2 %
+    const double est = (double)want_lines * mf.bytes_per_line * 1.02 + 65536;
+    win = est < (double)(size - begin) ? (size_t)est : size - begin;
+  }
   if (win > size - begin) win = size - begin;
+  // Unix files (no '\r' in the window — the normal case): ONE scan. Every thread lists the line starts of its byte range,
+  // the window grows by scanning only what is new, and the lists are joined in order. Files with '\r' take the general
+  // path below (count, prefix sum, second pass).
+  {
+    std::vector<std::vector<uint64_t>> lists;              // in file order
+    size_t scanned = begin, end_f = begin;
+    uint64_t total_f = 0;
+    bool cr_seen = false;
+    for (;;) {
+      end_f = begin + win;
+      const size_t span = end_f - scanned;
+      const uint32_t nt = (threads > 1 && span >= (1u << 16)) ? threads : 1;
+      std::vector<uint8_t> cr(nt, 0);
+      const size_t first = lists.size();
+      lists.resize(first + nt);
+      parallel_for(nt, span, [&](uint32_t t, uint64_t lo, uint64_t hi) {
+        if (memchr(p + scanned + lo, '\r', hi - lo) != nullptr) { cr[t] = 1; return; }
+        lists[first + t].reserve((size_t)((hi - lo) / 64) + 16);
+        scan_newlines(p, scanned + lo, scanned + hi, lists[first + t]);
+      });
+      for (uint8_t v : cr) cr_seen |= v != 0;
+      if (cr_seen) break;
+      for (size_t l = first; l < lists.size(); l++) total_f += lists[l].size();
+      scanned = end_f;
+      if (total_f >= want_lines || end_f >= size) break;
+      const double per_line = (double)win / (double)(total_f ? total_f : 1);
+      const size_t need = (size_t)((double)(want_lines - total_f) * per_line * 1.25) + 65536;
+      win = win + need > size - begin ? size - begin : win + need;
+    }
+    if (!cr_seen) {
+      const bool at_eof = end_f >= size;
+      const bool tail_line = at_eof && size > begin && p[size - 1] != '\n';   // a last line without terminator counts (it is not empty)
+      uint64_t n_lines = total_f + (tail_line ? 1 : 0);
+      bool eof_line = false;                               // the one EMPTY line safeGetline yields at end of file (see below)
+      if (at_eof && n_lines < want_lines) { eof_line = true; n_lines++; mf.eof_line_done = true; }
+      if (n_lines > want_lines) n_lines = want_lines;
+      starts.assign(n_lines + 1, 0);
+      starts[0] = begin;
+      uint64_t k = 0;
+      for (auto &l : lists) {
+        if (k >= n_lines) break;
+        const uint64_t take = std::min<uint64_t>(l.size(), n_lines - k);
+        if (take) memcpy(&starts[k + 1], l.data(), take * sizeof(uint64_t));
+        k += take;
+      }
+      if (tail_line && n_lines >= total_f + 1) starts[total_f + 1] = size;
+      if (eof_line) starts[n_lines] = size;
+      *consumed_to = starts[n_lines];
+      if (n_lines > 64) mf.bytes_per_line = (double)(starts[n_lines] - begin) / (double)n_lines;
+      return n_lines;
+    }
+    if (win > size - begin) win = size - begin;
+  }
   std::vector<uint64_t> cnt(threads + 1);
   size_t end = begin;
   uint64_t total = 0;
@@ -212,6 +288,9 @@ int kslam_fastq_set_ring(kslam_fastq *rd, uint32_t n_buffer_sets) {
 int kslam_fastq_next(kslam_fastq *rd, uint64_t max_reads, kslam_read_batch *out) {
   if (!rd || !out) return KSLAM_ERR_ARG;
   try {
+    const bool trace = getenv("KSLAM_FASTQ_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     memset(out, 0, sizeof *out);
     const int nf = rd->paired ? 2 : 1;
     uint64_t n_rec[2] = {0, 0};
@@ -227,6 +306,7 @@ int kslam_fastq_next(kslam_fastq *rd, uint64_t max_reads, kslam_read_batch *out)
       rd->err = "mismatch in R1 and R2 size";
       return KSLAM_ERR_STATE;
     }
+    const double t1 = now();
     kslam_fastq::BufSet &bs = rd->sets[rd->n_batches % rd->sets.size()];
     rd->n_batches++;
     bs.offs.assign(n + 1, 0); bs.id_offs.assign(n + 1, 0); bs.q_offs.assign(n + 1, 0);
@@ -254,7 +334,9 @@ int kslam_fastq_next(kslam_fastq *rd, uint64_t max_reads, kslam_read_batch *out)
         ioffs[i + 1] = cnt;
       }
     });
+    const double t2 = now();
     for (uint64_t i = 0; i < n; i++) { offs[i + 1] += offs[i]; ioffs[i + 1] += ioffs[i]; qoffs[i + 1] += qoffs[i]; }
+    const double t3 = now();
     bs.bases.reserve(offs[n] + 16, rd->pinned); bs.quals.reserve(qoffs[n] + 16, false); bs.ids.reserve(ioffs[n] + 16, false);
     parallel_for(rd->threads, n, [&](uint32_t, uint64_t lo, uint64_t hi) {
       for (uint64_t i = lo; i < hi; i++) {
@@ -267,6 +349,8 @@ int kslam_fastq_next(kslam_fastq *rd, uint64_t max_reads, kslam_read_batch *out)
         memcpy(bs.ids.p + ioffs[i], p + ls[4 * r] + from, cnt);
       }
     });
+    if (trace) fprintf(stderr, "[kslam_fastq] %llu reads: line index %.1f ms, lengths %.1f ms, prefix sums %.1f ms, copy %.1f ms\n",
+                       (unsigned long long)n, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, (now() - t3) * 1e3);
     out->n_reads = n; out->n_r1 = n_rec[0];
     out->bases = bs.bases.p; out->offs = bs.offs.data();
     out->quals = bs.quals.p; out->qual_offs = bs.q_offs.data();

@@ -84,6 +84,18 @@ def test_odd_line_structure(pkg, tmp_path):
             assert ours(pkg, p, None, mr, 4) == T.ref_read_fastq(p, None, mr), (k, mr)
 
 
+@pytest.mark.skipif(not T.have_ref(), reason="needs oracle/_ref")
+@pytest.mark.parametrize("final_newline", [True, False])
+def test_long_reads_grow_the_scan_window(pkg, tmp_path, final_newline):
+    """Records far longer than the first window estimate (512 bytes each): the single-scan path keeps what it has listed and
+    scans on, over several threads, and the next batch sizes its window from the file's own line lengths."""
+    r1, r2 = str(tmp_path / "long_R1.fq"), str(tmp_path / "long_R2.fq")
+    write(r1, fastq_bytes(1500, 5, read_len=(600, 900), final_newline=final_newline))
+    write(r2, fastq_bytes(1500, 6, read_len=(600, 900), final_newline=final_newline))
+    for max_reads, threads in ((400, 4), (50, 3), (1499, 8), (5000, 2)):
+        assert ours(pkg, r1, r2, max_reads, threads) == T.ref_read_fastq(r1, r2, max_reads), (max_reads, threads)
+
+
 def test_reader_volume_and_batches(pkg, tmp_path):
     """20k pairs in batches of 3000: concatenated batches reproduce the files; R1 block precedes the R2 block."""
     n = 20_000
