@@ -165,7 +165,7 @@ struct ArchiveReader {
   std::string_view view() {
     const uint64_t n = number();
     p += 1;                                                // exactly one separator, then n raw bytes (they may contain spaces)
-    if (p + n > d.size()) throw std::runtime_error("string runs past the end of the archive");
+    if (p > d.size() || n > d.size() - p) throw std::runtime_error("string runs past the end of the archive");
     const std::string_view v(d.data() + p, n);
     p += n;
     return v;

@@ -1,7 +1,7 @@
 """FASTQ ingest throughput: kslam_fastq_* (chunk-parallel) next to the reference's own reader (oracle/_ref) on the same
-files. Host-side measurement; run anywhere: python tools/bench_fastq.py [pairs]"""
+files. Host-side measurement; run anywhere: python tests/perf/bench_fastq.py [pairs]"""
 import os, sys, time, tempfile
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import __graft_entry__ as ge

@@ -1,6 +1,6 @@
 """Host-stage profile of a metagenomic batch without a GPU: config-2-like database (strains in a phylogeny, GenBank genes,
 taxonomy), alignments from the reference (oracle/_ref, test infrastructure), then kslam_batch_outputs + kslam_taxa_results
-timed with KSLAM_SAM_TRACE=1. Usage: python tools/prof_meta_host.py [pairs] [threads]"""
+timed with KSLAM_SAM_TRACE=1. Usage: python tests/perf/prof_meta_host.py [pairs] [threads]"""
 import os
 import pathlib
 import sys
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import _lib as T  # noqa: E402
 from test_taxon_host import make_db  # noqa: E402
 

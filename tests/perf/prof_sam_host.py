@@ -1,12 +1,12 @@
 """Host-stage profile without a GPU: alignments of a config-1-like batch from the reference (oracle/_ref, test infrastructure),
-then kslam_sam_batch timed with KSLAM_SAM_TRACE=1. Usage: python tools/prof_sam_host.py [pairs] [threads]"""
+then kslam_sam_batch timed with KSLAM_SAM_TRACE=1. Usage: python tests/perf/prof_sam_host.py [pairs] [threads]"""
 import os
 import sys
 import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import _lib as T  # noqa: E402
 
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 200_000
