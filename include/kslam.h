@@ -226,7 +226,17 @@ typedef struct {
   /* GenbankEntry::genes of GenBank databases (GenbankTools.h:67-110,149); all three NULL for FASTA databases.
    * Entry e owns genes[gene_offs[e] .. gene_offs[e+1]), in the entry's stored order. */
   const kslam_gene *genes; const uint64_t *gene_offs; const char *gene_strings;
+  /* Optional (NULL = scan every gene of the entry, as GenbankEntry::getGene does): lookup structure over the gene table
+   * from kslam_gene_index_build, same answers. kslam_index_db fills it in. */
+  const struct kslam_gene_index *gene_index;
 } kslam_sam_db;
+/* Per entry whose genes are ordered by CDS start (what the database builders produce): the running maximum of the CDS
+ * stops, so that the best gene of an alignment is found from a binary search and a short backward scan instead of a pass
+ * over the entry's whole gene list (thousands of genes per genome, once per alignment). Entries in any other order keep the
+ * full scan. The db's gene arrays must stay valid and unchanged while the index is in use. */
+typedef struct kslam_gene_index kslam_gene_index;
+int kslam_gene_index_build(const kslam_sam_db *db, kslam_gene_index **out);
+void kslam_gene_index_free(kslam_gene_index *index);
 int kslam_sam_header(const kslam_sam_db *db, const char *command_line, char **text, uint64_t *len);   /* getHeader, SAM.h:518-531 */
 int kslam_sam_batch(const kslam_sam_params *params, const kslam_sam_db *db, const kslam_read_batch *reads,
                     const kslam_pairs *pairs, char **text, uint64_t *len, uint32_t *max_insert_size /* may be NULL */);

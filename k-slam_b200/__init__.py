@@ -91,7 +91,7 @@ class SamParams(C.Structure):
 class _SamDb(C.Structure):
     _fields_ = [("n_entries", C.c_uint64), ("bases", C.c_void_p), ("offs", C.c_void_p), ("locus_tags", C.c_void_p),
                 ("locus_offs", C.c_void_p), ("taxonomy_ids", C.c_void_p),
-                ("genes", C.c_void_p), ("gene_offs", C.c_void_p), ("gene_strings", C.c_void_p)]
+                ("genes", C.c_void_p), ("gene_offs", C.c_void_p), ("gene_strings", C.c_void_p), ("gene_index", C.c_void_p)]
 
 
 def declared_symbols():
@@ -181,6 +181,9 @@ def lib():
     L.kslam_index_read.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.kslam_index_write.argtypes = [vp, C.c_char_p]
     L.kslam_index_db.argtypes = [vp, C.POINTER(_SamDb)]
+    L.kslam_gene_index_build.argtypes = [C.POINTER(_SamDb), C.POINTER(vp)]
+    L.kslam_gene_index_free.argtypes = [vp]
+    L.kslam_gene_index_free.restype = None
     L.kslam_index_error.restype = C.c_char_p
     L.kslam_index_free.argtypes = [vp]
     L.kslam_index_free.restype = None
@@ -520,7 +523,7 @@ class SamWriter:
     (PairedOverlap.h:314-576, SAM.h). Host code: works without a GPU on any (sorted_overlaps, cigar_pool, pairs)."""
 
     def __init__(self, gen_bases=None, gen_offs=None, locus_tags=None, taxonomy_ids=None, num_alignments=10, score_fraction_threshold=0.95,
-                 pseudo_assembly=True, report_cigar=True, sam_xa=False, threads=0, genes=None, index=None):
+                 pseudo_assembly=True, report_cigar=True, sam_xa=False, threads=0, genes=None, index=None, gene_index=True):
         """The database either as arrays (genes = (GENE_DT records, gene_offs u64[n+1], gene string bytes) or None) or as an
         Index (kslam_index_*), whose buffers are used in place."""
         self.L = lib()
@@ -537,7 +540,18 @@ class SamWriter:
                 self.genes = np.ascontiguousarray(genes[0], dtype=GENE_DT); self.gene_offs = _u64(genes[1])
                 self.gene_strings = _u8(genes[2]) if len(genes[2]) else np.zeros(1, np.uint8)
                 self.db.genes, self.db.gene_offs, self.db.gene_strings = self.genes.ctypes.data, self.gene_offs.ctypes.data, self.gene_strings.ctypes.data
+                if gene_index:                              # binary-search lookup of the best gene (same answers as the full scan)
+                    gi = C.c_void_p()
+                    if self.L.kslam_gene_index_build(C.byref(self.db), C.byref(gi)) != 0:
+                        raise KslamError("kslam_gene_index_build failed")
+                    self.db.gene_index = self._gene_index = gi
         self.prm = SamParams(num_alignments, int(pseudo_assembly), int(report_cigar), int(sam_xa), threads, score_fraction_threshold)
+
+    def __del__(self):
+        gi = getattr(self, "_gene_index", None)
+        if gi:
+            self.L.kslam_gene_index_free(gi)
+            self._gene_index = None
 
     def _take(self, ptr, n):
         try:

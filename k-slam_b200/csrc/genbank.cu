@@ -12,6 +12,7 @@
 #include "common.cuh"
 #include "host_stages.h"
 #include <algorithm>
+#include <climits>
 #include <ctype.h>
 #include <stdexcept>
 #include <stdio.h>
@@ -140,6 +141,8 @@ struct kslam_index {
     gene_offs.push_back(genes.size());
   }
   uint64_t n() const { return offs.size() - 1; }
+  mutable kslam_gene_index *gene_index = nullptr;          // built on the first kslam_index_db
+  ~kslam_index() { delete gene_index; }
 };
 
 namespace {
@@ -327,6 +330,30 @@ int kslam_index_write(const kslam_index *ix, const char *path) {      // writeIn
   return (fclose(f) == 0 && ok) ? KSLAM_OK : KSLAM_ERR_STATE;
 }
 
+int kslam_gene_index_build(const kslam_sam_db *db, kslam_gene_index **out) {
+  if (!db || !out || !db->genes || !db->gene_offs) return KSLAM_ERR_ARG;
+  try {
+    kslam_gene_index *gi = new kslam_gene_index();
+    gi->sorted.assign(db->n_entries, 0);
+    gi->max_stop.assign(db->gene_offs[db->n_entries], 0);
+    for (uint64_t e = 0; e < db->n_entries; e++) {
+      bool ok = true;
+      int32_t run = INT32_MIN;
+      for (uint64_t g = db->gene_offs[e]; g < db->gene_offs[e + 1]; g++) {
+        const kslam_gene &k = db->genes[g];
+        if (k.cds_start > (uint32_t)INT32_MAX || k.cds_stop > (uint32_t)INT32_MAX) ok = false;
+        if (g > db->gene_offs[e] && k.cds_start < db->genes[g - 1].cds_start) ok = false;
+        run = std::max(run, (int32_t)k.cds_stop);
+        gi->max_stop[g] = run;
+      }
+      gi->sorted[e] = ok;
+    }
+    *out = gi;
+    return KSLAM_OK;
+  } catch (const std::exception &) { return KSLAM_ERR_NOMEM; }
+}
+void kslam_gene_index_free(kslam_gene_index *index) { delete index; }
+
 int kslam_index_db(const kslam_index *ix, kslam_sam_db *out) {
   if (!ix || !out) return KSLAM_ERR_ARG;
   memset(out, 0, sizeof *out);
@@ -334,7 +361,11 @@ int kslam_index_db(const kslam_index *ix, kslam_sam_db *out) {
   out->bases = ix->bases.data(); out->offs = ix->offs.data();
   out->locus_tags = ix->locus.data(); out->locus_offs = ix->locus_offs.data();
   out->taxonomy_ids = ix->taxonomy_ids.data();
-  if (!ix->genes.empty()) { out->genes = ix->genes.data(); out->gene_offs = ix->gene_offs.data(); out->gene_strings = ix->gene_strings.data(); }
+  if (!ix->genes.empty()) {
+    out->genes = ix->genes.data(); out->gene_offs = ix->gene_offs.data(); out->gene_strings = ix->gene_strings.data();
+    if (!ix->gene_index && kslam_gene_index_build(out, &ix->gene_index) != KSLAM_OK) ix->gene_index = nullptr;
+    out->gene_index = ix->gene_index;
+  }
   return KSLAM_OK;
 }
 

@@ -2,6 +2,7 @@
 // taxon.cu: LCA, genes, XML). Host code only.
 #pragma once
 #include "../../include/kslam.h"
+#include <algorithm>
 #include <stdint.h>
 #include <string>
 #include <string_view>
@@ -47,13 +48,34 @@ inline std::string_view gene_str(const kslam_sam_db *db, const kslam_gene *g, in
 }
 enum { GENE_NAME = 0, GENE_LOCUS = 1, GENE_PROTEIN = 2, GENE_PRODUCT = 3, GENE_REFERENCE = 4 };
 
+}  // namespace kslam_host
+struct kslam_gene_index {
+  std::vector<uint8_t> sorted;       // per entry: genes ordered by cds_start (as int), every start / stop <= INT32_MAX
+  std::vector<int32_t> max_stop;     // per gene: largest cds_stop among the entry's genes up to and including this one
+};
+namespace kslam_host {
+
 // GenbankEntry::getGene, GenbankTools.h:170-185: the gene with the largest (strictly positive) overlap with
 // [startPos, endPos], first one on ties; nullptr when the entry has no gene table or nothing overlaps.
 inline const kslam_gene *best_gene(const kslam_sam_db *db, uint32_t entry, int32_t startPos, int32_t endPos) {
   if (!db->genes || !db->gene_offs) return nullptr;
   const kslam_gene *bestMatch = nullptr;
   int32_t largestOverlap = 0;
-  for (uint64_t gi = db->gene_offs[entry]; gi < db->gene_offs[entry + 1]; gi++) {
+  const uint64_t g0 = db->gene_offs[entry], g1 = db->gene_offs[entry + 1];
+  if (db->gene_index && db->gene_index->sorted[entry]) {
+    // genes that can overlap start before endPos: binary search for the first start >= endPos, then walk back while some
+    // gene at or before the position still ends after startPos. Walking back with >= keeps the FIRST gene among equals.
+    uint64_t lo = g0, hi = g1;
+    while (lo < hi) { const uint64_t mid = (lo + hi) / 2; if ((int32_t)db->genes[mid].cds_start < endPos) lo = mid + 1; else hi = mid; }
+    const int32_t *max_stop = db->gene_index->max_stop.data();
+    for (uint64_t gi = lo; gi > g0 && max_stop[gi - 1] > startPos; gi--) {
+      const kslam_gene *g = db->genes + (gi - 1);
+      const int32_t numBasesOverlap = std::min<int>(endPos, (int)g->cds_stop) - std::max<int>(startPos, (int)g->cds_start);
+      if (numBasesOverlap > 0 && numBasesOverlap >= largestOverlap) { bestMatch = g; largestOverlap = numBasesOverlap; }
+    }
+    return bestMatch;
+  }
+  for (uint64_t gi = g0; gi < g1; gi++) {
     const kslam_gene *g = db->genes + gi;
     const int32_t numBasesOverlap = std::min<int>(endPos, (int)g->cds_stop) - std::max<int>(startPos, (int)g->cds_start);
     if (numBasesOverlap > largestOverlap) { bestMatch = g; largestOverlap = numBasesOverlap; }

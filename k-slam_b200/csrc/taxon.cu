@@ -52,6 +52,55 @@ struct kslam_taxdb {
   // order writeTaxonomyIndex depends on is the same
   std::unordered_map<uint32_t, TaxEntry> nodes;
 
+  // Flat copy of the parent links for the LCA walks (built once by finalize()): node i has id[i]; next_id[i] is what
+  // getParentTaxID answers for it (0 ends the walk: the parent is the root, id 1, or absent); next_idx[i] is the node that
+  // id refers to, or -1 when it is not in the database (the walk records the id and ends). An open-addressing table maps
+  // an id to its node. A walk is then a chain of 4-byte loads in a dense array instead of one hash-map probe per level —
+  // with the NCBI taxonomy (2.5 M nodes, ~30 levels) the probes were the cost of the whole taxonomy stage.
+  std::vector<uint32_t> flat_id, flat_next_id, table;
+  std::vector<int32_t> flat_next_idx;
+  uint32_t table_mask = 0;
+  static uint32_t hash(uint32_t id) { return id * 2654435761u; }
+  int32_t find(uint32_t id) const {
+    if (table.empty()) return -1;
+    for (uint32_t h = hash(id) & table_mask;; h = (h + 1) & table_mask) {
+      const uint32_t slot = table[h];
+      if (slot == 0) return -1;
+      if (flat_id[slot - 1] == id) return (int32_t)(slot - 1);
+    }
+  }
+  void finalize() {
+    const size_t n = nodes.size();
+    flat_id.clear(); flat_next_id.clear(); flat_next_idx.assign(n, -1);
+    flat_id.reserve(n); flat_next_id.reserve(n);
+    size_t cap = 16;
+    while (cap < 2 * n + 2) cap <<= 1;
+    table.assign(cap, 0); table_mask = (uint32_t)(cap - 1);
+    for (auto &e : nodes) {
+      flat_id.push_back(e.first);
+      flat_next_id.push_back(e.second.parentTaxonomyID != 1 ? e.second.parentTaxonomyID : 0);
+      uint32_t h = hash(e.first) & table_mask;
+      while (table[h]) h = (h + 1) & table_mask;
+      table[h] = (uint32_t)flat_id.size();
+    }
+    for (size_t i = 0; i < n; i++) flat_next_idx[i] = flat_next_id[i] ? find(flat_next_id[i]) : -1;
+  }
+  // the ids from taxID up to the end of its walk, leaf first, into out[cap]; returns the count, or -1 when cap is too small
+  int path_of(uint32_t taxID, uint32_t *out, int cap) const {
+    int len = 0;
+    if (taxID == 0) return 0;
+    int32_t idx = find(taxID);
+    out[len++] = taxID;
+    while (idx >= 0) {
+      const uint32_t nid = flat_next_id[idx];
+      if (nid == 0) break;
+      if (len >= cap) return -1;
+      out[len++] = nid;
+      idx = flat_next_idx[idx];
+    }
+    return len;
+  }
+
   void read_index(const char *path) {                      // readTaxonomyIndex, TaxonomyDatabase.h:166-183
     std::ifstream in(path);
     if (!in.is_open()) throw std::runtime_error("unable to open taxonomy index file");
@@ -119,7 +168,27 @@ struct kslam_taxdb {
   // getLowestCommonAncestor, :185-223. Paths run from the node up to (not including) the root's child boundary, are
   // reversed, ordered by length, and compared position by position over the shortest one. The reference walks parent
   // links without a cycle check; a database with a cycle would hang it, here the walk stops after nodes.size() steps.
+  // What the comparison over root-first paths computes is the last element of the longest common prefix of all paths
+  // (cut at the shortest one): the prefix shared with the first path can only shrink as further paths are compared.
   uint32_t lca(const uint32_t *taxIDs, uint64_t n) const {
+    if (n == 0) return 0;
+    constexpr int CAP = 256;
+    uint32_t first[CAP], other[CAP];
+    const int len0 = path_of(taxIDs[0], first, CAP);
+    if (len0 < 0) return lca_generic(taxIDs, n);
+    int lcp = len0;
+    for (uint64_t k = 1; k < n && lcp > 0; k++) {
+      if (taxIDs[k] == taxIDs[k - 1]) continue;            // alignments of one read often share the entry's taxon
+      const int len = path_of(taxIDs[k], other, CAP);
+      if (len < 0) return lca_generic(taxIDs, n);
+      const int m = lcp < len ? lcp : len;
+      int i = 0;
+      while (i < m && first[len0 - 1 - i] == other[len - 1 - i]) i++;
+      lcp = i;
+    }
+    return lcp > 0 ? first[len0 - lcp] : 0;
+  }
+  uint32_t lca_generic(const uint32_t *taxIDs, uint64_t n) const {   // the literal form; used for paths deeper than 256 levels
     if (n == 0) return 0;
     std::vector<std::vector<uint32_t>> paths;
     for (uint64_t k = 0; k < n; k++) {
@@ -257,6 +326,7 @@ int kslam_taxdb_open(const char *path, kslam_taxdb **out) {          // Taxonomy
   try {
     db = new kslam_taxdb();
     db->read_index(path);
+    db->finalize();
     *out = db;
     return KSLAM_OK;
   } catch (const std::exception &) { delete db; return KSLAM_ERR_ARG; }   // unreadable file or a line stoi rejects

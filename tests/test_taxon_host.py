@@ -226,3 +226,42 @@ def test_metagenomic_golden(pkg, golden, tmp_path):
     sam, (per_read, xml, abbreviated) = run_ours(pkg, ix, str(taxdb), [batch], True)
     assert sam == g["sam"].tobytes()
     assert per_read == g["per_read"].tobytes() and xml == g["xml"].tobytes() and abbreviated == g["abbreviated"].tobytes()
+
+
+def test_gene_lookup_index_equals_full_scan(pkg, golden):
+    """kslam_gene_index (binary search + running maximum of the CDS stops) against GenbankEntry::getGene's scan over every
+    gene, on gene tables made to be hostile: nested and abutting genes, many equal overlaps (the FIRST gene must win), an
+    entry whose genes are not ordered by start (keeps the scan), an entry without genes."""
+    g = golden("meta_mini.npz")
+    gbff = g["gbff"].tobytes()
+    n_entries = gbff.count(b"\n//\n")
+    rng = np.random.default_rng(4)
+    genes, offs, strings = [], [0], bytearray()
+    for e in range(n_entries):
+        n = 0 if e == 1 else 120
+        starts = np.sort(rng.integers(0, 5900, size=n)) if e != 2 else rng.integers(0, 5900, size=n)   # entry 2: unordered
+        for k in range(n):
+            length = int(rng.choice([30, 30, 30, 90, 400, 2500]))          # equal lengths give equal overlaps
+            rec = np.zeros(1, pkg.GENE_DT)[0]
+            rec["cds_start"], rec["cds_stop"], rec["gene_id"] = int(starts[k]), int(starts[k]) + length, 1000 * e + k
+            so = []
+            for txt in (b"g%d_%d" % (e, k), b"l%d_%d" % (e, k), b"P%d_%d" % (e, k), b"prod %d" % k, b"ref%d" % e):
+                so.append(len(strings)); strings += txt
+            so.append(len(strings))
+            rec["str_offs"] = so
+            genes.append(rec)
+        offs.append(len(genes))
+    genes = np.array(genes, dtype=pkg.GENE_DT)
+    import tempfile, pathlib
+    d = pathlib.Path(tempfile.mkdtemp())
+    (d / "db.gbff").write_bytes(gbff)
+    base = pkg.Index.parse_genbank([str(d / "db.gbff")])
+    tags = base.locus_tags
+    outs = []
+    for use_index in (True, False):
+        w = pkg.SamWriter(base.bases, base.offs, tags, taxonomy_ids=base.taxonomy_ids, report_cigar=True,
+                          genes=(genes, np.array(offs, np.uint64), np.frombuffer(bytes(strings), np.uint8)), gene_index=use_index)
+        assert bool(w.db.gene_index) == use_index
+        text, _ = w.batch(g["rb"], g["ro"], g["quals"], g["ro"], g["ids"], g["id_offs"], g["ov"], g["pool"], g["pairs"])
+        outs.append(text)
+    assert outs[0] == outs[1] and outs[0].count(b"\tXG:Z:") > 500
