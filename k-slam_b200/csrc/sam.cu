@@ -659,6 +659,10 @@ int kslam_batch_outputs(const kslam_sam_params *prm, const kslam_sam_db *db, con
       t1 = now();
       rc = sam_finish(c, rp, true, want_sam != 0, text, len, max_insert_size, taxdb, taxa);
       t2 = now();
+      // one small heap block per read pair: give them back on all threads instead of in the vector's destructor
+      parallel_ranges(std::min(threads, 64u), rp.size(), [&](uint32_t, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) std::vector<POv>().swap(rp[i].pairs);
+      });
     }
     if (trace) fprintf(stderr, "[kslam_sam] grouping %.1f ms, stages %.1f ms, release %.1f ms\n", (t1 - t0) * 1e3, (t2 - t1) * 1e3, (now() - t2) * 1e3);
     return rc;
