@@ -17,9 +17,11 @@
 #include "common.cuh"
 #include "host_stages.h"
 #include <algorithm>
+#include <atomic>
 #include <fstream>
 #include <stdexcept>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <unordered_map>
 
@@ -373,32 +375,92 @@ int kslam_taxa_create(kslam_taxa **out) {
 void kslam_taxa_destroy(kslam_taxa *taxa) { delete taxa; }
 
 // End of the run, SLAM.h:256-265: <out>_PerRead from the per-read results in batch order; then one record per taxon.
+// The reference does all of this on one thread; for runs of 10^8 read pairs that would take longer than the alignment.
+// Here only combineTaxonomies' sort stays sequential — its permutation decides which of two genes that compare equal
+// represents the group, so it has to be THE std::sort; it runs over (taxon, index) pairs of 8 bytes instead of the
+// records (the permutation of std::sort depends on the comparisons only). Everything else is per taxon or per read range
+// and runs on all host threads: the _PerRead text, the per-taxon merges, the sorts of the read names (parallel chunks +
+// merges; names that compare equal are identical, so any algorithm gives the reference's sequence) and the XML text.
 int kslam_taxa_results(kslam_taxa *taxa, const kslam_taxdb *taxdb, uint32_t num_reads, char **per_read, uint64_t *per_read_len,
                        char **xml, uint64_t *xml_len, char **abbreviated, uint64_t *abbreviated_len) {
   if (!taxa || !taxdb) return KSLAM_ERR_ARG;
   try {
     const GeneOps ops{&taxa->db};
+    uint32_t threads = std::max(1u, std::thread::hardware_concurrency());
+    if (threads > 64) threads = 64;
+    if (const char *e = getenv("KSLAM_HOST_THREADS")) threads = (uint32_t)std::max(1, atoi(e));
+    size_t par_min = 1u << 16;                             // smaller inputs are handled on one thread (KSLAM_HOST_PAR_MIN: test hook)
+    if (const char *e = getenv("KSLAM_HOST_PAR_MIN")) par_min = (size_t)strtoull(e, nullptr, 10);
+    const std::vector<PerRead> &items = taxa->items;
     auto id_of = [&](const PerRead &r) { return std::string_view(taxa->ids.data() + r.id_off, r.id_len); };
+    auto join = [](std::vector<std::string> &parts, char **text, uint64_t *len) {
+      size_t total = 0;
+      for (auto &p : parts) total += p.size();
+      char *buf = (char *)malloc(total + 1);
+      if (!buf) return false;
+      size_t at = 0;
+      for (auto &p : parts) { memcpy(buf + at, p.data(), p.size()); at += p.size(); }
+      buf[total] = 0;
+      *text = buf;
+      if (len) *len = total;
+      return true;
+    };
     if (per_read) {                                        // writePerReadResults, MetagenomicResults.h:455-463
-      std::string t;
-      for (const PerRead &r : taxa->items)
-        if (r.has_read) { t += id_of(r); t.push_back('\t'); t += std::to_string(r.taxonomyID); t.push_back('\n'); }
-      *per_read = dup_text(t);
-      if (per_read_len) *per_read_len = t.size();
-      if (!*per_read) return KSLAM_ERR_NOMEM;
+      std::vector<std::string> parts(threads);
+      parallel_ranges(threads, items.size(), [&](uint32_t t, size_t lo, size_t hi) {
+        std::string &o = parts[t];
+        for (size_t i = lo; i < hi; i++)
+          if (items[i].has_read) { o += id_of(items[i]); o.push_back('\t'); o += std::to_string(items[i].taxonomyID); o.push_back('\n'); }
+      });
+      if (!join(parts, per_read, per_read_len)) return KSLAM_ERR_NOMEM;
     }
     if (!xml && !abbreviated) return KSLAM_OK;
     // combineTaxonomies, :149-176. The loop skips the first element and starts with testTaxID = 0: reads without a taxon
     // (id 0) sort first and are dropped, and when there are none the very first record of the sorted vector is left out
     // of its range (or its taxon dropped, if it was alone) — kept as is.
-    std::vector<PerRead> sorted(taxa->items);
-    std::sort(sorted.begin(), sorted.end(), [](const PerRead &i, const PerRead &j) { return i.taxonomyID < j.taxonomyID; });
-    std::vector<Combined> results;
-    auto combine = [&](size_t begin, size_t end) {         // combineRangeOfIdentifiedTaxonomy, :117-143
-      Combined t;
+    struct Key { uint32_t taxonomyID, index; };
+    std::vector<Key> sorted(items.size());
+    parallel_ranges(threads, items.size(), [&](uint32_t, size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; i++) sorted[i] = Key{items[i].taxonomyID, (uint32_t)i};
+    });
+    if (items.size() > UINT32_MAX) return KSLAM_ERR_ARG;
+    std::sort(sorted.begin(), sorted.end(), [](const Key &i, const Key &j) { return i.taxonomyID < j.taxonomyID; });
+    std::vector<std::pair<size_t, size_t>> ranges;          // [begin, end) of every taxon that is kept
+    if (!sorted.empty()) {
+      uint32_t testTaxID = 0;
+      size_t start = 0;
+      for (size_t tax = 1; tax < sorted.size(); tax++)
+        if (sorted[tax].taxonomyID != testTaxID) {
+          if (testTaxID != 0) ranges.push_back({start, tax});
+          testTaxID = sorted[tax].taxonomyID;
+          start = tax;
+        }
+      if (sorted[start].taxonomyID != 0) ranges.push_back({start, sorted.size()});
+    }
+    std::vector<Combined> results(ranges.size());
+    // sorted sequence of a big vector on all threads: sorted chunks, then rounds of pairwise merges
+    auto sort_views = [&](std::vector<std::string_view> &v) {
+      const size_t n = v.size();
+      if (threads <= 1 || n < par_min || n < 4 * (size_t)threads) { std::sort(v.begin(), v.end()); return; }
+      uint32_t chunks = 1;
+      while (chunks * 2 <= threads) chunks *= 2;
+      auto cut = [&](uint32_t c) { return n * c / chunks; };
+      parallel_threads(chunks, [&](uint32_t c) { std::sort(v.begin() + cut(c), v.begin() + cut(c + 1)); });
+      for (uint32_t width = 1; width < chunks; width *= 2)
+        parallel_threads(chunks / (2 * width), [&](uint32_t m) {
+          const uint32_t c = m * 2 * width;
+          std::inplace_merge(v.begin() + cut(c), v.begin() + cut(c + width), v.begin() + cut(c + 2 * width));
+        });
+    };
+    auto combine = [&](size_t which, bool inner_parallel) { // combineRangeOfIdentifiedTaxonomy, :117-143
+      Combined &t = results[which];
+      const size_t begin = ranges[which].first, end = ranges[which].second;
       t.taxonomyID = sorted[begin].taxonomyID;
+      size_t n_genes = 0;
+      for (size_t k = begin; k < end; k++) n_genes += items[sorted[k].index].n_genes;
+      t.genes.reserve(n_genes); t.reads.reserve(end - begin);
       for (size_t k = begin; k < end; k++) {
-        const PerRead &r = sorted[k];
+        const PerRead &r = items[sorted[k].index];
         t.genes.insert(t.genes.end(), taxa->genes.begin() + r.gene_off, taxa->genes.begin() + r.gene_off + r.n_genes);
         if (r.has_read) t.reads.push_back(id_of(r));
       }
@@ -412,39 +474,41 @@ int kslam_taxa_results(kslam_taxa *taxa, const kslam_taxdb *taxdb, uint32_t num_
         }
         t.genes.resize(std::distance(t.genes.begin(), ++result));
       }
-      results.push_back(std::move(t));
-    };
-    if (!sorted.empty()) {
-      uint32_t testTaxID = 0;
-      size_t start = 0;
-      for (size_t tax = 1; tax < sorted.size(); tax++)
-        if (sorted[tax].taxonomyID != testTaxID) {
-          if (testTaxID != 0) combine(start, tax);
-          testTaxID = sorted[tax].taxonomyID;
-          start = tax;
+      // sortResults, :254-275, the per-entry part (the order of the entries is decided below)
+      if (inner_parallel) sort_views(t.reads); else std::sort(t.reads.begin(), t.reads.end());
+      auto by_count = [&](const GeneHit &i, const GeneHit &j) {
+        if (i.count == j.count) {
+          if (i.g->cds_start == j.g->cds_start) return ops.s(i.g, GENE_LOCUS) < ops.s(j.g, GENE_LOCUS);
+          return i.g->cds_start < j.g->cds_start;
         }
-      if (sorted[start].taxonomyID != 0) combine(start, sorted.size());
-    }
-    auto sort_results = [&]() {                            // sortResults, :254-275
-      std::sort(results.begin(), results.end(), [](const Combined &i, const Combined &j) {
-        if (i.reads.size() == j.reads.size()) return i.taxonomyID < j.taxonomyID;
-        return i.reads.size() > j.reads.size();
-      });
-      for (auto &entry : results) {
-        std::sort(entry.reads.begin(), entry.reads.end());
-        std::sort(entry.genes.begin(), entry.genes.end(), [&](const GeneHit &i, const GeneHit &j) {
-          if (i.count == j.count) {
-            if (i.g->cds_start == j.g->cds_start) return ops.s(i.g, GENE_LOCUS) < ops.s(j.g, GENE_LOCUS);
-            return i.g->cds_start < j.g->cds_start;
-          }
-          return i.count > j.count;
-        });
-      }
+        return i.count > j.count;
+      };
+      std::sort(t.genes.begin(), t.genes.end(), by_count);  // (writeAbbreviatedResultsFile sorts once more AFTER the XML is out: no visible effect)
     };
-    sort_results();                                        // writeResults sorts, writeAbbreviatedResultsFile sorts again
+    // taxa with very many reads one at a time with all threads inside; the rest handed out one taxon per thread
+    const size_t big = std::max<size_t>(4 * par_min, getenv("KSLAM_HOST_PAR_MIN") ? 0 : sorted.size() / 8);
+    std::vector<size_t> small;
+    for (size_t i = 0; i < ranges.size(); i++) {
+      if (ranges[i].second - ranges[i].first >= big) combine(i, true);
+      else small.push_back(i);
+    }
+    {
+      std::atomic<size_t> next{0};
+      parallel_threads(small.size() < 2 ? 1u : threads, [&](uint32_t) { for (size_t k = next++; k < small.size(); k = next++) combine(small[k], false); });
+    }
+    auto by_size = [](const Combined &i, const Combined &j) {
+      if (i.reads.size() == j.reads.size()) return i.taxonomyID < j.taxonomyID;
+      return i.reads.size() > j.reads.size();
+    };
+    std::sort(results.begin(), results.end(), by_size);     // a total order (ids are unique): sorting twice changes nothing
     if (xml) {                                             // getXML, :302-369
-      std::string o;
-      for (const Combined &entry : results) {
+      std::vector<std::string> parts(results.size());
+      auto reads_block = [&](const Combined &entry, size_t lo, size_t hi, std::string &o) {
+        for (size_t i = lo; i < hi; i++) { o += "    <read>"; xml_escape(o, entry.reads[i]); o += "</read>\n"; }
+      };
+      auto entry_xml = [&](size_t which, bool inner_parallel) {
+        const Combined &entry = results[which];
+        std::string &o = parts[which];
         o += "<taxon>\n  <abundance numReads=\"";
         o += std::to_string(entry.reads.size());
         o += "\">";
@@ -469,15 +533,23 @@ int kslam_taxa_results(kslam_taxa *taxa, const kslam_taxdb *taxdb, uint32_t num_
           o += "</gene>\n";
         }
         o += "  </genes>\n  <reads>\n";
-        for (auto &read : entry.reads) { o += "    <read>"; xml_escape(o, read); o += "</read>\n"; }
+        if (inner_parallel) {
+          std::vector<std::string> sub(threads);
+          parallel_ranges(threads, entry.reads.size(), [&](uint32_t t, size_t lo, size_t hi) { reads_block(entry, lo, hi, sub[t]); });
+          for (auto &x : sub) o += x;
+        } else reads_block(entry, 0, entry.reads.size(), o);
         o += "  </reads>\n</taxon>\n";
+      };
+      std::vector<size_t> small_x;
+      for (size_t i = 0; i < results.size(); i++) {
+        if (results[i].reads.size() >= big) entry_xml(i, true);
+        else small_x.push_back(i);
       }
-      *xml = dup_text(o);
-      if (xml_len) *xml_len = o.size();
-      if (!*xml) return KSLAM_ERR_NOMEM;
+      std::atomic<size_t> next{0};
+      parallel_threads(small_x.size() < 2 ? 1u : threads, [&](uint32_t) { for (size_t k = next++; k < small_x.size(); k = next++) entry_xml(small_x[k], false); });
+      if (!join(parts, xml, xml_len)) return KSLAM_ERR_NOMEM;
     }
     if (abbreviated) {                                     // writeAbbreviatedResultsFile, :237-249 (ostream << double = %g)
-      sort_results();
       std::string o;
       char num[64];
       for (const Combined &entry : results) {

@@ -165,13 +165,16 @@ def run_ours(pkg, ix, taxdb_path, batches, want_sam, paired=True, **kw):
 
 
 @needs_ref
-@pytest.mark.parametrize("want_sam", [True, False])
-@pytest.mark.parametrize("paired", [True, False])
-def test_metagenomic_outputs_equal_reference(pkg, tmp_path, want_sam, paired):
+@pytest.mark.parametrize("want_sam,paired,par_min", [(True, True, None), (False, True, None), (True, False, None), (False, False, None),
+                                                     (True, True, 8), (False, False, 8)])
+def test_metagenomic_outputs_equal_reference(pkg, tmp_path, want_sam, paired, par_min, monkeypatch):
     """Two batches through SLAM.h:209-265 in the reference (database = what ITS createIndexFromGBFF parsed) and through
     kslam_batch_outputs + kslam_taxa_results on the same alignments: SAM text with XG / XP / XR / XT, _PerRead, XML,
     _abbreviated byte for byte. One OpenMP thread in the reference: combineTaxonomies' parallel sort is thread-count
-    dependent on ties (include/kslam.h)."""
+    dependent on ties (include/kslam.h). par_min forces the all-threads forms of the host stages and of the end-of-run merge
+    (parallel read-name sorts, XML blocks) onto this small run."""
+    if par_min is not None:
+        monkeypatch.setenv("KSLAM_HOST_PAR_MIN", str(par_min))
     gb, go, _, _, _, _, taxdb, paths = make_db(pkg, tmp_path, n_strains=20, length=12_000)
     L = T.ref()
     assert T.ref_parse_index(0, paths, taxdb) is not None
