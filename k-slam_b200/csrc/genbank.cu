@@ -12,12 +12,14 @@
 #include "common.cuh"
 #include "host_stages.h"
 #include <algorithm>
+#include <atomic>
 #include <climits>
 #include <ctype.h>
 #include <stdexcept>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <thread>
 
 namespace {
 
@@ -185,39 +187,84 @@ extern "C" {
 const char *kslam_index_error(void) { return g_error.c_str(); }
 void kslam_index_free(kslam_index *index) { delete index; }
 
-int kslam_index_parse_genbank(const char *const *paths, uint64_t n_paths, kslam_index **out) {   // createIndexFromGBFF, :481-527
+// One record: the lines of data[from, to), which end with the "//" line (or with the end of the file, for whatever follows
+// the last "//": parsed like the reference does, then dropped). Returns true when the "//" line closed the entry.
+static bool parse_genbank_record(const std::string &data, size_t from, size_t to, Entry &entry) {
+  std::string line, section;
+  for (size_t pos = from; pos < to;) {                     // std::getline: '\n' ends a line, a '\r' stays in it
+    size_t nl = data.find('\n', pos);
+    if (nl == std::string::npos || nl > to) nl = to;
+    line.assign(data, pos, nl - pos);
+    pos = nl + 1;
+    if (line.size() == 0) continue;
+    const size_t startPos = line.find_first_not_of(' ');
+    if (startPos < 12) {
+      parse_section(section, entry);
+      section = line;
+      if (line == "//") {
+        std::sort(entry.genes.begin(), entry.genes.end(), [](const Gene &i, const Gene &j) {
+          if (i.start == j.start) return i.proteinID.size() > j.proteinID.size();
+          return i.start < j.start;
+        });
+        auto it = std::unique(entry.genes.begin(), entry.genes.end(), [](const Gene &i, const Gene &j) { return i.start == j.start; });
+        entry.genes.resize(std::distance(entry.genes.begin(), it));
+        return true;
+      }
+    } else if (startPos == std::string::npos) continue;
+    else section.append(line.substr(startPos - 1));        // continuation line: one space + its text
+  }
+  return false;
+}
+
+// createIndexFromGBFF, :481-527. The reference walks every file line by line with one entry and one section in flight; a
+// line that is exactly "//" pushes the entry and starts a fresh one, and the section it leaves behind ("//") parses to
+// nothing — so records are independent and are parsed on all host threads here, files taken in groups of at most ~1 GB,
+// entries appended in file order.
+int kslam_index_parse_genbank(const char *const *paths, uint64_t n_paths, kslam_index **out) {
   if (!paths || !out) return KSLAM_ERR_ARG;
   kslam_index *index = nullptr;
   try {
     index = new kslam_index();
-    for (uint64_t f = 0; f < n_paths; f++) {
-      std::string data;
-      if (!read_file(paths[f], data)) throw std::runtime_error(std::string("unable to open index file ") + paths[f]);
-      std::string line, section;
-      Entry entry;
-      for (size_t pos = 0; pos < data.size();) {           // std::getline: '\n' ends a line, a '\r' stays in it
-        size_t nl = data.find('\n', pos);
-        if (nl == std::string::npos) nl = data.size();
-        line.assign(data, pos, nl - pos);
-        pos = nl + 1;
-        if (line.size() == 0) continue;
-        const size_t startPos = line.find_first_not_of(' ');
-        if (startPos < 12) {
-          parse_section(section, entry);
-          section = line;
-          if (line == "//") {
-            std::sort(entry.genes.begin(), entry.genes.end(), [](const Gene &i, const Gene &j) {
-              if (i.start == j.start) return i.proteinID.size() > j.proteinID.size();
-              return i.start < j.start;
-            });
-            auto it = std::unique(entry.genes.begin(), entry.genes.end(), [](const Gene &i, const Gene &j) { return i.start == j.start; });
-            entry.genes.resize(std::distance(entry.genes.begin(), it));
-            index->add(entry);
-            entry = Entry();
-          }
-        } else if (startPos == std::string::npos) continue;
-        else section.append(line.substr(startPos - 1));    // continuation line: one space + its text
+    const uint32_t threads = std::min(64u, std::max(1u, std::thread::hardware_concurrency()));
+    for (uint64_t f0 = 0; f0 < n_paths;) {
+      std::vector<std::string> datas;
+      size_t group_bytes = 0;
+      uint64_t f1 = f0;
+      while (f1 < n_paths && (f1 == f0 || group_bytes < (1ull << 30))) {
+        datas.emplace_back();
+        if (!read_file(paths[f1], datas.back())) throw std::runtime_error(std::string("unable to open index file ") + paths[f1]);
+        group_bytes += datas.back().size();
+        f1++;
       }
+      struct Chunk { uint32_t file; size_t from, to; Entry entry; bool closed = false; std::string error; };
+      std::vector<Chunk> chunks;
+      for (uint32_t k = 0; k < datas.size(); k++) {
+        const std::string &d = datas[k];
+        size_t from = 0;
+        for (size_t p = d.find("//"); p != std::string::npos; p = d.find("//", p + 2)) {
+          const bool line_start = p == 0 || d[p - 1] == '\n', line_end = p + 2 == d.size() || d[p + 2] == '\n';
+          if (!line_start || !line_end) continue;
+          const size_t to = std::min(p + 3, d.size());
+          if (p < from) continue;                          // "///..." overlap guard
+          chunks.push_back(Chunk{k, from, to});
+          from = to;
+        }
+        if (from < d.size()) chunks.push_back(Chunk{k, from, d.size()});   // after the last "//": parsed, never pushed
+      }
+      std::atomic<size_t> next{0};
+      kslam_host::parallel_threads(chunks.size() < 2 ? 1u : threads, [&](uint32_t) {
+        for (size_t c = next++; c < chunks.size(); c = next++) {
+          Chunk &ch = chunks[c];
+          try { ch.closed = parse_genbank_record(datas[ch.file], ch.from, ch.to, ch.entry); }
+          catch (const std::exception &e) { ch.error = e.what(); if (ch.error.empty()) ch.error = "parse error"; }
+        }
+      });
+      for (Chunk &ch : chunks) {
+        if (!ch.error.empty()) throw std::runtime_error(ch.error + " in " + paths[f0 + ch.file]);
+        if (ch.closed) index->add(ch.entry);
+        ch.entry = Entry();
+      }
+      f0 = f1;
     }
     *out = index;
     return KSLAM_OK;
