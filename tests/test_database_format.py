@@ -38,3 +38,30 @@ def test_rejects_garbage(pkg, tmp_path):
         p.write_bytes(blob)
         with pytest.raises(db.ArchiveError):
             db.read_database(p)
+
+
+def test_archive_header_constants_match_a_boost_library(pkg, tmp_path):
+    """The one piece of Boost.Serialization present in this image is a header-less libboost_serialization.so (1.78, bundled
+    with Nsight Compute). It exports the archive signature and library version: the header our writers emit is
+    `<len(signature)> <signature> <version>` with that signature, and the readers accept that library's version."""
+    import ctypes as C
+    import glob
+    from kslam_b200 import database
+    libs = glob.glob("/opt/nvidia/nsight-compute/*/host/*/libboost_serialization.so.1.78.0")
+    if not libs:
+        pytest.skip("no Boost serialization library in this image")
+    L = C.CDLL(libs[0])
+    sig = L._ZN5boost7archive23BOOST_ARCHIVE_SIGNATUREEv
+    sig.restype = C.c_char_p
+    ver = L._ZN5boost7archive21BOOST_ARCHIVE_VERSIONEv          # returns library_version_type through a hidden pointer
+    ver.restype, ver.argtypes = C.c_void_p, [C.c_void_p]
+    buf = (C.c_uint16 * 8)()
+    ver(C.byref(buf))
+    signature, version = sig(), int(buf[0])
+    assert database.HEADER == b"%d %s" % (len(signature), signature) and version >= 17
+    path = str(tmp_path / "database")
+    database.write_database(path, [dict(bases=b"ACGT", locus_tag=b"x")], libver=version)
+    assert open(path, "rb").read().startswith(b"22 serialization::archive %d 0 0" % version)
+    assert database.read_database(path)[0]["bases"] == b"ACGT"
+    ix = pkg.Index.read(path)
+    assert ix.n_entries == 1 and ix.bases.tobytes() == b"ACGT" and ix.locus_tags == [b"x"]
