@@ -283,7 +283,7 @@ int kslam_taxa_results(kslam_taxa *taxa, const kslam_taxdb *taxdb, uint32_t num_
  * kslam_index = GenbankIndex (GenbankTools.h:189-207). kslam_index_parse_genbank = createIndexFromGBFF (:481-527) with
  * parseSection (:348-476); kslam_index_parse_fasta = createIndexFromFASTA (:224-260); kslam_index_read / _write = the Boost
  * text archive of getIndexFromBoostSerial / writeIndexToBoostSerial (:201-205,336-344; grammar in SURVEY.md App. B.1 —
- * parity of the archive bytes is unpinned, no Boost in the build image). kslam_index_db fills a kslam_sam_db view whose
+ * the bytes are pinned against the real Boost.Serialization library, tests/test_database_format.py). kslam_index_db fills a kslam_sam_db view whose
  * pointers stay valid until kslam_index_free. */
 typedef struct kslam_index kslam_index;
 int kslam_index_parse_genbank(const char *const *paths, uint64_t n_paths, kslam_index **out);

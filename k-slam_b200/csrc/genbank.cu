@@ -6,9 +6,11 @@
 // The parsers follow the reference field by field, including what it does by accident (the taxon id is found because
 // stoul stops at the closing quote after an unsigned wrap-around of the substring length; a qualifier found anywhere in
 // a feature's text wins; every line of the ORIGIN block is a "section" of its own whose tag is the base counter).
-// The archive grammar is the one SURVEY.md App. B.1 spells out; this image has no Boost, so the bytes of a real
-// archive could not be compared ("parity unpinned" for the archive, pinned for the parsers: tests/test_taxon_host.py
-// runs the reference's own createIndexFromGBFF through oracle/_ref).
+// The archive grammar is the one SURVEY.md App. B.1 spells out. This image has no Boost headers (the reference's writer cannot
+// be compiled here), but the REAL Boost.Serialization 1.78 library is present as a header-less .so: oracle/boost_archive_probe.cpp
+// drives it, and tests/test_database_format.py checks this file's writer against its output byte for byte and this file's reader
+// on its archives. The parsers are pinned against the reference's own createIndexFromGBFF / createIndexFromFASTA
+// (tests/test_taxon_host.py, through oracle/_ref).
 #include "common.cuh"
 #include "host_stages.h"
 #include <algorithm>

@@ -11,9 +11,11 @@ Text-archive grammar: space-separated tokens after the header `22 serialization:
 every class type is preceded by its class information `<tracking> <version>` = `0 0`; `std::vector<T>` is
 `<count> <item_version>` then the items; `std::string` is `<len>`, one space, then exactly `len` raw bytes; bool is 0/1.
 
-PARITY UNPINNED: this image has no Boost, so neither the reference's writer nor a real archive could be run against this
-module; it follows Boost.Serialization's documented format (and SURVEY's worked example, which is a test vector here) and
-round-trips its own output. Validate against a real `SLAM --parse-fasta` database before relying on it.
+Parity: this image has no Boost headers, so the reference's own writer cannot be compiled here; the format is pinned
+against the REAL Boost.Serialization library instead — oracle/boost_archive_probe.cpp links the header-less
+libboost_serialization.so (1.78) that ships inside Nsight Compute and lets its save_object / text_oarchive machinery write
+the same index: tests/test_database_format.py compares the bytes (GenBank database with genes, FASTA database, empty
+database; only the library-version token differs) and reads the library's archive back.
 """
 from __future__ import annotations
 

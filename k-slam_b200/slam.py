@@ -56,7 +56,7 @@ def parse_fasta(paths):
 
 def load_database(fasta_paths=None, db_dir=None):
     """The genomes either from FASTA files (parsed as --parse-fasta does) or from a SLAM database directory (`--db DIR`:
-    DIR/database, database.py — format parity unpinned, see there). -> (bases, offs, locus tags, taxonomy ids or None)"""
+    DIR/database, database.py). -> (bases, offs, locus tags, taxonomy ids or None)"""
     if db_dir:
         import os
         from . import database

@@ -1,5 +1,6 @@
-"""CPU tier: DIR/database (Boost text archive of GenbankIndex). PARITY UNPINNED — no Boost in this image;
-the vectors below are SURVEY's worked example and this module's own round trip."""
+"""CPU tier: DIR/database (Boost text archive of GenbankIndex): SURVEY's worked example, round trips, and the
+bytes the REAL Boost.Serialization library writes for the same index (oracle/boost_archive_probe.cpp over the header-less
+libboost_serialization.so 1.78 that ships inside Nsight Compute — this image has no Boost headers)."""
 import numpy as np
 import pytest
 
@@ -65,3 +66,56 @@ def test_archive_header_constants_match_a_boost_library(pkg, tmp_path):
     assert database.read_database(path)[0]["bases"] == b"ACGT"
     ix = pkg.Index.read(path)
     assert ix.n_entries == 1 and ix.bases.tobytes() == b"ACGT" and ix.locus_tags == [b"x"]
+
+
+def _probe():
+    import os
+    import _lib as T
+    p = os.path.join(T.ORACLE_DIR, "_ref", "boost_archive_probe")
+    return p if os.path.exists(p) else None
+
+
+def _dump(entries):
+    """The index dump format of oracle/ref_driver.cpp / boost_archive_probe.cpp from database.read_database's dicts."""
+    F, R = b"\x1f", b"\x1e"
+    out = []
+    for e in entries:
+        out.append(F.join([b"E", e["locus_tag"], b"%d" % e["taxonomy_id"], b"%d" % e["genbank_id"], b"%d" % int(e["is_plasmid"]),
+                           b"%d" % int(e["is_16s"]), e["bases"]]) + R)
+        for g in e["genes"]:
+            out.append(F.join([b"G", g["gene_name"], g["locus_tag"], g["protein_id"], g["product"], g["reference_sequence"], b"%d" % g["gene_id"],
+                               b"%d" % g["start"], b"%d" % g["stop"], b"%d" % int(g["complement"])]) + R)
+    return b"".join(out)
+
+
+@pytest.mark.skipif(_probe() is None, reason="needs oracle/_ref/boost_archive_probe (built where the Boost serialization library exists)")
+def test_archive_bytes_equal_the_real_boost_library(pkg, tmp_path):
+    """DIR/database pinned: the same index written by kslam_index_write / database.write_database and by the REAL
+    Boost.Serialization 1.78 library (oracle/boost_archive_probe.cpp drives its save_object / text_oarchive machinery) —
+    byte for byte, the library version in the header aside — and the real library's archive read back by both readers.
+    GenBank database (genes, taxonomy ids, GI numbers, products with spaces), FASTA database (no genes), empty database."""
+    import subprocess
+    import _lib as T
+    from kslam_b200 import database
+    from test_taxon_host import make_db
+    *_, paths = make_db(pkg, tmp_path, n_strains=4, length=3000)
+    fa = tmp_path / "g.fa"
+    fa.write_bytes(b">a one\nacgt\nNNAC\n>b two\nGGGG\n>c x\nAC GT\n")
+    empty = tmp_path / "empty.fa"
+    empty.write_bytes(b"")
+    for name, ix in (("genbank", pkg.Index.parse_genbank(paths)), ("fasta", pkg.Index.parse_fasta([str(fa)])), ("empty", pkg.Index.parse_fasta([str(empty)]))):
+        ours, real, dump = tmp_path / (name + ".ours"), tmp_path / (name + ".real"), tmp_path / (name + ".dump")
+        ix.write(str(ours))
+        entries = database.read_database(str(ours))
+        dump.write_bytes(_dump(entries))
+        subprocess.run([_probe(), str(dump), str(real)], check=True)
+        want = real.read_bytes()
+        assert want.startswith(b"22 serialization::archive 19 ")
+        assert ours.read_bytes().replace(b"archive 17 ", b"archive 19 ", 1) == want, name
+        py = tmp_path / (name + ".py")
+        database.write_database(str(py), entries, libver=19)
+        assert py.read_bytes() == want, name
+        assert database.read_database(str(real)) == entries
+        assert T.index_entries(pkg.Index.read(str(real))) == T.index_entries(ix)
+        if name == "genbank":
+            assert sum(len(e["genes"]) for e in entries) > 4 and any(e["genbank_id"] for e in entries) and any(b" " in g["product"] for e in entries for g in e["genes"])

@@ -129,7 +129,7 @@ def test_genbank_and_fasta_parsers_equal_reference(pkg, tmp_path):
 
 
 def test_database_archive_round_trip(pkg, tmp_path):
-    """DIR/database: the C++ writer / reader agree with database.py (both follow SURVEY App. B.1; archive parity unpinned)."""
+    """DIR/database: the C++ writer / reader agree with database.py (the bytes are pinned against the real Boost library in tests/test_database_format.py)."""
     from kslam_b200 import database
     *_, paths = make_db(pkg, tmp_path, n_strains=4, length=3000)
     ix = pkg.Index.parse_genbank(paths)
