@@ -101,10 +101,34 @@ def meta_fixture(name):
     print(name, "pairs", len(pairs), "sam", len(sam), "xml", len(xml), "taxa", xml.count(b"<taxon>"))
 
 
+def boost_archive_fixture(name):
+    """A small GenBank index written by the REAL Boost.Serialization library (oracle/_ref/boost_archive_probe): the GenBank text
+    and the archive bytes."""
+    import pathlib
+    import subprocess
+    import tempfile
+    from test_taxon_host import make_db
+    from test_database_format import _dump, _probe
+    pkg = T.load_pkg()
+    from kslam_b200 import database
+    tmp = pathlib.Path(tempfile.mkdtemp())
+    *_, paths = make_db(pkg, tmp, n_strains=3, length=2500, files=1)
+    ix = pkg.Index.parse_genbank(paths)
+    ix.write(str(tmp / "ours"))
+    (tmp / "dump").write_bytes(_dump(database.read_database(str(tmp / "ours"))))
+    subprocess.run([_probe(), str(tmp / "dump"), str(tmp / "real")], check=True)
+    u = lambda b: np.frombuffer(b, np.uint8)   # noqa: E731
+    np.savez_compressed(os.path.join(HERE, name), gbff=u(open(paths[0], "rb").read()), archive=u((tmp / "real").read_bytes()))
+    print(name, "archive bytes", len((tmp / "real").read_bytes()))
+
+
 def main():
     sys.path.insert(0, os.path.dirname(HERE))
     if len(sys.argv) > 1 and sys.argv[1] == "meta":
         return meta_fixture("meta_mini.npz")
+    if len(sys.argv) > 1 and sys.argv[1] == "boost":
+        return boost_archive_fixture("database_boost178.npz")
+    boost_archive_fixture("database_boost178.npz")
     meta_fixture("meta_mini.npz")
     fastq_fixture("fastq_reader.npz")
     sam_fixture("sam_config1_mini.npz")

@@ -119,3 +119,20 @@ def test_archive_bytes_equal_the_real_boost_library(pkg, tmp_path):
         assert T.index_entries(pkg.Index.read(str(real))) == T.index_entries(ix)
         if name == "genbank":
             assert sum(len(e["genes"]) for e in entries) > 4 and any(e["genbank_id"] for e in entries) and any(b" " in g["product"] for e in entries for g in e["genes"])
+
+
+def test_archive_golden_from_the_boost_library(pkg, golden, tmp_path):
+    """The same check from a fixture (tests/golden/make_golden.py boost): an archive the real Boost 1.78 library wrote for a
+    small GenBank database travels with the repo; parsing the GenBank text and writing the index must give those bytes."""
+    g = golden("database_boost178.npz")
+    gbff = tmp_path / "db.gbff"
+    gbff.write_bytes(g["gbff"].tobytes())
+    ix = pkg.Index.parse_genbank([str(gbff)])
+    out = tmp_path / "database"
+    ix.write(str(out))
+    want = g["archive"].tobytes()
+    assert out.read_bytes().replace(b"archive 17 ", b"archive 19 ", 1) == want and len(want) > 5000
+    import _lib as T
+    real = tmp_path / "real"
+    real.write_bytes(want)
+    assert T.index_entries(pkg.Index.read(str(real))) == T.index_entries(ix)
