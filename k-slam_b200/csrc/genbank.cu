@@ -8,8 +8,9 @@
 // a feature's text wins; every line of the ORIGIN block is a "section" of its own whose tag is the base counter).
 // The archive grammar is the one SURVEY.md App. B.1 spells out. This image has no Boost headers (the reference's writer cannot
 // be compiled here), but the REAL Boost.Serialization 1.78 library is present as a header-less .so: oracle/boost_archive_probe.cpp
-// drives it, and tests/test_database_format.py checks this file's writer against its output byte for byte and this file's reader
-// on its archives. The parsers are pinned against the reference's own createIndexFromGBFF / createIndexFromFASTA
+// drives it, oracle/ref_shim_boost runs the reference's own writeIndexToBoostSerial / getIndexFromBoostSerial on it, and
+// tests/test_database_format.py checks this file's writer against both byte for byte, this file's reader on their archives, and the
+// reference's reader on this file's archives. The parsers are pinned against the reference's own createIndexFromGBFF / createIndexFromFASTA
 // (tests/test_taxon_host.py, through oracle/_ref).
 #include "common.cuh"
 #include "host_stages.h"

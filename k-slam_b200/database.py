@@ -14,8 +14,9 @@ every class type is preceded by its class information `<tracking> <version>` = `
 Parity: this image has no Boost headers, so the reference's own writer cannot be compiled here; the format is pinned
 against the REAL Boost.Serialization library instead — oracle/boost_archive_probe.cpp links the header-less
 libboost_serialization.so (1.78) that ships inside Nsight Compute and lets its save_object / text_oarchive machinery write
-the same index: tests/test_database_format.py compares the bytes (GenBank database with genes, FASTA database, empty
-database; only the library-version token differs) and reads the library's archive back.
+the same index, and oracle/ref_shim_boost lets the reference's OWN writeIndexToBoostSerial / getIndexFromBoostSerial run on
+that library: tests/test_database_format.py compares the bytes (only the library-version token differs) and has the
+reference's reader load our files.
 """
 from __future__ import annotations
 

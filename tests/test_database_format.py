@@ -136,3 +136,86 @@ def test_archive_golden_from_the_boost_library(pkg, golden, tmp_path):
     real = tmp_path / "real"
     real.write_bytes(want)
     assert T.index_entries(pkg.Index.read(str(real))) == T.index_entries(ix)
+
+
+def _refdb():
+    import os
+    import _lib as T
+    p = os.path.join(T.ORACLE_DIR, "_ref", "libkslam_refdb.so")
+    return p if os.path.exists(p) else None
+
+
+@pytest.mark.skipif(_refdb() is None, reason="needs oracle/_ref/libkslam_refdb.so (reference sources + the Boost serialization library)")
+def test_database_file_equals_the_reference_writing_through_real_boost(pkg, tmp_path):
+    """The reference's OWN `--parse-genbank` / `--parse-fasta` code path end to end — createIndexFromGBFF / createIndexFromFASTA
+    and its unmodified writeIndexToBoostSerial, with boost::archive::text_oarchive forwarding to the real Boost 1.78 library
+    (oracle/ref_shim_boost) — against the file `SLAM --parse-genbank` / `--parse-fasta` writes: byte for byte, the
+    library-version token aside. Member order, class nesting and every parsed field come from the reference's code here."""
+    import ctypes as C
+    import os
+    import subprocess
+    import _lib as T
+    from test_taxon_host import make_db
+    L = C.CDLL(_refdb())
+    L.kref_write_database.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_uint64, C.c_char_p]
+    *_, taxdb, paths = make_db(pkg, tmp_path, n_strains=6, length=5000)
+    fa1, fa2 = tmp_path / "a.fa", tmp_path / "b.fa"
+    fa1.write_bytes(b"acgtn\n>g1 first genome\nACGT\nacgtnn\n\n>nospace\nTTTT\n>g3 \n>g4 empty above\nGG\n")
+    fa2.write_bytes(b">c1 crlf\r\nACGT\r\nAC\r\n>c2 cr only\rGGCC\rTT")
+    exe = os.path.join(T.ROOT, "k-slam_b200", "SLAM")
+    cwd = os.getcwd()
+    work = tmp_path / "refcwd"
+    work.mkdir()
+    (work / "taxDB").write_bytes(open(taxdb, "rb").read())          # createIndexFromGBFF opens ./taxDB (GenbankTools.h:483)
+    for kind, flag, files in ((0, "--parse-genbank", paths), (1, "--parse-fasta", [str(fa1), str(fa2)])):
+        ref_out, our_out = str(tmp_path / f"ref{kind}"), str(tmp_path / f"ours{kind}")
+        arr = (C.c_char_p * len(files))(*[os.fsencode(f) for f in files])
+        os.chdir(work)
+        try:
+            assert L.kref_write_database(kind, arr, len(files), ref_out.encode()) == 0
+        finally:
+            os.chdir(cwd)
+        assert subprocess.run([exe, flag, "--output-file", our_out, *files], cwd=tmp_path).returncode == 0
+        want, got = open(ref_out, "rb").read(), open(our_out, "rb").read()
+        assert want.startswith(b"22 serialization::archive 19 ") and len(want) > 100
+        assert got.replace(b"archive 17 ", b"archive 19 ", 1) == want, flag
+        assert T.index_entries(pkg.Index.read(ref_out)) == T.index_entries(pkg.Index.read(our_out))
+
+
+@pytest.mark.skipif(_refdb() is None, reason="needs oracle/_ref/libkslam_refdb.so (reference sources + the Boost serialization library)")
+def test_the_reference_reads_our_database_through_real_boost(pkg, tmp_path):
+    """The other direction of the drop-in: the reference's OWN getIndexFromBoostSerial — boost::archive::text_iarchive forwarding
+    to the real Boost 1.78 library, whose init() checks the header and whose load_object reads the class preambles — loads the
+    file `SLAM --parse-genbank` wrote (library version 17 in the header) and ends up with the same GenbankIndex, genes included;
+    a truncated file makes it throw."""
+    import ctypes as C
+    import os
+    import subprocess
+    import numpy as np
+    import _lib as T
+    from test_taxon_host import make_db
+    L = C.CDLL(_refdb())
+    L.kref_read_database.restype = C.c_uint64
+    L.kref_read_database.argtypes = [C.c_char_p, C.c_void_p, C.c_uint64]
+    *_, paths = make_db(pkg, tmp_path, n_strains=5, length=4000)
+    exe = os.path.join(T.ROOT, "k-slam_b200", "SLAM")
+    db = str(tmp_path / "database")
+    assert subprocess.run([exe, "--parse-genbank", "--output-file", db, *paths], cwd=tmp_path).returncode == 0
+    cwd = os.getcwd()
+    os.chdir(tmp_path)                                       # the reference logs to ./log.txt
+    try:
+        n = L.kref_read_database(db.encode(), None, 0)
+        assert n != 2**64 - 1 and n > 20_000
+        buf = np.zeros(n, np.uint8)
+        L.kref_read_database(db.encode(), T._p(buf), n)
+        got = T.decode_index_dump(bytes(buf))
+        ours = T.index_entries(pkg.Index.read(db))
+        assert len(got) == len(ours) == 5
+        for g, w in zip(got, ours):
+            assert g["locus_tag"] == w["locus_tag"] and g["taxonomy_id"] == w["taxonomy_id"] and g["bases"] == w["bases"] and g["genes"] == w["genes"]
+        assert sum(len(e["genes"]) for e in got) > 10 and all(e["genbank_id"] > 0 for e in got)
+        cut = str(tmp_path / "cut")
+        open(cut, "wb").write(open(db, "rb").read()[:3000])
+        assert L.kref_read_database(cut.encode(), None, 0) == 2**64 - 1
+    finally:
+        os.chdir(cwd)
