@@ -266,7 +266,7 @@ def run_cli(args, pkg, meta):
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the matching path has no CPU fallback")
-    exe = os.path.join(ROOT, "k-slam_b200", "SLAM")
+    exe = os.environ.get("KSLAM_BENCH_EXE") or os.path.join(ROOT, "k-slam_b200", "SLAM")   # (the override times another build of the CLI)
     pairs = args.pairs or (2_000_000 if meta else 4_000_000)
     at_once = 1_000_000
     d = tempfile.mkdtemp(prefix="kslam_cli_")
@@ -323,6 +323,36 @@ def run_cli(args, pkg, meta):
             runs.append(dt)
     dt = float(np.mean(runs))
     out_bytes = {n: os.path.getsize(os.path.join(d, n)) for n in os.listdir(d) if n.startswith("out.")}
+    # the reference's OWN executable (oracle/_ref/SLAM_ref, its unmodified main.cpp) on the same files and database directory,
+    # bounded by --num-reads; our executable on the same prefix must write the same files
+    cpu_baseline = None
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "SLAM_ref")
+    try:
+        if not args.no_cpu_baseline and subprocess.run([ref_exe, "--version"], capture_output=True, timeout=60).stdout == b"1.0\n":
+            sample = args.cpu_sample or (50_000 if meta else 200_000)
+            cores = os.cpu_count() or 1
+            both = {}
+            for tag, exe in (("ref", ref_exe), ("ours", exe)):
+                wd = os.path.join(d, "cmp_" + tag); os.mkdir(wd)
+                cmd2 = [exe, "--db", db, "--sam-file", "o.sam", "--num-reads", str(sample), "--num-reads-at-once", str(at_once)]
+                cmd2 += ["--output-file", "o.xml"] if meta else ["--just-align"]
+                t0 = time.perf_counter()
+                r = subprocess.run(cmd2 + paths, cwd=wd, capture_output=True, env=dict(os.environ, OMP_NUM_THREADS=str(cores)))
+                both[tag] = (time.perf_counter() - t0, r.returncode, wd)
+            same = None
+            if both["ref"][1] == 0 and both["ours"][1] == 0:
+                def body(path):
+                    t = open(path, "rb").read()
+                    return t[t.index(b"@PG"):].split(b"\n", 1)[1] if path.endswith(".sam") else t
+                names = ["o.sam"] + (["o.xml_PerRead"] if meta else [])   # (the XML's gene representatives depend on the reference's thread count)
+                same = all(body(os.path.join(both["ref"][2], n)) == body(os.path.join(both["ours"][2], n)) for n in names)
+            cpu_baseline = {"value": sample / both["ref"][0] * 60 / 1e6, "unit": UNIT, "cores": cores, "kind": "reference",
+                            "sample": f"the reference's own executable (unmodified main.cpp) on the first {sample} pairs of the same files, "
+                                      f"whole process, {both['ref'][0]:.1f}s", "same_output_as_ours": same,
+                            "ours_on_the_same_sample_s": both["ours"][0]}
+            log(f"[bench/cli] reference executable: {sample} pairs in {both['ref'][0]:.1f}s; ours {both['ours'][0]:.2f}s; same output: {same}")
+    except Exception as e:   # noqa: BLE001
+        log(f"[bench/cli] reference executable leg skipped: {e}")
     shutil.rmtree(d, ignore_errors=True)
     emit({"metric": METRIC, "value": pairs / dt * 60 / 1e6, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
           "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16x2 (SW) / u64 (k-mers) / f64 (MAPQ)",
@@ -332,7 +362,7 @@ def run_cli(args, pkg, meta):
                                  + ("SAM + LCA XML + _PerRead + _abbreviated" if meta else "--just-align SAM"),
                      "includes": "process start, CUDA context, DIR/database parse, index build, FASTQ ingest, GPU matching path, host stages, output files",
                      "command": " ".join(os.path.basename(c) if os.sep in c else c for c in cmd)},
-          "output_bytes": out_bytes, "database_build_s": t_build})
+          "output_bytes": out_bytes, "database_build_s": t_build, "cpu_baseline": cpu_baseline})
 
 
 def run_reference_arm(args, pkg):
