@@ -4,7 +4,7 @@ the real Boost.Serialization library found in the image, boost::program_options 
   * the reference executable aligns against a database directory written by OUR executable and gives exactly what the in-memory
     harness of the reference's functions gives (the chain every GPU parity test compares the CUDA path with) — so the harness is the
     reference's process behaviour, and our database directory is a drop-in for it.
-The GPU tier (tests/test_gpu_cli.py) runs both executables on the same command line."""
+The GPU tier (tests/test_gpu_zz_executables.py) runs both executables on the same command lines."""
 import os
 import subprocess
 
