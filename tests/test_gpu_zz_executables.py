@@ -43,6 +43,9 @@ def test_both_executables_same_command_lines(pkg, tmp_path):
         (["--db", db, "--sam-file", "o.sam", "--output-file", "o.xml", "--num-reads-at-once", 150, r1, r2], ["o.sam", "o.xml", "o.xml_PerRead", "o.xml_abbreviated"]),
         (["--db=" + str(db), "--num-reads", 250, "--num-reads-at-once", 100, "--no-pseudo-assembly", "--score-fraction-threshold", 0.5, r1, r2], ["_PerRead"]),
         (["--db", db, "--just-align", "--sam-file", "s.sam", "--num-reads-at-once", 300, "--num-alignments", 3, r1], ["s.sam"]),
+        # everything in one go (main.cpp:146-166 takes metagenomicAnalysis then, whose per-read file has no underscore, SLAM.h:142)
+        (["--db", db, "--sam-file", "a.sam", "--output-file", "a.xml", "--num-reads-at-once", 4294967295, "--sam-xa", r1, r2],
+         ["a.sam", "a.xml", "a.xmlPerRead", "a.xml_abbreviated"]),
     ]
     for k, (args, files) in enumerate(commands):
         outs = []
