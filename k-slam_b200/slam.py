@@ -1,9 +1,10 @@
 """FASTQ + FASTA -> SAM through the library, batch by batch: the --just-align / --sam-file run of the reference
 (`SLAM --db DB --just-align --sam-file out.sam R1 R2`, SLAM.h:159-268) with every stage of its batch loop taken from
 libkslam.so: kslam_fastq_next (reader), kslam_align_pair_batch (alignToDatabase + screen + getPairedOverlaps on the GPU)
-and kslam_sam_batch (insert-size / score screens, pseudo-assembly, SAM records). The database is given as FASTA files
-and parsed the way --parse-fasta does (GenbankTools.h:224-260: locus tag = header up to the first space, bases
-upper-cased); the Boost text archive the reference stores in --db is not read here."""
+and kslam_sam_batch (insert-size / score screens, pseudo-assembly, SAM records). The database is given as FASTA files,
+parsed the way --parse-fasta does (GenbankTools.h:224-260: locus tag = header up to the first space, bases upper-cased),
+or as a --db directory (database.py). This is the Python form of the pipeline (tests, bench.py --workload sam); the C++
+form with the reference's full command line, taxonomy and XML included, is k-slam_b200/SLAM (csrc/slam_main.cpp)."""
 from __future__ import annotations
 
 import time
