@@ -79,18 +79,23 @@ template <class F> void parallel_for(uint32_t threads, uint64_t n, F f) {
 }
 
 // Offsets just past every '\n' of p[lo, hi) appended to `out` (the starts of the lines that follow). 64 bytes per step:
-// four SSE2 compares folded into one 64-bit mask, one entry per set bit. (memchr per line cost 4 calls per record.)
-void scan_newlines(const char *p, size_t lo, size_t hi, std::vector<uint64_t> &out) {
+// four SSE2 compares folded into one 64-bit mask, one entry per set bit (memchr per line cost 4 calls per record); the same
+// pass notices a '\r' anywhere in the range, which sends the window to the general path.
+bool scan_newlines(const char *p, size_t lo, size_t hi, std::vector<uint64_t> &out) {   // returns true when the range holds a '\r'
   size_t i = lo;
-  const __m128i nl = _mm_set1_epi8('\n');
+  const __m128i nl = _mm_set1_epi8('\n'), cr = _mm_set1_epi8('\r');
+  __m128i any_cr = _mm_setzero_si128();
   for (; i + 64 <= hi; i += 64) {
     const __m128i a = _mm_loadu_si128((const __m128i *)(p + i)), b = _mm_loadu_si128((const __m128i *)(p + i + 16));
     const __m128i c = _mm_loadu_si128((const __m128i *)(p + i + 32)), d = _mm_loadu_si128((const __m128i *)(p + i + 48));
+    any_cr = _mm_or_si128(any_cr, _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(a, cr), _mm_cmpeq_epi8(b, cr)), _mm_or_si128(_mm_cmpeq_epi8(c, cr), _mm_cmpeq_epi8(d, cr))));
     uint64_t m = (uint64_t)(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(a, nl)) | ((uint64_t)(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(b, nl)) << 16) |
                  ((uint64_t)(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(c, nl)) << 32) | ((uint64_t)(uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(d, nl)) << 48);
     while (m) { out.push_back(i + (size_t)__builtin_ctzll(m) + 1); m &= m - 1; }
   }
-  for (; i < hi; i++) if (p[i] == '\n') out.push_back(i + 1);
+  bool tail_cr = false;
+  for (; i < hi; i++) { if (p[i] == '\n') out.push_back(i + 1); tail_cr |= p[i] == '\r'; }
+  return tail_cr || _mm_movemask_epi8(any_cr) != 0;
 }
 
 // is byte i the end of a line? ('\r', or a '\n' that does not directly follow a '\r')
@@ -151,9 +156,8 @@ static uint64_t index_lines(MappedFile &mf, uint64_t max_reads, uint32_t threads
       const size_t first = lists.size();
       lists.resize(first + nt);
       parallel_for(nt, span, [&](uint32_t t, uint64_t lo, uint64_t hi) {
-        if (memchr(p + scanned + lo, '\r', hi - lo) != nullptr) { cr[t] = 1; return; }
         lists[first + t].reserve((size_t)((hi - lo) / 64) + 16);
-        scan_newlines(p, scanned + lo, scanned + hi, lists[first + t]);
+        cr[t] = scan_newlines(p, scanned + lo, scanned + hi, lists[first + t]);
       });
       for (uint8_t v : cr) cr_seen |= v != 0;
       if (cr_seen) break;
