@@ -77,44 +77,84 @@ std::vector<ReadPair> per_read(const kslam_pairs *in, uint32_t midpoint, uint32_
   return out;
 }
 
-uint32_t max_allowed_insert_size(const std::vector<ReadPair> &reads) {               // PairedOverlap.h:314-360
-  std::vector<int32_t> insertSizes;
+// ---- getMaxAllowedInsertSize, PairedOverlap.h:314-360 -------------------------------------------------------------
+// The reference sorts every non-zero insert size of the batch and reads order statistics off the sorted vector. What it
+// computes is a function of the value COUNTS only, so the batch is kept as a run-length list (value ascending, count,
+// cumulative count): order statistics are a binary search, the filtered moments a walk over the runs. The same structure
+// can be filled from a histogram computed elsewhere (insert_size_limit_from_runs).
+struct InsertRuns {
+  std::vector<int32_t> value;      // ascending, distinct
+  std::vector<uint64_t> upto;      // upto[k] = number of elements <= value[k]
+  uint64_t total() const { return upto.empty() ? 0 : upto.back(); }
+  int32_t at(uint64_t rank) const { return value[(size_t)(std::upper_bound(upto.begin(), upto.end(), rank) - upto.begin())]; }
+  void push(int32_t v, uint64_t count) { if (count) { value.push_back(v); upto.push_back(total() + count); } }
+};
+
+InsertRuns insert_size_runs(const std::vector<ReadPair> &reads) {
+  InsertRuns runs;
+  int64_t lo = INT64_MAX, hi = INT64_MIN;
+  uint64_t n = 0;
   for (auto &read : reads)
     for (auto &p : read.pairs)
-      if (p.insertSize != 0) insertSizes.push_back(p.insertSize);
-  if (insertSizes.size() == 0) return UINT32_MAX;
-  // std::sort in the reference; a sorted sequence of integers does not depend on the algorithm, so large batches of small
-  // values (the normal case: fragment lengths) take a counting sort
-  int32_t lo = insertSizes[0], hi = insertSizes[0];
-  for (int32_t v : insertSizes) { lo = std::min(lo, v); hi = std::max(hi, v); }
-  if (insertSizes.size() >= par_min() && lo >= 0 && hi < (1 << 22)) {
-    std::vector<uint32_t> count((size_t)hi + 1, 0);
-    for (int32_t v : insertSizes) count[v]++;
-    size_t at = 0;
-    for (int32_t v = lo; v <= hi; v++) { std::fill_n(insertSizes.begin() + at, count[v], v); at += count[v]; }
-  } else std::sort(insertSizes.begin(), insertSizes.end());
-  int32_t limit = 0;
-  for (int i = 0; i < 99; i++) {
-    if ((insertSizes[floor(insertSizes.size() * (i + 1) / 100.0)] - insertSizes[floor(insertSizes.size() * (i) / 100.0)]) > 1000) {
-      limit = insertSizes[floor(insertSizes.size() * (i) / 100)];
-      break;
-    }
+      if (p.insertSize != 0) { const int32_t v = (int32_t)p.insertSize; lo = std::min<int64_t>(lo, v); hi = std::max<int64_t>(hi, v); n++; }
+  if (!n) return runs;
+  if (hi - lo < (1 << 22)) {                               // the normal case (fragment lengths): one counter per value
+    std::vector<uint64_t> count((size_t)(hi - lo + 1), 0);
+    for (auto &read : reads)
+      for (auto &p : read.pairs)
+        if (p.insertSize != 0) count[(size_t)((int32_t)p.insertSize - lo)]++;
+    for (int64_t v = lo; v <= hi; v++) runs.push((int32_t)v, count[(size_t)(v - lo)]);
+  } else {
+    std::vector<int32_t> all; all.reserve(n);
+    for (auto &read : reads)
+      for (auto &p : read.pairs)
+        if (p.insertSize != 0) all.push_back((int32_t)p.insertSize);
+    std::sort(all.begin(), all.end());
+    for (size_t i = 0; i < all.size();) { size_t j = i; while (j < all.size() && all[j] == all[i]) j++; runs.push(all[i], j - i); i = j; }
   }
-  int32_t LQ = insertSizes[floor(insertSizes.size() * 0.25)];
-  int32_t UQ = insertSizes[floor(insertSizes.size() * 0.75)];
-  int32_t lowerLimit = 0;
-  int32_t upperLimit = UQ + 2 * (UQ - LQ);
-  if (limit) upperLimit = limit;
-  if (upperLimit == 0) upperLimit = INT32_MAX;
-  auto endPos = std::remove_if(insertSizes.begin(), insertSizes.end(), [&](const int32_t i) { return i < lowerLimit || i > upperLimit; });
-  insertSizes.resize(std::distance(insertSizes.begin(), endPos));
-  double sum = std::accumulate(insertSizes.begin(), insertSizes.end(), 0.0);
-  double mean = sum / insertSizes.size();
-  double sqSum = std::inner_product(insertSizes.begin(), insertSizes.end(), insertSizes.begin(), 0.0);
-  double stdDev = std::sqrt(sqSum / insertSizes.size() - mean * mean);
-  auto result = floor(mean + 6 * stdDev);
-  return std::isnan(result) ? UINT_MAX : result;
+  return runs;
 }
+
+// acc + v + v + ... (count times) exactly as a chain of double additions would give it: while every partial sum is an
+// integer below 2^53 the chain is exact, so it collapses into one addition; beyond that the additions are issued one by one
+inline double add_repeated(double acc, double v, uint64_t count) {
+  const double block = v * (double)count, lim = 9007199254740992.0;
+  if (std::fabs(acc) + std::fabs(block) < lim && count < (1ull << 52)) return acc + block;
+  while (count--) acc += v;
+  return acc;
+}
+
+uint32_t insert_size_limit_from_runs(const InsertRuns &runs) {
+  const uint64_t n = runs.total();
+  if (n == 0) return UINT32_MAX;
+  // first percentile step wider than 1000 (:327-333): the percentile positions are floor(n * i / 100.0)
+  int32_t spike = 0;
+  for (int pc = 0; pc < 99 && !spike; pc++) {
+    const int32_t here = runs.at((uint64_t)floor(n * pc / 100.0)), next = runs.at((uint64_t)floor(n * (pc + 1) / 100.0));
+    if (next - here > 1000) { spike = runs.at((uint64_t)(n * (uint64_t)pc / 100)); break; }
+  }
+  const int32_t q1 = runs.at((uint64_t)floor(n * 0.25)), q3 = runs.at((uint64_t)floor(n * 0.75));
+  int32_t ceiling = spike ? spike : q3 + 2 * (q3 - q1);
+  if (ceiling == 0) ceiling = INT32_MAX;
+  // mean and deviation of the values in [0, ceiling], accumulated in ascending order like the reference's accumulate /
+  // inner_product over the sorted vector (the square is an int product there, converted afterwards)
+  uint64_t kept = 0;
+  double sum = 0.0, squares = 0.0;
+  for (size_t k = 0; k < runs.value.size(); k++) {
+    const int32_t v = runs.value[k];
+    if (v < 0 || v > ceiling) continue;
+    const uint64_t count = runs.upto[k] - (k ? runs.upto[k - 1] : 0);
+    kept += count;
+    sum = add_repeated(sum, (double)v, count);
+    squares = add_repeated(squares, (double)(int32_t)((uint32_t)v * (uint32_t)v), count);
+  }
+  const double mean = sum / kept;
+  const double sigma = std::sqrt(squares / kept - mean * mean);
+  const double bound = floor(mean + 6 * sigma);
+  return std::isnan(bound) ? UINT_MAX : (uint32_t)bound;
+}
+
+uint32_t max_allowed_insert_size(const std::vector<ReadPair> &reads) { return insert_size_limit_from_runs(insert_size_runs(reads)); }
 
 void screen_by_insert_size(std::vector<ReadPair> &reads, const kslam_overlap *ov, const uint32_t insertSize, uint32_t threads) {   // :396-436, replace = true
   parallel_ranges(threads, reads.size(), [&](uint32_t, size_t lo, size_t hi) {
@@ -195,49 +235,46 @@ void pseudo_assembly(std::vector<ReadPair> &pairedAlignments, uint32_t threads, 
       }
     for (auto &entry : entriesAndOverlaps) entries.push_back(&entry.second);
   }
-  std::atomic<size_t> next{0};                            // entries differ a lot in size: hand them out one at a time
+  // One entry at a time (they differ a lot in size, so threads take them from a shared counter). Records ordered by start
+  // are cut into chains: a record opens a new chain when it starts more than 20 bases before the furthest stop seen so
+  // far is reached ... i.e. when start > reach - 20 (PairedOverlap.h:521-573). A chain of two or more records gives all its
+  // members the score  (bases / span) * (sum of per-base scores / members) * span,  evaluated in that order in double and
+  // truncated on assignment, as the reference does.
+  struct Chain {
+    size_t first = 0; int reach = -1000000; uint32_t bases = 0; double per_base_sum = 0;
+    void open(size_t at, const POv &r, int stop) {
+      first = at; reach = stop;
+      const int extent = abs(r.refEnd - r.refStart);
+      per_base_sum = r.combinedScore * 1.0 / extent; bases = (uint32_t)extent;
+    }
+    void extend(const POv &r, int stop) {
+      if (stop > reach) reach = stop;
+      const int extent = abs(r.refEnd - r.refStart);
+      per_base_sum += r.combinedScore * 1.0 / extent; bases += (uint32_t)extent;
+    }
+  };
+  std::atomic<size_t> next{0};
   parallel_threads(entries.size() < 2 ? 1u : threads, [&](uint32_t) {
-  for (size_t ei = next++; ei < entries.size(); ei = next++) {
-    struct { entryAndOverlaps &second; } entry{*entries[ei]};
-    std::sort(entry.second.reads.begin(), entry.second.reads.end(),
-              [](const std::pair<coverage, POv *> &i, const std::pair<coverage, POv *> &j) { return i.first.start < j.first.start; });
-    auto chainStart = entry.second.reads.begin();
-    int highestPos = -1000000;
-    uint32_t score = 0;
-    uint32_t numBases = 0;
-    double perBaseScore = 0;
-    for (auto overlap = entry.second.reads.begin(); overlap != entry.second.reads.end(); overlap++) {
-      if (overlap->first.start > highestPos - 20) {
-        auto chainLength = std::distance(chainStart, overlap);
-        if (chainLength > 1) {
-          double length = highestPos - chainStart->first.start;
-          double coverage = numBases / length;
-          double avgScorePerBase = perBaseScore / chainLength;
-          double score = coverage * avgScorePerBase * length;
-          for (auto overlap2 = chainStart; overlap2 != overlap; overlap2++) overlap2->second->combinedScore = score;
-        }
-        chainStart = overlap;
-        highestPos = overlap->first.stop;
-        score = overlap->second->combinedScore;
-        perBaseScore = overlap->second->combinedScore * 1.0 / abs(overlap->second->refEnd - overlap->second->refStart);
-        numBases = abs(overlap->second->refEnd - overlap->second->refStart);
-      } else {
-        if (overlap->first.stop > highestPos) highestPos = overlap->first.stop;
-        score += overlap->second->combinedScore;
-        perBaseScore += overlap->second->combinedScore * 1.0 / abs(overlap->second->refEnd - overlap->second->refStart);
-        numBases += abs(overlap->second->refEnd - overlap->second->refStart);
+    for (size_t ei = next++; ei < entries.size(); ei = next++) {
+      auto &recs = entries[ei]->reads;
+      std::sort(recs.begin(), recs.end(),
+                [](const std::pair<coverage, POv *> &a, const std::pair<coverage, POv *> &b) { return a.first.start < b.first.start; });
+      Chain chain;
+      auto close = [&](size_t end) {
+        const ptrdiff_t members = (ptrdiff_t)(end - chain.first);
+        if (members < 2) return;
+        const double span = chain.reach - recs[chain.first].first.start;
+        const double depth = chain.bases / span;
+        const double mean_per_base = chain.per_base_sum / members;
+        const double rescored = depth * mean_per_base * span;
+        for (size_t k = chain.first; k < end; k++) recs[k].second->combinedScore = rescored;
+      };
+      for (size_t k = 0; k < recs.size(); k++) {
+        if (recs[k].first.start > chain.reach - 20) { close(k); chain.open(k, *recs[k].second, recs[k].first.stop); }
+        else chain.extend(*recs[k].second, recs[k].first.stop);
       }
+      close(recs.size());
     }
-    auto chainLength = std::distance(chainStart, entry.second.reads.end());
-    if (chainLength > 1) {
-      double length = highestPos - chainStart->first.start;
-      double coverage = numBases / length;
-      double avgScorePerBase = perBaseScore / chainLength;
-      double score = coverage * avgScorePerBase * length;
-      for (auto overlap2 = chainStart; overlap2 != entry.second.reads.end(); overlap2++) overlap2->second->combinedScore = score;
-    }
-    (void)score;
-  }
   });
 }
 

@@ -34,18 +34,45 @@ struct TaxEntry {                                          // TaxonomyEntry, Tax
   std::string scientificName, rank;
 };
 
-// tokenise, sequenceTools.h:117-133
-std::vector<std::string> tokenise(const std::string &line, const char *delimiters) {
-  std::vector<std::string> tokens;
-  std::string::size_type lastPos = line.find_first_not_of(delimiters, 0);
-  std::string::size_type pos = line.find_first_of(delimiters, lastPos);
-  while (pos != std::string::npos || lastPos != std::string::npos) {
-    tokens.push_back(line.substr(lastPos, pos - lastPos));
-    lastPos = line.find_first_not_of(delimiters, pos);
-    pos = line.find_first_of(delimiters, lastPos);
+// The dump files (nodes.dmp / names.dmp) are read whole and walked as views: no per-line string, no token vector.
+struct DumpFile {
+  std::string text;
+  explicit DumpFile(const char *path, const char *what) {
+    FILE *f = fopen(path, "rb");
+    if (!f) throw std::runtime_error(std::string("unable to open ") + what + " file");
+    char buf[1 << 16];
+    for (size_t got; (got = fread(buf, 1, sizeof buf, f)) > 0;) text.append(buf, got);
+    fclose(f);
   }
-  return tokens;
+  // calls fn(begin, end) for every '\n'-terminated line and for what follows the last '\n' (possibly empty): the lines the
+  // reference's `while (good()) getline` loop sees (TaxonomyDatabase.h:99-101)
+  template <class F> void for_each_line(F fn) const {
+    const char *p = text.data(), *end = p + text.size();
+    for (;;) {
+      const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+      fn(p, nl ? nl : end);
+      if (!nl) break;
+      p = nl + 1;
+    }
+  }
+};
+struct Field { const char *b, *e; size_t size() const { return (size_t)(e - b); } };
+// The maximal runs of non-separator bytes of [b, e), at most cap of them; returns how many there are in total (what the
+// reference's tokenise, sequenceTools.h:117-133, would return as tokens.size())
+template <class IsSep> size_t split_fields(const char *b, const char *e, IsSep is_sep, Field *out, size_t cap) {
+  size_t n = 0;
+  while (b < e) {
+    while (b < e && is_sep(*b)) b++;
+    if (b == e) break;
+    const char *s = b;
+    while (b < e && !is_sep(*b)) b++;
+    if (n < cap) out[n] = Field{s, b};
+    n++;
+  }
+  return n;
 }
+// std::stoi of a field (same acceptance and the same exceptions as the reference's stoi(tokens[i]))
+int field_int(const Field &f) { return std::stoi(std::string(f.b, f.e)); }
 
 }  // namespace
 
@@ -115,43 +142,40 @@ struct kslam_taxdb {
       nodes.insert({e.taxonomyID, e});
     }
   }
-  void parse_nodes(const char *path) {                     // parseNodesDump, :95-117
-    std::ifstream in(path);
-    if (!in.is_open()) throw std::runtime_error("unable to open nodes file");
-    std::string line;
-    while (in.good()) {
-      getline(in, line);
-      std::vector<std::string> tokens = tokenise(line, "\t|");
-      if (tokens.size() > 2) {
-        TaxEntry e;
-        e.taxonomyID = stoi(tokens[0]);
-        e.parentTaxonomyID = stoi(tokens[1]);
-        e.rank = tokens[2];
-        nodes.insert({e.taxonomyID, e});                   // a repeated id keeps its first parent and rank (:111-114)
-      }
-    }
+  // parseNodesDump, TaxonomyDatabase.h:95-117: fields are separated by any run of tabs and bars; a line with at least three
+  // of them is a node (id, parent id, rank). A repeated id keeps its first parent and rank (:111-114).
+  void parse_nodes(const char *path) {
+    const DumpFile dump(path, "nodes");
+    dump.for_each_line([&](const char *b, const char *e) {
+      Field f[3];
+      if (split_fields(b, e, [](char c) { return c == '\t' || c == '|'; }, f, 3) < 3) return;
+      const uint32_t id = (uint32_t)field_int(f[0]), up = (uint32_t)field_int(f[1]);
+      auto slot = nodes.find(id);
+      if (slot != nodes.end()) return;
+      TaxEntry &node = nodes[id];
+      node.taxonomyID = id; node.parentTaxonomyID = up; node.rank.assign(f[2].b, f[2].e);
+    });
   }
-  void parse_names(const char *path) {                     // parseNamesDump, :118-151
-    std::ifstream in(path);
-    if (!in.is_open()) throw std::runtime_error("unable to open names file");
-    std::string line;
-    while (in.good()) {
-      getline(in, line);
-      std::vector<std::string> tokens = tokenise(line, "|");
-      for (auto &token : tokens)
-        if (token.size() > 1) {
-          if (token[0] == '\t') token.erase(0, 1);
-          if (token[token.size() - 1] == '\t') token.erase(token.size() - 1, 1);
+  // parseNamesDump, :118-151: fields are separated by bars, each loses one leading and then one trailing tab when it is
+  // longer than one byte; a line with at least four fields whose fourth is "scientific name" names the node of field one
+  // (the id is converted before the class is looked at, as in the reference: a malformed id throws either way).
+  void parse_names(const char *path) {
+    const DumpFile dump(path, "names");
+    static const char kClass[] = "scientific name";
+    dump.for_each_line([&](const char *b, const char *e) {
+      Field f[4];
+      if (split_fields(b, e, [](char c) { return c == '|'; }, f, 4) < 4) return;
+      for (Field &x : f)
+        if (x.size() > 1) {
+          if (*x.b == '\t') x.b++;
+          if (x.e[-1] == '\t') x.e--;
         }
-      if (tokens.size() > 3) {
-        TaxEntry e;
-        e.taxonomyID = stoi(tokens[0]);
-        if (tokens[3] != "scientific name") continue;
-        e.scientificName = tokens[1];
-        auto it = nodes.insert({e.taxonomyID, e});
-        if (!it.second) it.first->second.scientificName = e.scientificName;
-      }
-    }
+      const uint32_t id = (uint32_t)field_int(f[0]);
+      if (f[3].size() != sizeof kClass - 1 || memcmp(f[3].b, kClass, sizeof kClass - 1) != 0) return;
+      auto slot = nodes.find(id);
+      if (slot == nodes.end()) { TaxEntry &node = nodes[id]; node.taxonomyID = id; node.scientificName.assign(f[1].b, f[1].e); }
+      else slot->second.scientificName.assign(f[1].b, f[1].e);
+    });
   }
   uint32_t parent(uint32_t taxID) const {                  // getParentTaxID, :225-231: the root's children end the walk
     auto it = nodes.find(taxID);
@@ -177,12 +201,12 @@ struct kslam_taxdb {
     constexpr int CAP = 256;
     uint32_t first[CAP], other[CAP];
     const int len0 = path_of(taxIDs[0], first, CAP);
-    if (len0 < 0) return lca_generic(taxIDs, n);
+    if (len0 < 0) return lca_deep(taxIDs, n);
     int lcp = len0;
     for (uint64_t k = 1; k < n && lcp > 0; k++) {
       if (taxIDs[k] == taxIDs[k - 1]) continue;            // alignments of one read often share the entry's taxon
       const int len = path_of(taxIDs[k], other, CAP);
-      if (len < 0) return lca_generic(taxIDs, n);
+      if (len < 0) return lca_deep(taxIDs, n);
       const int m = lcp < len ? lcp : len;
       int i = 0;
       while (i < m && first[len0 - 1 - i] == other[len - 1 - i]) i++;
@@ -190,27 +214,24 @@ struct kslam_taxdb {
     }
     return lcp > 0 ? first[len0 - lcp] : 0;
   }
-  uint32_t lca_generic(const uint32_t *taxIDs, uint64_t n) const {   // the literal form; used for paths deeper than 256 levels
-    if (n == 0) return 0;
-    std::vector<std::vector<uint32_t>> paths;
-    for (uint64_t k = 0; k < n; k++) {
-      std::vector<uint32_t> path;
-      uint32_t t = taxIDs[k];
-      while (t != 0 && path.size() <= nodes.size()) { path.push_back(t); t = parent(t); }
-      paths.push_back(std::move(path));
+  // Same answer for walks longer than 256 levels (or a database whose parent links loop: a walk is cut after nodes.size() + 1
+  // ids): the prefix fold of lca() over heap-allocated leaf-first walks.
+  void walk_up(uint32_t taxID, std::vector<uint32_t> &ids) const {
+    ids.clear();
+    for (uint32_t t = taxID; t != 0 && ids.size() <= nodes.size(); t = parent(t)) ids.push_back(t);
+  }
+  uint32_t lca_deep(const uint32_t *taxIDs, uint64_t n) const {
+    std::vector<uint32_t> head, cur;
+    walk_up(taxIDs[0], head);
+    size_t shared = head.size();                           // how many ids, counted from the root end, every walk so far shares
+    for (uint64_t k = 1; k < n && shared > 0; k++) {
+      walk_up(taxIDs[k], cur);
+      const size_t lim = std::min(shared, cur.size());
+      size_t same = 0;
+      while (same < lim && head[head.size() - 1 - same] == cur[cur.size() - 1 - same]) same++;
+      shared = same;
     }
-    size_t shortest = paths[0].size();
-    for (auto &p : paths) { std::reverse(p.begin(), p.end()); shortest = std::min(shortest, p.size()); }
-    uint32_t consensus = 0;                                // the result does not depend on the order among equal lengths,
-    for (size_t i = 0; i < shortest; i++) {                // so the reference's sort by length reduces to "the shortest"
-      uint32_t temp = 0;
-      for (auto &p : paths) {
-        if (temp == 0) temp = p[i];
-        else if (temp != p[i]) return consensus;
-      }
-      consensus = temp;
-    }
-    return consensus;
+    return shared ? head[head.size() - shared] : 0;
   }
   std::string lineage(uint32_t taxonomyID) const {         // getLineage, :249-265 (131567 = cellular organisms, skipped)
     std::string lineage;
