@@ -14,6 +14,9 @@ struct CudaError {
   cudaError_t e; const char *what; const char *file; int line;
 };
 
+// thrown by internal stages for inputs the ABI cannot represent; API_END turns it into KSLAM_ERR_ARG
+struct ArgError { const char *what; };
+
 #define CUDA_TRY(x)                                                        \
   do {                                                                     \
     cudaError_t e_ = (x);                                                  \
@@ -191,6 +194,7 @@ int api_fail(kslam_ctx *c, int code, const std::string &msg);
     snprintf(buf, sizeof buf, "%s:%d: %s: %s", e.file, e.line, e.what, cudaGetErrorString(e.e)); \
     cudaGetLastError();                                                                         \
     return api_fail((ctx), e.e == cudaErrorMemoryAllocation ? KSLAM_ERR_NOMEM : KSLAM_ERR_CUDA, buf); \
+  } catch (const ArgError &e) { return api_fail((ctx), KSLAM_ERR_ARG, e.what);                      \
   } catch (const std::exception &e) { return api_fail((ctx), KSLAM_ERR_NOMEM, e.what()); }
 
 // api.cu: read a few words of device memory into PINNED host memory without the copy engine — a one-warp kernel

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include <chrono>
 #include <emmintrin.h>
+#include <errno.h>
 #include <fcntl.h>
 #include <stdlib.h>
 #include <string.h>
@@ -33,11 +34,32 @@ struct MappedFile {
   bool eof_line_done = false;   // the empty line safeGetline yields once at end of file has been handed out
   double bytes_per_line = 0;    // running estimate from the last batch (sizes the next scan window)
   int fd = -1;
+  char *heap = nullptr;         // contents of an input that cannot be mapped (pipe, process substitution, /dev/stdin)
   bool open(const char *path, std::string &err) {
     fd = ::open(path, O_RDONLY);
     if (fd < 0) { err = std::string("cannot open ") + path; return false; }
     struct stat st;
     if (fstat(fd, &st) != 0) { err = std::string("cannot stat ") + path; return false; }
+    if (!S_ISREG(st.st_mode)) {
+      // The reference reads through std::ifstream, which works on FIFOs (`SLAM ... <(zcat r1.fq.gz)`); a pipe has no size
+      // and cannot be mapped, so it is drained into memory and indexed like a mapping.
+      size_t cap = 1u << 24;
+      heap = (char *)malloc(cap);
+      if (!heap) { err = "out of memory reading " + std::string(path); return false; }
+      for (;;) {
+        if (size == cap) {
+          char *bigger = (char *)realloc(heap, cap * 2);
+          if (!bigger) { err = "out of memory reading " + std::string(path); return false; }
+          heap = bigger; cap *= 2;
+        }
+        const ssize_t got = ::read(fd, heap + size, cap - size);
+        if (got < 0) { if (errno == EINTR) continue; err = std::string("read error on ") + path; return false; }
+        if (got == 0) break;
+        size += (size_t)got;
+      }
+      p = heap;
+      return true;
+    }
     size = (size_t)st.st_size;
     if (size) {
       void *m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
@@ -48,9 +70,10 @@ struct MappedFile {
     return true;
   }
   void close() {
-    if (p) munmap((void *)p, size);
+    if (heap) free(heap);
+    else if (p) munmap((void *)p, size);
     if (fd >= 0) ::close(fd);
-    p = nullptr; fd = -1;
+    p = nullptr; heap = nullptr; fd = -1;
   }
 };
 

@@ -659,11 +659,22 @@ static int sam_finish(Ctx &c, std::vector<ReadPair> &rp, bool insert_screen, boo
 static int check_overlaps(const kslam_sam_db *db, const kslam_read_batch *reads, const kslam_overlap *ov, uint64_t n, const uint32_t *pool,
                           uint64_t n_pool) {
   // the records index each other and the read / entry arrays: refuse anything out of range instead of reading past a buffer
+  uint64_t undefined = 0;
   for (uint64_t i = 0; i < n; i++) {
     const kslam_overlap &o = ov[i];
     if (o.read >= reads->n_reads || o.entry >= db->n_entries) return KSLAM_ERR_ARG;
     if (o.cigar_len && pool && (uint64_t)o.cigar_off + o.cigar_len > n_pool) return KSLAM_ERR_ARG;
+    // A truncated CIGAR would give a wrong CIGAR / MD / NM without any sign of it. kslam_align_batch raises the pool stride
+    // until nothing overflows, so this only fires for records a caller built with a fixed pool (kslam_ssw_batch).
+    if (pool && (o.flags & KSLAM_FLAG_CIGAR_OVERFLOW)) {
+      fprintf(stderr, "kslam: alignment %llu carries a truncated CIGAR (KSLAM_FLAG_CIGAR_OVERFLOW): raise max_cigar_ops\n", (unsigned long long)i);
+      return KSLAM_ERR_STATE;
+    }
+    undefined += (o.flags & KSLAM_FLAG_UNDEFINED) != 0;
   }
+  if (undefined)
+    fprintf(stderr, "kslam: warning: %llu alignments are outside the reference's defined behaviour (score 0 with a CIGAR requested, or a "
+                    "traceback leaving its band); their records carry no CIGAR\n", (unsigned long long)undefined);
   return KSLAM_OK;
 }
 
@@ -677,7 +688,7 @@ int kslam_batch_outputs(const kslam_sam_params *prm, const kslam_sam_db *db, con
   if (!prm || !db || !reads || !pairs || (want_sam && !text) || ((taxdb != nullptr) != (taxa != nullptr))) return KSLAM_ERR_ARG;
   if ((db->genes != nullptr) != (db->gene_offs != nullptr) || (db->genes && !db->gene_strings)) return KSLAM_ERR_ARG;
   if (pairs->n_pairs && (!pairs->pairs || !pairs->sorted_overlaps)) return KSLAM_ERR_ARG;
-  if (check_overlaps(db, reads, pairs->sorted_overlaps, pairs->n_sorted, pairs->cigar_pool, pairs->n_cigar_words) != KSLAM_OK) return KSLAM_ERR_ARG;
+  if (int rc = check_overlaps(db, reads, pairs->sorted_overlaps, pairs->n_sorted, pairs->cigar_pool, pairs->n_cigar_words)) return rc;
   for (uint64_t i = 0; i < pairs->n_pairs; i++) {
     const kslam_pair &k = pairs->pairs[i];
     if ((k.r1_idx < 0 && k.r2_idx < 0) || k.r1_idx >= (int64_t)pairs->n_sorted || k.r2_idx >= (int64_t)pairs->n_sorted ||
@@ -719,7 +730,7 @@ int kslam_batch_outputs_single(const kslam_sam_params *prm, const kslam_sam_db *
   if (!prm || !db || !reads || !al || (want_sam && !text) || ((taxdb != nullptr) != (taxa != nullptr))) return KSLAM_ERR_ARG;
   if ((db->genes != nullptr) != (db->gene_offs != nullptr) || (db->genes && !db->gene_strings)) return KSLAM_ERR_ARG;
   if (al->n_overlaps && !al->overlaps) return KSLAM_ERR_ARG;
-  if (check_overlaps(db, reads, al->overlaps, al->n_overlaps, al->cigar_pool, al->n_cigar_words) != KSLAM_OK) return KSLAM_ERR_ARG;
+  if (int rc = check_overlaps(db, reads, al->overlaps, al->n_overlaps, al->cigar_pool, al->n_cigar_words)) return rc;
   try {
     kslam_pairs view;
     memset(&view, 0, sizeof view);

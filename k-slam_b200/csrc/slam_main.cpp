@@ -187,7 +187,9 @@ bool write_file(const std::string &path, const char *text, uint64_t len) {
 // (same rules as k-slam_b200/shard.py: pairing is per pair, seeds are per (read, genome)).
 void align_batch(const std::vector<kslam_ctx *> &ctxs, bool isPaired, Batch *b) {
   const kslam_read_batch &r = b->reads;
-  const size_t G = ctxs.size();
+  // (a paired batch with an odd read count — the reference's R1/R2 size check lets n2 = n1 + 1 through, FASTQsequence.h:118-122 —
+  // pairs its last read by index modulo the midpoint, which no contiguous split reproduces: such a batch runs on one context)
+  const size_t G = (isPaired && (r.n_reads & 1)) ? 1 : ctxs.size();
   if (G == 1) {
     if (isPaired) {
       kslam_pairs p;
@@ -278,7 +280,7 @@ int run_alignment(const Options &o, const std::string &commandLine) {      // me
   kslam_params prm;
   memset(&prm, 0, sizeof prm);
   prm.match = (uint8_t)o.match; prm.mismatch = (uint8_t)o.misMatch; prm.gap_open = (uint8_t)o.gapOpen; prm.gap_extend = (uint8_t)o.gapExtend;   // ssw_cpp.cpp:114-117
-  prm.score_threshold = (uint16_t)o.scoreThreshold; prm.report_cigar = wantSam ? 1 : 0; prm.device = o.devices[0];
+  prm.score_threshold = (uint16_t)(o.scoreThreshold > 65535u ? 65535u : o.scoreThreshold);   // sw_score is 16 bits (ssw_cpp.h:16): a larger threshold screens everything, as in the reference prm.report_cigar = wantSam ? 1 : 0; prm.device = o.devices[0];
   if (!kslam_params_exact(&prm))
     std::cerr << "SLAM: warning: scoring parameters outside the domain in which results are proven identical to SSW's (need gap-extend < gap-open and mismatch <= 2 * gap-extend)\n";
   // one context per entry of --devices, the genome index replicated in each (read pairs shard trivially)

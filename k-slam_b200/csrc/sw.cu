@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(128)
 k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, uint32_t n, const uint32_t *list,
                SwPlanes pl, SwScore sc, kslam_overlap *__restrict__ ov, uint32_t *__restrict__ cigs, int unflip,
                int mode, uint32_t *__restrict__ retry_list, uint32_t *__restrict__ retry_count,
-               uint8_t *__restrict__ big, size_t big_per_thread) {
+               uint32_t *__restrict__ overflow_count, uint8_t *__restrict__ big, size_t big_per_thread) {
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
   int32_t l_hb[SW_TB_MAXBAND * 2 + 3], l_eb[SW_TB_MAXBAND * 2 + 3], l_hc[SW_TB_MAXBAND * 2 + 3];
@@ -518,7 +518,10 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
           else o.flags |= KSLAM_FLAG_UNDEFINED;   // beyond even the big scratch: report, never guess
         } else if (len == -2) { o.cigar_len = 0; o.sw_score = 0; }           // ssw.c:941-944
         else if (len == -1) o.flags |= KSLAM_FLAG_UNDEFINED;
-        else { o.cigar_len = (uint32_t)len < sc.cigar_cap ? (uint32_t)len : sc.cigar_cap; if (overflow) o.flags |= KSLAM_FLAG_CIGAR_OVERFLOW; }
+        else {
+          o.cigar_len = (uint32_t)len < sc.cigar_cap ? (uint32_t)len : sc.cigar_cap;
+          if (overflow) { o.flags |= KSLAM_FLAG_CIGAR_OVERFLOW; atomicAdd(overflow_count, 1u); }
+        }
       }
     }
     if (deferred) continue;
@@ -543,6 +546,7 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
 #define CNT_RETRY 4
 #define CNT_EXTRA 5
 #define CNT_BAND64 6
+#define CNT_OVERFLOW 7   // alignments whose CIGAR has more ops than the pool stride (KSLAM_FLAG_CIGAR_OVERFLOW)
 #define CNT_TIER 16    // SWT_N_TIERS counters: alignments per work-list tier
 #define CNT_CUR 24     // SWT_N_TIERS cursors of k_tier_scatter
 #define CNT_WORDS 32
@@ -904,7 +908,40 @@ static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore 
   }
 }
 
-static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *ov, uint32_t *cig, int unflip) {
+// finalize every alignment (+ the diagonal fast path), then the literal banded_sw on what is left, then the big-scratch retry
+static void sw_traceback_stage(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore &sc, kslam_overlap *ov, uint32_t *cig, int unflip) {
+  SwWorkspace *w = c->sw;
+  cudaStream_t st = c->stream;
+  SwTask *tasks = w->tasks.as<SwTask>();
+  SwRes *res = w->res.as<SwRes>();
+  uint32_t *d_counts = c->counters.as<uint32_t>() + 32, *h_counts = c->h_counters.as<uint32_t>() + 32;
+  uint32_t *retry_count = d_counts + CNT_RETRY, *overflow_count = d_counts + CNT_OVERFLOW;
+  uint32_t *list1 = reinterpret_cast<uint32_t *>(w->keys.p), *list2 = reinterpret_cast<uint32_t *>(w->keys2.p);   // keys are dead by now
+  CUDA_TRY(cudaMemsetAsync(retry_count, 0, 4, st));
+  CUDA_TRY(cudaMemsetAsync(overflow_count, 0, 4, st));
+  k_sw_traceback<<<(n + 127) / 128, 128, 0, st>>>(tasks, res, n, nullptr, pl, sc, ov, cig, unflip, 0, list1, retry_count, overflow_count, nullptr, 0);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  const uint32_t n_dp = read_count(c, d_counts, h_counts, CNT_RETRY);
+  c->tm.n_traceback_dp = n_dp;
+  if (!n_dp) return;
+  CUDA_TRY(cudaMemsetAsync(retry_count, 0, 4, st));
+  k_sw_traceback<<<(n_dp + 127) / 128, 128, 0, st>>>(tasks, res, n_dp, list1, pl, sc, ov, cig, unflip, 1, list2, retry_count, overflow_count, nullptr, 0);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+  const uint32_t n_big = read_count(c, d_counts, h_counts, CNT_RETRY);
+  if (!n_big) return;
+  // up to 1 MiB per thread covers band 512 x 640 rows; few threads
+  const size_t per_thread = 1u << 20;
+  const uint32_t threads = n_big < 2048 ? n_big : 2048, rblocks = (threads + 127) / 128;
+  w->tb_scratch.reserve((size_t)rblocks * 128 * per_thread);
+  k_sw_traceback<<<rblocks, 128, 0, st>>>(tasks, res, n_big, list2, pl, sc, ov, cig, unflip, 2, nullptr, nullptr, overflow_count,
+                                           w->tb_scratch.as<uint8_t>(), per_thread);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+}
+
+static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *ov, uint32_t *cig, int unflip, DevBuf *grow_cig) {
   SwWorkspace *w = c->sw;
   cudaStream_t st = c->stream;
   const SwScore sc = make_score(c);
@@ -953,33 +990,15 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
     CUDA_TRY(cudaGetLastError());
   }
   cudaEvent_t e4 = tm_mark(c);
-  {
-    // finalize (+ diagonal fast path), then the literal banded_sw on what is left, then the big-scratch retry
-    uint32_t *retry_count = d_counts + CNT_RETRY;
-    uint32_t *list1 = reinterpret_cast<uint32_t *>(w->keys.p), *list2 = reinterpret_cast<uint32_t *>(w->keys2.p);   // keys are dead by now
-    CUDA_TRY(cudaMemsetAsync(retry_count, 0, 4, st));
-    k_sw_traceback<<<(n + 127) / 128, 128, 0, st>>>(tasks, res, n, nullptr, pl, sc, ov, cig, unflip, 0, list1, retry_count, nullptr, 0);
-    c->launches++;
-    CUDA_TRY(cudaGetLastError());
-    const uint32_t n_dp = read_count(c, d_counts, h_counts, CNT_RETRY);
-    c->tm.n_traceback_dp = n_dp;
-    if (n_dp) {
-      CUDA_TRY(cudaMemsetAsync(retry_count, 0, 4, st));
-      k_sw_traceback<<<(n_dp + 127) / 128, 128, 0, st>>>(tasks, res, n_dp, list1, pl, sc, ov, cig, unflip, 1, list2, retry_count, nullptr, 0);
-      c->launches++;
-      CUDA_TRY(cudaGetLastError());
-      const uint32_t n_big = read_count(c, d_counts, h_counts, CNT_RETRY);
-      if (n_big) {
-        // up to 1 MiB per thread covers band 512 x 640 rows; few threads
-        const size_t per_thread = 1u << 20;
-        uint32_t threads = n_big < 2048 ? n_big : 2048;
-        uint32_t rblocks = (threads + 127) / 128;
-        w->tb_scratch.reserve((size_t)rblocks * 128 * per_thread);
-        k_sw_traceback<<<rblocks, 128, 0, st>>>(tasks, res, n_big, list2, pl, sc, ov, cig, unflip, 2, nullptr, nullptr,
-                                                 w->tb_scratch.as<uint8_t>(), per_thread);
-        c->launches++;
-        CUDA_TRY(cudaGetLastError());
-      }
+  sw_traceback_stage(c, n, pl, make_score(c), ov, cig, unflip);
+  if (grow_cig) {
+    // A CIGAR longer than the pool stride was truncated and flagged. The reference has no such limit (ssw.c:760-790 grows
+    // its array), so the stride is raised and the stage re-run until nothing overflows; the larger stride stays with the ctx.
+    while (read_count(c, d_counts, h_counts, CNT_OVERFLOW) && c->prm.max_cigar_ops < (1u << 14)) {
+      c->prm.max_cigar_ops *= 4;
+      grow_cig->reserve((size_t)n * c->prm.max_cigar_ops * 4 + 64);
+      cig = grow_cig->as<uint32_t>();
+      sw_traceback_stage(c, n, pl, make_score(c), ov, cig, unflip);
     }
   }
   cudaEvent_t e5 = tm_mark(c);
@@ -1025,12 +1044,15 @@ __global__ void __launch_bounds__(256) k_cigar_lens(const kslam_overlap *__restr
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) lens[i] = ov[i].cigar_len;
 }
+// (the strided offset is recomputed in 64 bits: i * stride passes 2^32 words from 134 M alignments on at stride 32, and
+// ov[i].cigar_off, a u32, holds only its low half by then)
 __global__ void __launch_bounds__(256) k_cigar_compact(kslam_overlap *__restrict__ ov, uint32_t n, const uint32_t *__restrict__ offs,
-                                                       const uint32_t *__restrict__ strided, uint32_t *__restrict__ dense) {
+                                                       const uint32_t *__restrict__ strided, uint32_t stride, uint32_t *__restrict__ dense) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t len = ov[i].cigar_len, src = ov[i].cigar_off, dst = offs[i];
-  for (uint32_t j = 0; j < len; j++) dense[dst + j] = strided[src + j];
+  const uint32_t len = ov[i].cigar_len, dst = offs[i];
+  const uint32_t *src = strided + (size_t)i * stride;
+  for (uint32_t j = 0; j < len; j++) dense[dst + j] = src[j];
   ov[i].cigar_off = dst;
 }
 
@@ -1046,13 +1068,15 @@ static void compact_cigars(kslam_ctx *c, uint32_t n) {
   read_small(c, h_cnt, d_cnt, 8);
   CUDA_TRY(cudaStreamSynchronize(st));
   c->n_cig_words = h_cnt[0];
+  if (c->n_cig_words >> 32) throw ArgError{"the batch's CIGAR pool exceeds 2^32 words (kslam_overlap.cigar_off is 32 bits): use smaller batches"};
   c->cig_dense.reserve((size_t)c->n_cig_words * 4 + 64);
-  k_cigar_compact<<<(n + 255) / 256, 256, 0, st>>>(c->ov.as<kslam_overlap>(), n, offs, c->cig.as<uint32_t>(), c->cig_dense.as<uint32_t>());
+  k_cigar_compact<<<(n + 255) / 256, 256, 0, st>>>(c->ov.as<kslam_overlap>(), n, offs, c->cig.as<uint32_t>(), c->prm.max_cigar_ops, c->cig_dense.as<uint32_t>());
   c->launches += 2;
   CUDA_TRY(cudaGetLastError());
 }
 
 void sw_align_seeds(kslam_ctx *c) {
+  if (c->n_seeds >> 32) throw ArgError{"more than 2^32 seeds in one batch: use smaller batches (--num-reads-at-once)"};
   const uint32_t n = (uint32_t)c->n_seeds;
   sw_reset_timers(c);
   if (!n) return;
@@ -1073,7 +1097,7 @@ void sw_align_seeds(kslam_ctx *c) {
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   cudaEvent_t e1 = tm_mark(c);
-  sw_run(c, n, pl, c->ov.as<kslam_overlap>(), c->prm.report_cigar ? c->cig.as<uint32_t>() : nullptr, 1);
+  sw_run(c, n, pl, c->ov.as<kslam_overlap>(), c->prm.report_cigar ? c->cig.as<uint32_t>() : nullptr, 1, c->prm.report_cigar ? &c->cig : nullptr);
   cudaEvent_t e2 = tm_mark(c);
   compact_cigars(c, n);
   cudaEvent_t e3 = tm_mark(c);
@@ -1083,6 +1107,8 @@ void sw_align_seeds(kslam_ctx *c) {
 }
 
 void sw_align_pairs(kslam_ctx *c, uint64_t n64, kslam_overlap *out_dev, uint32_t *cig_dev) {
+  // the caller's pool is strided: alignment i owns words [i * max_cigar_ops, (i + 1) * max_cigar_ops), a 32-bit offset
+  if (cig_dev && (n64 * c->prm.max_cigar_ops) >> 32) throw ArgError{"n * max_cigar_ops exceeds 2^32 words: split the batch"};
   const uint32_t n = (uint32_t)n64;
   sw_reset_timers(c);
   if (!n) return;
@@ -1101,7 +1127,7 @@ void sw_align_pairs(kslam_ctx *c, uint64_t n64, kslam_overlap *out_dev, uint32_t
   c->launches++;
   CUDA_TRY(cudaGetLastError());
   cudaEvent_t e1 = tm_mark(c);
-  sw_run(c, n, pl, out_dev, cig_dev, 0);
+  sw_run(c, n, pl, out_dev, cig_dev, 0, nullptr);
   c->tm.ms_sw_prepare = tm_ms(e0, e1);
 }
 

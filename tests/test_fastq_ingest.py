@@ -134,3 +134,19 @@ def test_ring_keeps_older_batches_valid(pkg, tmp_path):
     with pkg.FastqReader(p, None) as rd:
         rd.next(10)
         assert rd.L.kslam_fastq_set_ring(rd.h, 2) != 0               # only before the first batch
+
+
+def test_fifo_input_reads_like_a_file(pkg, tmp_path):
+    """`SLAM ... <(zcat r1.fq.gz)`: a pipe has no size and cannot be mapped; the reader must drain it, not see an empty file."""
+    import threading
+    data1, data2 = fastq_bytes(300, 21, tricky=False), fastq_bytes(300, 22, tricky=False)
+    f1, f2 = str(tmp_path / "p_R1.fq"), str(tmp_path / "p_R2.fq")
+    write(f1, data1); write(f2, data2)
+    want = ours(pkg, f1, f2, 128, 3)
+    p1, p2 = str(tmp_path / "fifo1"), str(tmp_path / "fifo2")
+    os.mkfifo(p1); os.mkfifo(p2)
+    feeders = [threading.Thread(target=write, args=(p, d)) for p, d in ((p1, data1), (p2, data2))]
+    [t.start() for t in feeders]
+    got = ours(pkg, p1, p2, 128, 3)
+    [t.join() for t in feeders]
+    assert got == want and sum(len(b) for b in got) == 600

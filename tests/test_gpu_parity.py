@@ -165,6 +165,20 @@ def test_long_reads_take_the_slow_kernel(pkg):
     assert tm["n_sw_slow"] > 0
 
 
+def test_cigar_pool_stride_grows_instead_of_truncating(pkg):
+    """max_cigar_ops = 1 cannot hold a gapped CIGAR: kslam_align_batch raises the stride and re-runs the traceback until
+    nothing is flagged KSLAM_FLAG_CIGAR_OVERFLOW (the reference has no cap, ssw.c:760-790), so CIGARs equal the oracle's."""
+    gb, go = pkg.synth.random_genomes(3, 40_000, seed=5)
+    rb, ro, _ = pkg.synth.paired_reads(gb, go, 3000, seed=6, indel_frac=0.5)
+    P = T.default_params(report_cigar=1)
+    want = T.ko_pipeline(gb, go, rb, ro, P)
+    with pkg.Aligner(report_cigar=True, max_cigar_ops=1) as al:
+        al.load_genomes(gb, go)
+        got = al.align_batch(rb, ro)
+    assert (got.overlaps["cigar_len"] > 1).any() and not (got.overlaps["flags"] & 2).any()
+    check_overlaps(got.overlaps, got.cigar_pool, want["overlaps"], want["cigar_pool"])
+
+
 @pytest.mark.parametrize("name", ["ssw_150x150.npz", "ssw_150x300.npz", "ssw_101x140_nocigar.npz"])
 def test_ssw_golden(pkg, golden, name):
     g = golden(name)
