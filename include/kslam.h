@@ -20,8 +20,8 @@
  * GPU (and two per GPU to double-buffer). There is NO CPU fallback: every entry point that computes
  * fails with KSLAM_ERR_CUDA if no sm_100 device is usable.
  *
- * All arithmetic on this path is integer; results are bit-exact with the reference for scoring
- * parameters inside the domain reported by kslam_params_exact() (the defaults 2/3/5/2 are inside).
+ * All arithmetic on this path is integer; results are bit-exact with the reference for every scoring
+ * parameter set (kslam_params_fast() tells which kernels run).
  */
 #ifndef KSLAM_H_
 #define KSLAM_H_
@@ -105,9 +105,13 @@ typedef struct {
 int kslam_create(const kslam_params *params, kslam_ctx **out);
 void kslam_destroy(kslam_ctx *ctx);
 const char *kslam_last_error(const kslam_ctx *ctx); /* ctx may be NULL: last create error */
-/* 1 if results are proven bit-exact with the reference for these scoring parameters
- * (gap_extend < gap_open and mismatch <= 2*gap_extend, DESIGN.md §SSW equivalence), else 0. */
+/* Results are bit-exact with the reference for EVERY scoring parameter set (any u8 match / mismatch / gap_open /
+ * gap_extend, main.cpp:45-52): kslam_params_exact returns 1 for any non-NULL params and is kept for callers of the first
+ * release. kslam_params_fast says which kernels do the work: 1 = the packed band / wavefront kernels (SSW's striped
+ * kernels equal plain Gotoh there: gap_extend < gap_open and mismatch <= 2 * gap_extend; the defaults 2/3/5/2 are inside),
+ * 0 = the literal lane-for-lane restatement of SSW's striped byte / word kernels (ssw.c:143-592), slower. */
 int kslam_params_exact(const kslam_params *params);
+int kslam_params_fast(const kslam_params *params);
 const char *kslam_version(void);
 
 /* Pack the genomes, extract every genome_gap-th canonical 32-mer (KMer.h:160-181), sort once

@@ -124,6 +124,7 @@ def lib():
     L.kslam_last_error.restype = C.c_char_p
     L.kslam_version.restype = C.c_char_p
     L.kslam_params_exact.argtypes = [C.POINTER(Params)]
+    L.kslam_params_fast.argtypes = [C.POINTER(Params)]
     L.kslam_load_genomes.argtypes = [vp, u64, vp, vp]
     L.kslam_align_batch.argtypes = [vp, u64, vp, vp, C.POINTER(_Alignments)]
     L.kslam_upload_reads.argtypes = [vp, u64, vp, vp]
@@ -278,6 +279,11 @@ class Aligner:
     @property
     def exact(self):
         return bool(self.L.kslam_params_exact(C.byref(self.params)))
+
+    @property
+    def fast(self):
+        """True: packed band / wavefront kernels; False: the literal restatement of SSW's striped kernels (same results)."""
+        return bool(self.L.kslam_params_fast(C.byref(self.params)))
 
     # -- the path
     def load_genomes(self, bases, offs):

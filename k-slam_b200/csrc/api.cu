@@ -46,12 +46,14 @@ const char *kslam_version(void) { return "kslam-b200 0.1 (sm_100a)"; }
 
 const char *kslam_last_error(const kslam_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
-int kslam_params_exact(const kslam_params *p) {
+int kslam_params_fast(const kslam_params *p) {
   if (!p) return 0;
-  // DESIGN.md §SSW equivalence: SSW's lazy-F loop is only a full Gotoh F when gap_extend < gap_open, and its
-  // "E before lazy-F" shortcut only drops dominated paths when mismatch <= 2 * gap_extend.
-  return p->match >= 1 && p->gap_extend < p->gap_open && p->mismatch <= 2 * p->gap_extend;
+  // SSW's striped kernels compute plain Gotoh when gap_extend < gap_open (its lazy-F loops are then a full
+  // F) and mismatch <= 2 * gap_extend (its "E before lazy-F" shortcut then only drops dominated paths). Inside that domain
+  // the packed band / wavefront kernels run; outside it k_sw_striped restates the striped kernels lane for lane.
+  return p->match >= 1 && p->match <= 127 && p->mismatch <= 128 && p->gap_extend < p->gap_open && p->mismatch <= 2 * p->gap_extend;
 }
+int kslam_params_exact(const kslam_params *p) { return p != nullptr; }   // every parameter set is bit-exact now
 
 int kslam_create(const kslam_params *params, kslam_ctx **out) {
   if (!params || !out) return fail(nullptr, KSLAM_ERR_ARG, "null argument");

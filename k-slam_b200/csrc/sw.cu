@@ -77,6 +77,7 @@ struct SwPlanes {
 struct SwScore {
   int32_t match, mismatch, gap_open, gap_extend;   // positive magnitudes, as given
   uint32_t score_threshold; uint32_t report_cigar; uint32_t cigar_cap;
+  uint32_t literal;   // 1: scoring parameters outside the plain-Gotoh domain -> every alignment runs k_sw_striped
 };
 
 struct SwWorkspace {
@@ -325,6 +326,152 @@ k_sw_slow(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
   }
 }
 
+// ---------------------------------------------------------------- literal striped SSW (any scoring parameters)
+// SSW's striped kernels equal plain Gotoh only when gap_extend < gap_open and mismatch <= 2 * gap_extend (DESIGN.md
+// §3.4). Outside that domain the result depends on details of the striping itself: E is updated from the H value BEFORE
+// the lazy-F correction (ssw.c:257-264), the byte kernel's lazy-F loop runs until no lane's F exceeds H - gapO and
+// raises the column maximum as it goes (ssw.c:289-305), the word kernel's runs at most 8 rounds, leaves at the first
+// vector where no lane's F exceeds H - gapO and does NOT raise the column maximum (ssw.c:514-524). k_sw_striped
+// restates both kernels lane for lane — a group of 16 threads IS the 16 byte lanes (8 of them the word lanes), vector j
+// of lane l holds query row j + l * segLen (ssw.c:105-133,385-406), _mm_slli_si128 is a shuffle-up inside the group,
+// movemask tests are ballots — and then ssw_align's control flow: byte pass, word pass on overflow (ssw.c:868-877),
+// reverse pass over the reversed prefixes with the forward score as `terminate` (ssw.c:905-923). Speed is secondary
+// here (it only runs for non-default --match-score / --mismatch-penalty / --gap-* combinations); exactness is not.
+#define STR_GROUPS 8          // 16-lane groups per CTA
+#define STR_SMEM_SEGS 24      // state of reads up to 192 bases (word mode) lives in shared memory, longer ones in global scratch
+
+struct StripedEnd { int32_t score, ref, read; };
+
+__device__ __forceinline__ int32_t group_max16(uint32_t gmask, int32_t v) {
+#pragma unroll
+  for (int d = 8; d; d >>= 1) { const int32_t o = __shfl_xor_sync(gmask, v, d, 16); v = v > o ? v : o; }
+  return v;
+}
+__device__ __forceinline__ int32_t shift_lane(uint32_t gmask, uint32_t l, int32_t v) {   // _mm_slli_si128 by one lane
+  const int32_t o = __shfl_up_sync(gmask, v, 1, 16);
+  return l == 0 ? 0 : o;
+}
+
+// one sw_sse2_byte / sw_sse2_word call. st: 5 arrays of seg_cap * 16 shorts (Hstore, Hload, E, Hmax, row codes).
+__device__ StripedEnd striped_pass(const SwPlanes &pl, const SwTask &t, int32_t m8, int32_t x8, int32_t go, int32_t ge, int32_t bias,
+                                   bool reverse, int32_t refLen, int32_t readLen, int32_t ref_end, int32_t read_end,
+                                   int32_t terminate, bool word, int16_t *st, uint32_t seg_cap, uint32_t l, uint32_t gmask) {
+  const int32_t L = word ? 8 : 16;
+  const int32_t segLen = (readLen + L - 1) / L;
+  const bool act = (int32_t)l < L;
+  int16_t *Hs = st + l, *Hl = Hs + seg_cap * 16, *E = Hl + seg_cap * 16, *Hm = E + seg_cap * 16, *QC = Hm + seg_cap * 16;   // values fit 16 bits
+  for (int32_t j = 0; j < segLen; j++) {
+    const int32_t row = j + (int32_t)l * segLen;
+    Hs[j * 16] = 0; Hl[j * 16] = 0; E[j * 16] = 0; Hm[j * 16] = 0;
+    QC[j * 16] = (act && row < readLen) ? (int16_t)q_code(pl, t, (uint32_t)(reverse ? read_end - row : row)) : 5;   // 5 = padding row
+  }
+  int32_t max = 0, end_read = readLen - 1, end_ref = word ? 0 : -1;
+  int32_t vMaxScore = 0, vMaxMark = 0;
+  bool overflow = false;
+  for (int32_t step = 0; step < refLen; step++) {
+    const int32_t i = reverse ? refLen - 1 - step : step;
+    const int32_t c = (int32_t)w_code(pl, t, (uint32_t)i);
+    int32_t vF = 0, vMaxColumn = 0;
+    int32_t vH = shift_lane(gmask, l, Hs[(segLen - 1) * 16]);
+    { int16_t *tmp = Hl; Hl = Hs; Hs = tmp; }
+    for (int32_t j = 0; j < segLen; j++) {
+      const int32_t qc = QC[j * 16];
+      const int32_t sco = (qc == 5 || qc == 4 || c == 4) ? 0 : (qc == c ? m8 : x8);
+      int32_t h;
+      if (word) { h = vH + sco; h = h > 32767 ? 32767 : h; }                                // _mm_adds_epi16 (never below -32768 here)
+      else { h = vH + ((sco + bias) & 0xff); h = h > 255 ? 255 : h; h -= bias; h = h < 0 ? 0 : h; }   // _mm_adds_epu8, _mm_subs_epu8
+      int32_t e = E[j * 16];
+      h = h > e ? h : e; h = h > vF ? h : vF;
+      if (!act) h = 0;
+      vMaxColumn = vMaxColumn > h ? vMaxColumn : h;
+      Hs[j * 16] = (int16_t)h;
+      h -= go; h = h < 0 ? 0 : h;
+      e -= ge; e = e < 0 ? 0 : e; e = e > h ? e : h;
+      E[j * 16] = (int16_t)(act ? e : 0);
+      vF -= ge; vF = vF < 0 ? 0 : vF; vF = vF > h ? vF : h;
+      if (!act) vF = 0;
+      vH = Hl[j * 16];
+    }
+    if (!word) {                                                                             // ssw.c:276-305
+      int32_t j = 0;
+      vF = shift_lane(gmask, l, vF);
+      for (;;) {
+        int32_t h = Hs[j * 16];
+        int32_t tt = h - go; tt = tt < 0 ? 0 : tt;
+        if (!(__ballot_sync(gmask, act && vF > tt) & gmask)) break;
+        h = h > vF ? h : vF;
+        vMaxColumn = vMaxColumn > h ? vMaxColumn : h;
+        Hs[j * 16] = (int16_t)h;
+        vF -= ge; vF = vF < 0 ? 0 : vF;
+        if (++j >= segLen) { j = 0; vF = shift_lane(gmask, l, vF); }
+      }
+    } else {                                                                                 // ssw.c:512-524
+      bool done = false;
+      for (int k = 0; k < 8 && !done; k++) {
+        vF = shift_lane(gmask, l, vF);
+        if (!act) vF = 0;
+        for (int32_t j = 0; j < segLen; j++) {
+          int32_t h = Hs[j * 16];
+          h = h > vF ? h : vF;
+          Hs[j * 16] = (int16_t)h;
+          h -= go; h = h < 0 ? 0 : h;
+          vF -= ge; vF = vF < 0 ? 0 : vF;
+          if (!(__ballot_sync(gmask, act && vF > h) & gmask)) { done = true; break; }
+        }
+      }
+    }
+    vMaxScore = vMaxScore > vMaxColumn ? vMaxScore : vMaxColumn;
+    if (__ballot_sync(gmask, vMaxMark != vMaxScore) & gmask) {                              // ssw.c:307-327
+      vMaxMark = vMaxScore;
+      const int32_t temp = group_max16(gmask, vMaxScore);
+      if (temp > max) {
+        max = temp;
+        if (!word && max + bias >= 255) { overflow = true; break; }
+        end_ref = i;
+        for (int32_t j = 0; j < segLen; j++) Hm[j * 16] = Hs[j * 16];
+      }
+    }
+    if (group_max16(gmask, vMaxColumn) == terminate) break;
+  }
+  int32_t mine = end_read;                                                                   // ssw.c:334-342: smallest row holding max
+  if (act)
+    for (int32_t j = 0; j < segLen; j++)
+      if (Hm[j * 16] == max) { const int32_t row = j + (int32_t)l * segLen; mine = row < mine ? row : mine; }
+  end_read = -group_max16(gmask, -mine);
+  StripedEnd r;
+  r.score = overflow ? 255 : max; r.ref = end_ref; r.read = end_read;
+  return r;
+}
+
+__global__ void __launch_bounds__(STR_GROUPS * 16)
+k_sw_striped(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, uint32_t n_list, SwPlanes pl, SwScore sc,
+             SwRes *__restrict__ res, int16_t *__restrict__ scratch, uint32_t seg_cap) {
+  __shared__ int16_t s_state[STR_GROUPS][5 * STR_SMEM_SEGS * 16];
+  const uint32_t l = threadIdx.x & 15, grp = threadIdx.x >> 4;
+  const uint32_t gmask = 0xffffu << (threadIdx.x & 16);
+  const uint32_t slot = blockIdx.x * STR_GROUPS + grp, n_slots = gridDim.x * STR_GROUPS;
+  int16_t *st = seg_cap <= STR_SMEM_SEGS ? s_state[grp] : scratch + (size_t)slot * 5 * seg_cap * 16;
+  // the int8_t score matrix of BuildSwScoreMatrix (ssw_cpp.cpp:25-49) and ssw_init's bias (ssw.c:817-822)
+  const int32_t m8 = sc.match, x8 = -sc.mismatch;
+  int32_t bias = m8 < x8 ? m8 : x8; bias = bias < 0 ? -bias : 0;
+  for (uint32_t k = slot; k < n_list; k += n_slots) {
+    const uint32_t idx = list[k];
+    const SwTask t = tasks[idx];
+    const int32_t m = (int32_t)t.m, n = (int32_t)t.n;
+    bool word = false;
+    StripedEnd fw = striped_pass(pl, t, m8, x8, sc.gap_open, sc.gap_extend, bias, false, n, m, 0, 0, 255, false, st, seg_cap, l, gmask);
+    if (fw.score == 255) { fw = striped_pass(pl, t, m8, x8, sc.gap_open, sc.gap_extend, bias, false, n, m, 0, 0, 65535, true, st, seg_cap, l, gmask); word = true; }
+    SwRes o; o.flags = 0; o.pad0 = o.pad1 = 0;
+    o.score = fw.score; o.ref_end = fw.ref; o.read_end = fw.read; o.ref_begin = -1; o.read_begin = 0;
+    if (fw.score > 0) {
+      const StripedEnd rv = striped_pass(pl, t, m8, x8, sc.gap_open, sc.gap_extend, bias, true, fw.ref + 1, fw.read + 1, fw.ref, fw.read,
+                                         word ? fw.score : (fw.score & 0xff), word, st, seg_cap, l, gmask);
+      o.ref_begin = rv.ref; o.read_begin = fw.read - rv.read;
+    } else { o.ref_end = -1; o.read_end = 0; }
+    if (l == 0) res[idx] = o;
+  }
+}
+
 // ---------------------------------------------------------------- banded traceback (ssw.c:594-792)
 #define SET_U(u, w, i, j) { int x_ = (i) - (w); x_ = x_ > 0 ? x_ : 0; (u) = (j) - x_ + 1; }
 
@@ -339,19 +486,24 @@ __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const S
                                     uint32_t *overflow) {
   const int32_t go = sc.gap_open, ge = sc.gap_extend;
   int32_t band = (refLen > readLen ? refLen - readLen : readLen - refLen) + 1;
-  int32_t width = 0, width_d = 0, maxv = 0;
+  int32_t width = 0, width_d = 0, maxv = 0, ws = 0;
   do {
     width = band * 2 + 3; width_d = band * 2 + 1;
     if ((int64_t)width_d * readLen * 3 >= (1ll << 30)) return -2;
-    if ((uint32_t)width > arr_cap || (size_t)width_d * (size_t)readLen > dir_cap) return -3;
-    for (int32_t j = 1; j < width - 1; j++) h_b[j] = 0;
+    // A band wider than the reference sequence touches only slots 0..refLen of the rolling arrays and refLen direction
+    // cells per row (j stays inside [0, refLen)), so the scratch is sized by what is touched, not by the nominal width:
+    // the band may double up to the "no cigar" limit above without leaving the scratch.
+    const int32_t aw = width < refLen + 2 ? width : refLen + 2;
+    ws = width_d < refLen ? width_d : refLen;
+    if ((uint32_t)aw > arr_cap || (size_t)ws * (size_t)readLen > dir_cap) return -3;
+    for (int32_t j = 1; j < aw - 1; j++) h_b[j] = 0;
     for (int32_t i = 0; i < readLen; i++) {
       int32_t beg = i - band > 0 ? i - band : 0, end = i + band < refLen - 1 ? i + band : refLen - 1;
       int32_t edge = end + 1 < width - 1 ? end + 1 : width - 1, u = 0;
       int32_t f = 0;
       h_b[0] = 0; e_b[0] = 0; h_b[edge] = 0; e_b[edge] = 0; h_c[0] = 0;
       const uint32_t qc = q_code(pl, t, (uint32_t)(read0 + i));
-      uint8_t *dl = dir + (size_t)width_d * i * dstride;
+      uint8_t *dl = dir + (size_t)ws * i * dstride;
       const int32_t xoff = i - band > 0 ? i - band : 0;
       for (int32_t j = beg; j <= end; j++) {
         int32_t e, b, d;
@@ -390,7 +542,7 @@ __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const S
     while (i > 0) {
       const int32_t lo = i - band > 0 ? i - band : 0, hi = i + band < refLen - 1 ? i + band : refLen - 1;
       if (j < lo || j > hi) return -1;
-      const uint32_t cell = dir[((size_t)width_d * i + (size_t)(j - lo)) * dstride];
+      const uint32_t cell = dir[((size_t)ws * i + (size_t)(j - lo)) * dstride];
       uint32_t code = st == 2 ? (cell >> 2) : (st == 0 ? ((cell & 1u) ? 3u : 2u) : ((cell & 2u) ? 5u : 4u));
       switch (code) {
         case 1: --i; --j; st = 2; f = 0; break;
@@ -499,7 +651,7 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
         const int32_t refLen = r.ref_end - r.ref_begin + 1, readLen = r.read_end - r.read_begin + 1;
         uint32_t overflow = 0; int32_t len;
         if (mode == 0) {
-          if (refLen == readLen && sc.cigar_cap >= 1 && diagonal_score(pl, t, sc, r.ref_begin, r.read_begin, readLen) == r.score) {
+          if (!sc.literal && refLen == readLen && sc.cigar_cap >= 1 && diagonal_score(pl, t, sc, r.ref_begin, r.read_begin, readLen) == r.score) {
             cig[0] = (uint32_t)readLen << 4; len = 1;
           } else len = -3;
         } else if (mode == 1)
@@ -605,6 +757,7 @@ __device__ __forceinline__ void count_tier(uint32_t tier, uint32_t *__restrict__
 
 __device__ __forceinline__ uint32_t classify(uint32_t m, uint32_t n, const SwScore &sc) {
   if (m == 0 || n == 0) return SWC_NONE;
+  if (sc.literal) return SWC_SLOW;     // the slow list is run by k_sw_striped for such parameters
   const uint32_t mn = m < n ? m : n;
   // 16-bit cells: the largest possible score, scaled by 32 and biased (sw_bias), must stay below 2^15
   const bool score_ok = sc.match >= 1 && sc.match * 32 <= 127 && sc.mismatch * 32 <= 128 && sc.gap_open <= 100 && sc.gap_extend <= 100 &&
@@ -826,7 +979,10 @@ double sw_measure_int_peak(kslam_ctx *c) {
 // ---------------------------------------------------------------- host orchestration
 static SwScore make_score(const kslam_ctx *c) {
   SwScore s;
-  s.match = c->prm.match; s.mismatch = c->prm.mismatch; s.gap_open = c->prm.gap_open; s.gap_extend = c->prm.gap_extend;
+  // the reference stores the scores in an int8_t matrix: match as is, mismatch as static_cast<int8_t>(-mismatch) (ssw_cpp.cpp:25-49)
+  s.match = (int8_t)c->prm.match; s.mismatch = -(int32_t)(int8_t)(-(int32_t)c->prm.mismatch);
+  s.gap_open = c->prm.gap_open; s.gap_extend = c->prm.gap_extend;
+  s.literal = kslam_params_fast(&c->prm) ? 0u : 1u;
   s.score_threshold = c->prm.score_threshold; s.report_cigar = c->prm.report_cigar; s.cigar_cap = c->prm.max_cigar_ops;
   return s;
 }
@@ -984,8 +1140,16 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
     uint32_t max_rows = c->reads_loaded ? c->reads.max_len : 0;
     if (c->sw_loaded && c->swq.max_len > max_rows) max_rows = c->swq.max_len;
     uint32_t blocks = (n_slow + 127) / 128; if (blocks > (uint32_t)c->num_sms * 4) blocks = c->num_sms * 4;
+    if (sc.literal) {
+      const uint32_t seg_cap = (max_rows + 7) / 8 + 1;
+      blocks = (n_slow + STR_GROUPS - 1) / STR_GROUPS; if (blocks > (uint32_t)c->num_sms * 8) blocks = c->num_sms * 8;
+      if (seg_cap > STR_SMEM_SEGS) w->tb_scratch.reserve((size_t)blocks * STR_GROUPS * 5 * seg_cap * 16 * 2 + 64);
+      else w->tb_scratch.reserve(64);
+      k_sw_striped<<<blocks, STR_GROUPS * 16, 0, st>>>(tasks, slow_list, n_slow, pl, sc, res, w->tb_scratch.as<int16_t>(), seg_cap);
+    } else {
     w->tb_scratch.reserve((size_t)blocks * 128 * max_rows * 8 + 64);
     k_sw_slow<<<blocks, 128, 0, st>>>(tasks, slow_list, n_slow, pl, sc, res, w->tb_scratch.as<int32_t>(), max_rows);
+    }
     c->launches++;
     CUDA_TRY(cudaGetLastError());
   }

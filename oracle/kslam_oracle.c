@@ -123,15 +123,18 @@ static inline int8_t ssw_code(char c) {
     default: return 4;
   }
 }
-/* ssw_cpp.cpp:25-49 (BuildSwScoreMatrix): any pair involving code 4 scores 0 */
+/* ssw_cpp.cpp:25-49 (BuildSwScoreMatrix): any pair involving code 4 scores 0. match / mismatch arrive as uint8_t
+ * (ssw_cpp.cpp:114-117) and are stored in an int8_t matrix: match as is, mismatch as static_cast<int8_t>(-mismatch). */
 static inline int32_t sc(const ko_params *p, int8_t a, int8_t b) {
   if (a == 4 || b == 4) return 0;
-  return a == b ? (int32_t)(uint8_t)p->match : -(int32_t)(int8_t)(uint8_t)p->mismatch;
+  return a == b ? (int32_t)(int8_t)(uint8_t)p->match : (int32_t)(int8_t)(-(int32_t)(uint8_t)p->mismatch);
 }
 
 typedef struct { int32_t score, ref, read; } sw_end;
 
-/* ssw.c:143-383 / 408-592 restated without striping.
+/* ssw.c:143-383 / 408-592 restated without striping: plain Gotoh with SSW's tie rules.
+ * Equal to the striped kernels when gap_extend < gap_open and mismatch <= 2 * gap_extend (checked by
+ * tests/test_oracle_vs_ref.py); kept as the cross-check of sw_striped below, which is what ko_ssw_align uses.
  * Columns are scanned from `begin` in direction `step`; q[0..m) are query rows.
  * Returns the max score, the first column (scan order) attaining it, and the smallest row holding it
  * in that column. If terminate >= 0, stop after the first column whose max equals it (ssw.c:330,545). */
@@ -160,6 +163,112 @@ static sw_end sw_scan(const int8_t *ref, int32_t ref_len, int dir, const int8_t 
     if (terminate >= 0 && colmax == terminate) break;
   }
   return best;
+}
+
+/* sw_sse2_byte (ssw.c:143-383, word == 0) and sw_sse2_word (ssw.c:408-592, word == 1) LITERALLY, lane by lane: the
+ * striped layout (vector j, lane l <-> query row j + l * segLen, ssw.c:105-133,385-406), the saturating byte arithmetic
+ * with its bias, E updated from the H value BEFORE the lazy-F correction (:257-264), the two different lazy-F loops
+ * (byte: until no lane's F exceeds H - gapO, vMaxColumn updated inside, :289-305; word: at most 8 rounds, early exit on
+ * the first vector where no lane's F exceeds H - gapO, vMaxColumn NOT updated, :514-524) and the end-position rules
+ * (:307-343,526-558). For scoring parameters outside the "plain Gotoh" domain those details decide the result.
+ * buf: 9 * segLen * lanes int32 of scratch. Values are held in int32 but clamped exactly like the 8 / 16-bit lanes. */
+static sw_end sw_striped(const int8_t *ref, int dir, int32_t refLen, const int8_t *read, int32_t readLen, const int8_t *mat,
+                         int32_t go, int32_t ge, int32_t terminate, int word, int32_t bias, int32_t *buf) {
+  const int L = word ? 8 : 16;
+  const int32_t segLen = (readLen + L - 1) / L, N = segLen * L;
+  int32_t *Hs = buf, *Hl = buf + N, *E = buf + 2 * N, *Hm = buf + 3 * N, *P = buf + 4 * N;   /* P: 5 * N */
+  for (int32_t nt = 0; nt < 5; nt++)
+    for (int32_t i = 0; i < segLen; i++)
+      for (int l = 0; l < L; l++) {
+        const int32_t j = i + l * segLen;
+        if (word) P[nt * N + i * L + l] = j >= readLen ? 0 : mat[nt * 5 + read[j]];
+        else P[nt * N + i * L + l] = j >= readLen ? (uint8_t)bias : (uint8_t)(mat[nt * 5 + read[j]] + bias);
+      }
+  for (int32_t k = 0; k < 4 * N; k++) buf[k] = 0;
+  int32_t max = 0, end_read = readLen - 1, end_ref = word ? 0 : -1;
+  int32_t vMaxScore[16] = {0}, vMaxMark[16] = {0}, vF[16], vH[16], vMaxColumn[16];
+  const int32_t begin = dir ? refLen - 1 : 0, end = dir ? -1 : refLen, step = dir ? -1 : 1;
+  for (int32_t i = begin; i != end; i += step) {
+    for (int l = 0; l < L; l++) { vF[l] = 0; vMaxColumn[l] = 0; }
+    for (int l = L - 1; l > 0; l--) vH[l] = Hs[(segLen - 1) * L + l - 1];     /* _mm_slli_si128 by one lane */
+    vH[0] = 0;
+    const int32_t *vP = P + ref[i] * N;
+    { int32_t *t = Hl; Hl = Hs; Hs = t; }
+    for (int32_t j = 0; j < segLen; j++)
+      for (int l = 0; l < L; l++) {
+        int32_t h = vH[l] + vP[j * L + l];
+        if (word) { if (h > 32767) h = 32767; if (h < -32768) h = -32768; }   /* _mm_adds_epi16 */
+        else { if (h > 255) h = 255; h -= bias; if (h < 0) h = 0; }             /* _mm_adds_epu8, _mm_subs_epu8 */
+        int32_t e = E[j * L + l];
+        if (h < e) h = e;
+        if (h < vF[l]) h = vF[l];
+        if (vMaxColumn[l] < h) vMaxColumn[l] = h;
+        Hs[j * L + l] = h;
+        h -= go; if (h < 0) h = 0;
+        e -= ge; if (e < 0) e = 0;
+        if (e < h) e = h;
+        E[j * L + l] = e;
+        int32_t f = vF[l] - ge; if (f < 0) f = 0;
+        vF[l] = f > h ? f : h;
+        vH[l] = Hl[j * L + l];
+      }
+    if (!word) {                                                              /* ssw.c:276-305 */
+      int32_t j = 0;
+      for (int l = L - 1; l > 0; l--) vF[l] = vF[l - 1];
+      vF[0] = 0;
+      for (;;) {
+        int any = 0;
+        for (int l = 0; l < L; l++) { int32_t t = Hs[j * L + l] - go; if (t < 0) t = 0; any |= vF[l] > t; }
+        if (!any) break;
+        for (int l = 0; l < L; l++) {
+          int32_t h = Hs[j * L + l];
+          if (h < vF[l]) h = vF[l];
+          if (vMaxColumn[l] < h) vMaxColumn[l] = h;
+          Hs[j * L + l] = h;
+          vF[l] -= ge; if (vF[l] < 0) vF[l] = 0;
+        }
+        if (++j >= segLen) { j = 0; for (int l = L - 1; l > 0; l--) vF[l] = vF[l - 1]; vF[0] = 0; }
+      }
+    } else {                                                                  /* ssw.c:512-524 */
+      int done = 0;
+      for (int k = 0; k < 8 && !done; k++) {
+        for (int l = L - 1; l > 0; l--) vF[l] = vF[l - 1];
+        vF[0] = 0;
+        for (int32_t j = 0; j < segLen && !done; j++) {
+          int any = 0;
+          for (int l = 0; l < L; l++) {
+            int32_t h = Hs[j * L + l];
+            if (h < vF[l]) h = vF[l];
+            Hs[j * L + l] = h;
+            h -= go; if (h < 0) h = 0;
+            vF[l] -= ge; if (vF[l] < 0) vF[l] = 0;
+            any |= vF[l] > h;
+          }
+          if (!any) done = 1;
+        }
+      }
+    }
+    int differs = 0;
+    for (int l = 0; l < L; l++) { if (vMaxScore[l] < vMaxColumn[l]) vMaxScore[l] = vMaxColumn[l]; differs |= vMaxMark[l] != vMaxScore[l]; }
+    if (differs) {
+      int32_t temp = 0;
+      for (int l = 0; l < L; l++) { vMaxMark[l] = vMaxScore[l]; if (temp < vMaxScore[l]) temp = vMaxScore[l]; }
+      if (temp > max) {
+        max = temp;
+        if (!word && max + bias >= 255) break;                                /* overflow, ssw.c:318 */
+        end_ref = i;
+        for (int32_t k = 0; k < N; k++) Hm[k] = Hs[k];
+      }
+    }
+    int32_t colmax = 0;
+    for (int l = 0; l < L; l++) if (colmax < vMaxColumn[l]) colmax = vMaxColumn[l];
+    if (colmax == terminate) break;
+  }
+  for (int32_t k = 0; k < N; k++)                                             /* ssw.c:334-342,549-557 */
+    if (Hm[k] == max) { const int32_t row = k / L + k % L * segLen; if (row < end_read) end_read = row; }
+  sw_end r;
+  r.score = (!word && max + bias >= 255) ? 255 : max; r.ref = end_ref; r.read = end_read;
+  return r;
 }
 
 /* ssw.c:56-71 */
@@ -255,17 +364,24 @@ static int32_t banded_cigar(const int8_t *ref, const int8_t *read, int32_t refLe
   return n;
 }
 
-/* ssw_cpp.cpp:234-283 (Aligner::Align) -> ssw.c:841-951 (ssw_align) */
+/* ssw_cpp.cpp:234-283 (Aligner::Align) -> ssw.c:808-833 (ssw_init) + ssw.c:841-951 (ssw_align) */
 void ko_ssw_align(const char *qs, int32_t qlen, const char *rs, int32_t rlen, const ko_params *p,
                   ko_overlap *out, uint32_t *cigar, uint32_t cigar_cap) {
   int8_t *q = (int8_t *)malloc((size_t)qlen + 1), *r = (int8_t *)malloc((size_t)rlen + 1);
   int8_t *qr = (int8_t *)malloc((size_t)qlen + 1);
-  int32_t *H = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)(qlen + 1)), *E = H + qlen + 1;
+  int32_t *buf = (int32_t *)malloc(sizeof(int32_t) * 9 * (size_t)(qlen + 16));
   for (int32_t i = 0; i < qlen; i++) q[i] = ssw_code(qs[i]);
   for (int32_t i = 0; i < rlen; i++) r[i] = ssw_code(rs[i]);
+  int8_t mat[25];
+  int32_t bias = 0;
+  for (int a = 0; a < 5; a++) for (int b = 0; b < 5; b++) { mat[a * 5 + b] = (int8_t)sc(p, (int8_t)a, (int8_t)b); if (mat[a * 5 + b] < bias) bias = mat[a * 5 + b]; }
+  bias = abs(bias);                                                            /* ssw.c:817-822 */
+  const int32_t go = (uint8_t)p->gap_open, ge = (uint8_t)p->gap_extend;
   out->cigar_len = 0; out->flags = 0;
-  /* forward pass: byte pass and (on overflow) word pass give the same answer, ssw.c:871-877 */
-  sw_end fw = sw_scan(r, rlen, 0, q, qlen, p, -1, H, E);
+  /* forward: byte pass, word pass when the byte pass overflowed (ssw.c:868-877) */
+  int word = 0;
+  sw_end fw = sw_striped(r, 0, rlen, q, qlen, mat, go, ge, 255, 0, bias, buf);
+  if (fw.score == 255) { fw = sw_striped(r, 0, rlen, q, qlen, mat, go, ge, 65535, 1, bias, buf); word = 1; }
   out->sw_score = (uint16_t)fw.score; out->ref_end = fw.ref; out->query_end = fw.read;
   if (fw.score == 0) {
     /* degenerate (ssw.c:169 end_ref=-1; reverse pass over an empty range): begins -1 / 0;
@@ -276,12 +392,15 @@ void ko_ssw_align(const char *qs, int32_t qlen, const char *rs, int32_t rlen, co
   }
   /* reverse pass, ssw.c:905-923 */
   for (int32_t i = 0; i <= fw.read; i++) qr[i] = q[fw.read - i]; /* seq_reverse ssw.c:794-806 */
-  sw_end rv = sw_scan(r, fw.ref + 1, 1, qr, fw.read + 1, p, fw.score, H, E);
-  out->ref_begin = rv.ref; out->query_begin = fw.read - rv.read;
+  {
+    const sw_end rv = sw_striped(r, 1, fw.ref + 1, qr, fw.read + 1, mat, go, ge, word ? fw.score : (int32_t)(uint8_t)fw.score, word, bias, buf);
+    out->ref_begin = rv.ref; out->query_begin = fw.read - rv.read;
+  }
   /* cigar, ssw.c:924-946; flag = 0x0f iff report_cigar (ssw_cpp.cpp:90-93), filters = score_filter */
   if (p->report_cigar && fw.score >= (int32_t)(uint16_t)p->score_threshold) {
     int overflow = 0;
     int32_t refLen = out->ref_end - out->ref_begin + 1, readLen = out->query_end - out->query_begin + 1;
+    if (out->ref_begin < 0 || refLen <= 0 || readLen <= 0) { out->flags |= KO_FLAG_UNDEFINED; goto done; }   /* banded_sw would read outside ref / read */
     int32_t n = banded_cigar(r + out->ref_begin, q + out->query_begin, refLen, readLen, fw.score, p,
                              cigar, cigar_cap, &overflow);
     if (n == -2) { out->cigar_len = 0; out->sw_score = 0; }   /* ssw.c:941-944 */
@@ -289,6 +408,25 @@ void ko_ssw_align(const char *qs, int32_t qlen, const char *rs, int32_t rlen, co
     else { out->cigar_len = (uint32_t)n; if (overflow) out->flags |= KO_FLAG_CIGAR_OVERFLOW; }
   }
 done:
+  free(q); free(r); free(qr); free(buf);
+}
+
+/* The same alignment through the un-striped scan (plain Gotoh): the cross-check of the striped restatement inside the
+ * domain where the two are equal. Fills score and the four coordinates only. */
+void ko_ssw_align_gotoh(const char *qs, int32_t qlen, const char *rs, int32_t rlen, const ko_params *p, ko_overlap *out) {
+  int8_t *q = (int8_t *)malloc((size_t)qlen + 1), *r = (int8_t *)malloc((size_t)rlen + 1), *qr = (int8_t *)malloc((size_t)qlen + 1);
+  int32_t *H = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)(qlen + 1)), *E = H + qlen + 1;
+  for (int32_t i = 0; i < qlen; i++) q[i] = ssw_code(qs[i]);
+  for (int32_t i = 0; i < rlen; i++) r[i] = ssw_code(rs[i]);
+  memset(out, 0, sizeof *out);
+  sw_end fw = sw_scan(r, rlen, 0, q, qlen, p, -1, H, E);
+  out->sw_score = (uint16_t)fw.score; out->ref_end = fw.ref; out->query_end = fw.read;
+  if (fw.score == 0) { out->ref_end = -1; out->query_end = 0; out->ref_begin = -1; out->query_begin = 0; }
+  else {
+    for (int32_t i = 0; i <= fw.read; i++) qr[i] = q[fw.read - i];
+    sw_end rv = sw_scan(r, fw.ref + 1, 1, qr, fw.read + 1, p, fw.score, H, E);
+    out->ref_begin = rv.ref; out->query_begin = fw.read - rv.read;
+  }
   free(q); free(r); free(qr); free(H);
 }
 

@@ -67,6 +67,9 @@ uint64_t ko_sort_unique_seeds(ko_seed *seeds, uint64_t n);
  * cigar (capacity cigar_cap u32) may be NULL when !report_cigar. */
 void ko_ssw_align(const char *q, int32_t qlen, const char *r, int32_t rlen, const ko_params *p,
                   ko_overlap *out, uint32_t *cigar, uint32_t cigar_cap);
+/* Cross-check: the same alignment through plain (un-striped) Gotoh with SSW's tie rules; equal to ko_ssw_align's score and
+ * coordinates when gap_extend < gap_open and mismatch <= 2 * gap_extend. */
+void ko_ssw_align_gotoh(const char *q, int32_t qlen, const char *r, int32_t rlen, const ko_params *p, ko_overlap *out);
 /* Batched form used by tests and the CPU baseline; cigar pool has cigar_cap u32 per pair. */
 void ko_ssw_batch(uint64_t n, const char *q, const uint64_t *qoffs, const char *r,
                   const uint64_t *roffs, const ko_params *p, ko_overlap *out, uint32_t *cigar_pool,

@@ -80,6 +80,7 @@ def oracle():
         L.ko_sort_unique_seeds.argtypes = [C.c_void_p, C.c_uint64]
         L.ko_ssw_batch.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.POINTER(KoParams), C.c_void_p, C.c_void_p, C.c_uint32, C.c_int]
+        L.ko_ssw_align_gotoh.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(KoParams), C.c_void_p]
         L.ko_align_seeds.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(KoParams), C.c_void_p, C.c_uint32, C.c_int]
         L.ko_sort_for_pairing.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
@@ -211,6 +212,18 @@ def ko_ssw_batch(q, qoffs, r, roffs, params, cigar_cap=64, threads=8):
     pool = np.zeros(n * cigar_cap, dtype=np.uint32)
     L.ko_ssw_batch(n, _p(q), _p(qoffs), _p(r), _p(roffs), C.byref(params), _p(out), _p(pool), cigar_cap, threads)
     return out, pool
+
+
+def ko_ssw_gotoh(q, qoffs, r, roffs, params):
+    """Score and coordinates through the un-striped (plain Gotoh) scan: the cross-check of the striped restatement."""
+    L = oracle()
+    q = u8(q); r = u8(r)
+    n = len(qoffs) - 1
+    out = np.zeros(n, dtype=OVERLAP_DT)
+    for i in range(n):
+        L.ko_ssw_align_gotoh(q.ctypes.data + int(qoffs[i]), int(qoffs[i + 1] - qoffs[i]), r.ctypes.data + int(roffs[i]),
+                             int(roffs[i + 1] - roffs[i]), C.byref(params), out.ctypes.data + i * OVERLAP_DT.itemsize)
+    return out
 
 
 def ko_pipeline(gen_bases, gen_offs, read_bases, read_offs, params, cigar_cap=64, threads=8, paired=True):

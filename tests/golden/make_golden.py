@@ -37,9 +37,9 @@ def pipeline_fixture(name, gb, go, rb, ro, params):
           "pairs", len(pairs))
 
 
-def ssw_fixture(name, q, qo, r, ro, params):
-    a, pool = T.ref_ssw_batch(q, qo, r, ro, params, cigar_cap=32)
-    assert (a["cigar_len"] <= 32).all()
+def ssw_fixture(name, q, qo, r, ro, params, cigar_cap=32):
+    a, pool = T.ref_ssw_batch(q, qo, r, ro, params, cigar_cap=cigar_cap)
+    assert (a["cigar_len"] <= cigar_cap).all()
     np.savez_compressed(os.path.join(HERE, name), q=q, qoffs=qo, r=r, roffs=ro,
                         params=np.array([params.match, params.mismatch, params.gap_open, params.gap_extend,
                                          params.score_threshold, params.report_cigar], dtype=np.int64),
@@ -122,8 +122,18 @@ def boost_archive_fixture(name):
     print(name, "archive bytes", len((tmp / "real").read_bytes()))
 
 
+def ssw_params_fixtures():
+    """Scoring parameters outside the plain-Gotoh domain (SSW's result depends on its striping there)."""
+    q, qo, r, ro2 = synth.sw_pairs(800, 130, 150, seed=24)
+    for prm in ((5, 4, 10, 10), (2, 8, 3, 3), (1, 1, 1, 1)):
+        P = T.default_params(report_cigar=1, match=prm[0], mismatch=prm[1], gap_open=prm[2], gap_extend=prm[3])
+        ssw_fixture("ssw_params_%d_%d_%d_%d.npz" % prm, q, qo, r, ro2, P, cigar_cap=256)
+
+
 def main():
     sys.path.insert(0, os.path.dirname(HERE))
+    if len(sys.argv) > 1 and sys.argv[1] == "ssw-params":
+        return ssw_params_fixtures()
     if len(sys.argv) > 1 and sys.argv[1] == "meta":
         return meta_fixture("meta_mini.npz")
     if len(sys.argv) > 1 and sys.argv[1] == "boost":
@@ -145,6 +155,7 @@ def main():
     ssw_fixture("ssw_150x300.npz", q, qo, r, ro2, T.default_params(report_cigar=1))
     q, qo, r, ro2 = synth.sw_pairs(800, 101, 140, seed=23)
     ssw_fixture("ssw_101x140_nocigar.npz", q, qo, r, ro2, T.default_params(report_cigar=0))
+    ssw_params_fixtures()
 
 
 if __name__ == "__main__":

@@ -24,12 +24,13 @@ def test_record_layouts_match_header(pkg):
 
 
 def test_exact_domain(pkg):
+    """Every scoring parameter set is bit-exact; kslam_params_fast tells which kernels run (packed vs literal striped)."""
     L = pkg.lib()
     ok = pkg.Params(2, 3, 5, 2, 0, 0, 0, 0, 16, 32, 0)
-    assert L.kslam_params_exact(C.byref(ok)) == 1
-    for bad in [(5, 4, 10, 10), (1, 1, 1, 1), (2, 8, 3, 3)]:   # gap_extend >= gap_open or mismatch > 2*gap_extend
-        p = pkg.Params(*bad, 0, 0, 0, 0, 16, 32, 0)
-        assert L.kslam_params_exact(C.byref(p)) == 0
+    assert L.kslam_params_exact(C.byref(ok)) == 1 and L.kslam_params_fast(C.byref(ok)) == 1
+    for slow in [(5, 4, 10, 10), (1, 1, 1, 1), (2, 8, 3, 3)]:   # gap_extend >= gap_open or mismatch > 2*gap_extend
+        p = pkg.Params(*slow, 0, 0, 0, 0, 16, 32, 0)
+        assert L.kslam_params_exact(C.byref(p)) == 1 and L.kslam_params_fast(C.byref(p)) == 0
 
 
 def test_no_cpu_fallback(pkg):

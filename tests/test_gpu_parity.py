@@ -212,6 +212,78 @@ def test_ssw_vs_oracle(pkg, shape, cigar, band):
         assert tm["n_sw_band"] == 0 and tm["n_sw_fast"] == 20_000
 
 
+OUTSIDE = [(5, 4, 10, 10), (1, 1, 1, 1), (2, 8, 3, 3), (3, 1, 1, 4), (2, 9, 2, 1), (4, 6, 4, 4), (10, 2, 3, 3), (2, 3, 2, 5), (3, 0, 0, 0)]
+
+
+@pytest.mark.parametrize("prm", OUTSIDE)
+def test_ssw_scoring_outside_the_gotoh_domain(pkg, prm):
+    """gap_extend >= gap_open or mismatch > 2 * gap_extend (main.cpp:45-52 accepts anything): SSW's result depends on its
+    striping and k_sw_striped restates the striped byte / word kernels lane for lane (ssw.c:143-592). Score, coordinates and
+    CIGAR against the oracle, which tests/test_oracle_vs_ref.py pins to the compiled reference for these parameters."""
+    m, x, go, ge = prm
+    for shape, n, thr in (((150, 150), 4000, 0), ((120, 160), 3000, 90), ((40, 64), 1500, 0)):
+        q, qo, r, ro = pkg.synth.sw_pairs(n, shape[0], shape[1], seed=500 + shape[0] + m)
+        for cigar in (1, 0):
+            P = T.default_params(report_cigar=cigar, match=m, mismatch=x, gap_open=go, gap_extend=ge, score_threshold=thr)
+            want, wpool = T.ko_ssw_batch(q, qo, r, ro, P, cigar_cap=512)
+            with pkg.Aligner(match=m, mismatch=x, gap_open=go, gap_extend=ge, score_threshold=thr, report_cigar=bool(cigar), max_cigar_ops=512) as al:
+                assert al.exact and not al.fast
+                out, pool = al.ssw_batch(q, qo, r, ro)
+                tm = al.timings()
+            assert tm["n_sw_slow"] == n and tm["n_sw_fast"] == 0 and tm["n_sw_band"] == 0
+            check_overlaps(out, pool, want, wpool, fields=FIELDS[4:], cigars=bool(cigar))
+
+
+@pytest.mark.parametrize("name", ["ssw_params_5_4_10_10.npz", "ssw_params_2_8_3_3.npz", "ssw_params_1_1_1_1.npz"])
+def test_ssw_outside_domain_golden(pkg, golden, name):
+    """The same against vectors the UNMODIFIED reference produced here (tests/golden/make_golden.py)."""
+    g = golden(name)
+    P = params_of(g)
+    with pkg.Aligner(match=P.match, mismatch=P.mismatch, gap_open=P.gap_open, gap_extend=P.gap_extend, report_cigar=True, max_cigar_ops=256) as al:
+        out, pool = al.ssw_batch(g["q"], g["qoffs"], g["r"], g["roffs"])
+    check_overlaps(out, pool, g["expect"].copy(), g["cigar_pool"], fields=FIELDS[4:], cigars=True)
+
+
+def test_ssw_outside_domain_long_and_ragged_reads(pkg):
+    """Reads of 1-400 bases (the striped state of the long ones lives in global scratch), repeats, N's."""
+    rng = np.random.default_rng(9)
+    ACGT = pkg.synth.ACGT
+    qs, rs = [], []
+    for _ in range(1500):
+        per = int(rng.integers(2, 40)); unit = ACGT[rng.integers(0, 4, size=per)]
+        L = int(rng.integers(20, 420)); w = np.tile(unit, L // per + 2)[:L].copy()
+        mm = rng.random(L) < 0.05; w[mm] = ACGT[rng.integers(0, 4, size=int(mm.sum()))]
+        ql = int(rng.integers(1, 401)); st = int(rng.integers(0, max(1, L - ql))); qq = w[st:st + ql].copy()
+        if len(qq) == 0:
+            qq = ACGT[rng.integers(0, 4, size=5)]
+        mm = rng.random(len(qq)) < 0.05; qq[mm] = ACGT[rng.integers(0, 4, size=int(mm.sum()))]
+        if rng.random() < 0.1:
+            qq[rng.integers(0, len(qq))] = ord("N")
+        qs.append(qq); rs.append(w)
+    q, qo = T.concat(qs); r, ro = T.concat(rs)
+    for (m, x, go, ge) in [(5, 4, 10, 10), (2, 8, 3, 3)]:
+        P = T.default_params(report_cigar=1, match=m, mismatch=x, gap_open=go, gap_extend=ge)
+        want, wpool = T.ko_ssw_batch(q, qo, r, ro, P, cigar_cap=1024)
+        with pkg.Aligner(match=m, mismatch=x, gap_open=go, gap_extend=ge, report_cigar=True, max_cigar_ops=1024) as al:
+            out, pool = al.ssw_batch(q, qo, r, ro)
+        check_overlaps(out, pool, want, wpool, fields=FIELDS[4:], cigars=True)
+
+
+@pytest.mark.parametrize("prm", [(5, 4, 10, 10), (2, 8, 3, 3)])
+def test_pipeline_scoring_outside_the_gotoh_domain(pkg, prm):
+    """The whole path (seeds, windows, un-flip, CIGAR pool, pairing) with such parameters."""
+    m, x, go, ge = prm
+    gb, go_, rb, ro = pkg.synth.adversarial_set(seed=21, n_genomes=8, glen=10_000, n_pairs=1200)
+    P = T.default_params(report_cigar=1, match=m, mismatch=x, gap_open=go, gap_extend=ge)
+    want = T.ko_pipeline(gb, go_, rb, ro, P, cigar_cap=256)
+    with pkg.Aligner(match=m, mismatch=x, gap_open=go, gap_extend=ge, report_cigar=True) as al:
+        al.load_genomes(gb, go_)
+        got = al.align_batch(rb, ro)
+        pairs = al.pair_batch()
+    check_overlaps(got.overlaps, got.cigar_pool, want["overlaps"], want["cigar_pool"])
+    assert np.array_equal(pairs.pairs, want["pairs"])
+
+
 def test_ssw_ragged_lengths_and_repeats(pkg):
     rng = np.random.default_rng(5)
     ACGT = pkg.synth.ACGT

@@ -35,11 +35,12 @@ def test_pipeline_golden(golden, name):
     assert np.array_equal(got["pairs"], g["pairs"])
 
 
-@pytest.mark.parametrize("name", ["ssw_150x150.npz", "ssw_150x300.npz", "ssw_101x140_nocigar.npz"])
+@pytest.mark.parametrize("name", ["ssw_150x150.npz", "ssw_150x300.npz", "ssw_101x140_nocigar.npz",
+                                  "ssw_params_5_4_10_10.npz", "ssw_params_2_8_3_3.npz", "ssw_params_1_1_1_1.npz"])
 def test_ssw_golden(golden, name):
     g = golden(name)
     P = params_of(g)
-    b, pb = T.ko_ssw_batch(g["q"], g["qoffs"], g["r"], g["roffs"], P, cigar_cap=32)
+    b, pb = T.ko_ssw_batch(g["q"], g["qoffs"], g["r"], g["roffs"], P, cigar_cap=len(g["cigar_pool"]) // len(g["expect"]))
     a = g["expect"]
     for f in FIELDS[4:]:
         assert np.array_equal(a[f], b[f]), f

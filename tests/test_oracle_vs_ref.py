@@ -91,11 +91,53 @@ def test_ssw_tandem_repeats(pkg):
         assert_overlaps_equal(a[ok], pa, b[ok], pb)
 
 
-def test_ssw_other_scoring_inside_exact_domain(pkg):
-    """Parameters with gap_extend < gap_open and mismatch <= 2*gap_extend (DESIGN.md §SSW equivalence)."""
+COORDS = ["ref_begin", "ref_end", "query_begin", "query_end", "sw_score"]
+
+
+def test_ssw_other_scoring_inside_the_gotoh_domain(pkg):
+    """Parameters with gap_extend < gap_open and mismatch <= 2*gap_extend: the striped restatement equals
+    the reference, and plain Gotoh (what the packed CUDA kernels compute) equals both."""
     q, qo, r, ro = pkg.synth.sw_pairs(3000, 120, 160, seed=77)
-    for (m, x, go, ge) in [(1, 2, 6, 1), (2, 4, 6, 2), (3, 4, 5, 3), (1, 1, 3, 2)]:
+    for (m, x, go, ge) in [(1, 2, 6, 1), (2, 4, 6, 2), (3, 4, 5, 3), (1, 1, 3, 2), (3, 2, 9, 1), (2, 3, 5, 2)]:
         P = T.default_params(report_cigar=1, match=m, mismatch=x, gap_open=go, gap_extend=ge)
-        a, pa = T.ref_ssw_batch(q, qo, r, ro, P)
-        b, pb = T.ko_ssw_batch(q, qo, r, ro, P)
+        a, pa = T.ref_ssw_batch(q, qo, r, ro, P, cigar_cap=256)
+        b, pb = T.ko_ssw_batch(q, qo, r, ro, P, cigar_cap=256)
         assert_overlaps_equal(a, pa, b, pb)
+        g = T.ko_ssw_gotoh(q[:600 * 120], qo[:601], r[:600 * 160], ro[:601], P)
+        for f in COORDS:
+            assert np.array_equal(g[f], a[f][:600]), (f, (m, x, go, ge))
+
+
+@pytest.mark.parametrize("prm", [(5, 4, 10, 10), (1, 1, 1, 1), (2, 8, 3, 3), (3, 1, 1, 4), (2, 9, 2, 1), (4, 6, 4, 4), (10, 2, 3, 3), (2, 3, 2, 5)])
+def test_ssw_scoring_outside_the_gotoh_domain(pkg, prm):
+    """gap_extend >= gap_open or mismatch > 2 * gap_extend: SSW's answer depends on its striping (E before lazy-F, the two
+    lazy-F loops, ssw.c:257-305,514-524). The oracle restates the striped kernels lane by lane and must equal the reference:
+    score, the four coordinates and the CIGAR, with and without the score filter."""
+    m, x, go, ge = prm
+    q, qo, r, ro = pkg.synth.sw_pairs(2500, 120, 160, seed=78)
+    q2, qo2, r2, ro2 = pkg.synth.sw_pairs(1500, 150, 150, seed=79)
+    for (qq, qqo, rr, rro) in ((q, qo, r, ro), (q2, qo2, r2, ro2)):
+        for thr in (0, 90):
+            P = T.default_params(report_cigar=1, match=m, mismatch=x, gap_open=go, gap_extend=ge, score_threshold=thr)
+            a, pa = T.ref_ssw_batch(qq, qqo, rr, rro, P, cigar_cap=512)
+            b, pb = T.ko_ssw_batch(qq, qqo, rr, rro, P, cigar_cap=512)
+            ok = (b["flags"] & 1) == 0
+            assert ok.mean() > 0.999
+            assert_overlaps_equal(a[ok], pa, b[ok], pb)
+
+
+def test_ssw_random_parameter_sweep(pkg):
+    """40 random (match, mismatch, gap_open, gap_extend) over ragged lengths, repeats and N runs."""
+    rng = np.random.default_rng(1234)
+    q, qo, r, ro = pkg.synth.sw_pairs(700, 100, 130, seed=80)
+    for _ in range(40):
+        m, x, go, ge = int(rng.integers(1, 12)), int(rng.integers(0, 12)), int(rng.integers(0, 14)), int(rng.integers(0, 14))
+        P = T.default_params(report_cigar=1, match=m, mismatch=x, gap_open=go, gap_extend=ge)
+        a, pa = T.ref_ssw_batch(q, qo, r, ro, P, cigar_cap=512)
+        b, pb = T.ko_ssw_batch(q, qo, r, ro, P, cigar_cap=512)
+        ok = (b["flags"] & 1) == 0
+        assert ok.mean() > 0.99, (m, x, go, ge)
+        for f in COORDS + ["cigar_len"]:
+            assert np.array_equal(a[f][ok], b[f][ok]), (f, (m, x, go, ge))
+        ca, cb = T.cigars_of(a, pa), T.cigars_of(b, pb)
+        assert all(ca[i] == cb[i] for i in range(len(ca)) if ok[i]), (m, x, go, ge)
