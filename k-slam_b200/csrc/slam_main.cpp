@@ -280,7 +280,9 @@ int run_alignment(const Options &o, const std::string &commandLine) {      // me
   kslam_params prm;
   memset(&prm, 0, sizeof prm);
   prm.match = (uint8_t)o.match; prm.mismatch = (uint8_t)o.misMatch; prm.gap_open = (uint8_t)o.gapOpen; prm.gap_extend = (uint8_t)o.gapExtend;   // ssw_cpp.cpp:114-117
-  prm.score_threshold = (uint16_t)(o.scoreThreshold > 65535u ? 65535u : o.scoreThreshold);   // sw_score is 16 bits (ssw_cpp.h:16): a larger threshold screens everything, as in the reference prm.report_cigar = wantSam ? 1 : 0; prm.device = o.devices[0];
+  // sw_score is 16 bits (ssw_cpp.h:16): a larger threshold screens everything, as in the reference
+  prm.score_threshold = (uint16_t)(o.scoreThreshold > 65535u ? 65535u : o.scoreThreshold);
+  prm.report_cigar = wantSam ? 1 : 0; prm.device = o.devices[0];
   if (!kslam_params_fast(&prm))
     log("Scoring parameters outside gap-extend < gap-open, mismatch <= 2 * gap-extend: Smith-Waterman runs the lane-for-lane restatement of SSW's striped kernels (same results, slower)");
   // one context per entry of --devices, the genome index replicated in each (read pairs shard trivially)
