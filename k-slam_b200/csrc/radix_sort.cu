@@ -218,6 +218,186 @@ k_rs_onesweep(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n,
   }
 }
 
+// ---- one LSD pass, persistent form: tiles arrive by bulk copy (TMA) while the previous one is processed ---------
+// k_rs_onesweep above loads a tile into 32 registers per thread, ranks it, stages it and writes it out, one phase after
+// the other; at 128 registers + 72 KB only two CTAs share an SM and ncu shows the memory pipe idle while they rank
+// (24 % warps active, 0.23 eligible warps per cycle, dram at 30 % of peak although the traffic is exactly the algorithmic
+// 32 B per record). Here a CTA stays resident and takes tiles from the ticket counter; one thread starts the bulk copy
+// (cp.async.bulk -> mbarrier, SASS UBLKCP) of tile t+1 into the second arrival buffer as soon as it has the ticket, so
+// the copy runs under the ranking / look-back / scatter / write-out of tile t. Records are ranked FROM shared memory
+// (LDS.128, the digit and the 16-bit rank are all a thread keeps: no key / value register arrays), scattered into a
+// third buffer in digit order and written out in contiguous runs. Tickets are handed out in order, so every predecessor
+// a look-back waits for belongs to a CTA that is already running: no deadlock.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+
+#include "radix_pass2.cuh"
+
+template <int RS_THREADS, int RS_IPT, int CTAS_PER_SM>
+__global__ void __launch_bounds__(RS_THREADS, CTAS_PER_SM)
+k_rs_sweep_tma(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n, uint32_t shift, uint32_t mask,
+               uint32_t word,                                       // 0: sort by .key, 1: sort by .val
+               const unsigned long long *__restrict__ digit_base,  // [256] exclusive global offsets
+               volatile unsigned long long *tile_state,            // [tiles][256], zero-initialised
+               uint32_t *__restrict__ ticket, uint32_t n_tiles) {
+  constexpr int RS_WARPS = RS_THREADS / 32;
+  constexpr uint32_t RS_TILE = RS_THREADS * RS_IPT;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Rec16 *arrive0 = reinterpret_cast<Rec16 *>(smem_raw), *arrive1 = arrive0 + RS_TILE, *stage = arrive1 + RS_TILE;
+  uint32_t *whist = reinterpret_cast<uint32_t *>(stage + RS_TILE);   // [RS_WARPS][256]
+  __shared__ uint32_t s_dexcl[256];
+  __shared__ unsigned long long s_gbase[256];
+  __shared__ uint32_t s_scan[32];
+  __shared__ uint32_t s_tile[2];
+  __shared__ __align__(8) uint64_t s_bar[2];
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  auto start_copy = [&](uint32_t t, uint32_t slot) {       // one thread: arm the barrier, start the bulk copy of tile t
+    const uint64_t base = (uint64_t)t * RS_TILE;
+    const uint32_t cnt = (uint32_t)((n - base) < RS_TILE ? (n - base) : RS_TILE);
+    mbar_expect_tx(&s_bar[slot], cnt * (uint32_t)sizeof(Rec16));
+    bulk_load(slot ? arrive1 : arrive0, in + base, cnt * (uint32_t)sizeof(Rec16), &s_bar[slot]);
+  };
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t t = atomicAdd(ticket, 1u);
+    s_tile[0] = t;
+    if (t < n_tiles) start_copy(t, 0);
+  }
+  __syncthreads();
+
+  const uint32_t wbase = warp * 32 * RS_IPT;
+  const uint32_t lt_mask = (1u << lane) - 1;
+  uint32_t *myhist = whist + warp * 256;
+  uint32_t parity0 = 0, parity1 = 0;
+  for (uint32_t slot = 0;; slot ^= 1) {
+    const uint32_t tile = s_tile[slot];
+    if (tile >= n_tiles) break;
+    const Rec16 *arr = slot ? arrive1 : arrive0;
+    if (tid == 0) {                                        // next ticket, its copy goes into the other arrival buffer
+      const uint32_t t = atomicAdd(ticket, 1u);
+      s_tile[slot ^ 1] = t;
+      if (t < n_tiles) start_copy(t, slot ^ 1);
+    }
+#pragma unroll
+    for (uint32_t i = tid; i < RS_WARPS * 256; i += RS_THREADS) whist[i] = 0;
+    __syncthreads();                                       // histograms clear; the previous tile's write-out is over
+    const uint64_t tile_base = (uint64_t)tile * RS_TILE;
+    const uint32_t count = (uint32_t)((n - tile_base) < RS_TILE ? (n - tile_base) : RS_TILE);
+    mbar_wait(&s_bar[slot], slot ? parity1 : parity0);
+    if (slot) parity1 ^= 1; else parity0 ^= 1;
+
+    // 1. per-warp digit ranks, records read from the arrival buffer; (warp, item, lane) order == input order (stability)
+    uint32_t dr[RS_IPT];                                   // digit << 16 | rank inside (warp, digit)
+#pragma unroll
+    for (int i = 0; i < RS_IPT; i++) {
+      const uint32_t idx = wbase + i * 32 + lane;
+      uint32_t d = 255u;                                   // padding sorts to the very end of the tile
+      if (idx < count) {
+        const ulonglong2 r = *reinterpret_cast<const ulonglong2 *>(arr + idx);
+        d = (uint32_t)((word ? r.y : r.x) >> shift) & mask;
+      }
+      const uint32_t peers = digit_peers<true>(d);
+      const uint32_t old = myhist[d];
+      __syncwarp();
+      if ((peers & lt_mask) == 0) myhist[d] = old + __popc(peers);
+      __syncwarp();
+      dr[i] = (d << 16) | (old + __popc(peers & lt_mask));
+    }
+    __syncthreads();
+
+    // 2. thread d (< 256) owns digit d: exclusive offsets over warps, tile count, publish + look back, tile-local scan
+    uint32_t cnt_d = 0;
+    if (tid < 256) {
+#pragma unroll
+      for (int w = 0; w < RS_WARPS; w++) { const uint32_t t = whist[w * 256 + tid]; whist[w * 256 + tid] = cnt_d; cnt_d += t; }
+      uint32_t real_d = cnt_d;
+      if (tid == 255) real_d -= (RS_TILE - count);
+      s_gbase[tid] = digit_base[tid] + publish_and_look_back(tile_state, tile, tid, real_d);
+      uint32_t inc = cnt_d;
+#pragma unroll
+      for (int dlt = 1; dlt < 32; dlt <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, dlt); if (lane >= dlt) inc += t; }
+      if (lane == 31) s_scan[warp] = inc;
+      s_dexcl[tid] = inc - cnt_d;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t w = lane < 8 ? s_scan[lane] : 0;
+      uint32_t winc = w;
+#pragma unroll
+      for (int dlt = 1; dlt < 8; dlt <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, winc, dlt); if (lane >= dlt) winc += t; }
+      if (lane < 8) s_scan[lane] = winc - w;
+    }
+    __syncthreads();
+    if (tid < 256) s_dexcl[tid] += s_scan[warp];
+    __syncthreads();
+
+    // 3. scatter into digit order
+#pragma unroll
+    for (int i = 0; i < RS_IPT; i++) {
+      const uint32_t idx = wbase + i * 32 + lane;
+      if (idx < count) {
+        const uint32_t d = dr[i] >> 16;
+        const uint32_t pos = s_dexcl[d] + myhist[d] + (dr[i] & 0xffffu);
+        *reinterpret_cast<ulonglong2 *>(stage + pos) = *reinterpret_cast<const ulonglong2 *>(arr + idx);
+      }
+    }
+    __syncthreads();
+
+    // 4. write out: position j of the staged tile belongs to digit d at global gbase[d] + (j - dexcl[d])
+    for (uint32_t j = tid; j < count; j += RS_THREADS) {
+      const ulonglong2 r = *reinterpret_cast<const ulonglong2 *>(stage + j);
+      const uint32_t d = (uint32_t)((word ? r.y : r.x) >> shift) & mask;
+      *reinterpret_cast<ulonglong2 *>(out + s_gbase[d] + (j - s_dexcl[d])) = r;
+    }
+  }
+}
+
+template <int T, int I, int C>
+static void launch_sweep_tma(kslam_ctx *c, const Rec16 *in, Rec16 *out, uint64_t n, uint32_t shift, uint32_t mask,
+                             uint32_t word, const unsigned long long *base, unsigned long long *state, uint32_t *ticket) {
+  constexpr size_t smem = (size_t)3 * T * I * sizeof(Rec16) + (T / 32) * 256 * sizeof(uint32_t);
+  const uint64_t tiles = (n + (uint64_t)T * I - 1) / ((uint64_t)T * I);
+  static bool attr_set[64] = {false};   // per instantiation
+  if (!(c->device < 64 && attr_set[c->device])) {
+    CUDA_TRY(cudaFuncSetAttribute(k_rs_sweep_tma<T, I, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (c->device < 64) attr_set[c->device] = true;
+  }
+  uint64_t grid = (uint64_t)c->num_sms * C;
+  if (grid > tiles) grid = tiles;
+  k_rs_sweep_tma<T, I, C><<<(unsigned)grid, T, smem, c->stream>>>(in, out, n, shift, mask, word, base, state, ticket, (uint32_t)tiles);
+}
+
+template <int T, int I, int WORD>
+static void launch_pass2(kslam_ctx *c, const Rec16 *in, Rec16 *out, uint64_t n, uint32_t shift, uint32_t mask,
+                         const unsigned long long *base, uint32_t *state, uint32_t *ticket) {
+  constexpr size_t smem = (size_t)T * I * sizeof(Rec16) + (T / 32) * 256 * sizeof(uint32_t);
+  const uint64_t tiles = (n + (uint64_t)T * I - 1) / ((uint64_t)T * I);
+  static bool attr_set[64] = {false};   // per instantiation
+  if (!(c->device < 64 && attr_set[c->device])) {
+    CUDA_TRY(cudaFuncSetAttribute(k_rs_pass2<T, I, WORD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (c->device < 64) attr_set[c->device] = true;
+  }
+  k_rs_pass2<T, I, WORD><<<(unsigned)tiles, T, smem, c->stream>>>(in, out, n, shift, mask, base, state, ticket);
+}
+
 template <int T, int I, bool B>
 static void launch_onesweep(kslam_ctx *c, const Rec16 *in, Rec16 *out, uint64_t n, uint32_t shift, uint32_t mask,
                             uint32_t word, const unsigned long long *base, unsigned long long *state, uint32_t *ticket) {
@@ -246,11 +426,15 @@ Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, u
     uint32_t bits = hi_bit - s < 8 ? hi_bit - s : 8;
     plan.shift[plan.n_passes] = s; plan.mask[plan.n_passes] = (1u << bits) - 1; plan.n_passes++;
   }
-  const uint64_t tile_recs = cfg == 2 ? 8192 : (cfg == 5 ? 2048 : 4096);
+  const uint64_t tile_recs = cfg == 2 ? 8192 : ((cfg == 5 || cfg == 7) ? 2048 : 4096);
   const uint64_t tiles = (n + tile_recs - 1) / tile_recs;
-  // layout of sort_hist: [8*256 u64 hist][8 u32 trivial][8 u32 tickets][pad][tiles*256 u64 state]
+  // layout of sort_hist: [8*256 u64 hist][8 u32 trivial][8 u32 tickets][pad][tiles*256 u64 state / inclusive prefixes]
+  // (k_rs_pass2: tiles*256 u32)
   const size_t hist_bytes = RS_MAX_PASSES * 256 * 8, misc_bytes = 128;
-  c->sort_hist.reserve(hist_bytes + misc_bytes + tiles * 256 * 8);
+  const bool pass2 = (cfg == 0 || cfg == 10) && n < (1ull << 30);          // its 32-bit tile states hold prefixes below 2^30
+  const int variant = cfg == 10 ? 0 : 1;                   // 1: 256 threads x 16 records (default), 0: 512 x 8 (KSLAM_RS_CFG=10)
+  const size_t state_bytes = tiles * 256 * (pass2 ? 4 : 8);
+  c->sort_hist.reserve(hist_bytes + misc_bytes + state_bytes);
   unsigned long long *ghist = c->sort_hist.as<unsigned long long>();
   uint32_t *trivial = reinterpret_cast<uint32_t *>((char *)c->sort_hist.p + hist_bytes);
   uint32_t *tickets = trivial + 8;
@@ -270,16 +454,27 @@ Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, u
   CUDA_TRY(cudaStreamSynchronize(st));
   for (uint32_t p = 0; p < plan.n_passes; p++) {
     if (h_trivial[p]) continue;   // every record has the same digit: the pass would be the identity
-    CUDA_TRY(cudaMemsetAsync(state, 0, tiles * 256 * 8, st));
+    CUDA_TRY(cudaMemsetAsync(state, 0, state_bytes, st));
 #define RS_LAUNCH(T, I, B) launch_onesweep<T, I, B>(c, cur, alt, n, plan.shift[p], plan.mask[p], word, ghist + p * 256, state, tickets + p)
-    // KSLAM_RS_CFG picks an instance for experiments; measured on 32 M random records, 8 passes (gpurun, round 1):
-    //   0 ballots 256x16 3.05 ms (default) | 4 MATCH.ANY 256x16 3.46 | 1 ballots 512x8 3.16 | 5 ballots 256x8 (4 CTAs/SM) 3.55 |
+    // KSLAM_RS_CFG picks an instance for experiments. Round 2, 32 M / 128 M random records, 8 passes (gpurun_out/r2h_sort_cfgs.log):
+    //   0 k_rs_pass2 256x16 (default) 2.52 / 9.50 ms | 10 k_rs_pass2 512x8 2.70 / 10.1 | 9 k_rs_onesweep 256x16 3.05 / 11.6 |
+    //   6 persistent CTAs + double-buffered bulk copies, 512x8, one CTA per SM 4.08 / 16.4 | 7 the same 256x8, two per SM 6.1 / 24.7
+    // Round 1, 32 M records:
+    //   9 ballots 256x16 3.05 ms (the round-1 default) | 4 MATCH.ANY 256x16 3.46 | 1 ballots 512x8 3.16 | 5 ballots 256x8 (4 CTAs/SM) 3.55 |
     //   2 MATCH.ANY 512x16 (one CTA/SM). 256x12 at 3 CTAs/SM (3.25) and look-back before the ranking (3.04) were tried and dropped.
-    if (cfg == 1) RS_LAUNCH(512, 8, true);
+    if (cfg == 6) launch_sweep_tma<512, 8, 1>(c, cur, alt, n, plan.shift[p], plan.mask[p], word, ghist + p * 256, state, tickets + p);
+    else if (cfg == 7) launch_sweep_tma<256, 8, 2>(c, cur, alt, n, plan.shift[p], plan.mask[p], word, ghist + p * 256, state, tickets + p);
+    else if (cfg == 1) RS_LAUNCH(512, 8, true);
     else if (cfg == 2) RS_LAUNCH(512, 16, false);
     else if (cfg == 4) RS_LAUNCH(256, 16, false);
     else if (cfg == 5) RS_LAUNCH(256, 8, true);
-    else RS_LAUNCH(256, 16, true);
+    else if (!pass2) RS_LAUNCH(256, 16, true);
+    else {
+#define RS2_LAUNCH(T, I) (word ? launch_pass2<T, I, 1>(c, cur, alt, n, plan.shift[p], plan.mask[p], ghist + p * 256, reinterpret_cast<uint32_t *>(state), tickets + p) \
+                               : launch_pass2<T, I, 0>(c, cur, alt, n, plan.shift[p], plan.mask[p], ghist + p * 256, reinterpret_cast<uint32_t *>(state), tickets + p))
+      if (variant == 1) RS2_LAUNCH(256, 16); else RS2_LAUNCH(512, 8);
+#undef RS2_LAUNCH
+    }
 #undef RS_LAUNCH
     c->launches++;
     CUDA_TRY(cudaGetLastError());
