@@ -330,6 +330,9 @@ int kslam_get_kmer_sort_bits(const kslam_ctx *ctx);
  * pass). Whatever cannot be proven falls through to the full-matrix kernel. Results are identical at every level
  * (DESIGN.md §3.4). */
 int kslam_set_sw_band(kslam_ctx *ctx, int level);
+/* reportCigar (Globals.h:36; true iff --sam-file, SLAM.h:169) for the batches that follow: kslam_params.report_cigar, changeable
+ * between batches (one upload of a read / window set can then be aligned with and without CIGARs). */
+int kslam_set_report_cigar(kslam_ctx *ctx, int on);
 /* Keep (1, default) or drop (0) stage-tap buffers between stages; dropping saves HBM on big batches. */
 int kslam_set_debug_taps(kslam_ctx *ctx, int keep);
 

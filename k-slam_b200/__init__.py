@@ -143,6 +143,7 @@ def lib():
     L.kslam_set_debug_taps.argtypes = [vp, i32]
     L.kslam_measure_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.kslam_set_prefilter.argtypes = [vp, i32]
+    L.kslam_set_report_cigar.argtypes = [vp, i32]
     L.kslam_set_sw_band.argtypes = [vp, i32]
     u32 = C.c_uint32
     L.kslam_fastq_open.argtypes = [C.c_char_p, C.c_char_p, u32, C.POINTER(vp)]
@@ -438,6 +439,10 @@ class Aligner:
         v = C.c_double()
         self._check(self.L.kslam_measure_int_peak(self.h, C.byref(v)), "kslam_measure_int_peak")
         return v.value
+
+    def set_report_cigar(self, on: bool):
+        self._check(self.L.kslam_set_report_cigar(self.h, int(on)), "kslam_set_report_cigar")
+        self.params.report_cigar = int(on)
 
     def set_prefilter(self, on: bool):
         self._check(self.L.kslam_set_prefilter(self.h, int(on)), "kslam_set_prefilter")

@@ -120,6 +120,13 @@ int kslam_set_prefilter(kslam_ctx *ctx, int on) {
   return KSLAM_OK;
 }
 
+int kslam_set_report_cigar(kslam_ctx *ctx, int on) {
+  if (!ctx) return KSLAM_ERR_ARG;
+  ctx->prm.report_cigar = on != 0;
+  ctx->aligned = false; ctx->paired = false;      // results of the other mode are not mixed with this one
+  return KSLAM_OK;
+}
+
 int kslam_set_sw_band(kslam_ctx *ctx, int on) {
   if (!ctx) return KSLAM_ERR_ARG;
   ctx->sw_band = on != 0;          // 1: 32-wide sweep tier only; 2: + 64-wide tier; >= 3 (default): + direct tiers
