@@ -139,6 +139,80 @@ def make_workload(pkg, name, pairs, seed_shift=0, pin=False, reads=True):
     return gb, go, rb, ro, desc
 
 
+def make_comm(pkg, al, rank, world, local):
+    """kslam_comm for this rank: rank 0 draws the NCCL unique id, torch.distributed (the launcher's rendezvous) hands it out;
+    from then on the exchanges are the library's own ncclSend / ncclRecv (csrc/comm.cu)."""
+    import torch
+    if world == 1:
+        return pkg.Comm.init_rank(al, 0, 1, pkg.Comm.unique_id())
+    import torch.distributed as dist
+    uid = torch.frombuffer(bytearray(pkg.Comm.unique_id() if rank == 0 else bytes(128)), dtype=torch.uint8).to(f"cuda:{local}")
+    dist.broadcast(uid, src=0)
+    return pkg.Comm.init_rank(al, rank, world, bytes(uid.cpu().numpy().tobytes()))
+
+
+def config4_block(args, pkg, rank, world, local, barrier):
+    """Config 4: the genome k-mer list range-partitioned by k-mer prefix over the GPUs of the job, read k-mers routed to their
+    key owner and raw matches routed back with NCCL all-to-alls issued by the C++ host (kslam_comm, csrc/comm.cu). The
+    database grows with the job: 625 x 4 Mbp genomes per GPU (8 GPUs: the named 5,000 genomes, 20 Gbp, 1.25 G k-mer
+    records); it is generated ON each GPU and handed to the library as a device pointer. COLLECTIVE: every rank calls this."""
+    import torch
+    from kslam_b200 import synth_torch as st
+    ng = int(os.environ.get("KSLAM_CONFIG4_GENOMES_PER_GPU", "625")) * world
+    L, pairs = 4_000_000, args.pairs or 2_000_000
+    dev = torch.device("cuda", local)
+    g = st._gen(1, dev)
+    gdev = torch.empty(ng * L, dtype=torch.uint8, device=dev)
+    for lo in range(0, ng * L, 1 << 30):                    # the same seed on every rank: identical databases
+        hi = min(ng * L, lo + (1 << 30))
+        gdev[lo:hi] = st._acgt((hi - lo,), g, dev)
+    go = np.arange(ng + 1, dtype=np.uint64) * np.uint64(L)
+    al = pkg.Aligner(report_cigar=False, device=local)
+    al.set_debug_taps(False)
+    t0 = time.time()
+    al.load_genomes_part(gdev, go, rank, world)
+    t_load = time.time() - t0
+    rb, ro = st.paired_reads(gdev, go, pairs, seed=2 + rank, pin=True)
+    del gdev
+    torch.cuda.empty_cache()
+    comm = make_comm(pkg, al, rank, world, local)
+    al.upload_reads(rb, ro)
+    for _ in range(2):
+        comm.align_resident(fetch=False); al.pair_batch(fetch=False)
+    steps = 5
+    acc = {}
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        comm.align_resident(fetch=False); al.pair_batch(fetch=False)
+        for k, v in comm.stats().items():
+            acc[k] = acc.get(k, 0) + v / steps
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    dt = float(dt[0])
+    part = al.partition()
+    tm = al.timings()
+    comm.close(); al.close()
+    xk = acc["bytes_sent_kmers"] / (acc["ms_exchange_kmers"] / 1e3) / 1e9 if acc["ms_exchange_kmers"] > 0 else 0.0
+    xm = acc["bytes_sent_matches"] / (acc["ms_exchange_matches"] / 1e3) / 1e9 if acc["ms_exchange_matches"] > 0 else 0.0
+    step_ms = dt / steps * 1e3
+    return {"workload": f"config4: {ng} x 4 Mbp genomes ({part['n_genome_kmers_total'] / 1e6:.0f} M genome k-mer records, {16 * part['n_genome_kmers_total'] / 1e9:.1f} GB) "
+                        f"range-partitioned by k-mer prefix over {world} GPUs; {pairs} x 150bp pairs per GPU per step; exchanges = ncclSend/ncclRecv groups issued by libkslam (kslam_comm)",
+            "value": pairs * world * steps / dt * 60 / 1e6, "unit": UNIT, "n_gpus": world, "ms_per_step": step_ms, "scaling": "weak (reads and database grow with the job)",
+            "index_build_s": t_load, "rank0_stage_ms": {k: acc[k] for k in acc if k.startswith("ms_")} | {"ms_pair": tm["ms_pair"]},
+            "exchange": {"rank0_bytes_sent_per_step": {"kmers": acc["bytes_sent_kmers"], "matches": acc["bytes_sent_matches"]},
+                         "nvlink_gbs_out_of_rank0": {"kmers": xk, "matches": xm}, "peak_gbs_per_direction": 770.0,
+                         "share_of_step": (acc["ms_exchange_kmers"] + acc["ms_exchange_matches"]) / step_ms,
+                         "routing_share_of_step": (acc["ms_bucket_kmers"] + acc["ms_bucket_matches"]) / step_ms,
+                         "extract_prefilter_share_of_step": (acc["ms_route"] - acc["ms_bucket_kmers"]) / step_ms,
+                         "note": "exchange = device time of the two ncclSend/ncclRecv groups (CUDA events on the ctx stream); routing = the two bucketing steps the partition adds "
+                                 "(count + scatter by destination); extract + prefilter is the same work the replicated path does; "
+                                 "peak = the measured 770 GB/s peer copy per direction (B200_PROFILING.md)"}}
+
+
 def reference_run(pkg, gb, go, rb, ro, report_cigar, threshold=0, keep=False):
     """The reference's own alignToDatabase + screen + getPairedOverlaps (oracle/_ref, all host threads; the oracle port where
     _ref is absent) on the given reads. -> (seconds, cores, kind, outputs or None)"""
@@ -666,21 +740,18 @@ def main():
     partitioned = args.workload == "config4"
     t0 = time.time()
     if partitioned:
-        from kslam_b200 import dist as kd
         al.load_genomes_part(gb, go, rank, world)
-        engine = kd.CudaEngine(al, local)
-        exch = kd.TorchExchange(device=torch.device("cuda", local)) if world > 1 else kd.LoopbackGroup(1).exchange(0)
-        n_reads = len(ro) - 1
+        comm = make_comm(pkg, al, rank, world, local)
         xstats = {}
 
         def step_resident():
-            _, st = kd.align_partitioned(engine, exch, n_reads, fetch=False)
-            xstats.update(st)
+            comm.align_resident(fetch=False)
+            xstats.update(comm.stats())
             al.pair_batch(fetch=False)
 
         def step_e2e():
             al.upload_reads(rb_host, ro)
-            kd.align_partitioned(engine, exch, n_reads, fetch=False)
+            comm.align_resident(fetch=False)
             return None, al.pair_batch(fetch=True, copy=False)
     else:
         al.load_genomes(gb, go)
@@ -844,16 +915,26 @@ def main():
                                              "sw_cells_forward", "sw_cells_reverse", "sw_cells_computed", "n_sort_passes")},
                "genome_index_build_s": t_load}
         if partitioned:
-            out["exchange"] = {"rank0_records_per_step": xstats, "record_bytes": 16,
+            out["exchange"] = {"rank0_per_step": xstats, "record_bytes": 16, "issued_by": "libkslam (kslam_comm: ncclSend / ncclRecv groups on the ctx stream)",
                                "partition": {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in al.partition().items() if k != "splitters"}}
         if world == 1 and not args.no_cpu_baseline:
             cs = args.cpu_sample or CPU_SAMPLE[args.workload]
             out["cpu_baseline"] = cpu_baseline_block(pkg, al, gb, go, args.workload, cs, pairs, want_cigar)
-        al.close()
+    al.close()
+    extras_on = args.workload == "config2" and not args.no_extras and not partitioned
+    del gb, rb_host
+    # ---- config 4 next to the headline workload whenever the job has more than one GPU (all ranks take part)
+    if extras_on and world > 1 and time.time() - T_START < EXTRAS_BUDGET_S:
+        try:
+            blk = config4_block(args, pkg, rank, world, local, barrier)
+        except Exception as e:   # noqa: BLE001
+            blk = {"error": f"{type(e).__name__}: {e}"}
+        if rank == 0:
+            out["configs"] = {"config4": blk}
+    if rank == 0:
         # ---- the other named configurations (BASELINE.json configs 1, 3, 5 and the process interface), N = 1 only: bounded
         # blocks of their own next to the headline workload, each with its roofline / cpu_baseline / parity figures
-        if world == 1 and args.workload == "config2" and not args.no_extras and not partitioned:
-            del gb, rb_host
+        if extras_on and world == 1:
             extras = {}
             for name, fn in (("config1", lambda: config1_block(args, pkg, local)),
                              ("config3", lambda: config3_block(args, pkg, 100_000_000, 10_000_000)),
@@ -871,8 +952,6 @@ def main():
                 log(f"[bench] block {name} took {extras[name]['block_wall_s']:.1f}s")
             out["configs"] = extras
         emit(out)
-    else:
-        al.close()
     if world > 1:
         dist.destroy_process_group()
 

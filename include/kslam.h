@@ -15,7 +15,8 @@
  * Plain pointers and sizes only; no exceptions cross the boundary (0 = ok, negative = error, text
  * from kslam_last_error). Sequences are passed as ONE concatenated byte array plus n+1 offsets
  * (sequence i = bases[offs[i] .. offs[i+1])), exactly the bytes of std::string `bases` in the
- * reference's FASTQSequence / GenbankEntry. Result buffers are owned by the ctx and stay valid until
+ * reference's FASTQSequence / GenbankEntry. (`bases` is copied with cudaMemcpyDefault: a pointer into device or managed
+ * memory of the same process works too — a 20 Gbp database that was produced on the GPU need not visit the host.) Result buffers are owned by the ctx and stay valid until
  * the next call of the same function or kslam_destroy. One in-flight batch per ctx; use one ctx per
  * GPU (and two per GPU to double-buffer). There is NO CPU fallback: every entry point that computes
  * fails with KSLAM_ERR_CUDA if no sm_100 device is usable.
@@ -113,6 +114,8 @@ const char *kslam_last_error(const kslam_ctx *ctx); /* ctx may be NULL: last cre
 int kslam_params_exact(const kslam_params *params);
 int kslam_params_fast(const kslam_params *params);
 const char *kslam_version(void);
+/* HBM of a device (cudaMemGetInfo): a host that must choose between a replicated and a partitioned index asks here. */
+int kslam_device_memory(int32_t device, uint64_t *free_bytes, uint64_t *total_bytes);
 
 /* Pack the genomes, extract every genome_gap-th canonical 32-mer (KMer.h:160-181), sort once
  * (KMer.h:388-398) and keep everything resident in HBM. */
@@ -175,6 +178,31 @@ int kslam_part_join(kslam_ctx *ctx, uint64_t n_records, const uint32_t *id_bases
 int kslam_part_match_buffer(kslam_ctx *ctx, uint64_t n_matches, void **dev_ptr);
 int kslam_part_finish(kslam_ctx *ctx, uint64_t n_matches, uint32_t read_id_base, int fetch_results,
                       kslam_alignments *out /* may be NULL */);
+
+/* ---- the partitioned path driven by the library itself over NCCL (csrc/comm.cu) ------------------------------------------
+ * kslam_comm = one rank of a job whose genome k-mer list is range-partitioned over its GPUs: the ctx holds this rank's key
+ * range (kslam_load_genomes_part(part = rank, n_parts = ranks)); kslam_comm_align_resident is alignToDatabase (SLAM.h:60-79)
+ * for the reads this rank uploaded (kslam_upload_reads) — the three stages above with the two all-to-alls in between issued
+ * as ncclSend / ncclRecv groups on the ctx's stream (NVLink / NVSwitch). COLLECTIVE: every rank calls it once per batch.
+ * Results as kslam_align_resident, bit-identical to the unpartitioned path on the same reads; kslam_pair_batch follows.
+ * NCCL is opened at run time (dlopen libnccl.so.2); KSLAM_ERR_STATE when it is absent.
+ *   one process, several GPUs:  kslam_comm_init_all(n, ctxs, comms)   one ctx per DISTINCT device, one host thread per rank
+ *   one process per GPU:        rank 0: kslam_comm_unique_id(id) -> the launcher hands id to every rank ->
+ *                               kslam_comm_init_rank(ctx, rank, n_ranks, id, &comm) */
+typedef struct kslam_comm kslam_comm;
+typedef struct {
+  float ms_route, ms_exchange_kmers, ms_sort, ms_join, ms_exchange_matches, ms_finish;   /* device time of the stages of the last batch */
+  uint64_t kmers_sent, kmers_received, matches_sent, matches_received;                    /* 16-byte records, this rank */
+  uint64_t bytes_sent_kmers, bytes_sent_matches;                                          /* bytes that left this GPU (self excluded) */
+  float ms_bucket_kmers, ms_bucket_matches;   /* the part of ms_route / ms_join spent grouping records by destination (the work the partition adds) */
+} kslam_comm_stats;
+int kslam_comm_unique_id(void *id128 /* 128 bytes */);
+int kslam_comm_init_rank(kslam_ctx *ctx, uint32_t rank, uint32_t n_ranks, const void *id128, kslam_comm **out);
+int kslam_comm_init_all(uint32_t n, kslam_ctx *const *ctxs, kslam_comm **out /* n entries */);
+void kslam_comm_destroy(kslam_comm *comm);
+int kslam_comm_rank(const kslam_comm *comm, uint32_t *rank, uint32_t *n_ranks);
+int kslam_comm_align_resident(kslam_comm *comm, int fetch_results, kslam_alignments *out /* may be NULL */);
+int kslam_comm_get_stats(const kslam_comm *comm, kslam_comm_stats *out);
 
 /* ---- FASTQ ingest (host side) ------------------------------------------------------------------
  * Chunk-parallel restatement of the reference's reader: getSequencesFromFASTQFile / getPairedSequencesFromFASTQFiles

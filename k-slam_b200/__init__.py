@@ -78,6 +78,16 @@ class Timings(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "_pad"}
 
 
+class CommStats(C.Structure):
+    """kslam_comm_stats (include/kslam.h)"""
+    _fields_ = [(n, C.c_float) for n in ("ms_route", "ms_exchange_kmers", "ms_sort", "ms_join", "ms_exchange_matches", "ms_finish")] + \
+               [(n, C.c_uint64) for n in ("kmers_sent", "kmers_received", "matches_sent", "matches_received", "bytes_sent_kmers", "bytes_sent_matches")] + \
+               [(n, C.c_float) for n in ("ms_bucket_kmers", "ms_bucket_matches")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class _ReadBatch(C.Structure):
     _fields_ = [("n_reads", C.c_uint64), ("n_r1", C.c_uint64), ("bases", C.c_void_p), ("offs", C.c_void_p),
                 ("quals", C.c_void_p), ("qual_offs", C.c_void_p), ("ids", C.c_void_p), ("id_offs", C.c_void_p)]
@@ -144,6 +154,14 @@ def lib():
     L.kslam_measure_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.kslam_set_prefilter.argtypes = [vp, i32]
     L.kslam_set_report_cigar.argtypes = [vp, i32]
+    L.kslam_comm_unique_id.argtypes = [vp]
+    L.kslam_comm_init_rank.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.POINTER(vp)]
+    L.kslam_comm_init_all.argtypes = [C.c_uint32, C.POINTER(vp), C.POINTER(vp)]
+    L.kslam_comm_destroy.argtypes = [vp]
+    L.kslam_comm_destroy.restype = None
+    L.kslam_comm_rank.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.kslam_comm_align_resident.argtypes = [vp, i32, C.POINTER(_Alignments)]
+    L.kslam_comm_get_stats.argtypes = [vp, C.POINTER(CommStats)]
     L.kslam_set_sw_band.argtypes = [vp, i32]
     u32 = C.c_uint32
     L.kslam_fastq_open.argtypes = [C.c_char_p, C.c_char_p, u32, C.POINTER(vp)]
@@ -294,8 +312,16 @@ class Aligner:
 
     # -- k-mer-range partitioned database (include/kslam.h "partitioned"; protocol in dist.py)
     def load_genomes_part(self, bases, offs, part, n_parts):
-        bases, offs = _u8(bases), _u64(offs)
-        self._check(self.L.kslam_load_genomes_part(self.h, len(offs) - 1, _ptr(bases), _ptr(offs), part, n_parts),
+        """bases: host bytes, or a torch uint8 tensor on the ctx's GPU (include/kslam.h: the copy is cudaMemcpyDefault)"""
+        offs = _u64(offs)
+        if hasattr(bases, "data_ptr"):
+            if getattr(bases, "is_cuda", False):
+                import torch
+                torch.cuda.synchronize(bases.device)       # the library copies on its own stream: the producer must be done
+            ptr = C.c_void_p(bases.data_ptr())
+        else:
+            bases = _u8(bases); ptr = _ptr(bases)
+        self._check(self.L.kslam_load_genomes_part(self.h, len(offs) - 1, ptr, _ptr(offs), part, n_parts),
                     "kslam_load_genomes_part")
         self.n_parts = n_parts
 
@@ -463,6 +489,52 @@ class Aligner:
 
 
 @dataclass
+class Comm:
+    """kslam_comm: one rank of the k-mer-range partitioned path with the exchanges issued by the library over NCCL
+    (csrc/comm.cu). The Aligner must hold this rank's key range: load_genomes_part(bases, offs, rank, n_ranks)."""
+
+    def __init__(self, aligner, handle):
+        self.al, self.h, self.L = aligner, handle, aligner.L
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        if lib().kslam_comm_unique_id(buf) != 0:
+            raise KslamError("kslam_comm_unique_id failed: " + lib().kslam_last_error(None).decode())
+        return buf.raw
+
+    @classmethod
+    def init_rank(cls, aligner, rank, n_ranks, uid: bytes):
+        h = C.c_void_p()
+        aligner._check(aligner.L.kslam_comm_init_rank(aligner.h, rank, n_ranks, C.create_string_buffer(uid, 128), C.byref(h)), "kslam_comm_init_rank")
+        return cls(aligner, h)
+
+    @classmethod
+    def init_all(cls, aligners):
+        """One process, one Aligner per DISTINCT device; drive every returned Comm from its own host thread."""
+        n = len(aligners)
+        ctxs = (C.c_void_p * n)(*[a.h for a in aligners])
+        out = (C.c_void_p * n)()
+        aligners[0]._check(aligners[0].L.kslam_comm_init_all(n, ctxs, out), "kslam_comm_init_all")
+        return [cls(a, C.c_void_p(out[i])) for i, a in enumerate(aligners)]
+
+    def align_resident(self, fetch=True, copy=True):
+        """Collective: alignToDatabase over the partitioned index for the reads this rank uploaded (Aligner.upload_reads)."""
+        out = _Alignments()
+        self.al._check(self.L.kslam_comm_align_resident(self.h, int(fetch), C.byref(out)), "kslam_comm_align_resident")
+        return self.al._alignments(out, copy) if fetch else int(out.n_overlaps)
+
+    def stats(self) -> dict:
+        st = CommStats()
+        self.L.kslam_comm_get_stats(self.h, C.byref(st))
+        return st.as_dict()
+
+    def close(self):
+        if self.h:
+            self.L.kslam_comm_destroy(self.h)
+            self.h = None
+
+
 class ReadBatch:
     """One batch of the FASTQ reader: R1 block then R2 block, the layout Aligner.align_batch takes."""
     n_r1: int

@@ -120,6 +120,14 @@ int kslam_set_prefilter(kslam_ctx *ctx, int on) {
   return KSLAM_OK;
 }
 
+int kslam_device_memory(int32_t device, uint64_t *free_bytes, uint64_t *total_bytes) {
+  size_t f = 0, t = 0;
+  if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&f, &t) != cudaSuccess) { cudaGetLastError(); return KSLAM_ERR_CUDA; }
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return KSLAM_OK;
+}
+
 int kslam_set_report_cigar(kslam_ctx *ctx, int on) {
   if (!ctx) return KSLAM_ERR_ARG;
   ctx->prm.report_cigar = on != 0;

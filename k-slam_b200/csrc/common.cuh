@@ -137,6 +137,7 @@ struct kslam_ctx {
   DevBuf d_bounds;                   // u64[64] bucket bounds on the device (key splitters or read-id bases)
   DevBuf part_send, part_recv, part_tmp, part_m, part_msend, part_mrecv;
   uint64_t n_gk_total = 0;
+  float part_ms_bucket = 0, part_ms_bucket_matches = 0;   // device time of the two bucketing steps of the last partitioned batch
 
   // microbench / Aligner::Align batch
   PackedSeqs swq, swr;

@@ -230,10 +230,12 @@ int kslam_part_route_kmers(kslam_ctx *c, uint32_t read_id_base, const void **dev
     n = extract_read_kmers_filtered(c, c->reads, c->recA, read_id_base);
   }
   c->part_send.reserve((size_t)n * sizeof(Rec16) + 64);
+  cudaEvent_t em = tm_mark(c);
   bucket_records<0>(c, c->recA.as<Rec16>(), n, c->splitters.data(), c->part_send.as<Rec16>(), counts);
   cudaEvent_t e1 = tm_mark(c);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->tm.ms_extract = tm_ms(e0, e1);
+  c->part_ms_bucket = tm_ms(em, e1);
   c->tm.n_sorted_kmers = n;
   *dev_records = c->part_send.p;
   return KSLAM_OK;
@@ -265,10 +267,12 @@ int kslam_part_join(kslam_ctx *c, uint64_t n_records, const uint32_t *id_bases, 
   c->part_msend.reserve((size_t)n_m * sizeof(Rec16) + 64);
   uint64_t bounds[DIST_MAX_PARTS];
   for (uint32_t p = 0; p < c->n_parts; p++) bounds[p] = id_bases[p];
+  cudaEvent_t em = tm_mark(c);
   bucket_records<1>(c, c->part_m.as<Rec16>(), n_m, bounds, c->part_msend.as<Rec16>(), counts);
   cudaEvent_t e2 = tm_mark(c);
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   c->tm.ms_sort = tm_ms(e0, e1); c->tm.ms_join = tm_ms(e1, e2);
+  c->part_ms_bucket_matches = tm_ms(em, e2);
   c->tm.n_sort_passes = passes;
   *dev_matches = c->part_msend.p;
   return KSLAM_OK;

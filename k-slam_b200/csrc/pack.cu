@@ -115,7 +115,7 @@ void pack_sequences(kslam_ctx *c, PackedSeqs &s, uint64_t n, const char *bases, 
   s.raw.reserve(s.n_bases + 16);
   s.kbits.reserve((w + 2) * 8); s.sbits.reserve((w + 2) * 8); s.nmask.reserve((w + 2) * 4);
   s.xmask.reserve((w + 2) * 4);
-  if (s.n_bases) CUDA_TRY(cudaMemcpyAsync(s.raw.p, bases + offs[0], s.n_bases, cudaMemcpyHostToDevice, st));
+  if (s.n_bases) CUDA_TRY(cudaMemcpyAsync(s.raw.p, bases + offs[0], s.n_bases, cudaMemcpyDefault, st));   // host or (UVA) device source
   // two guard words past the end so funnel shifts / window gathers may read one word ahead
   CUDA_TRY(cudaMemsetAsync((char *)s.kbits.p + w * 8, 0, 16, st));
   CUDA_TRY(cudaMemsetAsync((char *)s.sbits.p + w * 8, 0, 16, st));

@@ -49,6 +49,8 @@ struct Options {                                           // main.cpp:36-82, de
   bool help = false, version = false, samXA = false, justAlign = false, noPseudoAssembly = false;
   bool parseGenbank = false, parseFasta = false, parseTaxonomy = false;
   std::vector<int> devices{0};                             // extension: --device N / --devices N,M,... (CUDA ordinals, one context each)
+  uint32_t maxCigarOps = 0;                                // extension: --max-cigar-ops N: initial CIGAR pool stride (it grows when a CIGAR needs more)
+  int partitionIndex = -1;                                 // extension: --partition-index 0|1 (-1 = decide from the database size)
   std::vector<std::string> inputs;
 };
 
@@ -57,7 +59,7 @@ const OptSpec kSpecs[] = {
     {"help", 0}, {"db", 1}, {"min-alignment-score", 1}, {"score-fraction-threshold", 1}, {"match-score", 1}, {"mismatch-penalty", 1},
     {"gap-open", 1}, {"gap-extend", 1}, {"num-reads", 1}, {"num-reads-at-once", 1}, {"output-file", 1}, {"sam-file", 1},
     {"num-alignments", 1}, {"sam-xa", 0}, {"version", 0}, {"just-align", 0}, {"no-pseudo-assembly", 0}, {"server", 0},
-    {"input-file", 1}, {"parse-genbank", 0}, {"parse-fasta", 0}, {"parse-taxonomy", 0}, {"alignment-only", 0}, {"device", 1}, {"devices", 1}};
+    {"input-file", 1}, {"parse-genbank", 0}, {"parse-fasta", 0}, {"parse-taxonomy", 0}, {"alignment-only", 0}, {"device", 1}, {"devices", 1}, {"partition-index", 1}, {"max-cigar-ops", 1}};
 
 uint32_t to_u32(const std::string &name, const std::string &v) {
   size_t used = 0;
@@ -120,6 +122,8 @@ Options parse_options(int argc, char **argv) {
     else if (name == "parse-fasta") o.parseFasta = true;
     else if (name == "parse-taxonomy") o.parseTaxonomy = true;
     else if (name == "device") o.devices.assign(1, (int)to_u32(name, value));
+    else if (name == "partition-index") o.partitionIndex = to_u32(name, value) ? 1 : 0;
+    else if (name == "max-cigar-ops") o.maxCigarOps = to_u32(name, value);
     else if (name == "devices") {
       o.devices.clear();
       for (size_t at = 0; at <= value.size();) {
@@ -158,7 +162,11 @@ void usage() {                                             // main.cpp:96-107
                "  --no-pseudo-assembly                  do not link alignments together\n"
                "  --device arg (=0)                     CUDA device ordinal (this implementation)\n"
                "  --devices arg                         comma-separated CUDA ordinals: every batch is split into that many contiguous\n"
-               "                                        ranges of read pairs, one context per entry (this implementation)\n\n";
+               "                                        ranges of read pairs, one context per entry (this implementation)\n"
+               "  --partition-index arg                 1: range-partition the genome k-mer index by k-mer prefix over --devices and route\n"
+               "                                        read k-mers / matches with NCCL all-to-alls; 0: replicate it; default: partition\n"
+               "                                        when a replica would not fit a device (this implementation)\n"
+               "  --max-cigar-ops arg (=32)             initial per-alignment CIGAR capacity; grown automatically (this implementation)\n\n";
 }
 
 // bounded hand-over between two pipeline stages
@@ -185,12 +193,14 @@ bool write_file(const std::string &path, const char *text, uint64_t len) {
 // pairs that keep mates together (R1 i and R2 i + mid), every context runs the whole path on its range, and the results are
 // joined in range order with read / overlap / cigar indices rebased — which is the order one context would have produced
 // (same rules as k-slam_b200/shard.py: pairing is per pair, seeds are per (read, genome)).
-void align_batch(const std::vector<kslam_ctx *> &ctxs, bool isPaired, Batch *b) {
+void align_batch(const std::vector<kslam_ctx *> &ctxs, const std::vector<kslam_comm *> &comms, bool isPaired, Batch *b) {
   const kslam_read_batch &r = b->reads;
   // (a paired batch with an odd read count — the reference's R1/R2 size check lets n2 = n1 + 1 through, FASTQsequence.h:118-122 —
   // pairs its last read by index modulo the midpoint, which no contiguous split reproduces: such a batch runs on one context)
-  const size_t G = (isPaired && (r.n_reads & 1)) ? 1 : ctxs.size();
-  if (G == 1) {
+  const bool partitioned = !comms.empty();                 // every rank takes part in every batch, even with an empty range
+  const size_t G = (!partitioned && isPaired && (r.n_reads & 1)) ? 1 : ctxs.size();
+  if (partitioned && isPaired && (r.n_reads & 1)) { b->error = "a paired batch with an odd read count cannot be sharded over a partitioned index"; return; }
+  if (G == 1 && !partitioned) {
     if (isPaired) {
       kslam_pairs p;
       if (kslam_align_pair_batch(ctxs[0], r.n_reads, r.bases, r.offs, &p) != KSLAM_OK) { b->error = kslam_last_error(ctxs[0]); return; }
@@ -212,10 +222,33 @@ void align_batch(const std::vector<kslam_ctx *> &ctxs, bool isPaired, Batch *b) 
   for (size_t g = 0; g < G; g++) {
     Shard &s = shards[g];
     s.lo = units * g / G; s.hi = units * (g + 1) / G;
-    if (s.hi == s.lo) continue;
+    if (s.hi == s.lo && !partitioned) continue;
     th.emplace_back([&, g] {
       Shard &s = shards[g];
       const uint64_t cnt = s.hi - s.lo;
+      if (partitioned) {
+        // kslam_comm: upload this rank's range, then the collective alignToDatabase over the k-mer-range partitioned index
+        // (csrc/comm.cu: both all-to-alls are ncclSend / ncclRecv groups issued by the library), then pairing as usual
+        if (isPaired) {
+          const uint64_t a0 = r.offs[s.lo], a1 = r.offs[s.hi], b0 = r.offs[mid + s.lo], b1 = r.offs[mid + s.hi];
+          s.bases.resize((a1 - a0) + (b1 - b0) + 1);
+          memcpy(s.bases.data(), r.bases + a0, a1 - a0);
+          memcpy(s.bases.data() + (a1 - a0), r.bases + b0, b1 - b0);
+          s.offs.assign(2 * cnt + 1, 0);
+          for (uint64_t i = 0; i <= cnt; i++) s.offs[i] = r.offs[s.lo + i] - a0;
+          for (uint64_t i = 1; i <= cnt; i++) s.offs[cnt + i] = (a1 - a0) + (r.offs[mid + s.lo + i] - b0);
+        } else {
+          s.offs.assign(cnt + 1, 0);
+          for (uint64_t i = 0; i <= cnt; i++) s.offs[i] = r.offs[s.lo + i] - r.offs[s.lo];
+        }
+        const char *base_ptr = isPaired ? s.bases.data() : r.bases + r.offs[s.lo];
+        const uint64_t n_here = isPaired ? 2 * cnt : cnt;
+        int rc = kslam_upload_reads(ctxs[g], n_here, base_ptr, s.offs.data());
+        if (rc == KSLAM_OK) rc = kslam_comm_align_resident(comms[g], isPaired ? 0 : 1, isPaired ? nullptr : &s.a);
+        if (rc == KSLAM_OK && isPaired) rc = kslam_pair_batch(ctxs[g], 1, &s.p);
+        if (rc != KSLAM_OK) s.error = kslam_last_error(ctxs[g]);
+        return;
+      }
       if (isPaired) {                                      // R1 block of the range, then its R2 block, in one array
         const uint64_t a0 = r.offs[s.lo], a1 = r.offs[s.hi], b0 = r.offs[mid + s.lo], b1 = r.offs[mid + s.hi];
         s.bases.resize((a1 - a0) + (b1 - b0));
@@ -282,7 +315,7 @@ int run_alignment(const Options &o, const std::string &commandLine) {      // me
   prm.match = (uint8_t)o.match; prm.mismatch = (uint8_t)o.misMatch; prm.gap_open = (uint8_t)o.gapOpen; prm.gap_extend = (uint8_t)o.gapExtend;   // ssw_cpp.cpp:114-117
   // sw_score is 16 bits (ssw_cpp.h:16): a larger threshold screens everything, as in the reference
   prm.score_threshold = (uint16_t)(o.scoreThreshold > 65535u ? 65535u : o.scoreThreshold);
-  prm.report_cigar = wantSam ? 1 : 0; prm.device = o.devices[0];
+  prm.report_cigar = wantSam ? 1 : 0; prm.device = o.devices[0]; prm.max_cigar_ops = o.maxCigarOps;
   if (!kslam_params_fast(&prm))
     log("Scoring parameters outside gap-extend < gap-open, mismatch <= 2 * gap-extend: Smith-Waterman runs the lane-for-lane restatement of SSW's striped kernels (same results, slower)");
   // one context per entry of --devices, the genome index replicated in each (read pairs shard trivially)
@@ -293,12 +326,30 @@ int run_alignment(const Options &o, const std::string &commandLine) {      // me
     if (kslam_create(&prm, &ctxs[g]) != KSLAM_OK) { std::cerr << "SLAM: " << kslam_last_error(nullptr) << "\n"; return 3; }
   }
   log("Getting k-mers from index");
+  // Replicate the genome k-mer index in every context, or — when a replica (16 B per record resident, three times that
+  // while it is built) would not fit a device, or on request — range-partition it by k-mer prefix over the devices
+  // (kslam_load_genomes_part + kslam_comm: read k-mers are routed to their key owner by NCCL all-to-all).
+  std::vector<kslam_comm *> comms;
   {
+    uint64_t n_records = 0;
+    for (uint64_t e = 0; e < db.n_entries; e++) { const uint64_t len = db.offs[e + 1] - db.offs[e]; if (len >= 32) n_records += (len - 32) / 16 + 1; }
+    uint64_t free_b = 0, total_b = 0;
+    kslam_device_memory(o.devices[0], &free_b, &total_b);
+    const bool too_big = (double)n_records * 48.0 + (double)db.offs[db.n_entries] * 1.8 > 0.8 * (double)total_b;
+    const bool partition = G > 1 && (o.partitionIndex == 1 || (o.partitionIndex < 0 && too_big));
+    if (too_big && !partition) log("Warning: the genome k-mer index may not fit one device; give several --devices to range-partition it");
     std::vector<int> rc(G, 0);
     std::vector<std::thread> th;
-    for (size_t g = 0; g < G; g++) th.emplace_back([&, g] { rc[g] = kslam_load_genomes(ctxs[g], db.n_entries, db.bases, db.offs); });
+    for (size_t g = 0; g < G; g++)
+      th.emplace_back([&, g] { rc[g] = partition ? kslam_load_genomes_part(ctxs[g], db.n_entries, db.bases, db.offs, (uint32_t)g, (uint32_t)G)
+                                                 : kslam_load_genomes(ctxs[g], db.n_entries, db.bases, db.offs); });
     for (auto &t : th) t.join();
     for (size_t g = 0; g < G; g++) if (rc[g] != KSLAM_OK) { std::cerr << "SLAM: " << kslam_last_error(ctxs[g]) << "\n"; return 3; }
+    if (partition) {
+      log("Genome k-mer index range-partitioned over " + std::to_string(G) + " devices (" + std::to_string(n_records) + " records)");
+      comms.assign(G, nullptr);
+      if (kslam_comm_init_all((uint32_t)G, ctxs.data(), comms.data()) != KSLAM_OK) { std::cerr << "SLAM: " << kslam_last_error(ctxs[0]) << "\n"; return 3; }
+    }
   }
 
   kslam_fastq *reader = nullptr;
@@ -341,7 +392,7 @@ int run_alignment(const Options &o, const std::string &commandLine) {      // me
   std::thread gpu([&] {                                    // stage 2: alignToDatabase + score screen + getPairedOverlaps on the GPU(s)
     for (;;) {
       Batch *b = to_gpu.take();
-      if (b->reads.n_reads && b->error.empty()) align_batch(ctxs, isPaired, b);
+      if (b->reads.n_reads && b->error.empty()) align_batch(ctxs, comms, isPaired, b);
       const bool last = b->reads.n_reads == 0 || !b->error.empty();
       to_host.put(b);
       if (last) return;
@@ -410,6 +461,7 @@ int run_alignment(const Options &o, const std::string &commandLine) {      // me
   fflush(stdout);
   if (getenv("KSLAM_FAST_EXIT")) _Exit(rc);
   kslam_fastq_close(reader);
+  for (kslam_comm *m : comms) kslam_comm_destroy(m);
   for (kslam_ctx *c : ctxs) kslam_destroy(c);
   kslam_taxa_destroy(taxa);
   kslam_taxdb_close(taxdb);

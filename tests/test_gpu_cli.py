@@ -87,6 +87,15 @@ def test_slam_executable_equals_reference(pkg, tmp_path):
         assert body((tmp_path / "m.sam").read_bytes()) == sam
         for suffix, want in zip(("_PerRead", "", "_abbreviated"), outs):
             assert (tmp_path / ("m.xml" + suffix)).read_bytes() == want, suffix
+        # the genome k-mer index range-partitioned over two GPUs, read k-mers routed by the library's own NCCL all-to-alls
+        import torch
+        if torch.cuda.device_count() >= 2:
+            r = run("--db", db, "--sam-file", "q.sam", "--output-file", "q.xml", "--num-reads-at-once", 150, "--devices", "0,1", "--partition-index", 1, r1, r2)
+            assert r.returncode == 0, r.stderr
+            assert body((tmp_path / "q.sam").read_bytes()) == sam
+            for suffix, want in zip(("_PerRead", "", "_abbreviated"), outs):
+                assert (tmp_path / ("q.xml" + suffix)).read_bytes() == want, suffix
+            assert b"range-partitioned over 2 devices" in (tmp_path / "log.txt").read_bytes()
         # paired, taxonomy only (no SAM: the records are not re-sorted before the taxonomy step), XML to stdout, --num-reads cut
         r = run("--db=" + str(db), "--num-reads", 250, "--num-reads-at-once", 100, "--no-pseudo-assembly", "--score-fraction-threshold", 0.5, r1, r2)
         assert r.returncode == 0, r.stderr

@@ -108,6 +108,61 @@ def test_partitioned_empty_rank_and_errors(pkg):
             al.part_route_kmers(0)                      # no reads uploaded
 
 
+def test_comm_single_rank_equals_unpartitioned(pkg):
+    """kslam_comm (the exchanges issued by the C++ host over NCCL, csrc/comm.cu) with one rank: every NCCL call of the
+    protocol runs (all-gathers, send / recv to self) and the result equals kslam_align_batch + the oracle."""
+    gb, go, rb, ro = pkg.synth.adversarial_set(seed=43, n_genomes=8, glen=8000, n_pairs=500)
+    want = T.ko_pipeline(gb, go, rb, ro, T.default_params(report_cigar=1))
+    with pkg.Aligner(report_cigar=True) as al:
+        al.load_genomes_part(gb, go, 0, 1)
+        comm = pkg.Comm.init_rank(al, 0, 1, pkg.Comm.unique_id())
+        for _ in range(2):                                   # a second batch reuses every buffer
+            al.upload_reads(rb, ro)
+            res = comm.align_resident()
+            pairs = al.pair_batch()
+            check_overlaps(res.overlaps, res.cigar_pool, want["overlaps"], want["cigar_pool"])
+            assert np.array_equal(pairs.pairs, want["pairs"])
+        st = comm.stats()
+        assert st["kmers_sent"] == st["kmers_received"] > 0 and st["matches_sent"] == st["matches_received"] > 0
+        assert st["bytes_sent_kmers"] == 0                   # nothing leaves the only GPU
+        comm.close()
+
+
+def test_comm_two_gpus_one_process(pkg):
+    """kslam_comm_init_all: one process, one ctx per GPU, one host thread per rank (what `SLAM --devices 0,1` does)."""
+    import torch
+    from kslam_b200 import shard
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, n_pairs = 2, 6000
+    gb, go = pkg.synth.random_genomes(12, 200_000, seed=7)
+    rb, ro, _ = pkg.synth.paired_reads(gb, go, n_pairs, seed=8)
+    reads = [shard.slice_reads(rb, ro, *shard.pair_range(n_pairs, world, r)) for r in range(world)]
+    als = [pkg.Aligner(report_cigar=True, device=r) for r in range(world)]
+    for r, al in enumerate(als):
+        al.load_genomes_part(gb, go, r, world)
+    comms = pkg.Comm.init_all(als)
+    out, errs = [None] * world, []
+
+    def run(r):
+        try:
+            als[r].upload_reads(*reads[r])
+            res = comms[r].align_resident()
+            out[r] = (res, als[r].pair_batch(), comms[r].stats())
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert not errs, errs
+    assert sum(o[2]["bytes_sent_kmers"] for o in out) > 0
+    P = T.default_params(report_cigar=1)
+    for r in range(world):
+        want = T.ko_pipeline(gb, go, *reads[r], P)
+        check_overlaps(out[r][0].overlaps, out[r][0].cigar_pool, want["overlaps"], want["cigar_pool"])
+        assert np.array_equal(out[r][1].pairs, want["pairs"])
+    [c.close() for c in comms]; [a.close() for a in als]
+
+
 def test_partitioned_nccl_two_gpus():
     """Real exchange: one process per GPU, NCCL all_to_all_single over NVLink (skipped on a single-GPU box)."""
     import os
