@@ -488,7 +488,6 @@ class Aligner:
         self._check(self.L.kslam_set_debug_taps(self.h, int(keep)), "kslam_set_debug_taps")
 
 
-@dataclass
 class Comm:
     """kslam_comm: one rank of the k-mer-range partitioned path with the exchanges issued by the library over NCCL
     (csrc/comm.cu). The Aligner must hold this rank's key range: load_genomes_part(bases, offs, rank, n_ranks)."""
@@ -535,6 +534,7 @@ class Comm:
             self.h = None
 
 
+@dataclass
 class ReadBatch:
     """One batch of the FASTQ reader: R1 block then R2 block, the layout Aligner.align_batch takes."""
     n_r1: int

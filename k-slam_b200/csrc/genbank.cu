@@ -13,6 +13,10 @@
 // reference's reader on this file's archives. The parsers are pinned against the reference's own createIndexFromGBFF / createIndexFromFASTA
 // (tests/test_taxon_host.py, through oracle/_ref).
 #include "common.cuh"
+#include <unistd.h>
+#include <sys/stat.h>
+#include <sys/mman.h>
+#include <fcntl.h>
 #include "host_stages.h"
 #include <algorithm>
 #include <atomic>
@@ -124,6 +128,9 @@ void parse_section(const std::string &field, Entry &entry) {          // parseSe
 // GenbankIndex held flat: what kslam_load_genomes, kslam_sam_db and the archive writer take without another copy.
 struct kslam_index {
   std::string bases; std::vector<uint64_t> offs{0};
+  // bases of an index that came from the side-car cache live in the mapping of that file, not in `bases`
+  const char *mapped_bases = nullptr; void *map = nullptr; size_t map_len = 0;
+  const char *bases_data() const { return mapped_bases ? mapped_bases : bases.data(); }
   std::string locus; std::vector<uint64_t> locus_offs{0};
   std::vector<uint32_t> taxonomy_ids, genbank_ids;
   std::vector<uint8_t> is_plasmid, is_16s;
@@ -147,7 +154,7 @@ struct kslam_index {
   }
   uint64_t n() const { return offs.size() - 1; }
   mutable kslam_gene_index *gene_index = nullptr;          // built on the first kslam_index_db
-  ~kslam_index() { delete gene_index; }
+  ~kslam_index() { delete gene_index; if (map) munmap(map, map_len); }
 };
 
 namespace {
@@ -182,6 +189,87 @@ struct ArchiveReader {
   void class_info(unsigned bit) { if (!(seen & bit)) { seen |= bit; number(); number(); } }
   uint64_t vector(unsigned bit) { class_info(bit); const uint64_t count = number(); number(); return count; }
 };
+
+// ---- side-car cache of DIR/database -------------------------------------------------------------------
+// DIR/database is a Boost TEXT archive (GenbankTools.h:197-205,336-344): reading it means tokenising every number and
+// copying every base. `<database>.kslam` holds the same GenbankIndex as flat binary arrays, keyed by the size and
+// modification time of the archive it was made from; it is mapped, the small tables are copied and the bases are used in
+// place. It is written (best effort, silently skipped in a read-only directory or with KSLAM_NO_INDEX_CACHE set) after
+// the first successful parse and ignored whenever its key no longer matches. Only the HOST side is cached: the device side
+// (2-bit planes, sorted genome k-mer list, prefilter bitmap) is ~2 bytes per base and the B200 rebuilds it from the bases at
+// ~0.15 s per Gbp — faster than those bytes come in over PCIe from pageable memory.
+struct CacheHeader {
+  char magic[8];
+  uint64_t src_size, src_mtime_ns, n_entries, n_bases, n_locus, n_genes, n_gene_strings;
+};
+const char kCacheMagic[8] = {'K', 'S', 'L', 'A', 'M', 'I', 'X', '1'};
+
+bool source_key(const char *path, uint64_t *size, uint64_t *mtime_ns) {
+  struct stat st;
+  if (stat(path, &st) != 0 || !S_ISREG(st.st_mode)) return false;
+  *size = (uint64_t)st.st_size; *mtime_ns = (uint64_t)st.st_mtim.tv_sec * 1000000000ull + (uint64_t)st.st_mtim.tv_nsec;
+  return true;
+}
+size_t pad8(size_t n) { return (n + 7) & ~(size_t)7; }
+
+kslam_index *cache_load(const std::string &cache_path, uint64_t src_size, uint64_t src_mtime_ns) {
+  const int fd = open(cache_path.c_str(), O_RDONLY);
+  if (fd < 0) return nullptr;
+  struct stat st;
+  if (fstat(fd, &st) != 0 || (size_t)st.st_size < sizeof(CacheHeader)) { close(fd); return nullptr; }
+  void *map = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (map == MAP_FAILED) return nullptr;
+  const CacheHeader *h = (const CacheHeader *)map;
+  const size_t n = (size_t)h->n_entries;
+  size_t need = sizeof(CacheHeader) + 3 * pad8((n + 1) * 8) + 2 * pad8(n * 4) + 2 * pad8(n) + pad8((size_t)h->n_genes * sizeof(kslam_gene)) +
+                pad8((size_t)h->n_locus) + pad8((size_t)h->n_gene_strings) + (size_t)h->n_bases;
+  if (memcmp(h->magic, kCacheMagic, 8) != 0 || h->src_size != src_size || h->src_mtime_ns != src_mtime_ns || need != (size_t)st.st_size) {
+    munmap(map, (size_t)st.st_size);
+    return nullptr;
+  }
+  kslam_index *ix = new kslam_index();
+  ix->map = map; ix->map_len = (size_t)st.st_size;
+  const char *p = (const char *)map + sizeof(CacheHeader);
+  auto take = [&](void *dst, size_t bytes) { memcpy(dst, p, bytes); p += pad8(bytes); };
+  ix->offs.resize(n + 1); take(ix->offs.data(), (n + 1) * 8);
+  ix->locus_offs.resize(n + 1); take(ix->locus_offs.data(), (n + 1) * 8);
+  ix->gene_offs.resize(n + 1); take(ix->gene_offs.data(), (n + 1) * 8);
+  ix->taxonomy_ids.resize(n); take(ix->taxonomy_ids.data(), n * 4);
+  ix->genbank_ids.resize(n); take(ix->genbank_ids.data(), n * 4);
+  ix->is_plasmid.resize(n); take(ix->is_plasmid.data(), n);
+  ix->is_16s.resize(n); take(ix->is_16s.data(), n);
+  ix->genes.resize((size_t)h->n_genes); take(ix->genes.data(), (size_t)h->n_genes * sizeof(kslam_gene));
+  ix->locus.resize((size_t)h->n_locus); take(&ix->locus[0], (size_t)h->n_locus);
+  ix->gene_strings.resize((size_t)h->n_gene_strings); take(&ix->gene_strings[0], (size_t)h->n_gene_strings);
+  ix->mapped_bases = p;
+  if (ix->offs[0] != 0 || ix->offs[n] != h->n_bases || ix->gene_offs[n] != h->n_genes) { delete ix; return nullptr; }
+  return ix;
+}
+
+void cache_store(const kslam_index *ix, const std::string &cache_path, uint64_t src_size, uint64_t src_mtime_ns) {
+  const std::string tmp = cache_path + ".tmp" + std::to_string((long)getpid());
+  FILE *f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  CacheHeader h;
+  memcpy(h.magic, kCacheMagic, 8);
+  const size_t n = ix->n();
+  h.src_size = src_size; h.src_mtime_ns = src_mtime_ns; h.n_entries = n; h.n_bases = ix->offs[n]; h.n_locus = ix->locus.size();
+  h.n_genes = ix->genes.size(); h.n_gene_strings = ix->gene_strings.size();
+  bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+  static const char zeros[8] = {0};
+  auto put = [&](const void *src, size_t bytes) {
+    if (bytes) ok = ok && fwrite(src, 1, bytes, f) == bytes;
+    if (pad8(bytes) != bytes) ok = ok && fwrite(zeros, 1, pad8(bytes) - bytes, f) == pad8(bytes) - bytes;
+  };
+  put(ix->offs.data(), (n + 1) * 8); put(ix->locus_offs.data(), (n + 1) * 8); put(ix->gene_offs.data(), (n + 1) * 8);
+  put(ix->taxonomy_ids.data(), n * 4); put(ix->genbank_ids.data(), n * 4); put(ix->is_plasmid.data(), n); put(ix->is_16s.data(), n);
+  put(ix->genes.data(), ix->genes.size() * sizeof(kslam_gene)); put(ix->locus.data(), ix->locus.size());
+  put(ix->gene_strings.data(), ix->gene_strings.size());
+  if (h.n_bases) ok = ok && fwrite(ix->bases_data(), 1, (size_t)h.n_bases, f) == (size_t)h.n_bases;
+  ok = fclose(f) == 0 && ok;
+  if (!ok || rename(tmp.c_str(), cache_path.c_str()) != 0) unlink(tmp.c_str());
+}
 
 }  // namespace
 
@@ -313,6 +401,10 @@ int kslam_index_parse_fasta(const char *const *paths, uint64_t n_paths, kslam_in
 int kslam_index_read(const char *path, kslam_index **out) {           // getIndexFromBoostSerial, :336-344
   if (!path || !out) return KSLAM_ERR_ARG;
   kslam_index *index = nullptr;
+  uint64_t src_size = 0, src_mtime = 0;
+  const bool use_cache = !getenv("KSLAM_NO_INDEX_CACHE") && source_key(path, &src_size, &src_mtime);
+  const std::string cache_path = std::string(path) + ".kslam";
+  if (use_cache && (index = cache_load(cache_path, src_size, src_mtime)) != nullptr) { *out = index; return KSLAM_OK; }
   try {
     std::string data;
     if (!read_file(path, data)) throw std::runtime_error("unable to open index file");
@@ -343,6 +435,7 @@ int kslam_index_read(const char *path, kslam_index **out) {           // getInde
       }
       index->add(en, bases);
     }
+    if (use_cache) cache_store(index, cache_path, src_size, src_mtime);
     *out = index;
     return KSLAM_OK;
   } catch (const std::exception &e) { g_error = e.what(); delete index; return KSLAM_ERR_ARG; }
@@ -361,7 +454,7 @@ int kslam_index_write(const kslam_index *ix, const char *path) {      // writeIn
   fprintf(f, " %llu 0", (unsigned long long)ix->n());
   for (uint64_t e = 0; e < ix->n(); e++) {
     info(ENTRY);
-    str(ix->bases.data() + ix->offs[e], ix->offs[e + 1] - ix->offs[e]);
+    str(ix->bases_data() + ix->offs[e], ix->offs[e + 1] - ix->offs[e]);
     fprintf(f, " %u %u %u %u", ix->taxonomy_ids[e], ix->genbank_ids[e], (unsigned)ix->is_plasmid[e], (unsigned)ix->is_16s[e]);
     str(ix->locus.data() + ix->locus_offs[e], ix->locus_offs[e + 1] - ix->locus_offs[e]);
     info(GENES);
@@ -408,7 +501,7 @@ int kslam_index_db(const kslam_index *ix, kslam_sam_db *out) {
   if (!ix || !out) return KSLAM_ERR_ARG;
   memset(out, 0, sizeof *out);
   out->n_entries = ix->n();
-  out->bases = ix->bases.data(); out->offs = ix->offs.data();
+  out->bases = ix->bases_data(); out->offs = ix->offs.data();
   out->locus_tags = ix->locus.data(); out->locus_offs = ix->locus_offs.data();
   out->taxonomy_ids = ix->taxonomy_ids.data();
   if (!ix->genes.empty()) {

@@ -296,6 +296,27 @@ int run_alignment(const Options &o, const std::string &commandLine) {      // me
   log("Performing metagenomic analysis");
   const bool isPaired = o.inputs.size() == 2;
   const bool wantSam = !o.samFileName.empty();
+  kslam_params prm;
+  memset(&prm, 0, sizeof prm);
+  prm.match = (uint8_t)o.match; prm.mismatch = (uint8_t)o.misMatch; prm.gap_open = (uint8_t)o.gapOpen; prm.gap_extend = (uint8_t)o.gapExtend;   // ssw_cpp.cpp:114-117
+  // sw_score is 16 bits (ssw_cpp.h:16): a larger threshold screens everything, as in the reference
+  prm.score_threshold = (uint16_t)(o.scoreThreshold > 65535u ? 65535u : o.scoreThreshold);
+  prm.report_cigar = wantSam ? 1 : 0; prm.device = o.devices[0]; prm.max_cigar_ops = o.maxCigarOps;
+  if (!kslam_params_fast(&prm))
+    log("Scoring parameters outside gap-extend < gap-open, mismatch <= 2 * gap-extend: Smith-Waterman runs the lane-for-lane restatement of SSW's striped kernels (same results, slower)");
+  // CUDA context creation (0.3-1.5 s) runs while the taxonomy and the database are read from disk
+  // one context per entry of --devices (read pairs shard trivially; the index is replicated or partitioned below)
+  const size_t G = o.devices.size();
+  std::vector<kslam_ctx *> ctxs(G, nullptr);
+  std::string create_error;
+  std::thread create([&] {
+    kslam_params p = prm;
+    for (size_t g = 0; g < G; g++) {
+      p.device = o.devices[g];
+      if (kslam_create(&p, &ctxs[g]) != KSLAM_OK) { create_error = kslam_last_error(nullptr); return; }
+    }
+  });
+  struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } join_on_any_return{create};
   kslam_taxdb *taxdb = nullptr;
   kslam_taxa *taxa = nullptr;
   if (!o.justAlign) {
@@ -310,21 +331,8 @@ int run_alignment(const Options &o, const std::string &commandLine) {      // me
   kslam_sam_db db;
   kslam_index_db(index, &db);
 
-  kslam_params prm;
-  memset(&prm, 0, sizeof prm);
-  prm.match = (uint8_t)o.match; prm.mismatch = (uint8_t)o.misMatch; prm.gap_open = (uint8_t)o.gapOpen; prm.gap_extend = (uint8_t)o.gapExtend;   // ssw_cpp.cpp:114-117
-  // sw_score is 16 bits (ssw_cpp.h:16): a larger threshold screens everything, as in the reference
-  prm.score_threshold = (uint16_t)(o.scoreThreshold > 65535u ? 65535u : o.scoreThreshold);
-  prm.report_cigar = wantSam ? 1 : 0; prm.device = o.devices[0]; prm.max_cigar_ops = o.maxCigarOps;
-  if (!kslam_params_fast(&prm))
-    log("Scoring parameters outside gap-extend < gap-open, mismatch <= 2 * gap-extend: Smith-Waterman runs the lane-for-lane restatement of SSW's striped kernels (same results, slower)");
-  // one context per entry of --devices, the genome index replicated in each (read pairs shard trivially)
-  const size_t G = o.devices.size();
-  std::vector<kslam_ctx *> ctxs(G, nullptr);
-  for (size_t g = 0; g < G; g++) {
-    prm.device = o.devices[g];
-    if (kslam_create(&prm, &ctxs[g]) != KSLAM_OK) { std::cerr << "SLAM: " << kslam_last_error(nullptr) << "\n"; return 3; }
-  }
+  create.join();
+  if (!create_error.empty()) { std::cerr << "SLAM: " << create_error << "\n"; return 3; }
   log("Getting k-mers from index");
   // Replicate the genome k-mer index in every context, or — when a replica (16 B per record resident, three times that
   // while it is built) would not fit a device, or on request — range-partition it by k-mer prefix over the devices

@@ -1,6 +1,8 @@
 """CPU tier: DIR/database (Boost text archive of GenbankIndex): SURVEY's worked example, round trips, and the
 bytes the REAL Boost.Serialization library writes for the same index (oracle/boost_archive_probe.cpp over the header-less
 libboost_serialization.so 1.78 that ships inside Nsight Compute — this image has no Boost headers)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -219,3 +221,49 @@ def test_the_reference_reads_our_database_through_real_boost(pkg, tmp_path):
         assert L.kref_read_database(cut.encode(), None, 0) == 2**64 - 1
     finally:
         os.chdir(cwd)
+
+
+def test_side_car_cache_of_the_database(pkg, tmp_path):
+    """DIR/database.kslam: written after the first parse, used while its key (size + mtime of the archive)
+    matches, ignored afterwards; an index that came from the cache is the same GenbankIndex (it writes the same archive)."""
+    import time
+    from test_taxon_host import make_db
+    _, _, _, _, _, _, _, paths = make_db(pkg, tmp_path, n_strains=6, length=5000)
+    ix = pkg.Index.parse_genbank(paths)
+    db = str(tmp_path / "database")
+    ix.write(db)
+    want = open(db, "rb").read()
+    cache = db + ".kslam"
+    assert not os.path.exists(cache)
+    a = pkg.Index.read(db)                                  # parses the text archive, leaves the side-car behind
+    assert os.path.exists(cache) and os.path.getsize(cache) > 6 * 5000
+    b = pkg.Index.read(db)                                  # comes from the side-car (mapped)
+    for k, got in enumerate((a, b)):
+        out = str(tmp_path / f"again{k}")
+        got.write(out)
+        assert open(out, "rb").read() == want, k
+        assert got.gene_records(0) == ix.gene_records(0)
+    a.close(); b.close()
+    # a stale side-car (the archive changed) is ignored and replaced
+    sub = tmp_path / "other"; sub.mkdir()
+    ix2 = pkg.Index.parse_genbank(make_db(pkg, sub, n_strains=4, length=3000)[7])
+    time.sleep(0.01)
+    ix2.write(db)
+    want2 = open(db, "rb").read()
+    c = pkg.Index.read(db)
+    out = str(tmp_path / "again2"); c.write(out)
+    assert open(out, "rb").read() == want2 != want
+    c.close()
+    # a truncated side-car is ignored too
+    open(cache, "r+b").truncate(100)
+    d = pkg.Index.read(db)
+    out = str(tmp_path / "again3"); d.write(out)
+    assert open(out, "rb").read() == want2
+    d.close()
+    os.environ["KSLAM_NO_INDEX_CACHE"] = "1"
+    try:
+        os.unlink(cache)
+        pkg.Index.read(db).close()
+        assert not os.path.exists(cache)
+    finally:
+        del os.environ["KSLAM_NO_INDEX_CACHE"]
