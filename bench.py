@@ -805,35 +805,14 @@ def main():
         ctxs.append(al2)
     last = [None] * depth
 
+    compact = not want_cigar                  # a run without --sam-file keeps only the compact pair records
+
     def run_e2e(n_batches):
         if depth == 1:
             for _ in range(n_batches):
                 last[0] = step_e2e()[1]
             return
-        errs = []
-        gpu_turn = threading.Lock()
-        trace = bool(os.environ.get("KSLAM_BENCH_TRACE"))
-
-        def worker(k):
-            try:
-                torch.cuda.set_device(local)
-                for _b in range(k, n_batches, depth):
-                    t0 = time.perf_counter()
-                    ctxs[k].upload_reads(rb_host, ro)
-                    t1 = time.perf_counter()
-                    with gpu_turn:
-                        t2 = time.perf_counter()
-                        ctxs[k].align_resident(fetch=False); ctxs[k].pair_batch(fetch=False)
-                        t3 = time.perf_counter()
-                    last[k] = ctxs[k].fetch_pairs(copy=False)
-                    if trace:
-                        log(f"[e2e ctx{k} batch{_b}] upload {t1 - t0:.3f}s wait {t2 - t1:.3f}s kernels {t3 - t2:.3f}s fetch {time.perf_counter() - t3:.3f}s")
-            except Exception as e:   # noqa: BLE001
-                errs.append(e)
-        th = [threading.Thread(target=worker, args=(k,)) for k in range(depth)]
-        [t.start() for t in th]; [t.join() for t in th]
-        if errs:
-            raise errs[0]
+        e2e_pipeline(ctxs, rb_host, ro, n_batches, local, compact, last)
 
     run_e2e(max(2, args.warmup - 1))
     barrier()
@@ -843,9 +822,8 @@ def main():
     tw3 = time.perf_counter()
     t_e2e = tw3 - tw0
     clocks = sampler.stop(tw_first, tw3) if rank == 0 else None
-    pr = last[0]
     h2d = int(rb_host.nbytes + 3 * ro.nbytes)
-    d2h = int(pr.sorted_overlaps.nbytes + pr.cigar_pool.nbytes + pr.pairs.nbytes)
+    d2h = d2h_bytes(last[0], compact and depth == 2)
     if depth == 2:
         al2.close()
 
@@ -902,7 +880,10 @@ def main():
                                        f"and of raw matches (NCCL)" if partitioned else f"read pairs, {world} ranks, no collective"),
                           "l2": "inputs larger than L2 (3.8 GB+ of k-mer records per step)", "report_cigar": want_cigar},
                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "call": "kslam_upload_reads + kslam_align_resident + kslam_pair_batch + kslam_fetch_pairs (host buffers in, pair-sorted overlaps + pairs back on the host)",
+                       "call": ("kslam_upload_reads + kslam_align_resident + kslam_pair_batch + kslam_fetch_pairs_compact (host buffers in; back on the host: what the batch loop of a run "
+                                "without --sam-file keeps — 24-byte pair records, the batch's insert-size limit computed from them, the mates of the pairs beyond it)"
+                                if compact and depth == 2 else
+                                "kslam_upload_reads + kslam_align_resident + kslam_pair_batch + kslam_fetch_pairs (host buffers in, pair-sorted overlaps + CIGAR pool + pairs back on the host)"),
                        "contexts_per_gpu": depth},
                "gpu_launches": int(launches),
                "clocks": clocks,
@@ -956,6 +937,45 @@ def main():
         dist.destroy_process_group()
 
 
+def e2e_pipeline(ctxs, rb, ro, n_batches, device, compact, last):
+    """Batches streamed through the contexts of one GPU (include/kslam.h: "two per GPU to double-buffer"), one host thread
+    each: kslam_upload_reads (H2D) | kslam_align_resident + kslam_pair_batch (kernels) | fetch (D2H). A host mutex around
+    the kernel phase hands the GPU from one context to the other, so the copies of one batch run under the kernels of the
+    other. compact: fetch = kslam_fetch_pairs_compact (runs without --sam-file), else kslam_fetch_pairs."""
+    import torch
+    depth = len(ctxs)
+    errs = []
+    gpu_turn = threading.Lock()
+    trace = bool(os.environ.get("KSLAM_BENCH_TRACE"))
+
+    def worker(k):
+        try:
+            torch.cuda.set_device(device)
+            for _b in range(k, n_batches, depth):
+                t0 = time.perf_counter()
+                ctxs[k].upload_reads(rb, ro)
+                t1 = time.perf_counter()
+                with gpu_turn:
+                    t2 = time.perf_counter()
+                    ctxs[k].align_resident(fetch=False); ctxs[k].pair_batch(fetch=False)
+                    t3 = time.perf_counter()
+                last[k] = ctxs[k].fetch_pairs_compact(copy=False) if compact else ctxs[k].fetch_pairs(copy=False)
+                if trace:
+                    log(f"[e2e ctx{k} batch{_b}] upload {t1 - t0:.3f}s wait {t2 - t1:.3f}s kernels {t3 - t2:.3f}s fetch {time.perf_counter() - t3:.3f}s")
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(depth)]
+    [t.start() for t in th]; [t.join() for t in th]
+    if errs:
+        raise errs[0]
+
+
+def d2h_bytes(res, compact):
+    if compact:
+        return int(res[0].nbytes + res[2].nbytes)
+    return int(res.sorted_overlaps.nbytes + res.cigar_pool.nbytes + res.pairs.nbytes)
+
+
 def config1_block(args, pkg, device):
     """Config 1 (the --just-align --sam-file run, reportCigar on): 1 M pairs vs 50 x 3 Mbp, resident value, e2e through the
     C ABI with pinned host buffers, stage times, the sort's HBM figure, and the reference on a sample with outputs compared."""
@@ -977,18 +997,23 @@ def config1_block(args, pkg, device):
             if k.startswith("ms_"):
                 stage[k] = stage.get(k, 0.0) + v / steps
     t_res = (time.perf_counter() - t0) / steps
-    al.align_pair_batch(rb, ro, copy=False)
+    al2 = pkg.Aligner(report_cigar=True, device=device)
+    al2.set_debug_taps(False)
+    al2.load_genomes(gb, go)
+    last = [None, None]
+    e2e_pipeline([al, al2], rb, ro, 4, device, False, last)
     t0 = time.perf_counter()
-    for _ in range(steps):
-        pr = al.align_pair_batch(rb, ro, copy=False)
-    t_e2e = (time.perf_counter() - t0) / steps
+    e2e_pipeline([al, al2], rb, ro, 2 * steps, device, False, last)
+    t_e2e = (time.perf_counter() - t0) / (2 * steps)
+    pr = last[0]
+    al2.close()
     peak, peak_src = measured_peaks()
     passes = max(1, al.kmer_sort_bits() // 8)
     n_rk = tm["n_sorted_kmers"]
     ach = 32.0 * n_rk / (stage["ms_sort"] / 1e3 / passes) / 1e9
     blk = {"workload": desc + ", CIGARs on", "value": pairs / t_res * 60 / 1e6, "unit": UNIT, "ms_per_step": t_res * 1e3,
            "e2e": {"value": pairs / t_e2e * 60 / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(rb.nbytes + 3 * ro.nbytes),
-                   "d2h_bytes_per_step": int(pr.sorted_overlaps.nbytes + pr.cigar_pool.nbytes + pr.pairs.nbytes), "contexts_per_gpu": 1},
+                   "d2h_bytes_per_step": d2h_bytes(pr, False), "contexts_per_gpu": 2},
            "stage_ms": stage, "roofline_hbm": {"kernel": "k_rs_pass2 (read k-mer LSD pass)", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                                "peak_source": peak_src, "note": f"32 B x {n_rk} records per pass / (sort stage incl. histogram / {passes} passes)"},
            "counts": {k: tm[k] for k in ("n_sorted_kmers", "n_raw_seeds", "n_seeds", "n_pairs", "n_sw_tier8", "n_sw_tier16", "n_sw_tier32", "n_sw_fast", "n_traceback_dp")}}

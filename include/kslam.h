@@ -139,6 +139,37 @@ int kslam_pair_batch(kslam_ctx *ctx, int fetch_results, kslam_pairs *out /* may 
  * of one batch always run under the kernels of the other (bench.py's e2e leg does exactly that). */
 int kslam_fetch_pairs(kslam_ctx *ctx, kslam_pairs *out);
 
+/* ---- compact results for runs WITHOUT --sam-file -------------------------------------------------------
+ * The host stages of an XML-only run (insert-size screen, score screens, pseudo-assembly, per-read LCA and genes; SLAM.h:215-249)
+ * read per pair record only: the read pair it belongs to, entry, reference span, insert size, score and which mates it has.
+ * kslam_fetch_pairs_compact ships exactly that — 24 bytes per pair instead of 32 + the 48-byte alignment records — after
+ * kslam_pair_batch(fetch_results = 0). The one place the mates themselves are looked at is the insert-size screen, which
+ * splits a pair beyond the batch's limit into its two single-ended records (PairedOverlap.h:396-436): the call computes the
+ * limit on the host (getMaxAllowedInsertSize, PairedOverlap.h:314-360, from the insert sizes it just received), then fetches
+ * the mates of the pairs beyond it, in pair order. kslam_batch_outputs_compact continues from there: same XML / _PerRead /
+ * _abbreviated as kslam_batch_outputs(want_sam = 0) on the full records. */
+typedef struct {
+  uint32_t pair_id;                /* index of the read pair (R1's read index) */
+  uint32_t entry; int32_t ref_start, ref_end; uint32_t insert_size;
+  uint32_t score_flags;            /* bits 0-29 combinedScore, bit 30 hasR1, bit 31 hasR2 */
+} kslam_pair_compact;
+typedef struct {
+  uint32_t pair_index;             /* index into kslam_pairs_compact.pairs */
+  uint32_t score1; int32_t ref_begin1, ref_end1;   /* the R1 alignment: sw_score, ref_begin, ref_end */
+  uint32_t score2; int32_t ref_begin2, ref_end2;   /* the R2 alignment */
+  uint32_t pad;
+} kslam_far_mates;
+typedef struct {
+  uint64_t n_pairs; const kslam_pair_compact *pairs;       /* getPairedOverlaps order; host, pinned, ctx-owned */
+  uint32_t insert_size_limit;                              /* getMaxAllowedInsertSize of this batch */
+  uint64_t n_far; const kslam_far_mates *far;              /* mates of the pairs with insert_size > insert_size_limit, ascending pair_index */
+} kslam_pairs_compact;
+int kslam_fetch_pairs_compact(kslam_ctx *ctx, uint32_t host_threads /* 0 = all cores */, kslam_pairs_compact *out);
+uint32_t kslam_insert_size_limit_compact(const kslam_pair_compact *pairs, uint64_t n, uint32_t host_threads);
+/* The far-mates table for a limit given by the caller: a batch sharded over several contexts has ONE limit (a statistic of the
+ * whole batch, PairedOverlap.h:314-360), computed from the merged compact records. */
+int kslam_fetch_far_mates(kslam_ctx *ctx, uint32_t insert_size_limit, uint64_t *n_far, const kslam_far_mates **far);
+
 /* The body of the reference's batch loop in one call (SLAM.h:209-214: alignToDatabase, score screen, getPairedOverlaps):
  * same results as kslam_align_batch + kslam_pair_batch, but the unsorted alignment vector — which the loop discards
  * once it is sorted — is never copied to the host. */
@@ -308,6 +339,10 @@ int kslam_batch_outputs(const kslam_sam_params *params, const kslam_sam_db *db, 
 int kslam_batch_outputs_single(const kslam_sam_params *params, const kslam_sam_db *db, const kslam_read_batch *reads,
                                const kslam_alignments *alignments, uint32_t score_threshold, int want_sam, char **sam_text,
                                uint64_t *sam_len, const kslam_taxdb *taxdb, kslam_taxa *taxa);
+/* kslam_batch_outputs(want_sam = 0) on the compact records of kslam_fetch_pairs_compact */
+int kslam_batch_outputs_compact(const kslam_sam_params *params, const kslam_sam_db *db, const kslam_read_batch *reads,
+                                const kslam_pairs_compact *pairs, uint32_t *max_insert_size /* may be NULL */,
+                                const kslam_taxdb *taxdb, kslam_taxa *taxa);
 int kslam_taxa_results(kslam_taxa *taxa, const kslam_taxdb *taxdb, uint32_t num_reads, char **per_read, uint64_t *per_read_len,
                        char **xml, uint64_t *xml_len, char **abbreviated, uint64_t *abbreviated_len);
 

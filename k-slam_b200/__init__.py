@@ -37,6 +37,9 @@ OVERLAP_DT = np.dtype([("read", "<u4"), ("entry", "<u4"), ("rel", "<i4"), ("rev_
                        ("sw_score", "<u4"), ("cigar_off", "<u4"), ("cigar_len", "<u4"), ("flags", "<u4")])
 PAIR_DT = np.dtype([("combined_score", "<u4"), ("entry", "<u4"), ("ref_start", "<i4"), ("ref_end", "<i4"),
                     ("insert_size", "<u4"), ("r1_idx", "<i4"), ("r2_idx", "<i4"), ("pad", "<u4")])
+PAIR_COMPACT_DT = np.dtype([("pair_id", "<u4"), ("entry", "<u4"), ("ref_start", "<i4"), ("ref_end", "<i4"), ("insert_size", "<u4"), ("score_flags", "<u4")])
+FAR_MATES_DT = np.dtype([("pair_index", "<u4"), ("score1", "<u4"), ("ref_begin1", "<i4"), ("ref_end1", "<i4"),
+                         ("score2", "<u4"), ("ref_begin2", "<i4"), ("ref_end2", "<i4"), ("pad", "<u4")])
 GENE_DT = np.dtype([("cds_start", "<u4"), ("cds_stop", "<u4"), ("gene_id", "<u4"), ("complement", "<u4"), ("str_offs", "<u8", (6,))])
 GENE_STRINGS = ("gene_name", "locus_tag", "protein_id", "product", "reference_sequence")
 FLAG_UNDEFINED = 1
@@ -62,6 +65,10 @@ class _Alignments(C.Structure):
 class _Pairs(C.Structure):
     _fields_ = [("n_sorted", C.c_uint64), ("sorted_overlaps", C.c_void_p), ("n_cigar_words", C.c_uint64),
                 ("cigar_pool", C.c_void_p), ("n_pairs", C.c_uint64), ("pairs", C.c_void_p)]
+
+
+class _PairsCompact(C.Structure):
+    _fields_ = [("n_pairs", C.c_uint64), ("pairs", C.c_void_p), ("insert_size_limit", C.c_uint32), ("n_far", C.c_uint64), ("far", C.c_void_p)]
 
 
 class Timings(C.Structure):
@@ -154,6 +161,10 @@ def lib():
     L.kslam_measure_int_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.kslam_set_prefilter.argtypes = [vp, i32]
     L.kslam_set_report_cigar.argtypes = [vp, i32]
+    L.kslam_fetch_pairs_compact.argtypes = [vp, C.c_uint32, C.POINTER(_PairsCompact)]
+    L.kslam_insert_size_limit_compact.argtypes = [vp, u64, C.c_uint32]
+    L.kslam_insert_size_limit_compact.restype = C.c_uint32
+    L.kslam_batch_outputs_compact.argtypes = [C.POINTER(SamParams), C.POINTER(_SamDb), C.POINTER(_ReadBatch), C.POINTER(_PairsCompact), C.POINTER(C.c_uint32), vp, vp]
     L.kslam_comm_unique_id.argtypes = [vp]
     L.kslam_comm_init_rank.argtypes = [vp, C.c_uint32, C.c_uint32, vp, C.POINTER(vp)]
     L.kslam_comm_init_all.argtypes = [C.c_uint32, C.POINTER(vp), C.POINTER(vp)]
@@ -399,6 +410,14 @@ class Aligner:
         if not fetch:
             return int(out.n_pairs)
         return self._pairs(out, copy)
+
+    def fetch_pairs_compact(self, copy=True, threads=0):
+        """After pair_batch(fetch=False): -> (compact pair records, insert-size limit of the batch, mates of the pairs beyond it)
+        (kslam_fetch_pairs_compact: 24 B per pair instead of the pair + alignment records; runs without --sam-file)."""
+        out = _PairsCompact()
+        self._check(self.L.kslam_fetch_pairs_compact(self.h, threads, C.byref(out)), "kslam_fetch_pairs_compact")
+        f = (lambda a: a.copy()) if copy else (lambda a: a)
+        return f(_view(out.pairs, out.n_pairs, PAIR_COMPACT_DT)), int(out.insert_size_limit), f(_view(out.far, out.n_far, FAR_MATES_DT))
 
     def fetch_pairs(self, copy=True) -> "Pairs":
         """D2H of the last pair_batch(fetch=False)."""
@@ -668,6 +687,20 @@ class SamWriter:
             return b""
         return self._take(ptr, ln)
 
+    def batch_compact(self, read_offs, ids, id_offs, compact, limit, far, taxdb=None, taxa=None):
+        """kslam_batch_outputs_compact: the host stages of a run without --sam-file on compact pair records. -> insert-size limit"""
+        ro, i, io = _u64(read_offs), _u8(ids), _u64(id_offs)
+        n = len(ro) - 1
+        reads = _ReadBatch(n, n // 2, None, ro.ctypes.data, None, None, i.ctypes.data, io.ctypes.data)
+        cp = np.ascontiguousarray(compact, dtype=PAIR_COMPACT_DT); fm = np.ascontiguousarray(far, dtype=FAR_MATES_DT)
+        p = _PairsCompact(len(cp), cp.ctypes.data if len(cp) else None, int(limit), len(fm), fm.ctypes.data if len(fm) else None)
+        mi = C.c_uint32()
+        rc = self.L.kslam_batch_outputs_compact(C.byref(self.prm), C.byref(self.db), C.byref(reads), C.byref(p), C.byref(mi),
+                                                taxdb.h if taxdb is not None else None, taxa.h if taxa is not None else None)
+        if rc != 0:
+            raise KslamError(f"kslam_batch_outputs_compact failed ({rc})")
+        return mi.value
+
     def batch(self, read_bases, read_offs, quals, qual_offs, ids, id_offs, sorted_overlaps, cigar_pool, pairs, out_file=None,
               want_sam=True, taxdb=None, taxa=None):
         """-> (SAM text of the batch, max allowed insert size); with out_file the text is written to it straight from the
@@ -698,6 +731,26 @@ class SamWriter:
                 self.L.kslam_sam_free(ptr)
             return ln.value, mi.value
         return self._take(ptr, ln), mi.value
+
+
+def compact_pairs_host(sorted_overlaps, pairs, midpoint):
+    """What kslam_fetch_pairs_compact ships, built on the host from full records (tests; a caller that already has them)."""
+    pr = np.ascontiguousarray(pairs, dtype=PAIR_DT); ov = np.ascontiguousarray(sorted_overlaps, dtype=OVERLAP_DT)
+    out = np.zeros(len(pr), dtype=PAIR_COMPACT_DT)
+    has1, has2 = pr["r1_idx"] >= 0, pr["r2_idx"] >= 0
+    rd = np.where(has1, ov["read"][np.maximum(pr["r1_idx"], 0)], ov["read"][np.maximum(pr["r2_idx"], 0)] - np.uint32(midpoint)) if len(pr) else np.zeros(0, np.uint32)
+    out["pair_id"] = rd
+    for f in ("entry", "ref_start", "ref_end", "insert_size"):
+        out[f] = pr[f]
+    out["score_flags"] = (pr["combined_score"] & np.uint32(0x3FFFFFFF)) | (has1.astype(np.uint32) << np.uint32(30)) | (has2.astype(np.uint32) << np.uint32(31))
+    limit = int(lib().kslam_insert_size_limit_compact(out.ctypes.data, len(out), 0)) if len(out) else 0xFFFFFFFF
+    sel = np.flatnonzero(pr["insert_size"] > np.uint32(limit))
+    far = np.zeros(len(sel), dtype=FAR_MATES_DT)
+    far["pair_index"] = sel
+    a, b = ov[pr["r1_idx"][sel]], ov[pr["r2_idx"][sel]]
+    far["score1"], far["ref_begin1"], far["ref_end1"] = a["sw_score"], a["ref_begin"], a["ref_end"]
+    far["score2"], far["ref_begin2"], far["ref_end2"] = b["sw_score"], b["ref_begin"], b["ref_end"]
+    return out, limit, far
 
 
 def _take_text(L, ptr, n):

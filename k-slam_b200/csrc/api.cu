@@ -104,9 +104,9 @@ void kslam_destroy(kslam_ctx *c) {
   DevBuf *bufs[] = {&c->g_keys, &c->g_vals, &c->recA, &c->recB, &c->sort_hist, &c->scan_tmp, &c->counters,
                     &c->raw_seeds, &c->seedA, &c->seedB, &c->seed_keep, &c->seeds, &c->ov, &c->cig, &c->cig_dense, &c->pair_keys,
                     &c->pair_keys2, &c->ov_sorted, &c->cig_sorted, &c->pair_cnt, &c->pairs, &c->bitmap, &c->d_bounds,
-                    &c->part_send, &c->part_recv, &c->part_tmp, &c->part_m, &c->part_msend, &c->part_mrecv};
+                    &c->part_send, &c->part_recv, &c->part_tmp, &c->part_m, &c->part_msend, &c->part_mrecv, &c->pairs_compact, &c->far_mates};
   for (DevBuf *b : bufs) b->release();
-  HostBuf *hb[] = {&c->h_stage, &c->h_counters, &c->h_ov, &c->h_cig, &c->h_ov_sorted, &c->h_cig_sorted, &c->h_pairs};
+  HostBuf *hb[] = {&c->h_stage, &c->h_counters, &c->h_ov, &c->h_cig, &c->h_ov_sorted, &c->h_cig_sorted, &c->h_pairs, &c->h_pairs_compact, &c->h_far_mates};
   for (HostBuf *b : hb) b->release();
   sw_workspace_free(c);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -387,6 +387,42 @@ int kslam_fetch_pairs(kslam_ctx *c, kslam_pairs *out) {
   API_BEGIN(c)
   if (!c->paired) return fail(c, KSLAM_ERR_STATE, "kslam_pair_batch first");
   fetch_pairs(c, out);
+  return KSLAM_OK;
+  API_END(c)
+}
+
+int kslam_fetch_pairs_compact(kslam_ctx *c, uint32_t host_threads, kslam_pairs_compact *out) {
+  API_BEGIN(c)
+  if (!c->paired) return fail(c, KSLAM_ERR_STATE, "kslam_pair_batch first");
+  if (!out) return fail(c, KSLAM_ERR_ARG, "null output");
+  const uint64_t n = c->n_pairs;
+  if (n >> 32) return fail(c, KSLAM_ERR_ARG, "more than 2^32 pair records in one batch");
+  c->pairs_compact.reserve((size_t)n * sizeof(kslam_pair_compact) + 64);
+  c->h_pairs_compact.reserve((size_t)n * sizeof(kslam_pair_compact) + 64);
+  pairs_compact_device(c, c->pairs_compact.as<kslam_pair_compact>());
+  if (n) CUDA_TRY(cudaMemcpyAsync(c->h_pairs_compact.p, c->pairs_compact.p, (size_t)n * sizeof(kslam_pair_compact), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  out->n_pairs = n; out->pairs = c->h_pairs_compact.as<kslam_pair_compact>();
+  // the batch's insert-size limit from the records that just arrived (host), then the mates of the pairs beyond it
+  out->insert_size_limit = kslam_insert_size_limit_compact(out->pairs, n, host_threads);
+  const uint64_t n_far = far_mates_device(c, out->insert_size_limit, c->far_mates);
+  c->h_far_mates.reserve((size_t)n_far * sizeof(kslam_far_mates) + 64);
+  if (n_far) CUDA_TRY(cudaMemcpyAsync(c->h_far_mates.p, c->far_mates.p, (size_t)n_far * sizeof(kslam_far_mates), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  out->n_far = n_far; out->far = c->h_far_mates.as<kslam_far_mates>();
+  return KSLAM_OK;
+  API_END(c)
+}
+
+int kslam_fetch_far_mates(kslam_ctx *c, uint32_t insert_size_limit, uint64_t *n_far, const kslam_far_mates **far) {
+  API_BEGIN(c)
+  if (!c->paired) return fail(c, KSLAM_ERR_STATE, "kslam_pair_batch first");
+  if (!n_far || !far) return fail(c, KSLAM_ERR_ARG, "null output");
+  const uint64_t n = far_mates_device(c, insert_size_limit, c->far_mates);
+  c->h_far_mates.reserve((size_t)n * sizeof(kslam_far_mates) + 64);
+  if (n) CUDA_TRY(cudaMemcpyAsync(c->h_far_mates.p, c->far_mates.p, (size_t)n * sizeof(kslam_far_mates), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  *n_far = n; *far = c->h_far_mates.as<kslam_far_mates>();
   return KSLAM_OK;
   API_END(c)
 }

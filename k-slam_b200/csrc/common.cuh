@@ -127,8 +127,8 @@ struct kslam_ctx {
   SwWorkspace *sw = nullptr;
   HostBuf h_ov, h_cig;
 
-  DevBuf pair_keys, pair_keys2, ov_sorted, cig_sorted, pair_cnt, pairs;
-  HostBuf h_ov_sorted, h_cig_sorted, h_pairs;
+  DevBuf pair_keys, pair_keys2, ov_sorted, cig_sorted, pair_cnt, pairs, pairs_compact, far_mates;
+  HostBuf h_ov_sorted, h_cig_sorted, h_pairs, h_pairs_compact, h_far_mates;
   uint64_t n_sorted = 0, n_pairs = 0;
 
   // k-mer-range partitioned database (dist.cu)
@@ -182,6 +182,8 @@ double sw_measure_int_peak(kslam_ctx *c);
 void part_matches_to_seeds(kslam_ctx *c, uint64_t n_matches, uint32_t read_id_base);
 // pair.cu
 void pair_overlaps(kslam_ctx *c);
+void pairs_compact_device(kslam_ctx *c, kslam_pair_compact *out_dev);
+uint64_t far_mates_device(kslam_ctx *c, uint32_t limit, DevBuf &out_buf);
 
 // api.cu: error plumbing of the C ABI (no exception crosses the boundary)
 int api_fail(kslam_ctx *c, int code, const std::string &msg);

@@ -39,6 +39,9 @@ template <class F> void parallel_threads(uint32_t threads, F f) {
 struct Ctx {
   const kslam_sam_params *prm; const kslam_sam_db *db; const kslam_read_batch *reads; const kslam_pairs *in;
   bool paired;                     // Globals.h pairedData
+  // compact input (kslam_pairs_compact, runs without --sam-file): `in` is null, POv::r1 / r2 hold the PAIR index, and the
+  // mates of the pairs beyond the insert-size limit come from `far` (ascending pair_index)
+  const kslam_far_mates *far = nullptr; uint64_t n_far = 0;
   std::string read_id(uint32_t i) const { return std::string(reads->ids + reads->id_offs[i], reads->ids + reads->id_offs[i + 1]); }
   std::string locus(uint32_t e) const { return std::string(db->locus_tags + db->locus_offs[e], db->locus_tags + db->locus_offs[e + 1]); }
 };

@@ -240,3 +240,76 @@ void pair_overlaps(kslam_ctx *c) {
   }
   CUDA_TRY(cudaGetLastError());
 }
+
+// ---- compact results for runs without --sam-file ----------------------------------------------------------
+// After pairing, a run that writes XML only needs per pair: which read pair it belongs to, entry, reference span, insert
+// size, score and which mates it has (PairedOverlap.h:32-58; MetagenomicResults.h:88-111 reads nothing else) — 24 bytes
+// instead of the 32-byte pair record plus the 48-byte alignment records it indexes. The one place the host stages look
+// at the mates of a pair is screenPairedAlignmentsByInsertSize(replace = true) (PairedOverlap.h:396-436), which splits a
+// pair whose insert size exceeds the batch's limit into its two single-ended records: those few pairs' mates are fetched
+// separately once the limit is known (k_far_flags / k_far_emit keep them in pair order).
+__global__ void __launch_bounds__(256)
+k_pairs_compact(const kslam_pair *__restrict__ pairs, const kslam_overlap *__restrict__ ov, uint64_t n, uint32_t mid,
+                kslam_pair_compact *__restrict__ out) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const kslam_pair p = pairs[i];
+    kslam_pair_compact r;
+    r.pair_id = p.r1_idx >= 0 ? ov[p.r1_idx].read : ov[p.r2_idx].read - mid;     // getPerReadOverlaps' thisReadPos, PairedOverlap.h:446-450
+    r.entry = p.entry; r.ref_start = p.ref_start; r.ref_end = p.ref_end; r.insert_size = p.insert_size;
+    r.score_flags = (p.combined_score & 0x3FFFFFFFu) | (p.r1_idx >= 0 ? 0x40000000u : 0u) | (p.r2_idx >= 0 ? 0x80000000u : 0u);
+    out[i] = r;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_far_flags(const kslam_pair *__restrict__ pairs, uint32_t n, uint32_t limit, uint32_t *__restrict__ flags) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flags[i] = pairs[i].insert_size > limit ? 1u : 0u;       // (a single-ended record has insert size 0)
+}
+
+__global__ void __launch_bounds__(256)
+k_far_emit(const kslam_pair *__restrict__ pairs, const kslam_overlap *__restrict__ ov, uint32_t n, const uint32_t *__restrict__ flags,
+           const uint32_t *__restrict__ pos, kslam_far_mates *__restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flags[i]) return;
+  const kslam_pair p = pairs[i];
+  kslam_far_mates f;
+  f.pair_index = i; f.pad = 0;
+  const kslam_overlap a = ov[p.r1_idx], b = ov[p.r2_idx];
+  f.score1 = a.sw_score; f.ref_begin1 = a.ref_begin; f.ref_end1 = a.ref_end;
+  f.score2 = b.sw_score; f.ref_begin2 = b.ref_begin; f.ref_end2 = b.ref_end;
+  out[pos[i]] = f;
+}
+
+void pairs_compact_device(kslam_ctx *c, kslam_pair_compact *out_dev) {
+  if (!c->n_pairs) return;
+  uint64_t blocks = (c->n_pairs + 255) / 256, maxb = (uint64_t)c->num_sms * 16;
+  if (blocks > maxb) blocks = maxb;
+  k_pairs_compact<<<(unsigned)blocks, 256, 0, c->stream>>>(c->pairs.as<kslam_pair>(), c->ov_sorted.as<kslam_overlap>(), c->n_pairs,
+                                                           (uint32_t)(c->reads.n / 2), out_dev);
+  c->launches++;
+  CUDA_TRY(cudaGetLastError());
+}
+
+// the mates of every pair whose insert size exceeds `limit`, in pair order, into out_buf (device); returns their number
+uint64_t far_mates_device(kslam_ctx *c, uint32_t limit, DevBuf &out_buf) {
+  const uint32_t n = (uint32_t)c->n_pairs;
+  if (!n) return 0;
+  cudaStream_t st = c->stream;
+  c->pair_cnt.reserve((size_t)n * 8 + 64);                  // free again after pairing: flags | positions
+  uint32_t *flags = c->pair_cnt.as<uint32_t>(), *pos = flags + n;
+  k_far_flags<<<(n + 255) / 256, 256, 0, st>>>(c->pairs.as<kslam_pair>(), n, limit, flags);
+  unsigned long long *d_tot = c->counters.as<unsigned long long>() + 30, *h_tot = c->h_counters.as<unsigned long long>() + 30;
+  exclusive_scan_u32(c, flags, pos, n, (uint64_t *)d_tot);
+  read_small(c, h_tot, d_tot, 8);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  const uint64_t n_far = h_tot[0];
+  if (n_far) {
+    out_buf.reserve((size_t)n_far * sizeof(kslam_far_mates) + 64);
+    k_far_emit<<<(n + 255) / 256, 256, 0, st>>>(c->pairs.as<kslam_pair>(), c->ov_sorted.as<kslam_overlap>(), n, flags, pos,
+                                                 out_buf.as<kslam_far_mates>());
+    CUDA_TRY(cudaGetLastError());
+  }
+  c->launches += 2;
+  return n_far;
+}

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "host_stages.h"
 #include <algorithm>
+#include <stdexcept>
 #include <atomic>
 #include <cmath>
 #include <climits>
@@ -156,8 +157,95 @@ uint32_t insert_size_limit_from_runs(const InsertRuns &runs) {
 
 uint32_t max_allowed_insert_size(const std::vector<ReadPair> &reads) { return insert_size_limit_from_runs(insert_size_runs(reads)); }
 
-void screen_by_insert_size(std::vector<ReadPair> &reads, const kslam_overlap *ov, const uint32_t insertSize, uint32_t threads) {   // :396-436, replace = true
+// the same statistic straight from compact pair records (kslam_pairs_compact): per-thread counters over value ranges
+InsertRuns insert_size_runs_compact(const kslam_pair_compact *p, uint64_t n, uint32_t threads) {
+  InsertRuns runs;
+  constexpr int64_t SPAN = 1 << 22;
+  if (threads < 1) threads = 1;
+  std::vector<std::vector<uint64_t>> cnt(threads);
+  std::vector<std::vector<int32_t>> rest(threads);          // values outside [0, SPAN)
+  parallel_ranges(threads, n, [&](uint32_t t, size_t lo, size_t hi) {
+    cnt[t].assign(SPAN, 0);
+    for (size_t i = lo; i < hi; i++) {
+      const int32_t v = (int32_t)p[i].insert_size;
+      if (v == 0) continue;
+      if (v > 0 && v < SPAN) cnt[t][v]++; else rest[t].push_back(v);
+    }
+  });
+  std::vector<int32_t> other;
+  for (auto &r : rest) other.insert(other.end(), r.begin(), r.end());
+  std::sort(other.begin(), other.end());
+  size_t k = 0;
+  auto flush_other = [&](int64_t below) {                   // runs of the sorted out-of-range values smaller than `below`
+    while (k < other.size() && other[k] < below) { size_t j = k; while (j < other.size() && other[j] == other[k]) j++; runs.push(other[k], j - k); k = j; }
+  };
+  flush_other(0);
+  for (int64_t v = 1; v < SPAN; v++) {
+    uint64_t c = 0;
+    for (uint32_t t = 0; t < threads; t++) if (!cnt[t].empty()) c += cnt[t][v];
+    runs.push((int32_t)v, c);
+  }
+  flush_other(INT64_MAX);
+  return runs;
+}
+
+std::vector<ReadPair> per_read_compact(const kslam_pairs_compact *in, uint32_t midpoint, uint32_t threads) {
+  const uint64_t n = in->n_pairs;
+  const kslam_pair_compact *rec = in->pairs;
+  auto range = [&](uint64_t lo, uint64_t hi, std::vector<ReadPair> &out) {
+    ReadPair cur;
+    uint32_t readPos = 0;
+    for (uint64_t i = lo; i < hi; i++) {
+      const kslam_pair_compact &k = rec[i];
+      POv p;
+      p.combinedScore = k.score_flags & 0x3FFFFFFFu; p.entry = k.entry; p.refStart = k.ref_start; p.refEnd = k.ref_end;
+      p.insertSize = k.insert_size; p.hasR1 = (k.score_flags >> 30) & 1u; p.hasR2 = (k.score_flags >> 31) & 1u;
+      p.r1 = p.hasR1 ? (int32_t)i : -1; p.r2 = p.hasR2 ? (int32_t)i : -1;           // the PAIR index (Ctx::far is keyed by it)
+      if (k.pair_id != readPos) {
+        if (cur.pairs.size()) { out.push_back(std::move(cur)); cur.pairs.clear(); }
+        readPos = k.pair_id;
+      }
+      cur.pairs.push_back(p);
+      cur.r1Pos = k.pair_id; cur.r2Pos = k.pair_id + midpoint;
+    }
+    if (cur.pairs.size()) out.push_back(cur);
+  };
+  std::vector<ReadPair> out;
+  if (threads <= 1 || n < par_min() || n < threads) { range(0, n, out); return out; }
+  std::vector<uint64_t> cut(threads + 1, n);
+  cut[0] = 0;
+  for (uint32_t t = 1; t < threads; t++) {
+    uint64_t b = std::max(cut[t - 1], n * t / threads);
+    while (b > 0 && b < n && rec[b].pair_id == rec[b - 1].pair_id) b++;
+    cut[t] = b;
+  }
+  std::vector<std::vector<ReadPair>> parts(threads);
+  parallel_threads(threads, [&](uint32_t t) { range(cut[t], cut[t + 1], parts[t]); });
+  size_t total = 0;
+  for (auto &pt : parts) total += pt.size();
+  out.reserve(total);
+  for (auto &pt : parts) for (auto &r : pt) out.push_back(std::move(r));
+  return out;
+}
+
+// score and reference span of the two alignments of a pair record: from the alignment vector, or (compact input) from the
+// far-mates table, which holds every pair the insert-size screen can ask about
+struct MatePair { uint32_t s1; int32_t b1, e1; uint32_t s2; int32_t b2, e2; };
+inline MatePair mates_of(const Ctx &c, const POv &p) {
+  if (c.in) {
+    const kslam_overlap &o1 = c.in->sorted_overlaps[p.r1], &o2 = c.in->sorted_overlaps[p.r2];
+    return MatePair{o1.sw_score, o1.ref_begin, o1.ref_end, o2.sw_score, o2.ref_begin, o2.ref_end};
+  }
+  const kslam_far_mates *f = std::lower_bound(c.far, c.far + c.n_far, (uint32_t)p.r1,
+                                              [](const kslam_far_mates &x, uint32_t idx) { return x.pair_index < idx; });
+  if (f == c.far + c.n_far || f->pair_index != (uint32_t)p.r1) throw std::runtime_error("pair beyond the insert-size limit without its mates");
+  return MatePair{f->score1, f->ref_begin1, f->ref_end1, f->score2, f->ref_begin2, f->ref_end2};
+}
+
+void screen_by_insert_size(std::vector<ReadPair> &reads, const Ctx &ctx, const uint32_t insertSize, uint32_t threads) {   // :396-436, replace = true
+  std::atomic<bool> failed{false};
   parallel_ranges(threads, reads.size(), [&](uint32_t, size_t lo, size_t hi) {
+  try {
   for (size_t ri = lo; ri < hi; ri++) {
     ReadPair &read = reads[ri];
     std::sort(read.pairs.begin(), read.pairs.end(), [](const POv &i, const POv &j) { return i.insertSize < j.insertSize; });
@@ -166,19 +254,20 @@ void screen_by_insert_size(std::vector<ReadPair> &reads, const kslam_overlap *ov
     read.pairs.reserve(read.pairs.size() + std::distance(cutoff, read.pairs.end()));
     const size_t oldEnd = read.pairs.size();
     for (size_t cur = (size_t)cutoffPos; cur < oldEnd; cur++) {
+      const MatePair m = mates_of(ctx, read.pairs[cur]);
       POv single;                                            // the R1 half becomes a pair record of its own
-      const kslam_overlap &o1 = ov[read.pairs[cur].r1];
-      single.combinedScore = (uint16_t)o1.sw_score; single.entry = read.pairs[cur].entry;
-      single.refStart = o1.ref_begin; single.refEnd = o1.ref_end; single.insertSize = 0;
+      single.combinedScore = (uint16_t)m.s1; single.entry = read.pairs[cur].entry;
+      single.refStart = m.b1; single.refEnd = m.e1; single.insertSize = 0;
       single.hasR1 = true; single.hasR2 = false; single.r1 = read.pairs[cur].r1; single.r2 = -1;
       read.pairs.push_back(single);
       POv &c = read.pairs[cur];                              // ... and the record itself keeps R2 only
-      const kslam_overlap &o2 = ov[c.r2];
-      c.combinedScore = (uint16_t)o2.sw_score; c.hasR1 = false; c.insertSize = 0; c.r1 = -1;
-      c.refStart = o2.ref_begin; c.refEnd = o2.ref_end;
+      c.combinedScore = (uint16_t)m.s2; c.hasR1 = false; c.insertSize = 0; c.r1 = -1;
+      c.refStart = m.b2; c.refEnd = m.e2;
     }
   }
+  } catch (const std::exception &) { failed = true; }
   });
+  if (failed) throw std::runtime_error("insert-size screen: mates missing");
 }
 
 void screen_by_score(std::vector<ReadPair> &reads, double fraction, uint32_t threads) {   // PairedOverlap.h:361-390
@@ -603,7 +692,7 @@ static int sam_finish(Ctx &c, std::vector<ReadPair> &rp, bool insert_screen, boo
   if (insert_screen) {
     const uint32_t maxInsert = max_allowed_insert_size(rp);
     if (max_insert_size) *max_insert_size = maxInsert;
-    screen_by_insert_size(rp, c.in->sorted_overlaps, maxInsert, threads);
+    screen_by_insert_size(rp, c, maxInsert, threads);
   } else if (max_insert_size) *max_insert_size = UINT32_MAX;
   double t2 = now();
   screen_by_score(rp, prm->score_fraction_threshold, threads);
@@ -715,6 +804,38 @@ int kslam_batch_outputs(const kslam_sam_params *prm, const kslam_sam_db *db, con
     if (trace) fprintf(stderr, "[kslam_sam] grouping %.1f ms, stages %.1f ms, release %.1f ms\n", (t1 - t0) * 1e3, (t2 - t1) * 1e3, (now() - t2) * 1e3);
     return rc;
   } catch (const std::exception &) { return KSLAM_ERR_NOMEM; }
+}
+
+uint32_t kslam_insert_size_limit_compact(const kslam_pair_compact *pairs, uint64_t n, uint32_t host_threads) {
+  if (!pairs || !n) return UINT32_MAX;
+  uint32_t threads = host_threads ? host_threads : std::max(1u, std::thread::hardware_concurrency());
+  if (threads > 16) threads = 16;                           // 32 MB of counters per thread
+  if (n < (1u << 20)) threads = 1;
+  try { return insert_size_limit_from_runs(insert_size_runs_compact(pairs, n, threads)); } catch (const std::exception &) { return UINT32_MAX; }
+}
+
+int kslam_batch_outputs_compact(const kslam_sam_params *prm, const kslam_sam_db *db, const kslam_read_batch *reads, const kslam_pairs_compact *in,
+                                uint32_t *max_insert_size, const kslam_taxdb *taxdb, kslam_taxa *taxa) {
+  if (!prm || !db || !reads || !in || ((taxdb != nullptr) != (taxa != nullptr))) return KSLAM_ERR_ARG;
+  if ((db->genes != nullptr) != (db->gene_offs != nullptr) || (db->genes && !db->gene_strings)) return KSLAM_ERR_ARG;
+  if ((in->n_pairs && !in->pairs) || (in->n_far && !in->far)) return KSLAM_ERR_ARG;
+  const uint32_t mid = (uint32_t)(reads->n_reads / 2);
+  for (uint64_t i = 0; i < in->n_pairs; i++)
+    if (in->pairs[i].entry >= db->n_entries || in->pairs[i].pair_id >= mid) return KSLAM_ERR_ARG;
+  try {
+    Ctx c{prm, db, reads, nullptr, true};
+    c.far = in->far; c.n_far = in->n_far;
+    const uint32_t threads = std::min(prm->threads ? (uint32_t)prm->threads : std::max(1u, std::thread::hardware_concurrency()), 64u);
+    auto rp = per_read_compact(in, mid, threads);
+    uint32_t limit = 0;
+    int rc = sam_finish(c, rp, true, false, nullptr, nullptr, &limit, taxdb, taxa);
+    if (rc == KSLAM_OK && limit != in->insert_size_limit) rc = KSLAM_ERR_STATE;   // the far-mates table was fetched for another limit
+    if (max_insert_size) *max_insert_size = limit;
+    parallel_ranges(threads, rp.size(), [&](uint32_t, size_t lo, size_t hi) {
+      for (size_t i = lo; i < hi; i++) std::vector<POv>().swap(rp[i].pairs);
+    });
+    return rc;
+  } catch (const std::exception &) { return KSLAM_ERR_STATE; }
 }
 
 // Single-end reads (SLAM.h:223-228): alignToDatabase's vector, score screen (Overlap.h:329-341), getPerReadOverlaps

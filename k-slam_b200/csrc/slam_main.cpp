@@ -179,6 +179,7 @@ template <class T> struct Slot {
 struct Batch {                                             // one batch on its way through the pipeline; n_reads == 0 ends the run
   kslam_read_batch reads{};
   std::vector<kslam_overlap> overlaps; std::vector<uint32_t> cigars; std::vector<kslam_pair> pairs;   // copies: the ctx reuses its buffers
+  std::vector<kslam_pair_compact> compact; std::vector<kslam_far_mates> far; uint32_t limit = 0;       // runs without --sam-file (paired)
   std::string error;
 };
 
@@ -189,105 +190,110 @@ bool write_file(const std::string &path, const char *text, uint64_t len) {
   return fclose(f) == 0 && ok;
 }
 
-// Stage 2 for one batch. One context: the library call as is. Several: the batch is cut into contiguous ranges of read
-// pairs that keep mates together (R1 i and R2 i + mid), every context runs the whole path on its range, and the results are
-// joined in range order with read / overlap / cigar indices rebased — which is the order one context would have produced
-// (same rules as k-slam_b200/shard.py: pairing is per pair, seeds are per (read, genome)).
-void align_batch(const std::vector<kslam_ctx *> &ctxs, const std::vector<kslam_comm *> &comms, bool isPaired, Batch *b) {
+// Stage 2 for one batch. The batch is cut into contiguous ranges of read pairs that keep mates together (R1 i and R2
+// i + mid), one per context (one range = the whole batch with a single context); every context runs the whole path on its
+// range — alignToDatabase over a replicated index, or the collective kslam_comm_align_resident over a k-mer-range
+// partitioned one — and the results are joined in range order with read / overlap / cigar / pair indices rebased, which
+// is the order one context would have produced (pairing is per pair, seeds are per (read, genome); k-slam_b200/shard.py
+// states the same rules). `compact` (paired runs without --sam-file): only the 24-byte pair records and the mates of the
+// pairs beyond the batch's insert-size limit leave the GPUs (kslam_fetch_pairs_compact).
+void align_batch(const std::vector<kslam_ctx *> &ctxs, const std::vector<kslam_comm *> &comms, bool isPaired, bool compact, Batch *b) {
   const kslam_read_batch &r = b->reads;
+  const bool partitioned = !comms.empty();                 // every rank takes part in every batch, even with an empty range
   // (a paired batch with an odd read count — the reference's R1/R2 size check lets n2 = n1 + 1 through, FASTQsequence.h:118-122 —
   // pairs its last read by index modulo the midpoint, which no contiguous split reproduces: such a batch runs on one context)
-  const bool partitioned = !comms.empty();                 // every rank takes part in every batch, even with an empty range
-  const size_t G = (!partitioned && isPaired && (r.n_reads & 1)) ? 1 : ctxs.size();
-  if (partitioned && isPaired && (r.n_reads & 1)) { b->error = "a paired batch with an odd read count cannot be sharded over a partitioned index"; return; }
-  if (G == 1 && !partitioned) {
-    if (isPaired) {
-      kslam_pairs p;
-      if (kslam_align_pair_batch(ctxs[0], r.n_reads, r.bases, r.offs, &p) != KSLAM_OK) { b->error = kslam_last_error(ctxs[0]); return; }
-      b->overlaps.assign(p.sorted_overlaps, p.sorted_overlaps + p.n_sorted);
-      b->cigars.assign(p.cigar_pool, p.cigar_pool + p.n_cigar_words);
-      b->pairs.assign(p.pairs, p.pairs + p.n_pairs);
-    } else {
-      kslam_alignments a;
-      if (kslam_align_batch(ctxs[0], r.n_reads, r.bases, r.offs, &a) != KSLAM_OK) { b->error = kslam_last_error(ctxs[0]); return; }
-      b->overlaps.assign(a.overlaps, a.overlaps + a.n_overlaps);
-      b->cigars.assign(a.cigar_pool, a.cigar_pool + a.n_cigar_words);
-    }
-    return;
-  }
-  struct Shard { uint64_t lo = 0, hi = 0; std::vector<char> bases; std::vector<uint64_t> offs; kslam_pairs p{}; kslam_alignments a{}; std::string error; };
+  const bool odd = isPaired && (r.n_reads & 1);
+  if (partitioned && odd) { b->error = "a paired batch with an odd read count cannot be sharded over a partitioned index"; return; }
+  const size_t G = odd ? 1 : ctxs.size();
+  struct Shard {
+    uint64_t lo = 0, hi = 0; std::vector<char> bases; std::vector<uint64_t> offs;
+    kslam_pairs p{}; kslam_alignments a{}; kslam_pairs_compact c{}; std::string error;
+  };
   std::vector<Shard> shards(G);
   const uint64_t units = isPaired ? r.n_reads / 2 : r.n_reads, mid = r.n_reads / 2;
-  std::vector<std::thread> th;
-  for (size_t g = 0; g < G; g++) {
+  auto run_shard = [&](size_t g) {
     Shard &s = shards[g];
-    s.lo = units * g / G; s.hi = units * (g + 1) / G;
-    if (s.hi == s.lo && !partitioned) continue;
-    th.emplace_back([&, g] {
-      Shard &s = shards[g];
-      const uint64_t cnt = s.hi - s.lo;
-      if (partitioned) {
-        // kslam_comm: upload this rank's range, then the collective alignToDatabase over the k-mer-range partitioned index
-        // (csrc/comm.cu: both all-to-alls are ncclSend / ncclRecv groups issued by the library), then pairing as usual
-        if (isPaired) {
-          const uint64_t a0 = r.offs[s.lo], a1 = r.offs[s.hi], b0 = r.offs[mid + s.lo], b1 = r.offs[mid + s.hi];
-          s.bases.resize((a1 - a0) + (b1 - b0) + 1);
-          memcpy(s.bases.data(), r.bases + a0, a1 - a0);
-          memcpy(s.bases.data() + (a1 - a0), r.bases + b0, b1 - b0);
-          s.offs.assign(2 * cnt + 1, 0);
-          for (uint64_t i = 0; i <= cnt; i++) s.offs[i] = r.offs[s.lo + i] - a0;
-          for (uint64_t i = 1; i <= cnt; i++) s.offs[cnt + i] = (a1 - a0) + (r.offs[mid + s.lo + i] - b0);
-        } else {
-          s.offs.assign(cnt + 1, 0);
-          for (uint64_t i = 0; i <= cnt; i++) s.offs[i] = r.offs[s.lo + i] - r.offs[s.lo];
-        }
-        const char *base_ptr = isPaired ? s.bases.data() : r.bases + r.offs[s.lo];
-        const uint64_t n_here = isPaired ? 2 * cnt : cnt;
-        int rc = kslam_upload_reads(ctxs[g], n_here, base_ptr, s.offs.data());
-        if (rc == KSLAM_OK) rc = kslam_comm_align_resident(comms[g], isPaired ? 0 : 1, isPaired ? nullptr : &s.a);
-        if (rc == KSLAM_OK && isPaired) rc = kslam_pair_batch(ctxs[g], 1, &s.p);
-        if (rc != KSLAM_OK) s.error = kslam_last_error(ctxs[g]);
-        return;
-      }
-      if (isPaired) {                                      // R1 block of the range, then its R2 block, in one array
+    const uint64_t cnt = s.hi - s.lo;
+    const char *base_ptr = r.bases;
+    const uint64_t *offs_ptr = r.offs;
+    uint64_t n_here = r.n_reads;
+    if (G > 1 || partitioned) {
+      if (isPaired) {                                        // R1 block of the range, then its R2 block, in one array
         const uint64_t a0 = r.offs[s.lo], a1 = r.offs[s.hi], b0 = r.offs[mid + s.lo], b1 = r.offs[mid + s.hi];
-        s.bases.resize((a1 - a0) + (b1 - b0));
+        s.bases.resize((a1 - a0) + (b1 - b0) + 1);
         memcpy(s.bases.data(), r.bases + a0, a1 - a0);
         memcpy(s.bases.data() + (a1 - a0), r.bases + b0, b1 - b0);
-        s.offs.resize(2 * cnt + 1);
+        s.offs.assign(2 * cnt + 1, 0);
         for (uint64_t i = 0; i <= cnt; i++) s.offs[i] = r.offs[s.lo + i] - a0;
         for (uint64_t i = 1; i <= cnt; i++) s.offs[cnt + i] = (a1 - a0) + (r.offs[mid + s.lo + i] - b0);
-        if (kslam_align_pair_batch(ctxs[g], 2 * cnt, s.bases.data(), s.offs.data(), &s.p) != KSLAM_OK) s.error = kslam_last_error(ctxs[g]);
-      } else {                                             // a contiguous slice of the batch: only the offsets are rebased
-        s.offs.resize(cnt + 1);
+        base_ptr = s.bases.data(); n_here = 2 * cnt;
+      } else {                                               // a contiguous slice of the batch: only the offsets are rebased
+        s.offs.assign(cnt + 1, 0);
         for (uint64_t i = 0; i <= cnt; i++) s.offs[i] = r.offs[s.lo + i] - r.offs[s.lo];
-        if (kslam_align_batch(ctxs[g], cnt, r.bases + r.offs[s.lo], s.offs.data(), &s.a) != KSLAM_OK) s.error = kslam_last_error(ctxs[g]);
+        base_ptr = r.bases + r.offs[s.lo]; n_here = cnt;
       }
-    });
+      offs_ptr = s.offs.data();
+    }
+    kslam_ctx *ctx = ctxs[g];
+    int rc = kslam_upload_reads(ctx, n_here, base_ptr, offs_ptr);
+    const int fetch_alignments = isPaired ? 0 : 1;
+    if (rc == KSLAM_OK) rc = partitioned ? kslam_comm_align_resident(comms[g], fetch_alignments, isPaired ? nullptr : &s.a)
+                                         : kslam_align_resident(ctx, fetch_alignments, isPaired ? nullptr : &s.a);
+    if (rc == KSLAM_OK && isPaired) rc = kslam_pair_batch(ctx, compact ? 0 : 1, compact ? nullptr : &s.p);
+    if (rc == KSLAM_OK && isPaired && compact) rc = kslam_fetch_pairs_compact(ctx, 0, &s.c);
+    if (rc != KSLAM_OK) s.error = kslam_last_error(ctx);
+  };
+  std::vector<std::thread> th;
+  for (size_t g = 0; g < G; g++) {
+    shards[g].lo = units * g / G; shards[g].hi = units * (g + 1) / G;
+    if (shards[g].hi == shards[g].lo && !partitioned && G > 1) continue;
+    if (G == 1) run_shard(0); else th.emplace_back(run_shard, g);
   }
   for (auto &t : th) t.join();
   for (Shard &s : shards) if (!s.error.empty()) { b->error = s.error; return; }
+  if (compact && isPaired) {
+    // compact records: rebase the read-pair ids; ONE insert-size limit for the batch (getMaxAllowedInsertSize is a statistic
+    // of the whole batch, PairedOverlap.h:314-360), so with several ranges the far-mates tables are fetched again for it
+    std::vector<uint64_t> pair_base(G, 0);
+    for (size_t g = 0; g < G; g++) {
+      const Shard &s = shards[g];
+      pair_base[g] = b->compact.size();
+      b->compact.insert(b->compact.end(), s.c.pairs, s.c.pairs + s.c.n_pairs);
+      for (uint64_t i = pair_base[g]; i < b->compact.size(); i++) b->compact[i].pair_id += (uint32_t)s.lo;
+    }
+    b->limit = G == 1 ? shards[0].c.insert_size_limit : kslam_insert_size_limit_compact(b->compact.data(), b->compact.size(), 0);
+    for (size_t g = 0; g < G; g++) {
+      Shard &s = shards[g];
+      uint64_t n_far = s.c.n_far; const kslam_far_mates *far = s.c.far;
+      if (s.c.insert_size_limit != b->limit && kslam_fetch_far_mates(ctxs[g], b->limit, &n_far, &far) != KSLAM_OK) { b->error = kslam_last_error(ctxs[g]); return; }
+      const uint64_t at = b->far.size();
+      b->far.insert(b->far.end(), far, far + n_far);
+      for (uint64_t i = at; i < b->far.size(); i++) b->far[i].pair_index += (uint32_t)pair_base[g];
+    }
+    return;
+  }
   for (Shard &s : shards) {
-    if (s.hi == s.lo) continue;
     const uint64_t cnt = s.hi - s.lo, ov_base = b->overlaps.size(), cg_base = b->cigars.size();
     const kslam_overlap *ov = isPaired ? s.p.sorted_overlaps : s.a.overlaps;
     const uint64_t n_ov = isPaired ? s.p.n_sorted : s.a.n_overlaps;
     const uint32_t *cg = isPaired ? s.p.cigar_pool : s.a.cigar_pool;
     const uint64_t n_cg = isPaired ? s.p.n_cigar_words : s.a.n_cigar_words;
-    b->overlaps.insert(b->overlaps.end(), ov, ov + n_ov);
-    for (uint64_t i = ov_base; i < b->overlaps.size(); i++) {
-      kslam_overlap &o = b->overlaps[i];
-      o.read = isPaired ? (uint32_t)(o.read < cnt ? s.lo + o.read : mid + s.lo + (o.read - cnt)) : (uint32_t)(o.read + s.lo);
-      if (o.cigar_len) o.cigar_off += (uint32_t)cg_base;
-    }
+    if (n_ov) b->overlaps.insert(b->overlaps.end(), ov, ov + n_ov);
+    if (G > 1 || partitioned)
+      for (uint64_t i = ov_base; i < b->overlaps.size(); i++) {
+        kslam_overlap &o = b->overlaps[i];
+        o.read = isPaired ? (uint32_t)(o.read < cnt ? s.lo + o.read : mid + s.lo + (o.read - cnt)) : (uint32_t)(o.read + s.lo);
+        if (o.cigar_len) o.cigar_off += (uint32_t)cg_base;
+      }
     if (n_cg) b->cigars.insert(b->cigars.end(), cg, cg + n_cg);
     if (isPaired) {
       const uint64_t pr_base = b->pairs.size();
-      b->pairs.insert(b->pairs.end(), s.p.pairs, s.p.pairs + s.p.n_pairs);
-      for (uint64_t i = pr_base; i < b->pairs.size(); i++) {
-        if (b->pairs[i].r1_idx >= 0) b->pairs[i].r1_idx += (int32_t)ov_base;
-        if (b->pairs[i].r2_idx >= 0) b->pairs[i].r2_idx += (int32_t)ov_base;
-      }
+      if (s.p.n_pairs) b->pairs.insert(b->pairs.end(), s.p.pairs, s.p.pairs + s.p.n_pairs);
+      if (ov_base)
+        for (uint64_t i = pr_base; i < b->pairs.size(); i++) {
+          if (b->pairs[i].r1_idx >= 0) b->pairs[i].r1_idx += (int32_t)ov_base;
+          if (b->pairs[i].r2_idx >= 0) b->pairs[i].r2_idx += (int32_t)ov_base;
+        }
     }
   }
 }
@@ -400,7 +406,7 @@ int run_alignment(const Options &o, const std::string &commandLine) {      // me
   std::thread gpu([&] {                                    // stage 2: alignToDatabase + score screen + getPairedOverlaps on the GPU(s)
     for (;;) {
       Batch *b = to_gpu.take();
-      if (b->reads.n_reads && b->error.empty()) align_batch(ctxs, comms, isPaired, b);
+      if (b->reads.n_reads && b->error.empty()) align_batch(ctxs, comms, isPaired, isPaired && !wantSam, b);
       const bool last = b->reads.n_reads == 0 || !b->error.empty();
       to_host.put(b);
       if (last) return;
@@ -421,7 +427,11 @@ int run_alignment(const Options &o, const std::string &commandLine) {      // me
     char *text = nullptr; uint64_t len = 0;
     int rc;
     if (wantSam) log("Writing SAM output");
-    if (isPaired) {
+    if (isPaired && !wantSam) {
+      kslam_pairs_compact pc;
+      pc.n_pairs = b->compact.size(); pc.pairs = b->compact.data(); pc.insert_size_limit = b->limit; pc.n_far = b->far.size(); pc.far = b->far.data();
+      rc = kslam_batch_outputs_compact(&sp, &db, &b->reads, &pc, nullptr, taxdb, taxa);
+    } else if (isPaired) {
       kslam_pairs p;
       p.n_sorted = b->overlaps.size(); p.sorted_overlaps = b->overlaps.data(); p.n_cigar_words = b->cigars.size(); p.cigar_pool = b->cigars.data();
       p.n_pairs = b->pairs.size(); p.pairs = b->pairs.data();

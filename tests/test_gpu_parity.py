@@ -419,6 +419,28 @@ def test_align_pair_batch_equals_two_calls(pkg):
         assert T.cigars_of(g.sorted_overlaps, g.cigar_pool) == T.cigars_of(want.sorted_overlaps, want.cigar_pool)
 
 
+def test_compact_pair_records(pkg):
+    """kslam_fetch_pairs_compact: the 24-byte records, the batch's insert-size limit and the mates of the
+    pairs beyond it equal what the full records give (built on the host), on data with far pairs."""
+    gb, go = pkg.synth.random_genomes(6, 120_000, seed=31)
+    rb, ro, _ = pkg.synth.paired_reads(gb, go, 8000, seed=32)
+    rb2, ro2, _ = pkg.synth.paired_reads(gb, go, 1500, seed=33, frag_mean=560.0, frag_sd=10.0)     # a second library far out
+    mid = 8000
+    rows = rb.reshape(2, mid, 150).copy(); far_rows = rb2.reshape(2, 1500, 150)
+    rows[:, :1500] = far_rows
+    rb = rows.reshape(-1)
+    with pkg.Aligner(report_cigar=False) as al:
+        al.load_genomes(gb, go)
+        al.upload_reads(rb, ro)
+        al.align_resident(fetch=False)
+        full = al.pair_batch(fetch=True)
+        compact, limit, far = al.fetch_pairs_compact()
+    want_c, want_limit, want_far = pkg.compact_pairs_host(full.sorted_overlaps, full.pairs, mid)
+    assert np.array_equal(compact, want_c) and limit == want_limit and len(compact) > 10_000
+    assert np.array_equal(far, want_far)
+    assert 0 < len(far) < len(compact) // 4 and limit < 620
+
+
 def test_fastq_to_alignments(pkg, tmp_path):
     """FASTQ files -> kslam_fastq_next (pinned batch, R1 block then R2 block) -> kslam_align_pair_batch: same pairs as
     handing the arrays over directly, batch by batch (--num-reads-at-once)."""

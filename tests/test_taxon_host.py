@@ -148,6 +148,19 @@ def test_database_archive_round_trip(pkg, tmp_path):
         pkg.Index.read(str(bad))
 
 
+def run_ours_compact(pkg, ix, taxdb_path, batches, **kw):
+    """The same run without --sam-file on COMPACT pair records (kslam_batch_outputs_compact)."""
+    w = pkg.SamWriter(index=ix, num_alignments=kw.get("num_alignments", 10), score_fraction_threshold=kw.get("fraction", 0.95),
+                      pseudo_assembly=kw.get("pseudo", True), report_cigar=False)
+    db, taxa = pkg.TaxDb(taxdb_path), pkg.Taxa()
+    n_reads, limits = 0, []
+    for (rb, ro, quals, idb, ido, ov, pool, pairs) in batches:
+        compact, limit, far = pkg.compact_pairs_host(ov, pairs, (len(ro) - 1) // 2)
+        limits.append((limit, w.batch_compact(ro, idb, ido, compact, limit, far, taxdb=db, taxa=taxa), len(far)))
+        n_reads += (len(ro) - 1) // 2
+    return taxa.results(db, n_reads), limits
+
+
 def run_ours(pkg, ix, taxdb_path, batches, want_sam, paired=True, **kw):
     w = pkg.SamWriter(index=ix, num_alignments=kw.get("num_alignments", 10), score_fraction_threshold=kw.get("fraction", 0.95),
                       pseudo_assembly=kw.get("pseudo", True), report_cigar=True, sam_xa=kw.get("sam_xa", False))
@@ -214,6 +227,21 @@ def test_metagenomic_outputs_equal_reference(pkg, tmp_path, want_sam, paired, pa
                     bad = [(i, x, y) for i, (x, y) in enumerate(zip(a, b_)) if x != y][:3]
                     raise AssertionError((name, kw, len(a), len(b_), bad))
             assert got[1].count(b"<taxon>") >= 3 and b"<gene protein=\"WP_" in got[1] and b"&lt;" in got[1] and len(got[0]) > 1000
+            if paired and not want_sam:
+                got_c, limits = run_ours_compact(pkg, ix, taxdb, batches, **kw)
+                assert got_c == got, "compact pair records give other result files"
+                assert all(a == b for a, b, _ in limits)
+                # pairs far beyond the insert-size limit are split into their mates (PairedOverlap.h:396-436): the full
+                # records read them from the alignment vector, the compact ones from the far-mates table
+                far_batches = []
+                for (rb, ro, quals, idb, ido, ov, pool, pairs) in batches:
+                    pr = pairs.copy()
+                    both = np.flatnonzero((pr["r1_idx"] >= 0) & (pr["r2_idx"] >= 0))
+                    pr["insert_size"][both[::7]] = 40_000
+                    far_batches.append((rb, ro, quals, idb, ido, ov, pool, pr))
+                _, want_far = run_ours(pkg, ix, taxdb, far_batches, False, paired=True, **kw)
+                got_far, limits = run_ours_compact(pkg, ix, taxdb, far_batches, **kw)
+                assert got_far == want_far and all(n_far > 0 for _, _, n_far in limits)
     finally:
         L.kref_set_threads(os.cpu_count() or 1)
         L.kref_taxdb_close(rt)
