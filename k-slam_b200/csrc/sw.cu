@@ -30,7 +30,7 @@
 #include <stdlib.h>
 
 #define SW_R 20
-#define SW_MAXCOLS 512
+#define SW_MAXCOLS 640
 #define SW_BLOCK 128
 #define SW_INVALID 0xFFFFFFFFu
 #define SW_TB_MAXBAND 7
@@ -47,7 +47,9 @@ struct __align__(16) SwTask {
 #define SWT_REV 1u
 #define SWT_BAND 2u   // shape allows the banded kernel (rows <= 160, no code-4 base in the window)
 #define SWT_CLEAN 4u  // no code-4 base in the window
-#define SWC_FAST8 0u
+#define SWC_FAST8 0u    // full-matrix kernel classes: 8 / 16 / 32 lanes x SW_R rows = reads up to 160 / 320 / 640 bases
+#define SWC_FAST16 1u
+#define SWC_FAST32 2u
 #define SWC_SLOW 3u
 #define SWC_NONE 4u   // empty query or window: score 0, nothing to run
 
@@ -141,6 +143,7 @@ k_sw_fast(const SwTask *__restrict__ tasks, const uint2 *__restrict__ items, uin
   if (item < n_items) it = items[item];
   if (it.x == SW_INVALID) return;            // whole group leaves together (shuffles below use gmask only)
   const SwTask ta = tasks[it.x], tb = tasks[it.y];
+  if (((ta.flags >> 8) & 0xffu) != (LANES == 8 ? SWC_FAST8 : LANES == 16 ? SWC_FAST16 : SWC_FAST32)) return;   // another instance's item
   SwRes ra, rb;
   uint32_t ncols, rowsA, rowsB;
   if (REVERSE) {
@@ -762,7 +765,11 @@ __device__ __forceinline__ uint32_t classify(uint32_t m, uint32_t n, const SwSco
   // 16-bit cells: the largest possible score, scaled by 32 and biased (sw_bias), must stay below 2^15
   const bool score_ok = sc.match >= 1 && sc.match * 32 <= 127 && sc.mismatch * 32 <= 128 && sc.gap_open <= 100 && sc.gap_extend <= 100 &&
                         (uint32_t)sc.match * mn * 32u + sw_bias(sc) + 64u <= 32767u;
-  if (score_ok && m <= 8 * SW_R && n <= SW_MAXCOLS) return SWC_FAST8;
+  if (score_ok && n <= SW_MAXCOLS) {
+    if (m <= 8 * SW_R) return SWC_FAST8;
+    if (m <= 16 * SW_R) return SWC_FAST16;
+    if (m <= 32 * SW_R) return SWC_FAST32;
+  }
   return SWC_SLOW;
 }
 
@@ -805,7 +812,7 @@ __device__ __forceinline__ void enlist(const SwPlanes &pl, const SwTask &t, uint
       const uint32_t tt = tier_of_width((int32_t)t.m, (int32_t)t.n, L, sc, level);
       if (tt != SWT_TIER_NONE) { tier = tt; res[i].score = L; }
     }
-  } else { const uint32_t k = list_slot(&counts[CNT_FULL]); full_keys[k].key = t.n; full_keys[k].val = i; }
+  } else { const uint32_t k = list_slot(&counts[CNT_FULL]); full_keys[k].key = t.n | ((uint64_t)cls << 16); full_keys[k].val = i; }   // same class + columns share a group
   tier_f[i] = (uint8_t)tier;
   count_tier(tier, counts);
 }
@@ -886,10 +893,11 @@ k_sw_rev_lists(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
   const SwTask t = tasks[i];
   uint32_t tier = SWT_TIER_NONE;
   const SwRes r = res[i];
-  if (((t.flags >> 8) & 0xffu) == SWC_FAST8 && r.score > 0) {
+  const uint32_t cls = (t.flags >> 8) & 0xffu;
+  if (cls <= SWC_FAST32 && r.score > 0) {
     const int32_t rows = r.read_end + 1, cols = r.ref_end + 1;
     if (t.flags & SWT_BAND) tier = tier_of_width(rows, cols, r.score, sc, level);
-    if (tier == SWT_TIER_NONE) { const uint32_t k = list_slot(&counts[CNT_FULL]); full_keys[k].key = (uint64_t)cols; full_keys[k].val = i; }
+    if (tier == SWT_TIER_NONE) { const uint32_t k = list_slot(&counts[CNT_FULL]); full_keys[k].key = (uint64_t)cols | ((uint64_t)cls << 16); full_keys[k].val = i; }
   }
   tier_r[i] = (uint8_t)tier;
   count_tier(tier, counts);
@@ -922,7 +930,7 @@ k_sw_cells(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, cons
   unsigned long long fw = 0, rv = 0, comp = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const SwTask t = tasks[i]; const SwRes r = res[i];
-    if (((t.flags >> 8) & 0xffu) != SWC_FAST8) continue;
+    if (((t.flags >> 8) & 0xffu) > SWC_FAST32) continue;
     fw += (unsigned long long)t.m * t.n;
     const uint32_t tf = tier_f[i], tr = tier_r[i], ft = (r.flags >> 8) & 7u;
     if (tf < SWT_N_DIRECT) comp += (unsigned long long)tier_width(tf) * t.m;
@@ -1051,7 +1059,7 @@ static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore 
   *n_full_done += n_full;
   if (n_full) {
     uint64_t passes = 0;
-    Rec16 *sorted = radix_sort(c, keys, keys2, n_full, 0, 0, 16, &passes);
+    Rec16 *sorted = radix_sort(c, keys, keys2, n_full, 0, 0, 18, &passes);    // columns | class << 16
     uint2 *items = w->items.as<uint2>();
     const uint32_t n_items = 2 * ((n_full + 1) / 2);
     CUDA_TRY(cudaMemsetAsync(items, 0xff, (size_t)n_items * sizeof(uint2), st));
@@ -1059,6 +1067,11 @@ static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore 
     k_sw_make_items<<<(n_items / 2 + 255) / 256, 256, 0, st>>>(sorted, n_full, items, d_counts + CNT_EXTRA);
     constexpr int GROUPS = SW_BLOCK / 8;
     k_sw_fast<8, REVERSE><<<(n_items + GROUPS - 1) / GROUPS, SW_BLOCK, 0, st>>>(tasks, items, n_items, pl, sc, res, 1u);
+    // reads of 161-320 / 321-640 bases: the same wavefront with 16 / 32 lanes per group; each instance skips the others' items
+    uint32_t longest = c->reads_loaded ? c->reads.max_len : 0;
+    if (c->sw_loaded && c->swq.max_len > longest) longest = c->swq.max_len;
+    if (longest > 8 * SW_R) { k_sw_fast<16, REVERSE><<<(n_items + SW_BLOCK / 16 - 1) / (SW_BLOCK / 16), SW_BLOCK, 0, st>>>(tasks, items, n_items, pl, sc, res, 1u); c->launches++; }
+    if (longest > 16 * SW_R) { k_sw_fast<32, REVERSE><<<(n_items + SW_BLOCK / 32 - 1) / (SW_BLOCK / 32), SW_BLOCK, 0, st>>>(tasks, items, n_items, pl, sc, res, 1u); c->launches++; }
     c->launches += 2;
     CUDA_TRY(cudaGetLastError());
   }

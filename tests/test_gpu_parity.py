@@ -157,12 +157,40 @@ def test_empty_and_ragged_inputs(pkg):
         assert len(al.align_batch(rb, ro).overlaps) == 0
 
 
-def test_long_reads_take_the_slow_kernel(pkg):
-    """Reads beyond the fast kernel's 160 rows are still aligned on the GPU (exact scalar kernel)."""
+@pytest.mark.parametrize("read_len,frag,kernel", [(251, 500, "fast"), (301, 560, "fast"), (500, 590, "fast"), (700, 900, "slow")])
+def test_long_reads(pkg, read_len, frag, kernel):
+    """Reads beyond the 160 rows of the 8-lane full-matrix kernel: 161-320 bases run the 16-lane instance (250 / 300-bp
+    MiSeq reads), 321-640 the 32-lane one, longer ones the exact scalar kernel — bit-exact either way."""
     gb, go = pkg.synth.random_genomes(3, 40_000, seed=8)
-    rb, ro, _ = pkg.synth.paired_reads(gb, go, 300, read_len=251, seed=9, frag_mean=500, frag_sd=30)
+    rb, ro, _ = pkg.synth.paired_reads(gb, go, 300, read_len=read_len, seed=9, frag_mean=frag, frag_sd=30)
     res, tm = check_pipeline(pkg, gb, go, rb, ro, T.default_params(report_cigar=1))
-    assert tm["n_sw_slow"] > 0
+    if kernel == "fast":
+        assert tm["n_sw_slow"] == 0 and tm["n_sw_fast"] > 0
+    else:
+        assert tm["n_sw_slow"] > 0
+
+
+def test_ssw_long_and_mixed_lengths(pkg):
+    """Aligner::Align batches mixing the three full-matrix classes (queries of 20-500 bases — 16-bit cells hold scores up to 2 x 507 —, windows up to 640)."""
+    rng = np.random.default_rng(17)
+    ACGT = pkg.synth.ACGT
+    qs, rs = [], []
+    for _ in range(3000):
+        L = int(rng.integers(30, 641)); w = ACGT[rng.integers(0, 4, size=L)]
+        ql = int(rng.integers(20, min(L, 500) + 1)); st = int(rng.integers(0, L - ql + 1)); qq = w[st:st + ql].copy()
+        mm = rng.random(ql) < 0.04; qq[mm] = ACGT[rng.integers(0, 4, size=int(mm.sum()))]
+        if rng.random() < 0.3 and ql > 40:
+            p = int(rng.integers(10, ql - 10)); k = int(rng.integers(1, 6)); qq = np.concatenate([qq[:p], qq[p + k:]])
+        qs.append(qq); rs.append(w)
+    q, qo = T.concat(qs); r, ro = T.concat(rs)
+    for cigar in (1, 0):
+        P = T.default_params(report_cigar=cigar)
+        want, wpool = T.ko_ssw_batch(q, qo, r, ro, P, cigar_cap=64)
+        with pkg.Aligner(report_cigar=bool(cigar), max_cigar_ops=64) as al:
+            out, pool = al.ssw_batch(q, qo, r, ro)
+            tm = al.timings()
+        check_overlaps(out, pool, want, wpool, fields=FIELDS[4:], cigars=bool(cigar))
+        assert tm["n_sw_slow"] == 0
 
 
 def test_cigar_pool_stride_grows_instead_of_truncating(pkg):
