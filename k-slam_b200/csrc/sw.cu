@@ -500,17 +500,25 @@ __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const S
     ws = width_d < refLen ? width_d : refLen;
     if ((uint32_t)aw > arr_cap || (size_t)ws * (size_t)readLen > dir_cap) return -3;
     for (int32_t j = 1; j < aw - 1; j++) h_b[j] = 0;
+    // Window codes of the band cells of a row, one nibble per cell (bands up to 7: 15 cells): nibble k of `wwin` holds the
+    // code of column i - band + k. A row needs ONE new code (column i + band); the plane loads of w_code were per cell.
+    const bool windowed = band <= SW_TB_MAXBAND;
+    uint64_t wwin = 0;
+    if (windowed)
+      for (int32_t k = band; k <= 2 * band; k++)
+        if (k - band < refLen) wwin |= (uint64_t)w_code(pl, t, (uint32_t)(ref0 + k - band)) << (4 * k);
     for (int32_t i = 0; i < readLen; i++) {
-      int32_t beg = i - band > 0 ? i - band : 0, end = i + band < refLen - 1 ? i + band : refLen - 1;
-      int32_t edge = end + 1 < width - 1 ? end + 1 : width - 1, u = 0;
-      int32_t f = 0;
+      const int32_t beg = i - band > 0 ? i - band : 0, end = i + band < refLen - 1 ? i + band : refLen - 1;
+      const int32_t edge = end + 1 < width - 1 ? end + 1 : width - 1;
+      int32_t u = 0, f = 0;
       h_b[0] = 0; e_b[0] = 0; h_b[edge] = 0; e_b[edge] = 0; h_c[0] = 0;
       const uint32_t qc = q_code(pl, t, (uint32_t)(read0 + i));
       uint8_t *dl = dir + (size_t)ws * i * dstride;
-      const int32_t xoff = i - band > 0 ? i - band : 0;
+      // set_u (ssw.c:56-61): u = j - max(i - band, 0) + 1 for row i; the row above is shifted by `up` = 0 or 1 slots
+      const int32_t xoff = beg, up = xoff - (i - 1 - band > 0 ? i - 1 - band : 0);
       for (int32_t j = beg; j <= end; j++) {
-        int32_t e, b, d;
-        SET_U(u, band, i, j); SET_U(e, band, i - 1, j); SET_U(b, band, i, j - 1); SET_U(d, band, i - 1, j - 1);
+        u = j - xoff + 1;
+        const int32_t e = u + up, b = u - 1, d = e - 1;
         int32_t t1 = i == 0 ? -go : h_b[e] - go;
         int32_t t2 = i == 0 ? -ge : e_b[e] - ge;
         const int32_t ev = t1 > t2 ? t1 : t2;
@@ -521,7 +529,7 @@ __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const S
         const uint32_t df = t1 > t2 ? 5u : 4u;
         const int32_t e1 = ev > 0 ? ev : 0, f1 = f > 0 ? f : 0;
         t1 = e1 > f1 ? e1 : f1;
-        const uint32_t wc = w_code(pl, t, (uint32_t)(ref0 + j));
+        const uint32_t wc = windowed ? (uint32_t)(wwin >> (4 * (j - i + band))) & 7u : w_code(pl, t, (uint32_t)(ref0 + j));
         const int32_t s = (wc == 4 || qc == 4) ? 0 : (wc == qc ? sc.match : -sc.mismatch);
         t2 = h_b[d] + s;
         const int32_t hv = t1 > t2 ? t1 : t2;
@@ -531,6 +539,11 @@ __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const S
         dl[(size_t)(j - xoff) * dstride] = (uint8_t)((de == 3u) | ((df == 5u) << 1) | (dh << 2));
       }
       for (int32_t j = 1; j <= u; j++) h_b[j] = h_c[j];
+      if (windowed) {
+        wwin >>= 4;
+        const int32_t col = i + 1 + band;
+        if (col < refLen) wwin |= (uint64_t)w_code(pl, t, (uint32_t)(ref0 + col)) << (8 * band);
+      }
     }
     band *= 2;
   } while (maxv < score);
