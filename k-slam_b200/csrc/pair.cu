@@ -95,14 +95,25 @@ k_pair_merge(const kslam_overlap *__restrict__ ov, const uint32_t *__restrict__ 
     if (!less_ba(b, a)) lo = a + 1; else hi = a;
   }
   uint32_t a = lo, b = diag - lo;
+  __shared__ uint32_t s_out[PM_TILE];                             // source record of every output of the tile
 #pragma unroll
   for (int k = 0; k < PM_IPT; k++) {
     const uint32_t o = diag + k;
     if (o >= ca + cb) break;
     const bool take_b = a >= ca || (b < cb && less_ba(b, a));
-    const uint32_t src = take_b ? s_src[ca + b] : s_src[a];
+    s_out[o] = take_b ? s_src[ca + b] : s_src[a];
     if (take_b) b++; else a++;
-    out[d0 + o] = ov[src];                                        // cigar_off keeps pointing into the batch's dense CIGAR pool
+  }
+  __syncthreads();
+  // The records move as 16-byte thirds, consecutive threads on consecutive thirds: coalesced stores, and loads that are
+  // sequential inside each source list (one thread copying its eight 48-byte records wrote 384-byte strides per lane:
+  // 19 ms for 167 M records in profiles/r2_launches_bench_config2.txt against ~3 ms of bandwidth).
+  static_assert(sizeof(kslam_overlap) == 48, "three 16-byte thirds per record");
+  const uint4 *src16 = reinterpret_cast<const uint4 *>(ov);
+  uint4 *dst16 = reinterpret_cast<uint4 *>(out + d0);
+  for (uint32_t c = threadIdx.x; c < 3 * (ca + cb); c += PM_THREADS) {
+    const uint32_t o = c / 3, part = c - 3 * o;
+    dst16[c] = __ldg(src16 + (size_t)s_out[o] * 3 + part);        // cigar_off keeps pointing into the batch's dense CIGAR pool
   }
 }
 

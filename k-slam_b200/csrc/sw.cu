@@ -765,10 +765,17 @@ __device__ __forceinline__ uint32_t tier_of_width(int32_t rows, int32_t cols, in
   if (width <= 32) return 2u;
   return (level >= 2 && width <= 64) ? 4u : SWT_TIER_NONE;
 }
-// one counter per tier, one atomic per (warp, tier)
-__device__ __forceinline__ void count_tier(uint32_t tier, uint32_t *__restrict__ counts) {
-  const uint32_t peers = __match_any_sync(__activemask(), tier);
-  if (tier != SWT_TIER_NONE && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&counts[CNT_TIER + tier], (uint32_t)__popc(peers));
+// One counter per tier, one GLOBAL atomic per (CTA, tier): every thread of the CTA calls this once at the end of its kernel
+// (dead threads with SWT_TIER_NONE). Per-warp global atomics — 5 M warps x up to 6 tiers on six addresses — serialised in
+// L2: k_sw_rev_lists took 14.5 ms for 167 M alignments (profiles/r2_launches_bench_config2.txt), 10 ms of it these atomics.
+__device__ __forceinline__ void count_tier_block(uint32_t tier, uint32_t *__restrict__ counts) {
+  __shared__ uint32_t s_cnt[SWT_N_TIERS];
+  if (threadIdx.x < SWT_N_TIERS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t peers = __match_any_sync(0xffffffffu, tier);
+  if (tier != SWT_TIER_NONE && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_cnt[tier], (uint32_t)__popc(peers));
+  __syncthreads();
+  if (threadIdx.x < SWT_N_TIERS && s_cnt[threadIdx.x]) atomicAdd(&counts[CNT_TIER + threadIdx.x], s_cnt[threadIdx.x]);
 }
 
 __device__ __forceinline__ uint32_t classify(uint32_t m, uint32_t n, const SwScore &sc) {
@@ -810,7 +817,7 @@ __device__ __forceinline__ bool window_clean(const uint32_t *__restrict__ nmask,
 // `tiers` on, the seed-diagonal lower bound L picks the narrowest band that provably holds every optimal alignment
 // (res[].score = L is what MODE 2 of k_sw_band places the band with); otherwise, or when L allows nothing <= 64
 // diagonals (e.g. an indel splits the read over two diagonals), the 32-wide sweep-and-verify tier.
-__device__ __forceinline__ void enlist(const SwPlanes &pl, const SwTask &t, uint32_t i, uint32_t cls, int32_t d0, bool seeded, uint32_t level,
+__device__ __forceinline__ uint32_t enlist(const SwPlanes &pl, const SwTask &t, uint32_t i, uint32_t cls, int32_t d0, bool seeded, uint32_t level,
                                        const SwScore &sc, SwRes *__restrict__ res, uint8_t *__restrict__ tier_f,
                                        Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list, uint32_t *__restrict__ counts) {
   uint32_t tier = SWT_TIER_NONE;
@@ -827,35 +834,40 @@ __device__ __forceinline__ void enlist(const SwPlanes &pl, const SwTask &t, uint
     }
   } else { const uint32_t k = list_slot(&counts[CNT_FULL]); full_keys[k].key = t.n | ((uint64_t)cls << 16); full_keys[k].val = i; }   // same class + columns share a group
   tier_f[i] = (uint8_t)tier;
-  count_tier(tier, counts);
+  return tier;
 }
 
 // tier byte array -> one list per tier inside `list` (tier t starts at offs[t]); order inside a list is arbitrary
 __global__ void __launch_bounds__(256)
 k_tier_scatter(const uint8_t *__restrict__ tier, uint32_t n, const uint32_t *__restrict__ counts, uint32_t *__restrict__ cursors,
                uint32_t *__restrict__ list) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ uint32_t s_wcnt[8][SWT_N_TIERS];          // per warp and tier: members, then the warp's offset inside the CTA's run
+  __shared__ uint32_t s_base[SWT_N_TIERS];             // where the CTA's run of a tier starts in that tier's list
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t t = i < n ? tier[i] : SWT_TIER_NONE;
+  if (threadIdx.x < 8 * SWT_N_TIERS) (&s_wcnt[0][0])[threadIdx.x] = 0;
+  __syncthreads();
   const uint32_t peers = __match_any_sync(0xffffffffu, t);
-  if (t == SWT_TIER_NONE) return;
-  const uint32_t lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(&cursors[t], (uint32_t)__popc(peers));
-  base = __shfl_sync(peers, base, leader);
-  uint32_t off = 0;
-  for (uint32_t k = 0; k < t; k++) off += counts[CNT_TIER + k];
-  list[off + base + __popc(peers & ((1u << lane) - 1u))] = i;
+  if (t != SWT_TIER_NONE && lane == (uint32_t)(__ffs(peers) - 1)) s_wcnt[warp][t] = (uint32_t)__popc(peers);
+  __syncthreads();
+  if (threadIdx.x < SWT_N_TIERS) {                       // one global atomic per (CTA, tier)
+    uint32_t run = 0;
+    for (int w = 0; w < 8; w++) { const uint32_t c = s_wcnt[w][threadIdx.x]; s_wcnt[w][threadIdx.x] = run; run += c; }
+    uint32_t off = 0;
+    for (uint32_t k = 0; k < threadIdx.x; k++) off += counts[CNT_TIER + k];
+    s_base[threadIdx.x] = off + (run ? atomicAdd(&cursors[threadIdx.x], run) : 0u);
+  }
+  __syncthreads();
+  if (t != SWT_TIER_NONE) list[s_base[t] + s_wcnt[warp][t] + __popc(peers & ((1u << lane) - 1u))] = i;
 }
 
 // pipeline mode: one task per seed (SmithWaterman.h:199-211)
-__global__ void __launch_bounds__(256)
-k_sw_prepare_seeds(const kslam_seed *__restrict__ seeds, uint32_t n, const uint64_t *__restrict__ r_offs,
-                   const uint64_t *__restrict__ r_word, const uint64_t *__restrict__ g_offs,
-                   const uint64_t *__restrict__ g_word, const uint32_t *__restrict__ g_nmask, SwScore sc, uint32_t use_band,
-                   SwPlanes pl, SwTask *__restrict__ tasks, SwRes *__restrict__ res, uint8_t *__restrict__ tier_f,
-                   Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list, uint32_t *__restrict__ counts) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ uint32_t
+prepare_seed(uint32_t i, const kslam_seed *__restrict__ seeds, const uint64_t *__restrict__ r_offs,
+             const uint64_t *__restrict__ r_word, const uint64_t *__restrict__ g_offs,
+             const uint64_t *__restrict__ g_word, const uint32_t *__restrict__ g_nmask, const SwScore &sc, uint32_t use_band,
+             const SwPlanes &pl, SwTask *__restrict__ tasks, SwRes *__restrict__ res, uint8_t *__restrict__ tier_f,
+             Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list, uint32_t *__restrict__ counts) {
   const kslam_seed s = seeds[i];
   const uint64_t qlen = r_offs[s.read + 1] - r_offs[s.read], glen = g_offs[s.entry + 1] - g_offs[s.entry];
   const uint64_t start = s.rel > 0 ? (uint64_t)s.rel : 0;                     // :205
@@ -871,7 +883,18 @@ k_sw_prepare_seeds(const kslam_seed *__restrict__ seeds, uint32_t n, const uint6
   // matrix diagonal of the seed's exact 32-mer match: forward seeds put read base i on genome base rel + i; reverse-
   // complement seeds put rc(read) base i there and Align sees the window reversed (SmithWaterman.h:205-208)
   const int32_t d0 = s.rev_comp ? (int32_t)t.w_start + (int32_t)t.n - s.rel - (int32_t)t.m : s.rel - (int32_t)t.w_start;
-  enlist(pl, t, i, cls, d0, true, use_band, sc, res, tier_f, full_keys, slow_list, counts);
+  return enlist(pl, t, i, cls, d0, true, use_band, sc, res, tier_f, full_keys, slow_list, counts);
+}
+__global__ void __launch_bounds__(256)
+k_sw_prepare_seeds(const kslam_seed *__restrict__ seeds, uint32_t n, const uint64_t *__restrict__ r_offs,
+                   const uint64_t *__restrict__ r_word, const uint64_t *__restrict__ g_offs,
+                   const uint64_t *__restrict__ g_word, const uint32_t *__restrict__ g_nmask, SwScore sc, uint32_t use_band,
+                   SwPlanes pl, SwTask *__restrict__ tasks, SwRes *__restrict__ res, uint8_t *__restrict__ tier_f,
+                   Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list, uint32_t *__restrict__ counts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t tier = SWT_TIER_NONE;
+  if (i < n) tier = prepare_seed(i, seeds, r_offs, r_word, g_offs, g_word, g_nmask, sc, use_band, pl, tasks, res, tier_f, full_keys, slow_list, counts);
+  count_tier_block(tier, counts);       // every thread of the CTA, from this one place (it holds barriers and a full-warp match)
 }
 
 // Aligner::Align batch mode: query i against ref i, whole sequences
@@ -883,16 +906,19 @@ k_sw_prepare_pairs(uint32_t n, const uint64_t *__restrict__ q_offs, const uint64
                    uint8_t *__restrict__ tier_f, Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list,
                    uint32_t *__restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  SwTask t;
-  t.q_word = q_word[i]; t.w_word = r_word[i];
-  t.m = (uint32_t)(q_offs[i + 1] - q_offs[i]); t.n = (uint32_t)(r_offs[i + 1] - r_offs[i]); t.w_start = 0;
-  const uint32_t cls = classify(t.m, t.n, sc);
-  t.flags = cls << 8;
-  if (cls != SWC_NONE && window_clean(r_nmask, t.w_word, 0, t.n)) t.flags |= SWT_CLEAN;
-  if (use_band && cls == SWC_FAST8 && band_shape_ok(t.m, t.n) && (t.flags & SWT_CLEAN)) t.flags |= SWT_BAND;
-  tasks[i] = t;
-  enlist(pl, t, i, cls, 0, false, use_band, sc, res, tier_f, full_keys, slow_list, counts);   // no seed: try the main diagonal
+  uint32_t tier = SWT_TIER_NONE;
+  if (i < n) {
+    SwTask t;
+    t.q_word = q_word[i]; t.w_word = r_word[i];
+    t.m = (uint32_t)(q_offs[i + 1] - q_offs[i]); t.n = (uint32_t)(r_offs[i + 1] - r_offs[i]); t.w_start = 0;
+    const uint32_t cls = classify(t.m, t.n, sc);
+    t.flags = cls << 8;
+    if (cls != SWC_NONE && window_clean(r_nmask, t.w_word, 0, t.n)) t.flags |= SWT_CLEAN;
+    if (use_band && cls == SWC_FAST8 && band_shape_ok(t.m, t.n) && (t.flags & SWT_CLEAN)) t.flags |= SWT_BAND;
+    tasks[i] = t;
+    tier = enlist(pl, t, i, cls, 0, false, use_band, sc, res, tier_f, full_keys, slow_list, counts);   // no seed: try the main diagonal
+  }
+  count_tier_block(tier, counts);
 }
 
 // reverse pass work lists: score 0 has no reverse pass (ssw.c:903 is reached with an empty range). The forward score S
@@ -902,18 +928,19 @@ k_sw_rev_lists(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
                uint8_t *__restrict__ tier_r, uint32_t level,
                Rec16 *__restrict__ full_keys, uint32_t *__restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const SwTask t = tasks[i];
   uint32_t tier = SWT_TIER_NONE;
-  const SwRes r = res[i];
-  const uint32_t cls = (t.flags >> 8) & 0xffu;
-  if (cls <= SWC_FAST32 && r.score > 0) {
-    const int32_t rows = r.read_end + 1, cols = r.ref_end + 1;
-    if (t.flags & SWT_BAND) tier = tier_of_width(rows, cols, r.score, sc, level);
-    if (tier == SWT_TIER_NONE) { const uint32_t k = list_slot(&counts[CNT_FULL]); full_keys[k].key = (uint64_t)cols | ((uint64_t)cls << 16); full_keys[k].val = i; }
+  if (i < n) {
+    const SwTask t = tasks[i];
+    const SwRes r = res[i];
+    const uint32_t cls = (t.flags >> 8) & 0xffu;
+    if (cls <= SWC_FAST32 && r.score > 0) {
+      const int32_t rows = r.read_end + 1, cols = r.ref_end + 1;
+      if (t.flags & SWT_BAND) tier = tier_of_width(rows, cols, r.score, sc, level);
+      if (tier == SWT_TIER_NONE) { const uint32_t k = list_slot(&counts[CNT_FULL]); full_keys[k].key = (uint64_t)cols | ((uint64_t)cls << 16); full_keys[k].val = i; }
+    }
+    tier_r[i] = (uint8_t)tier;
   }
-  tier_r[i] = (uint8_t)tier;
-  count_tier(tier, counts);
+  count_tier_block(tier, counts);
 }
 
 // sorted (by columns) task ids -> work items of the full-matrix kernel: two alignments with the same column count
