@@ -79,10 +79,11 @@ class Timings(C.Structure):
                [(n, C.c_uint64) for n in ("n_read_kmers", "n_sorted_kmers", "n_genome_kmers", "n_raw_seeds", "n_seeds", "n_sort_passes",
                                           "sw_cells_forward", "sw_cells_reverse", "sw_cells_computed", "n_sw_fast", "n_sw_slow", "n_sw_band", "n_sw_band64", "n_sw_band_rev", "n_traceback_dp", "n_pairs",
                                           "n_sw_tier8", "n_sw_tier16", "n_sw_tier32", "n_sw_tier48", "n_sw_tier64", "n_sw_sweep32",
-                                          "kernel_launches")]
+                                          "n_sw_tier96", "n_sw_tier128")] + \
+               [("n_sw_rev_tier", C.c_uint64 * 7), ("kernel_launches", C.c_uint64)]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_ if n != "_pad"}
+        return {n: (list(getattr(self, n)) if n == "n_sw_rev_tier" else getattr(self, n)) for n, _ in self._fields_ if n != "_pad"}
 
 
 class CommStats(C.Structure):

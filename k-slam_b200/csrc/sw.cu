@@ -58,18 +58,18 @@ struct __align__(16) SwRes {
   uint32_t flags, pad0, pad1;   // flags: low byte = KSLAM_FLAG_*, bits 8-10 forward tier, bits 11-13 reverse tier
 };
 // tier code of the sweep that produced the result: 0 = full-matrix / scalar kernel, 1..4 = band of 8 / 16 / 32 / 64
-// diagonals, 5 = 48 diagonals
-#define SWR_TIER_OF_W(W) ((W) == 8 ? 1u : (W) == 16 ? 2u : (W) == 32 ? 3u : (W) == 64 ? 4u : 5u)
+// diagonals, 5 = 48, 6 = 96, 7 = 128 diagonals
+#define SWR_TIER_OF_W(W) ((W) == 8 ? 1u : (W) == 16 ? 2u : (W) == 32 ? 3u : (W) == 64 ? 4u : (W) == 48 ? 5u : (W) == 96 ? 6u : 7u)
 #define SWR_FWD_TIER(t) ((uint32_t)(t) << 8)
 #define SWR_REV_TIER(t) ((uint32_t)(t) << 11)
-// work-list tier of an alignment (byte arrays tier_f / tier_r): 0..4 = band of 8 / 16 / 32 / 48 / 64 diagonals placed
-// exactly on the interval a known score bound allows (no verification needed), 5 = 32 diagonals centred,
-// sweep-and-verify, 255 = not in a band list
-#define SWT_N_DIRECT 5u
-#define SWT_TIER_SWEEP 5u
-#define SWT_N_TIERS 6u
+// work-list tier of an alignment (byte arrays tier_f / tier_r): 0..6 = band of 8 / 16 / 32 / 48 / 64 / 96 / 128 diagonals
+// placed exactly on the interval a known score bound allows (no verification needed; 96 and 128 are swept by three / four
+// lanes of 32 slots each), 7 = 32 diagonals centred, sweep-and-verify, 255 = not in a band list
+#define SWT_N_DIRECT 7u
+#define SWT_TIER_SWEEP 7u
+#define SWT_N_TIERS 8u
 #define SWT_TIER_NONE 255u
-__host__ __device__ __forceinline__ uint32_t tier_width(uint32_t t) { return t == 0 ? 8u : t == 1 ? 16u : t == 2 ? 32u : t == 3 ? 48u : 64u; }
+__host__ __device__ __forceinline__ uint32_t tier_width(uint32_t t) { return t == 0 ? 8u : t == 1 ? 16u : t == 2 ? 32u : t == 3 ? 48u : t == 4 ? 64u : t == 5 ? 96u : 128u; }
 
 struct SwPlanes {
   const uint64_t *q_sbits; const uint32_t *q_nmask;
@@ -80,6 +80,8 @@ struct SwScore {
   int32_t match, mismatch, gap_open, gap_extend;   // positive magnitudes, as given
   uint32_t score_threshold; uint32_t report_cigar; uint32_t cigar_cap;
   uint32_t literal;   // 1: scoring parameters outside the plain-Gotoh domain -> every alignment runs k_sw_striped
+  uint32_t max_band;  // widest band tier in use (128; KSLAM_SW_MAX_BAND=64 leaves the multi-lane tiers out: ablation)
+  uint32_t anchored;  // 1: reverse sweeps run in the anchored band (KSLAM_SW_REV_ANCHOR=0: the interval [-(rows - a), cols - a])
 };
 
 struct SwWorkspace {
@@ -713,7 +715,7 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
 #define CNT_SLOW 2
 #define CNT_RETRY 4
 #define CNT_EXTRA 5
-#define CNT_BAND64 6
+#define CNT_BAND64 8   // three counters: failures of the sweep tier that fit 64 / 96 / 128 diagonals
 #define CNT_OVERFLOW 7   // alignments whose CIGAR has more ops than the pool stride (KSLAM_FLAG_CIGAR_OVERFLOW)
 #define CNT_TIER 16    // SWT_N_TIERS counters: alignments per work-list tier
 #define CNT_CUR 24     // SWT_N_TIERS cursors of k_tier_scatter
@@ -758,12 +760,15 @@ __device__ int32_t diag_lower_bound(const SwPlanes &pl, const SwTask &t, int32_t
 // smallest direct tier (0..4 = 8 / 16 / 32 / 48 / 64 diagonals) whose band holds [-(rows - a), cols - a],
 // a = ceil(score / match); SWT_TIER_NONE when the interval is wider than the widest tier allowed or the score says
 // nothing. level: 1 = 32 only, 2 = 32 and 64, 3 = all five widths.
-__device__ __forceinline__ uint32_t tier_of_width(int32_t rows, int32_t cols, int32_t score, const SwScore &sc, uint32_t level) {
-  if (score <= 0) return SWT_TIER_NONE;
-  const int32_t width = rows + cols - 2 * ceil_div_pos(score, sc.match) + 1;
-  if (level >= 3) return width <= 8 ? 0u : width <= 16 ? 1u : width <= 32 ? 2u : width <= 48 ? 3u : width <= 64 ? 4u : SWT_TIER_NONE;
+__device__ __forceinline__ uint32_t tier_of_interval(int32_t width, uint32_t level, const SwScore &sc) {
+  if (width > (int32_t)sc.max_band) return SWT_TIER_NONE;
+  if (level >= 3) return width <= 8 ? 0u : width <= 16 ? 1u : width <= 32 ? 2u : width <= 48 ? 3u : width <= 64 ? 4u : width <= 96 ? 5u : width <= 128 ? 6u : SWT_TIER_NONE;
   if (width <= 32) return 2u;
   return (level >= 2 && width <= 64) ? 4u : SWT_TIER_NONE;
+}
+__device__ __forceinline__ uint32_t tier_of_width(int32_t rows, int32_t cols, int32_t score, const SwScore &sc, uint32_t level) {
+  if (score <= 0) return SWT_TIER_NONE;
+  return tier_of_interval(rows + cols - 2 * ceil_div_pos(score, sc.match) + 1, level, sc);
 }
 // One counter per tier, one GLOBAL atomic per (CTA, tier): every thread of the CTA calls this once at the end of its kernel
 // (dead threads with SWT_TIER_NONE). Per-warp global atomics — 5 M warps x up to 6 tiers on six addresses — serialised in
@@ -794,7 +799,7 @@ __device__ __forceinline__ uint32_t classify(uint32_t m, uint32_t n, const SwSco
 }
 
 // A band can only ever hold [-(m - a), n - a] (sw_band.cuh) when that interval's minimum width |n - m| + 1 (reached at
-// a = min(m, n)) fits the widest tier; wider shapes (e.g. a 150-base read in a 300-base window) go straight to the
+// a = min(m, n)) fits the widest tier (128); wider shapes (e.g. a 150-base read in a 300-base window) go straight to the
 // full-matrix kernel instead of paying for a sweep that cannot prove anything.
 __device__ __forceinline__ bool band_shape_ok(uint32_t m, uint32_t n) {
   const uint32_t d = m > n ? m - n : n - m;
@@ -922,7 +927,7 @@ k_sw_prepare_pairs(uint32_t n, const uint64_t *__restrict__ q_offs, const uint64
 }
 
 // reverse pass work lists: score 0 has no reverse pass (ssw.c:903 is reached with an empty range). The forward score S
-// is known, so the band [-(rows - a), cols - a] (sw_band.cuh) is exact and its width picks the tier directly.
+// is known, so the interval an anchored path can reach (reverse_band, sw_band.cuh) is exact and its width picks the tier.
 __global__ void __launch_bounds__(256)
 k_sw_rev_lists(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, uint32_t n, SwScore sc,
                uint8_t *__restrict__ tier_r, uint32_t level,
@@ -935,7 +940,11 @@ k_sw_rev_lists(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
     const uint32_t cls = (t.flags >> 8) & 0xffu;
     if (cls <= SWC_FAST32 && r.score > 0) {
       const int32_t rows = r.read_end + 1, cols = r.ref_end + 1;
-      if (t.flags & SWT_BAND) tier = tier_of_width(rows, cols, r.score, sc, level);
+      if (t.flags & SWT_BAND) {
+        int32_t lo, hi;
+        reverse_band(rows, cols, r.score, sc, &lo, &hi);
+        tier = tier_of_interval(hi - lo + 1, level, sc);
+      }
       if (tier == SWT_TIER_NONE) { const uint32_t k = list_slot(&counts[CNT_FULL]); full_keys[k].key = (uint64_t)cols | ((uint64_t)cls << 16); full_keys[k].val = i; }
     }
     tier_r[i] = (uint8_t)tier;
@@ -974,7 +983,7 @@ k_sw_cells(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, cons
     fw += (unsigned long long)t.m * t.n;
     const uint32_t tf = tier_f[i], tr = tier_r[i], ft = (r.flags >> 8) & 7u;
     if (tf < SWT_N_DIRECT) comp += (unsigned long long)tier_width(tf) * t.m;
-    if (tf == SWT_TIER_SWEEP) { comp += 32ull * t.m; if (ft == 4u) comp += 64ull * t.m; }
+    if (tf == SWT_TIER_SWEEP) { comp += 32ull * t.m; if (ft == 4u) comp += 64ull * t.m; if (ft == 6u) comp += 96ull * t.m; if (ft == 7u) comp += 128ull * t.m; }
     if (ft == 0u) comp += (unsigned long long)t.m * t.n;
     if (r.score > 0) {
       const unsigned long long rows = (unsigned long long)(r.read_end + 1), cols = (unsigned long long)(r.ref_end + 1);
@@ -1031,6 +1040,9 @@ static SwScore make_score(const kslam_ctx *c) {
   s.match = (int8_t)c->prm.match; s.mismatch = -(int32_t)(int8_t)(-(int32_t)c->prm.mismatch);
   s.gap_open = c->prm.gap_open; s.gap_extend = c->prm.gap_extend;
   s.literal = kslam_params_fast(&c->prm) ? 0u : 1u;
+  static const char *mb = getenv("KSLAM_SW_MAX_BAND"), *ra = getenv("KSLAM_SW_REV_ANCHOR");
+  s.max_band = mb && atoi(mb) == 64 ? 64u : 128u;
+  s.anchored = ra && atoi(ra) == 0 ? 0u : 1u;
   s.score_threshold = c->prm.score_threshold; s.report_cigar = c->prm.report_cigar; s.cigar_cap = c->prm.max_cigar_ops;
   return s;
 }
@@ -1042,14 +1054,15 @@ static uint32_t read_count(kslam_ctx *c, uint32_t *d_counts, uint32_t *h_counts,
 }
 
 // one banded tier over a list: the sweep kernel unpacks its own selector streams into shared memory
-template <int MODE, int W>
+template <int MODE, int WP, int PARTS = 1>
 static void run_band(kslam_ctx *c, const SwPlanes &pl, const SwScore &sc, const uint32_t *list, uint32_t n_list,
-                     uint32_t *d_counts, uint32_t *next_list) {
+                     uint32_t *d_counts, uint32_t *next_list, uint32_t next_stride = 0) {
   if (!n_list) return;
   SwWorkspace *w = c->sw;
-  const uint32_t pairs = (n_list + 1) / 2, blocks = (pairs + SWB_BLOCK - 1) / SWB_BLOCK;
-  k_sw_band<MODE, W><<<blocks, SWB_BLOCK, BandSmem<W>::BYTES, c->stream>>>(w->tasks.as<SwTask>(), list, n_list, pl, sc, w->res.as<SwRes>(),
-      w->keys.as<Rec16>(), d_counts + CNT_FULL, next_list, d_counts + CNT_BAND64, 1u);
+  const uint32_t pairs = (n_list + 1) / 2, per_block = PARTS == 1 ? SWB_BLOCK : (SWB_BLOCK / 32) * (32 / PARTS);
+  const uint32_t blocks = (pairs + per_block - 1) / per_block;
+  k_sw_band<MODE, WP, PARTS><<<blocks, SWB_BLOCK, BandSmem<WP>::BYTES, c->stream>>>(w->tasks.as<SwTask>(), list, n_list, pl, sc, w->res.as<SwRes>(),
+      w->keys.as<Rec16>(), d_counts + CNT_FULL, next_list, d_counts + CNT_BAND64, next_stride, 1u);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
 }
@@ -1079,9 +1092,9 @@ static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore 
   cudaStream_t st = c->stream;
   SwTask *tasks = w->tasks.as<SwTask>();
   SwRes *res = w->res.as<SwRes>();
-  uint32_t *lists = w->lists.as<uint32_t>(), *list64 = lists + 2 * (size_t)n;
+  uint32_t *lists = w->lists.as<uint32_t>(), *list64 = lists + 2 * (size_t)n;      // then the 96- and 128-wide lists, stride n
   Rec16 *keys = w->keys.as<Rec16>(), *keys2 = w->keys2.as<Rec16>();
-  uint32_t off[SWT_N_TIERS] = {0, 0, 0, 0, 0, 0};
+  uint32_t off[SWT_N_TIERS] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (uint32_t t = 1; t < SWT_N_TIERS; t++) off[t] = off[t - 1] + cnt[t - 1];
   constexpr int DM = REVERSE ? 1 : 2;
   run_band<DM, 8>(c, pl, sc, lists + off[0], cnt[0], d_counts, nullptr);
@@ -1089,11 +1102,17 @@ static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore 
   run_band<DM, 32>(c, pl, sc, lists + off[2], cnt[2], d_counts, nullptr);
   run_band<DM, 48>(c, pl, sc, lists + off[3], cnt[3], d_counts, nullptr);
   run_band<DM, 64>(c, pl, sc, lists + off[4], cnt[4], d_counts, nullptr);
+  run_band<DM, 32, 3>(c, pl, sc, lists + off[5], cnt[5], d_counts, nullptr);
+  run_band<DM, 32, 4>(c, pl, sc, lists + off[6], cnt[6], d_counts, nullptr);
   if (!REVERSE && cnt[SWT_TIER_SWEEP]) {
-    run_band<0, 32>(c, pl, sc, lists + off[SWT_TIER_SWEEP], cnt[SWT_TIER_SWEEP], d_counts, c->sw_band64 ? list64 : nullptr);
-    const uint32_t n64 = read_count(c, d_counts, h_counts, CNT_BAND64);     // 32-wide failures that fit 64 diagonals
+    run_band<0, 32>(c, pl, sc, lists + off[SWT_TIER_SWEEP], cnt[SWT_TIER_SWEEP], d_counts, c->sw_band64 ? list64 : nullptr, n);
+    read_small(c, h_counts + CNT_BAND64, d_counts + CNT_BAND64, 12);       // 32-wide failures that fit 64 / 96 / 128 diagonals
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const uint32_t n64 = h_counts[CNT_BAND64], n96 = h_counts[CNT_BAND64 + 1], n128 = h_counts[CNT_BAND64 + 2];
     run_band<2, 64>(c, pl, sc, list64, n64, d_counts, nullptr);
-    *n_band64_via_sweep += n64;
+    run_band<2, 32, 3>(c, pl, sc, list64 + (size_t)n, n96, d_counts, nullptr);
+    run_band<2, 32, 4>(c, pl, sc, list64 + 2 * (size_t)n, n128, d_counts, nullptr);
+    *n_band64_via_sweep += n64 + n96 + n128;
   }
   const uint32_t n_full = read_count(c, d_counts, h_counts, CNT_FULL);
   *n_full_done += n_full;
@@ -1170,22 +1189,24 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
   uint64_t band64_sweep = 0, full_done = 0;
   sw_pass<false>(c, n, pl, sc, cnt, d_counts, h_counts, &band64_sweep, &full_done);
   c->tm.n_sw_fast = full_done; c->tm.n_sw_slow = n_slow;
-  c->tm.n_sw_band = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4] + cnt[5];
+  c->tm.n_sw_band = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4] + cnt[5] + cnt[6] + cnt[7];
   c->tm.n_sw_band64 = cnt[4] + band64_sweep;
+  c->tm.n_sw_tier96 = cnt[5]; c->tm.n_sw_tier128 = cnt[6];
   c->tm.n_sw_tier8 = cnt[0]; c->tm.n_sw_tier16 = cnt[1]; c->tm.n_sw_tier32 = cnt[2]; c->tm.n_sw_tier48 = cnt[3]; c->tm.n_sw_tier64 = cnt[4];
   c->tm.n_sw_sweep32 = cnt[SWT_TIER_SWEEP];
   cudaEvent_t e2 = tm_mark(c);
 
   // ---- reverse
   CUDA_TRY(cudaMemsetAsync(d_counts + CNT_BAND, 0, 8, st));   // band + full counters
-  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_BAND64, 0, 4, st));
+  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_BAND64, 0, 12, st));
   CUDA_TRY(cudaMemsetAsync(d_counts + CNT_TIER, 0, SWT_N_TIERS * 4, st));
   k_sw_rev_lists<<<nb, 256, 0, st>>>(tasks, res, n, sc, tier_r, sw_level(c), w->keys.as<Rec16>(), d_counts);
   c->launches++;
   make_tier_lists(c, n, tier_r, d_counts, h_counts, cnt);
   uint64_t dummy = 0, full_rev = 0;
   sw_pass<true>(c, n, pl, sc, cnt, d_counts, h_counts, &dummy, &full_rev);
-  c->tm.n_sw_band_rev = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4];
+  c->tm.n_sw_band_rev = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4] + cnt[5] + cnt[6];
+  for (uint32_t t = 0; t < SWT_N_DIRECT; t++) c->tm.n_sw_rev_tier[t] = cnt[t];
   cudaEvent_t e3 = tm_mark(c);
 
   // ---- exact scalar fallback for shapes outside the fast kernels
@@ -1242,7 +1263,7 @@ static void sw_reserve(kslam_ctx *c, uint32_t n) {
   w->keys.reserve((size_t)n * sizeof(Rec16) + 64);
   w->keys2.reserve((size_t)n * sizeof(Rec16) + 64);
   w->items.reserve((size_t)(2 * ((n + 1) / 2)) * sizeof(uint2) + 64);
-  w->lists.reserve((size_t)n * 12 + 64);      // tier lists | slow list | 64-wide list of the sweep tier's failures
+  w->lists.reserve((size_t)n * 20 + 64);      // tier lists | slow list | 64- / 96- / 128-wide lists of the sweep tier's failures
   w->tier.reserve((size_t)n * 2 + 64);        // work-list tier of every alignment: forward | reverse
   c->counters.reserve(64 * 8); c->h_counters.reserve(64 * 8);
   w->n = n;
@@ -1253,6 +1274,8 @@ static void sw_reset_timers(kslam_ctx *c) {
   c->tm.sw_cells_forward = c->tm.sw_cells_reverse = 0;
   c->tm.n_sw_fast = c->tm.n_sw_slow = c->tm.n_sw_band = c->tm.n_sw_band64 = c->tm.n_sw_band_rev = 0; c->tm.n_traceback_dp = 0;
   c->tm.n_sw_tier8 = c->tm.n_sw_tier16 = c->tm.n_sw_tier32 = c->tm.n_sw_tier48 = c->tm.n_sw_tier64 = c->tm.n_sw_sweep32 = 0; c->tm.sw_cells_computed = 0;
+  c->tm.n_sw_tier96 = c->tm.n_sw_tier128 = 0;
+  for (uint32_t t = 0; t < 7; t++) c->tm.n_sw_rev_tier[t] = 0;
 }
 
 // ---- CIGAR pool compaction: the traceback writes alignment i's ops at the fixed stride i * cigar_cap; almost every

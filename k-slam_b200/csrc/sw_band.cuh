@@ -12,7 +12,8 @@
 //     else the full-matrix kernel k_sw_fast).
 //   MODE 2 (forward, lower bound S' known): band placed at c0 = -(m - a'); it contains every alignment scoring
 //     >= S', so the sweep is exact without a further check (the check is still evaluated; a failure would fall back).
-//   MODE 1 (reverse pass, ssw.c:905-923): S is known, the band is exactly [-(rows - a), cols - a].
+//   MODE 1 (reverse pass, ssw.c:905-923): S is known and every alignment scoring S starts at the reversed origin, so
+//     the band is the interval an anchored path can reach (reverse_band below), about half of [-(rows - a), cols - a].
 //
 // Mapping: ONE THREAD owns two alignments (halves of s16x2 registers) and keeps the band's previous row (H), the
 // vertical-gap state (V) and W PRMT column selectors in registers; it walks the rows, W cells per row fully
@@ -26,13 +27,13 @@
 
 #define SWB_MAXROWS 160
 #define SWB_BLOCK 64
-#define SWB_MAXW 64
+#define SWB_MAXW 128
 
 // shared-memory selector streams of one CTA, word w of thread t at [w * SWB_BLOCK + t] (conflict-free): per alignment
 // (SWB_MAXROWS + W + 4) column-selector bytes, plus one byte per query row holding both alignments' row codes
-template <int W> struct BandSmem {
-  static constexpr int COLW = (SWB_MAXROWS + W + 4 + 3) / 4;
-  static constexpr int QW = (SWB_MAXROWS + 4 + 3) / 4;
+template <int W> struct BandSmem {      // W = slots per lane; + 4: the lanes of a multi-lane band lag up to 3 rows
+  static constexpr int COLW = (SWB_MAXROWS + 4 + W + 4 + 3) / 4;
+  static constexpr int QW = (SWB_MAXROWS + 4 + 4 + 3) / 4;
   static constexpr int WORDS = 2 * COLW + QW;
   static constexpr size_t BYTES = (size_t)WORDS * SWB_BLOCK * 4;
 };
@@ -45,6 +46,15 @@ __device__ __forceinline__ uint32_t list_slot(uint32_t *counter) {
   const uint32_t peers = __activemask(), lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
   uint32_t base = 0;
   if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  return base + __popc(peers & ((1u << lane) - 1u));
+}
+
+// the same with one counter per key: the lanes here together are grouped by key first
+__device__ __forceinline__ uint32_t list_slot_keyed(uint32_t *counters, uint32_t key) {
+  const uint32_t peers = __match_any_sync(__activemask(), key), lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(counters + key, (uint32_t)__popc(peers));
   base = __shfl_sync(peers, base, leader);
   return base + __popc(peers & ((1u << lane) - 1u));
 }
@@ -75,6 +85,35 @@ __device__ __forceinline__ uint64_t reverse_pairs(uint64_t e) {     // 2-bit gro
   return ((e >> 1) & 0x5555555555555555ull) | ((e & 0x5555555555555555ull) << 1);
 }
 
+// ---- reverse pass: the band an ANCHORED alignment can reach -------------------------------------------------
+// The reverse sweep (ssw.c:905-923) runs over the reversed prefixes read[0..read_end], ref[0..ref_end] and looks for the
+// first column holding a cell with H == S, S the forward score. Every alignment scoring S inside that prefix rectangle
+// ends exactly at (read_end, ref_end): the forward pass took the FIRST column attaining S and the SMALLEST row in it
+// (ssw.c:316-342), so none can end in an earlier column or row. In the reversed matrix all of them therefore start at the
+// origin, offset 0, and one that touches offset d > 0 holds at least d horizontal gap bases — cost >= gapOpen +
+// (d - 1) gapExtend, one gap being the cheapest way to get there while gapExtend <= gapOpen (always true where these
+// kernels run, kslam_params_fast) — and has at most min(rows, cols - d) diagonal steps. It can only score S if
+//     match * min(rows, cols - d) - gapOpen - (d - 1) gapExtend >= S.
+// anchored_reach() is the largest such d (0: the path stays on the main diagonal); the same with rows and columns swapped
+// bounds the negative offsets. The interval is about half of [-(rows - a), cols - a], which ignores both the anchor and
+// the gap costs, so most reverse sweeps drop one tier. The in-band cells are a lower bound of the true H (paths leaving
+// the band are cut) and never exceed S, so a cell equals S iff an S-path reaches it: the set SSW's rule looks at.
+__host__ __device__ __forceinline__ int32_t anchored_reach(int32_t other, int32_t shrinking, int32_t S, int32_t match, int32_t go, int32_t ge) {
+  const int32_t nb = match * shrinking - go + ge - S;      // match (shrinking - d) - go - (d - 1) ge >= S
+  const int32_t na = match * other - go - S;               // match other - go - (d - 1) ge >= S
+  if (nb < 0 || na < 0) return 0;
+  int32_t d = nb / (match + ge);
+  if (ge > 0) { const int32_t da = 1 + na / ge; d = d < da ? d : da; }
+  if (d > shrinking - 1) d = shrinking - 1;
+  return d > 0 ? d : 0;
+}
+// offsets [lo, hi] of the reverse band of an alignment scoring S whose reversed prefixes are rows x cols
+__host__ __device__ __forceinline__ void reverse_band(int32_t rows, int32_t cols, int32_t S, const SwScore &sc, int32_t *lo, int32_t *hi) {
+  if (!sc.anchored) { const int32_t a = (S + sc.match - 1) / sc.match; *lo = -(rows - a); *hi = cols - a; return; }
+  *hi = anchored_reach(rows, cols, S, sc.match, sc.gap_open, sc.gap_extend);
+  *lo = -anchored_reach(cols, rows, S, sc.match, sc.gap_open, sc.gap_extend);
+}
+
 // geometry of one alignment inside the band sweep
 struct BandGeo { int32_t rows, cols, c0; };
 
@@ -83,7 +122,8 @@ __device__ __forceinline__ BandGeo band_geo(const SwTask &t, const SwRes &r, con
   BandGeo g;
   if (MODE == 1) {
     g.rows = r.read_end + 1; g.cols = r.ref_end + 1;
-    g.c0 = -(g.rows - ceil_div_pos(r.score, sc.match));
+    int32_t hi;
+    reverse_band(g.rows, g.cols, r.score, sc, &g.c0, &hi);
   } else {
     g.rows = (int32_t)t.m; g.cols = (int32_t)t.n;
     if (MODE == 0) g.c0 = ((g.cols - g.rows) >> 1) - W / 2;   // centre of [-(m - a), n - a] is (n - m) / 2 whatever a is
@@ -169,34 +209,55 @@ __device__ __forceinline__ void q_group(const SwPlanes &pl, const SwTask &t, int
   }
 }
 
-// Slot pairs (2p, 2p+1) of `list` share a thread. Failures go to next_list (the 64-wide tier; score lower bound left in
-// res[].score) when the interval they need is <= SWB_MAXW wide, else to fb_keys (full-matrix kernel, key = columns).
-template <int MODE, int W>
-__global__ void __launch_bounds__(SWB_BLOCK, (W > 32 ? 4 : 6))
+// Slot pairs (2p, 2p+1) of `list` share a thread group. Failures of the sweep-and-verify tier go to one of the next lists
+// (list k of next_list, stride next_stride: the 64- / 96- / 128-wide tiers; the score lower bound is left in res[].score)
+// when the interval they need fits that tier, else to fb_keys (full-matrix kernel, key = columns).
+//
+// PARTS > 1: the band is PARTS x WP diagonals wide and PARTS neighbouring lanes share it, lane `part` owning slots
+// [part * WP, (part + 1) * WP). A cell needs its left neighbour of the same row (horizontal gap), the cell above-right
+// in band coordinates (vertical gap) and its own slot of the row above (diagonal), so lane `part` runs `part` rows
+// behind lane 0: at step s it works on row s - part, takes the horizontal-gap state its left neighbour left at the end of
+// step s - 1 (same row) and, after its FIRST cell, hands that cell's vertical-gap output to its left neighbour, whose
+// LAST cell of this step (one row further down, one column to the left in band terms = the same matrix column) is the
+// one that needs it. Two shuffles per row and lane; everything else is the one-lane sweep with c0 advanced by
+// part * (WP - 1) and the query rows delayed by `part`.
+template <int MODE, int WP, int PARTS>
+__global__ void __launch_bounds__(SWB_BLOCK, (WP > 32 ? 4 : 6))
 k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, uint32_t n_list, SwPlanes pl, SwScore sc,
           SwRes *__restrict__ res, Rec16 *__restrict__ fb_keys, uint32_t *__restrict__ fb_count,
-          uint32_t *__restrict__ next_list, uint32_t *__restrict__ next_count, uint32_t one /* == 1, opaque to ptxas */) {
+          uint32_t *__restrict__ next_list, uint32_t *__restrict__ next_count, uint32_t next_stride, uint32_t one /* == 1, opaque to ptxas */) {
   constexpr bool REVERSE = MODE == 1;
-  constexpr int NH = (W + 31) / 32;            // tracking keys per 32-slot half
-  constexpr int COLW = BandSmem<W>::COLW;
+  constexpr int W = WP * PARTS;                // diagonals of the whole band
+  constexpr int NH = (WP + 31) / 32;           // tracking keys per 32-slot half
+  constexpr int COLW = BandSmem<WP>::COLW;
+  constexpr int GPW = 32 / PARTS;              // lane groups per warp (PARTS = 3 leaves two lanes idle)
   extern __shared__ uint32_t smem[];
   uint32_t *colA = smem + threadIdx.x, *colB = colA + COLW * SWB_BLOCK, *qAB = colB + COLW * SWB_BLOCK;
-  const uint32_t p = blockIdx.x * SWB_BLOCK + threadIdx.x;
-  if (2 * p >= n_list) return;
+  const uint32_t lane = threadIdx.x & 31, part = PARTS == 1 ? 0u : lane % PARTS;
+  uint32_t p;
+  if (PARTS == 1) p = blockIdx.x * SWB_BLOCK + threadIdx.x;
+  else {
+    if (lane >= GPW * PARTS) return;
+    p = (blockIdx.x * (SWB_BLOCK / 32) + (threadIdx.x >> 5)) * GPW + lane / PARTS;
+  }
+  if (2 * p >= n_list) return;                 // a whole group leaves together
+  const uint32_t gmask = PARTS == 1 ? 0u : (((1u << PARTS) - 1u) << (lane - part));
   const bool single = 2 * p + 1 >= n_list;
   const uint32_t ia = list[2 * p], ib = single ? ia : list[2 * p + 1];
   const SwTask ta = tasks[ia], tb = tasks[ib];
   SwRes ra, rb;
   if (MODE != 0) { ra = res[ia]; rb = res[ib]; }
-  const BandGeo ga = band_geo<MODE, W>(ta, ra, sc), gb = band_geo<MODE, W>(tb, rb, sc);
+  BandGeo ga = band_geo<MODE, W>(ta, ra, sc), gb = band_geo<MODE, W>(tb, rb, sc);
   const int32_t rows[2] = {ga.rows, gb.rows}, cols[2] = {ga.cols, gb.cols}, c0[2] = {ga.c0, gb.c0};
   const int32_t rows_max = rows[0] > rows[1] ? rows[0] : rows[1];
-  const int32_t rows4 = (rows_max + 3) & ~3;                   // the sweep runs whole groups of four rows
+  const int32_t rows4 = (rows_max + (PARTS - 1) + 3) & ~3;     // steps of the sweep, whole groups of four (lane `part` lags `part` rows)
+  const int32_t slot0 = (int32_t)part * WP;                    // first band slot of this lane
+  ga.c0 += (int32_t)part * (WP - 1); gb.c0 += (int32_t)part * (WP - 1);   // step s, local slot t <-> column s + t + c0
 
   // ---- unpack this thread's selector streams (low half = alignment A, high half = B; an unpaired last slot runs the
   // same alignment in both halves and drops the second result)
-  fill_col_stream<MODE>(pl, ta, ra, ga, false, rows4 + W, colA);
-  fill_col_stream<MODE>(pl, tb, rb, gb, true, rows4 + W, colB);
+  fill_col_stream<MODE>(pl, ta, ra, ga, false, rows4 + WP, colA);
+  fill_col_stream<MODE>(pl, tb, rb, gb, true, rows4 + WP, colB);
   for (int32_t g = 0; 32 * g < rows4 + 4; g++) {
     uint32_t qa[8], qb[8];
     q_group<MODE>(pl, ta, rows[0], g, qa);
@@ -218,9 +279,9 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
   const uint32_t KB = sw_bias(sc), K2 = KB * 0x10001u;
   const uint32_t NEG_GO32 = (uint32_t)(-(int32_t)(sc.gap_open * 32) * 0x10001);
 
-  uint32_t H[W], V[W], sel[W];
+  uint32_t H[WP], V[WP], sel[WP];
 #pragma unroll
-  for (int t = 0; t < W; t += 4) {
+  for (int t = 0; t < WP; t += 4) {
     const uint32_t wa = colA[(size_t)(t / 4) * SWB_BLOCK], wb = colB[(size_t)(t / 4) * SWB_BLOCK];
 #pragma unroll
     for (int r = 0; r < 4; r++) { H[t + r] = K2; V[t + r] = K2; sel[t + r] = prmt(wa, wb, (uint32_t)(((4 + r) << 4) | r)); }
@@ -230,21 +291,25 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
   uint32_t keyA = KB + 31u, keyB = KB + 31u, infoA = 0, infoB = 0;
   uint32_t rcolA = 0xffffffffu, rcolB = 0xffffffffu;
   const uint32_t thrA = REVERSE ? (uint32_t)ra.score * 32u + KB : 0u, thrB = REVERSE ? (uint32_t)rb.score * 32u + KB : 0u;
+  uint32_t e_end = K2, qprev = 0x55555555u;                   // (row code 5 for both alignments: the rows before row 0)
+  const uint32_t qshift = 0x7654u - 0x1111u * part;           // bytes of {qprev, qcur} holding rows s - part .. s - part + 3
   for (int32_t i0 = 0; i0 < rows4; i0 += 4) {
-    const uint32_t qword = qAB[(size_t)(i0 / 4) * SWB_BLOCK];
-    const uint32_t ewa = colA[(size_t)((i0 + W) / 4) * SWB_BLOCK], ewb = colB[(size_t)((i0 + W) / 4) * SWB_BLOCK];
+    uint32_t qword = qAB[(size_t)(i0 / 4) * SWB_BLOCK];
+    if (PARTS > 1) { const uint32_t qcur = qword; qword = __byte_perm(qprev, qcur, qshift); qprev = qcur; }
+    const uint32_t ewa = colA[(size_t)((i0 + WP) / 4) * SWB_BLOCK], ewb = colB[(size_t)((i0 + WP) / 4) * SWB_BLOCK];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-      const int32_t i = i0 + r;
+      const int32_t i = i0 + r - (int32_t)part;               // the matrix row this lane works on (negative: not started)
       // row profiles [s(q,A) s(q,C) s(q,G) s(q,T)] x 32 of both alignments from the row's code byte, PRMTs only
       const uint32_t codes = prmt(qword, 0u, 0x4440u | (uint32_t)r);
       const uint32_t q32 = prmt(QSRC, 0u, prmt(QLUT0, QLUT1, codes));
       const uint32_t PA = prmt(PSRC, 0u, q32), PB = prmt(PSRC, 0u, q32 >> 16);
       uint32_t e = K2, acc[NH];
+      if (PARTS > 1) { const uint32_t left = __shfl_sync(gmask, e_end, part ? lane - 1 : lane); if (part) e = left; }
 #pragma unroll
       for (int h = 0; h < NH; h++) acc[h] = 0;
 #pragma unroll
-      for (int t = 0; t < W; t++) {
+      for (int t = 0; t < WP; t++) {
         const uint32_t s = prmt(PA, PB, sel[t]);
         const uint32_t v = V[t];
         uint32_t h = __viaddmax_s16x2(H[t], s, v);                // max(H[i-1][j-1] + s, vertical gap)
@@ -253,12 +318,17 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
         const uint32_t hgo = mad_add(h, one, NEG_GO32);             // H - gapOpen in both halves, on the FMA pipe
         e = __viaddmax_s16x2(e, NEG_GE, hgo);                      // horizontal gap into (i, j+1)
         if (t > 0) V[t - 1] = __viaddmax_s16x2(v, NEG_GE, hgo);    // vertical gap into (i+1, j): band slot t-1 next row
+        else if (PARTS > 1) {                                      // ... which for slot 0 is the left neighbour's last slot, this step
+          const uint32_t down = __shfl_sync(gmask, __viaddmax_s16x2(v, NEG_GE, hgo), part + 1 < PARTS ? lane + 1 : lane);
+          V[WP - 1] = part + 1 < PARTS ? down : K2;
+        }
         acc[t / 32] = __viaddmax_s16x2(h, (uint32_t)(31 - (t & 31)) * 0x10001u, acc[t / 32]);   // H*32 + (31 - slot): smallest column wins ties
       }
+      e_end = e;
       // slide the column selectors: next row's slot t is this row's slot t+1; the last slot takes the entering column
 #pragma unroll
-      for (int t = 0; t < W - 1; t++) sel[t] = sel[t + 1];
-      sel[W - 1] = prmt(ewa, ewb, (uint32_t)(((4 + r) << 4) | r));
+      for (int t = 0; t < WP - 1; t++) sel[t] = sel[t + 1];
+      sel[WP - 1] = prmt(ewa, ewb, (uint32_t)(((4 + r) << 4) | r));
       // row winners -> running best. SSW's rule: first column attaining the maximum, then the smallest row
       // (ssw.c:316-342). Rows only grow, so a strictly larger score always wins (the common, branch-free path) and an
       // equal score wins only with a strictly smaller column.
@@ -266,12 +336,12 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
       for (int h = 0; h < NH; h++) {
         const uint32_t aA = acc[h] & 0xffffu, aB = acc[h] >> 16;
         if (REVERSE) {
-          if (aA >= thrA) { const uint32_t j = (uint32_t)(i + 32 * h + (int32_t)(31u - (aA & 31u)) + c0[0]);
+          if (aA >= thrA) { const uint32_t j = (uint32_t)(i + slot0 + 32 * h + (int32_t)(31u - (aA & 31u)) + c0[0]);
                             if (j < rcolA && j < 4096u) { rcolA = j; infoA = (uint32_t)i; } }
-          if (aB >= thrB) { const uint32_t j = (uint32_t)(i + 32 * h + (int32_t)(31u - (aB & 31u)) + c0[1]);
+          if (aB >= thrB) { const uint32_t j = (uint32_t)(i + slot0 + 32 * h + (int32_t)(31u - (aB & 31u)) + c0[1]);
                             if (j < rcolB && j < 4096u) { rcolB = j; infoB = (uint32_t)i; } }
         } else {
-          const uint32_t nA = ((uint32_t)i << 8) | ((uint32_t)(32 * h + 31) - (aA & 31u)), nB = ((uint32_t)i << 8) | ((uint32_t)(32 * h + 31) - (aB & 31u));
+          const uint32_t nA = ((uint32_t)i << 8) | ((uint32_t)(slot0 + 32 * h + 31) - (aA & 31u)), nB = ((uint32_t)i << 8) | ((uint32_t)(slot0 + 32 * h + 31) - (aB & 31u));
           if (aA > keyA) { keyA = aA | 31u; infoA = nA; }
           else if ((aA | 31u) == keyA && aA > KB + 31u && (nA >> 8) + (nA & 255u) < (infoA >> 8) + (infoA & 255u)) infoA = nA;
           if (aB > keyB) { keyB = aB | 31u; infoB = nB; }
@@ -281,35 +351,58 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
     }
   }
 
+  // ---- per-lane winners as one comparable word: forward score << 20 | (1023 - column) << 10 | (1023 - row), reverse
+  // 1 << 31 | (4095 - column) << 12 | (4095 - row); 0 = nothing. The lanes of a group keep the largest.
+  uint32_t win[2];
+#pragma unroll
+  for (int al = 0; al < 2; al++) {
+    if (REVERSE) {
+      const uint32_t rcol = al ? rcolB : rcolA, rrow = al ? infoB : infoA;
+      win[al] = rcol != 0xffffffffu ? (0x80000000u | ((4095u - rcol) << 12) | (4095u - rrow)) : 0u;
+    } else {
+      const uint32_t key = al ? keyB : keyA, info = al ? infoB : infoA;
+      const uint32_t S = (key - KB) >> 5, brow = info >> 8, bcol = (uint32_t)((int32_t)brow + (int32_t)(info & 255u) + c0[al]);
+      win[al] = S > 0 ? ((S << 20) | ((1023u - bcol) << 10) | (1023u - brow)) : 0u;
+    }
+    if (PARTS > 1) {
+#pragma unroll
+      for (int k = 1; k < PARTS; k++) {
+        const uint32_t o = __shfl_sync(gmask, win[al], lane - part + (part + k) % PARTS);
+        win[al] = win[al] > o ? win[al] : o;
+      }
+    }
+  }
+  if (part != 0) return;
+
 #pragma unroll
   for (int al = 0; al < 2; al++) {
     if (al == 1 && single) break;
     const uint32_t idx = al ? ib : ia;
     if (REVERSE) {
       const SwRes &r0 = al ? rb : ra;
-      const uint32_t rcol = al ? rcolB : rcolA, rrow = al ? infoB : infoA;
-      if (rcol != 0xffffffffu) {
-        res[idx].ref_begin = r0.ref_end - (int32_t)rcol;
-        res[idx].read_begin = r0.read_end - (int32_t)rrow;
+      if (win[al]) {
+        res[idx].ref_begin = r0.ref_end - (int32_t)(4095u - ((win[al] >> 12) & 4095u));
+        res[idx].read_begin = r0.read_end - (int32_t)(4095u - (win[al] & 4095u));
         res[idx].flags = r0.flags | SWR_REV_TIER(SWR_TIER_OF_W(W));
       } else {                      // cannot happen when the bound holds; never guess: hand over to the full kernel
         const uint32_t k = list_slot(fb_count);
         fb_keys[k].key = (uint64_t)(r0.ref_end + 1); fb_keys[k].val = idx;
       }
     } else {
-      const uint32_t key = al ? keyB : keyA, info = al ? infoB : infoA;
-      const int32_t S = (int32_t)((key - KB) >> 5);
-      const int32_t brow = (int32_t)(info >> 8), bcol = brow + (int32_t)(info & 255u) + c0[al];
+      const int32_t S = (int32_t)(win[al] >> 20);
+      const int32_t bcol = (int32_t)(1023u - ((win[al] >> 10) & 1023u)), brow = (int32_t)(1023u - (win[al] & 1023u));
       const int32_t a = ceil_div_pos(S, sc.match);
       const bool proven = S > 0 && c0[al] <= -(rows[al] - a) && (cols[al] - a) <= c0[al] + (W - 1);
+      const int32_t need = rows[al] + cols[al] - 2 * a + 1;      // width of the interval every alignment scoring >= S lies in
       if (proven) {
         SwRes o;
         o.flags = SWR_FWD_TIER(SWR_TIER_OF_W(W)); o.pad0 = o.pad1 = 0; o.ref_begin = -1; o.read_begin = 0;
         o.score = S; o.ref_end = bcol; o.read_end = brow;
         res[idx] = o;
-      } else if (MODE == 0 && next_list && S > 0 && rows[al] + cols[al] - 2 * a + 1 <= SWB_MAXW) {
+      } else if (MODE == 0 && next_list && S > 0 && need <= (int32_t)sc.max_band) {
         res[idx].score = S;         // lower bound: every alignment scoring >= S lies in [-(m - a), n - a]
-        next_list[list_slot(next_count)] = idx;
+        const uint32_t k = need <= 64 ? 0u : need <= 96 ? 1u : 2u;
+        next_list[(size_t)k * next_stride + list_slot_keyed(next_count, k)] = idx;
       } else {
         const uint32_t k = list_slot(fb_count);
         fb_keys[k].key = (uint64_t)(al ? tb.n : ta.n); fb_keys[k].val = idx;

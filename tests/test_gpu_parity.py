@@ -340,6 +340,68 @@ def test_ssw_ragged_lengths_and_repeats(pkg):
         check_overlaps(out, pool, want, wpool, fields=FIELDS[4:])
 
 
+def diverged_pairs(pkg, n, read_len, window_len, seed):
+    """(read, window) pairs whose optimal alignments need every band tier: per-pair substitution rate 0-30 %, 0-4 indels
+    of 1-12 bases, a quarter of the reads keep only a prefix / suffix of the planted copy (partial hits), some windows
+    carry a tandem repeat (ties between begin positions)."""
+    rng = np.random.default_rng(seed)
+    ACGT = pkg.synth.ACGT
+    qs, rs = [], []
+    for _ in range(n):
+        w = ACGT[rng.integers(0, 4, size=window_len)]
+        if rng.random() < 0.1:
+            per = int(rng.integers(1, 9)); st = int(rng.integers(0, window_len - 40)); ln = int(rng.integers(20, 80))
+            w[st:st + ln] = np.tile(w[st:st + per], ln // per + 1)[:len(w[st:st + ln])]
+        off = int(rng.integers(0, max(1, window_len - read_len + 1)))     # a window shorter than the read: the read is padded below
+        src = list(w[off:off + read_len])
+        for _k in range(int(rng.integers(0, 5))):
+            pos = int(rng.integers(5, max(6, len(src) - 5))); ln = int(rng.integers(1, 13))
+            if rng.random() < 0.5:
+                del src[pos:pos + ln]
+            else:
+                src[pos:pos] = list(ACGT[rng.integers(0, 4, size=ln)])
+        q = np.array(src[:read_len], dtype=np.uint8)
+        if len(q) < read_len:
+            q = np.concatenate([q, ACGT[rng.integers(0, 4, size=read_len - len(q))]])
+        rate = rng.random() * 0.3
+        m = rng.random(read_len) < rate
+        q[m] = ACGT[rng.integers(0, 4, size=int(m.sum()))]
+        u = rng.random()
+        if u < 0.125:
+            k = int(rng.integers(20, read_len - 20)); q[k:] = ACGT[rng.integers(0, 4, size=read_len - k)]
+        elif u < 0.25:
+            k = int(rng.integers(20, read_len - 20)); q[:k] = ACGT[rng.integers(0, 4, size=k)]
+        qs.append(q); rs.append(w)
+    q, qo = T.concat(qs); r, ro = T.concat(rs)
+    return q, qo, r, ro
+
+
+@pytest.mark.parametrize("shape", [(150, 150), (150, 190), (120, 160), (160, 100)])
+@pytest.mark.parametrize("cigar", [0, 1])
+def test_ssw_diverged_reads_use_every_band_tier(pkg, shape, cigar):
+    """Diverged, gapped and partial hits against the oracle: the forward intervals [-(m - a), n - a] of such alignments are
+    65-128 diagonals wide (the multi-lane tiers) and their reverse sweeps run in the anchored band (sw_band.cuh), which must
+    find the same begin coordinates as SSW's full reverse pass."""
+    q, qo, r, ro = diverged_pairs(pkg, 12_000, shape[0], shape[1], seed=500 + shape[0] + shape[1] + cigar)
+    P = T.default_params(report_cigar=cigar)
+    want, wpool = T.ko_ssw_batch(q, qo, r, ro, P, cigar_cap=64)
+    res = {}
+    for band in (0, 3):
+        with pkg.Aligner(report_cigar=bool(cigar), max_cigar_ops=64) as al:
+            al.set_sw_band(band)
+            out, pool = al.ssw_batch(q, qo, r, ro)
+            res[band] = al.timings()
+        check_overlaps(out, pool, want, wpool, fields=FIELDS[4:], cigars=bool(cigar))
+    tm = res[3]
+    assert tm["n_sw_slow"] == 0
+    if shape == (150, 150):
+        assert tm["n_sw_tier96"] > 100 and tm["n_sw_tier128"] > 100, tm        # direct, from the seed-diagonal bound
+    assert tm["n_sw_tier96"] + tm["n_sw_tier128"] + tm["n_sw_band64"] > 100, tm  # ... or after the 32-wide trial sweep
+    rev = tm["n_sw_rev_tier"]
+    assert sum(rev) > 8_000 and rev[0] > 500 and rev[4] + rev[5] + rev[6] > 100, rev
+    assert tm["sw_cells_computed"] < res[0]["sw_cells_computed"]
+
+
 def test_radix_sort_matches_numpy(pkg):
     rng = np.random.default_rng(3)
     with pkg.Aligner() as al:
