@@ -101,7 +101,8 @@ typedef struct {
   uint64_t sw_cells_forward, sw_cells_reverse, sw_cells_computed, n_sw_fast, n_sw_slow, n_sw_band, n_sw_band64, n_sw_band_rev, n_traceback_dp, n_pairs;
   uint64_t n_sw_tier8, n_sw_tier16, n_sw_tier32, n_sw_tier48, n_sw_tier64, n_sw_sweep32; /* forward work-list tiers */
   uint64_t n_sw_tier96, n_sw_tier128;  /* forward tiers swept by three / four lanes of 32 diagonals */
-  uint64_t n_sw_rev_tier[7];           /* reverse work-list tiers: 8 / 16 / 32 / 48 / 64 / 96 / 128 diagonals */
+  uint64_t n_sw_fwd_tier[12];          /* alignments per forward band tier: 8 16 24 32 40 48 56 64 72 80 96 128 diagonals */
+  uint64_t n_sw_rev_tier[12];          /* ... and per reverse band tier */
   uint64_t kernel_launches;
 } kslam_timings;
 

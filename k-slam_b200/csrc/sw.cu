@@ -55,21 +55,26 @@ struct __align__(16) SwTask {
 
 struct __align__(16) SwRes {
   int32_t score, ref_end, read_end, ref_begin, read_begin;
-  uint32_t flags, pad0, pad1;   // flags: low byte = KSLAM_FLAG_*, bits 8-10 forward tier, bits 11-13 reverse tier
+  uint32_t flags, pad0, pad1;   // flags: low byte = KSLAM_FLAG_*, bits 8-11 forward tier code, bits 12-15 reverse tier code
 };
-// tier code of the sweep that produced the result: 0 = full-matrix / scalar kernel, 1..4 = band of 8 / 16 / 32 / 64
-// diagonals, 5 = 48, 6 = 96, 7 = 128 diagonals
-#define SWR_TIER_OF_W(W) ((W) == 8 ? 1u : (W) == 16 ? 2u : (W) == 32 ? 3u : (W) == 64 ? 4u : (W) == 48 ? 5u : (W) == 96 ? 6u : 7u)
-#define SWR_FWD_TIER(t) ((uint32_t)(t) << 8)
-#define SWR_REV_TIER(t) ((uint32_t)(t) << 11)
-// work-list tier of an alignment (byte arrays tier_f / tier_r): 0..6 = band of 8 / 16 / 32 / 48 / 64 / 96 / 128 diagonals
-// placed exactly on the interval a known score bound allows (no verification needed; 96 and 128 are swept by three / four
-// lanes of 32 slots each), 7 = 32 diagonals centred, sweep-and-verify, 255 = not in a band list
-#define SWT_N_DIRECT 7u
-#define SWT_TIER_SWEEP 7u
-#define SWT_N_TIERS 8u
+// Work-list tier of an alignment (byte arrays tier_f / tier_r): a band of tier_width(t) diagonals placed exactly on the
+// interval a known score bound allows (no verification needed):
+//   t         0   1   2   3   4     5     6     7     8     9     10    11
+//   diagonals 8   16  24  32  40    48    56    64    72    80    96    128
+//   lanes     1   1   1   1   2x20  2x24  2x28  2x32  3x24  4x20  3x32  4x32      (k_sw_band<MODE, slots per lane, lanes>)
+// 12 = 32 diagonals centred, sweep-and-verify; 255 = not in a band list. A forward tier byte with SWT_SWEPT set: the
+// alignment went through the 32-wide trial sweep first and then into that tier with the score the sweep found as its bound.
+// Tier code in SwRes.flags: tier + 1, 0 = full-matrix / scalar kernel.
+#define SWT_N_DIRECT 12u
+#define SWT_TIER_SWEEP 12u
+#define SWT_N_TIERS 13u
+#define SWT_SWEPT 0x40u
 #define SWT_TIER_NONE 255u
-__host__ __device__ __forceinline__ uint32_t tier_width(uint32_t t) { return t == 0 ? 8u : t == 1 ? 16u : t == 2 ? 32u : t == 3 ? 48u : t == 4 ? 64u : t == 5 ? 96u : 128u; }
+#define SWR_FWD_TIER(code) ((uint32_t)(code) << 8)
+#define SWR_REV_TIER(code) ((uint32_t)(code) << 12)
+__host__ __device__ __forceinline__ constexpr uint32_t tier_width(uint32_t t) { return t < 8 ? 8u * (t + 1) : t == 8 ? 72u : t == 9 ? 80u : t == 10 ? 96u : 128u; }
+__host__ __device__ __forceinline__ constexpr uint32_t tier_of_band_width(uint32_t w) { return w <= 64 ? (w + 7) / 8 - 1 : w <= 72 ? 8u : w <= 80 ? 9u : w <= 96 ? 10u : 11u; }
+#define SWR_TIER_OF_W(W) (tier_of_band_width(W) + 1u)
 
 struct SwPlanes {
   const uint64_t *q_sbits; const uint32_t *q_nmask;
@@ -126,6 +131,28 @@ __device__ __forceinline__ uint32_t mad_add(uint32_t a, uint32_t one, uint32_t c
   asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(c));
   return d;
 }
+
+// smallest tier whose band holds an interval of `width` diagonals; SWT_TIER_NONE when nothing allowed does.
+// level: 1 = 32 only, 2 = 32 and 64, 3 = every width.
+__host__ __device__ __forceinline__ uint32_t tier_of_interval(int32_t width, uint32_t level, const SwScore &sc) {
+  if (width > (int32_t)sc.max_band) return SWT_TIER_NONE;
+  if (level >= 3) return tier_of_band_width((uint32_t)(width > 0 ? width : 1));
+  if (width <= 32) return 3u;
+  return (level >= 2 && width <= 64) ? 7u : SWT_TIER_NONE;
+}
+
+// counters (u32) in c->counters + 32
+#define CNT_BAND 0
+#define CNT_FULL 1
+#define CNT_SLOW 2
+#define CNT_RETRY 4
+#define CNT_EXTRA 5
+#define CNT_OVERFLOW 7   // alignments whose CIGAR has more ops than the pool stride (KSLAM_FLAG_CIGAR_OVERFLOW)
+#define CNT_NEXT 8       // failures of the sweep tier that go on to a direct tier (second round)
+#define CNT_TIER 16      // SWT_N_TIERS counters: alignments per work-list tier
+#define CNT_CUR 32       // SWT_N_TIERS cursors of k_tier_scatter
+#define CNT_TIER2 48     // SWT_N_DIRECT counters: second-round alignments per tier
+#define CNT_WORDS 64
 
 #include "sw_band.cuh"
 
@@ -708,18 +735,6 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
 }
 
 // ---------------------------------------------------------------- task preparation and work lists
-// counters (u32) in c->counters + 32: [0] band list, [1] full-kernel keys, [2] slow list, [3] band fallbacks,
-// [4] traceback retries, [5] make_items extras
-#define CNT_BAND 0
-#define CNT_FULL 1
-#define CNT_SLOW 2
-#define CNT_RETRY 4
-#define CNT_EXTRA 5
-#define CNT_BAND64 8   // three counters: failures of the sweep tier that fit 64 / 96 / 128 diagonals
-#define CNT_OVERFLOW 7   // alignments whose CIGAR has more ops than the pool stride (KSLAM_FLAG_CIGAR_OVERFLOW)
-#define CNT_TIER 16    // SWT_N_TIERS counters: alignments per work-list tier
-#define CNT_CUR 24     // SWT_N_TIERS cursors of k_tier_scatter
-#define CNT_WORDS 32
 
 // ---- lower bound of the optimal score from the seed's own diagonal ------------------------------------------
 // Best ungapped local segment (Kadane) along matrix diagonal j = i + d0, in the orientation Align sees. It is the score
@@ -760,12 +775,6 @@ __device__ int32_t diag_lower_bound(const SwPlanes &pl, const SwTask &t, int32_t
 // smallest direct tier (0..4 = 8 / 16 / 32 / 48 / 64 diagonals) whose band holds [-(rows - a), cols - a],
 // a = ceil(score / match); SWT_TIER_NONE when the interval is wider than the widest tier allowed or the score says
 // nothing. level: 1 = 32 only, 2 = 32 and 64, 3 = all five widths.
-__device__ __forceinline__ uint32_t tier_of_interval(int32_t width, uint32_t level, const SwScore &sc) {
-  if (width > (int32_t)sc.max_band) return SWT_TIER_NONE;
-  if (level >= 3) return width <= 8 ? 0u : width <= 16 ? 1u : width <= 32 ? 2u : width <= 48 ? 3u : width <= 64 ? 4u : width <= 96 ? 5u : width <= 128 ? 6u : SWT_TIER_NONE;
-  if (width <= 32) return 2u;
-  return (level >= 2 && width <= 64) ? 4u : SWT_TIER_NONE;
-}
 __device__ __forceinline__ uint32_t tier_of_width(int32_t rows, int32_t cols, int32_t score, const SwScore &sc, uint32_t level) {
   if (score <= 0) return SWT_TIER_NONE;
   return tier_of_interval(rows + cols - 2 * ceil_div_pos(score, sc.match) + 1, level, sc);
@@ -843,13 +852,16 @@ __device__ __forceinline__ uint32_t enlist(const SwPlanes &pl, const SwTask &t, 
 }
 
 // tier byte array -> one list per tier inside `list` (tier t starts at offs[t]); order inside a list is arbitrary
+// (src: the alignments to list, nullptr = all of 0..n-1; counts: the per-tier totals the lists are laid out by)
 __global__ void __launch_bounds__(256)
-k_tier_scatter(const uint8_t *__restrict__ tier, uint32_t n, const uint32_t *__restrict__ counts, uint32_t *__restrict__ cursors,
-               uint32_t *__restrict__ list) {
+k_tier_scatter(const uint8_t *__restrict__ tier, const uint32_t *__restrict__ src, uint32_t n, const uint32_t *__restrict__ counts,
+               uint32_t *__restrict__ cursors, uint32_t *__restrict__ list) {
   __shared__ uint32_t s_wcnt[8][SWT_N_TIERS];          // per warp and tier: members, then the warp's offset inside the CTA's run
   __shared__ uint32_t s_base[SWT_N_TIERS];             // where the CTA's run of a tier starts in that tier's list
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t t = i < n ? tier[i] : SWT_TIER_NONE;
+  const uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t i = k0 < n ? (src ? src[k0] : k0) : 0u;
+  uint32_t t = k0 < n ? tier[i] : SWT_TIER_NONE;
+  if (t != SWT_TIER_NONE) t &= ~SWT_SWEPT;
   if (threadIdx.x < 8 * SWT_N_TIERS) (&s_wcnt[0][0])[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t peers = __match_any_sync(0xffffffffu, t);
@@ -859,7 +871,7 @@ k_tier_scatter(const uint8_t *__restrict__ tier, uint32_t n, const uint32_t *__r
     uint32_t run = 0;
     for (int w = 0; w < 8; w++) { const uint32_t c = s_wcnt[w][threadIdx.x]; s_wcnt[w][threadIdx.x] = run; run += c; }
     uint32_t off = 0;
-    for (uint32_t k = 0; k < threadIdx.x; k++) off += counts[CNT_TIER + k];
+    for (uint32_t k = 0; k < threadIdx.x; k++) off += counts[k];
     s_base[threadIdx.x] = off + (run ? atomicAdd(&cursors[threadIdx.x], run) : 0u);
   }
   __syncthreads();
@@ -981,9 +993,9 @@ k_sw_cells(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, cons
     const SwTask t = tasks[i]; const SwRes r = res[i];
     if (((t.flags >> 8) & 0xffu) > SWC_FAST32) continue;
     fw += (unsigned long long)t.m * t.n;
-    const uint32_t tf = tier_f[i], tr = tier_r[i], ft = (r.flags >> 8) & 7u;
-    if (tf < SWT_N_DIRECT) comp += (unsigned long long)tier_width(tf) * t.m;
-    if (tf == SWT_TIER_SWEEP) { comp += 32ull * t.m; if (ft == 4u) comp += 64ull * t.m; if (ft == 6u) comp += 96ull * t.m; if (ft == 7u) comp += 128ull * t.m; }
+    const uint32_t tf = tier_f[i], tr = tier_r[i], ft = (r.flags >> 8) & 15u;
+    if (tf == SWT_TIER_SWEEP || (tf != SWT_TIER_NONE && (tf & SWT_SWEPT))) comp += 32ull * t.m;      // the trial sweep
+    if (tf != SWT_TIER_NONE && (tf & ~SWT_SWEPT) < SWT_N_DIRECT) comp += (unsigned long long)tier_width(tf & ~SWT_SWEPT) * t.m;
     if (ft == 0u) comp += (unsigned long long)t.m * t.n;
     if (r.score > 0) {
       const unsigned long long rows = (unsigned long long)(r.read_end + 1), cols = (unsigned long long)(r.ref_end + 1);
@@ -1054,15 +1066,16 @@ static uint32_t read_count(kslam_ctx *c, uint32_t *d_counts, uint32_t *h_counts,
 }
 
 // one banded tier over a list: the sweep kernel unpacks its own selector streams into shared memory
+static uint32_t sw_level(const kslam_ctx *c);
 template <int MODE, int WP, int PARTS = 1>
 static void run_band(kslam_ctx *c, const SwPlanes &pl, const SwScore &sc, const uint32_t *list, uint32_t n_list,
-                     uint32_t *d_counts, uint32_t *next_list, uint32_t next_stride = 0) {
+                     uint32_t *d_counts, uint32_t *next_list) {
   if (!n_list) return;
   SwWorkspace *w = c->sw;
   const uint32_t pairs = (n_list + 1) / 2, per_block = PARTS == 1 ? SWB_BLOCK : (SWB_BLOCK / 32) * (32 / PARTS);
   const uint32_t blocks = (pairs + per_block - 1) / per_block;
   k_sw_band<MODE, WP, PARTS><<<blocks, SWB_BLOCK, BandSmem<WP>::BYTES, c->stream>>>(w->tasks.as<SwTask>(), list, n_list, pl, sc, w->res.as<SwRes>(),
-      w->keys.as<Rec16>(), d_counts + CNT_FULL, next_list, d_counts + CNT_BAND64, next_stride, 1u);
+      w->keys.as<Rec16>(), d_counts + CNT_FULL, next_list, d_counts + CNT_NEXT, w->tier.as<uint8_t>(), d_counts + CNT_TIER2, sw_level(c), 1u);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
 }
@@ -1070,16 +1083,38 @@ static void run_band(kslam_ctx *c, const SwPlanes &pl, const SwScore &sc, const 
 // 0 = full-matrix only, 1 = 32-wide sweep tier, 2 = + 64-wide tier, 3 = + direct tiers from the seed-diagonal bound
 static uint32_t sw_level(const kslam_ctx *c) { return !c->sw_band ? 0u : (!c->sw_band64 ? 1u : (c->sw_tiers ? 3u : 2u)); }
 
-// tier byte array -> per-tier lists at the front of w->lists; returns the list sizes
-static void make_tier_lists(kslam_ctx *c, uint32_t n, const uint8_t *tier, uint32_t *d_counts, uint32_t *h_counts, uint32_t cnt[SWT_N_TIERS]) {
+// one direct tier over its list (tier table: top of this file)
+template <int MODE>
+static void run_tier(kslam_ctx *c, const SwPlanes &pl, const SwScore &sc, uint32_t t, const uint32_t *list, uint32_t n_list, uint32_t *d_counts) {
+  switch (t) {
+    case 0: run_band<MODE, 8>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    case 1: run_band<MODE, 16>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    case 2: run_band<MODE, 24>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    case 3: run_band<MODE, 32>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    case 4: run_band<MODE, 20, 2>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    case 5: run_band<MODE, 24, 2>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    case 6: run_band<MODE, 28, 2>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    case 7: run_band<MODE, 32, 2>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    case 8: run_band<MODE, 24, 3>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    case 9: run_band<MODE, 20, 4>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    case 10: run_band<MODE, 32, 3>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    default: run_band<MODE, 32, 4>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+  }
+}
+
+// tier byte array -> per-tier lists in `out` (of the alignments in src, nullptr = all n); d_cnt: the per-tier totals
+static void make_tier_lists(kslam_ctx *c, uint32_t n, const uint8_t *tier, const uint32_t *src, uint32_t *d_counts, uint32_t *h_counts,
+                            uint32_t cnt_at, uint32_t n_tiers, uint32_t *out, uint32_t *cnt) {
   cudaStream_t st = c->stream;
   CUDA_TRY(cudaMemsetAsync(d_counts + CNT_CUR, 0, SWT_N_TIERS * 4, st));
-  k_tier_scatter<<<(n + 255) / 256, 256, 0, st>>>(tier, n, d_counts, d_counts + CNT_CUR, c->sw->lists.as<uint32_t>());
-  c->launches++;
-  CUDA_TRY(cudaGetLastError());
-  read_small(c, h_counts + CNT_TIER, d_counts + CNT_TIER, SWT_N_TIERS * 4);
+  if (n) {
+    k_tier_scatter<<<(n + 255) / 256, 256, 0, st>>>(tier, src, n, d_counts + cnt_at, d_counts + CNT_CUR, out);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  read_small(c, h_counts + cnt_at, d_counts + cnt_at, n_tiers * 4);
   CUDA_TRY(cudaStreamSynchronize(st));
-  for (uint32_t t = 0; t < SWT_N_TIERS; t++) cnt[t] = h_counts[CNT_TIER + t];
+  for (uint32_t t = 0; t < n_tiers; t++) cnt[t] = h_counts[cnt_at + t];
 }
 
 // one direction (forward or reverse) over the tier lists: the direct tiers (band placed exactly, 8 / 16 / 32 / 64
@@ -1092,27 +1127,20 @@ static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore 
   cudaStream_t st = c->stream;
   SwTask *tasks = w->tasks.as<SwTask>();
   SwRes *res = w->res.as<SwRes>();
-  uint32_t *lists = w->lists.as<uint32_t>(), *list64 = lists + 2 * (size_t)n;      // then the 96- and 128-wide lists, stride n
+  uint32_t *lists = w->lists.as<uint32_t>(), *next = lists + 2 * (size_t)n, *lists2 = lists + 3 * (size_t)n;
   Rec16 *keys = w->keys.as<Rec16>(), *keys2 = w->keys2.as<Rec16>();
-  uint32_t off[SWT_N_TIERS] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (uint32_t t = 1; t < SWT_N_TIERS; t++) off[t] = off[t - 1] + cnt[t - 1];
+  uint32_t off[SWT_N_TIERS + 1] = {0};
+  for (uint32_t t = 1; t <= SWT_N_TIERS; t++) off[t] = off[t - 1] + cnt[t - 1];
   constexpr int DM = REVERSE ? 1 : 2;
-  run_band<DM, 8>(c, pl, sc, lists + off[0], cnt[0], d_counts, nullptr);
-  run_band<DM, 16>(c, pl, sc, lists + off[1], cnt[1], d_counts, nullptr);
-  run_band<DM, 32>(c, pl, sc, lists + off[2], cnt[2], d_counts, nullptr);
-  run_band<DM, 48>(c, pl, sc, lists + off[3], cnt[3], d_counts, nullptr);
-  run_band<DM, 64>(c, pl, sc, lists + off[4], cnt[4], d_counts, nullptr);
-  run_band<DM, 32, 3>(c, pl, sc, lists + off[5], cnt[5], d_counts, nullptr);
-  run_band<DM, 32, 4>(c, pl, sc, lists + off[6], cnt[6], d_counts, nullptr);
+  for (uint32_t t = 0; t < SWT_N_DIRECT; t++) run_tier<DM>(c, pl, sc, t, lists + off[t], cnt[t], d_counts);
   if (!REVERSE && cnt[SWT_TIER_SWEEP]) {
-    run_band<0, 32>(c, pl, sc, lists + off[SWT_TIER_SWEEP], cnt[SWT_TIER_SWEEP], d_counts, c->sw_band64 ? list64 : nullptr, n);
-    read_small(c, h_counts + CNT_BAND64, d_counts + CNT_BAND64, 12);       // 32-wide failures that fit 64 / 96 / 128 diagonals
-    CUDA_TRY(cudaStreamSynchronize(st));
-    const uint32_t n64 = h_counts[CNT_BAND64], n96 = h_counts[CNT_BAND64 + 1], n128 = h_counts[CNT_BAND64 + 2];
-    run_band<2, 64>(c, pl, sc, list64, n64, d_counts, nullptr);
-    run_band<2, 32, 3>(c, pl, sc, list64 + (size_t)n, n96, d_counts, nullptr);
-    run_band<2, 32, 4>(c, pl, sc, list64 + 2 * (size_t)n, n128, d_counts, nullptr);
-    *n_band64_via_sweep += n64 + n96 + n128;
+    // trial sweep; what it bounds but cannot prove goes through the direct tiers once more (second round)
+    run_band<0, 32>(c, pl, sc, lists + off[SWT_TIER_SWEEP], cnt[SWT_TIER_SWEEP], d_counts, c->sw_band64 ? next : nullptr);
+    const uint32_t n_next = read_count(c, d_counts, h_counts, CNT_NEXT);
+    uint32_t cnt2[SWT_N_DIRECT], off2 = 0;
+    make_tier_lists(c, n_next, w->tier.as<uint8_t>(), next, d_counts, h_counts, CNT_TIER2, SWT_N_DIRECT, lists2, cnt2);
+    for (uint32_t t = 0; t < SWT_N_DIRECT; t++) { run_tier<2>(c, pl, sc, t, lists2 + off2, cnt2[t], d_counts); off2 += cnt2[t]; c->tm.n_sw_fwd_tier[t] += cnt2[t]; }
+    *n_band64_via_sweep += n_next;
   }
   const uint32_t n_full = read_count(c, d_counts, h_counts, CNT_FULL);
   *n_full_done += n_full;
@@ -1184,29 +1212,30 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
   // ---- forward
   cudaEvent_t e1 = tm_mark(c);
   uint32_t cnt[SWT_N_TIERS];
-  make_tier_lists(c, n, tier_f, d_counts, h_counts, cnt);
+  make_tier_lists(c, n, tier_f, nullptr, d_counts, h_counts, CNT_TIER, SWT_N_TIERS, w->lists.as<uint32_t>(), cnt);
   const uint32_t n_slow = read_count(c, d_counts, h_counts, CNT_SLOW);
+  for (uint32_t t = 0; t < SWT_N_DIRECT; t++) c->tm.n_sw_fwd_tier[t] = cnt[t];
   uint64_t band64_sweep = 0, full_done = 0;
   sw_pass<false>(c, n, pl, sc, cnt, d_counts, h_counts, &band64_sweep, &full_done);
   c->tm.n_sw_fast = full_done; c->tm.n_sw_slow = n_slow;
-  c->tm.n_sw_band = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4] + cnt[5] + cnt[6] + cnt[7];
-  c->tm.n_sw_band64 = cnt[4] + band64_sweep;
-  c->tm.n_sw_tier96 = cnt[5]; c->tm.n_sw_tier128 = cnt[6];
-  c->tm.n_sw_tier8 = cnt[0]; c->tm.n_sw_tier16 = cnt[1]; c->tm.n_sw_tier32 = cnt[2]; c->tm.n_sw_tier48 = cnt[3]; c->tm.n_sw_tier64 = cnt[4];
+  c->tm.n_sw_band = 0;
+  for (uint32_t t = 0; t < SWT_N_TIERS; t++) c->tm.n_sw_band += cnt[t];
+  c->tm.n_sw_band64 = cnt[7] + band64_sweep;        // the 64-wide tier + everything that ran a direct tier after the trial sweep
+  c->tm.n_sw_tier96 = cnt[10]; c->tm.n_sw_tier128 = cnt[11];
+  c->tm.n_sw_tier8 = cnt[0]; c->tm.n_sw_tier16 = cnt[1]; c->tm.n_sw_tier32 = cnt[3]; c->tm.n_sw_tier48 = cnt[5]; c->tm.n_sw_tier64 = cnt[7];
   c->tm.n_sw_sweep32 = cnt[SWT_TIER_SWEEP];
   cudaEvent_t e2 = tm_mark(c);
 
   // ---- reverse
   CUDA_TRY(cudaMemsetAsync(d_counts + CNT_BAND, 0, 8, st));   // band + full counters
-  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_BAND64, 0, 12, st));
   CUDA_TRY(cudaMemsetAsync(d_counts + CNT_TIER, 0, SWT_N_TIERS * 4, st));
   k_sw_rev_lists<<<nb, 256, 0, st>>>(tasks, res, n, sc, tier_r, sw_level(c), w->keys.as<Rec16>(), d_counts);
   c->launches++;
-  make_tier_lists(c, n, tier_r, d_counts, h_counts, cnt);
+  make_tier_lists(c, n, tier_r, nullptr, d_counts, h_counts, CNT_TIER, SWT_N_TIERS, w->lists.as<uint32_t>(), cnt);
   uint64_t dummy = 0, full_rev = 0;
   sw_pass<true>(c, n, pl, sc, cnt, d_counts, h_counts, &dummy, &full_rev);
-  c->tm.n_sw_band_rev = (uint64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4] + cnt[5] + cnt[6];
-  for (uint32_t t = 0; t < SWT_N_DIRECT; t++) c->tm.n_sw_rev_tier[t] = cnt[t];
+  c->tm.n_sw_band_rev = 0;
+  for (uint32_t t = 0; t < SWT_N_DIRECT; t++) { c->tm.n_sw_rev_tier[t] = cnt[t]; c->tm.n_sw_band_rev += cnt[t]; }
   cudaEvent_t e3 = tm_mark(c);
 
   // ---- exact scalar fallback for shapes outside the fast kernels
@@ -1263,7 +1292,7 @@ static void sw_reserve(kslam_ctx *c, uint32_t n) {
   w->keys.reserve((size_t)n * sizeof(Rec16) + 64);
   w->keys2.reserve((size_t)n * sizeof(Rec16) + 64);
   w->items.reserve((size_t)(2 * ((n + 1) / 2)) * sizeof(uint2) + 64);
-  w->lists.reserve((size_t)n * 20 + 64);      // tier lists | slow list | 64- / 96- / 128-wide lists of the sweep tier's failures
+  w->lists.reserve((size_t)n * 16 + 64);      // tier lists | slow list | second-round alignments (sweep tier's failures) | their tier lists
   w->tier.reserve((size_t)n * 2 + 64);        // work-list tier of every alignment: forward | reverse
   c->counters.reserve(64 * 8); c->h_counters.reserve(64 * 8);
   w->n = n;
@@ -1275,7 +1304,7 @@ static void sw_reset_timers(kslam_ctx *c) {
   c->tm.n_sw_fast = c->tm.n_sw_slow = c->tm.n_sw_band = c->tm.n_sw_band64 = c->tm.n_sw_band_rev = 0; c->tm.n_traceback_dp = 0;
   c->tm.n_sw_tier8 = c->tm.n_sw_tier16 = c->tm.n_sw_tier32 = c->tm.n_sw_tier48 = c->tm.n_sw_tier64 = c->tm.n_sw_sweep32 = 0; c->tm.sw_cells_computed = 0;
   c->tm.n_sw_tier96 = c->tm.n_sw_tier128 = 0;
-  for (uint32_t t = 0; t < 7; t++) c->tm.n_sw_rev_tier[t] = 0;
+  for (uint32_t t = 0; t < 12; t++) c->tm.n_sw_rev_tier[t] = c->tm.n_sw_fwd_tier[t] = 0;
 }
 
 // ---- CIGAR pool compaction: the traceback writes alignment i's ops at the fixed stride i * cigar_cap; almost every

@@ -209,9 +209,9 @@ __device__ __forceinline__ void q_group(const SwPlanes &pl, const SwTask &t, int
   }
 }
 
-// Slot pairs (2p, 2p+1) of `list` share a thread group. Failures of the sweep-and-verify tier go to one of the next lists
-// (list k of next_list, stride next_stride: the 64- / 96- / 128-wide tiers; the score lower bound is left in res[].score)
-// when the interval they need fits that tier, else to fb_keys (full-matrix kernel, key = columns).
+// Slot pairs (2p, 2p+1) of `list` share a thread group. Failures of the sweep-and-verify tier go to next_list (second
+// round: tier_f[] gets the direct tier the interval they need fits, marked SWT_SWEPT and counted in tier2_count[]; the
+// score lower bound is left in res[].score), else to fb_keys (full-matrix kernel, key = columns).
 //
 // PARTS > 1: the band is PARTS x WP diagonals wide and PARTS neighbouring lanes share it, lane `part` owning slots
 // [part * WP, (part + 1) * WP). A cell needs its left neighbour of the same row (horizontal gap), the cell above-right
@@ -225,7 +225,8 @@ template <int MODE, int WP, int PARTS>
 __global__ void __launch_bounds__(SWB_BLOCK, (WP > 32 ? 4 : 6))
 k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, uint32_t n_list, SwPlanes pl, SwScore sc,
           SwRes *__restrict__ res, Rec16 *__restrict__ fb_keys, uint32_t *__restrict__ fb_count,
-          uint32_t *__restrict__ next_list, uint32_t *__restrict__ next_count, uint32_t next_stride, uint32_t one /* == 1, opaque to ptxas */) {
+          uint32_t *__restrict__ next_list, uint32_t *__restrict__ next_count, uint8_t *__restrict__ tier_f,
+          uint32_t *__restrict__ tier2_count, uint32_t level, uint32_t one /* == 1, opaque to ptxas */) {
   constexpr bool REVERSE = MODE == 1;
   constexpr int W = WP * PARTS;                // diagonals of the whole band
   constexpr int NH = (WP + 31) / 32;           // tracking keys per 32-slot half
@@ -399,10 +400,12 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
         o.flags = SWR_FWD_TIER(SWR_TIER_OF_W(W)); o.pad0 = o.pad1 = 0; o.ref_begin = -1; o.read_begin = 0;
         o.score = S; o.ref_end = bcol; o.read_end = brow;
         res[idx] = o;
-      } else if (MODE == 0 && next_list && S > 0 && need <= (int32_t)sc.max_band) {
+      } else if (MODE == 0 && next_list && S > 0 && tier_of_interval(need, level, sc) != SWT_TIER_NONE) {
         res[idx].score = S;         // lower bound: every alignment scoring >= S lies in [-(m - a), n - a]
-        const uint32_t k = need <= 64 ? 0u : need <= 96 ? 1u : 2u;
-        next_list[(size_t)k * next_stride + list_slot_keyed(next_count, k)] = idx;
+        const uint32_t t2 = tier_of_interval(need, level, sc);
+        tier_f[idx] = (uint8_t)(t2 | SWT_SWEPT);
+        list_slot_keyed(tier2_count, t2);
+        next_list[list_slot(next_count)] = idx;
       } else {
         const uint32_t k = list_slot(fb_count);
         fb_keys[k].key = (uint64_t)(al ? tb.n : ta.n); fb_keys[k].val = idx;
