@@ -24,6 +24,7 @@
 // from two planes written by k_band_bytes as ready-made PRMT selectors, one coalesced load each per row and pair, so
 // the per-row overhead next to the W x 7 cell ops is two PRMTs, the row-winner compare and the selector slide.
 #pragma once
+#include <type_traits>
 
 #define SWB_MAXROWS 160
 #define SWB_BLOCK 64
@@ -294,7 +295,20 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
   const uint32_t thrA = REVERSE ? (uint32_t)ra.score * 32u + KB : 0u, thrB = REVERSE ? (uint32_t)rb.score * 32u + KB : 0u;
   uint32_t e_end = K2, qprev = 0x55555555u;                   // (row code 5 for both alignments: the rows before row 0)
   const uint32_t qshift = 0x7654u - 0x1111u * part;           // bytes of {qprev, qcur} holding rows s - part .. s - part + 3
-  for (int32_t i0 = 0; i0 < rows4; i0 += 4) {
+  // A cell of row i ends at most i + 1 diagonal steps, so it can reach the known bound B (MODE 2: the lower bound the
+  // band was placed with; MODE 1: the forward score) only from row ceil(B / match) - 1 on: the rows before it run without
+  // the tracking op (5 ALU ops per cell pair instead of 6) and without the row-winner code. The switch row is the
+  // smallest one among the lanes that are here together, so a warp changes loops once.
+  int32_t n_quiet = 0;
+  if (MODE != 0) {
+    const int32_t qa = ceil_div_pos(ra.score, sc.match) - 1, qb = ceil_div_pos(rb.score, sc.match) - 1;
+    n_quiet = __reduce_min_sync(__activemask(), (qa < qb ? qa : qb)) & ~3;
+    if (n_quiet < 0) n_quiet = 0;
+    if (n_quiet > rows4) n_quiet = rows4;
+  }
+  auto sweep = [&](auto track_c, const int32_t i_begin, const int32_t i_end) {
+  constexpr bool TRACK = decltype(track_c)::value;
+  for (int32_t i0 = i_begin; i0 < i_end; i0 += 4) {
     uint32_t qword = qAB[(size_t)(i0 / 4) * SWB_BLOCK];
     if (PARTS > 1) { const uint32_t qcur = qword; qword = __byte_perm(qprev, qcur, qshift); qprev = qcur; }
     const uint32_t ewa = colA[(size_t)((i0 + WP) / 4) * SWB_BLOCK], ewb = colB[(size_t)((i0 + WP) / 4) * SWB_BLOCK];
@@ -323,7 +337,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
           const uint32_t down = __shfl_sync(gmask, __viaddmax_s16x2(v, NEG_GE, hgo), part + 1 < PARTS ? lane + 1 : lane);
           V[WP - 1] = part + 1 < PARTS ? down : K2;
         }
-        acc[t / 32] = __viaddmax_s16x2(h, (uint32_t)(31 - (t & 31)) * 0x10001u, acc[t / 32]);   // H*32 + (31 - slot): smallest column wins ties
+        if (TRACK) acc[t / 32] = __viaddmax_s16x2(h, (uint32_t)(31 - (t & 31)) * 0x10001u, acc[t / 32]);   // H*32 + (31 - slot): smallest column wins ties
       }
       e_end = e;
       // slide the column selectors: next row's slot t is this row's slot t+1; the last slot takes the entering column
@@ -333,6 +347,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
       // row winners -> running best. SSW's rule: first column attaining the maximum, then the smallest row
       // (ssw.c:316-342). Rows only grow, so a strictly larger score always wins (the common, branch-free path) and an
       // equal score wins only with a strictly smaller column.
+      if (TRACK) {
 #pragma unroll
       for (int h = 0; h < NH; h++) {
         const uint32_t aA = acc[h] & 0xffffu, aB = acc[h] >> 16;
@@ -349,8 +364,12 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
           else if ((aB | 31u) == keyB && aB > KB + 31u && (nB >> 8) + (nB & 255u) < (infoB >> 8) + (infoB & 255u)) infoB = nB;
         }
       }
+      }
     }
   }
+  };
+  sweep(std::false_type{}, 0, n_quiet);
+  sweep(std::true_type{}, n_quiet, rows4);
 
   // ---- per-lane winners as one comparable word: forward score << 20 | (1023 - column) << 10 | (1023 - row), reverse
   // 1 << 31 | (4095 - column) << 12 | (4095 - row); 0 = nothing. The lanes of a group keep the largest.
