@@ -119,6 +119,7 @@ struct kslam_ctx {
   DevBuf seed_keep;         // u8
   DevBuf seeds;             // kslam_seed, de-duplicated, final order
   uint64_t n_raw = 0, n_seeds = 0;
+  bool seeds_compact = false;   // seedA holds one-word seeds (join.cu: SeedBits)
 
   DevBuf ov;                // kslam_overlap[n_seeds]
   DevBuf cig;               // u32[n_seeds * max_cigar_ops]: traceback scratch, fixed stride
@@ -162,6 +163,7 @@ void extract_genome_kmers_range(kslam_ctx *c, const PackedSeqs &s, uint32_t gap,
 // radix_sort.cu
 // Sorts n records by bits [lo_bit, hi_bit) of their .key (word 0) or .val (word 1); stable.
 // Returns the buffer (a or b) holding the result; *passes_done is incremented per executed pass.
+uint64_t *radix_sort_u64(kslam_ctx *c, uint64_t *a, uint64_t *b, uint64_t n, uint32_t lo_bit, uint32_t hi_bit, uint64_t *passes_done);
 Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, uint32_t lo_bit, uint32_t hi_bit,
                   uint64_t *passes_done);
 // scan.cu
@@ -169,7 +171,7 @@ void exclusive_scan_u32(kslam_ctx *c, const uint32_t *in, uint32_t *out, uint64_
 // join.cu
 void join_and_unique(kslam_ctx *c);
 void seed_sort_unique(kslam_ctx *c);
-uint64_t run_join(kslam_ctx *c, const Rec16 *R, uint64_t n_r, bool match, DevBuf &outbuf);
+uint64_t run_join(kslam_ctx *c, const Rec16 *R, uint64_t n_r, bool match, DevBuf &outbuf, bool compact = false);
 void matches_to_seeds(kslam_ctx *c, const Rec16 *m, uint64_t n, uint32_t id_base);
 // api.cu: sort an extracted genome k-mer list into the reference's order and split it into g_keys / g_vals
 void finish_genome_index(kslam_ctx *c, DevBuf &a, DevBuf &b, uint64_t n);

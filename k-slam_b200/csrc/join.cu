@@ -31,6 +31,40 @@ __device__ __forceinline__ Rec16 pack_seed(uint32_t read, uint32_t entry, int32_
   return s;
 }
 
+// Compact seeds: when read id, entry, rel + bias and the strand bit fit 64 bits together (every workload of BASELINE.json:
+// 25 + 9 + 23 bits for config 2) a seed is ONE word, read | entry | (rel + bias) << 1 | rev_comp from the top down, whose
+// plain integer order is the seed order (read, entry, rel, rev_comp). The join writes 8 bytes per seed instead of 16 and
+// the seed sort is a sort of bare keys over the bits in use (radix_sort_u64): 16 B per seed and pass instead of 32 B, 7
+// passes instead of 9 for config 2.
+struct SeedBits { uint32_t rel_bits, ebits, rbits, compact; };
+static SeedBits seed_bits(const kslam_ctx *c) {
+  SeedBits b;
+  b.rel_bits = ceil_log2_u64((uint64_t)c->max_genome_len + 2ull * c->reads.max_len + 2) + 1;   // (rel + bias) << 1 | rev_comp
+  if (b.rel_bits > 33) b.rel_bits = 33;
+  b.ebits = ceil_log2_u64(c->genomes.n > 1 ? c->genomes.n : 2);
+  b.rbits = ceil_log2_u64(c->reads.n > 1 ? c->reads.n : 2);
+  static const char *off = getenv("KSLAM_SEEDS_16B");
+  b.compact = (b.rel_bits + b.ebits + b.rbits <= 64 && !(off && atoi(off))) ? 1u : 0u;
+  return b;
+}
+__device__ __forceinline__ uint64_t pack_seed64(uint32_t read, uint32_t entry, int32_t rel, uint32_t rc, uint32_t bias, uint32_t rel_bits, uint32_t ebits) {
+  return ((((uint64_t)read << ebits) | entry) << rel_bits) | ((uint64_t)(uint32_t)(rel + (int32_t)bias) << 1) | rc;
+}
+__device__ __forceinline__ Rec16 unpack_seed64(uint64_t k, uint32_t rel_bits, uint32_t ebits) {
+  Rec16 s;
+  const uint64_t re = k >> rel_bits;
+  s.key = ((re >> ebits) << 32) | (re & ((1ull << ebits) - 1ull));
+  s.val = k & ((1ull << rel_bits) - 1ull);
+  return s;
+}
+__global__ void __launch_bounds__(256)
+k_seeds_expand(const uint64_t *__restrict__ in, uint64_t n, uint32_t rel_bits, uint32_t ebits, Rec16 *__restrict__ out) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const Rec16 s = unpack_seed64(in[i], rel_bits, ebits);
+    *reinterpret_cast<ulonglong2 *>(out + i) = make_ulonglong2(s.key, s.val);
+  }
+}
+
 // first index in keys[0..n) with keys[idx] >= target (upper=false) or > target (upper=true); whole warp cooperates
 __device__ __forceinline__ uint64_t warp_bound(const uint64_t *__restrict__ keys, uint64_t n, uint64_t target, bool upper) {
   const uint32_t lane = threadIdx.x & 31;
@@ -57,11 +91,14 @@ __device__ __forceinline__ uint64_t warp_bound(const uint64_t *__restrict__ keys
 // MATCH = false: emit packed seeds (needs the read lengths, i.e. the reads live on this GPU).
 // MATCH = true (k-mer-range partitioned database, dist.cu): emit the raw match {read record val, genome record val};
 // the GPU that owns the read turns it into a seed (k_matches_to_seeds) because only it knows the read length.
-template <bool MATCH>
+// COMPACT: emit one-word seeds (see SeedBits) into out64.
+template <bool MATCH, bool COMPACT>
 __global__ void __launch_bounds__(JN_THREADS)
 k_join(const Rec16 *__restrict__ R, uint64_t n_r, const uint64_t *__restrict__ gkeys,
        const uint64_t *__restrict__ gvals, uint64_t n_g, const uint64_t *__restrict__ read_offs,
-       Rec16 *__restrict__ out, uint64_t cap, unsigned long long *__restrict__ counter, uint32_t bias, uint64_t low_mask) {
+       Rec16 *__restrict__ out, uint64_t cap, unsigned long long *__restrict__ counter, uint32_t bias, uint64_t low_mask,
+       uint32_t rel_bits, uint32_t ebits) {
+  uint64_t *out64 = reinterpret_cast<uint64_t *>(out);
   // R is ordered on the key bits above low_mask only (the radix sort stops there: the binary search below does not
   // need more), so the tile's key range is widened by the unsorted low bits
   __shared__ uint64_t s_g[JN_GCAP];
@@ -133,6 +170,7 @@ k_join(const Rec16 *__restrict__ R, uint64_t n_r, const uint64_t *__restrict__ g
         uint32_t gf = (uint32_t)gv, g_off = (uint32_t)(gv >> 32);
         uint32_t g_rc = (gf >> 30) & 1;
         uint32_t off = g_rc ? rlen - r_off - KSLAM_K : r_off;           // Overlap.h:185-189
+        if (COMPACT) { out64[o] = pack_seed64(rid, gf & 0x3FFFFFFFu, (int32_t)(g_off - off), g_rc != r_rc, bias, rel_bits, ebits); o++; continue; }
         Rec16 s = pack_seed(rid, gf & 0x3FFFFFFFu, (int32_t)(g_off - off), g_rc != r_rc, bias);
         *reinterpret_cast<ulonglong2 *>(out + o) = make_ulonglong2(s.key, s.val);
         o++;
@@ -156,6 +194,43 @@ k_unique_flags(const Rec16 *__restrict__ s, uint64_t n, uint32_t *__restrict__ k
       int64_t d = rel - last; if (d < 0) d = -d;
       if (d < 3) keep[j] = 0; else { keep[j] = 1; last = rel; }
     }
+  }
+}
+
+// the same over one-word seeds: a run is the seeds sharing the bits above rel_bits
+__global__ void __launch_bounds__(256)
+k_unique_flags64(const uint64_t *__restrict__ s, uint64_t n, uint32_t rel_bits, uint32_t *__restrict__ keep) {
+  const uint64_t rmask = (1ull << rel_bits) - 1ull;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t v = s[i], k = v >> rel_bits;
+    if (i > 0 && (s[i - 1] >> rel_bits) == k) continue;       // not a run head
+    int64_t last = (int64_t)((v & rmask) >> 1);
+    keep[i] = 1;
+    for (uint64_t j = i + 1; j < n; j++) {
+      const uint64_t w = s[j];
+      if ((w >> rel_bits) != k) break;
+      const int64_t rel = (int64_t)((w & rmask) >> 1);
+      int64_t d = rel - last; if (d < 0) d = -d;
+      if (d < 3) keep[j] = 0; else { keep[j] = 1; last = rel; }
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+k_unique_compact64(const uint64_t *__restrict__ s, uint64_t n, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ pos,
+                   uint32_t bias, uint32_t rel_bits, uint32_t ebits, kslam_seed *__restrict__ seeds, kslam_overlap *__restrict__ ov) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    if (!keep[i]) continue;
+    const Rec16 r = unpack_seed64(s[i], rel_bits, ebits);
+    kslam_seed o;
+    o.read = (uint32_t)(r.key >> 32); o.entry = (uint32_t)r.key;
+    o.rel = (int32_t)((uint32_t)(r.val >> 1) - bias); o.rev_comp = (uint32_t)(r.val & 1);
+    const uint32_t p = pos[i];
+    seeds[p] = o;
+    kslam_overlap v;
+    v.read = o.read; v.entry = o.entry; v.rel = o.rel; v.rev_comp = o.rev_comp;
+    v.ref_begin = v.ref_end = v.query_begin = v.query_end = 0;
+    v.sw_score = 0; v.cigar_off = 0; v.cigar_len = 0; v.flags = 0;
+    ov[p] = v;
   }
 }
 
@@ -198,6 +273,7 @@ k_matches_to_seeds(const Rec16 *__restrict__ m, uint64_t n, uint32_t id_base, co
 
 void matches_to_seeds(kslam_ctx *c, const Rec16 *m, uint64_t n, uint32_t id_base) {
   c->n_raw = n;
+  c->seeds_compact = false;
   if (!n) return;
   c->seedA.reserve((size_t)n * sizeof(Rec16));
   uint64_t blocks = (n + 255) / 256, maxb = (uint64_t)c->num_sms * 16;
@@ -210,7 +286,8 @@ void matches_to_seeds(kslam_ctx *c, const Rec16 *m, uint64_t n, uint32_t id_base
 
 // merge-join of n_r sorted read records against the resident genome list; returns the number of records emitted
 // into `outbuf` (packed seeds, or raw matches when `match` is set). The buffer is regrown once on overflow.
-uint64_t run_join(kslam_ctx *c, const Rec16 *R, uint64_t n_r, bool match, DevBuf &outbuf) {
+// (compact: one-word seeds, see SeedBits; not with `match`)
+uint64_t run_join(kslam_ctx *c, const Rec16 *R, uint64_t n_r, bool match, DevBuf &outbuf, bool compact) {
   cudaStream_t st = c->stream;
   unsigned long long *d_cnt = c->counters.as<unsigned long long>();
   unsigned long long *h_cnt = c->h_counters.as<unsigned long long>();
@@ -218,25 +295,30 @@ uint64_t run_join(kslam_ctx *c, const Rec16 *R, uint64_t n_r, bool match, DevBuf
   const uint32_t sb = kmer_sort_bits(c);
   const uint64_t low_mask = sb >= 64 ? 0ull : (~0ull >> sb);
   if (!n_r || !c->n_gk) return 0;
-  uint64_t cap = outbuf.cap / sizeof(Rec16);
-  if (cap < (1u << 20)) { outbuf.reserve((size_t)(n_r / 8 + (1u << 20)) * sizeof(Rec16)); cap = outbuf.cap / sizeof(Rec16); }
+  const SeedBits sb64 = seed_bits(c);
+  const size_t rec = compact ? 8 : sizeof(Rec16);
+  uint64_t cap = outbuf.cap > 64 ? (outbuf.cap - 64) / rec : 0;                  // (64 bytes of slack: radix_pass2.cuh's bulk copies)
+  if (cap < (1u << 20)) { outbuf.reserve((size_t)(n_r / 8 + (1u << 20)) * rec + 64); cap = (outbuf.cap - 64) / rec; }
   const uint64_t tiles = (n_r + JN_TILE - 1) / JN_TILE;
   for (int attempt = 0; attempt < 2; attempt++) {
     CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 8, st));
     if (match)
-      k_join<true><<<(unsigned)tiles, JN_THREADS, 0, st>>>(R, n_r, c->g_keys.as<uint64_t>(), c->g_vals.as<uint64_t>(), c->n_gk,
-                                                           nullptr, outbuf.as<Rec16>(), cap, d_cnt, bias, low_mask);
+      k_join<true, false><<<(unsigned)tiles, JN_THREADS, 0, st>>>(R, n_r, c->g_keys.as<uint64_t>(), c->g_vals.as<uint64_t>(), c->n_gk,
+                                                                  nullptr, outbuf.as<Rec16>(), cap, d_cnt, bias, low_mask, 0, 0);
+    else if (compact)
+      k_join<false, true><<<(unsigned)tiles, JN_THREADS, 0, st>>>(R, n_r, c->g_keys.as<uint64_t>(), c->g_vals.as<uint64_t>(), c->n_gk,
+                                                                  c->reads.offs.as<uint64_t>(), outbuf.as<Rec16>(), cap, d_cnt, bias, low_mask, sb64.rel_bits, sb64.ebits);
     else
-      k_join<false><<<(unsigned)tiles, JN_THREADS, 0, st>>>(R, n_r, c->g_keys.as<uint64_t>(), c->g_vals.as<uint64_t>(), c->n_gk,
-                                                            c->reads.offs.as<uint64_t>(), outbuf.as<Rec16>(), cap, d_cnt, bias, low_mask);
+      k_join<false, false><<<(unsigned)tiles, JN_THREADS, 0, st>>>(R, n_r, c->g_keys.as<uint64_t>(), c->g_vals.as<uint64_t>(), c->n_gk,
+                                                                   c->reads.offs.as<uint64_t>(), outbuf.as<Rec16>(), cap, d_cnt, bias, low_mask, 0, 0);
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     read_small(c, h_cnt, d_cnt, 8);
     CUDA_TRY(cudaStreamSynchronize(st));
     if (h_cnt[0] <= cap) break;
     if (attempt == 1) throw CudaError{cudaErrorMemoryAllocation, "seed buffer overflow after regrow", __FILE__, __LINE__};
-    outbuf.reserve((size_t)h_cnt[0] * sizeof(Rec16));   // exact size is now known: grow once and redo
-    cap = outbuf.cap / sizeof(Rec16);
+    outbuf.reserve((size_t)h_cnt[0] * rec + 64);   // exact size is now known: grow once and redo
+    cap = (outbuf.cap - 64) / rec;
   }
   return h_cnt[0];
 }
@@ -246,7 +328,8 @@ void join_and_unique(kslam_ctx *c) {
   c->h_counters.reserve(64 * 8);
   c->n_raw = 0; c->n_seeds = 0;
   cudaEvent_t e0 = tm_mark(c);
-  c->n_raw = run_join(c, c->sorted_rk, c->n_rk, false, c->seedA);
+  c->seeds_compact = seed_bits(c).compact != 0;
+  c->n_raw = run_join(c, c->sorted_rk, c->n_rk, false, c->seedA, c->seeds_compact);
   cudaEvent_t e1 = tm_mark(c);
   seed_sort_unique(c);
   c->tm.ms_join = tm_ms(e0, e1);
@@ -264,7 +347,44 @@ void seed_sort_unique(kslam_ctx *c) {
   cudaEvent_t e1 = tm_mark(c);
   c->tm.n_raw_seeds = c->n_raw;
   cudaEvent_t e2 = e1, e3 = e1;
-  if (c->n_raw) {
+  const SeedBits sb = seed_bits(c);
+  uint64_t eblocks = (c->n_raw + 255) / 256;
+  if (eblocks > (uint64_t)c->num_sms * 16) eblocks = (uint64_t)c->num_sms * 16;
+  if (c->n_raw && c->seeds_compact && c->n_raw >= (1ull << 30)) {     // beyond radix_sort_u64's range: back to 16-byte records
+    c->seedB.reserve((size_t)c->n_raw * sizeof(Rec16));
+    k_seeds_expand<<<(unsigned)eblocks, 256, 0, st>>>(c->seedA.as<uint64_t>(), c->n_raw, sb.rel_bits, sb.ebits, c->seedB.as<Rec16>());
+    c->launches++;
+    DevBuf t = c->seedA; c->seedA = c->seedB; c->seedB = t;
+    c->seeds_compact = false;
+  }
+  if (c->n_raw && c->seeds_compact) {
+    c->seedB.reserve((size_t)c->n_raw * 8 + 64);
+    if (c->keep_taps) {   // tap: raw seeds before sorting (order is not contractual), in the 16-byte form the getter unpacks
+      c->raw_seeds.reserve((size_t)c->n_raw * sizeof(Rec16));
+      k_seeds_expand<<<(unsigned)eblocks, 256, 0, st>>>(c->seedA.as<uint64_t>(), c->n_raw, sb.rel_bits, sb.ebits, c->raw_seeds.as<Rec16>());
+      c->launches++;
+    }
+    uint64_t passes = 0;
+    uint64_t *cur = radix_sort_u64(c, c->seedA.as<uint64_t>(), c->seedB.as<uint64_t>(), c->n_raw, 0, sb.rel_bits + sb.ebits + sb.rbits, &passes);
+    c->tm.n_sort_passes += passes;
+    e2 = tm_mark(c);
+    c->seed_keep.reserve((size_t)c->n_raw * 8 + 64);
+    uint32_t *keep = c->seed_keep.as<uint32_t>();
+    uint32_t *pos = keep + c->n_raw;
+    k_unique_flags64<<<(unsigned)eblocks, 256, 0, st>>>(cur, c->n_raw, sb.rel_bits, keep);
+    c->launches++;
+    exclusive_scan_u32(c, keep, pos, c->n_raw, (uint64_t *)(d_cnt + 1));
+    read_small(c, h_cnt + 1, d_cnt + 1, 8);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    c->n_seeds = h_cnt[1];
+    c->seeds.reserve((size_t)c->n_seeds * sizeof(kslam_seed) + 64);
+    c->ov.reserve((size_t)c->n_seeds * sizeof(kslam_overlap) + 64);
+    k_unique_compact64<<<(unsigned)eblocks, 256, 0, st>>>(cur, c->n_raw, keep, pos, bias, sb.rel_bits, sb.ebits, c->seeds.as<kslam_seed>(),
+                                                         c->ov.as<kslam_overlap>());
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    e3 = tm_mark(c);
+  } else if (c->n_raw) {
     c->seedB.reserve((size_t)c->n_raw * sizeof(Rec16));
     if (c->keep_taps) {   // tap: raw seeds before sorting (order is not contractual)
       c->raw_seeds.reserve((size_t)c->n_raw * sizeof(Rec16));

@@ -69,9 +69,11 @@ __device__ __forceinline__ uint32_t rs2_look_back(volatile uint32_t *state, uint
   return excl;
 }
 
-template <int RS_THREADS, int RS_IPT, int WORD>
+// REC = Rec16: 16-byte records sorted by .key (WORD 0) or .val (WORD 1); REC = uint64_t: bare 8-byte keys (half the bytes
+// per record and pass: the packed seeds of join.cu, WORD ignored).
+template <int RS_THREADS, int RS_IPT, int WORD, typename REC>
 __global__ void __launch_bounds__(RS_THREADS, 2)
-k_rs_pass2(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n, uint32_t shift, uint32_t mask,
+k_rs_pass2(const REC *__restrict__ in, REC *__restrict__ out, uint64_t n, uint32_t shift, uint32_t mask,
            const unsigned long long *__restrict__ digit_base,  // [256] exclusive global offsets
            volatile uint32_t *state,                           // [tiles][256], zero-initialised
            uint32_t *__restrict__ ticket) {
@@ -79,8 +81,9 @@ k_rs_pass2(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n, ui
   constexpr uint32_t RS_TILE = RS_THREADS * RS_IPT;
   static_assert(RS_THREADS >= 256 && RS_THREADS % 256 == 0, "threads 0..255 own one digit each");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Rec16 *stage = reinterpret_cast<Rec16 *>(smem_raw);                               // RS_TILE records
-  uint32_t *whist = reinterpret_cast<uint32_t *>(smem_raw + RS_TILE * sizeof(Rec16)); // [RS_WARPS][256]
+  constexpr bool BARE = sizeof(REC) == 8;
+  REC *stage = reinterpret_cast<REC *>(smem_raw);                                   // RS_TILE records
+  uint32_t *whist = reinterpret_cast<uint32_t *>(smem_raw + RS_TILE * sizeof(REC)); // [RS_WARPS][256]
   __shared__ unsigned long long s_delta[256];
   __shared__ uint32_t s_scan[8];
   __shared__ uint32_t s_tile;
@@ -97,8 +100,9 @@ k_rs_pass2(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n, ui
     const uint32_t cnt = (uint32_t)((n - base) < RS_TILE ? (n - base) : RS_TILE);
     mbar_init(&s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(&s_bar, cnt * (uint32_t)sizeof(Rec16));
-    bulk_load(stage, in + base, cnt * (uint32_t)sizeof(Rec16), &s_bar);
+    const uint32_t bytes = (cnt * (uint32_t)sizeof(REC) + 15u) & ~15u;      // bulk copies move multiples of 16 bytes: the buffers of
+    mbar_expect_tx(&s_bar, bytes);                                          // bare 8-byte keys carry 16 bytes of slack behind the last one
+    bulk_load(stage, in + base, bytes, &s_bar);
   }
 #pragma unroll
   for (uint32_t i = tid; i < RS_WARPS * 256; i += RS_THREADS) whist[i] = 0;
@@ -109,15 +113,16 @@ k_rs_pass2(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n, ui
   mbar_wait(&s_bar, 0);
 
   // records to registers, warp-striped so that (warp, item, lane) order == input order (stability)
-  uint64_t key[RS_IPT], val[RS_IPT];
+  uint64_t key[RS_IPT], val[BARE ? 1 : RS_IPT];
   const uint32_t wbase = warp * 32 * RS_IPT;
 #pragma unroll
   for (int i = 0; i < RS_IPT; i++) {
     const uint32_t idx = wbase + i * 32 + lane;
-    if (idx < count) {
+    if (BARE) key[i] = idx < count ? *reinterpret_cast<const uint64_t *>(stage + idx) : ~0ull;
+    else if (idx < count) {
       const ulonglong2 r = *reinterpret_cast<const ulonglong2 *>(stage + idx);
-      key[i] = r.x; val[i] = r.y;
-    } else { key[i] = ~0ull; val[i] = ~0ull; }   // padding: digit 255 whatever the shift, sorts to the very end of the tile
+      key[i] = r.x; val[BARE ? 0 : i] = r.y;
+    } else { key[i] = ~0ull; val[BARE ? 0 : i] = ~0ull; }   // padding: digit 255 whatever the shift, sorts to the very end of the tile
   }
 
   // 2. per-warp digit ranks: rank = earlier peers in this row + the warp's running count of the digit
@@ -126,7 +131,7 @@ k_rs_pass2(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n, ui
   uint32_t dr[RS_IPT];                                    // digit << 16 | rank inside (warp, digit)
 #pragma unroll
   for (int i = 0; i < RS_IPT; i++) {
-    const uint32_t d = (uint32_t)((WORD ? val[i] : key[i]) >> shift) & mask & 255u;   // (padding stays 255: mask may be narrower)
+    const uint32_t d = (uint32_t)(((WORD && !BARE) ? val[BARE ? 0 : i] : key[i]) >> shift) & mask & 255u;   // (padding stays 255: mask may be narrower)
     const uint32_t dd = (wbase + i * 32 + lane < count) ? d : 255u;
     const uint32_t peers = rs2_digit_peers(dd);
     const uint32_t old = myhist[dd];
@@ -167,13 +172,30 @@ k_rs_pass2(const Rec16 *__restrict__ in, Rec16 *__restrict__ out, uint64_t n, ui
 #pragma unroll
   for (int i = 0; i < RS_IPT; i++) {
     const uint32_t pos = myhist[dr[i] >> 16] + (dr[i] & 0xffffu);
-    *reinterpret_cast<ulonglong2 *>(stage + pos) = make_ulonglong2(key[i], val[i]);
+    if (BARE) *reinterpret_cast<uint64_t *>(stage + pos) = key[i];
+    else *reinterpret_cast<ulonglong2 *>(stage + pos) = make_ulonglong2(key[i], val[BARE ? 0 : i]);
   }
   __syncthreads();
 
   // 5. write out: staged position j belongs to digit d at global s_delta[d] + j. Full tiles take the unrolled form: the
   // shared-memory loads of all items are in flight together instead of one dependent LDS -> LDS -> STG chain per item.
-  if (count == RS_TILE) {
+  if (BARE) {
+    if (count == RS_TILE) {
+      uint64_t r[RS_IPT];
+#pragma unroll
+      for (int i = 0; i < RS_IPT; i++) r[i] = *reinterpret_cast<const uint64_t *>(stage + tid + i * RS_THREADS);
+#pragma unroll
+      for (int i = 0; i < RS_IPT; i++) {
+        const uint32_t d = (uint32_t)(r[i] >> shift) & mask;
+        *reinterpret_cast<uint64_t *>(out + s_delta[d] + (tid + i * RS_THREADS)) = r[i];
+      }
+    } else {
+      for (uint32_t j = tid; j < count; j += RS_THREADS) {
+        const uint64_t r = *reinterpret_cast<const uint64_t *>(stage + j);
+        *reinterpret_cast<uint64_t *>(out + s_delta[(uint32_t)(r >> shift) & mask] + j) = r;
+      }
+    }
+  } else if (count == RS_TILE) {
     ulonglong2 r[RS_IPT];
 #pragma unroll
     for (int i = 0; i < RS_IPT; i++) r[i] = *reinterpret_cast<const ulonglong2 *>(stage + tid + i * RS_THREADS);

@@ -26,15 +26,18 @@ struct PassPlan {
 };
 
 // ---- histogram of all digits in one read of the keys ----------------------------------------
+template <typename REC>
 __global__ void __launch_bounds__(512)
-k_rs_hist(const Rec16 *__restrict__ in, uint64_t n, PassPlan plan, uint32_t word,
+k_rs_hist(const REC *__restrict__ in, uint64_t n, PassPlan plan, uint32_t word,
           unsigned long long *__restrict__ ghist) {
   __shared__ uint32_t s_hist[RS_MAX_PASSES * 256];
   for (uint32_t i = threadIdx.x; i < plan.n_passes * 256; i += blockDim.x) s_hist[i] = 0;
   __syncthreads();
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x) {
-    uint64_t key = word ? __ldg(&in[i].val) : __ldg(&in[i].key);
+    uint64_t key;
+    if constexpr (sizeof(REC) == 8) key = __ldg(&in[i]);
+    else key = word ? __ldg(&in[i].val) : __ldg(&in[i].key);
 #pragma unroll
     for (uint32_t p = 0; p < RS_MAX_PASSES; p++)
       if (p < plan.n_passes) atomicAdd(&s_hist[p * 256 + ((uint32_t)(key >> plan.shift[p]) & plan.mask[p])], 1u);
@@ -385,17 +388,17 @@ static void launch_sweep_tma(kslam_ctx *c, const Rec16 *in, Rec16 *out, uint64_t
   k_rs_sweep_tma<T, I, C><<<(unsigned)grid, T, smem, c->stream>>>(in, out, n, shift, mask, word, base, state, ticket, (uint32_t)tiles);
 }
 
-template <int T, int I, int WORD>
-static void launch_pass2(kslam_ctx *c, const Rec16 *in, Rec16 *out, uint64_t n, uint32_t shift, uint32_t mask,
+template <int T, int I, int WORD, typename REC = Rec16>
+static void launch_pass2(kslam_ctx *c, const REC *in, REC *out, uint64_t n, uint32_t shift, uint32_t mask,
                          const unsigned long long *base, uint32_t *state, uint32_t *ticket) {
-  constexpr size_t smem = (size_t)T * I * sizeof(Rec16) + (T / 32) * 256 * sizeof(uint32_t);
+  constexpr size_t smem = (size_t)T * I * sizeof(REC) + (T / 32) * 256 * sizeof(uint32_t);
   const uint64_t tiles = (n + (uint64_t)T * I - 1) / ((uint64_t)T * I);
   static bool attr_set[64] = {false};   // per instantiation
   if (!(c->device < 64 && attr_set[c->device])) {
-    CUDA_TRY(cudaFuncSetAttribute(k_rs_pass2<T, I, WORD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_rs_pass2<T, I, WORD, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (c->device < 64) attr_set[c->device] = true;
   }
-  k_rs_pass2<T, I, WORD><<<(unsigned)tiles, T, smem, c->stream>>>(in, out, n, shift, mask, base, state, ticket);
+  k_rs_pass2<T, I, WORD, REC><<<(unsigned)tiles, T, smem, c->stream>>>(in, out, n, shift, mask, base, state, ticket);
 }
 
 template <int T, int I, bool B>
@@ -444,7 +447,7 @@ Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, u
     uint64_t blocks = (n + 512 * 16 - 1) / (512 * 16);
     uint64_t maxb = (uint64_t)c->num_sms * 4;
     if (blocks > maxb) blocks = maxb;
-    k_rs_hist<<<(unsigned)blocks, 512, 0, st>>>(cur, n, plan, word, ghist);
+    k_rs_hist<Rec16><<<(unsigned)blocks, 512, 0, st>>>(cur, n, plan, word, ghist);
     k_rs_scan_hist<<<1, 256, 0, st>>>(ghist, plan.n_passes, n, trivial);
     c->launches += 2;
   }
@@ -479,6 +482,58 @@ Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, u
     c->launches++;
     CUDA_TRY(cudaGetLastError());
     Rec16 *t = cur; cur = alt; alt = t;
+    if (passes_done) (*passes_done)++;
+  }
+  return cur;
+}
+
+
+// Bare 8-byte keys (n < 2^30), bits [lo_bit, hi_bit): the same histogram + k_rs_pass2 passes at 16 B per key and pass.
+// KSLAM_RS_U64_IPT=16 picks 4096-key tiles (default 8192).
+uint64_t *radix_sort_u64(kslam_ctx *c, uint64_t *a, uint64_t *b, uint64_t n, uint32_t lo_bit, uint32_t hi_bit, uint64_t *passes_done) {
+  if (n < 2 || hi_bit <= lo_bit) return a;
+  if (hi_bit > 64) hi_bit = 64;
+  if (n >= (1ull << 30)) throw ArgError{"radix_sort_u64: more than 2^30 keys"};
+  cudaStream_t st = c->stream;
+  uint64_t *cur = a, *alt = b;
+  static int ipt = -1;
+  if (ipt < 0) { const char *e = getenv("KSLAM_RS_U64_IPT"); ipt = e && atoi(e) == 16 ? 16 : 32; }
+  PassPlan plan;
+  plan.n_passes = 0;
+  for (uint32_t s = lo_bit; s < hi_bit && plan.n_passes < RS_MAX_PASSES; s += 8) {
+    uint32_t bits = hi_bit - s < 8 ? hi_bit - s : 8;
+    plan.shift[plan.n_passes] = s; plan.mask[plan.n_passes] = (1u << bits) - 1; plan.n_passes++;
+  }
+  const uint64_t tile_recs = 256 * (uint64_t)ipt;
+  const uint64_t tiles = (n + tile_recs - 1) / tile_recs;
+  const size_t hist_bytes = RS_MAX_PASSES * 256 * 8, misc_bytes = 128;
+  const size_t state_bytes = tiles * 256 * 4;
+  c->sort_hist.reserve(hist_bytes + misc_bytes + state_bytes);
+  unsigned long long *ghist = c->sort_hist.as<unsigned long long>();
+  uint32_t *trivial = reinterpret_cast<uint32_t *>((char *)c->sort_hist.p + hist_bytes);
+  uint32_t *tickets = trivial + 8;
+  uint32_t *state = reinterpret_cast<uint32_t *>((char *)c->sort_hist.p + hist_bytes + misc_bytes);
+  CUDA_TRY(cudaMemsetAsync(c->sort_hist.p, 0, hist_bytes + misc_bytes, st));
+  {
+    uint64_t blocks = (n + 512 * 16 - 1) / (512 * 16);
+    uint64_t maxb = (uint64_t)c->num_sms * 4;
+    if (blocks > maxb) blocks = maxb;
+    k_rs_hist<uint64_t><<<(unsigned)blocks, 512, 0, st>>>(cur, n, plan, 0, ghist);
+    k_rs_scan_hist<<<1, 256, 0, st>>>(ghist, plan.n_passes, n, trivial);
+    c->launches += 2;
+  }
+  c->h_counters.reserve(64 * 8);
+  uint32_t *h_trivial = c->h_counters.as<uint32_t>() + 112;
+  read_small(c, h_trivial, trivial, 8 * sizeof(uint32_t));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (uint32_t p = 0; p < plan.n_passes; p++) {
+    if (h_trivial[p]) continue;
+    CUDA_TRY(cudaMemsetAsync(state, 0, state_bytes, st));
+    if (ipt == 16) launch_pass2<256, 16, 0, uint64_t>(c, cur, alt, n, plan.shift[p], plan.mask[p], ghist + p * 256, state, tickets + p);
+    else launch_pass2<256, 32, 0, uint64_t>(c, cur, alt, n, plan.shift[p], plan.mask[p], ghist + p * 256, state, tickets + p);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    uint64_t *t = cur; cur = alt; alt = t;
     if (passes_done) (*passes_done)++;
   }
   return cur;
