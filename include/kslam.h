@@ -169,6 +169,8 @@ typedef struct {
 } kslam_pairs_compact;
 int kslam_fetch_pairs_compact(kslam_ctx *ctx, uint32_t host_threads /* 0 = all cores */, kslam_pairs_compact *out);
 uint32_t kslam_insert_size_limit_compact(const kslam_pair_compact *pairs, uint64_t n, uint32_t host_threads);
+/* The same statistic from value counts (counts[v] = pair records with insert size v, v = 0 .. top; counts[0] is ignored). */
+uint32_t kslam_insert_size_limit_counts(const uint64_t *counts, uint32_t top);
 /* The far-mates table for a limit given by the caller: a batch sharded over several contexts has ONE limit (a statistic of the
  * whole batch, PairedOverlap.h:314-360), computed from the merged compact records. */
 int kslam_fetch_far_mates(kslam_ctx *ctx, uint32_t insert_size_limit, uint64_t *n_far, const kslam_far_mates **far);

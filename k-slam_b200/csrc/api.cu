@@ -104,9 +104,9 @@ void kslam_destroy(kslam_ctx *c) {
   DevBuf *bufs[] = {&c->g_keys, &c->g_vals, &c->recA, &c->recB, &c->sort_hist, &c->scan_tmp, &c->counters,
                     &c->raw_seeds, &c->seedA, &c->seedB, &c->seed_keep, &c->seeds, &c->ov, &c->cig, &c->cig_dense, &c->pair_keys,
                     &c->pair_keys2, &c->ov_sorted, &c->cig_sorted, &c->pair_cnt, &c->pairs, &c->bitmap, &c->d_bounds,
-                    &c->part_send, &c->part_recv, &c->part_tmp, &c->part_m, &c->part_msend, &c->part_mrecv, &c->pairs_compact, &c->far_mates};
+                    &c->part_send, &c->part_recv, &c->part_tmp, &c->part_m, &c->part_msend, &c->part_mrecv, &c->pairs_compact, &c->far_mates, &c->insert_hist};
   for (DevBuf *b : bufs) b->release();
-  HostBuf *hb[] = {&c->h_stage, &c->h_counters, &c->h_ov, &c->h_cig, &c->h_ov_sorted, &c->h_cig_sorted, &c->h_pairs, &c->h_pairs_compact, &c->h_far_mates};
+  HostBuf *hb[] = {&c->h_stage, &c->h_counters, &c->h_ov, &c->h_cig, &c->h_ov_sorted, &c->h_cig_sorted, &c->h_pairs, &c->h_pairs_compact, &c->h_far_mates, &c->h_insert_hist};
   for (HostBuf *b : hb) b->release();
   sw_workspace_free(c);
   for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -399,12 +399,16 @@ int kslam_fetch_pairs_compact(kslam_ctx *c, uint32_t host_threads, kslam_pairs_c
   if (n >> 32) return fail(c, KSLAM_ERR_ARG, "more than 2^32 pair records in one batch");
   c->pairs_compact.reserve((size_t)n * sizeof(kslam_pair_compact) + 64);
   c->h_pairs_compact.reserve((size_t)n * sizeof(kslam_pair_compact) + 64);
+  // The batch's insert-size limit is a function of the value counts: they are taken on the device (k_insert_hist) and only
+  // the few hundred counters in use cross PCIe before the records do, so the mates of the pairs beyond the limit are
+  // picked while the records are still on their way. (Values outside (0, 2^22): counted from the records on the host.)
+  const unsigned long long *hist = nullptr; uint32_t top = 0;
+  const bool counted = insert_hist_device(c, &hist, &top);
   pairs_compact_device(c, c->pairs_compact.as<kslam_pair_compact>());
   if (n) CUDA_TRY(cudaMemcpyAsync(c->h_pairs_compact.p, c->pairs_compact.p, (size_t)n * sizeof(kslam_pair_compact), cudaMemcpyDeviceToHost, c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
   out->n_pairs = n; out->pairs = c->h_pairs_compact.as<kslam_pair_compact>();
-  // the batch's insert-size limit from the records that just arrived (host), then the mates of the pairs beyond it
-  out->insert_size_limit = kslam_insert_size_limit_compact(out->pairs, n, host_threads);
+  if (counted) out->insert_size_limit = kslam_insert_size_limit_counts((const uint64_t *)hist, top);
+  else { CUDA_TRY(cudaStreamSynchronize(c->stream)); out->insert_size_limit = kslam_insert_size_limit_compact(out->pairs, n, host_threads); }
   const uint64_t n_far = far_mates_device(c, out->insert_size_limit, c->far_mates);
   c->h_far_mates.reserve((size_t)n_far * sizeof(kslam_far_mates) + 64);
   if (n_far) CUDA_TRY(cudaMemcpyAsync(c->h_far_mates.p, c->far_mates.p, (size_t)n_far * sizeof(kslam_far_mates), cudaMemcpyDeviceToHost, c->stream));

@@ -128,8 +128,8 @@ struct kslam_ctx {
   SwWorkspace *sw = nullptr;
   HostBuf h_ov, h_cig;
 
-  DevBuf pair_keys, pair_keys2, ov_sorted, cig_sorted, pair_cnt, pairs, pairs_compact, far_mates;
-  HostBuf h_ov_sorted, h_cig_sorted, h_pairs, h_pairs_compact, h_far_mates;
+  DevBuf pair_keys, pair_keys2, ov_sorted, cig_sorted, pair_cnt, pairs, pairs_compact, far_mates, insert_hist;
+  HostBuf h_ov_sorted, h_cig_sorted, h_pairs, h_pairs_compact, h_far_mates, h_insert_hist;
   uint64_t n_sorted = 0, n_pairs = 0;
 
   // k-mer-range partitioned database (dist.cu)
@@ -186,6 +186,7 @@ void part_matches_to_seeds(kslam_ctx *c, uint64_t n_matches, uint32_t read_id_ba
 void pair_overlaps(kslam_ctx *c);
 void pairs_compact_device(kslam_ctx *c, kslam_pair_compact *out_dev);
 uint64_t far_mates_device(kslam_ctx *c, uint32_t limit, DevBuf &out_buf);
+bool insert_hist_device(kslam_ctx *c, const unsigned long long **h_hist, uint32_t *top);
 
 // api.cu: error plumbing of the C ABI (no exception crosses the boundary)
 int api_fail(kslam_ctx *c, int code, const std::string &msg);

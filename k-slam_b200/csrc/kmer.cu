@@ -118,30 +118,41 @@ k_extract_reads_filtered(const uint64_t *__restrict__ kbits, const uint64_t *__r
     uint32_t len = (uint32_t)len64;
     uint64_t woff = __ldg(&word_off[seq]);
     uint32_t nk = len - KSLAM_K + 1;
-    for (uint32_t p0 = 0; p0 < nk; p0 += 32) {
-      uint32_t p = p0 + lane;
-      bool keep = false;
-      uint64_t key = 0, val = 0;
-      if (p < nk) {
-        uint64_t f = kmer_at(kbits, woff, p), rc = revcomp32(f);
-        uint32_t flags = ((uint32_t)seq + id_base) & 0x3FFFFFFFu;   // id_base != 0: job-global read ids (dist.cu)
-        if (f < rc) { key = f; val = (uint64_t)flags | ((uint64_t)p << 32); }
-        else { key = rc; val = (uint64_t)(flags | 0x40000000u) | ((uint64_t)(len - KSLAM_K - p) << 32); }
-        if (key != 0) { uint64_t h = kmer_hash(key, bits); keep = (__ldg(&bitmap[h >> 5]) >> (h & 31)) & 1; }
+    // four rounds of 32 positions at a time: the four bitmap probes of a lane are independent loads in flight together
+    // (one round at a time left every probe waiting out its own L2 / HBM latency: 26 ms per config-2 batch)
+    for (uint32_t p0 = 0; p0 < nk; p0 += 128) {
+      uint64_t key[4], val[4];
+      uint32_t word[4], bit[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t p = p0 + 32 * j + lane;
+        key[j] = 0; val[j] = 0; word[j] = 0; bit[j] = 0;
+        if (p < nk) {
+          uint64_t f = kmer_at(kbits, woff, p), rc = revcomp32(f);
+          uint32_t flags = ((uint32_t)seq + id_base) & 0x3FFFFFFFu;   // id_base != 0: job-global read ids (dist.cu)
+          if (f < rc) { key[j] = f; val[j] = (uint64_t)flags | ((uint64_t)p << 32); }
+          else { key[j] = rc; val[j] = (uint64_t)(flags | 0x40000000u) | ((uint64_t)(len - KSLAM_K - p) << 32); }
+          if (key[j] != 0) { const uint64_t h = kmer_hash(key[j], bits); word[j] = __ldg(&bitmap[h >> 5]); bit[j] = (uint32_t)h & 31u; }
+        }
       }
-      uint32_t m = __ballot_sync(0xffffffffu, keep);
-      if (keep) *reinterpret_cast<ulonglong2 *>(&buf[pending + __popc(m & ((1u << lane) - 1))]) = make_ulonglong2(key, val);
-      pending += __popc(m);
-      if (pending > XF_WBUF - 32) {
-        __syncwarp();
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(counter, (unsigned long long)pending);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base + pending <= cap)       // overflow: the counter still ends at the exact total and the host re-runs
-          for (uint32_t i = lane; i < pending; i += 32)
-            *reinterpret_cast<ulonglong2 *>(out + base + i) = *reinterpret_cast<const ulonglong2 *>(&buf[i]);
-        __syncwarp();
-        pending = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        if (p0 + 32 * j >= nk) break;                                  // warp-uniform
+        const bool keep = (word[j] >> bit[j]) & 1u;                    // (zero k-mers and lanes past the end probe nothing: word 0)
+        uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (keep) *reinterpret_cast<ulonglong2 *>(&buf[pending + __popc(m & ((1u << lane) - 1))]) = make_ulonglong2(key[j], val[j]);
+        pending += __popc(m);
+        if (pending > XF_WBUF - 32) {
+          __syncwarp();
+          unsigned long long base = 0;
+          if (lane == 0) base = atomicAdd(counter, (unsigned long long)pending);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (base + pending <= cap)       // overflow: the counter still ends at the exact total and the host re-runs
+            for (uint32_t i = lane; i < pending; i += 32)
+              *reinterpret_cast<ulonglong2 *>(out + base + i) = *reinterpret_cast<const ulonglong2 *>(&buf[i]);
+          __syncwarp();
+          pending = 0;
+        }
       }
     }
   }

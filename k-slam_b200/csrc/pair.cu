@@ -292,6 +292,58 @@ k_far_emit(const kslam_pair *__restrict__ pairs, const kslam_overlap *__restrict
   out[pos[i]] = f;
 }
 
+// Insert-size histogram of the batch's pair records: getMaxAllowedInsertSize (PairedOverlap.h:314-360) is a function of the
+// value counts only (sam.cu: InsertRuns), so the host needs the counts, not a pass over 100 M records. Fragment lengths
+// crowd a few hundred values: the low range is counted in shared memory per CTA; what falls outside (0, span) is only
+// counted (the caller then takes the host path over the records).
+#define IH_LOW 4096u
+__global__ void __launch_bounds__(256)
+k_insert_hist(const kslam_pair *__restrict__ pairs, uint64_t n, uint32_t span, unsigned long long *__restrict__ hist,
+              unsigned long long *__restrict__ misc /* [0] values outside (0, span), [1] largest value inside */) {
+  __shared__ uint32_t s_low[IH_LOW];
+  for (uint32_t i = threadIdx.x; i < IH_LOW; i += blockDim.x) s_low[i] = 0;
+  __syncthreads();
+  uint32_t outside = 0, top = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t v = pairs[i].insert_size;
+    if (v == 0) continue;                                   // single-ended records (PairedOverlap.h:321)
+    if (v >= span) { outside++; continue; }                 // (also every value that is negative as an int32)
+    top = v > top ? v : top;
+    if (v < IH_LOW) atomicAdd(&s_low[v], 1u); else atomicAdd(&hist[v], 1ull);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < IH_LOW; i += blockDim.x) if (s_low[i]) atomicAdd(&hist[i], (unsigned long long)s_low[i]);
+  for (int d = 16; d; d >>= 1) { outside += __shfl_xor_sync(0xffffffffu, outside, d); const uint32_t o = __shfl_xor_sync(0xffffffffu, top, d); top = o > top ? o : top; }
+  if ((threadIdx.x & 31) == 0) { if (outside) atomicAdd(&misc[0], (unsigned long long)outside); if (top) atomicMax(&misc[1], (unsigned long long)top); }
+}
+
+// counts of the insert sizes 0 .. *top of the batch into the ctx's pinned buffer; false when some value lies outside
+// (0, 2^22) — the caller falls back to the records
+bool insert_hist_device(kslam_ctx *c, const unsigned long long **h_hist, uint32_t *top) {
+  constexpr uint32_t SPAN = 1u << 22;
+  cudaStream_t st = c->stream;
+  c->insert_hist.reserve((size_t)(SPAN + 2) * 8);
+  unsigned long long *d = c->insert_hist.as<unsigned long long>(), *misc = d + SPAN;
+  CUDA_TRY(cudaMemsetAsync(d, 0, (size_t)(SPAN + 2) * 8, st));
+  if (c->n_pairs) {
+    uint64_t blocks = (c->n_pairs + 256 * 16 - 1) / (256 * 16), maxb = (uint64_t)c->num_sms * 8;
+    if (blocks > maxb) blocks = maxb;
+    k_insert_hist<<<(unsigned)blocks, 256, 0, st>>>(c->pairs.as<kslam_pair>(), c->n_pairs, SPAN, d, misc);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  unsigned long long *h_misc = c->h_counters.as<unsigned long long>() + 60;   // (bytes 480-495 of the 512-byte block: nobody else's)
+  read_small(c, h_misc, misc, 16);
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (h_misc[0]) return false;
+  *top = (uint32_t)h_misc[1];
+  c->h_insert_hist.reserve((size_t)(*top + 1) * 8 + 64);
+  CUDA_TRY(cudaMemcpyAsync(c->h_insert_hist.p, d, (size_t)(*top + 1) * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *h_hist = c->h_insert_hist.as<unsigned long long>();
+  return true;
+}
+
 void pairs_compact_device(kslam_ctx *c, kslam_pair_compact *out_dev) {
   if (!c->n_pairs) return;
   uint64_t blocks = (c->n_pairs + 255) / 256, maxb = (uint64_t)c->num_sms * 16;

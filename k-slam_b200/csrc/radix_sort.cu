@@ -391,6 +391,8 @@ static void launch_sweep_tma(kslam_ctx *c, const Rec16 *in, Rec16 *out, uint64_t
 template <int T, int I, int WORD, typename REC = Rec16>
 static void launch_pass2(kslam_ctx *c, const REC *in, REC *out, uint64_t n, uint32_t shift, uint32_t mask,
                          const unsigned long long *base, uint32_t *state, uint32_t *ticket) {
+  static int flat = -1;                                    // KSLAM_RS_LB=0: the one-level look-back (experiments)
+  if (flat < 0) { const char *e = getenv("KSLAM_RS_LB"); flat = e && atoi(e) == 0 ? 1 : 0; }
   constexpr size_t smem = (size_t)T * I * sizeof(REC) + (T / 32) * 256 * sizeof(uint32_t);
   const uint64_t tiles = (n + (uint64_t)T * I - 1) / ((uint64_t)T * I);
   static bool attr_set[64] = {false};   // per instantiation
@@ -398,7 +400,8 @@ static void launch_pass2(kslam_ctx *c, const REC *in, REC *out, uint64_t n, uint
     CUDA_TRY(cudaFuncSetAttribute(k_rs_pass2<T, I, WORD, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (c->device < 64) attr_set[c->device] = true;
   }
-  k_rs_pass2<T, I, WORD, REC><<<(unsigned)tiles, T, smem, c->stream>>>(in, out, n, shift, mask, base, state, ticket);
+  // the group states sit behind the tile states (the caller's memset covers both)
+  k_rs_pass2<T, I, WORD, REC><<<(unsigned)tiles, T, smem, c->stream>>>(in, out, n, shift, mask, base, state, flat ? nullptr : state + tiles * 256, ticket);
 }
 
 template <int T, int I, bool B>
@@ -436,7 +439,7 @@ Rec16 *radix_sort(kslam_ctx *c, Rec16 *a, Rec16 *b, uint64_t n, uint32_t word, u
   const size_t hist_bytes = RS_MAX_PASSES * 256 * 8, misc_bytes = 128;
   const bool pass2 = (cfg == 0 || cfg == 10) && n < (1ull << 30);          // its 32-bit tile states hold prefixes below 2^30
   const int variant = cfg == 10 ? 0 : 1;                   // 1: 256 threads x 16 records (default), 0: 512 x 8 (KSLAM_RS_CFG=10)
-  const size_t state_bytes = tiles * 256 * (pass2 ? 4 : 8);
+  const size_t state_bytes = tiles * 256 * (pass2 ? 4 : 8) + (pass2 ? (tiles / 16 + 1) * 256 * 4 : 0);   // + k_rs_pass2's group states
   c->sort_hist.reserve(hist_bytes + misc_bytes + state_bytes);
   unsigned long long *ghist = c->sort_hist.as<unsigned long long>();
   uint32_t *trivial = reinterpret_cast<uint32_t *>((char *)c->sort_hist.p + hist_bytes);
@@ -507,7 +510,7 @@ uint64_t *radix_sort_u64(kslam_ctx *c, uint64_t *a, uint64_t *b, uint64_t n, uin
   const uint64_t tile_recs = 256 * (uint64_t)ipt;
   const uint64_t tiles = (n + tile_recs - 1) / tile_recs;
   const size_t hist_bytes = RS_MAX_PASSES * 256 * 8, misc_bytes = 128;
-  const size_t state_bytes = tiles * 256 * 4;
+  const size_t state_bytes = tiles * 256 * 4 + (tiles / 16 + 1) * 256 * 4;   // tile states + group states
   c->sort_hist.reserve(hist_bytes + misc_bytes + state_bytes);
   unsigned long long *ghist = c->sort_hist.as<unsigned long long>();
   uint32_t *trivial = reinterpret_cast<uint32_t *>((char *)c->sort_hist.p + hist_bytes);

@@ -806,6 +806,17 @@ int kslam_batch_outputs(const kslam_sam_params *prm, const kslam_sam_db *db, con
   } catch (const std::exception &) { return KSLAM_ERR_NOMEM; }
 }
 
+// the same from value counts: counts[v] = number of pair records with insert size v, v = 0 .. top (counts[0] is ignored:
+// single-ended records carry insert size 0 and never enter the statistic, PairedOverlap.h:321)
+uint32_t kslam_insert_size_limit_counts(const uint64_t *counts, uint32_t top) {
+  if (!counts) return UINT32_MAX;
+  try {
+    InsertRuns runs;
+    for (uint32_t v = 1; v <= top; v++) runs.push((int32_t)v, counts[v]);
+    return insert_size_limit_from_runs(runs);
+  } catch (const std::exception &) { return UINT32_MAX; }
+}
+
 uint32_t kslam_insert_size_limit_compact(const kslam_pair_compact *pairs, uint64_t n, uint32_t host_threads) {
   if (!pairs || !n) return UINT32_MAX;
   uint32_t threads = host_threads ? host_threads : std::max(1u, std::thread::hardware_concurrency());
