@@ -69,7 +69,8 @@ __device__ __forceinline__ uint32_t rs2_look_back(volatile uint32_t *state, uint
   return excl;
 }
 
-// Two-level look-back. With ~300 tiles in flight the flat walk above sums up to a few hundred predecessor aggregates,
+// Two-level look-back (an experiment, off by default: KSLAM_RS_LB=1; it measured 4 % slower than the flat walk, so the
+// chain of predecessor loads is not what bounds a tile). With ~300 tiles in flight the flat walk above sums up to a few hundred predecessor aggregates,
 // eight loads per round trip to L2, and that chain — not the bytes — sets the life time of a tile (the pass sat at 0.53
 // of the copy peak). Tiles are grouped by RS2_GROUP: a tile sums the aggregates of the predecessors of ITS group (at most
 // 15: two rounds), the last tile of a group publishes the group's total as soon as it has that sum, and everybody then

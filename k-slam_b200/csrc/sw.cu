@@ -511,10 +511,15 @@ k_sw_striped(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list
 // -3 = scratch too small for the band this alignment needs (caller retries with the big-scratch path).
 // dir holds one byte per band cell: bit0 = (E came from H, code 3), bit1 = (F came from H, code 5),
 // bits 2-4 = the H direction code 1..5 exactly as banded_sw would store it.
+// rowdir (bands up to SW_TB_MAXBAND, i.e. at most 15 cells per row): the same as ONE 64-bit word per row, 4 bits per
+// cell — bit0, bit1 as above, bits 2-3 = where H came from (0 diagonal, 1 E, 2 F; the code 2/3 or 4/5 banded_sw stores is
+// the cell's own E / F code). The threads of a warp walk the rows together, so the row words of a warp's 32 alignments
+// are one coalesced local-memory store per row; the byte-per-cell form scattered 32 single bytes per cell (1.15 GB of
+// DRAM traffic for 400 k alignments, profiles/r1_ncu_summaries.txt).
 __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const SwScore &sc, int32_t ref0,
                                     int32_t read0, int32_t refLen, int32_t readLen, int32_t score, int32_t *h_b,
                                     int32_t *e_b, int32_t *h_c, uint32_t arr_cap, uint8_t *dir, size_t dir_cap,
-                                    size_t dstride, uint32_t *cig, uint32_t cig_cap, bool reverse_out,
+                                    size_t dstride, uint64_t *rowdir, uint32_t *cig, uint32_t cig_cap, bool reverse_out,
                                     uint32_t *overflow) {
   const int32_t go = sc.gap_open, ge = sc.gap_extend;
   int32_t band = (refLen > readLen ? refLen - readLen : readLen - refLen) + 1;
@@ -527,7 +532,7 @@ __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const S
     // the band may double up to the "no cigar" limit above without leaving the scratch.
     const int32_t aw = width < refLen + 2 ? width : refLen + 2;
     ws = width_d < refLen ? width_d : refLen;
-    if ((uint32_t)aw > arr_cap || (size_t)ws * (size_t)readLen > dir_cap) return -3;
+    if ((uint32_t)aw > arr_cap || (rowdir ? (ws > 2 * SW_TB_MAXBAND + 1 || readLen > SW_TB_MAXROWS) : (size_t)ws * (size_t)readLen > dir_cap)) return -3;
     for (int32_t j = 1; j < aw - 1; j++) h_b[j] = 0;
     // Window codes of the band cells of a row, one nibble per cell (bands up to 7: 15 cells): nibble k of `wwin` holds the
     // code of column i - band + k. A row needs ONE new code (column i + band); the plane loads of w_code were per cell.
@@ -542,7 +547,8 @@ __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const S
       int32_t u = 0, f = 0;
       h_b[0] = 0; e_b[0] = 0; h_b[edge] = 0; e_b[edge] = 0; h_c[0] = 0;
       const uint32_t qc = q_code(pl, t, (uint32_t)(read0 + i));
-      uint8_t *dl = dir + (size_t)ws * i * dstride;
+      uint8_t *dl = rowdir ? nullptr : dir + (size_t)ws * i * dstride;
+      uint64_t rowbits = 0;
       // set_u (ssw.c:56-61): u = j - max(i - band, 0) + 1 for row i; the row above is shifted by `up` = 0 or 1 slots
       const int32_t xoff = beg, up = xoff - (i - 1 - band > 0 ? i - 1 - band : 0);
       for (int32_t j = beg; j <= end; j++) {
@@ -565,8 +571,10 @@ __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const S
         h_c[u] = hv;
         if (hv > maxv) maxv = hv;
         const uint32_t dh = t1 <= t2 ? 1u : (e1 > f1 ? de : df);
-        dl[(size_t)(j - xoff) * dstride] = (uint8_t)((de == 3u) | ((df == 5u) << 1) | (dh << 2));
+        if (rowdir) rowbits |= (uint64_t)((de == 3u) | ((df == 5u) << 1) | ((dh == 1u ? 0u : (dh <= 3u ? 1u : 2u)) << 2)) << (4 * (j - xoff));
+        else dl[(size_t)(j - xoff) * dstride] = (uint8_t)((de == 3u) | ((df == 5u) << 1) | (dh << 2));
       }
+      if (rowdir) rowdir[i] = rowbits;
       for (int32_t j = 1; j <= u; j++) h_b[j] = h_c[j];
       if (windowed) {
         wwin >>= 4;
@@ -587,7 +595,12 @@ __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const S
     while (i > 0) {
       const int32_t lo = i - band > 0 ? i - band : 0, hi = i + band < refLen - 1 ? i + band : refLen - 1;
       if (j < lo || j > hi) return -1;
-      const uint32_t cell = dir[((size_t)ws * i + (size_t)(j - lo)) * dstride];
+      uint32_t cell;
+      if (rowdir) {
+        cell = (uint32_t)(rowdir[i] >> (4 * (j - lo))) & 15u;
+        const uint32_t from = cell >> 2;                    // -> the byte form: H code 1, the cell's E code or its F code
+        cell = (cell & 3u) | ((from == 0u ? 1u : from == 1u ? ((cell & 1u) ? 3u : 2u) : ((cell & 2u) ? 5u : 4u)) << 2);
+      } else cell = dir[((size_t)ws * i + (size_t)(j - lo)) * dstride];
       uint32_t code = st == 2 ? (cell >> 2) : (st == 0 ? ((cell & 1u) ? 3u : 2u) : ((cell & 2u) ? 5u : 4u));
       switch (code) {
         case 1: --i; --j; st = 2; f = 0; break;
@@ -678,7 +691,7 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
   int32_t l_hb[SW_TB_MAXBAND * 2 + 3], l_eb[SW_TB_MAXBAND * 2 + 3], l_hc[SW_TB_MAXBAND * 2 + 3];
-  uint8_t l_dir[SW_TB_MAXROWS * (SW_TB_MAXBAND * 2 + 1)];
+  uint64_t l_rowdir[SW_TB_MAXROWS];
   for (uint32_t k = gtid; k < n; k += nthreads) {
     const uint32_t idx = list ? list[k] : k;
     const SwTask t = tasks[idx];
@@ -701,14 +714,14 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
           } else len = -3;
         } else if (mode == 1)
           len = banded_traceback(pl, t, sc, r.ref_begin, r.read_begin, refLen, readLen, r.score, l_hb, l_eb, l_hc,
-                                 SW_TB_MAXBAND * 2 + 3, l_dir, sizeof(l_dir), 1, cig, sc.cigar_cap, rev && unflip, &overflow);
+                                 SW_TB_MAXBAND * 2 + 3, nullptr, 0, 1, l_rowdir, cig, sc.cigar_cap, rev && unflip, &overflow);
         else {
           uint8_t *base = big + (size_t)gtid * big_per_thread;
           const uint32_t arr_cap = (uint32_t)(big_per_thread / 64);   // ints per rolling array
           int32_t *hb = reinterpret_cast<int32_t *>(base), *eb = hb + arr_cap, *hc = eb + arr_cap;
           uint8_t *d = base + (size_t)arr_cap * 12;
           len = banded_traceback(pl, t, sc, r.ref_begin, r.read_begin, refLen, readLen, r.score, hb, eb, hc, arr_cap, d,
-                                 big_per_thread - (size_t)arr_cap * 12, 1, cig, sc.cigar_cap, rev && unflip, &overflow);
+                                 big_per_thread - (size_t)arr_cap * 12, 1, nullptr, cig, sc.cigar_cap, rev && unflip, &overflow);
         }
         if (len == -3) {
           if (mode < 2) { deferred = true; retry_list[list_slot(retry_count)] = idx; }
@@ -984,29 +997,38 @@ k_sw_make_items(const Rec16 *__restrict__ sorted, uint32_t n_fast, uint2 *__rest
 
 // out[0..1]: matrix cells (readLen x windowLen) of the forward / reverse sweeps — the GCUPS numerator.
 // out[2]: cells actually computed by the sweep kernels (band cells of every tier an alignment went through, the whole
-// matrix for the full-matrix kernel), the numerator of the integer-pipe roofline (7 ALU ops per two cells).
+// matrix for the full-matrix kernel). out[3]: ALU-pipe thread-ops those cells need, the numerator of the integer-pipe
+// roofline: 3 per cell (6 per s16x2 cell pair: PRMT + 5 DPX), 2.5 in the rows a direct-tier sweep runs without the
+// tracking op (estimated from the final score, which can only under-count: the kernel switches at the smallest bound of
+// its warp and, forward, with the lower bound it was given). Stored as twice the count to stay integral.
 __global__ void __launch_bounds__(256)
 k_sw_cells(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, const uint8_t *__restrict__ tier_f,
-           const uint8_t *__restrict__ tier_r, uint32_t n, unsigned long long *out) {
-  unsigned long long fw = 0, rv = 0, comp = 0;
+           const uint8_t *__restrict__ tier_r, uint32_t n, int32_t sc_match, unsigned long long *out) {
+  unsigned long long fw = 0, rv = 0, comp = 0, ops2 = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const SwTask t = tasks[i]; const SwRes r = res[i];
     if (((t.flags >> 8) & 0xffu) > SWC_FAST32) continue;
     fw += (unsigned long long)t.m * t.n;
     const uint32_t tf = tier_f[i], tr = tier_r[i], ft = (r.flags >> 8) & 15u;
-    if (tf == SWT_TIER_SWEEP || (tf != SWT_TIER_NONE && (tf & SWT_SWEPT))) comp += 32ull * t.m;      // the trial sweep
-    if (tf != SWT_TIER_NONE && (tf & ~SWT_SWEPT) < SWT_N_DIRECT) comp += (unsigned long long)tier_width(tf & ~SWT_SWEPT) * t.m;
-    if (ft == 0u) comp += (unsigned long long)t.m * t.n;
+    unsigned long long quiet = r.score > 0 ? (unsigned long long)(((r.score + sc_match - 1) / sc_match - 1) & ~3) : 0ull;
+    if (tf == SWT_TIER_SWEEP || (tf != SWT_TIER_NONE && (tf & SWT_SWEPT))) { comp += 32ull * t.m; ops2 += 6ull * 32ull * t.m; }      // the trial sweep
+    if (tf != SWT_TIER_NONE && (tf & ~SWT_SWEPT) < SWT_N_DIRECT) {
+      const unsigned long long w = tier_width(tf & ~SWT_SWEPT), q = quiet < t.m ? quiet : t.m;
+      comp += w * t.m; ops2 += w * (5ull * q + 6ull * (t.m - q));
+    }
+    if (ft == 0u) { comp += (unsigned long long)t.m * t.n; ops2 += 6ull * t.m * t.n; }
     if (r.score > 0) {
       const unsigned long long rows = (unsigned long long)(r.read_end + 1), cols = (unsigned long long)(r.ref_end + 1);
       rv += rows * cols;
-      comp += tr < SWT_N_DIRECT ? (unsigned long long)tier_width(tr) * rows : rows * cols;
+      if (tr < SWT_N_DIRECT) { const unsigned long long w = tier_width(tr), q = quiet < rows ? quiet : rows; comp += w * rows; ops2 += w * (5ull * q + 6ull * (rows - q)); }
+      else { comp += rows * cols; ops2 += 6ull * rows * cols; }
     }
   }
   for (int d = 16; d; d >>= 1) {
     fw += __shfl_xor_sync(0xffffffffu, fw, d); rv += __shfl_xor_sync(0xffffffffu, rv, d); comp += __shfl_xor_sync(0xffffffffu, comp, d);
+    ops2 += __shfl_xor_sync(0xffffffffu, ops2, d);
   }
-  if ((threadIdx.x & 31) == 0) { atomicAdd(out, fw); atomicAdd(out + 1, rv); atomicAdd(out + 2, comp); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, fw); atomicAdd(out + 1, rv); atomicAdd(out + 2, comp); atomicAdd(out + 3, ops2); }
 }
 
 // Integer-pipe issue-rate microbenchmark: dependency-free streams of the DPX op the sweeps are made of
@@ -1270,13 +1292,13 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
   }
   cudaEvent_t e5 = tm_mark(c);
   unsigned long long *d_cells = c->counters.as<unsigned long long>() + 8;
-  CUDA_TRY(cudaMemsetAsync(d_cells, 0, 24, st));
-  k_sw_cells<<<c->num_sms * 2, 256, 0, st>>>(tasks, res, tier_f, tier_r, n, d_cells);
+  CUDA_TRY(cudaMemsetAsync(d_cells, 0, 32, st));
+  k_sw_cells<<<c->num_sms * 2, 256, 0, st>>>(tasks, res, tier_f, tier_r, n, sc.match, d_cells);
   c->launches++;
   unsigned long long *h_cells = c->h_counters.as<unsigned long long>() + 8;
-  read_small(c, h_cells, d_cells, 24);
+  read_small(c, h_cells, d_cells, 32);
   CUDA_TRY(cudaStreamSynchronize(st));
-  c->tm.sw_cells_forward = h_cells[0]; c->tm.sw_cells_reverse = h_cells[1]; c->tm.sw_cells_computed = h_cells[2];
+  c->tm.sw_cells_forward = h_cells[0]; c->tm.sw_cells_reverse = h_cells[1]; c->tm.sw_cells_computed = h_cells[2]; c->tm.sw_alu_ops = h_cells[3] / 2;
   c->tm.ms_sw_forward = tm_ms(e1, e2);
   c->tm.ms_sw_reverse = tm_ms(e2, e3);
   c->tm.ms_sw_slow = tm_ms(e3, e4);
@@ -1303,7 +1325,7 @@ static void sw_reset_timers(kslam_ctx *c) {
   c->tm.sw_cells_forward = c->tm.sw_cells_reverse = 0;
   c->tm.n_sw_fast = c->tm.n_sw_slow = c->tm.n_sw_band = c->tm.n_sw_band64 = c->tm.n_sw_band_rev = 0; c->tm.n_traceback_dp = 0;
   c->tm.n_sw_tier8 = c->tm.n_sw_tier16 = c->tm.n_sw_tier32 = c->tm.n_sw_tier48 = c->tm.n_sw_tier64 = c->tm.n_sw_sweep32 = 0; c->tm.sw_cells_computed = 0;
-  c->tm.n_sw_tier96 = c->tm.n_sw_tier128 = 0;
+  c->tm.n_sw_tier96 = c->tm.n_sw_tier128 = 0; c->tm.sw_alu_ops = 0;
   for (uint32_t t = 0; t < 12; t++) c->tm.n_sw_rev_tier[t] = c->tm.n_sw_fwd_tier[t] = 0;
 }
 
