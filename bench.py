@@ -894,7 +894,7 @@ def main():
                "counts": {k: tm[k] for k in ("n_read_kmers", "n_sorted_kmers", "n_genome_kmers", "n_raw_seeds", "n_seeds", "n_pairs",
                                              "n_sw_band", "n_sw_band64", "n_sw_fast", "n_sw_slow", "n_sw_band_rev",
                                              "n_sw_tier8", "n_sw_tier16", "n_sw_tier32", "n_sw_tier48", "n_sw_tier64", "n_sw_sweep32",
-                                             "n_sw_tier96", "n_sw_tier128", "n_sw_fwd_tier", "n_sw_rev_tier",
+                                             "n_sw_tier96", "n_sw_tier128", "n_sw_fwd_tier", "n_sw_rev_tier", "n_sw_rev_diagonal",
                                              "sw_cells_forward", "sw_cells_reverse", "sw_cells_computed", "n_sort_passes")},
                "genome_index_build_s": t_load}
         if partitioned:

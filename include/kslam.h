@@ -103,6 +103,7 @@ typedef struct {
   uint64_t n_sw_tier96, n_sw_tier128;  /* forward tiers swept by three / four lanes of 32 diagonals */
   uint64_t n_sw_fwd_tier[12];          /* alignments per forward band tier: 8 16 24 32 40 48 56 64 72 80 96 128 diagonals */
   uint64_t n_sw_rev_tier[12];          /* ... and per reverse band tier */
+  uint64_t n_sw_rev_diagonal;          /* reverse sweeps replaced by a diagonal score (bands one diagonal wide) */
   uint64_t sw_alu_ops;                 /* ALU-pipe thread-ops the computed cells need (3 per cell, 2.5 where the sweep runs without tracking) */
   uint64_t kernel_launches;
 } kslam_timings;

@@ -80,7 +80,7 @@ class Timings(C.Structure):
                                           "sw_cells_forward", "sw_cells_reverse", "sw_cells_computed", "n_sw_fast", "n_sw_slow", "n_sw_band", "n_sw_band64", "n_sw_band_rev", "n_traceback_dp", "n_pairs",
                                           "n_sw_tier8", "n_sw_tier16", "n_sw_tier32", "n_sw_tier48", "n_sw_tier64", "n_sw_sweep32",
                                           "n_sw_tier96", "n_sw_tier128")] + \
-               [("n_sw_fwd_tier", C.c_uint64 * 12), ("n_sw_rev_tier", C.c_uint64 * 12), ("sw_alu_ops", C.c_uint64), ("kernel_launches", C.c_uint64)]
+               [("n_sw_fwd_tier", C.c_uint64 * 12), ("n_sw_rev_tier", C.c_uint64 * 12), ("n_sw_rev_diagonal", C.c_uint64), ("sw_alu_ops", C.c_uint64), ("kernel_launches", C.c_uint64)]
 
     def as_dict(self):
         return {n: (list(getattr(self, n)) if n in ("n_sw_rev_tier", "n_sw_fwd_tier") else getattr(self, n)) for n, _ in self._fields_ if n != "_pad"}

@@ -953,8 +953,15 @@ k_sw_prepare_pairs(uint32_t n, const uint64_t *__restrict__ q_offs, const uint64
 
 // reverse pass work lists: score 0 has no reverse pass (ssw.c:903 is reached with an empty range). The forward score S
 // is known, so the interval an anchored path can reach (reverse_band, sw_band.cuh) is exact and its width picks the tier.
+// A band that is ONE diagonal wide (score within a mismatch or so of the perfect one) leaves only gap-free alignments
+// on the main diagonal of the reversed matrix: k steps back from the end score match * k - (match + mismatch) * x with x
+// mismatches, the first column holding S is the smallest such k, i.e. the smallest x — x = 0, then x = 1 are tried with
+// one word-parallel diagonal score each (the rows on the way stay below S: they have fewer steps). Found: the begin
+// coordinates are written here and the alignment needs no reverse sweep at all (tier code 15); not found (more
+// mismatches, code-4 bases): the 8-diagonal tier as before.
+#define SWR_CODE_DIAGONAL 15u
 __global__ void __launch_bounds__(256)
-k_sw_rev_lists(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, uint32_t n, SwScore sc,
+k_sw_rev_lists(const SwTask *__restrict__ tasks, SwRes *__restrict__ res, uint32_t n, SwScore sc, SwPlanes pl,
                uint8_t *__restrict__ tier_r, uint32_t level,
                Rec16 *__restrict__ full_keys, uint32_t *__restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -969,12 +976,38 @@ k_sw_rev_lists(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
         int32_t lo, hi;
         reverse_band(rows, cols, r.score, sc, &lo, &hi);
         tier = tier_of_interval(hi - lo + 1, level, sc);
+        if (lo == 0 && hi == 0 && sc.anchored && level >= 3) tier = SWT_TIER_SWEEP;     // (the reverse pass has no trial sweep: this list is k_sw_rev_diagonal's)
       }
       if (tier == SWT_TIER_NONE) { const uint32_t k = list_slot(&counts[CNT_FULL]); full_keys[k].key = (uint64_t)cols | ((uint64_t)cls << 16); full_keys[k].val = i; }
     }
     tier_r[i] = (uint8_t)tier;
   }
   count_tier_block(tier, counts);
+}
+
+// the diagonal shortcut over its own dense list (inside k_sw_rev_lists one alignment in eight took it and every warp paid)
+__global__ void __launch_bounds__(256)
+k_sw_rev_diagonal(const SwTask *__restrict__ tasks, SwRes *__restrict__ res, const uint32_t *__restrict__ list, uint32_t n_list, SwScore sc,
+                  SwPlanes pl, uint8_t *__restrict__ tier_r, uint32_t *__restrict__ next_list, uint32_t *__restrict__ next_count) {
+  const uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k0 >= n_list) return;
+  const uint32_t i = list[k0];
+  const SwTask t = tasks[i];
+  const SwRes r = res[i];
+  const int32_t rows = r.read_end + 1, cols = r.ref_end + 1;
+  for (int32_t x = 0; x < 2; x++) {
+    const int32_t num = r.score + (sc.match + sc.mismatch) * x;
+    if (num % sc.match) continue;
+    const int32_t k = num / sc.match;
+    if (k < 1 || k > rows || k > cols) continue;
+    if (diagonal_score(pl, t, sc, r.ref_end - k + 1, r.read_end - k + 1, k) != r.score) continue;
+    res[i].ref_begin = r.ref_end - k + 1; res[i].read_begin = r.read_end - k + 1;
+    res[i].flags = r.flags | SWR_REV_TIER(SWR_CODE_DIAGONAL);
+    tier_r[i] = (uint8_t)SWT_TIER_NONE;
+    return;
+  }
+  tier_r[i] = 0;                                      // the 8-diagonal tier after all
+  next_list[list_slot(next_count)] = i;
 }
 
 // sorted (by columns) task ids -> work items of the full-matrix kernel: two alignments with the same column count
@@ -1021,7 +1054,7 @@ k_sw_cells(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, cons
       const unsigned long long rows = (unsigned long long)(r.read_end + 1), cols = (unsigned long long)(r.ref_end + 1);
       rv += rows * cols;
       if (tr < SWT_N_DIRECT) { const unsigned long long w = tier_width(tr), q = quiet < rows ? quiet : rows; comp += w * rows; ops2 += w * (5ull * q + 6ull * (rows - q)); }
-      else { comp += rows * cols; ops2 += 6ull * rows * cols; }
+      else if (((r.flags >> 12) & 15u) != SWR_CODE_DIAGONAL) { comp += rows * cols; ops2 += 6ull * rows * cols; }      // (the diagonal shortcut sweeps nothing)
     }
   }
   for (int d = 16; d; d >>= 1) {
@@ -1155,6 +1188,17 @@ static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore 
   for (uint32_t t = 1; t <= SWT_N_TIERS; t++) off[t] = off[t - 1] + cnt[t - 1];
   constexpr int DM = REVERSE ? 1 : 2;
   for (uint32_t t = 0; t < SWT_N_DIRECT; t++) run_tier<DM>(c, pl, sc, t, lists + off[t], cnt[t], d_counts);
+  if (REVERSE && cnt[SWT_TIER_SWEEP]) {
+    // one-diagonal bands: begin coordinates from a word-parallel diagonal score, no sweep; what it cannot settle runs 8 diagonals
+    CUDA_TRY(cudaMemsetAsync(d_counts + CNT_NEXT, 0, 4, st));
+    k_sw_rev_diagonal<<<(cnt[SWT_TIER_SWEEP] + 255) / 256, 256, 0, st>>>(tasks, res, lists + off[SWT_TIER_SWEEP], cnt[SWT_TIER_SWEEP], sc, pl,
+                                                                       w->tier.as<uint8_t>() + n, next, d_counts + CNT_NEXT);
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+    const uint32_t n_next = read_count(c, d_counts, h_counts, CNT_NEXT);
+    run_band<1, 8>(c, pl, sc, next, n_next, d_counts, nullptr);
+    c->tm.n_sw_rev_diagonal = cnt[SWT_TIER_SWEEP] - n_next;
+  }
   if (!REVERSE && cnt[SWT_TIER_SWEEP]) {
     // trial sweep; what it bounds but cannot prove goes through the direct tiers once more (second round)
     run_band<0, 32>(c, pl, sc, lists + off[SWT_TIER_SWEEP], cnt[SWT_TIER_SWEEP], d_counts, c->sw_band64 ? next : nullptr);
@@ -1251,7 +1295,7 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
   // ---- reverse
   CUDA_TRY(cudaMemsetAsync(d_counts + CNT_BAND, 0, 8, st));   // band + full counters
   CUDA_TRY(cudaMemsetAsync(d_counts + CNT_TIER, 0, SWT_N_TIERS * 4, st));
-  k_sw_rev_lists<<<nb, 256, 0, st>>>(tasks, res, n, sc, tier_r, sw_level(c), w->keys.as<Rec16>(), d_counts);
+  k_sw_rev_lists<<<nb, 256, 0, st>>>(tasks, res, n, sc, pl, tier_r, sw_level(c), w->keys.as<Rec16>(), d_counts);
   c->launches++;
   make_tier_lists(c, n, tier_r, nullptr, d_counts, h_counts, CNT_TIER, SWT_N_TIERS, w->lists.as<uint32_t>(), cnt);
   uint64_t dummy = 0, full_rev = 0;
@@ -1327,6 +1371,7 @@ static void sw_reset_timers(kslam_ctx *c) {
   c->tm.n_sw_tier8 = c->tm.n_sw_tier16 = c->tm.n_sw_tier32 = c->tm.n_sw_tier48 = c->tm.n_sw_tier64 = c->tm.n_sw_sweep32 = 0; c->tm.sw_cells_computed = 0;
   c->tm.n_sw_tier96 = c->tm.n_sw_tier128 = 0; c->tm.sw_alu_ops = 0;
   for (uint32_t t = 0; t < 12; t++) c->tm.n_sw_rev_tier[t] = c->tm.n_sw_fwd_tier[t] = 0;
+  c->tm.n_sw_rev_diagonal = 0;
 }
 
 // ---- CIGAR pool compaction: the traceback writes alignment i's ops at the fixed stride i * cigar_cap; almost every

@@ -20,7 +20,7 @@ def test_record_layouts_match_header(pkg):
     assert pkg.KMER_DT.itemsize == 16 and pkg.SEED_DT.itemsize == 16
     assert pkg.OVERLAP_DT.itemsize == 48 and pkg.PAIR_DT.itemsize == 32
     assert C.sizeof(pkg.Params) == 24
-    assert C.sizeof(pkg.Timings) == 16 * 4 + (23 + 2 + 2 * 12 + 1) * 8      # + tier96 / tier128, forward and reverse counts of the 12 band tiers
+    assert C.sizeof(pkg.Timings) == 16 * 4 + (23 + 2 + 2 * 12 + 2) * 8      # + tier96 / tier128, forward and reverse counts of the 12 band tiers
 
 
 def test_exact_domain(pkg):
