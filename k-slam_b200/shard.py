@@ -43,15 +43,19 @@ def globalize_reads(read_local: np.ndarray, lo: int, cnt: int, mid: int) -> np.n
     return np.where(r < cnt, r + lo, r - cnt + mid + lo).astype(np.uint32)
 
 
-def merge_alignments(parts, ranges, n_pairs: int, cigar_cap: int = 0):
+def merge_alignments(parts, ranges, n_pairs: int, cigar_cap: int = 0, moved=None):
     """parts[r] = (overlaps, cigar_pool) of rank r (local read ids); returns the batch-order arrays.
 
     Global order is (read, entry, rel) with all R1 reads before all R2 reads, so the R1 segments of every rank
-    come first (rank order), then the R2 segments."""
+    come first (rank order), then the R2 segments. `moved` (a list, one entry per rank) receives, per rank, the pair
+    (old cigar_off, new cigar_off) of every alignment, so that other records pointing into a rank's pool (the pair-sorted
+    overlaps) can follow the CIGARs into the merged pool."""
     mid = n_pairs
     segs_ov, segs_cg, base = [], [], 0
+    if moved is not None:
+        moved[:] = [([], []) for _ in parts]
     for want_r2 in (False, True):
-        for (ov, pool), (lo, hi) in zip(parts, ranges):
+        for rank, ((ov, pool), (lo, hi)) in enumerate(zip(parts, ranges)):
             cnt = hi - lo
             split = int(np.searchsorted(ov["read"], cnt, side="left"))
             seg = ov[split:] if want_r2 else ov[:split]
@@ -63,6 +67,8 @@ def merge_alignments(parts, ranges, n_pairs: int, cigar_cap: int = 0):
                 starts = np.cumsum(lens) - lens
                 idx = np.repeat(seg["cigar_off"].astype(np.int64) - starts, lens) + np.arange(int(lens.sum()), dtype=np.int64)
                 segs_cg.append(pool[idx])
+                if moved is not None:
+                    moved[rank][0].append(seg["cigar_off"].astype(np.int64)); moved[rank][1].append(starts + base)
                 seg["cigar_off"] = (starts + base).astype(np.uint32)
                 base += int(lens.sum())
             segs_ov.append(seg)
@@ -71,13 +77,23 @@ def merge_alignments(parts, ranges, n_pairs: int, cigar_cap: int = 0):
     return ov, pool
 
 
-def merge_pairs(parts, ranges, n_pairs: int):
+def merge_pairs(parts, ranges, n_pairs: int, moved=None):
     """parts[r] = (sorted_overlaps, pairs) of rank r; pair ids are contiguous per rank so rank order is the
-    global (pair id, entry, rel) order; r1_idx / r2_idx are rebased onto the concatenated overlap array."""
+    global (pair id, entry, rel) order; r1_idx / r2_idx are rebased onto the concatenated overlap array. With `moved`
+    (from merge_alignments) the cigar_off of every pair-sorted overlap is rebased onto the merged CIGAR pool too; without
+    it they keep indexing the rank's own pool."""
     mid = n_pairs
     ovs, prs, base = [], [], 0
-    for (so, pr), (lo, hi) in zip(parts, ranges):
+    for rank, ((so, pr), (lo, hi)) in enumerate(zip(parts, ranges)):
         so = so.copy(); pr = pr.copy()
+        if moved is not None and len(so) and moved[rank][0]:
+            old = np.concatenate(moved[rank][0]); new = np.concatenate(moved[rank][1])
+            order = np.argsort(old, kind="stable")
+            old, new = old[order], new[order]
+            has = so["cigar_len"] > 0                      # (records without a CIGAR carry no meaningful offset)
+            at = np.searchsorted(old, so["cigar_off"][has].astype(np.int64))
+            assert (at < len(old)).all() and (old[at] == so["cigar_off"][has]).all(), "a pair-sorted overlap points outside its rank's CIGARs"
+            off = so["cigar_off"].copy(); off[has] = new[at].astype(np.uint32); so["cigar_off"] = off
         so["read"] = globalize_reads(so["read"], lo, hi - lo, mid)
         for f in ("r1_idx", "r2_idx"):
             pr[f] = np.where(pr[f] >= 0, pr[f] + base, -1)
@@ -97,6 +113,7 @@ def align_sharded(align_fn, bases, offs, rank: int, world: int, gather_fn):
     cap = (len(pool) // max(1, len(ov))) if len(ov) and len(pool) else 0
     gathered = gather_fn((ov, pool, so, pr, cap))
     cap = max(g[4] for g in gathered)
-    m_ov, m_pool = merge_alignments([(g[0], g[1]) for g in gathered], ranges, n_pairs, cap)
-    m_so, m_pr = merge_pairs([(g[2], g[3]) for g in gathered], ranges, n_pairs)
+    moved = []
+    m_ov, m_pool = merge_alignments([(g[0], g[1]) for g in gathered], ranges, n_pairs, cap, moved)
+    m_so, m_pr = merge_pairs([(g[2], g[3]) for g in gathered], ranges, n_pairs, moved)      # (m_so's CIGARs index m_pool as well)
     return m_ov, m_pool, m_so, m_pr

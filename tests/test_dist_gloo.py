@@ -38,4 +38,6 @@ def test_world2_gloo_matches_single_process(pkg, tmp_path):
     assert T.cigars_of(got["ov"], got["pool"]) == T.cigars_of(want["overlaps"], want["cigar_pool"])
     for f in FIELDS:
         assert np.array_equal(got["so"][f], want["pair_sorted_overlaps"][f]), f
+    # the pair-sorted overlaps follow their CIGARs into the merged pool (their cigar_off is rebased, not left rank-local)
+    assert T.cigars_of(got["so"], got["pool"]) == T.cigars_of(want["pair_sorted_overlaps"], want["cigar_pool"])
     assert np.array_equal(got["pr"], want["pairs"])
