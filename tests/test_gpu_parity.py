@@ -403,6 +403,28 @@ def test_ssw_diverged_reads_use_every_band_tier(pkg, shape, cigar):
         assert tm["sw_cells_computed"] < res[0]["sw_cells_computed"]
 
 
+INSIDE = [(1, 2, 3, 1), (3, 4, 9, 2), (2, 0, 2, 1), (1, 1, 2, 1), (3, 6, 10, 3), (2, 4, 3, 2), (1, 0, 1, 0)]
+
+
+@pytest.mark.parametrize("prm", INSIDE)
+def test_ssw_fast_domain_other_parameters(pkg, prm):
+    """Scoring parameters other than 2/3/5/2 INSIDE the plain-Gotoh domain (gap_extend < gap_open, mismatch <= 2 gap_extend):
+    the packed band kernels run, and every bound they are placed with depends on the parameters — the forward interval on
+    match, the anchored reverse band on match and both gap costs, the untracked rows on match, the diagonal shortcut on
+    match + mismatch. Diverged / gapped / partial pairs against the oracle (pinned to the reference for such sets in
+    tests/test_oracle_vs_ref.py)."""
+    m, x, go, ge = prm
+    q, qo, r, ro = diverged_pairs(pkg, 6_000, 150, 150, seed=900 + 7 * m + x + go)
+    P = T.default_params(report_cigar=1, match=m, mismatch=x, gap_open=go, gap_extend=ge)
+    want, wpool = T.ko_ssw_batch(q, qo, r, ro, P, cigar_cap=64)
+    with pkg.Aligner(report_cigar=True, max_cigar_ops=64, match=m, mismatch=x, gap_open=go, gap_extend=ge) as al:
+        assert al.fast
+        out, pool = al.ssw_batch(q, qo, r, ro)
+        tm = al.timings()
+    check_overlaps(out, pool, want, wpool, fields=FIELDS[4:])
+    assert tm["n_sw_slow"] == 0 and tm["n_sw_band"] > 3_000
+
+
 def test_radix_sort_matches_numpy(pkg):
     rng = np.random.default_rng(3)
     with pkg.Aligner() as al:
