@@ -518,7 +518,7 @@ k_sw_striped(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list
 // DRAM traffic for 400 k alignments, profiles/r1_ncu_summaries.txt).
 __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const SwScore &sc, int32_t ref0,
                                     int32_t read0, int32_t refLen, int32_t readLen, int32_t score, int32_t *h_b,
-                                    int32_t *e_b, int32_t *h_c, uint32_t arr_cap, uint8_t *dir, size_t dir_cap,
+                                    int32_t *e_b, int32_t *h_c, uint32_t hs /* stride of the three rolling arrays */, uint32_t arr_cap, uint8_t *dir, size_t dir_cap,
                                     size_t dstride, uint64_t *rowdir, uint32_t *cig, uint32_t cig_cap, bool reverse_out,
                                     uint32_t *overflow) {
   const int32_t go = sc.gap_open, ge = sc.gap_extend;
@@ -533,7 +533,7 @@ __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const S
     const int32_t aw = width < refLen + 2 ? width : refLen + 2;
     ws = width_d < refLen ? width_d : refLen;
     if ((uint32_t)aw > arr_cap || (rowdir ? (ws > 2 * SW_TB_MAXBAND + 1 || readLen > SW_TB_MAXROWS) : (size_t)ws * (size_t)readLen > dir_cap)) return -3;
-    for (int32_t j = 1; j < aw - 1; j++) h_b[j] = 0;
+    for (int32_t j = 1; j < aw - 1; j++) h_b[(j) * hs] = 0;
     // Window codes of the band cells of a row, one nibble per cell (bands up to 7: 15 cells): nibble k of `wwin` holds the
     // code of column i - band + k. A row needs ONE new code (column i + band); the plane loads of w_code were per cell.
     const bool windowed = band <= SW_TB_MAXBAND;
@@ -545,7 +545,7 @@ __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const S
       const int32_t beg = i - band > 0 ? i - band : 0, end = i + band < refLen - 1 ? i + band : refLen - 1;
       const int32_t edge = end + 1 < width - 1 ? end + 1 : width - 1;
       int32_t u = 0, f = 0;
-      h_b[0] = 0; e_b[0] = 0; h_b[edge] = 0; e_b[edge] = 0; h_c[0] = 0;
+      h_b[(0) * hs] = 0; e_b[(0) * hs] = 0; h_b[(edge) * hs] = 0; e_b[(edge) * hs] = 0; h_c[(0) * hs] = 0;
       const uint32_t qc = q_code(pl, t, (uint32_t)(read0 + i));
       uint8_t *dl = rowdir ? nullptr : dir + (size_t)ws * i * dstride;
       uint64_t rowbits = 0;
@@ -554,28 +554,28 @@ __device__ int32_t banded_traceback(const SwPlanes &pl, const SwTask &t, const S
       for (int32_t j = beg; j <= end; j++) {
         u = j - xoff + 1;
         const int32_t e = u + up, b = u - 1, d = e - 1;
-        int32_t t1 = i == 0 ? -go : h_b[e] - go;
-        int32_t t2 = i == 0 ? -ge : e_b[e] - ge;
+        int32_t t1 = i == 0 ? -go : h_b[(e) * hs] - go;
+        int32_t t2 = i == 0 ? -ge : e_b[(e) * hs] - ge;
         const int32_t ev = t1 > t2 ? t1 : t2;
         const uint32_t de = t1 > t2 ? 3u : 2u;
-        e_b[u] = ev;
-        t1 = h_c[b] - go; t2 = f - ge;
+        e_b[(u) * hs] = ev;
+        t1 = h_c[(b) * hs] - go; t2 = f - ge;
         f = t1 > t2 ? t1 : t2;
         const uint32_t df = t1 > t2 ? 5u : 4u;
         const int32_t e1 = ev > 0 ? ev : 0, f1 = f > 0 ? f : 0;
         t1 = e1 > f1 ? e1 : f1;
         const uint32_t wc = windowed ? (uint32_t)(wwin >> (4 * (j - i + band))) & 7u : w_code(pl, t, (uint32_t)(ref0 + j));
         const int32_t s = (wc == 4 || qc == 4) ? 0 : (wc == qc ? sc.match : -sc.mismatch);
-        t2 = h_b[d] + s;
+        t2 = h_b[(d) * hs] + s;
         const int32_t hv = t1 > t2 ? t1 : t2;
-        h_c[u] = hv;
+        h_c[(u) * hs] = hv;
         if (hv > maxv) maxv = hv;
         const uint32_t dh = t1 <= t2 ? 1u : (e1 > f1 ? de : df);
         if (rowdir) rowbits |= (uint64_t)((de == 3u) | ((df == 5u) << 1) | ((dh == 1u ? 0u : (dh <= 3u ? 1u : 2u)) << 2)) << (4 * (j - xoff));
         else dl[(size_t)(j - xoff) * dstride] = (uint8_t)((de == 3u) | ((df == 5u) << 1) | (dh << 2));
       }
       if (rowdir) rowdir[i] = rowbits;
-      for (int32_t j = 1; j <= u; j++) h_b[j] = h_c[j];
+      for (int32_t j = 1; j <= u; j++) h_b[(j) * hs] = h_c[(j) * hs];
       if (windowed) {
         wwin >>= 4;
         const int32_t col = i + 1 + band;
@@ -690,7 +690,11 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
                uint32_t *__restrict__ overflow_count, uint8_t *__restrict__ big, size_t big_per_thread) {
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t nthreads = gridDim.x * blockDim.x;
-  int32_t l_hb[SW_TB_MAXBAND * 2 + 3], l_eb[SW_TB_MAXBAND * 2 + 3], l_hc[SW_TB_MAXBAND * 2 + 3];
+  // the three rolling arrays of banded_sw, touched for every cell: shared memory, [slot][thread] (conflict-free). In local
+  // memory they (and the direction words) took 1.5 KB per thread — 3 MB per SM at full occupancy, far beyond L1 — and every
+  // cell waited on L2. The direction words stay in local memory: one coalesced store per row, read once by the trace.
+  __shared__ int32_t s_roll[3 * (SW_TB_MAXBAND * 2 + 3) * 128];
+  int32_t *l_hb = s_roll + threadIdx.x, *l_eb = l_hb + (SW_TB_MAXBAND * 2 + 3) * 128, *l_hc = l_eb + (SW_TB_MAXBAND * 2 + 3) * 128;
   uint64_t l_rowdir[SW_TB_MAXROWS];
   for (uint32_t k = gtid; k < n; k += nthreads) {
     const uint32_t idx = list ? list[k] : k;
@@ -713,14 +717,14 @@ k_sw_traceback(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, 
             cig[0] = (uint32_t)readLen << 4; len = 1;
           } else len = -3;
         } else if (mode == 1)
-          len = banded_traceback(pl, t, sc, r.ref_begin, r.read_begin, refLen, readLen, r.score, l_hb, l_eb, l_hc,
+          len = banded_traceback(pl, t, sc, r.ref_begin, r.read_begin, refLen, readLen, r.score, l_hb, l_eb, l_hc, 128,
                                  SW_TB_MAXBAND * 2 + 3, nullptr, 0, 1, l_rowdir, cig, sc.cigar_cap, rev && unflip, &overflow);
         else {
           uint8_t *base = big + (size_t)gtid * big_per_thread;
           const uint32_t arr_cap = (uint32_t)(big_per_thread / 64);   // ints per rolling array
           int32_t *hb = reinterpret_cast<int32_t *>(base), *eb = hb + arr_cap, *hc = eb + arr_cap;
           uint8_t *d = base + (size_t)arr_cap * 12;
-          len = banded_traceback(pl, t, sc, r.ref_begin, r.read_begin, refLen, readLen, r.score, hb, eb, hc, arr_cap, d,
+          len = banded_traceback(pl, t, sc, r.ref_begin, r.read_begin, refLen, readLen, r.score, hb, eb, hc, 1, arr_cap, d,
                                  big_per_thread - (size_t)arr_cap * 12, 1, nullptr, cig, sc.cigar_cap, rev && unflip, &overflow);
         }
         if (len == -3) {
