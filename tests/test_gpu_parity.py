@@ -403,7 +403,7 @@ def test_ssw_diverged_reads_use_every_band_tier(pkg, shape, cigar):
         assert tm["sw_cells_computed"] < res[0]["sw_cells_computed"]
 
 
-INSIDE = [(1, 2, 3, 1), (3, 4, 9, 2), (2, 0, 2, 1), (1, 1, 2, 1), (3, 6, 10, 3), (2, 4, 3, 2), (1, 0, 1, 0)]
+INSIDE = [(1, 2, 3, 1), (3, 4, 9, 2), (2, 0, 2, 1), (1, 1, 2, 1), (2, 4, 12, 7), (2, 4, 3, 2), (1, 0, 1, 0)]       # (the packed cells hold match <= 3, mismatch <= 4)
 
 
 @pytest.mark.parametrize("prm", INSIDE)
