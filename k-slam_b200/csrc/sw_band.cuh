@@ -33,7 +33,7 @@
 // shared-memory selector streams of one CTA, word w of thread t at [w * SWB_BLOCK + t] (conflict-free): per alignment
 // (SWB_MAXROWS + W + 4) column-selector bytes, plus one byte per query row holding both alignments' row codes
 template <int W> struct BandSmem {      // W = slots per lane; + 4: the lanes of a multi-lane band lag up to 3 rows
-  static constexpr int COLW = (SWB_MAXROWS + 4 + W + 4 + 3) / 4;
+  static constexpr int COLW = (SWB_MAXROWS + 4 + W + 4 + 7) / 8;        // column stream: one NIBBLE per column, eight per word
   static constexpr int QW = (SWB_MAXROWS + 4 + 4 + 3) / 4;
   static constexpr int WORDS = 2 * COLW + QW;
   static constexpr size_t BYTES = (size_t)WORDS * SWB_BLOCK * 4;
@@ -141,13 +141,13 @@ __device__ __forceinline__ BandGeo band_geo(const SwTask &t, const SwRes &r, con
 template <int MODE>
 __device__ __forceinline__ void fill_col_stream(const SwPlanes &pl, const SwTask &t, const SwRes &r, const BandGeo &g, bool is_b,
                                                 int32_t kmax, uint32_t *__restrict__ col) {
+  (void)is_b;                                               // (the streams hold codes; col_selectors() makes them selectors)
   constexpr bool REVERSE = MODE == 1;
   const bool rev = (t.flags & SWT_REV) != 0;
   // genome position of matrix column j is P0 + sg * j (window reversal and the reverse sweep both flip the sign)
   int32_t P0, sg;
   if (!REVERSE) { P0 = rev ? (int32_t)(t.w_start + t.n - 1) : (int32_t)t.w_start; sg = rev ? -1 : 1; }
   else { P0 = rev ? (int32_t)(t.w_start + t.n - 1) - r.ref_end : (int32_t)t.w_start + r.ref_end; sg = rev ? 1 : -1; }
-  const uint32_t LUT = is_b ? 0xF7E6D5C4u : 0xB3A29180u, OUT = is_b ? 0xCCu : 0x88u;
   for (int32_t k0 = 0; k0 < kmax; k0 += 32) {
     const int32_t j0 = g.c0 + k0;
     const int32_t lo = j0 < 0 ? -j0 : 0, hi = g.cols - j0 < 32 ? g.cols - j0 : 32;
@@ -166,19 +166,25 @@ __device__ __forceinline__ void fill_col_stream(const SwPlanes &pl, const SwTask
       }
     }
 #pragma unroll
-    for (int grp = 0; grp < 8; grp++) {
-      if (k0 + 4 * grp >= kmax) break;
-      const uint32_t x8 = (uint32_t)(codes >> (8 * grp)) & 0xffu;
-      uint32_t nib = (x8 | (x8 << 4)) & 0x0f0fu; nib = (nib | (nib << 2)) & 0x3333u;      // nibble b = code of column b
-      uint32_t bytes = prmt(LUT, 0u, nib);
-      const uint32_t v4 = (valid >> (4 * grp)) & 15u;
-      if (v4 != 15u) {
-#pragma unroll
-        for (int b = 0; b < 4; b++) if (!((v4 >> b) & 1u)) bytes = (bytes & ~(0xffu << (8 * b))) | (OUT << (8 * b));
+    for (int grp = 0; grp < 4; grp++) {                      // eight columns per word: nibble = 2-bit code, 4 = outside the matrix
+      if (k0 + 8 * grp >= kmax) break;
+      uint32_t n = (uint32_t)(codes >> (16 * grp)) & 0xffffu;
+      n = (n | (n << 8)) & 0x00ff00ffu; n = (n | (n << 4)) & 0x0f0f0f0fu; n = (n | (n << 2)) & 0x33333333u;
+      const uint32_t inv = ~(valid >> (8 * grp)) & 0xffu;
+      if (inv) {
+        uint32_t m = (inv | (inv << 12)) & 0x000f000fu; m = (m | (m << 6)) & 0x03030303u; m = (m | (m << 3)) & 0x11111111u;   // bit 0 of nibble b
+        n = (n & ~(m * 3u)) | (m << 2);
       }
-      col[(size_t)(k0 / 4 + grp) * SWB_BLOCK] = bytes;
+      col[(size_t)(k0 / 8 + grp) * SWB_BLOCK] = n;
     }
   }
+}
+// four selector bytes (columns k .. k + 3 of a nibble stream, k a multiple of 4) for alignment A (nibbles {w, 8|w} on
+// profile A) or B ({4|w, 12|w} on profile B); outside the matrix: replicate the sign of byte 0. PRMT reads the low 16
+// bits of its selector only, so the four nibbles need no masking.
+__device__ __forceinline__ uint32_t col_selectors(const uint32_t *__restrict__ col, int32_t k, bool is_b) {
+  const uint32_t w = col[(size_t)(k >> 3) * SWB_BLOCK] >> (4 * (k & 7));
+  return is_b ? prmt(0xF7E6D5C4u, 0x000000CCu, w) : prmt(0xB3A29180u, 0x00000088u, w);
 }
 
 // row codes of one alignment for rows 32g .. 32g+31 of the sweep as bytes in four-row words: 0-3 = base, 4 = code-4
@@ -222,8 +228,11 @@ __device__ __forceinline__ void q_group(const SwPlanes &pl, const SwTask &t, int
 // LAST cell of this step (one row further down, one column to the left in band terms = the same matrix column) is the
 // one that needs it. Two shuffles per row and lane; everything else is the one-lane sweep with c0 advanced by
 // part * (WP - 1) and the query rows delayed by `part`.
+// resident CTAs per SM a tier is compiled for: narrow single-lane tiers need few registers and, with nibble streams, 22 KB
+// of shared memory per CTA — their stalls are the plane loads of the stream fill, which more warps hide
+template <int WP, int PARTS> struct BandOcc { static constexpr int CTAS = PARTS > 1 ? 6 : (WP <= 8 ? 10 : (WP <= 16 ? 9 : (WP <= 24 ? 7 : 6))); };
 template <int MODE, int WP, int PARTS>
-__global__ void __launch_bounds__(SWB_BLOCK, (WP > 32 ? 4 : 6))
+__global__ void __launch_bounds__(SWB_BLOCK, (BandOcc<WP, PARTS>::CTAS))
 k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, uint32_t n_list, SwPlanes pl, SwScore sc,
           SwRes *__restrict__ res, Rec16 *__restrict__ fb_keys, uint32_t *__restrict__ fb_count,
           uint32_t *__restrict__ next_list, uint32_t *__restrict__ next_count, uint8_t *__restrict__ tier_f,
@@ -284,7 +293,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
   uint32_t H[WP], V[WP], sel[WP];
 #pragma unroll
   for (int t = 0; t < WP; t += 4) {
-    const uint32_t wa = colA[(size_t)(t / 4) * SWB_BLOCK], wb = colB[(size_t)(t / 4) * SWB_BLOCK];
+    const uint32_t wa = col_selectors(colA, t, false), wb = col_selectors(colB, t, true);
 #pragma unroll
     for (int r = 0; r < 4; r++) { H[t + r] = K2; V[t + r] = K2; sel[t + r] = prmt(wa, wb, (uint32_t)(((4 + r) << 4) | r)); }
   }
@@ -311,7 +320,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
   for (int32_t i0 = i_begin; i0 < i_end; i0 += 4) {
     uint32_t qword = qAB[(size_t)(i0 / 4) * SWB_BLOCK];
     if (PARTS > 1) { const uint32_t qcur = qword; qword = __byte_perm(qprev, qcur, qshift); qprev = qcur; }
-    const uint32_t ewa = colA[(size_t)((i0 + WP) / 4) * SWB_BLOCK], ewb = colB[(size_t)((i0 + WP) / 4) * SWB_BLOCK];
+    const uint32_t ewa = col_selectors(colA, i0 + WP, false), ewb = col_selectors(colB, i0 + WP, true);
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const int32_t i = i0 + r - (int32_t)part;               // the matrix row this lane works on (negative: not started)
