@@ -45,8 +45,8 @@ struct __align__(16) SwTask {
   uint32_t flags;    // bit0: window is reverse-complemented; bits 8-15: class
 };
 #define SWT_REV 1u
-#define SWT_BAND 2u   // shape allows the banded kernel (rows <= 160, no code-4 base in the window)
-#define SWT_CLEAN 4u  // no code-4 base in the window
+#define SWT_BAND 2u   // shape allows the banded kernel (rows <= 160)
+#define SWT_CLEAN 4u  // no code-4 base in the window (SWT_BAND without it: the masked variants of the band tiers)
 #define SWC_FAST8 0u    // full-matrix kernel classes: 8 / 16 / 32 lanes x SW_R rows = reads up to 160 / 320 / 640 bases
 #define SWC_FAST16 1u
 #define SWC_FAST32 2u
@@ -65,11 +65,19 @@ struct __align__(16) SwRes {
 // 12 = 32 diagonals centred, sweep-and-verify; 255 = not in a band list. A forward tier byte with SWT_SWEPT set: the
 // alignment went through the 32-wide trial sweep first and then into that tier with the score the sweep found as its bound.
 // Tier code in SwRes.flags: tier + 1, 0 = full-matrix / scalar kernel.
+// A tier byte with SWT_NCOL set: the window has code-4 columns (score 0 against every row, ssw_cpp.cpp:43-48), which a
+// PRMT column selector cannot express; such alignments run the NCOL instances of the kernel (a second PRMT per cell masks
+// the score), which exist for the tiers of 16, 32, 64 and 128 diagonals and the trial sweep, and have lists of their own
+// (list index = tier, + SWT_N_TIERS for NCOL).
 #define SWT_N_DIRECT 12u
 #define SWT_TIER_SWEEP 12u
 #define SWT_N_TIERS 13u
+#define SWT_N_LISTS 26u
+#define SWT_NCOL 0x20u
 #define SWT_SWEPT 0x40u
 #define SWT_TIER_NONE 255u
+__host__ __device__ __forceinline__ uint32_t tier_list(uint32_t t) { return (t & SWT_NCOL) ? SWT_N_TIERS + (t & 0x1fu) : (t & 0x1fu); }   // t != SWT_TIER_NONE
+__host__ __device__ __forceinline__ uint32_t ncol_tier(uint32_t t) { return t <= 1 ? 1u : t <= 3 ? 3u : t <= 7 ? 7u : 11u; }             // direct tier -> the NCOL tier that holds it
 #define SWR_FWD_TIER(code) ((uint32_t)(code) << 8)
 #define SWR_REV_TIER(code) ((uint32_t)(code) << 12)
 __host__ __device__ __forceinline__ constexpr uint32_t tier_width(uint32_t t) { return t < 8 ? 8u * (t + 1) : t == 8 ? 72u : t == 9 ? 80u : t == 10 ? 96u : 128u; }
@@ -87,6 +95,7 @@ struct SwScore {
   uint32_t literal;   // 1: scoring parameters outside the plain-Gotoh domain -> every alignment runs k_sw_striped
   uint32_t max_band;  // widest band tier in use (128; KSLAM_SW_MAX_BAND=64 leaves the multi-lane tiers out: ablation)
   uint32_t anchored;  // 1: reverse sweeps run in the anchored band (KSLAM_SW_REV_ANCHOR=0: the interval [-(rows - a), cols - a])
+  uint32_t ncol;      // 1: windows with code-4 columns run the masked band tiers (KSLAM_SW_NCOL=0: the full-matrix kernel, as before)
 };
 
 struct SwWorkspace {
@@ -149,10 +158,10 @@ __host__ __device__ __forceinline__ uint32_t tier_of_interval(int32_t width, uin
 #define CNT_EXTRA 5
 #define CNT_OVERFLOW 7   // alignments whose CIGAR has more ops than the pool stride (KSLAM_FLAG_CIGAR_OVERFLOW)
 #define CNT_NEXT 8       // failures of the sweep tier that go on to a direct tier (second round)
-#define CNT_TIER 16      // SWT_N_TIERS counters: alignments per work-list tier
-#define CNT_CUR 32       // SWT_N_TIERS cursors of k_tier_scatter
-#define CNT_TIER2 48     // SWT_N_DIRECT counters: second-round alignments per tier
-#define CNT_WORDS 64
+#define CNT_TIER 16      // SWT_N_LISTS counters: alignments per work list
+#define CNT_CUR 42       // SWT_N_LISTS cursors of k_tier_scatter
+#define CNT_TIER2 68     // 2 * SWT_N_DIRECT counters: second-round alignments per direct tier (clean, NCOL)
+#define CNT_WORDS 92
 
 #include "sw_band.cuh"
 
@@ -800,13 +809,13 @@ __device__ __forceinline__ uint32_t tier_of_width(int32_t rows, int32_t cols, in
 // (dead threads with SWT_TIER_NONE). Per-warp global atomics — 5 M warps x up to 6 tiers on six addresses — serialised in
 // L2: k_sw_rev_lists took 14.5 ms for 167 M alignments (profiles/r2_launches_bench_config2.txt), 10 ms of it these atomics.
 __device__ __forceinline__ void count_tier_block(uint32_t tier, uint32_t *__restrict__ counts) {
-  __shared__ uint32_t s_cnt[SWT_N_TIERS];
-  if (threadIdx.x < SWT_N_TIERS) s_cnt[threadIdx.x] = 0;
+  __shared__ uint32_t s_cnt[SWT_N_LISTS];
+  if (threadIdx.x < SWT_N_LISTS) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t peers = __match_any_sync(0xffffffffu, tier);
-  if (tier != SWT_TIER_NONE && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_cnt[tier], (uint32_t)__popc(peers));
+  if (tier != SWT_TIER_NONE && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&s_cnt[tier_list(tier)], (uint32_t)__popc(peers));
   __syncthreads();
-  if (threadIdx.x < SWT_N_TIERS && s_cnt[threadIdx.x]) atomicAdd(&counts[CNT_TIER + threadIdx.x], s_cnt[threadIdx.x]);
+  if (threadIdx.x < SWT_N_LISTS && s_cnt[threadIdx.x]) atomicAdd(&counts[CNT_TIER + threadIdx.x], s_cnt[threadIdx.x]);
 }
 
 __device__ __forceinline__ uint32_t classify(uint32_t m, uint32_t n, const SwScore &sc) {
@@ -856,6 +865,7 @@ __device__ __forceinline__ uint32_t enlist(const SwPlanes &pl, const SwTask &t, 
     SwRes o; o.score = 0; o.ref_end = -1; o.read_end = 0; o.ref_begin = -1; o.read_begin = 0; o.flags = 0; o.pad0 = o.pad1 = 0;
     res[i] = o;
   } else if (cls == SWC_SLOW) slow_list[list_slot(&counts[CNT_SLOW])] = i;
+  else if ((t.flags & SWT_BAND) && !(t.flags & SWT_CLEAN)) tier = SWT_TIER_SWEEP | SWT_NCOL;   // code-4 columns: trial sweep of the masked variant
   else if (t.flags & SWT_BAND) {
     tier = SWT_TIER_SWEEP;
     if (level >= 3) {
@@ -872,19 +882,19 @@ __device__ __forceinline__ uint32_t enlist(const SwPlanes &pl, const SwTask &t, 
 // (src: the alignments to list, nullptr = all of 0..n-1; counts: the per-tier totals the lists are laid out by)
 __global__ void __launch_bounds__(256)
 k_tier_scatter(const uint8_t *__restrict__ tier, const uint32_t *__restrict__ src, uint32_t n, const uint32_t *__restrict__ counts,
-               uint32_t *__restrict__ cursors, uint32_t *__restrict__ list) {
-  __shared__ uint32_t s_wcnt[8][SWT_N_TIERS];          // per warp and tier: members, then the warp's offset inside the CTA's run
-  __shared__ uint32_t s_base[SWT_N_TIERS];             // where the CTA's run of a tier starts in that tier's list
+               uint32_t *__restrict__ cursors, uint32_t *__restrict__ list, uint32_t ncol_base /* first list of the NCOL tiers */) {
+  __shared__ uint32_t s_wcnt[8][SWT_N_LISTS];          // per warp and list: members, then the warp's offset inside the CTA's run
+  __shared__ uint32_t s_base[SWT_N_LISTS];             // where the CTA's run of a list starts in that list
   const uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t i = k0 < n ? (src ? src[k0] : k0) : 0u;
   uint32_t t = k0 < n ? tier[i] : SWT_TIER_NONE;
-  if (t != SWT_TIER_NONE) t &= ~SWT_SWEPT;
-  if (threadIdx.x < 8 * SWT_N_TIERS) (&s_wcnt[0][0])[threadIdx.x] = 0;
+  if (t != SWT_TIER_NONE) t = (t & SWT_NCOL) ? ncol_base + (t & 0x1fu) : (t & 0x1fu);
+  if (threadIdx.x < 8 * SWT_N_LISTS) (&s_wcnt[0][0])[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t peers = __match_any_sync(0xffffffffu, t);
   if (t != SWT_TIER_NONE && lane == (uint32_t)(__ffs(peers) - 1)) s_wcnt[warp][t] = (uint32_t)__popc(peers);
   __syncthreads();
-  if (threadIdx.x < SWT_N_TIERS) {                       // one global atomic per (CTA, tier)
+  if (threadIdx.x < SWT_N_LISTS) {                       // one global atomic per (CTA, list)
     uint32_t run = 0;
     for (int w = 0; w < 8; w++) { const uint32_t c = s_wcnt[w][threadIdx.x]; s_wcnt[w][threadIdx.x] = run; run += c; }
     uint32_t off = 0;
@@ -912,7 +922,7 @@ prepare_seed(uint32_t i, const kslam_seed *__restrict__ seeds, const uint64_t *_
   const uint32_t cls = classify(t.m, t.n, sc);
   t.flags = (s.rev_comp ? SWT_REV : 0u) | (cls << 8);
   if (cls != SWC_NONE && window_clean(g_nmask, t.w_word, t.w_start, t.n)) t.flags |= SWT_CLEAN;
-  if (use_band && cls == SWC_FAST8 && band_shape_ok(t.m, t.n) && (t.flags & SWT_CLEAN)) t.flags |= SWT_BAND;
+  if (use_band && cls == SWC_FAST8 && band_shape_ok(t.m, t.n) && ((t.flags & SWT_CLEAN) || (use_band >= 3 && sc.ncol))) t.flags |= SWT_BAND;
   tasks[i] = t;
   // matrix diagonal of the seed's exact 32-mer match: forward seeds put read base i on genome base rel + i; reverse-
   // complement seeds put rc(read) base i there and Align sees the window reversed (SmithWaterman.h:205-208)
@@ -948,7 +958,7 @@ k_sw_prepare_pairs(uint32_t n, const uint64_t *__restrict__ q_offs, const uint64
     const uint32_t cls = classify(t.m, t.n, sc);
     t.flags = cls << 8;
     if (cls != SWC_NONE && window_clean(r_nmask, t.w_word, 0, t.n)) t.flags |= SWT_CLEAN;
-    if (use_band && cls == SWC_FAST8 && band_shape_ok(t.m, t.n) && (t.flags & SWT_CLEAN)) t.flags |= SWT_BAND;
+    if (use_band && cls == SWC_FAST8 && band_shape_ok(t.m, t.n) && ((t.flags & SWT_CLEAN) || (use_band >= 3 && sc.ncol))) t.flags |= SWT_BAND;
     tasks[i] = t;
     tier = enlist(pl, t, i, cls, 0, false, use_band, sc, res, tier_f, full_keys, slow_list, counts);   // no seed: try the main diagonal
   }
@@ -980,7 +990,8 @@ k_sw_rev_lists(const SwTask *__restrict__ tasks, SwRes *__restrict__ res, uint32
         int32_t lo, hi;
         reverse_band(rows, cols, r.score, sc, &lo, &hi);
         tier = tier_of_interval(hi - lo + 1, level, sc);
-        if (lo == 0 && hi == 0 && sc.anchored && level >= 3) tier = SWT_TIER_SWEEP;     // (the reverse pass has no trial sweep: this list is k_sw_rev_diagonal's)
+        if (!(t.flags & SWT_CLEAN)) { if (tier != SWT_TIER_NONE) tier = ncol_tier(tier) | SWT_NCOL; }
+        else if (lo == 0 && hi == 0 && sc.anchored && level >= 3) tier = SWT_TIER_SWEEP;     // (the reverse pass has no trial sweep: this list is k_sw_rev_diagonal's)
       }
       if (tier == SWT_TIER_NONE) { const uint32_t k = list_slot(&counts[CNT_FULL]); full_keys[k].key = (uint64_t)cols | ((uint64_t)cls << 16); full_keys[k].val = i; }
     }
@@ -1048,16 +1059,16 @@ k_sw_cells(const SwTask *__restrict__ tasks, const SwRes *__restrict__ res, cons
     fw += (unsigned long long)t.m * t.n;
     const uint32_t tf = tier_f[i], tr = tier_r[i], ft = (r.flags >> 8) & 15u;
     unsigned long long quiet = r.score > 0 ? (unsigned long long)(((r.score + sc_match - 1) / sc_match - 1) & ~3) : 0ull;
-    if (tf == SWT_TIER_SWEEP || (tf != SWT_TIER_NONE && (tf & SWT_SWEPT))) { comp += 32ull * t.m; ops2 += 6ull * 32ull * t.m; }      // the trial sweep
-    if (tf != SWT_TIER_NONE && (tf & ~SWT_SWEPT) < SWT_N_DIRECT) {
-      const unsigned long long w = tier_width(tf & ~SWT_SWEPT), q = quiet < t.m ? quiet : t.m;
+    if (tf != SWT_TIER_NONE && ((tf & 0x1fu) == SWT_TIER_SWEEP || (tf & SWT_SWEPT))) { comp += 32ull * t.m; ops2 += 6ull * 32ull * t.m; }      // the trial sweep
+    if (tf != SWT_TIER_NONE && (tf & 0x1fu) < SWT_N_DIRECT) {
+      const unsigned long long w = tier_width(tf & 0x1fu), q = quiet < t.m ? quiet : t.m;
       comp += w * t.m; ops2 += w * (5ull * q + 6ull * (t.m - q));
     }
     if (ft == 0u) { comp += (unsigned long long)t.m * t.n; ops2 += 6ull * t.m * t.n; }
     if (r.score > 0) {
       const unsigned long long rows = (unsigned long long)(r.read_end + 1), cols = (unsigned long long)(r.ref_end + 1);
       rv += rows * cols;
-      if (tr < SWT_N_DIRECT) { const unsigned long long w = tier_width(tr), q = quiet < rows ? quiet : rows; comp += w * rows; ops2 += w * (5ull * q + 6ull * (rows - q)); }
+      if (tr != SWT_TIER_NONE && (tr & 0x1fu) < SWT_N_DIRECT) { const unsigned long long w = tier_width(tr & 0x1fu), q = quiet < rows ? quiet : rows; comp += w * rows; ops2 += w * (5ull * q + 6ull * (rows - q)); }
       else if (((r.flags >> 12) & 15u) != SWR_CODE_DIAGONAL) { comp += rows * cols; ops2 += 6ull * rows * cols; }      // (the diagonal shortcut sweeps nothing)
     }
   }
@@ -1114,6 +1125,8 @@ static SwScore make_score(const kslam_ctx *c) {
   static const char *mb = getenv("KSLAM_SW_MAX_BAND"), *ra = getenv("KSLAM_SW_REV_ANCHOR");
   s.max_band = mb && atoi(mb) == 64 ? 64u : 128u;
   s.anchored = ra && atoi(ra) == 0 ? 0u : 1u;
+  static const char *nc = getenv("KSLAM_SW_NCOL");
+  s.ncol = nc && atoi(nc) == 0 ? 0u : 1u;
   s.score_threshold = c->prm.score_threshold; s.report_cigar = c->prm.report_cigar; s.cigar_cap = c->prm.max_cigar_ops;
   return s;
 }
@@ -1126,14 +1139,14 @@ static uint32_t read_count(kslam_ctx *c, uint32_t *d_counts, uint32_t *h_counts,
 
 // one banded tier over a list: the sweep kernel unpacks its own selector streams into shared memory
 static uint32_t sw_level(const kslam_ctx *c);
-template <int MODE, int WP, int PARTS = 1>
+template <int MODE, int WP, int PARTS = 1, bool NCOL = false>
 static void run_band(kslam_ctx *c, const SwPlanes &pl, const SwScore &sc, const uint32_t *list, uint32_t n_list,
                      uint32_t *d_counts, uint32_t *next_list) {
   if (!n_list) return;
   SwWorkspace *w = c->sw;
   const uint32_t pairs = (n_list + 1) / 2, per_block = PARTS == 1 ? SWB_BLOCK : (SWB_BLOCK / 32) * (32 / PARTS);
   const uint32_t blocks = (pairs + per_block - 1) / per_block;
-  k_sw_band<MODE, WP, PARTS><<<blocks, SWB_BLOCK, BandSmem<WP>::BYTES, c->stream>>>(w->tasks.as<SwTask>(), list, n_list, pl, sc, w->res.as<SwRes>(),
+  k_sw_band<MODE, WP, PARTS, NCOL><<<blocks, SWB_BLOCK, BandSmem<WP>::BYTES, c->stream>>>(w->tasks.as<SwTask>(), list, n_list, pl, sc, w->res.as<SwRes>(),
       w->keys.as<Rec16>(), d_counts + CNT_FULL, next_list, d_counts + CNT_NEXT, w->tier.as<uint8_t>(), d_counts + CNT_TIER2, sw_level(c), 1u);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -1160,14 +1173,26 @@ static void run_tier(kslam_ctx *c, const SwPlanes &pl, const SwScore &sc, uint32
     default: run_band<MODE, 32, 4>(c, pl, sc, list, n_list, d_counts, nullptr); break;
   }
 }
+// ... and its masked variant for windows with code-4 columns (tiers of 16, 32, 64 and 128 diagonals only: ncol_tier())
+template <int MODE>
+static void run_tier_ncol(kslam_ctx *c, const SwPlanes &pl, const SwScore &sc, uint32_t t, const uint32_t *list, uint32_t n_list, uint32_t *d_counts) {
+  if (!n_list) return;
+  switch (t) {
+    case 1: run_band<MODE, 16, 1, true>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    case 3: run_band<MODE, 32, 1, true>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    case 7: run_band<MODE, 32, 2, true>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    case 11: run_band<MODE, 32, 4, true>(c, pl, sc, list, n_list, d_counts, nullptr); break;
+    default: throw ArgError{"internal: no masked band kernel for this tier"};
+  }
+}
 
 // tier byte array -> per-tier lists in `out` (of the alignments in src, nullptr = all n); d_cnt: the per-tier totals
 static void make_tier_lists(kslam_ctx *c, uint32_t n, const uint8_t *tier, const uint32_t *src, uint32_t *d_counts, uint32_t *h_counts,
                             uint32_t cnt_at, uint32_t n_tiers, uint32_t *out, uint32_t *cnt) {
   cudaStream_t st = c->stream;
-  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_CUR, 0, SWT_N_TIERS * 4, st));
+  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_CUR, 0, SWT_N_LISTS * 4, st));
   if (n) {
-    k_tier_scatter<<<(n + 255) / 256, 256, 0, st>>>(tier, src, n, d_counts + cnt_at, d_counts + CNT_CUR, out);
+    k_tier_scatter<<<(n + 255) / 256, 256, 0, st>>>(tier, src, n, d_counts + cnt_at, d_counts + CNT_CUR, out, n_tiers / 2);   // (lists: clean tiers, then NCOL tiers)
     c->launches++;
     CUDA_TRY(cudaGetLastError());
   }
@@ -1180,7 +1205,7 @@ static void make_tier_lists(kslam_ctx *c, uint32_t n, const uint8_t *tier, const
 // diagonals), forward only: the 32-wide sweep-and-verify tier and the 64-wide tier for what it could not prove but
 // bounded; then every remaining alignment through the full-matrix kernel, bucketed by column count
 template <bool REVERSE>
-static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore &sc, const uint32_t cnt[SWT_N_TIERS], uint32_t *d_counts,
+static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore &sc, const uint32_t cnt[SWT_N_LISTS], uint32_t *d_counts,
                     uint32_t *h_counts, uint64_t *n_band64_via_sweep, uint64_t *n_full_done) {
   SwWorkspace *w = c->sw;
   cudaStream_t st = c->stream;
@@ -1188,10 +1213,11 @@ static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore 
   SwRes *res = w->res.as<SwRes>();
   uint32_t *lists = w->lists.as<uint32_t>(), *next = lists + 2 * (size_t)n, *lists2 = lists + 3 * (size_t)n;
   Rec16 *keys = w->keys.as<Rec16>(), *keys2 = w->keys2.as<Rec16>();
-  uint32_t off[SWT_N_TIERS + 1] = {0};
-  for (uint32_t t = 1; t <= SWT_N_TIERS; t++) off[t] = off[t - 1] + cnt[t - 1];
+  uint32_t off[SWT_N_LISTS + 1] = {0};
+  for (uint32_t t = 1; t <= SWT_N_LISTS; t++) off[t] = off[t - 1] + cnt[t - 1];
   constexpr int DM = REVERSE ? 1 : 2;
   for (uint32_t t = 0; t < SWT_N_DIRECT; t++) run_tier<DM>(c, pl, sc, t, lists + off[t], cnt[t], d_counts);
+  for (uint32_t t = 0; t < SWT_N_DIRECT; t++) run_tier_ncol<DM>(c, pl, sc, t, lists + off[SWT_N_TIERS + t], cnt[SWT_N_TIERS + t], d_counts);
   if (REVERSE && cnt[SWT_TIER_SWEEP]) {
     // one-diagonal bands: begin coordinates from a word-parallel diagonal score, no sweep; what it cannot settle runs 8 diagonals
     CUDA_TRY(cudaMemsetAsync(d_counts + CNT_NEXT, 0, 4, st));
@@ -1203,13 +1229,17 @@ static void sw_pass(kslam_ctx *c, uint32_t n, const SwPlanes &pl, const SwScore 
     run_band<1, 8>(c, pl, sc, next, n_next, d_counts, nullptr);
     c->tm.n_sw_rev_diagonal = cnt[SWT_TIER_SWEEP] - n_next;
   }
-  if (!REVERSE && cnt[SWT_TIER_SWEEP]) {
+  if (!REVERSE && cnt[SWT_TIER_SWEEP] + cnt[SWT_N_TIERS + SWT_TIER_SWEEP]) {
     // trial sweep; what it bounds but cannot prove goes through the direct tiers once more (second round)
     run_band<0, 32>(c, pl, sc, lists + off[SWT_TIER_SWEEP], cnt[SWT_TIER_SWEEP], d_counts, c->sw_band64 ? next : nullptr);
+    run_band<0, 32, 1, true>(c, pl, sc, lists + off[SWT_N_TIERS + SWT_TIER_SWEEP], cnt[SWT_N_TIERS + SWT_TIER_SWEEP], d_counts, c->sw_band64 ? next : nullptr);
     const uint32_t n_next = read_count(c, d_counts, h_counts, CNT_NEXT);
-    uint32_t cnt2[SWT_N_DIRECT], off2 = 0;
-    make_tier_lists(c, n_next, w->tier.as<uint8_t>(), next, d_counts, h_counts, CNT_TIER2, SWT_N_DIRECT, lists2, cnt2);
+    uint32_t cnt2[2 * SWT_N_DIRECT], off2 = 0;
+    make_tier_lists(c, n_next, w->tier.as<uint8_t>(), next, d_counts, h_counts, CNT_TIER2, 2 * SWT_N_DIRECT, lists2, cnt2);
     for (uint32_t t = 0; t < SWT_N_DIRECT; t++) { run_tier<2>(c, pl, sc, t, lists2 + off2, cnt2[t], d_counts); off2 += cnt2[t]; c->tm.n_sw_fwd_tier[t] += cnt2[t]; }
+    for (uint32_t t = 0; t < SWT_N_DIRECT; t++) {
+      run_tier_ncol<2>(c, pl, sc, t, lists2 + off2, cnt2[SWT_N_DIRECT + t], d_counts); off2 += cnt2[SWT_N_DIRECT + t]; c->tm.n_sw_fwd_tier[t] += cnt2[SWT_N_DIRECT + t];
+    }
     *n_band64_via_sweep += n_next;
   }
   const uint32_t n_full = read_count(c, d_counts, h_counts, CNT_FULL);
@@ -1281,31 +1311,31 @@ static void sw_run(kslam_ctx *c, uint32_t n, const SwPlanes &pl, kslam_overlap *
 
   // ---- forward
   cudaEvent_t e1 = tm_mark(c);
-  uint32_t cnt[SWT_N_TIERS];
-  make_tier_lists(c, n, tier_f, nullptr, d_counts, h_counts, CNT_TIER, SWT_N_TIERS, w->lists.as<uint32_t>(), cnt);
+  uint32_t cnt[SWT_N_LISTS];
+  make_tier_lists(c, n, tier_f, nullptr, d_counts, h_counts, CNT_TIER, SWT_N_LISTS, w->lists.as<uint32_t>(), cnt);
   const uint32_t n_slow = read_count(c, d_counts, h_counts, CNT_SLOW);
-  for (uint32_t t = 0; t < SWT_N_DIRECT; t++) c->tm.n_sw_fwd_tier[t] = cnt[t];
+  for (uint32_t t = 0; t < SWT_N_DIRECT; t++) c->tm.n_sw_fwd_tier[t] = cnt[t] + cnt[SWT_N_TIERS + t];
   uint64_t band64_sweep = 0, full_done = 0;
   sw_pass<false>(c, n, pl, sc, cnt, d_counts, h_counts, &band64_sweep, &full_done);
   c->tm.n_sw_fast = full_done; c->tm.n_sw_slow = n_slow;
   c->tm.n_sw_band = 0;
-  for (uint32_t t = 0; t < SWT_N_TIERS; t++) c->tm.n_sw_band += cnt[t];
+  for (uint32_t t = 0; t < SWT_N_LISTS; t++) c->tm.n_sw_band += cnt[t];
   c->tm.n_sw_band64 = cnt[7] + band64_sweep;        // the 64-wide tier + everything that ran a direct tier after the trial sweep
   c->tm.n_sw_tier96 = cnt[10]; c->tm.n_sw_tier128 = cnt[11];
   c->tm.n_sw_tier8 = cnt[0]; c->tm.n_sw_tier16 = cnt[1]; c->tm.n_sw_tier32 = cnt[3]; c->tm.n_sw_tier48 = cnt[5]; c->tm.n_sw_tier64 = cnt[7];
-  c->tm.n_sw_sweep32 = cnt[SWT_TIER_SWEEP];
+  c->tm.n_sw_sweep32 = cnt[SWT_TIER_SWEEP] + cnt[SWT_N_TIERS + SWT_TIER_SWEEP];
   cudaEvent_t e2 = tm_mark(c);
 
   // ---- reverse
   CUDA_TRY(cudaMemsetAsync(d_counts + CNT_BAND, 0, 8, st));   // band + full counters
-  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_TIER, 0, SWT_N_TIERS * 4, st));
+  CUDA_TRY(cudaMemsetAsync(d_counts + CNT_TIER, 0, SWT_N_LISTS * 4, st));
   k_sw_rev_lists<<<nb, 256, 0, st>>>(tasks, res, n, sc, pl, tier_r, sw_level(c), w->keys.as<Rec16>(), d_counts);
   c->launches++;
-  make_tier_lists(c, n, tier_r, nullptr, d_counts, h_counts, CNT_TIER, SWT_N_TIERS, w->lists.as<uint32_t>(), cnt);
+  make_tier_lists(c, n, tier_r, nullptr, d_counts, h_counts, CNT_TIER, SWT_N_LISTS, w->lists.as<uint32_t>(), cnt);
   uint64_t dummy = 0, full_rev = 0;
   sw_pass<true>(c, n, pl, sc, cnt, d_counts, h_counts, &dummy, &full_rev);
   c->tm.n_sw_band_rev = 0;
-  for (uint32_t t = 0; t < SWT_N_DIRECT; t++) { c->tm.n_sw_rev_tier[t] = cnt[t]; c->tm.n_sw_band_rev += cnt[t]; }
+  for (uint32_t t = 0; t < SWT_N_DIRECT; t++) { c->tm.n_sw_rev_tier[t] = cnt[t] + cnt[SWT_N_TIERS + t]; c->tm.n_sw_band_rev += cnt[t] + cnt[SWT_N_TIERS + t]; }
   cudaEvent_t e3 = tm_mark(c);
 
   // ---- exact scalar fallback for shapes outside the fast kernels

@@ -138,7 +138,9 @@ __device__ __forceinline__ BandGeo band_geo(const SwTask &t, const SwRes &r, con
 // for alignment A (low half of the s16x2 registers) nibbles {w, 8|w}: copy byte w of profile A and replicate its sign;
 // for B nibbles {4|w, 12|w} on profile B; columns outside the matrix replicate the sign of byte 0 (score 0 or -1, never
 // positive). 32 columns are fetched as one oriented 2-bit word and turned into bytes four at a time by one PRMT.
-template <int MODE>
+// NCOL: the window may hold code-4 bases; their columns get nibble 5 (the selector LUTs answer it with a byte whose bit 7
+// is clear, which make_selector turns into a masking second selector).
+template <int MODE, bool NCOL>
 __device__ __forceinline__ void fill_col_stream(const SwPlanes &pl, const SwTask &t, const SwRes &r, const BandGeo &g, bool is_b,
                                                 int32_t kmax, uint32_t *__restrict__ col) {
   (void)is_b;                                               // (the streams hold codes; col_selectors() makes them selectors)
@@ -151,7 +153,7 @@ __device__ __forceinline__ void fill_col_stream(const SwPlanes &pl, const SwTask
   for (int32_t k0 = 0; k0 < kmax; k0 += 32) {
     const int32_t j0 = g.c0 + k0;
     const int32_t lo = j0 < 0 ? -j0 : 0, hi = g.cols - j0 < 32 ? g.cols - j0 : 32;
-    uint32_t valid = 0;
+    uint32_t valid = 0, ncols = 0;
     uint64_t codes = 0;
     if (hi > lo) {
       valid = (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u) << lo);
@@ -159,10 +161,12 @@ __device__ __forceinline__ void fill_col_stream(const SwPlanes &pl, const SwTask
         const int32_t p = P0 + j0;
         codes = bits_at(pl.w_sbits, t.w_word, p);
         if (rev) codes ^= pair_mask(~mask_at(pl.w_xmask, t.w_word, p));          // complement unless a/c/g/t/U/u
+        if (NCOL) ncols = mask_at(pl.w_nmask, t.w_word, p) & valid;
       } else {
         const int32_t p = P0 - j0 - 31;                                            // column j0 + b <-> base p + 31 - b
         codes = reverse_pairs(bits_at(pl.w_sbits, t.w_word, p));
         if (rev) codes ^= pair_mask(~__brev(mask_at(pl.w_xmask, t.w_word, p)));
+        if (NCOL) ncols = __brev(mask_at(pl.w_nmask, t.w_word, p)) & valid;
       }
     }
 #pragma unroll
@@ -175,6 +179,13 @@ __device__ __forceinline__ void fill_col_stream(const SwPlanes &pl, const SwTask
         uint32_t m = (inv | (inv << 12)) & 0x000f000fu; m = (m | (m << 6)) & 0x03030303u; m = (m | (m << 3)) & 0x11111111u;   // bit 0 of nibble b
         n = (n & ~(m * 3u)) | (m << 2);
       }
+      if (NCOL) {
+        const uint32_t nc = (ncols >> (8 * grp)) & 0xffu;
+        if (nc) {
+          uint32_t m = (nc | (nc << 12)) & 0x000f000fu; m = (m | (m << 6)) & 0x03030303u; m = (m | (m << 3)) & 0x11111111u;
+          n = (n & ~(m * 15u)) | (m * 5u);
+        }
+      }
       col[(size_t)(k0 / 8 + grp) * SWB_BLOCK] = n;
     }
   }
@@ -184,7 +195,17 @@ __device__ __forceinline__ void fill_col_stream(const SwPlanes &pl, const SwTask
 // bits of its selector only, so the four nibbles need no masking.
 __device__ __forceinline__ uint32_t col_selectors(const uint32_t *__restrict__ col, int32_t k, bool is_b) {
   const uint32_t w = col[(size_t)(k >> 3) * SWB_BLOCK] >> (4 * (k & 7));
-  return is_b ? prmt(0xF7E6D5C4u, 0x000000CCu, w) : prmt(0xB3A29180u, 0x00000088u, w);
+  return is_b ? prmt(0xF7E6D5C4u, 0x000044CCu, w) : prmt(0xB3A29180u, 0x00000088u, w);     // nibble 5 (code-4 column): 0x44 / 0x00, bit 7 clear
+}
+// One selector register from byte r of both alignments' selector words. NCOL: its upper half carries a SECOND selector for
+// a PRMT over (score, 0) that passes the score of an alignment through (bytes 0-1 / 2-3) or replaces it by zero where that
+// alignment's column is a code-4 base (selector byte with bit 7 clear): 0x3210 -> 0x..44 / 0x44...
+template <bool NCOL>
+__device__ __forceinline__ uint32_t make_selector(uint32_t wa, uint32_t wb, int r) {
+  const uint32_t x = prmt(wa, wb, (uint32_t)(((4 + r) << 4) | r));
+  if (!NCOL) return x;
+  const uint32_t ma = ((x >> 7) & 1u) - 1u, mb = ((x >> 15) & 1u) - 1u;                      // all ones where the column is a code-4 base
+  return (x & 0xffffu) | ((0x3210u ^ (ma & 0x0054u) ^ (mb & 0x7600u)) << 16);
 }
 
 // row codes of one alignment for rows 32g .. 32g+31 of the sweep as bytes in four-row words: 0-3 = base, 4 = code-4
@@ -231,7 +252,7 @@ __device__ __forceinline__ void q_group(const SwPlanes &pl, const SwTask &t, int
 // resident CTAs per SM a tier is compiled for: narrow single-lane tiers need few registers and, with nibble streams, 22 KB
 // of shared memory per CTA — their stalls are the plane loads of the stream fill, which more warps hide
 template <int WP, int PARTS> struct BandOcc { static constexpr int CTAS = PARTS > 1 ? 6 : (WP <= 8 ? 10 : (WP <= 16 ? 9 : (WP <= 24 ? 7 : 6))); };
-template <int MODE, int WP, int PARTS>
+template <int MODE, int WP, int PARTS, bool NCOL>
 __global__ void __launch_bounds__(SWB_BLOCK, (BandOcc<WP, PARTS>::CTAS))
 k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, uint32_t n_list, SwPlanes pl, SwScore sc,
           SwRes *__restrict__ res, Rec16 *__restrict__ fb_keys, uint32_t *__restrict__ fb_count,
@@ -267,8 +288,8 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
 
   // ---- unpack this thread's selector streams (low half = alignment A, high half = B; an unpaired last slot runs the
   // same alignment in both halves and drops the second result)
-  fill_col_stream<MODE>(pl, ta, ra, ga, false, rows4 + WP, colA);
-  fill_col_stream<MODE>(pl, tb, rb, gb, true, rows4 + WP, colB);
+  fill_col_stream<MODE, NCOL>(pl, ta, ra, ga, false, rows4 + WP, colA);
+  fill_col_stream<MODE, NCOL>(pl, tb, rb, gb, true, rows4 + WP, colB);
   for (int32_t g = 0; 32 * g < rows4 + 4; g++) {
     uint32_t qa[8], qb[8];
     q_group<MODE>(pl, ta, rows[0], g, qa);
@@ -295,7 +316,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
   for (int t = 0; t < WP; t += 4) {
     const uint32_t wa = col_selectors(colA, t, false), wb = col_selectors(colB, t, true);
 #pragma unroll
-    for (int r = 0; r < 4; r++) { H[t + r] = K2; V[t + r] = K2; sel[t + r] = prmt(wa, wb, (uint32_t)(((4 + r) << 4) | r)); }
+    for (int r = 0; r < 4; r++) { H[t + r] = K2; V[t + r] = K2; sel[t + r] = make_selector<NCOL>(wa, wb, r); }
   }
   // forward: key = score * 32 | 31 of the best cell so far, info = row << 8 | band slot of that cell;
   // reverse: (rcol, info) = first (smallest scan column, then smallest row) cell reaching the forward score
@@ -334,7 +355,8 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
       for (int h = 0; h < NH; h++) acc[h] = 0;
 #pragma unroll
       for (int t = 0; t < WP; t++) {
-        const uint32_t s = prmt(PA, PB, sel[t]);
+        uint32_t s = prmt(PA, PB, sel[t]);
+        if (NCOL) s = prmt(s, 0u, sel[t] >> 16);                   // code-4 columns score 0 against every row
         const uint32_t v = V[t];
         uint32_t h = __viaddmax_s16x2(H[t], s, v);                // max(H[i-1][j-1] + s, vertical gap)
         h = __vimax3_s16x2(h, e, K2);                               // ... the horizontal gap and the floor (0, biased)
@@ -352,7 +374,7 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
       // slide the column selectors: next row's slot t is this row's slot t+1; the last slot takes the entering column
 #pragma unroll
       for (int t = 0; t < WP - 1; t++) sel[t] = sel[t + 1];
-      sel[WP - 1] = prmt(ewa, ewb, (uint32_t)(((4 + r) << 4) | r));
+      sel[WP - 1] = make_selector<NCOL>(ewa, ewb, r);
       // row winners -> running best. SSW's rule: first column attaining the maximum, then the smallest row
       // (ssw.c:316-342). Rows only grow, so a strictly larger score always wins (the common, branch-free path) and an
       // equal score wins only with a strictly smaller column.
@@ -430,9 +452,9 @@ k_sw_band(const SwTask *__restrict__ tasks, const uint32_t *__restrict__ list, u
         res[idx] = o;
       } else if (MODE == 0 && next_list && S > 0 && tier_of_interval(need, level, sc) != SWT_TIER_NONE) {
         res[idx].score = S;         // lower bound: every alignment scoring >= S lies in [-(m - a), n - a]
-        const uint32_t t2 = tier_of_interval(need, level, sc);
-        tier_f[idx] = (uint8_t)(t2 | SWT_SWEPT);
-        list_slot_keyed(tier2_count, t2);
+        const uint32_t t2 = NCOL ? ncol_tier(tier_of_interval(need, level, sc)) : tier_of_interval(need, level, sc);
+        tier_f[idx] = (uint8_t)(t2 | SWT_SWEPT | (NCOL ? SWT_NCOL : 0u));
+        list_slot_keyed(tier2_count, t2 + (NCOL ? SWT_N_DIRECT : 0u));
         next_list[list_slot(next_count)] = idx;
       } else {
         const uint32_t k = list_slot(fb_count);

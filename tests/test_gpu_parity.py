@@ -425,6 +425,34 @@ def test_ssw_fast_domain_other_parameters(pkg, prm):
     assert tm["n_sw_slow"] == 0 and tm["n_sw_band"] > 3_000
 
 
+@pytest.mark.parametrize("shape", [(150, 150), (120, 160)])
+@pytest.mark.parametrize("cigar", [0, 1])
+def test_ssw_windows_with_code4_columns(pkg, shape, cigar):
+    """Windows holding code-4 bases (N runs, lower-case n, IUPAC letters: score 0 against every row, ssw_cpp.cpp:43-48) run
+    the masked variants of the band tiers instead of the full-matrix kernel; same results as the oracle on diverged, gapped
+    and partial pairs, forward and reverse, with N runs in most windows and some reads."""
+    q, qo, r, ro = diverged_pairs(pkg, 10_000, shape[0], shape[1], seed=700 + shape[0] + cigar)
+    rng = np.random.default_rng(71)
+    q = q.copy(); r = r.copy()
+    for i in range(10_000):
+        if rng.random() < 0.7:
+            for _k in range(int(rng.integers(1, 4))):
+                st = int(rng.integers(0, shape[1] - 1)); ln = int(rng.integers(1, 13))
+                r[int(ro[i]) + st:min(int(ro[i]) + st + ln, int(ro[i + 1]))] = rng.choice(np.frombuffer(b"NnRYK", dtype=np.uint8))
+        if rng.random() < 0.1:
+            st = int(rng.integers(0, shape[0] - 1)); ln = int(rng.integers(1, 9))
+            q[int(qo[i]) + st:min(int(qo[i]) + st + ln, int(qo[i + 1]))] = ord("N")
+    P = T.default_params(report_cigar=cigar)
+    want, wpool = T.ko_ssw_batch(q, qo, r, ro, P, cigar_cap=64)
+    with pkg.Aligner(report_cigar=bool(cigar), max_cigar_ops=64) as al:
+        out, pool = al.ssw_batch(q, qo, r, ro)
+        tm = al.timings()
+    check_overlaps(out, pool, want, wpool, fields=FIELDS[4:], cigars=bool(cigar))
+    assert tm["n_sw_slow"] == 0
+    assert tm["n_sw_band"] == 10_000, tm["n_sw_band"]          # every window is band-eligible, clean or not
+    assert tm["n_sw_fast"] < 9_000, tm["n_sw_fast"]            # (what is left: trial sweeps that bound nothing <= 128 diagonals)
+
+
 def test_radix_sort_matches_numpy(pkg):
     rng = np.random.default_rng(3)
     with pkg.Aligner() as al:
