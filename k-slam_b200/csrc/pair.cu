@@ -47,6 +47,15 @@ k_pair_compact(const uint32_t *__restrict__ pass, const uint32_t *__restrict__ p
   if (i < n && pass[i]) idx[pos[i]] = i;
 }
 
+// the index list of the passing overlaps; nullptr = every overlap passed (threshold 0: the list would be the identity)
+__device__ __forceinline__ uint32_t idx_at(const uint32_t *__restrict__ idx, uint32_t i) { return idx ? idx[i] : i; }
+// threshold 0: n_r1[0] = number of overlaps of R1 reads = first position whose read is >= mid (the array is ordered by read)
+__global__ void k_pair_first_r2(const kslam_overlap *__restrict__ ov, uint32_t n, uint32_t mid, uint32_t *__restrict__ n_r1) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (ov[m].read < mid) lo = m + 1; else hi = m; }
+  *n_r1 = lo;
+}
+
 // number of R1-list elements among the first `diag` outputs of the merge of A = idx[0..na) and B = idx[na..na+nb)
 __device__ __forceinline__ uint32_t merge_split(const kslam_overlap *__restrict__ ov, const uint32_t *__restrict__ idx, uint32_t na,
                                                 uint32_t nb, uint32_t diag, uint32_t mid, uint32_t bias) {
@@ -54,7 +63,7 @@ __device__ __forceinline__ uint32_t merge_split(const kslam_overlap *__restrict_
   while (lo < hi) {
     const uint32_t a = (lo + hi) >> 1, b = diag - 1 - a;                        // compare A[a] with B[b]
     // A[a] goes before B[b] unless B[b] is strictly smaller (ties: A first)
-    if (!key_less(pair_key(ov, idx[na + b], mid, bias), pair_key(ov, idx[a], mid, bias))) lo = a + 1; else hi = a;
+    if (!key_less(pair_key(ov, idx_at(idx, na + b), mid, bias), pair_key(ov, idx_at(idx, a), mid, bias))) lo = a + 1; else hi = a;
   }
   return lo;
 }
@@ -80,7 +89,7 @@ k_pair_merge(const kslam_overlap *__restrict__ ov, const uint32_t *__restrict__ 
   const uint32_t a0 = tile_a[tile], a1 = tile_a[tile + 1], b0 = d0 - a0, b1 = d1 - a1;
   const uint32_t ca = a1 - a0, cb = b1 - b0;                     // ca + cb == d1 - d0; A keys at [0, ca), B keys at [ca, ca + cb)
   for (uint32_t i = threadIdx.x; i < ca + cb; i += PM_THREADS) {
-    const uint32_t src = i < ca ? idx[a0 + i] : idx[na + b0 + (i - ca)];
+    const uint32_t src = i < ca ? idx_at(idx, a0 + i) : idx_at(idx, na + b0 + (i - ca));
     const PairKey k = pair_key(ov, src, mid, bias);
     s_hi[i] = k.hi; s_lo[i] = k.lo; s_src[i] = src;
   }
@@ -214,16 +223,27 @@ void pair_overlaps(kslam_ctx *c) {
   uint32_t *pass = c->pair_keys.as<uint32_t>(), *ppos = pass + n, *idx = ppos + n, *tile_a = idx + n;
   CUDA_TRY(cudaMemsetAsync(d_cnt, 0, 16, st));
   const unsigned nb = (n + 255) / 256;
-  k_pair_flags<<<nb, 256, 0, st>>>(c->ov.as<kslam_overlap>(), n, mid, c->prm.score_threshold, pass, d_cnt);
-  unsigned long long *d_ns = c->counters.as<unsigned long long>() + 31;
-  exclusive_scan_u32(c, pass, ppos, n, (uint64_t *)d_ns);
-  k_pair_compact<<<nb, 256, 0, st>>>(pass, ppos, n, idx);
-  c->launches += 2;
-  unsigned long long *h_ns = c->h_counters.as<unsigned long long>() + 31;
-  read_small(c, h_cnt, d_cnt, 4);
-  read_small(c, h_ns, d_ns, 8);
-  CUDA_TRY(cudaStreamSynchronize(st));
-  const uint32_t ns = (uint32_t)h_ns[0], na = h_cnt[0], nbb = ns - na;
+  uint32_t ns, na;
+  if (c->prm.score_threshold == 0) {
+    // every score passes (Overlap.h:335 compares >= 0): no flags, no scan, no index list — only where the R2 part starts
+    k_pair_first_r2<<<1, 1, 0, st>>>(c->ov.as<kslam_overlap>(), n, mid, d_cnt);
+    c->launches++;
+    read_small(c, h_cnt, d_cnt, 4);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ns = n; na = h_cnt[0]; idx = nullptr;
+  } else {
+    k_pair_flags<<<nb, 256, 0, st>>>(c->ov.as<kslam_overlap>(), n, mid, c->prm.score_threshold, pass, d_cnt);
+    unsigned long long *d_ns = c->counters.as<unsigned long long>() + 31;
+    exclusive_scan_u32(c, pass, ppos, n, (uint64_t *)d_ns);
+    k_pair_compact<<<nb, 256, 0, st>>>(pass, ppos, n, idx);
+    c->launches += 2;
+    unsigned long long *h_ns = c->h_counters.as<unsigned long long>() + 31;
+    read_small(c, h_cnt, d_cnt, 4);
+    read_small(c, h_ns, d_ns, 8);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ns = (uint32_t)h_ns[0]; na = h_cnt[0];
+  }
+  const uint32_t nbb = ns - na;
   c->n_sorted = ns;
   if (!ns) return;
   c->ov_sorted.reserve((size_t)ns * sizeof(kslam_overlap) + 64);
