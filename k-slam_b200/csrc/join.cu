@@ -350,7 +350,9 @@ void seed_sort_unique(kslam_ctx *c) {
   const SeedBits sb = seed_bits(c);
   uint64_t eblocks = (c->n_raw + 255) / 256;
   if (eblocks > (uint64_t)c->num_sms * 16) eblocks = (uint64_t)c->num_sms * 16;
-  if (c->n_raw && c->seeds_compact && c->n_raw >= (1ull << 30)) {     // beyond radix_sort_u64's range: back to 16-byte records
+  static const char *xe = getenv("KSLAM_SEEDS_EXPAND_AT");            // (tests: take the fall-back below on small inputs)
+  const uint64_t expand_at = xe && atoll(xe) > 0 ? (uint64_t)atoll(xe) : (1ull << 30);
+  if (c->n_raw && c->seeds_compact && c->n_raw >= expand_at) {        // beyond radix_sort_u64's range: back to 16-byte records
     c->seedB.reserve((size_t)c->n_raw * sizeof(Rec16));
     k_seeds_expand<<<(unsigned)eblocks, 256, 0, st>>>(c->seedA.as<uint64_t>(), c->n_raw, sb.rel_bits, sb.ebits, c->seedB.as<Rec16>());
     c->launches++;
