@@ -117,6 +117,11 @@ const char *kslam_last_error(const kslam_ctx *ctx); /* ctx may be NULL: last cre
  * kernels equal plain Gotoh there: gap_extend < gap_open and mismatch <= 2 * gap_extend; the defaults 2/3/5/2 are inside),
  * 0 = the literal lane-for-lane restatement of SSW's striped byte / word kernels (ssw.c:143-592), slower. */
 int kslam_params_exact(const kslam_params *params);
+/* The offsets [lo, hi] (column - row in the reversed matrix) that the reverse pass of an alignment scoring `score` sweeps
+ * when its reversed prefixes are rows x cols (ssw.c:905-923: every alignment reaching the forward score starts at the
+ * reversed origin). Pure arithmetic on the host, for parameters inside kslam_params_fast; KSLAM_ERR_ARG
+ * otherwise. */
+int kslam_reverse_band(int32_t rows, int32_t cols, int32_t score, const kslam_params *params, int32_t *lo, int32_t *hi);
 int kslam_params_fast(const kslam_params *params);
 const char *kslam_version(void);
 /* HBM of a device (cudaMemGetInfo): a host that must choose between a replicated and a partitioned index asks here. */

@@ -1501,6 +1501,16 @@ void sw_align_pairs(kslam_ctx *c, uint64_t n64, kslam_overlap *out_dev, uint32_t
   c->tm.ms_sw_prepare = tm_ms(e0, e1);
 }
 
+// the band of the reverse sweeps as a host function (pure arithmetic: tests/test_reverse_band.py checks it against a
+// brute-force scan of the full reversed matrix without a GPU)
+extern "C" int kslam_reverse_band(int32_t rows, int32_t cols, int32_t score, const kslam_params *p, int32_t *lo, int32_t *hi) {
+  if (!p || !lo || !hi || rows < 1 || cols < 1 || score < 1 || !kslam_params_fast(p)) return KSLAM_ERR_ARG;
+  SwScore sc{};
+  sc.match = (int8_t)p->match; sc.mismatch = p->mismatch; sc.gap_open = p->gap_open; sc.gap_extend = p->gap_extend; sc.anchored = 1;
+  reverse_band(rows, cols, score, sc, lo, hi);
+  return KSLAM_OK;
+}
+
 void sw_workspace_free(kslam_ctx *c) {
   if (!c->sw) return;
   c->sw->tasks.release(); c->sw->res.release(); c->sw->keys.release(); c->sw->keys2.release();
