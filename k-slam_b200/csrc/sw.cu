@@ -93,7 +93,7 @@ struct SwScore {
   int32_t match, mismatch, gap_open, gap_extend;   // positive magnitudes, as given
   uint32_t score_threshold; uint32_t report_cigar; uint32_t cigar_cap;
   uint32_t literal;   // 1: scoring parameters outside the plain-Gotoh domain -> every alignment runs k_sw_striped
-  uint32_t max_band;  // widest band tier in use (128; KSLAM_SW_MAX_BAND=64 leaves the multi-lane tiers out: ablation)
+  uint32_t max_band;  // widest band tier in use (128; KSLAM_SW_MAX_BAND=64 leaves the tiers of 72-128 diagonals out: ablation)
   uint32_t anchored;  // 1: reverse sweeps run in the anchored band (KSLAM_SW_REV_ANCHOR=0: the interval [-(rows - a), cols - a])
   uint32_t ncol;      // 1: windows with code-4 columns run the masked band tiers (KSLAM_SW_NCOL=0: the full-matrix kernel, as before)
 };
