@@ -74,10 +74,11 @@ struct PackedSeqs {
   DevBuf nmask;            // u32 per word: bit set where the SSW code is 4
   DevBuf xmask;            // u32 per word: bit set for a c g t U u (SSW code < 4 but never complemented)
   DevBuf kmer_off;         // u64 n+1: first k-mer record index of each sequence
+  DevBuf has_n;            // u8 per sequence: 1 when it holds a code-4 base anywhere (genomes only; empty otherwise)
   uint64_t n_kmers = 0;
   uint32_t max_len = 0;
   void release() { raw.release(); offs.release(); word_off.release(); kbits.release(); sbits.release();
-                   nmask.release(); xmask.release(); kmer_off.release(); }
+                   nmask.release(); xmask.release(); kmer_off.release(); has_n.release(); }
 };
 
 struct SwWorkspace;

@@ -75,6 +75,19 @@ k_uniform_offsets(uint64_t n, uint64_t len, uint64_t wpl, uint64_t kpl, uint64_t
   }
 }
 
+// has_n[seq] = 1 when any nmask word of the sequence is non-zero: one warp per sequence (genomes: few, long)
+__global__ void __launch_bounds__(256)
+k_seq_has_n(const uint32_t *__restrict__ nmask, const uint64_t *__restrict__ word_off, uint64_t n, uint8_t *__restrict__ has_n) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t seq = warp; seq < n; seq += nwarps) {
+    uint32_t any = 0;
+    for (uint64_t w = word_off[seq] + lane; w < word_off[seq + 1]; w += 32) any |= nmask[w];
+    any = __reduce_or_sync(0xffffffffu, any);
+    if (lane == 0) has_n[seq] = any ? 1 : 0;
+  }
+}
+
 void pack_sequences(kslam_ctx *c, PackedSeqs &s, uint64_t n, const char *bases, const uint64_t *offs,
                     uint32_t kmer_gap, bool keep_raw) {
   ensure_tables(c->device);
@@ -128,6 +141,14 @@ void pack_sequences(kslam_ctx *c, PackedSeqs &s, uint64_t n, const char *bases, 
     k_pack<<<(unsigned)blocks, 256, 0, st>>>(s.raw.as<uint8_t>(), s.offs.as<uint64_t>(),
                                              s.word_off.as<uint64_t>(), n, w, s.kbits.as<uint64_t>(),
                                              s.sbits.as<uint64_t>(), s.nmask.as<uint32_t>(), s.xmask.as<uint32_t>());
+    c->launches++;
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (!keep_raw && n) {      // genomes: which of them hold code-4 bases at all (their windows need no scan for them otherwise)
+    s.has_n.reserve(n + 64);
+    uint64_t blocks = (n * 32 + 255) / 256, maxb = (uint64_t)c->num_sms * 8;
+    if (blocks > maxb) blocks = maxb;
+    k_seq_has_n<<<(unsigned)blocks, 256, 0, st>>>(s.nmask.as<uint32_t>(), s.word_off.as<uint64_t>(), n, s.has_n.as<uint8_t>());
     c->launches++;
     CUDA_TRY(cudaGetLastError());
   }

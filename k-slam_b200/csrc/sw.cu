@@ -909,7 +909,7 @@ k_tier_scatter(const uint8_t *__restrict__ tier, const uint32_t *__restrict__ sr
 __device__ __forceinline__ uint32_t
 prepare_seed(uint32_t i, const kslam_seed *__restrict__ seeds, const uint64_t *__restrict__ r_offs,
              const uint64_t *__restrict__ r_word, const uint64_t *__restrict__ g_offs,
-             const uint64_t *__restrict__ g_word, const uint32_t *__restrict__ g_nmask, const SwScore &sc, uint32_t use_band,
+             const uint64_t *__restrict__ g_word, const uint32_t *__restrict__ g_nmask, const uint8_t *__restrict__ g_has_n, const SwScore &sc, uint32_t use_band,
              const SwPlanes &pl, SwTask *__restrict__ tasks, SwRes *__restrict__ res, uint8_t *__restrict__ tier_f,
              Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list, uint32_t *__restrict__ counts) {
   const kslam_seed s = seeds[i];
@@ -921,7 +921,7 @@ prepare_seed(uint32_t i, const kslam_seed *__restrict__ seeds, const uint64_t *_
   t.m = (uint32_t)qlen; t.n = (uint32_t)wlen; t.w_start = (uint32_t)start;
   const uint32_t cls = classify(t.m, t.n, sc);
   t.flags = (s.rev_comp ? SWT_REV : 0u) | (cls << 8);
-  if (cls != SWC_NONE && window_clean(g_nmask, t.w_word, t.w_start, t.n)) t.flags |= SWT_CLEAN;
+  if (cls != SWC_NONE && ((g_has_n && !__ldg(&g_has_n[s.entry])) || window_clean(g_nmask, t.w_word, t.w_start, t.n))) t.flags |= SWT_CLEAN;   // (a genome without any code-4 base: no scan)
   if (use_band && cls == SWC_FAST8 && band_shape_ok(t.m, t.n) && ((t.flags & SWT_CLEAN) || (use_band >= 3 && sc.ncol))) t.flags |= SWT_BAND;
   tasks[i] = t;
   // matrix diagonal of the seed's exact 32-mer match: forward seeds put read base i on genome base rel + i; reverse-
@@ -932,12 +932,12 @@ prepare_seed(uint32_t i, const kslam_seed *__restrict__ seeds, const uint64_t *_
 __global__ void __launch_bounds__(256)
 k_sw_prepare_seeds(const kslam_seed *__restrict__ seeds, uint32_t n, const uint64_t *__restrict__ r_offs,
                    const uint64_t *__restrict__ r_word, const uint64_t *__restrict__ g_offs,
-                   const uint64_t *__restrict__ g_word, const uint32_t *__restrict__ g_nmask, SwScore sc, uint32_t use_band,
+                   const uint64_t *__restrict__ g_word, const uint32_t *__restrict__ g_nmask, const uint8_t *__restrict__ g_has_n, SwScore sc, uint32_t use_band,
                    SwPlanes pl, SwTask *__restrict__ tasks, SwRes *__restrict__ res, uint8_t *__restrict__ tier_f,
                    Rec16 *__restrict__ full_keys, uint32_t *__restrict__ slow_list, uint32_t *__restrict__ counts) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t tier = SWT_TIER_NONE;
-  if (i < n) tier = prepare_seed(i, seeds, r_offs, r_word, g_offs, g_word, g_nmask, sc, use_band, pl, tasks, res, tier_f, full_keys, slow_list, counts);
+  if (i < n) tier = prepare_seed(i, seeds, r_offs, r_word, g_offs, g_word, g_nmask, g_has_n, sc, use_band, pl, tasks, res, tier_f, full_keys, slow_list, counts);
   count_tier_block(tier, counts);       // every thread of the CTA, from this one place (it holds barriers and a full-warp match)
 }
 
@@ -1462,7 +1462,7 @@ void sw_align_seeds(kslam_ctx *c) {
               c->genomes.nmask.as<uint32_t>(), c->genomes.xmask.as<uint32_t>()};
   k_sw_prepare_seeds<<<(n + 255) / 256, 256, 0, st>>>(c->seeds.as<kslam_seed>(), n, c->reads.offs.as<uint64_t>(),
       c->reads.word_off.as<uint64_t>(), c->genomes.offs.as<uint64_t>(), c->genomes.word_off.as<uint64_t>(),
-      c->genomes.nmask.as<uint32_t>(), make_score(c), sw_level(c), pl, w->tasks.as<SwTask>(), w->res.as<SwRes>(), w->tier.as<uint8_t>(),
+      c->genomes.nmask.as<uint32_t>(), c->genomes.has_n.p ? c->genomes.has_n.as<uint8_t>() : nullptr, make_score(c), sw_level(c), pl, w->tasks.as<SwTask>(), w->res.as<SwRes>(), w->tier.as<uint8_t>(),
       w->keys.as<Rec16>(), w->lists.as<uint32_t>() + n, d_counts);
   c->launches++;
   CUDA_TRY(cudaGetLastError());
