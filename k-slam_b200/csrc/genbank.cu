@@ -243,7 +243,20 @@ kslam_index *cache_load(const std::string &cache_path, uint64_t src_size, uint64
   ix->locus.resize((size_t)h->n_locus); take(&ix->locus[0], (size_t)h->n_locus);
   ix->gene_strings.resize((size_t)h->n_gene_strings); take(&ix->gene_strings[0], (size_t)h->n_gene_strings);
   ix->mapped_bases = p;
-  if (ix->offs[0] != 0 || ix->offs[n] != h->n_bases || ix->gene_offs[n] != h->n_genes) { delete ix; return nullptr; }
+  // the key matched, but the tables are still a file's contents: every offset table must start at 0, never decrease and
+  // end at the size of what it indexes, or the side-car is dropped like a stale one (the archive is parsed instead)
+  auto table_ok = [n](const std::vector<uint64_t> &t, uint64_t total) {
+    if (t[0] != 0 || t[n] != total) return false;
+    for (size_t i = 0; i < n; i++) if (t[i] > t[i + 1]) return false;
+    return true;
+  };
+  bool ok = table_ok(ix->offs, h->n_bases) && table_ok(ix->locus_offs, h->n_locus) && table_ok(ix->gene_offs, h->n_genes);
+  for (size_t g = 0; ok && g < ix->genes.size(); g++) {
+    const uint64_t *so = ix->genes[g].str_offs;
+    for (int k = 0; k < 5; k++) ok = ok && so[k] <= so[k + 1];
+    ok = ok && so[5] <= h->n_gene_strings;
+  }
+  if (!ok) { delete ix; return nullptr; }
   return ix;
 }
 

@@ -260,6 +260,15 @@ def test_side_car_cache_of_the_database(pkg, tmp_path):
     out = str(tmp_path / "again3"); d.write(out)
     assert open(out, "rb").read() == want2
     d.close()
+    # a side-car whose key still matches but whose offset tables are damaged is dropped, not trusted
+    good = open(cache, "rb").read()
+    for at in (64 + 8, 64 + 8 * 3):                         # entry offsets of the bases table (header: 8 + 7 x 8 bytes)
+        bad = bytearray(good); bad[at:at + 8] = (2**62).to_bytes(8, "little")
+        open(cache, "wb").write(bytes(bad))
+        e = pkg.Index.read(db)
+        out = str(tmp_path / "again4"); e.write(out)
+        assert open(out, "rb").read() == want2
+        e.close()
     os.environ["KSLAM_NO_INDEX_CACHE"] = "1"
     try:
         os.unlink(cache)
