@@ -245,6 +245,10 @@ int kslam_comm_init_all(uint32_t n, kslam_ctx *const *ctxs, kslam_comm **out /* 
 void kslam_comm_destroy(kslam_comm *comm);
 int kslam_comm_rank(const kslam_comm *comm, uint32_t *rank, uint32_t *n_ranks);
 int kslam_comm_align_resident(kslam_comm *comm, int fetch_results, kslam_alignments *out /* may be NULL */);
+/* A rank that cannot take part in a batch (its kslam_upload_reads failed, say) calls this INSTEAD of
+ * kslam_comm_align_resident: the other ranks' calls then return KSLAM_ERR_STATE instead of waiting for it. The same
+ * holds inside kslam_comm_align_resident: a stage that fails on one rank ends the batch with an error on every rank. */
+int kslam_comm_abort_batch(kslam_comm *comm);
 int kslam_comm_get_stats(const kslam_comm *comm, kslam_comm_stats *out);
 
 /* ---- FASTQ ingest (host side) ------------------------------------------------------------------

@@ -174,6 +174,7 @@ def lib():
     L.kslam_comm_rank.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.kslam_comm_align_resident.argtypes = [vp, i32, C.POINTER(_Alignments)]
     L.kslam_comm_get_stats.argtypes = [vp, C.POINTER(CommStats)]
+    L.kslam_comm_abort_batch.argtypes = [vp]
     L.kslam_set_sw_band.argtypes = [vp, i32]
     u32 = C.c_uint32
     L.kslam_fastq_open.argtypes = [C.c_char_p, C.c_char_p, u32, C.POINTER(vp)]
@@ -542,6 +543,10 @@ class Comm:
         out = _Alignments()
         self.al._check(self.L.kslam_comm_align_resident(self.h, int(fetch), C.byref(out)), "kslam_comm_align_resident")
         return self.al._alignments(out, copy) if fetch else int(out.n_overlaps)
+
+    def abort_batch(self):
+        """Collective stand-in for align_resident on a rank that cannot take part: the other ranks' calls fail instead of waiting."""
+        self.al._check(self.L.kslam_comm_abort_batch(self.h), "kslam_comm_abort_batch")
 
     def stats(self) -> dict:
         st = CommStats()

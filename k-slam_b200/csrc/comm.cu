@@ -93,13 +93,25 @@ void allgather_u64(kslam_comm *m, const uint64_t *mine, uint32_t n, uint64_t *al
   for (size_t i = 0; i < (size_t)n * m->n_ranks; i++) all[i] = h[n + i];
 }
 
+// A collective must be entered by every rank or the others wait for ever, so a rank whose local stage failed still takes
+// part in the size exchange that follows it, with a flag next to its (zero) counts; every rank then sees the flag and
+// leaves the batch before the data exchange. Thrown by the ranks that did NOT fail themselves.
+struct PeerFailed { uint32_t rank; };
+
 // counts[p] records of `send` (grouped by destination, in rank order) go to rank p; recv is filled in source-rank order.
-// Returns the number of records received; *ms = device time of the exchange.
-uint64_t all_to_all_records(kslam_comm *m, const Rec16 *send, const uint64_t *counts, bool matches, float *ms, uint64_t *bytes_out) {
+// Returns the number of records received; *ms = device time of the exchange. failed: this rank has nothing to send
+// because its stage failed — returns ~0 on it, throws PeerFailed on the others, and nobody exchanges records.
+uint64_t all_to_all_records(kslam_comm *m, const Rec16 *send, const uint64_t *counts, bool failed, bool matches, float *ms, uint64_t *bytes_out) {
   kslam_ctx *c = m->ctx;
   const uint32_t P = m->n_ranks;
-  std::vector<uint64_t> all((size_t)P * P);
-  allgather_u64(m, counts, P, all.data());
+  std::vector<uint64_t> row(P + 1, 0), gathered((size_t)(P + 1) * P), all((size_t)P * P);
+  if (!failed) for (uint32_t p = 0; p < P; p++) row[p] = counts[p];
+  row[P] = failed ? 1 : 0;
+  allgather_u64(m, row.data(), P + 1, gathered.data());
+  for (uint32_t src = 0; src < P; src++) {
+    if (gathered[(size_t)src * (P + 1) + P]) { if (failed) return ~0ull; throw PeerFailed{src}; }
+    for (uint32_t p = 0; p < P; p++) all[(size_t)src * P + p] = gathered[(size_t)src * (P + 1) + p];
+  }
   uint64_t n_recv = 0;
   for (uint32_t src = 0; src < P; src++) n_recv += all[(size_t)src * P + m->rank];
   void *recv_ptr = nullptr;
@@ -131,6 +143,8 @@ uint64_t all_to_all_records(kslam_comm *m, const Rec16 *send, const uint64_t *co
   kslam_ctx *c = (m)->ctx;                                                                     \
   API_BEGIN(c)
 #define COMM_END(m)                                                                            \
+  } catch (const PeerFailed &e) {                                                              \
+    return api_fail(c, KSLAM_ERR_STATE, "rank " + std::to_string(e.rank) + " of the communicator failed in this batch (its own error says why)"); \
   } catch (const NcclError &e) {                                                               \
     return api_fail(c, KSLAM_ERR_CUDA, std::string(e.what) + ": " + nccl()->GetErrorString(e.r)); \
   API_END(c)
@@ -197,40 +211,60 @@ int kslam_comm_rank(const kslam_comm *m, uint32_t *rank, uint32_t *n_ranks) {
 
 // alignToDatabase over the partitioned index for the reads this rank has uploaded (kslam_upload_reads). Collective: every
 // rank of the communicator calls it once per batch (a rank without reads uploads an empty batch).
+// Every rank of the communicator enters the batch (first_gather) whatever state it is in: a rank that cannot take part
+// says so there, and all ranks return an error instead of waiting for it.
+static void first_gather(kslam_comm *m, uint64_t n_reads_mine, bool failed, std::vector<uint64_t> &n_reads) {
+  const uint32_t P = m->n_ranks;
+  const uint64_t mine[2] = {failed ? 0 : n_reads_mine, failed ? 1ull : 0ull};
+  std::vector<uint64_t> g((size_t)2 * P);
+  allgather_u64(m, mine, 2, g.data());
+  n_reads.resize(P);
+  for (uint32_t p = 0; p < P; p++) n_reads[p] = g[(size_t)2 * p];
+  if (failed) return;
+  for (uint32_t p = 0; p < P; p++) if (g[(size_t)2 * p + 1]) throw PeerFailed{p};
+}
+
+int kslam_comm_abort_batch(kslam_comm *m) {
+  COMM_BEGIN(m)
+  std::vector<uint64_t> n_reads;
+  first_gather(m, 0, true, n_reads);
+  return KSLAM_OK;
+  COMM_END(m)
+}
+
 int kslam_comm_align_resident(kslam_comm *m, int fetch, kslam_alignments *out) {
   COMM_BEGIN(m)
-  if (!c->reads_loaded) return comm_fail(m, KSLAM_ERR_STATE, "kslam_upload_reads first");
-  if (c->n_parts != m->n_ranks || c->part != m->rank)
-    return comm_fail(m, KSLAM_ERR_STATE, "kslam_load_genomes_part(part = rank, n_parts = ranks of the communicator) first");
   const uint32_t P = m->n_ranks;
   kslam_comm_stats &st = m->st;
   memset(&st, 0, sizeof st);
+  const char *not_ready = !c->reads_loaded ? "kslam_upload_reads first"
+                          : (c->n_parts != m->n_ranks || c->part != m->rank) ? "kslam_load_genomes_part(part = rank, n_parts = ranks of the communicator) first" : nullptr;
   // job-global read ids: rank r's reads are numbered from the sum of the counts before it
-  std::vector<uint64_t> n_reads(P);
-  const uint64_t mine = c->reads.n;
-  allgather_u64(m, &mine, 1, n_reads.data());
+  std::vector<uint64_t> n_reads;
+  first_gather(m, c->reads.n, not_ready != nullptr, n_reads);
+  if (not_ready) return comm_fail(m, KSLAM_ERR_STATE, not_ready);
   std::vector<uint32_t> id_bases(P + 1, 0);
   uint64_t run = 0;
   for (uint32_t p = 0; p < P; p++) { id_bases[p] = (uint32_t)run; run += n_reads[p]; }
-  if (run > (1ull << 30)) return comm_fail(m, KSLAM_ERR_ARG, "more than 2^30 reads in one job-wide batch (KMer.h:65-66)");
+  if (run > (1ull << 30)) return comm_fail(m, KSLAM_ERR_ARG, "more than 2^30 reads in one job-wide batch (KMer.h:65-66)");   // (the same sum on every rank)
   id_bases[P] = (uint32_t)run;
   // read owner: extract, prefilter, bucket by key owner
   const void *send = nullptr;
   std::vector<uint64_t> counts(P);
   int rc = kslam_part_route_kmers(c, id_bases[m->rank], &send, counts.data());
-  if (rc != KSLAM_OK) return rc;
   st.ms_route = c->tm.ms_extract; st.ms_bucket_kmers = c->part_ms_bucket;
-  for (uint32_t p = 0; p < P; p++) st.kmers_sent += counts[p];
-  const uint64_t n_recv = all_to_all_records(m, (const Rec16 *)send, counts.data(), false, &st.ms_exchange_kmers, &st.bytes_sent_kmers);
+  if (rc == KSLAM_OK) for (uint32_t p = 0; p < P; p++) st.kmers_sent += counts[p];
+  const uint64_t n_recv = all_to_all_records(m, (const Rec16 *)send, counts.data(), rc != KSLAM_OK, false, &st.ms_exchange_kmers, &st.bytes_sent_kmers);
+  if (rc != KSLAM_OK) return rc;                            // (the ctx's error text is the stage's)
   st.kmers_received = n_recv;
   // key owner: sort, merge-join, bucket raw matches by read owner
   const void *msend = nullptr;
   std::vector<uint64_t> mcounts(P);
   rc = kslam_part_join(c, n_recv, id_bases.data(), &msend, mcounts.data());
-  if (rc != KSLAM_OK) return rc;
   st.ms_sort = c->tm.ms_sort; st.ms_join = c->tm.ms_join; st.ms_bucket_matches = c->part_ms_bucket_matches;
-  for (uint32_t p = 0; p < P; p++) st.matches_sent += mcounts[p];
-  const uint64_t n_m = all_to_all_records(m, (const Rec16 *)msend, mcounts.data(), true, &st.ms_exchange_matches, &st.bytes_sent_matches);
+  if (rc == KSLAM_OK) for (uint32_t p = 0; p < P; p++) st.matches_sent += mcounts[p];
+  const uint64_t n_m = all_to_all_records(m, (const Rec16 *)msend, mcounts.data(), rc != KSLAM_OK, true, &st.ms_exchange_matches, &st.bytes_sent_matches);
+  if (rc != KSLAM_OK) return rc;
   st.matches_received = n_m;
   // read owner: the single-GPU path from the seeds on
   rc = kslam_part_finish(c, n_m, id_bases[m->rank], fetch, out);

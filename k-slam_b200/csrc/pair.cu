@@ -262,6 +262,7 @@ void pair_overlaps(kslam_ctx *c) {
   unsigned long long *h_tot = c->h_counters.as<unsigned long long>() + 30;
   read_small(c, h_tot, d_tot, 8);
   CUDA_TRY(cudaStreamSynchronize(st));
+  if (h_tot[0] >> 32) throw ArgError{"more than 2^32 pair records in one batch: use smaller batches (--num-reads-at-once)"};   // (pos[] is 32-bit)
   c->n_pairs = h_tot[0];
   if (c->n_pairs) {
     c->pairs.reserve((size_t)c->n_pairs * sizeof(kslam_pair) + 64);

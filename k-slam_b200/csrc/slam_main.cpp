@@ -236,6 +236,11 @@ void align_batch(const std::vector<kslam_ctx *> &ctxs, const std::vector<kslam_c
     }
     kslam_ctx *ctx = ctxs[g];
     int rc = kslam_upload_reads(ctx, n_here, base_ptr, offs_ptr);
+    if (rc != KSLAM_OK && partitioned) {                     // the other ranks are about to enter the collective: tell them
+      s.error = kslam_last_error(ctx);
+      kslam_comm_abort_batch(comms[g]);
+      return;
+    }
     const int fetch_alignments = isPaired ? 0 : 1;
     if (rc == KSLAM_OK) rc = partitioned ? kslam_comm_align_resident(comms[g], fetch_alignments, isPaired ? nullptr : &s.a)
                                          : kslam_align_resident(ctx, fetch_alignments, isPaired ? nullptr : &s.a);

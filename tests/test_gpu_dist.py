@@ -128,6 +128,61 @@ def test_comm_single_rank_equals_unpartitioned(pkg):
         comm.close()
 
 
+def test_comm_failed_rank_ends_the_batch_for_everyone(pkg):
+    """A rank that cannot take part must not leave the others waiting in a collective: with one rank, a call before any
+    upload and an aborted batch both return errors and the communicator stays usable for the next batch."""
+    gb, go, rb, ro = pkg.synth.adversarial_set(seed=44, n_genomes=6, glen=6000, n_pairs=200)
+    want = T.ko_pipeline(gb, go, rb, ro, T.default_params(report_cigar=1))
+    with pkg.Aligner(report_cigar=True) as al:
+        al.load_genomes_part(gb, go, 0, 1)
+        comm = pkg.Comm.init_rank(al, 0, 1, pkg.Comm.unique_id())
+        with pytest.raises(pkg.KslamError, match="kslam_upload_reads first"):
+            comm.align_resident()                            # took part in the first gather, then reported its own state
+        comm.abort_batch()
+        al.upload_reads(rb, ro)
+        res = comm.align_resident()
+        check_overlaps(res.overlaps, res.cigar_pool, want["overlaps"], want["cigar_pool"])
+        comm.close()
+
+
+def test_comm_two_gpus_abort_reaches_the_peer(pkg):
+    """Two ranks in one process: rank 1 aborts the batch, rank 0's kslam_comm_align_resident returns an error naming it
+    (instead of waiting for ever); the next batch runs normally on both."""
+    import torch
+    from kslam_b200 import shard
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    world, n_pairs = 2, 2000
+    gb, go = pkg.synth.random_genomes(6, 100_000, seed=17)
+    rb, ro, _ = pkg.synth.paired_reads(gb, go, n_pairs, seed=18)
+    reads = [shard.slice_reads(rb, ro, *shard.pair_range(n_pairs, world, r)) for r in range(world)]
+    als = [pkg.Aligner(report_cigar=True, device=r) for r in range(world)]
+    for r, al in enumerate(als):
+        al.load_genomes_part(gb, go, r, world)
+    comms = pkg.Comm.init_all(als)
+    seen, out = [None] * world, [None] * world
+
+    def run(r):
+        als[r].upload_reads(*reads[r])
+        try:                                                 # batch 1: rank 1 cannot take part
+            if r == 1:
+                comms[r].abort_batch()
+            else:
+                comms[r].align_resident()
+        except pkg.KslamError as e:
+            seen[r] = str(e)
+        out[r] = comms[r].align_resident()                   # batch 2: both ranks
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in th]; [t.join(timeout=120) for t in th]
+    assert not any(t.is_alive() for t in th), "a rank is still waiting in a collective"
+    assert seen[0] and "rank 1" in seen[0] and seen[1] is None
+    P = T.default_params(report_cigar=1)
+    for r in range(world):
+        want = T.ko_pipeline(gb, go, *reads[r], P)
+        check_overlaps(out[r].overlaps, out[r].cigar_pool, want["overlaps"], want["cigar_pool"])
+    [c.close() for c in comms]; [a.close() for a in als]
+
+
 def test_comm_two_gpus_one_process(pkg):
     """kslam_comm_init_all: one process, one ctx per GPU, one host thread per rank (what `SLAM --devices 0,1` does)."""
     import torch
