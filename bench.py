@@ -213,7 +213,7 @@ def config4_block(args, pkg, rank, world, local, barrier):
                                  "peak = the measured 770 GB/s peer copy per direction (B200_PROFILING.md)"}}
 
 
-def reference_run(pkg, gb, go, rb, ro, report_cigar, threshold=0, keep=False):
+def reference_run(pkg, gb, go, rb, ro, report_cigar, threshold=0, keep=False, threads=0):
     """The reference's own alignToDatabase + screen + getPairedOverlaps (oracle/_ref, all host threads; the oracle port where
     _ref is absent) on the given reads. -> (seconds, cores, kind, outputs or None)"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -221,7 +221,7 @@ def reference_run(pkg, gb, go, rb, ro, report_cigar, threshold=0, keep=False):
     P = T.default_params(report_cigar=int(report_cigar), score_threshold=threshold)
     out = None
     if T.have_ref():
-        T.ref().kref_set_threads(os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1: ask for every core
+        T.ref().kref_set_threads(threads or os.cpu_count() or 1)     # torchrun exports OMP_NUM_THREADS=1: ask for every core
         R = T.Ref(gb, go, rb, ro, P)
         cores = T.ref().kref_num_threads()
         t0 = time.time()
@@ -233,7 +233,7 @@ def reference_run(pkg, gb, go, rb, ro, report_cigar, threshold=0, keep=False):
         R.close()
         kind = "reference"
     else:
-        cores = os.cpu_count() or 1
+        cores = threads or os.cpu_count() or 1
         t0 = time.time()
         w = T.ko_pipeline(gb, go, rb, ro, P, threads=cores)
         dt = time.time() - t0
@@ -290,7 +290,21 @@ def cpu_baseline_block(pkg, al, gb, go, workload, sample, full_pairs, report_cig
     block["amortised"] = {"value": full_pairs / (a + b * full_pairs) * 60 / 1e6, "unit": UNIT, "at_pairs": full_pairs,
                           "fit": {"fixed_s": a, "s_per_pair": b, "points": [[half, dt2], [sample, dt]]},
                           "note": "t = fixed + per_pair * pairs fitted on two sample sizes; value = the reference's projected rate on the full batch"}
-    log(f"[bench/{workload}] cpu_baseline {block['value']:.3f} M pairs/min on the sample, {block['amortised']['value']:.3f} amortised; parity {block['parity']}")
+    # one host thread, on a sixteenth of the sample; one run only, so the per-batch genome work (which a
+    # single thread pays in full) stays inside the figure
+    try:
+        n1 = max(1000, sample // 16)
+        rb1 = np.concatenate([rb[:n1 * 150], rb[sample * 150:(sample + n1) * 150]])
+        ro1 = np.arange(2 * n1 + 1, dtype=np.uint64) * np.uint64(150)
+        t1, c1, _, _ = reference_run(pkg, gb, go, rb1, ro1, report_cigar, threads=1)
+        block["one_thread"] = {"value": n1 / t1 * 60 / 1e6, "unit": UNIT, "cores": c1,
+                               "sample": f"{n1} pairs in {t1:.1f}s, per-batch genome k-mer extraction + sort included (not amortised)"}
+    except Exception as e:   # noqa: BLE001  (a reported extra: never costs the line)
+        block["one_thread"] = {"error": str(e)[:200]}
+    T_ = sys.modules.get("_lib")
+    if T_ is not None and T_.have_ref():
+        T_.ref().kref_set_threads(os.cpu_count() or 1)
+    log(f"[bench/{workload}] cpu_baseline {block['value']:.3f} M pairs/min on the sample, {block['amortised']['value']:.3f} amortised; one thread {block['one_thread']}; parity {block['parity']}")
     return block
 
 
