@@ -233,21 +233,33 @@ struct kslam_taxdb {
     }
     return shared ? head[head.size() - shared] : 0;
   }
-  std::string lineage(uint32_t taxonomyID) const {         // getLineage, :249-265 (131567 = cellular organisms, skipped)
-    std::string lineage;
-    for (size_t steps = 0; steps <= nodes.size() + 1; steps++) {
-      if (taxonomyID != 131567) {
-        if (lineage.size()) lineage.insert(0, "; ");
-        lineage.insert(0, name(taxonomyID));
-        if (rank(taxonomyID) == "species") lineage.clear();
+  // getLineage, :249-265. Walking towards the root the reference puts each node's name in FRONT of the text so far
+  // ("; " between, only when there is text already) and empties the text at every node of rank "species"; 131567
+  // (cellular organisms) is never named; "." closes a non-empty text once the root is passed. So the text holds the
+  // ancestors above the topmost species node (all nodes when there is none): collected leaf-first here, written root-first.
+  std::string lineage(uint32_t start) const {
+    std::vector<uint32_t> kept;
+    bool reached_root = false;
+    uint32_t id = start;
+    for (size_t steps = 0; steps <= nodes.size() + 1 && !reached_root; steps++) {   // (bounded: a cyclic parent table ends the walk)
+      if (id != 131567) {
+        kept.push_back(id);
+        if (rank(id) == "species") kept.clear();
       }
-      taxonomyID = parent(taxonomyID);
-      if (taxonomyID == 0) {
-        if (lineage.size()) lineage.append(".");
-        break;
-      }
+      id = parent(id);
+      reached_root = id == 0;
     }
-    return lineage;
+    // separator after a name <=> some name below it is non-empty (that is when the text was non-empty as it went in front)
+    std::vector<uint8_t> text_below(kept.size(), 0);
+    bool any = false;
+    for (size_t k = 0; k < kept.size(); k++) { text_below[k] = any; any = any || !name(kept[k]).empty(); }
+    std::string out;
+    for (size_t k = kept.size(); k-- > 0;) {
+      out += name(kept[k]);
+      if (text_below[k]) out += "; ";
+    }
+    if (reached_root && !out.empty()) out += '.';
+    return out;
   }
 };
 
@@ -486,15 +498,12 @@ int kslam_taxa_results(kslam_taxa *taxa, const kslam_taxdb *taxdb, uint32_t num_
         if (r.has_read) t.reads.push_back(id_of(r));
       }
       std::sort(t.genes.begin(), t.genes.end(), [&](const GeneHit &x, const GeneHit &y) { return ops.less(x, y); });
-      auto first = t.genes.begin(), last = t.genes.end();
-      if (first != last) {
-        auto result = first;
-        while (++first != last) {
-          if (!ops.equal(*result, *first)) *(++result) = *first;
-          else result->count++;
-        }
-        t.genes.resize(std::distance(t.genes.begin(), ++result));
+      size_t n_runs = 0;                                      // equal neighbours collapse into the first of their run, which counts them
+      for (size_t k = 0; k < t.genes.size(); k++) {
+        if (n_runs && ops.equal(t.genes[n_runs - 1], t.genes[k])) t.genes[n_runs - 1].count++;
+        else { if (n_runs != k) t.genes[n_runs] = t.genes[k]; n_runs++; }
       }
+      t.genes.resize(n_runs);
       // sortResults, :254-275, the per-entry part (the order of the entries is decided below)
       if (inner_parallel) sort_views(t.reads); else std::sort(t.reads.begin(), t.reads.end());
       auto by_count = [&](const GeneHit &i, const GeneHit &j) {
