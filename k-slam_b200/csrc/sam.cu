@@ -428,11 +428,10 @@ __attribute__((noinline)) double match_run(const char *ref, const unsigned char 
 // The walk for one strand. RC: query[p] = complement(read[len - 1 - p]), quality[p] = qualities[len - 1 - p] — the pointers
 // start at the read's end and step backwards.
 template <bool RC>
-SequenceDifference cigar_and_md_walk(const char *ref, const unsigned char *qp, const unsigned char *qqp, int qlen, const uint32_t *cig,
-                                     const kslam_overlap &overlap) {
+void cigar_and_md_walk(const char *ref, const unsigned char *qp, const unsigned char *qqp, int qlen, const uint32_t *cig,
+                       const kslam_overlap &overlap, SequenceDifference &sd) {
   constexpr int STEP = RC ? -1 : 1;
   const double *matchTable = log_match_table().data(), *misMatchTable = log_mismatch_table().data();
-  SequenceDifference sd;
   double logp = 0;
   uint32_t nm = 0;
   int refPos = overlap.ref_begin;
@@ -485,165 +484,158 @@ SequenceDifference cigar_and_md_walk(const char *ref, const unsigned char *qp, c
   const int end = qlen - overlap.query_end - 1;
   if (end > 0) { put_int(sd.cigar, end); sd.cigar.push_back('S'); }
   sd.NM = nm; sd.logProbability = logp;
-  return sd;
 }
 
 
-SequenceDifference cigar_and_md(const Ctx &c, const kslam_overlap &overlap) {
-  if (!overlap.cigar_len || !c.in->cigar_pool) return SequenceDifference();            // Alignment::cigar == nullptr
+// (sd is the caller's, reused from alignment to alignment so that its strings keep their capacity)
+void cigar_and_md(const Ctx &c, const kslam_overlap &overlap, SequenceDifference &sd) {
+  sd.cigar.clear(); sd.MD.clear(); sd.NM = 0; sd.logProbability = 0;
+  if (!overlap.cigar_len || !c.in->cigar_pool) return;                                  // Alignment::cigar == nullptr
   const char *ref = c.db->bases + c.db->offs[overlap.entry];
   const unsigned char *rb = (const unsigned char *)c.reads->bases + c.reads->offs[overlap.read];
   const int qlen = (int)(c.reads->offs[overlap.read + 1] - c.reads->offs[overlap.read]);
   const unsigned char *qq = (const unsigned char *)c.reads->quals + c.reads->qual_offs[overlap.read];
   const int qqlen = (int)(c.reads->qual_offs[overlap.read + 1] - c.reads->qual_offs[overlap.read]);
   const uint32_t *cig = c.in->cigar_pool + overlap.cigar_off;
-  if (overlap.rev_comp) return cigar_and_md_walk<true>(ref, rb + qlen - 1, qq + qqlen - 1, qlen, cig, overlap);
-  return cigar_and_md_walk<false>(ref, rb, qq, qlen, cig, overlap);
+  if (overlap.rev_comp) cigar_and_md_walk<true>(ref, rb + qlen - 1, qq + qqlen - 1, qlen, cig, overlap, sd);
+  else cigar_and_md_walk<false>(ref, rb, qq, qlen, cig, overlap, sd);
 }
 
-struct SAMEntry {                                        // SAM.h:240-281
-  std::string_view qname, rname;   // views into the batch's read ids / the database's locus tags
-  uint32_t pos = 0; uint8_t mapq = 255;
-  std::string cigar = "*"; std::string_view rnext = "=";
-  uint32_t pnext = 0; int32_t tlen = 0;
-  bool multipleSegments = false, allSegmentsAligned = false, thisSegmentUnmapped = false, nextSegmentUnmapped = false;
-  bool revComp = false, nextRevComp = false, first = false, secondary = true;
-  std::string MD; uint16_t AS = 0; uint32_t NM = 0; uint16_t XS = 0; uint32_t XO = 0, XT = 0;
-  std::string_view XG, XP, XR;    // gene, protein id, product (views into the database's gene strings)
+// ---- SAM lines of one read (getSAMFromPair + writeSAMOutputPairs + SAMEntry::getEntry / getFlag, SAM.h:240-517) ------------
+// The reference fills two SAMEntry objects per pair record, copies them into a vector and prints them. Here a pair record
+// becomes two `Mate`s — what differs between its two lines — in a per-thread scratch that is reused from read to read,
+// and each line is composed from those values directly. The rules, restated:
+//   * the read's records are taken best combined score first, at most --num-alignments of them (at least one); X0 of a
+//     line is the number of TAKEN records that have this mate (:455-466);
+//   * an unmapped mate shows its partner's RNAME and POS; with one mapped mate every PNEXT of the record is that mate's
+//     POS, with both it is the partner's (:402-417);
+//   * FLAG: 0x1 paired data; 0x2 both mates mapped; 0x4 this mate unmapped and its partner mapped; 0x8 the reverse;
+//     0x10 this mate reverse-complemented; 0x20 its partner is (only when both are mapped); 0x40 / 0x80 first / second
+//     line of paired data; 0x100 every record but the read's first (:373-401, 309-326);
+//   * TLEN is the record's refEnd - refStart + 1, with a minus sign on the first line when both mates are mapped and R1
+//     does not start before R2, on the second line otherwise (:419-424);
+//   * MAPQ = ceil(-10 log10(max(1 - p / sum of p over the read's taken records of that mate, 1e-5))), p = 10 ^ (sum of the
+//     per-base log-probabilities of the alignment) (:488-498); an unmapped mate has p = 0;
+//   * single-end data: one line per record, RNEXT "*", PNEXT 0, never 0x8 (:425-429);
+//   * the line of a mate flagged 0x4 ends after QUAL; SEQ and QUAL are "*" (:282-297).
+struct Mate {
+  bool mapped = false, rev = false;
+  int32_t ref_begin = 0;            // POS - 1
+  uint32_t score = 0;               // AS
+  std::string_view rname;
+  SequenceDifference diff;          // CIGAR, MD, NM and the log-probability (getCigarAndMD)
   double prob = 0;
 };
+struct RecordLines { Mate mate[2]; const POv *rec = nullptr; const kslam_gene *gene = nullptr; };
 
-uint16_t sam_flag(const SAMEntry &e, bool pairedData) {  // SAM.h:309-326
-  uint16_t flag = 0;
-  if (e.multipleSegments) flag |= 0x1;
-  if (e.allSegmentsAligned) flag |= 0x2;
-  if (e.thisSegmentUnmapped) flag |= 0x4;
-  if (e.nextSegmentUnmapped) flag |= 0x8;
-  if (e.revComp) flag |= 0x10;
-  if (e.nextRevComp) flag |= 0x20;
-  if (pairedData) flag |= e.first ? 0x40 : 0x80;
-  if (e.secondary) flag |= 0x100;
-  return flag;
-}
+static const struct Digits2 { char t[200]; Digits2() { for (int i = 0; i < 100; i++) { t[2 * i] = (char)('0' + i / 10); t[2 * i + 1] = (char)('0' + i % 10); } } } kDigits2;
 
-// raw-pointer writers for sam_line: the line is composed in place at the end of the output string
+// raw-pointer writers: a line is composed in place at the end of the output string (the caller has made room)
 inline char *w_bytes(char *p, const char *s, size_t n) { memcpy(p, s, n); return p + n; }
+inline char *w_view(char *p, std::string_view v) { return w_bytes(p, v.data(), v.size()); }
 template <size_t N> inline char *w_lit(char *p, const char (&lit)[N]) { memcpy(p, lit, N - 1); return p + (N - 1); }
-inline char *w_uint(char *p, uint64_t v) {
-  char buf[24]; int n = 0;
-  do { buf[n++] = (char)('0' + v % 10); v /= 10; } while (v);
-  while (n) *p++ = buf[--n];
-  return p;
+inline char *w_uint(char *p, uint64_t v) {                 // two digits per division; most fields have one to four digits
+  if (v < 10) { *p = (char)('0' + v); return p + 1; }
+  if (v < 100) { memcpy(p, kDigits2.t + 2 * v, 2); return p + 2; }
+  char buf[20], *q = buf + 20;
+  if (v <= 0xffffffffull) {
+    uint32_t w = (uint32_t)v;
+    while (w >= 100) { q -= 2; memcpy(q, kDigits2.t + 2 * (w % 100), 2); w /= 100; }
+    if (w >= 10) { q -= 2; memcpy(q, kDigits2.t + 2 * w, 2); } else *--q = (char)('0' + w);
+  } else {
+    while (v >= 100) { q -= 2; memcpy(q, kDigits2.t + 2 * (v % 100), 2); v /= 100; }
+    if (v >= 10) { q -= 2; memcpy(q, kDigits2.t + 2 * v, 2); } else *--q = (char)('0' + v);
+  }
+  const size_t n = (size_t)(buf + 20 - q);
+  memcpy(p, q, n);
+  return p + n;
 }
 inline char *w_int(char *p, int64_t v) { if (v < 0) { *p++ = '-'; return w_uint(p, (uint64_t)(-v)); } return w_uint(p, (uint64_t)v); }
 
-void sam_line(std::string &out, const SAMEntry &e, bool reportCigar, bool pairedData) {   // SAMEntry::getEntry, SAM.h:282-308, + '\n'
+// line of mate m of one record; k = the record's rank among the read's taken records
+void sam_line(std::string &out, const Ctx &c, const RecordLines &L, int m, size_t k, std::string_view qname, uint32_t hits, uint8_t mapq) {
+  const Mate &me = L.mate[m], &partner = L.mate[1 - m];
+  const bool paired = c.paired, report_cigar = c.prm->report_cigar != 0;
+  const bool both = me.mapped && partner.mapped, ends_early = !me.mapped && partner.mapped;
+  const Mate &shown = me.mapped || !partner.mapped ? me : partner;       // whose RNAME / POS this line carries
+  unsigned flag = (paired ? 0x1u : 0u) | (both ? 0x2u : 0u) | (ends_early ? 0x4u : 0u) | (me.mapped && me.rev ? 0x10u : 0u) |
+                  (both && partner.rev ? 0x20u : 0u) | (paired ? (m == 0 ? 0x40u : 0x80u) : 0u) | (k != 0 ? 0x100u : 0u);
+  if (me.mapped && !partner.mapped && (paired || m != 0)) flag |= 0x8u;
+  const uint32_t pos = (uint32_t)(shown.ref_begin + 1);
+  uint32_t pnext = both ? (uint32_t)(partner.ref_begin + 1) : pos;
+  int32_t tlen = me.mapped || partner.mapped ? L.rec->refEnd - L.rec->refStart + 1 : 0;
+  if (both && !(L.mate[0].ref_begin < L.mate[1].ref_begin)) tlen *= -1;
+  if (m == 1) tlen *= -1;
+  const bool star_next = !paired && m == 0;
+  if (star_next) pnext = 0;
+  std::string_view xg, xp, xr;
+  if (L.gene) { xg = gene_str(c.db, L.gene, GENE_NAME); xp = gene_str(c.db, L.gene, GENE_PROTEIN); xr = gene_str(c.db, L.gene, GENE_PRODUCT); }
   // one bounds check per line instead of one per field: 13 numbers of at most 20 digits + ~70 bytes of literals + the strings
-  const size_t bound = e.qname.size() + e.rname.size() + e.cigar.size() + e.rnext.size() + e.MD.size() + e.XG.size() + e.XP.size() + e.XR.size() + 400;
+  const size_t bound = qname.size() + shown.rname.size() + me.diff.cigar.size() + me.diff.MD.size() + xg.size() + xp.size() + xr.size() + 400;
   const size_t old = out.size();
   if (out.capacity() < old + bound) out.reserve(std::max(out.capacity() * 2, old + bound));
   out.resize(old + bound);
   char *p = &out[old];
-  p = w_bytes(p, e.qname.data(), e.qname.size()); *p++ = '\t'; p = w_uint(p, sam_flag(e, pairedData)); *p++ = '\t';
-  p = w_bytes(p, e.rname.data(), e.rname.size()); *p++ = '\t'; p = w_uint(p, e.pos); *p++ = '\t'; p = w_uint(p, e.mapq); *p++ = '\t';
-  if (reportCigar) p = w_bytes(p, e.cigar.data(), e.cigar.size()); else *p++ = '*';
-  *p++ = '\t'; p = w_bytes(p, e.rnext.data(), e.rnext.size()); *p++ = '\t'; p = w_uint(p, e.pnext); *p++ = '\t'; p = w_int(p, e.tlen);
+  p = w_view(p, qname); *p++ = '\t'; p = w_uint(p, flag); *p++ = '\t';
+  p = w_view(p, shown.rname); *p++ = '\t'; p = w_uint(p, pos); *p++ = '\t'; p = w_uint(p, mapq); *p++ = '\t';
+  if (report_cigar && me.mapped) p = w_view(p, me.diff.cigar); else *p++ = '*';
+  *p++ = '\t'; *p++ = star_next ? '*' : '='; *p++ = '\t'; p = w_uint(p, pnext); *p++ = '\t'; p = w_int(p, tlen);
   p = w_lit(p, "\t*\t*");
-  if (!e.thisSegmentUnmapped) {
-    if (reportCigar) { p = w_lit(p, "\tMD:Z:"); p = w_bytes(p, e.MD.data(), e.MD.size()); }
-    p = w_lit(p, "\tAS:i:"); p = w_uint(p, e.AS);
-    p = w_lit(p, "\tXS:i:"); p = w_uint(p, e.XS);
-    p = w_lit(p, "\tNM:i:"); p = w_uint(p, e.NM);
-    p = w_lit(p, "\tX0:i:"); p = w_uint(p, e.XO);
-    if (e.XT != 0) { p = w_lit(p, "\tXT:i:"); p = w_uint(p, e.XT); }
-    if (e.XG.size()) { p = w_lit(p, "\tXG:Z:"); p = w_bytes(p, e.XG.data(), e.XG.size()); }
-    if (e.XP.size()) { p = w_lit(p, "\tXP:Z:"); p = w_bytes(p, e.XP.data(), e.XP.size()); }
-    if (e.XR.size()) { p = w_lit(p, "\tXR:Z:\""); p = w_bytes(p, e.XR.data(), e.XR.size()); *p++ = '"'; }
+  if (!ends_early) {
+    if (report_cigar) { p = w_lit(p, "\tMD:Z:"); if (me.mapped) p = w_view(p, me.diff.MD); }
+    p = w_lit(p, "\tAS:i:"); p = w_uint(p, me.mapped ? (uint16_t)me.score : 0u);
+    p = w_lit(p, "\tXS:i:"); p = w_uint(p, (uint16_t)L.rec->combinedScore);
+    p = w_lit(p, "\tNM:i:"); p = w_uint(p, me.mapped ? me.diff.NM : 0u);
+    p = w_lit(p, "\tX0:i:"); p = w_uint(p, hits);
+    const uint32_t tax = c.db->taxonomy_ids ? c.db->taxonomy_ids[L.rec->entry] : 0;
+    if (tax != 0) { p = w_lit(p, "\tXT:i:"); p = w_uint(p, tax); }
+    if (xg.size()) { p = w_lit(p, "\tXG:Z:"); p = w_view(p, xg); }
+    if (xp.size()) { p = w_lit(p, "\tXP:Z:"); p = w_view(p, xp); }
+    if (xr.size()) { p = w_lit(p, "\tXR:Z:\""); p = w_view(p, xr); *p++ = '"'; }
   }
   *p++ = '\n';
   out.resize((size_t)(p - out.data()));
 }
 
-void sam_init(SAMEntry &s, const Ctx &c, const kslam_overlap &overlap) {              // SAM.h:344-356
-  auto sd = cigar_and_md(c, overlap);
-  s.cigar = std::move(sd.cigar); s.MD = std::move(sd.MD); s.NM = sd.NM;
-  s.prob = std::pow(10, sd.logProbability);
-  s.rname = std::string_view(c.db->locus_tags + c.db->locus_offs[overlap.entry], (size_t)(c.db->locus_offs[overlap.entry + 1] - c.db->locus_offs[overlap.entry]));
-  s.pos = overlap.ref_begin + 1;
-  s.AS = (uint16_t)overlap.sw_score;
-}
-
-std::pair<SAMEntry, SAMEntry> sam_from_pair(const Ctx &c, const POv &ap) {             // SAM.h:357-441
-  const kslam_overlap *ov = c.in->sorted_overlaps;
-  SAMEntry r1, r2;
-  r1.first = true; r2.first = false;
-  if (const kslam_gene *gene = best_gene(c.db, ap.entry, ap.refStart, ap.refEnd)) {     // SAM.h:361-370
-    r1.XG = r2.XG = gene_str(c.db, gene, GENE_NAME);
-    r1.XP = r2.XP = gene_str(c.db, gene, GENE_PROTEIN);
-    r1.XR = r2.XR = gene_str(c.db, gene, GENE_PRODUCT);
-  }
-  const uint32_t tax = c.db->taxonomy_ids ? c.db->taxonomy_ids[ap.entry] : 0;
-  r1.XT = tax; r2.XT = tax;
-  bool conventionalSequence = true;
-  bool bothAligned = ap.hasR1 && ap.hasR2;
-  if (c.paired) { r1.multipleSegments = true; r2.multipleSegments = true; }
-  if (bothAligned) {
-    r1.allSegmentsAligned = true; r2.allSegmentsAligned = true;
-    conventionalSequence = ov[ap.r1].ref_begin < ov[ap.r2].ref_begin;
-    if (ov[ap.r1].rev_comp) { r1.revComp = true; r2.nextRevComp = true; }
-    if (ov[ap.r2].rev_comp) { r2.revComp = true; r1.nextRevComp = true; }
-  } else if (ap.hasR1) {
-    r1.nextSegmentUnmapped = true; r2.thisSegmentUnmapped = true;
-    if (ov[ap.r1].rev_comp) r1.revComp = true;
-  } else if (ap.hasR2) {
-    r2.nextSegmentUnmapped = true; r1.thisSegmentUnmapped = true;
-    if (ov[ap.r2].rev_comp) r2.revComp = true;
-  }
-  if (ap.hasR1) sam_init(r1, c, ov[ap.r1]);
-  if (ap.hasR2) sam_init(r2, c, ov[ap.r2]);
-  r1.pnext = r2.pos; r2.pnext = r1.pos;
-  if (!ap.hasR1) { r1.rname = r2.rname; r1.pos = r2.pos; r2.pnext = r2.pos; r1.pnext = r2.pos; }
-  if (!ap.hasR2) { r2.rname = r1.rname; r2.pos = r1.pos; r1.pnext = r1.pos; r2.pnext = r1.pos; }
-  if (!c.paired) { r1.rnext = "*"; r1.pnext = 0; r1.nextSegmentUnmapped = false; }     // SAM.h:425-429
-  int32_t tlen = ap.refEnd - ap.refStart + 1;
-  if (!(ap.hasR1 || ap.hasR2)) tlen = 0;
-  if (!conventionalSequence) tlen *= -1;
-  r1.tlen = tlen; r2.tlen = tlen * -1;
-  r1.XS = ap.combinedScore; r2.XS = ap.combinedScore;
-  return {r1, r2};
-}
-
-void write_pairs(std::string &out, const Ctx &c, ReadPair &read) {                    // SAM.h:451-517
+void write_pairs(std::string &out, const Ctx &c, ReadPair &read) {
+  // best combined score first, IN PLACE as in the reference: the taxonomy stage that follows sees the records in this order
+  // (SLAM.h:235-246), and where std::sort leaves equal scores is part of the output
   std::sort(read.pairs.begin(), read.pairs.end(), [](const POv &i, const POv &j) { return i.combinedScore > j.combinedScore; });
-  std::vector<std::pair<SAMEntry, SAMEntry>> SAMPairs;
-  SAMPairs.reserve(read.pairs.size() < c.prm->num_alignments ? read.pairs.size() : c.prm->num_alignments);
-  uint32_t r1NumHits = 0, r2NumHits = 0;
-  for (auto &ap : read.pairs) {
-    if (ap.hasR1) r1NumHits++;
-    if (ap.hasR2) r2NumHits++;
-    SAMPairs.push_back(sam_from_pair(c, ap));
-    if (SAMPairs.size() >= c.prm->num_alignments) break;
+  const size_t n = std::min<size_t>(read.pairs.size(), std::max<uint32_t>(1u, c.prm->num_alignments));
+  if (n == 0) return;                                      // (the reference would dereference begin() of an empty vector here)
+  static thread_local std::vector<RecordLines> scratch;
+  if (scratch.size() < n) scratch.resize(n);
+  const kslam_overlap *ov = c.in->sorted_overlaps;
+  uint32_t hits[2] = {0, 0};
+  double prob_sum[2] = {0, 0};
+  for (size_t k = 0; k < n; k++) {
+    const POv &rec = read.pairs[k];
+    RecordLines &L = scratch[k];
+    L.rec = &rec;
+    L.gene = best_gene(c.db, rec.entry, rec.refStart, rec.refEnd);                       // SAM.h:361-370
+    for (int m = 0; m < 2; m++) {
+      Mate &mate = L.mate[m];
+      mate.mapped = m == 0 ? rec.hasR1 : rec.hasR2;
+      if (!mate.mapped) { mate.rev = false; mate.ref_begin = -1; mate.score = 0; mate.rname = std::string_view(); mate.prob = 0; continue; }
+      const kslam_overlap &o = ov[m == 0 ? rec.r1 : rec.r2];
+      hits[m]++;
+      cigar_and_md(c, o, mate.diff);
+      mate.prob = std::pow(10, mate.diff.logProbability);
+      mate.rev = o.rev_comp != 0; mate.ref_begin = o.ref_begin; mate.score = o.sw_score;
+      mate.rname = std::string_view(c.db->locus_tags + c.db->locus_offs[o.entry], (size_t)(c.db->locus_offs[o.entry + 1] - c.db->locus_offs[o.entry]));
+    }
+    prob_sum[0] += L.mate[0].prob; prob_sum[1] += L.mate[1].prob;                        // in record order (:474-475)
   }
-  if (SAMPairs.empty()) return;                          // the reference would dereference begin() here; nothing to write
-  auto primary = SAMPairs.begin();
-  double r1SumProb = 0, r2SumProb = 0;
   auto id_view = [&](uint32_t i) { return std::string_view(c.reads->ids + c.reads->id_offs[i], (size_t)(c.reads->id_offs[i + 1] - c.reads->id_offs[i])); };
-  const std::string_view q1 = id_view(read.r1Pos), q2 = id_view(read.r2Pos);
-  for (auto sp = SAMPairs.begin(); sp != SAMPairs.end(); sp++) {
-    sp->first.qname = q1; sp->second.qname = q2;
-    r1SumProb += sp->first.prob; r2SumProb += sp->second.prob;
-    sp->first.XO = r1NumHits; sp->second.XO = r2NumHits;
-  }
-  primary->first.secondary = false; primary->second.secondary = false;
-  for (auto sp = SAMPairs.begin(); sp != SAMPairs.end(); sp++) {
-    double temp = 1.0 - sp->first.prob / r1SumProb;
-    if (temp <= 0.00001) temp = 0.00001;
-    double temp2 = 1.0 - sp->second.prob / r2SumProb;
-    if (temp2 <= 0.00001) temp2 = 0.00001;
-    sp->first.mapq = ceil(-10.0 * std::log10(temp));
-    sp->second.mapq = ceil(-10.0 * std::log10(temp2));
-    sam_line(out, sp->first, c.prm->report_cigar != 0, c.paired);
-    if (c.paired) sam_line(out, sp->second, c.prm->report_cigar != 0, c.paired);
+  const std::string_view qname[2] = {id_view(read.r1Pos), c.paired ? id_view(read.r2Pos) : std::string_view()};
+  const int lines_per_record = c.paired ? 2 : 1;
+  for (size_t k = 0; k < n; k++) {
+    for (int m = 0; m < lines_per_record; m++) {
+      double miss = 1.0 - scratch[k].mate[m].prob / prob_sum[m];
+      if (miss <= 0.00001) miss = 0.00001;
+      const uint8_t mapq = ceil(-10.0 * std::log10(miss));
+      sam_line(out, c, scratch[k], m, k, qname[m], hits[m], mapq);
+    }
     if (c.prm->sam_xa) break;
   }
 }
@@ -717,12 +709,14 @@ static int sam_finish(Ctx &c, std::vector<ReadPair> &rp, bool insert_screen, boo
     };
     parallel_ranges(threads, rp.size(), [&](uint32_t t, size_t lo, size_t hi) {
       constexpr size_t AHEAD = 4;
+      parts[t].reserve((hi - lo) * 2 * 128);             // about two short lines per read pair: most of the growth (and its page faults) up front
       for (size_t i = lo; i < std::min(hi, lo + AHEAD); i++) prefetch_windows(rp[i]);
       for (size_t i = lo; i < hi; i++) {
         if (i + AHEAD < hi) prefetch_windows(rp[i + AHEAD]);
         write_pairs(parts[t], c, rp[i]);
       }
     });
+    const double t_lines = now();
     size_t total = 0;
     std::vector<size_t> at(threads + 1, 0);
     for (uint32_t t = 0; t < threads; t++) { at[t] = total; total += parts[t].size(); }
@@ -734,6 +728,7 @@ static int sam_finish(Ctx &c, std::vector<ReadPair> &rp, bool insert_screen, boo
     *text = buf;
     if (len) *len = total;
     if (!buf) rc = KSLAM_ERR_NOMEM;
+    if (trace) fprintf(stderr, "[kslam_sam] lines %.1f ms, joined into one buffer %.1f ms\n", (t_lines - t3) * 1e3, (now() - t_lines) * 1e3);
   } else {
     if (text) *text = nullptr;
     if (len) *len = 0;
