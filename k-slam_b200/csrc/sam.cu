@@ -24,6 +24,8 @@
 #include <string.h>
 #include <chrono>
 #include <stdlib.h>
+#include <malloc.h>
+#include <mutex>
 #include <thread>
 #include <unordered_map>
 
@@ -670,6 +672,48 @@ int kslam_sam_header(const kslam_sam_db *db, const char *command_line, char **te
   return *text ? KSLAM_OK : KSLAM_ERR_NOMEM;
 }
 
+// Text buffers are recycled from batch to batch. A 10 M-pair batch writes ~2 GB of SAM text, first into one string per
+// thread, then into the buffer handed to the caller; taken fresh from malloc every batch, each of those pages is faulted in
+// (and zeroed) again, which costs more than writing the text. The pool keeps the per-thread strings (emptied, capacity
+// kept) and the one largest buffer given back through kslam_sam_free; a second writer running at the same time simply
+// allocates. KSLAM_SAM_NO_POOL=1 switches it off (nothing is retained between batches).
+struct TextPool {
+  std::mutex m;
+  std::vector<std::string> parts;
+  char *buf = nullptr; size_t cap = 0;
+  const bool off = getenv("KSLAM_SAM_NO_POOL") != nullptr;
+  ~TextPool() { free(buf); }
+  std::vector<std::string> take_parts(uint32_t threads) {
+    std::vector<std::string> p;
+    if (!off) { std::lock_guard<std::mutex> l(m); p.swap(parts); }
+    p.resize(threads);                                       // (a different thread count keeps what fits)
+    return p;
+  }
+  void give_parts(std::vector<std::string> &p) {
+    if (off) return;
+    for (std::string &x : p) x.clear();
+    std::lock_guard<std::mutex> l(m);
+    if (parts.empty()) parts.swap(p);
+  }
+  char *take_buf(size_t bytes) {
+    if (!off) {
+      std::lock_guard<std::mutex> l(m);
+      if (buf && cap >= bytes) { char *b = buf; buf = nullptr; cap = 0; return b; }
+    }
+    return (char *)malloc(bytes);
+  }
+  void give_buf(char *b) {
+    if (!b) return;
+    const size_t have = off ? 0 : malloc_usable_size(b);
+    if (have >= (1u << 20)) {                                // small texts (headers) are not worth keeping
+      std::lock_guard<std::mutex> l(m);
+      if (have > cap) { std::swap(b, buf); cap = have; }
+    }
+    free(b);
+  }
+};
+static TextPool &text_pool() { static TextPool p; return p; }
+
 // everything after the per-read grouping: screens, pseudo-assembly, records, text (shared by paired and single-end input);
 // with a taxonomy database the per-read records then go to taxon.cu, after the SAM records exactly as in the batch loop
 // (writeSAMOutputPairs re-sorts every read's records in place before the taxonomy step sees them, SLAM.h:235-246)
@@ -692,7 +736,7 @@ static int sam_finish(Ctx &c, std::vector<ReadPair> &rp, bool insert_screen, boo
   double t3 = now();
   int rc = KSLAM_OK;
   if (want_sam) {
-    std::vector<std::string> parts(threads);
+    std::vector<std::string> parts = text_pool().take_parts(threads);
     // Every alignment reads ~150 reference bases at an unrelated place of the database: three cache lines that are never
     // in cache. They are requested a few read pairs ahead of their use.
     auto prefetch_windows = [&](const ReadPair &read) {
@@ -720,7 +764,7 @@ static int sam_finish(Ctx &c, std::vector<ReadPair> &rp, bool insert_screen, boo
     size_t total = 0;
     std::vector<size_t> at(threads + 1, 0);
     for (uint32_t t = 0; t < threads; t++) { at[t] = total; total += parts[t].size(); }
-    char *buf = (char *)malloc(total + 1);                      // the threads' pieces go straight into the result buffer
+    char *buf = text_pool().take_buf(total + 1);                // the threads' pieces go straight into the result buffer
     if (buf) {
       parallel_threads(threads, [&](uint32_t t) { memcpy(buf + at[t], parts[t].data(), parts[t].size()); });
       buf[total] = 0;
@@ -728,6 +772,7 @@ static int sam_finish(Ctx &c, std::vector<ReadPair> &rp, bool insert_screen, boo
     *text = buf;
     if (len) *len = total;
     if (!buf) rc = KSLAM_ERR_NOMEM;
+    text_pool().give_parts(parts);
     if (trace) fprintf(stderr, "[kslam_sam] lines %.1f ms, joined into one buffer %.1f ms\n", (t_lines - t3) * 1e3, (now() - t_lines) * 1e3);
   } else {
     if (text) *text = nullptr;
@@ -885,6 +930,6 @@ int kslam_batch_outputs_single(const kslam_sam_params *prm, const kslam_sam_db *
   } catch (const std::exception &) { return KSLAM_ERR_NOMEM; }
 }
 
-void kslam_sam_free(char *text) { free(text); }
+void kslam_sam_free(char *text) { text_pool().give_buf(text); }
 
 }  // extern "C"

@@ -78,6 +78,25 @@ def test_sam_golden(pkg, golden):
     assert w.header("SLAM golden") == g["header"].tobytes()
 
 
+def test_sam_text_buffers_are_recycled_between_batches(pkg, golden):
+    """The library keeps the per-thread strings and the largest buffer given back through kslam_sam_free for the next batch
+    (page faults cost more than the text): a long batch, a short one and the long one again, with different thread counts,
+    must give the same texts as the reference (> 1 MB so that the buffer is actually kept)."""
+    gb, go, rb, ro, quals, idb, ido = make_inputs(pkg, 5, n_pairs=6000, kind="random")
+    tags = [f"g{i}" for i in range(len(go) - 1)]
+    ov, pool, pairs, want, want_mi, _ = reference_side(gb, go, rb, ro, quals, 1)
+    assert len(want) > (1 << 20)
+    g = golden("sam_config1_mini.npz")
+    gtags = [f"g{i}" for i in range(len(g["go"]) - 1)]
+    for threads in (4, 2, 7):
+        w = pkg.SamWriter(gb, go, tags, report_cigar=True, threads=threads)
+        got, mi = w.batch(rb, ro, quals, ro, idb, ido, ov, pool, pairs)
+        assert got == want and mi == want_mi
+        ws = pkg.SamWriter(g["gb"], g["go"], gtags, report_cigar=True, threads=threads)
+        got, _ = ws.batch(g["rb"], g["ro"], g["quals"], g["ro"], g["ids"], g["id_offs"], g["ov"], g["pool"], g["pairs"])
+        assert got == g["sam"].tobytes()
+
+
 def test_sam_empty_batch(pkg):
     gb, go = pkg.synth.random_genomes(2, 1000, seed=1)
     w = pkg.SamWriter(gb, go, ["a", "b"])
